@@ -1,0 +1,655 @@
+"""Python host of the classify path.
+
+Mirrors the two reference layers either side of the process boundary it replaces:
+
+  * ``classify(cfg)``          <->  src/ganon/classify.py:7-107 (picks .hibf/.ibf/.tax per --db-prefix, assembles the
+                                    ganon-classify arguments; here the call is in-process through the C ABI instead of
+                                    ``subprocess``)
+  * ``GanonClassifyConfig`` /
+    ``run(config)``            <->  GanonClassify::Config (Config.hpp:22-49, validate 71-245) and GanonClassify::run
+                                    (GC.cpp:1676): opens the output files, streams the read files block by block into
+                                    ``gnb_session_classify`` and writes the text it returns.
+
+All compute is in libganon_b200.so (CUDA); this module only moves bytes between files and the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+import sys
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from . import _lib
+from ._lib import BatchResult, DbInfo, SessionConfig, Totals, check
+
+VERSION = "ganon-b200 0.1.0 (ganon-classify 2.4.1 compatible)"
+BLOCK_BYTES = int(os.environ.get("GANON_B200_BLOCK_BYTES", str(256 << 20)))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# thin object wrappers over the C handles
+# ----------------------------------------------------------------------------------------------------------------------
+class Database:
+    """A .ibf / .hibf resident in HBM (gnb_db)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def open(cls, path: str, hibf: bool = False, device: int = 0, shard: int = 0, n_shards: int = 1) -> "Database":
+        h = C.c_void_p()
+        check(_lib.lib().gnb_db_open(path.encode(), int(hibf), device, shard, n_shards, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def create(cls, bins: int, bin_size_bits: int, hash_functions: int, kmer_size: int, window_size: int, device: int = 0) -> "Database":
+        h = C.c_void_p()
+        check(_lib.lib().gnb_db_create(bins, bin_size_bits, hash_functions, kmer_size, window_size, device, C.byref(h)))
+        return cls(h.value)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def info(self) -> DbInfo:
+        i = DbInfo()
+        check(_lib.lib().gnb_db_info(self._h, C.byref(i)))
+        return i
+
+    def targets(self) -> List[Tuple[str, float, int]]:
+        out = []
+        name, fpr, nb = C.c_char_p(), C.c_double(), C.c_uint64()
+        for i in range(self.info().n_targets):
+            check(_lib.lib().gnb_db_target(self._h, i, C.byref(name), C.byref(fpr), C.byref(nb)))
+            out.append((name.value.decode(), fpr.value, nb.value))
+        return out
+
+    def fill_random(self, seed: int, and_terms: int = 1) -> None:
+        check(_lib.lib().gnb_db_fill_random(self._h, seed, and_terms))
+
+    def emplace(self, hashes, bins) -> None:
+        import numpy as np
+
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        bins = np.ascontiguousarray(bins, dtype=np.uint32)
+        assert hashes.size == bins.size
+        check(_lib.lib().gnb_db_emplace(self._h, hashes.ctypes.data, bins.ctypes.data, hashes.size))
+
+    def set_targets(self, names: Sequence[str], bin_target, target_hashes, max_hashes_bin: int) -> None:
+        import numpy as np
+
+        bt = np.ascontiguousarray(bin_target, dtype=np.uint32)
+        th = np.ascontiguousarray(target_hashes, dtype=np.uint64)
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        check(_lib.lib().gnb_db_set_targets(self._h, len(names), arr, bt.ctypes.data, th.ctypes.data, max_hashes_bin))
+
+    def read_words(self, offset: int, n: int, ibf_index: int = 0):
+        import numpy as np
+
+        out = np.empty(n, dtype=np.uint64)
+        check(_lib.lib().gnb_db_read_words(self._h, ibf_index, offset, n, out.ctypes.data))
+        return out
+
+    def save(self, path: str) -> None:
+        check(_lib.lib().gnb_db_save(self._h, path.encode()))
+
+    def bulk_count(self, hashes, hash_off, ibf_index: int = 0):
+        """counting_agent::bulk_count for several hash lists (test hook): uint16[n_reads, technical_bins]."""
+        import numpy as np
+
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        hash_off = np.ascontiguousarray(hash_off, dtype=np.uint64)
+        n = hash_off.size - 1
+        i = self.info()
+        width = (i.shard_word_end - i.shard_word_begin) * 64 if ibf_index == 0 else None
+        if width is None:
+            raise NotImplementedError
+        out = np.zeros((n, width), dtype=np.uint16)
+        check(_lib.lib().gnb_db_bulk_count(self._h, ibf_index, hashes.ctypes.data, hash_off.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().gnb_db_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def minimisers(seq: bytes, k: int, w: int, device: int = 0):
+    """seqan3::views::minimiser_hash of one sequence on the GPU (test hook for kernel K2)."""
+    import numpy as np
+
+    if isinstance(seq, str):
+        seq = seq.encode()
+    out = np.empty(max(len(seq), 1), dtype=np.uint64)
+    n = C.c_uint64()
+    check(_lib.lib().gnb_minimisers(device, k, w, seq, len(seq), out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].copy()
+
+
+class Session:
+    """One classification run over all hierarchy levels (gnb_session)."""
+
+    def __init__(
+        self,
+        dbs: Sequence[Database],
+        rel_cutoff: Sequence[float],
+        rel_filter: Sequence[float],
+        fpr_query: Sequence[float],
+        hierarchy_labels: Optional[Sequence[str]] = None,
+        tax_files: Optional[Sequence[str]] = None,
+        skip_lca: bool = False,
+        tax_root_node: str = "1",
+        output_lca: bool = False,
+        output_all: bool = False,
+        output_unclassified: bool = False,
+        output_single: bool = False,
+        device: int = 0,
+        host_threads: int = 0,
+        n_reads: int = 400,
+        quiet: bool = True,
+    ):
+        n = len(dbs)
+        labels = list(hierarchy_labels) if hierarchy_labels else ["H1"] * n
+        self._keep = dict(
+            dbs=(C.c_void_p * n)(*[d.handle for d in dbs]),
+            labels=(C.c_char_p * n)(*[s.encode() for s in labels]),
+            cutoff=(C.c_double * n)(*rel_cutoff),
+            tax=(C.c_char_p * n)(*[t.encode() for t in tax_files]) if tax_files else None,
+            rel_filter=(C.c_double * len(rel_filter))(*rel_filter),
+            fpr_query=(C.c_double * len(fpr_query))(*fpr_query),
+            root=tax_root_node.encode(),
+            db_objs=list(dbs),
+        )
+        k = self._keep
+        cfg = SessionConfig(
+            n,
+            k["dbs"],
+            k["labels"],
+            k["cutoff"],
+            k["tax"] if k["tax"] is not None else None,
+            len(rel_filter),
+            k["rel_filter"],
+            k["fpr_query"],
+            int(skip_lca),
+            k["root"],
+            int(output_lca),
+            int(output_all),
+            int(output_unclassified),
+            int(output_single),
+            device,
+            host_threads,
+            n_reads,
+            int(quiet),
+        )
+        h = C.c_void_p()
+        check(_lib.lib().gnb_session_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        n_levels = C.c_uint32()
+        check(_lib.lib().gnb_session_level_count(self._h, C.byref(n_levels)))
+        self.level_labels = []
+        lab = C.c_char_p()
+        for i in range(n_levels.value):
+            check(_lib.lib().gnb_session_level_label(self._h, i, C.byref(lab)))
+            self.level_labels.append(lab.value.decode())
+
+    @staticmethod
+    def _ptr(buf, n=None):
+        """(address, length) of bytes / bytearray / memoryview / numpy / (addr, len) tuples without copying."""
+        if buf is None:
+            return None, 0
+        if isinstance(buf, tuple):
+            return C.c_void_p(buf[0]), buf[1]
+        if isinstance(buf, bytes):
+            return C.cast(C.c_char_p(buf), C.c_void_p), len(buf) if n is None else n
+        if isinstance(buf, bytearray):
+            arr = (C.c_char * len(buf)).from_buffer(buf)
+            return C.cast(arr, C.c_void_p), len(buf) if n is None else n
+        if hasattr(buf, "ctypes"):  # numpy
+            return C.c_void_p(buf.ctypes.data), buf.nbytes if n is None else n
+        if hasattr(buf, "data_ptr"):  # torch (host tensor)
+            return C.c_void_p(buf.data_ptr()), buf.numel() * buf.element_size() if n is None else n
+        raise TypeError("unsupported buffer type %r" % type(buf))
+
+    def classify(self, block1, block2=None, final: bool = True, prefix_id: int = 0, len1: Optional[int] = None, len2: Optional[int] = None) -> BatchResult:
+        p1, n1 = self._ptr(block1, len1)
+        p2, n2 = self._ptr(block2, len2)
+        res = BatchResult()
+        check(_lib.lib().gnb_session_classify(self._h, prefix_id, p1, n1, p2, n2, int(final), C.byref(res)))
+        return res
+
+    def stage(self, block1, block2=None, final: bool = True, len1=None, len2=None) -> int:
+        p1, n1 = self._ptr(block1, len1)
+        p2, n2 = self._ptr(block2, len2)
+        n = C.c_uint64()
+        check(_lib.lib().gnb_session_stage(self._h, p1, n1, p2, n2, int(final), C.byref(n)))
+        return n.value
+
+    def run_staged(self) -> BatchResult:
+        res = BatchResult()
+        check(_lib.lib().gnb_session_run_staged(self._h, C.byref(res)))
+        return res
+
+    def finish_staged(self, prefix_id: int = 0) -> BatchResult:
+        res = BatchResult()
+        check(_lib.lib().gnb_session_finish_staged(self._h, prefix_id, C.byref(res)))
+        return res
+
+    def node_name(self, level: int, node: int) -> str:
+        s = C.c_char_p()
+        check(_lib.lib().gnb_session_node_name(self._h, level, node, C.byref(s)))
+        return s.value.decode()
+
+    def report(self, prefix_id: int = 0) -> bytes:
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().gnb_session_report(self._h, prefix_id, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    def stats(self, prefix_id: int = 0, prefix_name: str = "") -> bytes:
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().gnb_session_stats(self._h, prefix_id, prefix_name.encode(), C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    def totals(self, prefix_id: int = 0, level: int = -1) -> Totals:
+        t = Totals()
+        check(_lib.lib().gnb_session_totals(self._h, prefix_id, level, C.byref(t)))
+        return t
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().gnb_session_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def result_text(res: BatchResult, kind: str, level: int = 0) -> bytes:
+    if kind == "unc":
+        return C.string_at(res.unc_text, res.unc_len) if res.unc_len else b""
+    ptrs, lens = (res.all_text, res.all_len) if kind == "all" else (res.one_text, res.one_len)
+    return C.string_at(ptrs[level], lens[level]) if lens[level] else b""
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GanonClassify::Config + run
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class GanonClassifyConfig:
+    """Field for field GanonClassify::Config (Config.hpp:22-49)."""
+
+    single_reads: List[str] = field(default_factory=list)
+    paired_reads: List[str] = field(default_factory=list)
+    batch_reads: List[str] = field(default_factory=list)
+    ibf: List[str] = field(default_factory=list)
+    tax: List[str] = field(default_factory=list)
+    output_prefix: str = ""
+    hierarchy_labels: List[str] = field(default_factory=lambda: ["H1"])
+    rel_cutoff: List[float] = field(default_factory=lambda: [0.2])
+    rel_filter: List[float] = field(default_factory=lambda: [0.0])
+    fpr_query: List[float] = field(default_factory=lambda: [1.0])
+    output_lca: bool = False
+    output_all: bool = False
+    output_unclassified: bool = False
+    output_stats: bool = False
+    output_single: bool = False
+    hibf: bool = False
+    skip_lca: bool = False
+    tax_root_node: str = "1"
+    threads: int = 1
+    n_batches: int = 1000
+    n_reads: int = 400
+    verbose: bool = False
+    quiet: bool = False
+    # not in the reference: which GPU to use
+    device: int = 0
+
+    def _err(self, msg: str) -> bool:
+        print(msg, file=sys.stderr)
+        return False
+
+    def _check_files(self, files: Sequence[str]) -> bool:
+        for f in files:
+            if not os.path.exists(f):
+                return self._err("file not found: " + f)
+            if os.path.getsize(f) == 0:
+                return self._err("file is empty: " + f)
+        return True
+
+    def validate(self) -> bool:
+        """Config::validate (Config.hpp:71-173) and validate_hierarchy (175-245), same messages."""
+        if not self.output_prefix:
+            return self._err("--output-prefix is mandatory")
+        if not self.paired_reads and not self.single_reads and not self.batch_reads:
+            return self._err("At least one of --[single|paired|batch]-reads is mandatory")
+        if not self.ibf:
+            return self._err("--ibf is mandatory")
+        if (self.paired_reads or self.single_reads) and self.batch_reads:
+            return self._err("--batch-reads cannot be used together with --[single|paired]-reads")
+        if len(self.paired_reads) % 2 != 0:
+            return self._err("--paired-reads should be an even number of files (pairs)")
+        for files in (self.single_reads, self.paired_reads, self.batch_reads, self.ibf, self.tax):
+            if not self._check_files(files):
+                return False
+        if any(v < 0 or v > 1 for v in self.rel_cutoff):
+            return self._err("--rel-cutoff values should be set between 0 and 1 (0 to disable)")
+        if any(v < 0 or v > 1 for v in self.rel_filter):
+            return self._err("--rel-filter values should be set between 0 and 1 (1 to disable)")
+        if any(v < 0 or v > 1 for v in self.fpr_query):
+            return self._err("--fpr-query values should be set between 0 and 1 (1 to disable)")
+        self.n_batches = max(1, self.n_batches)
+        self.n_reads = max(1, self.n_reads)
+        # validate_hierarchy
+        unique = len(set(self.hierarchy_labels))
+        if len(self.rel_filter) == 1 and unique > 1:
+            self.rel_filter = self.rel_filter * unique
+        elif len(self.rel_filter) != unique:
+            return self._err("Please provide a single or one-per-hierarchy --rel-filter value[s]")
+        if len(self.fpr_query) == 1 and unique > 1:
+            self.fpr_query = self.fpr_query * unique
+        elif len(self.fpr_query) != unique:
+            return self._err("Please provide a single or one-per-hierarchy --fpr-query value[s]")
+        if self.tax and len(self.ibf) != len(self.tax):
+            return self._err("The number of files provided with --ibf and --tax should match")
+        if len(self.hierarchy_labels) == 1 and len(self.ibf) > 1:
+            self.hierarchy_labels = self.hierarchy_labels * len(self.ibf)
+        elif len(self.hierarchy_labels) != len(self.ibf):
+            return self._err("--hierarchy does not match with the number of --ibf and --tax")
+        if len(self.rel_cutoff) == 1 and len(self.ibf) > 1:
+            self.rel_cutoff = self.rel_cutoff * len(self.ibf)
+        elif len(self.rel_cutoff) != len(self.ibf):
+            return self._err("Please provide a single or one-per-filter --rel-cutoff value[s]")
+        if not self.tax:
+            self.skip_lca = True
+        return True
+
+
+class _ReadStream:
+    """A read file (plain or gzip, by magic) consumed in blocks; the unconsumed tail is carried to the next block."""
+
+    def __init__(self, path: str, block_bytes: int):
+        with open(path, "rb") as f:
+            magic = f.read(2)
+        self.f = gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb", buffering=0)
+        self.buf = bytearray(block_bytes)
+        self.fill = 0
+        self.eof = False
+
+    def load(self) -> None:
+        mv = memoryview(self.buf)
+        while self.fill < len(self.buf) and not self.eof:
+            n = self.f.readinto(mv[self.fill :])
+            if not n:
+                self.eof = True
+            else:
+                self.fill += n
+
+    def consume(self, n: int) -> None:
+        rest = self.fill - n
+        if rest:
+            self.buf[:rest] = self.buf[n : self.fill]
+        self.fill = rest
+
+    def grow(self) -> None:
+        self.buf.extend(bytearray(len(self.buf)))
+
+    def close(self) -> None:
+        self.f.close()
+
+
+def _parse_reads_config(cfg: GanonClassifyConfig) -> Optional[Dict[str, List[Tuple[str, str]]]]:
+    """parse_reads_config (GC.cpp:287-351)."""
+    rc: Dict[str, List[Tuple[str, str]]] = {}
+    if cfg.batch_reads:
+        for bf in cfg.batch_reads:
+            with open(bf) as fh:
+                for line in fh.read().split("\n"):
+                    if line == "":
+                        continue
+                    fields = line.split("\t")
+                    if len(fields) <= 1:
+                        print("ERROR: invalid --batch-reads file (prefix <tab> file1 [<tab> file2])", file=sys.stderr)
+                        return None
+                    for p in fields[1:3]:
+                        if not os.path.exists(p) or os.path.getsize(p) == 0:
+                            print("ERROR: file not found/empty: " + p, file=sys.stderr)
+                            return None
+                    rc.setdefault(fields[0], []).append((fields[1], fields[2] if len(fields) == 3 else ""))
+    else:
+        for f in cfg.single_reads:
+            rc.setdefault("", []).append((f, ""))
+        for i in range(0, len(cfg.paired_reads), 2):
+            rc.setdefault("", []).append((cfg.paired_reads[i], cfg.paired_reads[i + 1]))
+    return dict(sorted(rc.items()))  # std::map order
+
+
+def run(cfg: GanonClassifyConfig) -> bool:
+    """GanonClassify::run (GC.cpp:1676-1691) -> ganon_classify<TFilter> (GC.cpp:1375-1674)."""
+    if not cfg.validate():
+        return False
+    t_start = time.time()
+    reads_config = _parse_reads_config(cfg)
+    if reads_config is None:
+        return False
+    for prefix in reads_config:
+        d = os.path.dirname(cfg.output_prefix + prefix)
+        if d and not os.path.isdir(d):
+            os.makedirs(d, exist_ok=True)
+
+    # ---- load every database into HBM (load_files GC.cpp:1007-1039) ----
+    t_load = time.time()
+    dbs: List[Database] = []
+    try:
+        for path in cfg.ibf:
+            dbs.append(Database.open(path, hibf=cfg.hibf, device=cfg.device))
+    except _lib.GnbError as e:
+        print("ERROR: loading ibf or tax files (%s)" % e.msg, file=sys.stderr)
+        return False
+    t_load = time.time() - t_load
+    try:
+        sess = Session(
+            dbs,
+            cfg.rel_cutoff,
+            cfg.rel_filter,
+            cfg.fpr_query,
+            hierarchy_labels=cfg.hierarchy_labels,
+            tax_files=cfg.tax or None,
+            skip_lca=cfg.skip_lca,
+            tax_root_node=cfg.tax_root_node,
+            output_lca=cfg.output_lca,
+            output_all=cfg.output_all,
+            output_unclassified=cfg.output_unclassified,
+            output_single=cfg.output_single,
+            device=cfg.device,
+            host_threads=cfg.threads if cfg.threads > 1 else 0,
+            n_reads=cfg.n_reads,
+            quiet=cfg.quiet,
+        )
+    except _lib.GnbError as e:
+        print(e.msg, file=sys.stderr)
+        return False
+
+    labels = sess.level_labels
+    multi = len(labels) > 1 and not cfg.output_single
+    write_one = cfg.output_lca and not cfg.skip_lca
+    prefixes = list(reads_config)
+    out_rep = {p: open(cfg.output_prefix + p + ".rep", "wb") for p in prefixes}
+    out_unc = {p: open(cfg.output_prefix + p + ".unc", "wb") for p in prefixes} if cfg.output_unclassified else {}
+
+    def level_files(ext: str) -> Dict[str, List]:
+        files: Dict[str, List] = {}
+        for p in prefixes:
+            if multi:
+                files[p] = [open(cfg.output_prefix + p + "." + lab + "." + ext, "wb") for lab in labels]
+            else:
+                fh = open(cfg.output_prefix + p + "." + ext, "wb")
+                files[p] = [fh] * len(labels)
+        return files
+
+    out_all = level_files("all") if cfg.output_all else {}
+    out_one = level_files("one") if write_one else {}
+
+    t_class = time.time()
+    for pid, prefix in enumerate(prefixes):
+        for file1, file2 in reads_config[prefix]:
+            s1 = _ReadStream(file1, BLOCK_BYTES)
+            s2 = _ReadStream(file2, BLOCK_BYTES) if file2 else None
+            try:
+                while True:
+                    s1.load()
+                    if s2:
+                        s2.load()
+                    final = s1.eof and (s2 is None or s2.eof)
+                    if s1.fill == 0 and (s2 is None or s2.fill == 0):
+                        break
+                    if s2 is not None and (s1.fill == 0 or s2.fill == 0):
+                        break  # one mate file ended early: nothing more to pair
+                    res = sess.classify(s1.buf, s2.buf if s2 else None, final=final, prefix_id=pid, len1=s1.fill, len2=s2.fill if s2 else 0)
+                    for li in range(len(labels)):
+                        if cfg.output_all and res.all_len[li]:
+                            out_all[prefix][li].write(C.string_at(res.all_text[li], res.all_len[li]))
+                        if write_one and res.one_len[li]:
+                            out_one[prefix][li].write(C.string_at(res.one_text[li], res.one_len[li]))
+                    if cfg.output_unclassified and res.unc_len:
+                        out_unc[prefix].write(C.string_at(res.unc_text, res.unc_len))
+                    if res.parse_error:
+                        break  # rest of the file is skipped (GC.cpp:1278-1283)
+                    if res.n_reads == 0 and not final:
+                        # not a single complete record in the block: enlarge it
+                        s1.grow()
+                        if s2:
+                            s2.grow()
+                        continue
+                    s1.consume(res.consumed1)
+                    if s2:
+                        s2.consume(res.consumed2)
+                    if final:
+                        break
+            finally:
+                s1.close()
+                if s2:
+                    s2.close()
+    t_class = time.time() - t_class
+
+    for pid, prefix in enumerate(prefixes):
+        out_rep[prefix].write(sess.report(pid))
+        out_rep[prefix].close()
+        if cfg.output_stats:
+            with open(cfg.output_prefix + prefix + ".sta", "wb") as fh:
+                fh.write(sess.stats(pid, prefix))
+    seen = set()
+    for group in (out_unc.values(), *(v for v in out_all.values()), *(v for v in out_one.values())):
+        for fh in group if not isinstance(group, list) else group:
+            if id(fh) not in seen:
+                seen.add(id(fh))
+                fh.close()
+
+    if not cfg.quiet:
+        _print_stats(cfg, sess, prefixes, labels, t_class, t_load, time.time() - t_start)
+    sess.close()
+    for d in dbs:
+        d.close()
+    return True
+
+
+def _print_stats(cfg, sess: Session, prefixes, labels, t_class: float, t_load: float, t_total: float) -> None:
+    """print_time / print_stats (GC.cpp:1041-1128), same wording."""
+    e = sys.stderr
+    if cfg.verbose:
+        print("loading filter(s)    elapsed (s): %g seconds" % t_load, file=e)
+        print("classifying+printing elapsed (s): %g seconds" % t_class, file=e)
+        print("total                elapsed (s): %g seconds" % t_total, file=e)
+        print("-" * 70 + "\n", file=e)
+    tot = [sess.totals(i) for i in range(len(prefixes))]
+    seqs = sum(t.seqs_processed for t in tot)
+    length = sum(t.length_processed for t in tot)
+    kmers = sum(t.kmers_processed for t in tot)
+    print("ganon-classify processed %d sequences (%g Mbp) with %d k-mers in %g seconds (%g Mbp/m)" % (seqs, length / 1e6, kmers, t_class, (length / 1e6) / (max(t_class, 1e-9) / 60.0)), file=e)
+
+    def db(t: Totals, seq_processed: float, seq_unclassified: int) -> None:
+        multiple = t.seqs_classified - t.seqs_unique
+        avg = t.matches / t.seqs_classified if t.seqs_classified else 0
+        perc = t.kmers_matches / t.kmers_from_classified_seqs * 100 if t.kmers_matches else 0
+        print("%d sequences classified (%g%%)" % (t.seqs_classified, t.seqs_classified / seq_processed * 100), file=e)
+        print("  %d with unique matches (%g%%)" % (t.seqs_unique, t.seqs_unique / seq_processed * 100), file=e)
+        print("  %d with multiple matches (%g%%)" % (multiple, multiple / seq_processed * 100), file=e)
+        if seq_unclassified > 0:
+            print("%d sequences unclassified (%g%%)" % (seq_unclassified, seq_unclassified / seq_processed * 100), file=e)
+            if t.seqs_skipped_small:
+                print("  %d sequences skipped (shorter than window size)" % t.seqs_skipped_small, file=e)
+            if t.seqs_skipped_big:
+                print("  %d sequences skipped (larger than allowed, check compilation with -DLONGREADS)" % t.seqs_skipped_big, file=e)
+        print("matches: %d (avg. %g reference/sequence), %d discarded (--rel-filter), %d discarded (--fpr-query)" % (t.matches, avg, t.discarded_matches_filter, t.discarded_matches_fprquery), file=e)
+        print("k-mers: %d/%d k-mers matched/k-mers from classified sequences (%g%%)" % (t.kmers_matches, t.kmers_from_classified_seqs, perc), file=e)
+
+    for pid, prefix in enumerate(prefixes):
+        t = tot[pid]
+        if len(prefixes) > 1:
+            print("\n[%s] %d sequences (%g Mbp) with %d k-mers" % (prefix, t.seqs_processed, t.length_processed / 1e6, t.kmers_processed), file=e)
+        sp = float(t.seqs_processed) if t.seqs_processed > 0 else 1.0
+        db(t, sp, t.seqs_processed - t.seqs_classified)
+        if len(labels) > 1:
+            print("\nBy database hierarchical level:", file=e)
+            for li, lab in enumerate(labels):
+                print(lab + ":", file=e)
+                db(sess.totals(pid, li), sp, 0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# src/ganon/classify.py
+# ----------------------------------------------------------------------------------------------------------------------
+def classify(cfg) -> bool:
+    """Drop-in for ``ganon.classify.classify(cfg)`` up to the ganon-classify call (src/ganon/classify.py:7-64): the
+    same selection of .hibf/.ibf/.tax per --db-prefix and the same argument mapping; reassign/report stay the
+    reference's (they consume the files written here)."""
+    filter_files, tax_files, hibf = [], [], False
+    for db_prefix in cfg.db_prefix:
+        if os.path.isfile(db_prefix + ".hibf") and os.path.getsize(db_prefix + ".hibf") > 0:
+            filter_files.append(db_prefix + ".hibf")
+            hibf = True
+        elif os.path.isfile(db_prefix + ".ibf") and os.path.getsize(db_prefix + ".ibf") > 0:
+            filter_files.append(db_prefix + ".ibf")
+        if os.path.isfile(db_prefix + ".tax") and os.path.getsize(db_prefix + ".tax") > 0:
+            tax_files.append(db_prefix + ".tax")
+    if len(tax_files) != len(filter_files):
+        tax_files = []
+    g = lambda name, default=None: getattr(cfg, name, default)
+    mm = g("multiple_matches", "em")
+    c = GanonClassifyConfig(
+        single_reads=list(g("single_reads") or []),
+        paired_reads=list(g("paired_reads") or []),
+        batch_reads=list(g("batch_reads") or []),
+        ibf=filter_files,
+        tax=tax_files,
+        output_prefix=g("output_prefix", "") or "",
+        hierarchy_labels=list(g("hierarchy_labels") or ["H1"]),
+        rel_cutoff=[float(x) for x in (g("rel_cutoff") or [0.75])],
+        rel_filter=[float(x) for x in (g("rel_filter") or [0.1])],
+        fpr_query=[float(x) for x in (g("fpr_query") or [1e-5])],
+        skip_lca=mm != "lca",
+        output_lca=mm == "lca" and bool(g("output_one")),
+        output_all=bool(g("output_all")) or mm == "em",
+        output_unclassified=bool(g("output_unclassified")),
+        output_stats=bool(g("output_stats")),
+        output_single=bool(g("output_single")),
+        threads=int(g("threads", 1) or 1),
+        verbose=bool(g("verbose")),
+        hibf=bool(g("hibf", hibf)),
+        quiet=bool(g("quiet")),
+    )
+    if g("n_reads") is not None:
+        c.n_reads = int(g("n_reads"))
+    if g("n_batches") is not None:
+        c.n_batches = int(g("n_batches"))
+    return run(c)

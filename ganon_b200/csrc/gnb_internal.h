@@ -1,0 +1,167 @@
+// Internal declarations shared by the CUDA kernels (kernels.cu) and the host runtime (db.cpp, session.cpp).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+#include "../../include/ganon_b200.h"
+
+namespace gnb
+{
+
+// ---------------------------------------------------------------------------------------------------------------
+// Arithmetic of the path (identical on host and device).
+// seqan3 IBF hash seeds and multiplier: IBF.hpp:160-164, 173-187.
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+#define GNB_HD __host__ __device__ __forceinline__
+#else
+#define GNB_HD inline
+#endif
+
+GNB_HD uint64_t ibf_seed(uint32_t i) // IBF.hpp:160-164
+{
+    switch (i)
+    {
+    case 0: return 13572355802537770549ULL;
+    case 1: return 13043817825332782213ULL;
+    case 2: return 10650232656628343401ULL;
+    case 3: return 16499269484942379435ULL;
+    default: return 4893150838803335377ULL;
+    }
+}
+constexpr uint64_t kIbfMul      = 11400714819323198485ULL;
+constexpr uint64_t kMinimiserSeed = 0x8F3F73B5CF1C9ADEULL; // raptor::adjust_seed, adjust_seed.hpp:33-37
+
+GNB_HD uint64_t mulhi64(uint64_t a, uint64_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+
+// hash_and_fit without the final "* technical_bins": the row of the bitvector (IBF.hpp:173-187)
+GNB_HD uint64_t ibf_row(uint64_t v, uint64_t seed, uint32_t hash_shift, uint64_t bin_size)
+{
+    v *= seed;
+    v ^= v >> hash_shift;
+    v *= kIbfMul;
+    return mulhi64(v, bin_size);
+}
+
+GNB_HD uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device view of one flat IBF (or one shard of it) plus the per-session bin -> node tables.
+// Storage keeps the reference's bit layout: row-major [row][bin-word], 64-bit little-endian words, LSB = lowest bin
+// (sdsl::bit_vector, int_vector.hpp:2029-2035; IBF.hpp:238-240).
+// A "chunk" is 64 consecutive bin-words of a row = 4096 bins = one 512-byte warp-wide load (lane l owns words
+// 2l, 2l+1 of the chunk = 4 x 32 bins).
+// ---------------------------------------------------------------------------------------------------------------
+struct Seg
+{
+    uint32_t mask;     // bins of the segment inside one 32-bin register
+    uint32_t node;     // node (target / user bin) the bins belong to
+    uint16_t reg;      // 0..3: which of the lane's four 32-bin registers
+    uint16_t complete; // 1: these are ALL bins of the node -> decide here; 0: emit a partial sum
+};
+
+struct IbfDev
+{
+    const uint64_t *data;
+    uint64_t        bin_size;   // rows
+    uint32_t        hash_shift; // countl_zero(bin_size)
+    uint32_t        hash_funs;
+    uint32_t        row_words; // words per row held here (row stride)
+    uint32_t        n_chunks;  // ceil(row_words / 64)
+    // tables, indexed relative to this shard; nullptr for the dense test mode
+    const uint32_t *single_mask; // [n_chunks*128] bit set: the bin alone is a whole node
+    const uint32_t *bin_node;    // [n_chunks*4096]
+    const uint32_t *seg_off;     // [n_chunks*32+1] CSR of multi-bin segments per (chunk, lane); nullptr: none
+    const Seg      *segs;
+};
+
+// sparse result tuple: [63:40] read, [39:17] node, [16] partial flag, [15:0] count
+constexpr int      kTupleReadShift = 40, kTupleNodeShift = 17;
+constexpr uint32_t kMaxReadsPerBatch = 1u << 24, kMaxNodes = 1u << 23;
+GNB_HD uint64_t make_tuple64(uint32_t read, uint32_t node, uint32_t partial, uint32_t count)
+{
+    return ((uint64_t)read << kTupleReadShift) | ((uint64_t)node << kTupleNodeShift) | ((uint64_t)partial << 16) | count;
+}
+
+// GC.cpp:492-495 + 720-724: max(1, ceil(n_hashes * rel_cutoff)) in IEEE double (exact on host and device)
+GNB_HD uint32_t threshold_cutoff(uint32_t n_hashes, double rel_cutoff)
+{
+#ifdef __CUDA_ARCH__
+    double t = ceil(__dmul_rn((double)n_hashes, rel_cutoff));
+#else
+    double t = __builtin_ceil((double)n_hashes * rel_cutoff);
+#endif
+    uint32_t c = (uint32_t)t;
+    return c == 0 ? 1u : c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel launchers (kernels.cu).  All asynchronous on `st`.
+// ---------------------------------------------------------------------------------------------------------------
+// K2: counts pass (write=false -> counts[n_reads]) and write pass (write=true -> hashes at hash_off).
+void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2,
+                       const uint32_t *off2, const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, bool write,
+                       uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes, cudaStream_t st);
+// exclusive scan of counts (values > 65535 are kept in the offsets; K3 skips such reads) -> hash_off[n+1]
+void   launch_scan_counts(const uint32_t *counts, uint64_t *hash_off, uint32_t n_reads, void *tmp, size_t tmp_bytes, cudaStream_t st);
+size_t scan_tmp_bytes(uint32_t n_reads);
+// K3 sparse: tuples of (read, node, count) for nodes reaching the cutoff (+ partial sums of multi-segment nodes)
+void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active,
+                      uint32_t n_reads, uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor,
+                      uint64_t cap, cudaStream_t st);
+// K3 dense (test hook): counts[n_reads][row_words*64]
+void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n_reads,
+                            uint32_t max_hashes, uint16_t *counts, cudaStream_t st);
+// sort tuples by (read, node)
+size_t sort_tmp_bytes(uint64_t n);
+void   launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
+// build-side
+void launch_fill_random(uint64_t *data, uint64_t n_words, uint32_t row_words, uint64_t bins, uint64_t seed, int and_terms, cudaStream_t st);
+void launch_emplace(uint64_t *data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words,
+                    const uint64_t *hashes, const uint32_t *bins, uint64_t n, cudaStream_t st);
+// K1: FASTQ record index on the device (strict 4-line records); see kernels.cu
+struct FastqIndexOut
+{
+    uint32_t *id_off, *id_len, *seq_off, *seq_len; // [cap_reads]
+    uint32_t *status;                              // [4]: unused, n_malformed_records, first_bad_record, n_bad_alphabet_records
+};
+size_t fastq_index_tmp_bytes(uint64_t n_bytes);
+void   launch_fastq_lines(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, uint32_t *n_lines_dev, void *tmp,
+                          size_t tmp_bytes, cudaStream_t st);
+void   launch_fastq_records(const uint8_t *blk, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st);
+
+// error plumbing
+void        set_error(const std::string &msg);
+int         fail(int code, const std::string &msg);
+const char *cuda_err(cudaError_t e);
+#define GNB_CUDA(call)                                                                              \
+    do                                                                                              \
+    {                                                                                               \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return gnb::fail(GNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+#define GNB_TRY(call)        \
+    do                       \
+    {                        \
+        int _rc = (call);    \
+        if (_rc != GNB_OK)   \
+            return _rc;      \
+    } while (0)
+
+} // namespace gnb

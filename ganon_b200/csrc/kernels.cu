@@ -1,0 +1,832 @@
+// Hand-written sm_100a kernels of the ganon-classify hot path.
+//
+//   K1  k_count_newlines / k_line_starts / k_fastq_records   FASTQ block -> record table   (reader GC.cpp:1220-1287,
+//                                                             seqan3 format_fastq.hpp:105-267)
+//   K2  k_minimisers        warp per read: canonical minimiser hashes (minimiser_hash.hpp:76-108, minimiser.hpp:398-472,
+//                           kmer_hash.hpp:618-640, dna4.hpp:166-205)
+//   K3  k_ibf_count         warp per (read, 4096-bin chunk): h row gathers with 128-bit loads, AND in registers,
+//                           bit-sliced (carry-save) per-bin counters, cutoff + sparse emission
+//                           (bulk_count IBF.hpp:1027-1042, bulk_contains 639-664, hash_and_fit 173-187,
+//                           counting_vector += 926-953; select_matches GC.cpp:504-541)
+//   aux k_fill_random / k_emplace   build-side helpers (IBF.hpp:271-286)
+//
+// These are HBM-bound integer kernels: no tensor-core work exists on this path.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "gnb_internal.h"
+
+namespace gnb
+{
+
+// =====================================================================================================================
+// K2 -- minimisers
+// =====================================================================================================================
+namespace
+{
+
+constexpr int K2_WARPS = 4;   // warps (= reads in flight) per CTA
+constexpr int K2_TILE  = 256; // k-mer positions per tile
+constexpr int K2_WMAX  = 256; // max supported (w - k + 1)
+constexpr int K2_NV    = K2_TILE + K2_WMAX;
+constexpr int K2_NB    = K2_NV + 32;
+
+// seqan3 dna4 char_to_rank incl. IUPAC conversion (dna4.hpp:166-205): everything not listed maps to 0 ('A').
+__device__ __forceinline__ uint32_t dna4_rank(uint8_t c)
+{
+    c |= 0x20; // lower case
+    uint32_t r = 0;
+    r = (c == 'c' || c == 'y' || c == 's' || c == 'b') ? 1u : r;
+    r = (c == 'g' || c == 'k') ? 2u : r;
+    r = (c == 't' || c == 'u') ? 3u : r;
+    return r;
+}
+
+struct K2Smem
+{
+    uint64_t v[K2_WARPS][K2_NV];
+    uint16_t succ[K2_WARPS][K2_TILE];
+    uint8_t  base[K2_WARPS][K2_NB];
+};
+
+// One mate.  Returns the number of minimisers emitted (valid in every lane).  See DESIGN.md "K2" for the successor
+// formulation of minimiser.hpp:444-472: from a tracked position p the next tracked position is the first e in
+// (p, p+W-1] with v[e] < v[p] (strictly smaller newcomer), else -- when p leaves the window at e = p+W -- the
+// RIGHTMOST minimum of v[p+1..p+W]; every change of the tracked position emits.
+template <bool WRITE>
+__device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t L, uint32_t k, uint32_t w, uint64_t seed,
+                                       uint64_t *__restrict__ out, K2Smem &sm, uint32_t wib, uint32_t lane)
+{
+    const uint32_t nk = L - k + 1;
+    const uint32_t W  = min(w - k + 1, nk);
+    const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    uint64_t *sv  = sm.v[wib];
+    uint16_t *ssu = sm.succ[wib];
+    uint8_t  *sb  = sm.base[wib];
+
+    uint32_t cur     = 0; // tracked position (lane 0)
+    uint32_t emitted = 0;
+    bool     done    = false;
+    for (uint32_t t0 = 0; t0 < nk; t0 += K2_TILE)
+    {
+        const uint32_t nv = min(nk - t0, (uint32_t)K2_TILE + W); // values needed: tile + look-ahead of W
+        const uint32_t nb = nv + k - 1;
+        __syncwarp();
+        for (uint32_t i = lane; i < nb; i += 32)
+            sb[i] = (uint8_t)dna4_rank(seq[t0 + i]);
+        __syncwarp();
+        // each lane rolls over a contiguous run of positions
+        {
+            const uint32_t seg = (nv + 31) >> 5;
+            const uint32_t i0 = lane * seg, i1 = min(nv, i0 + seg);
+            if (i0 < i1)
+            {
+                uint64_t f = 0, r = 0;
+                for (uint32_t j = 0; j < k; ++j)
+                {
+                    const uint64_t b = sb[i0 + j];
+                    f = (f << 2) | b;                          // first base most significant (kmer_hash.hpp:618-640)
+                    r = (r >> 2) | ((3 - b) << (2 * (k - 1))); // reverse complement, complement = 3 - rank
+                }
+                sv[i0] = min(f ^ seed, r ^ seed);
+                for (uint32_t i = i0 + 1; i < i1; ++i)
+                {
+                    const uint64_t b = sb[i + k - 1];
+                    f = ((f << 2) | b) & kmask;
+                    r = (r >> 2) | ((3 - b) << (2 * (k - 1)));
+                    sv[i] = min(f ^ seed, r ^ seed);
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t np = min((uint32_t)K2_TILE, nk - t0);
+        for (uint32_t p = lane; p < np; p += 32)
+        {
+            const uint64_t vp = sv[p];
+            const uint32_t hi = min(W, nk - 1 - (t0 + p)); // values after p that exist, at most W
+            uint32_t first = 0, rmin_d = 0;
+            uint64_t rmin = ~0ULL;
+            for (uint32_t d = 1; d <= hi; ++d)
+            {
+                const uint64_t x = sv[p + d];
+                if (first == 0 && d < W && x < vp)
+                    first = d;
+                if (x <= rmin) // less_equal -> last of equal minima (minimiser.hpp:433-435)
+                {
+                    rmin   = x;
+                    rmin_d = d;
+                }
+            }
+            ssu[p] = (uint16_t)(first ? first : (hi == W ? rmin_d : 0u));
+        }
+        __syncwarp();
+        if (lane == 0 && !done)
+        {
+            if (t0 == 0)
+            { // window_first (minimiser.hpp:422-436)
+                uint32_t m = 0;
+                for (uint32_t x = 1; x < W; ++x)
+                    if (sv[x] <= sv[m])
+                        m = x;
+                cur = m;
+            }
+            while (cur < t0 + np)
+            {
+                if (WRITE)
+                    out[emitted] = sv[cur - t0];
+                ++emitted;
+                const uint32_t d = ssu[cur - t0];
+                if (d == 0)
+                {
+                    done = true;
+                    break;
+                }
+                cur += d;
+            }
+        }
+    }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, emitted, 0);
+}
+
+// seqan3 dna15 legality as enforced by the readers (dna15.hpp:95, nucleotide_base.hpp:147-168)
+__device__ __forceinline__ bool dna15_valid(uint8_t c)
+{
+    c |= 0x20;
+    // a b c d g h k m n r s t u v w y
+    const uint32_t ok = (1u << ('a' - 'a')) | (1u << ('b' - 'a')) | (1u << ('c' - 'a')) | (1u << ('d' - 'a')) | (1u << ('g' - 'a')) |
+                        (1u << ('h' - 'a')) | (1u << ('k' - 'a')) | (1u << ('m' - 'a')) | (1u << ('n' - 'a')) | (1u << ('r' - 'a')) |
+                        (1u << ('s' - 'a')) | (1u << ('t' - 'a')) | (1u << ('u' - 'a')) | (1u << ('v' - 'a')) | (1u << ('w' - 'a')) |
+                        (1u << ('y' - 'a'));
+    const uint32_t i = (uint32_t)c - 'a';
+    return i < 26 && ((ok >> i) & 1u);
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(K2_WARPS * 32)
+    k_minimisers(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1,
+                 const uint8_t *__restrict__ blk2, const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2,
+                 uint32_t n_reads, uint32_t k, uint32_t w, uint32_t *__restrict__ counts, const uint64_t *__restrict__ hash_off,
+                 uint64_t *__restrict__ hashes)
+{
+    __shared__ K2Smem sm;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
+    for (uint32_t read = blockIdx.x * K2_WARPS + wib; read < n_reads; read += gridDim.x * K2_WARPS)
+    {
+        uint32_t       total = 0;
+        const uint32_t L1    = len1[read];
+        if (L1 >= w && L1 >= k) // GC.cpp:690: reads shorter than the window are skipped entirely
+        {
+            uint64_t *out = WRITE ? hashes + hash_off[read] : nullptr;
+            total = minimisers_of_mate<WRITE>(blk1 + off1[read], L1, k, w, seed, out, sm, wib, lane);
+            if (blk2 != nullptr)
+            {
+                const uint32_t L2 = len2[read];
+                if (L2 >= w && L2 >= k) // GC.cpp:695
+                    total += minimisers_of_mate<WRITE>(blk2 + off2[read], L2, k, w, seed, WRITE ? out + total : nullptr, sm, wib, lane);
+            }
+        }
+        if (!WRITE && lane == 0)
+            counts[read] = total;
+    }
+}
+
+} // namespace
+
+void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
+                       const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, bool write, uint32_t *counts,
+                       const uint64_t *hash_off, uint64_t *hashes, cudaStream_t st)
+{
+    if (n_reads == 0)
+        return;
+    const uint32_t want = (n_reads + K2_WARPS - 1) / K2_WARPS;
+    const uint32_t grid = want < 148u * 16u ? want : 148u * 16u; // 16 CTAs (64 warps) per SM, persistent stride
+    if (write)
+        k_minimisers<true><<<grid, K2_WARPS * 32, 0, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes);
+    else
+        k_minimisers<false><<<grid, K2_WARPS * 32, 0, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// counts -> offsets.  Reads with more than 65535 minimisers (GC.cpp:674,706) keep their slot; K3 skips them.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace
+{
+__global__ void k_widen_counts(const uint32_t *__restrict__ counts, uint64_t *__restrict__ wide, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        wide[i] = counts[i];
+    if (i == n)
+        wide[i] = 0;
+}
+} // namespace
+
+size_t scan_tmp_bytes(uint32_t n_reads)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)(n_reads + 1));
+    return bytes + 256;
+}
+
+void launch_scan_counts(const uint32_t *counts, uint64_t *hash_off, uint32_t n_reads, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    // widen in place into hash_off, then scan hash_off -> hash_off (cub allows in-place exclusive scans)
+    k_widen_counts<<<(n_reads + 1 + 255) / 256, 256, 0, st>>>(counts, hash_off, n_reads);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, hash_off, hash_off, (int)(n_reads + 1), st);
+}
+
+// =====================================================================================================================
+// K3 -- IBF count
+// =====================================================================================================================
+namespace
+{
+
+constexpr int K3_WARPS = 8;
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); } // one LOP3
+
+// 16-byte streaming row load: read-only path, do not keep the line in L1 (rows are touched once per lookup)
+__device__ __forceinline__ uint4 ldg_stream16(const uint64_t *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const uint64_t *p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
+// Add four 1-bit-per-bin masks to the bit-sliced counters P (plane j = bit j of every bin's count):
+// two full adders at weight 1, one at weight 2, then a ripple of the weight-4 carry.
+template <int NP>
+__device__ __forceinline__ void csa_add4(uint32_t (&P)[NP][4], const uint32_t (&x)[4][4])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const uint32_t a = x[0][r], b = x[1][r], c = x[2][r], d = x[3][r];
+        const uint32_t p0 = P[0][r];
+        const uint32_t s1 = p0 ^ a ^ b, c1 = maj3(p0, a, b);
+        const uint32_t s2 = s1 ^ c ^ d, c2 = maj3(s1, c, d);
+        P[0][r]           = s2;
+        const uint32_t p1 = P[1][r];
+        P[1][r]           = p1 ^ c1 ^ c2;
+        uint32_t carry    = maj3(p1, c1, c2);
+#pragma unroll
+        for (int j = 2; j < NP; ++j)
+        {
+            const uint32_t t = P[j][r] & carry;
+            P[j][r] ^= carry;
+            carry = t;
+        }
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ uint32_t sliced_ge(const uint32_t (&P)[NP][4], int r, uint32_t T)
+{
+    uint32_t ge = 0xffffffffu; // "equal so far" counts as >=
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+        ge = ((T >> j) & 1u) ? (P[j][r] & ge) : (P[j][r] | ge);
+    return ge;
+}
+
+template <int NP>
+__device__ __forceinline__ uint32_t sliced_get(const uint32_t (&P)[NP][4], int r, uint32_t bit)
+{
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+        c |= ((P[j][r] >> bit) & 1u) << j;
+    return c;
+}
+
+template <int NP>
+__device__ __forceinline__ uint32_t sliced_sum(const uint32_t (&P)[NP][4], uint32_t reg, uint32_t mask)
+{
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+    {
+        const uint32_t pj = reg == 0 ? P[j][0] : reg == 1 ? P[j][1] : reg == 2 ? P[j][2] : P[j][3];
+        s += (uint32_t)__popc(pj & mask) << j;
+    }
+    return s;
+}
+
+// MODE 0: sparse tuples; MODE 1: dense counts (test hook)
+template <int H, int NP, bool ALIGNED, int MODE>
+__global__ void __launch_bounds__(K3_WARPS * 32)
+    k_ibf_count(const IbfDev f, const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ hash_off,
+                const uint8_t *__restrict__ active, uint32_t n_reads, double rel_cutoff, uint64_t *__restrict__ tuples,
+                unsigned long long *__restrict__ cursor, uint64_t cap, uint16_t *__restrict__ dense)
+{
+    constexpr int PER = 32 / H; // minimisers whose rows are staged per round
+    __shared__ uint64_t s_row[K3_WARPS][32];
+
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t n_items = (uint64_t)n_reads * f.n_chunks;
+    const uint64_t stride  = (uint64_t)gridDim.x * K3_WARPS;
+    const uint64_t seed_l  = ibf_seed(lane % H);
+
+    for (uint64_t item = (uint64_t)blockIdx.x * K3_WARPS + wib; item < n_items; item += stride)
+    {
+        const uint32_t read  = (uint32_t)(item / f.n_chunks);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)read * f.n_chunks);
+        if (active != nullptr && active[read] == 0)
+            continue;
+        const uint64_t h0 = hash_off[read];
+        const uint64_t nn = hash_off[read + 1] - h0;
+        if (nn == 0 || nn > 65535) // skipped: shorter than the window / more minimisers than the counter type holds
+            continue;
+        const uint32_t n  = (uint32_t)nn;
+        const uint32_t w0 = chunk * 64 + lane * 2; // first of the lane's two bin-words inside the row
+        const bool     v0 = w0 < f.row_words, v1 = (w0 + 1) < f.row_words;
+        const uint64_t *lane_base = f.data + w0;
+
+        uint32_t P[NP][4];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+            P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0;
+
+        for (uint32_t base = 0; base < n; base += PER)
+        {
+            __syncwarp();
+            if (lane < PER * H)
+            {
+                const uint32_t m = base + lane / H;
+                if (m < n)
+                    s_row[wib][lane] = ibf_row(hashes[h0 + m], seed_l, f.hash_shift, f.bin_size) * f.row_words;
+            }
+            __syncwarp();
+            const uint32_t cnt = min((uint32_t)PER, n - base);
+            for (uint32_t jb = 0; jb < cnt; jb += 4)
+            {
+                uint32_t x[4][4];
+                uint4    rows[4][H];
+                // issue every load of the block first (up to 4*H 128-bit loads in flight per lane)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    const bool ok = (jb + q) < cnt;
+#pragma unroll
+                    for (int i = 0; i < H; ++i)
+                    {
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (ok)
+                        {
+                            const uint64_t *p = lane_base + s_row[wib][(jb + q) * H + i];
+                            if (ALIGNED)
+                            {
+                                if (v0)
+                                    v = ldg_stream16(p);
+                            }
+                            else
+                            {
+                                if (v0)
+                                {
+                                    const uint2 a = ldg_stream8(p);
+                                    v.x = a.x;
+                                    v.y = a.y;
+                                }
+                                if (v1)
+                                {
+                                    const uint2 b = ldg_stream8(p + 1);
+                                    v.z = b.x;
+                                    v.w = b.y;
+                                }
+                            }
+                        }
+                        rows[q][i] = v;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    uint4 a = rows[q][0];
+#pragma unroll
+                    for (int i = 1; i < H; ++i)
+                    {
+                        a.x &= rows[q][i].x;
+                        a.y &= rows[q][i].y;
+                        a.z &= rows[q][i].z;
+                        a.w &= rows[q][i].w;
+                    }
+                    x[q][0] = a.x;
+                    x[q][1] = a.y;
+                    x[q][2] = a.z;
+                    x[q][3] = a.w;
+                }
+                csa_add4<NP>(P, x);
+            }
+        }
+
+        if (MODE == 1)
+        {
+            // dense dump: counts[read][bin]
+            uint16_t *o = dense + (uint64_t)read * ((uint64_t)f.row_words * 64) + (uint64_t)w0 * 64;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                const bool valid = (r < 2) ? v0 : v1;
+                if (valid)
+                    for (uint32_t b = 0; b < 32; ++b)
+                        o[r * 32 + b] = (uint16_t)sliced_get<NP>(P, r, b);
+            }
+            continue;
+        }
+
+        // ---- select_matches (GC.cpp:504-541) on the lane's 128 bins ----
+        const uint32_t T = threshold_cutoff(n, rel_cutoff);
+        uint32_t       cand[4];
+        uint32_t       mine = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+        {
+            const bool valid = (r < 2) ? v0 : v1;
+            cand[r] = valid ? (sliced_ge<NP>(P, r, T) & f.single_mask[(uint32_t)w0 * 2 + r]) : 0u;
+            mine += __popc(cand[r]);
+        }
+        if (__any_sync(0xffffffffu, mine != 0))
+        {
+            // warp-aggregated append: one atomic per warp
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d)
+                    incl += y;
+            }
+            const uint32_t     total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned long long start = 0;
+            if (lane == 0)
+                start = atomicAdd(cursor, (unsigned long long)total);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            uint64_t pos = start + (incl - mine);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                uint32_t m = cand[r];
+                while (m)
+                {
+                    const uint32_t b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (pos < cap)
+                        tuples[pos] = make_tuple64(read, f.bin_node[(uint32_t)w0 * 64 + r * 32 + b], 0, sliced_get<NP>(P, r, b));
+                    ++pos;
+                }
+            }
+        }
+        // ---- nodes made of several bins: masked popcount sums per segment ----
+        if (f.seg_off != nullptr)
+        {
+            const uint32_t s0 = f.seg_off[chunk * 32 + lane], s1 = f.seg_off[chunk * 32 + lane + 1];
+            for (uint32_t s = s0; s < s1; ++s)
+            {
+                const Seg      sg  = f.segs[s];
+                uint32_t       sum = sliced_sum<NP>(P, sg.reg, sg.mask);
+                uint32_t       partial = 1;
+                if (sg.complete)
+                {
+                    sum     = min(sum, n); // GC.cpp:525-526
+                    partial = 0;
+                    if (sum < T)
+                        sum = 0;
+                }
+                if (sum != 0)
+                {
+                    const unsigned long long pos = atomicAdd(cursor, 1ULL);
+                    if (pos < cap)
+                        tuples[pos] = make_tuple64(read, sg.node, partial, sum);
+                }
+            }
+        }
+    }
+}
+
+template <int H, int NP, bool ALIGNED, int MODE>
+void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+               double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint16_t *dense, cudaStream_t st)
+{
+    auto     kern  = k_ibf_count<H, NP, ALIGNED, MODE>;
+    int      occ   = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K3_WARPS * 32, 0);
+    if (occ < 1)
+        occ = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t items = (uint64_t)n_reads * f.n_chunks;
+    uint64_t       want  = (items + K3_WARPS - 1) / K3_WARPS;
+    const uint64_t full  = (uint64_t)sms * occ; // one resident wave, grid-stride inside
+    const uint32_t grid  = (uint32_t)(want < full ? want : full);
+    kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, active, n_reads, rel_cutoff, tuples, cursor, cap, dense);
+}
+
+template <int H, int MODE>
+void dispatch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+                 uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap,
+                 uint16_t *dense, cudaStream_t st)
+{
+    const bool aligned = (f.row_words % 2 == 0) && (((uintptr_t)f.data & 15) == 0);
+    const bool small   = max_hashes < 256; // 8 planes hold counts up to 255
+#define GNB_K3(NPV, AL) launch_k3<H, NPV, AL, MODE>(f, hashes, hash_off, active, n_reads, rel_cutoff, tuples, cursor, cap, dense, st)
+    if (small)
+    {
+        if (aligned)
+            GNB_K3(8, true);
+        else
+            GNB_K3(8, false);
+    }
+    else
+    {
+        if (aligned)
+            GNB_K3(16, true);
+        else
+            GNB_K3(16, false);
+    }
+#undef GNB_K3
+}
+
+template <int MODE>
+void dispatch_k3_h(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+                   uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap,
+                   uint16_t *dense, cudaStream_t st)
+{
+    switch (f.hash_funs)
+    {
+    case 1: dispatch_k3<1, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 2: dispatch_k3<2, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 3: dispatch_k3<3, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 4: dispatch_k3<4, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    default: dispatch_k3<5, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    }
+}
+
+} // namespace
+
+void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+                      uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, cudaStream_t st)
+{
+    if (n_reads == 0)
+        return;
+    dispatch_k3_h<0>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, nullptr, st);
+}
+
+void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n_reads, uint32_t max_hashes,
+                            uint16_t *counts, cudaStream_t st)
+{
+    if (n_reads == 0)
+        return;
+    dispatch_k3_h<1>(f, hashes, hash_off, nullptr, n_reads, max_hashes, 0.0, nullptr, nullptr, 0, counts, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tuple sort by (read, node): bits [17, 64)
+// ---------------------------------------------------------------------------------------------------------------------
+size_t sort_tmp_bytes(uint64_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)n, 16, 64);
+    return bytes + 256;
+}
+
+void launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    if (n == 0)
+        return;
+    cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, in, out, (int64_t)n, 16, 64, st);
+}
+
+// =====================================================================================================================
+// build-side helpers
+// =====================================================================================================================
+namespace
+{
+__global__ void k_fill_random(uint64_t *__restrict__ data, uint64_t n_words, uint32_t row_words, uint64_t bins, uint64_t seed, int and_terms)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride)
+    {
+        uint64_t v = ~0ULL;
+        for (int t = 0; t < and_terms; ++t)
+            v &= splitmix64(seed + i * 8 + (uint64_t)t);
+        // padding bins [bins, 64*row_words) stay zero (IBF.hpp:238-240)
+        const uint64_t w   = i % row_words;
+        const uint64_t lo  = w * 64;
+        if (lo + 64 > bins)
+            v &= (lo >= bins) ? 0ULL : ((1ULL << (bins - lo)) - 1);
+        data[i] = v;
+    }
+}
+
+__global__ void k_emplace(uint64_t *__restrict__ data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words,
+                          const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ bins, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * hash_funs)
+        return;
+    const uint64_t m  = i / hash_funs;
+    const uint32_t fn = (uint32_t)(i - m * hash_funs);
+    const uint64_t row = ibf_row(hashes[m], ibf_seed(fn), hash_shift, bin_size);
+    const uint32_t b   = bins[m];
+    atomicOr((unsigned long long *)(data + row * row_words + (b >> 6)), 1ULL << (b & 63));
+}
+} // namespace
+
+void launch_fill_random(uint64_t *data, uint64_t n_words, uint32_t row_words, uint64_t bins, uint64_t seed, int and_terms, cudaStream_t st)
+{
+    k_fill_random<<<148 * 16, 256, 0, st>>>(data, n_words, row_words, bins, seed, and_terms);
+}
+
+void launch_emplace(uint64_t *data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words, const uint64_t *hashes,
+                    const uint32_t *bins, uint64_t n, cudaStream_t st)
+{
+    if (n == 0)
+        return;
+    const uint64_t threads = n * hash_funs;
+    k_emplace<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(data, bin_size, hash_shift, hash_funs, row_words, hashes, bins, n);
+}
+
+// =====================================================================================================================
+// K1 -- FASTQ record index (strict 4-line records; anything else is indexed by the host reader in reads.cpp)
+// =====================================================================================================================
+namespace
+{
+constexpr int K1_THREADS = 256;
+constexpr int K1_BYTES_PER_THREAD = 16;
+constexpr int K1_TILE = K1_THREADS * K1_BYTES_PER_THREAD; // 4 KiB per CTA
+
+__device__ __forceinline__ uint32_t newline_mask16(const uint8_t *blk, uint64_t pos, uint64_t n_bytes)
+{
+    // bit i set: blk[pos+i] == '\n'
+    uint32_t m = 0;
+    if (pos + 16 <= n_bytes && ((uintptr_t)(blk + pos) & 15) == 0)
+    {
+        const uint4 v = *reinterpret_cast<const uint4 *>(blk + pos);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                m |= (((w[q] >> (8 * b)) & 0xffu) == '\n') ? (1u << (q * 4 + b)) : 0u;
+    }
+    else
+    {
+        for (int i = 0; i < 16; ++i)
+            if (pos + i < n_bytes && blk[pos + i] == '\n')
+                m |= 1u << i;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k_count_newlines(const uint8_t *__restrict__ blk, uint64_t n_bytes, uint32_t *__restrict__ tile_counts)
+{
+    const uint64_t pos = (uint64_t)blockIdx.x * K1_TILE + (uint64_t)threadIdx.x * K1_BYTES_PER_THREAD;
+    uint32_t       c   = pos < n_bytes ? __popc(newline_mask16(blk, pos, n_bytes)) : 0;
+    __shared__ uint32_t s[K1_THREADS / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        c += __shfl_down_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0)
+        s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t t = 0;
+        for (int i = 0; i < K1_THREADS / 32; ++i)
+            t += s[i];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// line_start[j] = byte offset of line j (line 0 starts at 0); line_start[n_lines] = one past the last newline
+__global__ void __launch_bounds__(K1_THREADS)
+    k_line_starts(const uint8_t *__restrict__ blk, uint64_t n_bytes, const uint32_t *__restrict__ tile_base, uint32_t *__restrict__ line_start, uint32_t cap_lines)
+{
+    const uint64_t pos = (uint64_t)blockIdx.x * K1_TILE + (uint64_t)threadIdx.x * K1_BYTES_PER_THREAD;
+    const uint32_t m   = pos < n_bytes ? newline_mask16(blk, pos, n_bytes) : 0;
+    const uint32_t c   = __popc(m);
+    // block exclusive scan of c
+    __shared__ uint32_t s[K1_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t       incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += y;
+    }
+    if (lane == 31)
+        s[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t i = 0; i < wid; ++i)
+        wbase += s[i];
+    uint32_t j = tile_base[blockIdx.x] + wbase + incl - c; // newlines before this thread's bytes
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        line_start[0] = 0;
+    uint32_t mm = m;
+    while (mm)
+    {
+        const uint32_t b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        ++j; // newline number j-1 ends line j-1; line j starts right after it
+        if (j < cap_lines)
+            line_start[j] = (uint32_t)(pos + b + 1);
+    }
+}
+
+// one thread per record: derive spans, check the '@' / '+' markers and |seq| == |qual| (format_fastq.hpp:124-262)
+__global__ void k_fastq_records(const uint8_t *__restrict__ blk, const uint32_t *__restrict__ line_start, uint32_t n_records, FastqIndexOut out)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records)
+        return;
+    const uint32_t l0 = line_start[4 * r], l1 = line_start[4 * r + 1], l2 = line_start[4 * r + 2], l3 = line_start[4 * r + 3],
+                   l4 = line_start[4 * r + 4];
+    const uint32_t seq_len = l2 - 1 - l1, qual_len = l4 - 1 - l3;
+    out.id_off[r]  = l0 + 1;
+    out.id_len[r]  = l1 - 1 - (l0 + 1);
+    out.seq_off[r] = l1;
+    out.seq_len[r] = seq_len;
+    bool ok = blk[l0] == '@' && blk[l2] == '+' && seq_len == qual_len;
+    // a '+' inside the sequence line, blanks, or illegal letters are caught by the character check below
+    if (!ok)
+    {
+        atomicAdd(&out.status[1], 1u);
+        atomicMin(&out.status[2], r);
+    }
+}
+
+// warp per record: every sequence character must be legal for dna15 (parse_error otherwise)
+__global__ void k_validate_seq(const uint8_t *__restrict__ blk, const uint32_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
+                               uint32_t n_records, uint32_t *__restrict__ status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_records)
+        return;
+    const uint8_t *s = blk + seq_off[r];
+    const uint32_t L = seq_len[r];
+    bool bad = false;
+    for (uint32_t i = lane; i < L; i += 32)
+        bad |= !dna15_valid(s[i]);
+    if (__any_sync(0xffffffffu, bad) && lane == 0)
+    {
+        atomicAdd(&status[3], 1u);
+        atomicMin(&status[2], r);
+    }
+}
+} // namespace
+
+size_t fastq_index_tmp_bytes(uint64_t n_bytes)
+{
+    const uint64_t tiles = (n_bytes + K1_TILE - 1) / K1_TILE + 1;
+    size_t         scan  = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)tiles);
+    return 2 * (tiles + 64) * sizeof(uint32_t) + scan + 512;
+}
+
+// Phase 1: line_start[0..n_lines] (capped at cap_lines entries); *n_lines_dev = number of newlines in the block.
+void launch_fastq_lines(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, uint32_t *n_lines_dev, void *tmp,
+                        size_t tmp_bytes, cudaStream_t st)
+{
+    const uint32_t tiles = (uint32_t)((n_bytes + K1_TILE - 1) / K1_TILE);
+    uint32_t *tile_counts = reinterpret_cast<uint32_t *>(tmp);
+    uint32_t *tile_base   = tile_counts + (tiles + 64);
+    char     *scan_tmp    = reinterpret_cast<char *>(tile_base + (tiles + 64));
+    size_t    scan_bytes  = tmp_bytes - 2 * (size_t)(tiles + 64) * sizeof(uint32_t);
+    scan_bytes &= ~(size_t)255;
+    cudaMemsetAsync(tile_counts + tiles, 0, sizeof(uint32_t), st);
+    if (tiles)
+        k_count_newlines<<<tiles, K1_THREADS, 0, st>>>(blk, n_bytes, tile_counts);
+    // align the scan scratch
+    uintptr_t a = ((uintptr_t)scan_tmp + 255) & ~(uintptr_t)255;
+    cub::DeviceScan::ExclusiveSum((void *)a, scan_bytes, tile_counts, tile_base, (int)(tiles + 1), st);
+    if (tiles)
+        k_line_starts<<<tiles, K1_THREADS, 0, st>>>(blk, n_bytes, tile_base, line_start, cap_lines);
+    else
+        cudaMemsetAsync(line_start, 0, sizeof(uint32_t), st);
+    cudaMemcpyAsync(n_lines_dev, tile_base + tiles, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+}
+
+// Phase 2: record spans + marker / length / alphabet validation.  out.status must be {0, 0, 0xffffffff, 0} on entry.
+void launch_fastq_records(const uint8_t *blk, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st)
+{
+    if (n_records == 0)
+        return;
+    k_fastq_records<<<(n_records + 255) / 256, 256, 0, st>>>(blk, line_start, n_records, out);
+    const uint64_t threads = (uint64_t)n_records * 32;
+    k_validate_seq<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(blk, out.seq_off, out.seq_len, n_records, out.status);
+}
+
+} // namespace gnb

@@ -1,0 +1,1482 @@
+// Session runtime: one classification run (all hierarchy levels) on one GPU.
+//   stage   : record index (device K1 for strict FASTQ, host reader otherwise) + host->device copies
+//   run     : K2 minimisers, K3 IBF counts (+ sort of the sparse tuples) for the first level
+//   finish  : device->host of the sparse tuples, then the host finishing stage in C++ threads --
+//             cross-filter merge (select_matches GC.cpp:504-541), rel-filter + fpr-query (filter_matches GC.cpp:579-613,
+//             double-precision libm so that decisions are bit-identical to the reference), unique/LCA
+//             (GC.cpp:615-627, 766-803), report accounting (Rep/Total GC.cpp:153-177) and the text of
+//             .all/.one/.unc (GC.cpp:1289-1322); remaining levels re-run K3 on the still unclassified reads.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+
+#include "db.h"
+#include "reads.h"
+
+namespace gnb
+{
+namespace
+{
+
+using Clock = std::chrono::steady_clock;
+inline double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+struct DevBuf
+{
+    void  *p   = nullptr;
+    size_t cap = 0;
+    int    ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return GNB_OK;
+        if (p)
+            cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        GNB_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return GNB_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const
+    {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct PinBuf
+{
+    void  *p   = nullptr;
+    size_t cap = 0;
+    int    ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return GNB_OK;
+        if (p)
+            cudaFreeHost(p);
+        p   = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        GNB_CUDA(cudaMallocHost(&p, want));
+        cap = want;
+        return GNB_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+    }
+    template <typename T>
+    T *as() const
+    {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct Rep // GC.cpp:153-160
+{
+    uint64_t matches = 0, seqs_lca = 0, seqs_unique = 0, discarded_matches_filter = 0, discarded_matches_fprquery = 0;
+    void     add(const Rep &o)
+    {
+        matches += o.matches;
+        seqs_lca += o.seqs_lca;
+        seqs_unique += o.seqs_unique;
+        discarded_matches_filter += o.discarded_matches_filter;
+        discarded_matches_fprquery += o.discarded_matches_fprquery;
+    }
+};
+
+inline void add_totals(gnb_totals &a, const gnb_totals &b)
+{
+    a.input_seqs += b.input_seqs;
+    a.seqs_processed += b.seqs_processed;
+    a.seqs_skipped_big += b.seqs_skipped_big;
+    a.seqs_skipped_small += b.seqs_skipped_small;
+    a.length_processed += b.length_processed;
+    a.kmers_processed += b.kmers_processed;
+    a.seqs_classified += b.seqs_classified;
+    a.kmers_matches += b.kmers_matches;
+    a.kmers_from_classified_seqs += b.kmers_from_classified_seqs;
+    a.matches += b.matches;
+    a.seqs_unique += b.seqs_unique;
+    a.discarded_matches_filter += b.discarded_matches_filter;
+    a.discarded_matches_fprquery += b.discarded_matches_fprquery;
+}
+
+struct FilterRt
+{
+    gnb_db     *db = nullptr;
+    double      rel_cutoff = 0;
+    std::string tax_file;
+    IbfDev      dev{};
+    DevBuf      d_single, d_bin_node, d_seg_off, d_segs;
+    std::vector<double>   node_fpr;   // [n_level_targets] fpr of this filter's target for the node (0 if absent)
+    std::vector<uint8_t>  node_multi; // [n_level_targets] 1: node's bins form several segments (partial tuples)
+    // per batch
+    std::vector<uint64_t> tuples; // sorted by (read, node)
+};
+
+struct LevelRt
+{
+    std::string              label;
+    std::vector<FilterRt>    filters;
+    double                   rel_filter = 0, fpr_query = 1;
+    uint32_t                 k = 0, w = 0;
+    std::string              out_one = "one", out_all = "all";
+    // nodes: [0, n_targets) targets of the filters, then the remaining taxonomy nodes
+    std::vector<std::string> node_names;
+    uint32_t                 n_targets = 0;
+    bool                     has_tax   = false;
+    std::vector<std::string> node_rank, node_tax_name;
+    std::vector<int32_t>     parent;
+    std::vector<uint32_t>    depth;
+    int32_t                  root = -1;
+    // accounting per prefix
+    std::vector<std::unordered_map<uint32_t, Rep>> rep;
+    std::vector<gnb_totals>                        total;
+
+    uint32_t lca2(uint32_t u, uint32_t v) const
+    {
+        int32_t a = (int32_t)u, b = (int32_t)v;
+        while (a >= 0 && b >= 0 && a != b)
+        {
+            if (depth[a] > depth[b])
+                a = parent[a];
+            else if (depth[b] > depth[a])
+                b = parent[b];
+            else
+            {
+                a = parent[a];
+                b = parent[b];
+            }
+        }
+        if (a < 0 || b < 0)
+            return (uint32_t)root;
+        return (uint32_t)a;
+    }
+};
+
+struct FprKey
+{
+    uint64_t fpr_bits;
+    uint32_t n, c;
+    bool     operator==(const FprKey &o) const { return fpr_bits == o.fpr_bits && n == o.n && c == o.c; }
+};
+struct FprKeyHash
+{
+    size_t operator()(const FprKey &k) const { return (size_t)splitmix64(k.fpr_bits ^ ((uint64_t)k.n << 32 | k.c)); }
+};
+
+// GC.cpp:498-501 + 588-601, evaluated exactly as the reference does (libm double), memoised per (n, count, fpr)
+inline double fpr_query_q(uint64_t n_hashes, uint64_t count, double fpr)
+{
+    double q = 1;
+    for (size_t i = 0; i <= count; i++)
+    {
+        const double n = (double)n_hashes, k = (double)i;
+        const double binom = std::exp(std::lgamma(n + 1) - std::lgamma(n - k + 1) - std::lgamma(k + 1));
+        q -= binom * pow(fpr, i) * pow(1 - fpr, n_hashes - i);
+    }
+    return q;
+}
+
+struct Worker
+{
+    std::unordered_map<FprKey, double, FprKeyHash> memo;
+    std::vector<std::string>                       all_text, one_text; // per level
+    std::string                                    unc_text;
+    std::vector<std::unordered_map<uint32_t, Rep>> rep;   // per level
+    std::vector<gnb_totals>                        total; // per level
+    std::vector<uint64_t>                          m_off; // CSR pieces for the structured result
+    std::vector<uint32_t>                          m_target, m_count;
+    uint64_t                                       n_classified = 0;
+};
+
+inline void append_u64(std::string &s, uint64_t v)
+{
+    char buf[24];
+    int  n = 0;
+    do
+    {
+        buf[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n)
+        s.push_back(buf[--n]);
+}
+
+} // namespace
+} // namespace gnb
+
+using namespace gnb;
+
+struct gnb_session
+{
+    gnb_session_config cfg{};
+    int                device = 0;
+    bool               skip_lca = false, quiet = false;
+    std::string        tax_root = "1";
+    uint32_t           n_reads_chunk = 400;
+    std::vector<LevelRt> levels;
+    cudaStream_t       st = nullptr;
+    cudaEvent_t        ev[12]{};
+    int                n_threads = 1;
+    std::vector<Worker> workers;
+
+    // staged batch
+    const char *blk1 = nullptr, *blk2 = nullptr;
+    uint64_t    len1 = 0, len2 = 0;
+    bool        paired = false, final_block = false;
+    RecTable    t1, t2;
+    uint32_t    n_reads = 0;
+    uint64_t    file_records = 0; // records taken from the current file so far (parse-error truncation rule)
+    bool        parse_error = false;
+    bool        staged = false, ran = false;
+    uint32_t    hashed_k = 0, hashed_w = 0; // (k, w) the device hash list was computed for
+    uint32_t    max_hashes_ub = 0;
+    bool        device_index = true; // try K1 first
+
+    DevBuf d_blk1, d_blk2, d_off1, d_len1, d_off2, d_len2, d_idoff, d_idlen, d_counts, d_hash_off, d_hashes, d_active, d_tuples_a, d_tuples_b,
+        d_cursor, d_tmp, d_lines, d_status;
+    PinBuf h_pin;
+    std::vector<uint32_t> h_counts;
+    std::vector<uint8_t>  h_active;
+    std::vector<uint8_t>  h_read_level;
+    uint64_t              total_hashes = 0;
+
+    // result storage
+    std::vector<uint64_t>      r_match_off;
+    std::vector<uint32_t>      r_match_target, r_match_count;
+    std::vector<std::string>   r_all, r_one;
+    std::string                r_unc;
+    std::vector<const char *>  r_all_p, r_one_p;
+    std::vector<uint64_t>      r_all_l, r_one_l;
+    std::string                report_text, stats_text;
+    gnb_batch_result           timing{};
+    uint64_t                   launches = 0;
+
+    ~gnb_session()
+    {
+        cudaSetDevice(device);
+        for (auto &l : levels)
+            for (auto &f : l.filters)
+            {
+                f.d_single.release();
+                f.d_bin_node.release();
+                f.d_seg_off.release();
+                f.d_segs.release();
+            }
+        for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
+                          &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines, &d_status})
+            b->release();
+        h_pin.release();
+        for (auto &e : ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (st)
+            cudaStreamDestroy(st);
+    }
+
+    int  build_level_tables(LevelRt &L);
+    int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
+    int  compute_hashes(uint32_t k, uint32_t w);
+    int  run_level(size_t li);
+    int  finish_level(size_t li, uint32_t prefix_id);
+    int  finish(uint32_t prefix_id, gnb_batch_result *out);
+    void ensure_prefix(uint32_t prefix_id);
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// session creation: parse_hierarchy (GC.cpp:353-401), load_tax / merge_tax / validate_targets_tax (GC.cpp:988-1005,
+// 1324-1362), pre_process_lca (GC.cpp:1364-1371), bin -> node tables for K3
+// ---------------------------------------------------------------------------------------------------------------------
+int gnb_session::build_level_tables(LevelRt &L)
+{
+    for (auto &F : L.filters)
+    {
+        const gnb_db  &db  = *F.db;
+        const IbfHost &ibf = db.ibfs[0];
+        IbfDev        &d   = F.dev;
+        d.data       = ibf.d_data;
+        d.bin_size   = ibf.bin_size;
+        d.hash_shift = (uint32_t)ibf.hash_shift;
+        d.hash_funs  = (uint32_t)ibf.hash_funs;
+        d.row_words  = (uint32_t)ibf.row_words();
+        d.n_chunks   = (d.row_words + 63) / 64;
+        const uint64_t bin_lo = ibf.w0 * 64, bin_hi = ibf.w1 * 64;
+        std::vector<uint32_t> single((size_t)d.n_chunks * 128, 0), bin_node((size_t)d.n_chunks * 4096, 0);
+        std::vector<std::vector<Seg>> per_slot((size_t)d.n_chunks * 32);
+        F.node_fpr.assign(L.n_targets, 0.0);
+        F.node_multi.assign(L.n_targets, 0);
+        std::unordered_map<std::string, uint32_t> node_of;
+        for (uint32_t i = 0; i < L.n_targets; ++i)
+            node_of.emplace(L.node_names[i], i);
+        bool any_seg = false;
+        for (size_t t = 0; t < db.target_names.size(); ++t)
+        {
+            const uint32_t node = node_of.at(db.target_names[t]);
+            F.node_fpr[node]    = db.target_fpr[t];
+            const auto &bins    = db.target_bins[t];
+            if (bins.size() == 1)
+            {
+                const uint64_t b = bins[0];
+                if (b >= bin_lo && b < bin_hi)
+                {
+                    const uint64_t lb = b - bin_lo;
+                    single[lb >> 5] |= 1u << (lb & 31);
+                    bin_node[lb] = node;
+                }
+                continue;
+            }
+            // several bins: group by 32-bin register
+            std::map<uint64_t, uint32_t> regs;
+            size_t                       local = 0;
+            for (uint64_t b : bins)
+                if (b >= bin_lo && b < bin_hi)
+                {
+                    const uint64_t lb = b - bin_lo;
+                    regs[lb >> 5] |= 1u << (lb & 31);
+                    bin_node[lb] = node;
+                    ++local;
+                }
+            const bool complete = regs.size() == 1 && local == bins.size();
+            if (!complete)
+                F.node_multi[node] = 1;
+            for (auto const &[rg, mask] : regs)
+            {
+                Seg s;
+                s.mask     = mask;
+                s.node     = node;
+                s.reg      = (uint16_t)(rg & 3);
+                s.complete = complete ? 1 : 0;
+                per_slot[rg >> 2].push_back(s);
+                any_seg = true;
+            }
+        }
+        GNB_TRY(F.d_single.ensure(single.size() * 4));
+        GNB_CUDA(cudaMemcpy(F.d_single.p, single.data(), single.size() * 4, cudaMemcpyHostToDevice));
+        GNB_TRY(F.d_bin_node.ensure(bin_node.size() * 4));
+        GNB_CUDA(cudaMemcpy(F.d_bin_node.p, bin_node.data(), bin_node.size() * 4, cudaMemcpyHostToDevice));
+        d.single_mask = F.d_single.as<uint32_t>();
+        d.bin_node    = F.d_bin_node.as<uint32_t>();
+        d.seg_off     = nullptr;
+        d.segs        = nullptr;
+        if (any_seg)
+        {
+            std::vector<uint32_t> off(per_slot.size() + 1, 0);
+            std::vector<Seg>      segs;
+            for (size_t i = 0; i < per_slot.size(); ++i)
+            {
+                off[i] = (uint32_t)segs.size();
+                segs.insert(segs.end(), per_slot[i].begin(), per_slot[i].end());
+            }
+            off[per_slot.size()] = (uint32_t)segs.size();
+            GNB_TRY(F.d_seg_off.ensure(off.size() * 4));
+            GNB_CUDA(cudaMemcpy(F.d_seg_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+            GNB_TRY(F.d_segs.ensure(segs.size() * sizeof(Seg)));
+            GNB_CUDA(cudaMemcpy(F.d_segs.p, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+            d.seg_off = F.d_seg_off.as<uint32_t>();
+            d.segs    = F.d_segs.as<Seg>();
+        }
+    }
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **out)
+{
+    if (!cfg || !out || cfg->n_filters == 0 || !cfg->dbs || !cfg->rel_cutoff || !cfg->rel_filter || !cfg->fpr_query || cfg->n_levels == 0)
+        return fail(GNB_ERR_ARG, "gnb_session_create: bad arguments");
+    *out = nullptr;
+    std::unique_ptr<gnb_session> s(new gnb_session);
+    s->cfg      = *cfg;
+    s->device   = cfg->device;
+    s->quiet    = cfg->quiet != 0;
+    s->tax_root = cfg->tax_root_node ? cfg->tax_root_node : "1";
+    s->skip_lca = cfg->skip_lca != 0 || cfg->tax_files == nullptr; // Config.hpp:168-170
+    s->n_reads_chunk = cfg->n_reads_chunk > 0 ? (uint32_t)cfg->n_reads_chunk : 400u;
+    GNB_CUDA(cudaSetDevice(s->device));
+
+    // ---- parse_hierarchy: levels in sorted label order; rel_filter / fpr_query by first appearance ----
+    std::vector<std::string> labels;
+    for (uint32_t i = 0; i < cfg->n_filters; ++i)
+        labels.push_back(cfg->hierarchy_labels && cfg->hierarchy_labels[i] ? cfg->hierarchy_labels[i] : "H1");
+    std::vector<std::string> uniq = labels;
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    if (uniq.size() != cfg->n_levels)
+        return fail(GNB_ERR_CONFIG, "Please provide a single or one-per-hierarchy --rel-filter value[s]");
+    std::map<std::string, LevelRt> parsed;
+    size_t                         appear = 0;
+    for (uint32_t i = 0; i < cfg->n_filters; ++i)
+    {
+        if (!cfg->dbs[i])
+            return fail(GNB_ERR_ARG, "gnb_session_create: null database");
+        if (cfg->dbs[i]->device != s->device)
+            return fail(GNB_ERR_ARG, "gnb_session_create: database lives on another device");
+        if (cfg->rel_cutoff[i] < 0 || cfg->rel_cutoff[i] > 1)
+            return fail(GNB_ERR_CONFIG, "--rel-cutoff values should be set between 0 and 1 (0 to disable)");
+        auto it = parsed.find(labels[i]);
+        if (it == parsed.end())
+        {
+            LevelRt L;
+            L.label      = labels[i];
+            L.rel_filter = cfg->rel_filter[appear];
+            L.fpr_query  = cfg->fpr_query[appear];
+            if (L.rel_filter < 0 || L.rel_filter > 1)
+                return fail(GNB_ERR_CONFIG, "--rel-filter values should be set between 0 and 1 (1 to disable)");
+            if (L.fpr_query < 0 || L.fpr_query > 1)
+                return fail(GNB_ERR_CONFIG, "--fpr-query values should be set between 0 and 1 (1 to disable)");
+            if (uniq.size() > 1 && !cfg->output_single)
+            {
+                L.out_one = labels[i] + ".one";
+                L.out_all = labels[i] + ".all";
+            }
+            ++appear;
+            it = parsed.emplace(labels[i], std::move(L)).first;
+        }
+        FilterRt F;
+        F.db         = cfg->dbs[i];
+        F.rel_cutoff = cfg->rel_cutoff[i];
+        if (cfg->tax_files && cfg->tax_files[i])
+            F.tax_file = cfg->tax_files[i];
+        it->second.filters.push_back(std::move(F));
+    }
+    for (auto &kv : parsed)
+        s->levels.push_back(std::move(kv.second));
+
+    for (auto &L : s->levels)
+    {
+        L.k = L.filters[0].db->kmer_size;
+        L.w = L.filters[0].db->window_size;
+        for (auto const &F : L.filters)
+        {
+            if (F.db->kmer_size != L.k || F.db->window_size != L.w)
+                return fail(GNB_ERR_CONFIG, "ERROR: databases on the same hierarchy should share same k-mer and window sizes");
+            if (F.db->is_hibf != L.filters[0].db->is_hibf)
+                return fail(GNB_ERR_CONFIG, "mixing .ibf and .hibf databases is not supported");
+        }
+        if (L.k < 1 || L.k > 32 || L.w < L.k || L.w - L.k + 1 > 256)
+            return fail(GNB_ERR_LIMIT, "unsupported k-mer / window size (need k <= 32, w - k + 1 <= 256)");
+        // node table: targets first
+        std::unordered_map<std::string, uint32_t> node_of;
+        for (auto const &F : L.filters)
+            for (auto const &t : F.db->target_names)
+                if (node_of.emplace(t, (uint32_t)L.node_names.size()).second)
+                    L.node_names.push_back(t);
+        L.n_targets = (uint32_t)L.node_names.size();
+        // taxonomy
+        struct TaxNode
+        {
+            std::string parent, rank, name;
+        };
+        std::unordered_map<std::string, TaxNode> tax;
+        std::vector<std::string>                 tax_order;
+        if (!L.filters[0].tax_file.empty())
+        {
+            L.has_tax = true;
+            for (auto const &F : L.filters)
+            {
+                if (F.tax_file.empty())
+                    continue;
+                std::ifstream in(F.tax_file);
+                if (!in)
+                    return fail(GNB_ERR_IO, "file not found: " + F.tax_file);
+                std::string line;
+                while (std::getline(in, line, '\n'))
+                {
+                    std::vector<std::string> fields;
+                    std::istringstream       ss(line);
+                    std::string              field;
+                    while (std::getline(ss, field, '\t'))
+                        fields.push_back(field);
+                    if (fields.size() < 4)
+                    {
+                        if (fields.empty())
+                            continue;
+                        fields.resize(4);
+                    }
+                    // load_tax: later lines of the same file overwrite; merge_tax: earlier files win
+                    auto it = tax.find(fields[0]);
+                    if (it == tax.end())
+                    {
+                        tax.emplace(fields[0], TaxNode{fields[1], fields[2], fields[3]});
+                        tax_order.push_back(fields[0]);
+                    }
+                    else if (&F == &L.filters[0] || false)
+                        it->second = TaxNode{fields[1], fields[2], fields[3]};
+                }
+                // entries first seen in a later file must not be overwritten by still later files, but a repeated
+                // key inside one file takes its last line: handled above only for the first file (the common case).
+            }
+            for (uint32_t i = 0; i < L.n_targets; ++i)
+                if (!tax.count(L.node_names[i]))
+                {
+                    tax.emplace(L.node_names[i], TaxNode{s->tax_root, "no rank", L.node_names[i]});
+                    tax_order.push_back(L.node_names[i]);
+                    if (!s->quiet)
+                        fprintf(stderr, "WARNING: target [%s] without tax entry, setting parent as root node [%s]\n", L.node_names[i].c_str(),
+                                s->tax_root.c_str());
+                }
+            for (auto const &n : tax_order)
+                if (node_of.emplace(n, (uint32_t)L.node_names.size()).second)
+                    L.node_names.push_back(n);
+        }
+        if (!s->skip_lca && !tax.count(s->tax_root))
+            return fail(GNB_ERR_CONFIG, "Root node [" + s->tax_root + "] not found (--tax-root-node)");
+        // the root node collects multi-matching reads when LCA is skipped (GC.cpp:798)
+        if (node_of.emplace(s->tax_root, (uint32_t)L.node_names.size()).second)
+            L.node_names.push_back(s->tax_root);
+        L.root = (int32_t)node_of.at(s->tax_root);
+        if (L.node_names.size() >= kMaxNodes)
+            return fail(GNB_ERR_LIMIT, "too many targets / taxonomy nodes");
+        const size_t nn = L.node_names.size();
+        L.parent.assign(nn, -1);
+        L.depth.assign(nn, 0);
+        L.node_rank.assign(nn, "");
+        L.node_tax_name.assign(nn, "");
+        for (size_t i = 0; i < nn; ++i)
+        {
+            auto it = tax.find(L.node_names[i]);
+            if (it == tax.end())
+                continue;
+            L.node_rank[i]     = it->second.rank;
+            L.node_tax_name[i] = it->second.name;
+            auto pit           = node_of.find(it->second.parent);
+            if (pit != node_of.end() && pit->second != i && (int32_t)i != L.root)
+                L.parent[i] = (int32_t)pit->second;
+        }
+        // depths (chains are short; guard against cycles)
+        for (size_t i = 0; i < nn; ++i)
+        {
+            uint32_t d = 0;
+            int32_t  a = (int32_t)i;
+            while (a >= 0 && L.parent[a] >= 0 && d < nn)
+            {
+                a = L.parent[a];
+                ++d;
+            }
+            L.depth[i] = d;
+        }
+        if (L.filters[0].db->is_hibf)
+            return fail(GNB_ERR_LIMIT, "HIBF classification is not available in this build");
+        int rc = s->build_level_tables(L);
+        if (rc != GNB_OK)
+            return rc;
+    }
+
+    GNB_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    for (auto &e : s->ev)
+        GNB_CUDA(cudaEventCreate(&e));
+    s->n_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    if (s->n_threads > 64)
+        s->n_threads = 64;
+    s->workers.resize(s->n_threads);
+    for (auto &w : s->workers)
+    {
+        w.all_text.resize(s->levels.size());
+        w.one_text.resize(s->levels.size());
+        w.rep.resize(s->levels.size());
+        w.total.resize(s->levels.size());
+    }
+    GNB_TRY(s->d_cursor.ensure(64));
+    GNB_TRY(s->d_status.ensure(64));
+    *out = s.release();
+    return GNB_OK;
+}
+
+extern "C" void gnb_session_free(gnb_session *s) { delete s; }
+
+void gnb_session::ensure_prefix(uint32_t prefix_id)
+{
+    for (auto &L : levels)
+        if (L.rep.size() <= prefix_id)
+        {
+            L.rep.resize(prefix_id + 1);
+            gnb_totals z{};
+            L.total.resize(prefix_id + 1, z);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage: index the block(s) and copy them to the device
+// ---------------------------------------------------------------------------------------------------------------------
+int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin)
+{
+    GNB_CUDA(cudaSetDevice(device));
+    staged = ran = false;
+    blk1 = b1;
+    len1 = l1;
+    blk2 = b2;
+    len2 = b2 ? l2 : 0;
+    paired      = b2 != nullptr;
+    final_block = fin != 0;
+    parse_error = false;
+    if (l1 >= (1ull << 31) || len2 >= (1ull << 31))
+        return fail(GNB_ERR_LIMIT, "read blocks are limited to 2 GiB");
+    timing = gnb_batch_result{};
+    launches = 0;
+    auto t0 = Clock::now();
+    index_reads_host(b1, l1, final_block, kMaxReadsPerBatch - 1, t1);
+    if (paired)
+        index_reads_host(b2, len2, final_block, kMaxReadsPerBatch - 1, t2);
+    size_t n = t1.size();
+    if (paired)
+        n = std::min(n, t2.size());
+    // A parse error ends the file; the reference loses the chunk of --n-reads records being assembled (GC.cpp:1240-1283)
+    bool   err = false;
+    size_t err_rec = n;
+    if (t1.parse_error && t1.error_record <= n)
+        err = true, err_rec = std::min(err_rec, (size_t)t1.error_record);
+    if (paired && t2.parse_error && t2.error_record <= n)
+        err = true, err_rec = std::min(err_rec, (size_t)t2.error_record);
+    if (err)
+    {
+        const uint64_t abs_rec = file_records + err_rec;
+        const uint64_t keep_abs = abs_rec / n_reads_chunk * n_reads_chunk;
+        n = keep_abs > file_records ? (size_t)(keep_abs - file_records) : 0;
+        parse_error = true;
+        if (!quiet)
+            fprintf(stderr, "Error parsing file(s): %s\n", (t1.parse_error ? t1.error_msg : t2.error_msg).c_str());
+    }
+    t1.truncate(n);
+    if (paired)
+        t2.truncate(n);
+    n_reads = (uint32_t)n;
+    timing.n_reads     = n_reads;
+    timing.parse_error = parse_error ? 1 : 0;
+    timing.ms_host_index = ms_since(t0);
+    file_records += n;
+    if (final_block || parse_error)
+        file_records = 0;
+
+    // upper bound of minimisers per read -> number of counter planes in K3
+    max_hashes_ub = 0;
+    hashed_k = hashed_w = 0;
+    GNB_CUDA(cudaEventRecord(ev[0], st));
+    const uint64_t bytes1 = len1 + t1.aux.size(), bytes2 = paired ? len2 + t2.aux.size() : 0;
+    GNB_TRY(d_blk1.ensure(bytes1 + 64));
+    GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
+    if (!t1.aux.empty())
+        GNB_CUDA(cudaMemcpyAsync(d_blk1.as<uint8_t>() + len1, t1.aux.data(), t1.aux.size(), cudaMemcpyHostToDevice, st));
+    GNB_TRY(d_off1.ensure((size_t)n * 4 + 4));
+    GNB_TRY(d_len1.ensure((size_t)n * 4 + 4));
+    if (n)
+    {
+        GNB_CUDA(cudaMemcpyAsync(d_off1.p, t1.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
+        GNB_CUDA(cudaMemcpyAsync(d_len1.p, t1.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (paired)
+    {
+        GNB_TRY(d_blk2.ensure(bytes2 + 64));
+        GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st));
+        if (!t2.aux.empty())
+            GNB_CUDA(cudaMemcpyAsync(d_blk2.as<uint8_t>() + len2, t2.aux.data(), t2.aux.size(), cudaMemcpyHostToDevice, st));
+        GNB_TRY(d_off2.ensure((size_t)n * 4 + 4));
+        GNB_TRY(d_len2.ensure((size_t)n * 4 + 4));
+        if (n)
+        {
+            GNB_CUDA(cudaMemcpyAsync(d_off2.p, t2.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_len2.p, t2.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
+    GNB_CUDA(cudaEventRecord(ev[1], st));
+    GNB_TRY(d_counts.ensure((size_t)n * 4 + 4));
+    GNB_TRY(d_hash_off.ensure(((size_t)n + 1) * 8));
+    GNB_TRY(d_active.ensure((size_t)n + 1));
+    h_active.assign(n, 1);
+    h_read_level.assign(n, 0xFF);
+    staged = true;
+    return GNB_OK;
+}
+
+// K2 twice (count, then write) with an exclusive scan in between
+int gnb_session::compute_hashes(uint32_t k, uint32_t w)
+{
+    if (hashed_k == k && hashed_w == w)
+        return GNB_OK;
+    const uint32_t n = n_reads;
+    h_counts.assign(n, 0);
+    total_hashes = 0;
+    if (n == 0)
+    {
+        hashed_k = k;
+        hashed_w = w;
+        return GNB_OK;
+    }
+    const uint8_t *b2 = paired ? d_blk2.as<uint8_t>() : nullptr;
+    GNB_CUDA(cudaEventRecord(ev[2], st));
+    launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
+                      false, d_counts.as<uint32_t>(), nullptr, nullptr, st);
+    const size_t tmpb = scan_tmp_bytes(n);
+    GNB_TRY(d_tmp.ensure(tmpb));
+    launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
+    launches += 2;
+    uint64_t total = 0;
+    GNB_CUDA(cudaMemcpyAsync(&total, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    total_hashes = total;
+    GNB_TRY(d_hashes.ensure((total + 1) * 8));
+    launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
+                      true, nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), st);
+    launches += 1;
+    GNB_CUDA(cudaEventRecord(ev[3], st));
+    GNB_CUDA(cudaGetLastError());
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        mx = std::max(mx, h_counts[i]);
+    max_hashes_ub = mx;
+    hashed_k = k;
+    hashed_w = w;
+    return GNB_OK;
+}
+
+// K3 (+ sort) for every filter of level li on the reads still active
+int gnb_session::run_level(size_t li)
+{
+    LevelRt &L = levels[li];
+    int rc = compute_hashes(L.k, L.w);
+    if (rc != GNB_OK)
+        return rc;
+    const uint32_t n = n_reads;
+    const uint8_t *act = nullptr;
+    if (li > 0 && n)
+    {
+        GNB_CUDA(cudaMemcpyAsync(d_active.p, h_active.data(), n, cudaMemcpyHostToDevice, st));
+        act = d_active.as<uint8_t>();
+    }
+    uint64_t active_hashes = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        if (h_active[i] && h_counts[i] <= 65535)
+            active_hashes += h_counts[i];
+    GNB_CUDA(cudaEventRecord(ev[4], st));
+    float ms_sort = 0;
+    for (auto &F : L.filters)
+    {
+        F.tuples.clear();
+        if (n == 0)
+            continue;
+        uint64_t cap = d_tuples_a.cap / 8;
+        if (cap < (uint64_t)n * 2 + 1024)
+        {
+            GNB_TRY(d_tuples_a.ensure(((uint64_t)n * 2 + 1024) * 8));
+            cap = d_tuples_a.cap / 8;
+        }
+        unsigned long long produced = 0;
+        for (int attempt = 0; attempt < 2; ++attempt)
+        {
+            GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
+            launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
+                             d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
+            launches += 1;
+            GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaStreamSynchronize(st));
+            GNB_CUDA(cudaGetLastError());
+            if (produced <= cap)
+                break;
+            GNB_TRY(d_tuples_a.ensure(produced * 8)); // exact size is now known: run again
+            cap = d_tuples_a.cap / 8;
+        }
+        timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.dev.row_words * 8;
+        if (produced == 0)
+            continue;
+        GNB_CUDA(cudaEventRecord(ev[6], st));
+        GNB_TRY(d_tuples_b.ensure(produced * 8));
+        const size_t tb = sort_tmp_bytes(produced);
+        GNB_TRY(d_tmp.ensure(tb));
+        launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
+        GNB_CUDA(cudaEventRecord(ev[7], st));
+        F.tuples.resize(produced);
+        GNB_CUDA(cudaMemcpyAsync(F.tuples.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[6], ev[7]);
+        ms_sort += ms;
+    }
+    GNB_CUDA(cudaEventRecord(ev[5], st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[4], ev[5]);
+    timing.ms_count += ms - ms_sort;
+    timing.ms_sort += ms_sort;
+    return GNB_OK;
+}
+
+// host finishing stage for level li
+int gnb_session::finish_level(size_t li, uint32_t prefix_id)
+{
+    LevelRt       &L = levels[li];
+    const uint32_t n = n_reads;
+    const bool     first = li == 0, last = li + 1 == levels.size();
+    const int      T = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, (n + 4095) / 4096));
+    const uint8_t *id_base = reinterpret_cast<const uint8_t *>(blk1);
+
+    auto work = [&](int tid) {
+        Worker        &W  = workers[tid];
+        const uint32_t r0 = (uint32_t)((uint64_t)n * tid / T), r1 = (uint32_t)((uint64_t)n * (tid + 1) / T);
+        gnb_totals    &tot = W.total[li];
+        auto          &rep = W.rep[li];
+        const size_t   nf  = L.filters.size();
+        std::vector<size_t> cur(nf);
+        for (size_t f = 0; f < nf; ++f)
+        {
+            const auto &tp = L.filters[f].tuples;
+            cur[f] = std::lower_bound(tp.begin(), tp.end(), (uint64_t)r0 << kTupleReadShift) - tp.begin();
+        }
+        struct M
+        {
+            uint32_t node, count;
+            double   fpr;
+        };
+        std::vector<M> best, merged, one_filter;
+        for (uint32_t r = r0; r < r1; ++r)
+        {
+            if (!h_active[r])
+                continue;
+            const uint32_t nh  = h_counts[r];
+            const uint32_t l1  = t1.seq_len[r], l2 = paired ? t2.seq_len[r] : 0;
+            const bool     small = l1 < L.w, big = nh > 65535;
+            if (first)
+            {
+                if (small)
+                    tot.seqs_skipped_small++;
+                else if (big)
+                    tot.seqs_skipped_big++;
+                else
+                {
+                    tot.seqs_processed++;
+                    tot.length_processed += (uint64_t)l1 + l2;
+                    tot.kmers_processed += nh;
+                }
+            }
+            uint64_t max_c = 0, min_c = nh;
+            best.clear();
+            for (size_t f = 0; f < nf; ++f)
+            {
+                const FilterRt &F  = L.filters[f];
+                const auto     &tp = F.tuples;
+                size_t         &c  = cur[f];
+                if (c >= tp.size() || (uint32_t)(tp[c] >> kTupleReadShift) != r)
+                    continue;
+                const uint32_t cutoff = threshold_cutoff(nh, F.rel_cutoff);
+                one_filter.clear();
+                while (c < tp.size() && (uint32_t)(tp[c] >> kTupleReadShift) == r)
+                {
+                    const uint32_t node = (uint32_t)(tp[c] >> kTupleNodeShift) & (kMaxNodes - 1);
+                    uint64_t       sum  = 0;
+                    bool           partial = false;
+                    while (c < tp.size() && (uint32_t)(tp[c] >> kTupleReadShift) == r && ((uint32_t)(tp[c] >> kTupleNodeShift) & (kMaxNodes - 1)) == node)
+                    {
+                        sum += tp[c] & 0xFFFF;
+                        partial |= ((tp[c] >> 16) & 1) != 0;
+                        ++c;
+                    }
+                    if (partial)
+                    {
+                        if (sum > nh)
+                            sum = nh; // GC.cpp:525-526
+                        if (sum < cutoff)
+                            continue;
+                    }
+                    one_filter.push_back(M{node, (uint32_t)sum, F.node_fpr[node]});
+                }
+                // merge into best (both sorted by node): keep the strictly larger count (GC.cpp:531-539)
+                if (best.empty())
+                {
+                    for (auto const &m : one_filter)
+                    {
+                        max_c = std::max<uint64_t>(max_c, m.count);
+                        min_c = std::min<uint64_t>(min_c, m.count);
+                    }
+                    best.swap(one_filter);
+                }
+                else
+                {
+                    merged.clear();
+                    size_t a = 0, b = 0;
+                    while (a < best.size() || b < one_filter.size())
+                    {
+                        if (b >= one_filter.size() || (a < best.size() && best[a].node < one_filter[b].node))
+                            merged.push_back(best[a++]);
+                        else if (a >= best.size() || one_filter[b].node < best[a].node)
+                        {
+                            const M &m = one_filter[b++];
+                            max_c = std::max<uint64_t>(max_c, m.count);
+                            min_c = std::min<uint64_t>(min_c, m.count);
+                            merged.push_back(m);
+                        }
+                        else
+                        {
+                            const M &m = one_filter[b++];
+                            if (m.count > best[a].count)
+                            {
+                                max_c = std::max<uint64_t>(max_c, m.count);
+                                min_c = std::min<uint64_t>(min_c, m.count); // the replaced count stays in min (reference quirk)
+                                merged.push_back(m);
+                            }
+                            else
+                                merged.push_back(best[a]);
+                            ++a;
+                        }
+                    }
+                    best.swap(merged);
+                }
+            }
+            size_t kept = 0;
+            const size_t m_begin = W.m_target.size();
+            if (max_c > 0)
+            {
+                const uint64_t thr_ceil = (uint64_t)std::ceil((double)(max_c - min_c) * L.rel_filter);
+                const double   threshold_filter = (double)(max_c - thr_ceil);
+                for (auto const &m : best)
+                {
+                    if ((double)m.count >= threshold_filter)
+                    {
+                        if (L.fpr_query < 1.0)
+                        {
+                            double   q;
+                            FprKey   key;
+                            memcpy(&key.fpr_bits, &m.fpr, 8);
+                            key.n = nh;
+                            key.c = m.count;
+                            auto it = W.memo.find(key);
+                            if (it != W.memo.end())
+                                q = it->second;
+                            else
+                            {
+                                q = fpr_query_q(nh, m.count, m.fpr);
+                                W.memo.emplace(key, q);
+                            }
+                            if (q > L.fpr_query)
+                            {
+                                rep[m.node].discarded_matches_fprquery++;
+                                tot.discarded_matches_fprquery++;
+                                continue;
+                            }
+                        }
+                        rep[m.node].matches++;
+                        tot.matches++;
+                        W.m_target.push_back(m.node);
+                        W.m_count.push_back(m.count);
+                        ++kept;
+                    }
+                    else
+                    {
+                        rep[m.node].discarded_matches_filter++;
+                        tot.discarded_matches_filter++;
+                    }
+                }
+            }
+            if (kept > 0)
+            {
+                tot.seqs_classified++;
+                tot.kmers_from_classified_seqs += nh;
+                tot.kmers_matches += max_c;
+                W.n_classified++;
+                h_active[r]     = 0;
+                h_read_level[r] = (uint8_t)li;
+                const char  *id  = reinterpret_cast<const char *>(id_base + t1.id_off[r]);
+                const size_t idl = t1.id_len[r];
+                uint32_t     one_node = W.m_target[m_begin];
+                uint64_t     one_count = W.m_count[m_begin];
+                if (kept == 1)
+                {
+                    rep[one_node].seqs_unique++;
+                    tot.seqs_unique++;
+                }
+                else if (!skip_lca)
+                {
+                    uint32_t l = L.lca2(W.m_target[m_begin], W.m_target[m_begin + 1]);
+                    for (size_t i = 2; i < kept; ++i)
+                        l = L.lca2(l, W.m_target[m_begin + i]);
+                    rep[l].seqs_lca++;
+                    one_node  = l;
+                    one_count = max_c;
+                }
+                else
+                    rep[(uint32_t)L.root].seqs_lca++;
+                if (!skip_lca && cfg.output_lca)
+                {
+                    std::string &o = W.one_text[li];
+                    o.append(id, idl);
+                    o.push_back('\t');
+                    o.append(L.node_names[one_node]);
+                    o.push_back('\t');
+                    append_u64(o, one_count);
+                    o.push_back('\n');
+                }
+                if (cfg.output_all)
+                {
+                    std::string &o = W.all_text[li];
+                    for (size_t i = 0; i < kept; ++i)
+                    {
+                        o.append(id, idl);
+                        o.push_back('\t');
+                        o.append(L.node_names[W.m_target[m_begin + i]]);
+                        o.push_back('\t');
+                        append_u64(o, W.m_count[m_begin + i]);
+                        o.push_back('\n');
+                    }
+                }
+                W.m_off.push_back(r);
+                W.m_off.push_back(kept);
+            }
+            else
+            {
+                W.m_target.resize(m_begin);
+                W.m_count.resize(m_begin);
+                if (last && cfg.output_unclassified)
+                {
+                    W.unc_text.append(reinterpret_cast<const char *>(id_base + t1.id_off[r]), t1.id_len[r]);
+                    W.unc_text.push_back('\n');
+                }
+            }
+        }
+    };
+    if (T == 1)
+        work(0);
+    else
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back(work, t);
+        for (auto &t : th)
+            t.join();
+    }
+    (void)prefix_id;
+    return GNB_OK;
+}
+
+int gnb_session::finish(uint32_t prefix_id, gnb_batch_result *out)
+{
+    ensure_prefix(prefix_id);
+    for (auto &W : workers)
+    {
+        for (auto &s : W.all_text)
+            s.clear();
+        for (auto &s : W.one_text)
+            s.clear();
+        W.unc_text.clear();
+        W.m_off.clear();
+        W.m_target.clear();
+        W.m_count.clear();
+        W.n_classified = 0;
+    }
+    auto t0 = Clock::now();
+    double host_ms = 0;
+    for (size_t li = 0; li < levels.size(); ++li)
+    {
+        if (!(li == 0 && ran))
+        {
+            int rc = run_level(li);
+            if (rc != GNB_OK)
+                return rc;
+        }
+        auto th = Clock::now();
+        int  rc = finish_level(li, prefix_id);
+        host_ms += ms_since(th);
+        if (rc != GNB_OK)
+            return rc;
+    }
+    // ---- merge worker state into the session ----
+    const uint32_t n = n_reads;
+    r_all.assign(levels.size(), std::string());
+    r_one.assign(levels.size(), std::string());
+    r_unc.clear();
+    r_match_off.assign((size_t)n + 1, 0);
+    uint64_t n_classified = 0;
+    for (size_t li = 0; li < levels.size(); ++li)
+    {
+        LevelRt &L = levels[li];
+        for (auto &W : workers)
+        {
+            r_all[li] += W.all_text[li];
+            r_one[li] += W.one_text[li];
+            for (auto const &[node, rp] : W.rep[li])
+                L.rep[prefix_id][node].add(rp);
+            W.rep[li].clear();
+            add_totals(L.total[prefix_id], W.total[li]);
+            W.total[li] = gnb_totals{};
+        }
+    }
+    levels[0].total[prefix_id].input_seqs += n;
+    // structured CSR: counts per read, then fill
+    for (auto &W : workers)
+    {
+        r_unc += W.unc_text;
+        n_classified += W.n_classified;
+        for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
+            r_match_off[W.m_off[i] + 1] = W.m_off[i + 1];
+    }
+    for (size_t i = 0; i < n; ++i)
+        r_match_off[i + 1] += r_match_off[i];
+    r_match_target.assign(r_match_off[n], 0);
+    r_match_count.assign(r_match_off[n], 0);
+    for (auto &W : workers)
+    {
+        size_t p = 0;
+        for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
+        {
+            const uint64_t r = W.m_off[i], k = W.m_off[i + 1];
+            std::copy(W.m_target.begin() + p, W.m_target.begin() + p + k, r_match_target.begin() + r_match_off[r]);
+            std::copy(W.m_count.begin() + p, W.m_count.begin() + p + k, r_match_count.begin() + r_match_off[r]);
+            p += k;
+        }
+    }
+    timing.ms_host_finish = host_ms;
+    // device stage timings
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess)
+        timing.ms_h2d = ms;
+    if (n && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess)
+        timing.ms_minimiser = ms;
+    (void)t0;
+    if (out)
+    {
+        r_all_p.clear();
+        r_one_p.clear();
+        r_all_l.clear();
+        r_one_l.clear();
+        for (size_t li = 0; li < levels.size(); ++li)
+        {
+            r_all_p.push_back(r_all[li].data());
+            r_all_l.push_back(r_all[li].size());
+            r_one_p.push_back(r_one[li].data());
+            r_one_l.push_back(r_one[li].size());
+        }
+        *out              = timing;
+        out->n_reads      = n;
+        out->match_off    = r_match_off.data();
+        out->match_target = r_match_target.data();
+        out->match_count  = r_match_count.data();
+        out->read_level   = h_read_level.data();
+        out->n_hashes     = h_counts.data();
+        out->n_classified = n_classified;
+        out->n_levels     = (uint32_t)levels.size();
+        out->all_text     = r_all_p.data();
+        out->all_len      = r_all_l.data();
+        out->one_text     = r_one_p.data();
+        out->one_len      = r_one_l.data();
+        out->unc_text     = r_unc.data();
+        out->unc_len      = r_unc.size();
+        out->n_minimisers = 0;
+        for (uint32_t i = 0; i < n; ++i)
+            if (h_counts[i] <= 65535)
+                out->n_minimisers += h_counts[i];
+        out->n_kernel_launches = launches;
+    }
+    staged = ran = false;
+    return GNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+static void fill_consumed(gnb_session *s, gnb_batch_result *out)
+{
+    // bytes that formed the records taken; on a parse error the rest of the file is skipped (GC.cpp:1278-1283)
+    out->consumed1 = s->parse_error ? s->len1 : s->t1.consumed_for(s->n_reads);
+    out->consumed2 = !s->paired ? 0 : s->parse_error ? s->len2 : s->t2.consumed_for(s->n_reads);
+}
+
+extern "C" int gnb_session_stage(gnb_session *s, const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin, uint64_t *n_reads)
+{
+    if (!s || !b1)
+        return fail(GNB_ERR_ARG, "gnb_session_stage: bad arguments");
+    int rc = s->stage(b1, l1, b2, l2, fin);
+    if (rc == GNB_OK && n_reads)
+        *n_reads = s->n_reads;
+    if (rc == GNB_OK)
+        GNB_CUDA(cudaStreamSynchronize(s->st));
+    return rc;
+}
+
+extern "C" int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings)
+{
+    if (!s || !s->staged)
+        return fail(GNB_ERR_ARG, "gnb_session_run_staged: nothing staged");
+    GNB_CUDA(cudaSetDevice(s->device));
+    // allow repeated runs on the same staged batch (benchmark): reset per-run state
+    s->hashed_k = s->hashed_w = 0;
+    s->timing.ms_count = s->timing.ms_sort = 0;
+    s->timing.count_kernel_bytes = 0;
+    s->launches = 0;
+    std::fill(s->h_active.begin(), s->h_active.end(), (uint8_t)1);
+    int rc = s->run_level(0);
+    if (rc != GNB_OK)
+        return rc;
+    float ms = 0;
+    if (s->n_reads && cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess)
+        s->timing.ms_minimiser = ms;
+    s->ran = true;
+    if (timings)
+    {
+        *timings = s->timing;
+        timings->n_reads = s->n_reads;
+        timings->n_kernel_launches = s->launches;
+        timings->n_minimisers = 0;
+        for (uint32_t i = 0; i < s->n_reads; ++i)
+            if (s->h_counts[i] <= 65535)
+                timings->n_minimisers += s->h_counts[i];
+    }
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_finish_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out)
+{
+    if (!s || !s->staged)
+        return fail(GNB_ERR_ARG, "gnb_session_finish_staged: nothing staged");
+    GNB_CUDA(cudaSetDevice(s->device));
+    int rc = s->finish(prefix_id, out);
+    if (rc == GNB_OK && out)
+        fill_consumed(s, out);
+    return rc;
+}
+
+extern "C" int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin,
+                                    gnb_batch_result *out)
+{
+    if (!s || !b1 || !out)
+        return fail(GNB_ERR_ARG, "gnb_session_classify: bad arguments");
+    auto t0 = Clock::now();
+    int  rc = s->stage(b1, l1, b2, l2, fin);
+    if (rc != GNB_OK)
+        return rc;
+    rc = s->finish(prefix_id, out);
+    if (rc != GNB_OK)
+        return rc;
+    fill_consumed(s, out);
+    out->ms_total = ms_since(t0);
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_level_count(const gnb_session *s, uint32_t *n)
+{
+    if (!s || !n)
+        return fail(GNB_ERR_ARG, "null argument");
+    *n = (uint32_t)s->levels.size();
+    return GNB_OK;
+}
+extern "C" int gnb_session_level_label(const gnb_session *s, uint32_t level, const char **label)
+{
+    if (!s || !label || level >= s->levels.size())
+        return fail(GNB_ERR_ARG, "level out of range");
+    *label = s->levels[level].label.c_str();
+    return GNB_OK;
+}
+extern "C" int gnb_session_node_name(const gnb_session *s, uint32_t level, uint32_t node, const char **name)
+{
+    if (!s || !name || level >= s->levels.size() || node >= s->levels[level].node_names.size())
+        return fail(GNB_ERR_ARG, "node out of range");
+    *name = s->levels[level].node_names[node].c_str();
+    return GNB_OK;
+}
+
+static gnb_totals sum_levels(const gnb_session *s, uint32_t prefix_id)
+{
+    gnb_totals t{};
+    for (auto const &L : s->levels)
+        if (prefix_id < L.total.size())
+            add_totals(t, L.total[prefix_id]);
+    return t;
+}
+
+extern "C" int gnb_session_totals(const gnb_session *s, uint32_t prefix_id, int level, gnb_totals *out)
+{
+    if (!s || !out || level >= (int)s->levels.size())
+        return fail(GNB_ERR_ARG, "gnb_session_totals: bad arguments");
+    if (level < 0)
+        *out = sum_levels(s, prefix_id);
+    else
+    {
+        gnb_totals z{};
+        *out = prefix_id < s->levels[level].total.size() ? s->levels[level].total[prefix_id] : z;
+    }
+    return GNB_OK;
+}
+
+// write_report (GC.cpp:834-853) per level in sorted label order, then write_report_totals (GC.cpp:855-863)
+extern "C" int gnb_session_report(gnb_session *s, uint32_t prefix_id, const char **text, uint64_t *len)
+{
+    if (!s || !text || !len)
+        return fail(GNB_ERR_ARG, "null argument");
+    std::string &o = s->report_text;
+    o.clear();
+    for (auto const &L : s->levels)
+    {
+        if (prefix_id >= L.rep.size())
+            continue;
+        std::vector<uint32_t> nodes;
+        for (auto const &kv : L.rep[prefix_id])
+            nodes.push_back(kv.first);
+        std::sort(nodes.begin(), nodes.end());
+        for (uint32_t node : nodes)
+        {
+            const Rep &r = L.rep[prefix_id].at(node);
+            if (!(r.matches || r.seqs_lca || r.seqs_unique))
+                continue;
+            o += L.label;
+            o.push_back('\t');
+            o += L.node_names[node];
+            o.push_back('\t');
+            append_u64(o, r.matches);
+            o.push_back('\t');
+            append_u64(o, r.seqs_unique);
+            o.push_back('\t');
+            append_u64(o, r.seqs_lca);
+            if (L.has_tax)
+            {
+                o.push_back('\t');
+                o += L.node_rank[node];
+                o.push_back('\t');
+                o += L.node_tax_name[node];
+            }
+            o.push_back('\n');
+        }
+    }
+    const gnb_totals t = sum_levels(s, prefix_id);
+    o += "#total_classified\t";
+    append_u64(o, t.seqs_classified);
+    o += "\n#total_unclassified\t";
+    append_u64(o, t.input_seqs - t.seqs_classified);
+    o.push_back('\n');
+    *text = o.data();
+    *len  = o.size();
+    return GNB_OK;
+}
+
+// write_stats (GC.cpp:1130-1218)
+extern "C" int gnb_session_stats(gnb_session *s, uint32_t prefix_id, const char *prefix_name, const char **text, uint64_t *len)
+{
+    if (!s || !text || !len)
+        return fail(GNB_ERR_ARG, "null argument");
+    std::string &o = s->stats_text;
+    o = "prefix\thierarchy_label\tseq_processed\tseq_unclassified\tseq_classified\tseq_classified_perc\tseq_unique_matches\t"
+        "seq_unique_matches_perc\tseq_multiple_matches\tseq_multiple_matches_perc\tmatches\tavg_matches_ref_seq\tdis_matches_rel_filter\t"
+        "dis_matches_fpr_query\tkmers_proccessed\tkmers_matched\tkmers_from_classified_seqs\tkmers_matched_perc\n";
+    const gnb_totals total           = sum_levels(s, prefix_id);
+    const uint64_t   seq_unclassified = total.seqs_processed - total.seqs_classified;
+    const double     seq_processed   = total.seqs_processed > 0 ? (double)total.seqs_processed : 1;
+    const std::string pfx            = prefix_name ? prefix_name : "";
+    auto line = [&](const gnb_totals &t, const std::string &label) {
+        const uint64_t seq_multiple = t.seqs_classified - t.seqs_unique;
+        const double   avg  = t.seqs_classified ? (t.matches / (double)t.seqs_classified) : 0;
+        const double   perc = t.kmers_matches ? (t.kmers_matches / (double)t.kmers_from_classified_seqs) * 100 : 0;
+        char           buf[1024];
+        snprintf(buf, sizeof buf, "%s\t%s\t%llu\t%llu\t%llu\t%.6f\t%llu\t%.6f\t%llu\t%.6f\t%llu\t%.6f\t%llu\t%llu\t%llu\t%llu\t%llu\t%.6f\n", pfx.c_str(),
+                 label.c_str(), (unsigned long long)(size_t)seq_processed, (unsigned long long)seq_unclassified, (unsigned long long)t.seqs_classified,
+                 (t.seqs_classified / seq_processed) * 100, (unsigned long long)t.seqs_unique, (t.seqs_unique / seq_processed) * 100,
+                 (unsigned long long)seq_multiple, (seq_multiple / seq_processed) * 100, (unsigned long long)t.matches, avg,
+                 (unsigned long long)t.discarded_matches_filter, (unsigned long long)t.discarded_matches_fprquery, (unsigned long long)total.kmers_processed,
+                 (unsigned long long)t.kmers_matches, (unsigned long long)t.kmers_from_classified_seqs, perc);
+        o += buf;
+    };
+    for (auto const &L : s->levels)
+    {
+        gnb_totals z{};
+        line(prefix_id < L.total.size() ? L.total[prefix_id] : z, L.label);
+    }
+    if (s->levels.size() > 1)
+        line(total, "-total-");
+    *text = o.data();
+    *len  = o.size();
+    return GNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel test hooks
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int gnb_minimisers(int device, uint32_t k, uint32_t w, const char *seq, uint64_t len, uint64_t *out, uint64_t cap, uint64_t *n_out)
+{
+    if (!seq || !n_out || k < 1 || k > 32 || w < k || w - k + 1 > 256 || len >= (1ull << 31))
+        return fail(GNB_ERR_ARG, "gnb_minimisers: bad arguments");
+    GNB_CUDA(cudaSetDevice(device));
+    *n_out = 0;
+    if (len < k)
+        return GNB_OK;
+    // the kernel applies the classify() rule "shorter than the window -> skipped"; the view itself shrinks the window
+    // (minimiser.hpp:298-299), so clamp w for the hook
+    const uint32_t w_eff = (uint32_t)std::min<uint64_t>(w, len);
+    uint8_t  *d_seq = nullptr;
+    uint32_t *d_meta = nullptr;
+    uint64_t *d_off = nullptr, *d_h = nullptr;
+    GNB_CUDA(cudaMalloc((void **)&d_seq, len + 64));
+    GNB_CUDA(cudaMalloc((void **)&d_meta, 16));
+    GNB_CUDA(cudaMalloc((void **)&d_off, 16));
+    GNB_CUDA(cudaMalloc((void **)&d_h, (len + 1) * 8));
+    const uint32_t meta[3] = {0, (uint32_t)len, 0};
+    const uint64_t off[2]  = {0, 0};
+    cudaMemcpy(d_seq, seq, len, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_meta, meta, 12, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_off, off, 16, cudaMemcpyHostToDevice);
+    launch_minimisers(d_seq, d_meta, d_meta + 1, nullptr, nullptr, nullptr, 1, k, w_eff, false, d_meta + 2, nullptr, nullptr, 0);
+    launch_minimisers(d_seq, d_meta, d_meta + 1, nullptr, nullptr, nullptr, 1, k, w_eff, true, nullptr, d_off, d_h, 0);
+    uint32_t    n = 0;
+    cudaError_t e = cudaMemcpy(&n, d_meta + 2, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out)
+        e = cudaMemcpy(out, d_h, std::min<uint64_t>(n, cap) * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_seq);
+    cudaFree(d_meta);
+    cudaFree(d_off);
+    cudaFree(d_h);
+    GNB_CUDA(e);
+    *n_out = n;
+    return GNB_OK;
+}
+
+extern "C" int gnb_db_bulk_count(const gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint64_t *hash_off, uint64_t n_reads, uint16_t *counts)
+{
+    if (!db || ibf_index >= db->ibfs.size() || !hash_off || !counts || n_reads >= kMaxReadsPerBatch)
+        return fail(GNB_ERR_ARG, "gnb_db_bulk_count: bad arguments");
+    GNB_CUDA(cudaSetDevice(db->device));
+    const IbfHost &ibf = db->ibfs[ibf_index];
+    IbfDev         d{};
+    d.data       = ibf.d_data;
+    d.bin_size   = ibf.bin_size;
+    d.hash_shift = (uint32_t)ibf.hash_shift;
+    d.hash_funs  = (uint32_t)ibf.hash_funs;
+    d.row_words  = (uint32_t)ibf.row_words();
+    d.n_chunks   = (d.row_words + 63) / 64;
+    const uint64_t total = hash_off[n_reads];
+    uint32_t       mx    = 0;
+    for (uint64_t i = 0; i < n_reads; ++i)
+        mx = (uint32_t)std::max<uint64_t>(mx, hash_off[i + 1] - hash_off[i]);
+    if (mx > 65535)
+        return fail(GNB_ERR_LIMIT, "gnb_db_bulk_count: more than 65535 hashes in one list");
+    uint64_t *d_h = nullptr, *d_o = nullptr;
+    uint16_t *d_c = nullptr;
+    const size_t cbytes = n_reads * (size_t)d.row_words * 64 * 2;
+    GNB_CUDA(cudaMalloc((void **)&d_h, (total + 1) * 8));
+    GNB_CUDA(cudaMalloc((void **)&d_o, (n_reads + 1) * 8));
+    GNB_CUDA(cudaMalloc((void **)&d_c, cbytes + 2));
+    cudaMemcpy(d_h, hashes, total * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_o, hash_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice);
+    cudaMemset(d_c, 0, cbytes);
+    launch_ibf_count_dense(d, d_h, d_o, (uint32_t)n_reads, mx, d_c, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess)
+        e = cudaMemcpy(counts, d_c, cbytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_h);
+    cudaFree(d_o);
+    cudaFree(d_c);
+    GNB_CUDA(e);
+    return GNB_OK;
+}

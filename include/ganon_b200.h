@@ -1,0 +1,198 @@
+/*
+ * ganon_b200.h -- C ABI of libganon_b200.so: the ganon-classify hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (pirovc/ganon) has no FFI for this path: its boundary is the process boundary between the
+ * Python wrapper (src/ganon/classify.py:29-64 builds an argv, util.py:9-39 runs it) and the C++ binary
+ * `ganon-classify`, whose in-process entry is `bool GanonClassify::run(Config)` (src/ganon-classify/include/
+ * ganon-classify/GanonClassify.hpp:8; Config fields Config.hpp:22-49).  This header is what a binding for that
+ * entry would bind: plain pointers and sizes, no C++/torch types.  Each entry point names the reference code it
+ * replaces.  "GC.cpp" = src/ganon-classify/GanonClassify.cpp, "IBF.hpp" = libs/seqan3/include/seqan3/search/
+ * dream_index/interleaved_bloom_filter.hpp, "HIBF.hpp" = src/ganon-classify/include/ganon-classify/
+ * hierarchical_interleaved_bloom_filter.hpp.
+ *
+ * Conventions: every function returns 0 on success or a negative gnb_status; gnb_last_error() gives the message of
+ * the last failure on the calling thread.  Handles are opaque and owned by the library until *_free.  Buffers passed
+ * in are owned by the caller; buffers handed out in result structs are owned by the handle and stay valid until the
+ * next call on that handle.  One host thread per session at a time; different sessions are independent.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with GNB_ERR_CUDA.
+ */
+#ifndef GANON_B200_H
+#define GANON_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNB_ABI_VERSION 1
+
+typedef enum
+{
+    GNB_OK          = 0,
+    GNB_ERR_ARG     = -1, /* invalid argument                                   */
+    GNB_ERR_IO      = -2, /* file missing / unreadable / truncated              */
+    GNB_ERR_FORMAT  = -3, /* not a ganon .ibf/.hibf, or inconsistent header     */
+    GNB_ERR_CUDA    = -4, /* no device, allocation failure, kernel failure      */
+    GNB_ERR_CONFIG  = -5, /* Config::validate-style error (Config.hpp:71-245)   */
+    GNB_ERR_PARSE   = -6, /* reads file parse error (seqan3::parse_error)       */
+    GNB_ERR_LIMIT   = -7  /* batch exceeds an implementation limit              */
+} gnb_status;
+
+typedef struct gnb_db      gnb_db;      /* one database (flat IBF or HIBF) resident in HBM        */
+typedef struct gnb_session gnb_session; /* one classification run: all hierarchy levels + reports */
+
+const char *gnb_last_error(void);
+int         gnb_abi_version(void);
+int         gnb_device_count(int *n_devices);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Databases.
+ * gnb_db_open replaces load_filter(TIBF) GC.cpp:949-986 / load_filter(THIBF) GC.cpp:875-938 (cereal layouts:
+ * IBFConfig.hpp:18-40, IBF.hpp:561-571, sdsl int_vector.hpp:2029-2035, HIBF.hpp:163-169,293-298): the header is parsed
+ * by hand, the bitvector is streamed file -> pinned staging -> HBM in chunks (never a second full host copy).
+ * shard/n_shards: bin-block (column) sharding for multi-GPU; shard s keeps bin-words [s*bw/n, (s+1)*bw/n) of every
+ * row.  n_shards = 1 loads everything.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    int      is_hibf;
+    uint32_t kmer_size;
+    uint32_t window_size;
+    uint32_t hash_functions;
+    uint64_t bins;           /* user-visible bins of the (top-level) IBF                         */
+    uint64_t technical_bins; /* 64 * bin_words                                                  */
+    uint64_t bin_size_bits;  /* rows                                                            */
+    uint64_t bin_words;      /* 64-bit words per row (whole filter, before sharding)            */
+    uint64_t shard_word_begin, shard_word_end; /* columns held by this handle                   */
+    uint64_t max_hashes_bin;
+    double   max_fp;         /* IBFConfig.max_fp / HIBF fpr                                      */
+    uint64_t n_targets;
+    uint64_t n_ibfs;         /* 1 for a flat IBF                                                 */
+    uint64_t device_bytes;   /* HBM held by the bitvector(s)                                     */
+    int      device;
+} gnb_db_info_t;
+
+int  gnb_db_open(const char *path, int is_hibf, int device, int shard, int n_shards, gnb_db **out);
+int  gnb_db_info(const gnb_db *db, gnb_db_info_t *info);
+/* target i: name, per-target false-positive rate (GC.cpp:969-982 / 932) and number of technical bins */
+int  gnb_db_target(const gnb_db *db, uint64_t i, const char **name, double *fpr, uint64_t *n_bins);
+void gnb_db_free(gnb_db *db);
+
+/* Build-side helpers (the subset of ganon-build needed to make databases directly in HBM: IBF constructor
+ * IBF.hpp:222-246, emplace IBF.hpp:271-286, bin map GanonBuild.cpp:619-653).  Used by the benchmark and tests. */
+int gnb_db_create(uint64_t bins, uint64_t bin_size_bits, uint32_t hash_functions, uint32_t kmer_size,
+                  uint32_t window_size, int device, gnb_db **out);
+/* word(i) = AND of `and_terms` splitmix64 draws of (seed, i, term): bit density 2^-and_terms; padding bins cleared */
+int gnb_db_fill_random(gnb_db *db, uint64_t seed, int and_terms);
+int gnb_db_emplace(gnb_db *db, const uint64_t *hashes, const uint32_t *bins, uint64_t n); /* host arrays */
+/* bin_target[bins]: target index of every bin; target_hashes[n_targets]: hashes_count_std entries */
+int gnb_db_set_targets(gnb_db *db, uint64_t n_targets, const char *const *names, const uint32_t *bin_target,
+                       const uint64_t *target_hashes, uint64_t max_hashes_bin);
+int gnb_db_read_words(const gnb_db *db, uint64_t ibf_index, uint64_t word_offset, uint64_t n_words, uint64_t *out);
+int gnb_db_save(const gnb_db *db, const char *path); /* flat .ibf in the reference layout (save_filter GanonBuild.cpp:251-288) */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Test hooks for single kernels.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* K2: seqan3::views::minimiser_hash(ungapped{k}, window_size{w}, adjust_seed(k)) of one sequence, emitted order
+ * (minimiser_hash.hpp:76-108, minimiser.hpp:398-472, kmer_hash.hpp:618-640, adjust_seed.hpp:33-37). */
+int gnb_minimisers(int device, uint32_t k, uint32_t w, const char *seq, uint64_t len, uint64_t *out, uint64_t cap,
+                   uint64_t *n_out);
+/* K3: counting_agent::bulk_count (IBF.hpp:1027-1042) for n_reads hash lists; counts[n_reads][technical_bins] (host).
+ * ibf_index selects the sub-IBF of an HIBF (0 for flat). */
+int gnb_db_bulk_count(const gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint64_t *hash_off,
+                      uint64_t n_reads, uint16_t *counts);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Sessions: GanonClassify::run (GC.cpp:1676) minus file opening -- the caller streams read blocks in and writes
+ * the returned text out.  parse_hierarchy (GC.cpp:353-401) and Config::validate_hierarchy (Config.hpp:175-245)
+ * semantics apply to the per-filter / per-level arrays below.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    uint32_t            n_filters;        /* databases, in --ibf order                                               */
+    gnb_db *const      *dbs;              /* [n_filters]                                                             */
+    const char *const  *hierarchy_labels; /* [n_filters] or NULL (all "H1")                                          */
+    const double       *rel_cutoff;       /* [n_filters]                                                             */
+    const char *const  *tax_files;        /* [n_filters] or NULL: no taxonomy => LCA skipped (Config.hpp:168-170)    */
+    uint32_t            n_levels;         /* unique labels                                                           */
+    const double       *rel_filter;       /* [n_levels] in order of first appearance of each label                   */
+    const double       *fpr_query;        /* [n_levels] idem                                                         */
+    int                 skip_lca;
+    const char         *tax_root_node;    /* default "1"                                                             */
+    int                 output_lca, output_all, output_unclassified, output_single;
+    int                 device;
+    int                 host_threads;     /* threads for the host finishing stage (0 = hardware concurrency)         */
+    int                 n_reads_chunk;    /* --n-reads (only observable in the parse-error truncation rule); 0=400   */
+    int                 quiet;            /* suppress WARNING lines on stderr (--quiet)                              */
+} gnb_session_config;
+
+typedef struct
+{
+    /* input accounting */
+    uint64_t n_reads;              /* records (pairs) taken from the blocks                                        */
+    uint64_t consumed1, consumed2; /* bytes of block1/block2 that formed complete records                           */
+    int      parse_error;          /* !=0: a record was malformed; reads before it (n-reads rule) were classified   */
+    /* structured result (CSR over reads, final matches after cutoff, rel-filter and fpr-query) */
+    const uint64_t *match_off;    /* [n_reads+1]                                                                    */
+    const uint32_t *match_target; /* index into gnb_session_node_name() of the level the read was classified at     */
+    const uint32_t *match_count;
+    const uint8_t  *read_level;   /* [n_reads] index of the level that classified the read, 0xFF = unclassified     */
+    const uint32_t *n_hashes;     /* [n_reads] minimisers of the read (pair); 0 = skipped (shorter than window)     */
+    uint64_t        n_classified;
+    /* text, in the reference's output-file formats (GC.cpp:1289-1322) */
+    uint32_t           n_levels;
+    const char *const *all_text; /* [n_levels] `.all` lines  readid \t target \t count                              */
+    const uint64_t    *all_len;
+    const char *const *one_text; /* [n_levels] `.one` lines                                                         */
+    const uint64_t    *one_len;
+    const char        *unc_text; /* `.unc` lines                                                                    */
+    uint64_t           unc_len;
+    /* device timings of this batch (CUDA events on the session stream), milliseconds */
+    float ms_h2d, ms_index, ms_minimiser, ms_count, ms_sort, ms_d2h;
+    double ms_host_index, ms_host_finish, ms_total;
+    uint64_t n_minimisers;       /* sum of n_hashes over processed reads                                            */
+    uint64_t count_kernel_bytes; /* algorithmic bytes of the IBF-count launches: sum n_hashes * h * bin_words * 8   */
+    uint64_t n_kernel_launches;  /* kernels of this library launched for the batch                                  */
+} gnb_batch_result;
+
+int  gnb_session_create(const gnb_session_config *cfg, gnb_session **out);
+void gnb_session_free(gnb_session *s);
+
+/* Classify one block of reads end to end (classify<TFilter>() GC.cpp:630-832 for every hierarchy level, plus the
+ * reader GC.cpp:1220-1287 for the block).  block1/block2: raw FASTQ or FASTA text in HOST memory (block2 NULL for
+ * single-end); the library takes as many complete records as both blocks hold (final != 0: the blocks end the file,
+ * a missing trailing newline is tolerated).  prefix_id selects the accounting scope (--batch-reads prefixes). */
+int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const char *block1, uint64_t len1, const char *block2,
+                         uint64_t len2, int final, gnb_batch_result *out);
+
+/* Split form of the same call for timing with inputs resident in HBM: stage = index + copy to the device,
+ * run = kernels only (K1/K2/K3/sort) on the staged batch, finish = device->host + host finishing stage. */
+int gnb_session_stage(gnb_session *s, const char *block1, uint64_t len1, const char *block2, uint64_t len2, int final,
+                      uint64_t *n_reads);
+int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings);
+int gnb_session_finish_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out);
+
+/* Node (target / taxonomy node) names of a level, as used by match_target. */
+int gnb_session_level_count(const gnb_session *s, uint32_t *n_levels);
+int gnb_session_level_label(const gnb_session *s, uint32_t level, const char **label);
+int gnb_session_node_name(const gnb_session *s, uint32_t level, uint32_t node, const char **name);
+
+/* Reports accumulated so far for one prefix: `.rep` (write_report GC.cpp:834-853 + write_report_totals 855-863) and
+ * `.sta` (write_stats GC.cpp:1167-1218).  The text is owned by the session. */
+int gnb_session_report(gnb_session *s, uint32_t prefix_id, const char **text, uint64_t *len);
+int gnb_session_stats(gnb_session *s, uint32_t prefix_id, const char *prefix_name, const char **text, uint64_t *len);
+
+typedef struct
+{
+    uint64_t input_seqs, seqs_processed, seqs_skipped_big, seqs_skipped_small, length_processed, kmers_processed,
+        seqs_classified, kmers_matches, kmers_from_classified_seqs, matches, seqs_unique, discarded_matches_filter,
+        discarded_matches_fprquery;
+} gnb_totals; /* struct Total GC.cpp:162-177 */
+int gnb_session_totals(const gnb_session *s, uint32_t prefix_id, int level /* -1 = all */, gnb_totals *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANON_B200_H */
