@@ -64,6 +64,7 @@ class SessionConfig(C.Structure):
         ("host_threads", C.c_int),
         ("n_reads_chunk", C.c_int),
         ("quiet", C.c_int),
+        ("cuda_stream", C.c_void_p),
     ]
 
 
@@ -98,6 +99,8 @@ class BatchResult(C.Structure):
         ("n_minimisers", C.c_uint64),
         ("count_kernel_bytes", C.c_uint64),
         ("n_kernel_launches", C.c_uint64),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
     ]
 
 
@@ -122,6 +125,7 @@ SYMBOLS = {
     "gnb_db_read_words": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "gnb_db_save": (C.c_int, [_P, C.c_char_p]),
     "gnb_minimisers": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "gnb_minimisers_batch": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64, _P, _P, C.c_uint64]),
     "gnb_db_bulk_count": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64, _P]),
     "gnb_session_create": (C.c_int, [C.POINTER(SessionConfig), C.POINTER(_P)]),
     "gnb_session_free": (None, [_P]),

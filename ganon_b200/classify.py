@@ -123,6 +123,21 @@ class Database:
             pass
 
 
+def minimisers_batch(seqs: Sequence[bytes], k: int, w: int, device: int = 0):
+    """Minimiser hashes of many sequences (reads shorter than w give none): (hash_off uint64[n+1], hashes uint64[])."""
+    import numpy as np
+
+    blob = b"".join(seqs)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(x) for x in seqs])
+    hoff = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    L = _lib.lib()
+    check(L.gnb_minimisers_batch(device, k, w, blob, off.ctypes.data, len(seqs), hoff.ctypes.data, None, 0))
+    hashes = np.empty(int(hoff[-1]) + 1, dtype=np.uint64)
+    check(L.gnb_minimisers_batch(device, k, w, blob, off.ctypes.data, len(seqs), hoff.ctypes.data, hashes.ctypes.data, hashes.size))
+    return hoff, hashes[: int(hoff[-1])]
+
+
 def minimisers(seq: bytes, k: int, w: int, device: int = 0):
     """seqan3::views::minimiser_hash of one sequence on the GPU (test hook for kernel K2)."""
     import numpy as np
@@ -156,6 +171,7 @@ class Session:
         host_threads: int = 0,
         n_reads: int = 400,
         quiet: bool = True,
+        cuda_stream: int = 0,
     ):
         n = len(dbs)
         labels = list(hierarchy_labels) if hierarchy_labels else ["H1"] * n
@@ -189,6 +205,7 @@ class Session:
             host_threads,
             n_reads,
             int(quiet),
+            C.c_void_p(cuda_stream) if cuda_stream else None,
         )
         h = C.c_void_p()
         check(_lib.lib().gnb_session_create(C.byref(cfg), C.byref(h)))

@@ -237,6 +237,7 @@ struct gnb_session
     uint32_t           n_reads_chunk = 400;
     std::vector<LevelRt> levels;
     cudaStream_t       st = nullptr;
+    bool               own_stream = true;
     cudaEvent_t        ev[12]{};
     int                n_threads = 1;
     std::vector<Worker> workers;
@@ -291,7 +292,7 @@ struct gnb_session
         for (auto &e : ev)
             if (e)
                 cudaEventDestroy(e);
-        if (st)
+        if (st && own_stream)
             cudaStreamDestroy(st);
     }
 
@@ -582,7 +583,13 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
             return rc;
     }
 
-    GNB_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    if (cfg->cuda_stream)
+    {
+        s->st         = (cudaStream_t)cfg->cuda_stream;
+        s->own_stream = false;
+    }
+    else
+        GNB_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     for (auto &e : s->ev)
         GNB_CUDA(cudaEventCreate(&e));
     s->n_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
@@ -672,6 +679,7 @@ int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2,
     hashed_k = hashed_w = 0;
     GNB_CUDA(cudaEventRecord(ev[0], st));
     const uint64_t bytes1 = len1 + t1.aux.size(), bytes2 = paired ? len2 + t2.aux.size() : 0;
+    timing.h2d_bytes = bytes1 + bytes2 + (uint64_t)n * 8 * (paired ? 2 : 1);
     GNB_TRY(d_blk1.ensure(bytes1 + 64));
     GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
     if (!t1.aux.empty())
@@ -734,6 +742,7 @@ int gnb_session::compute_hashes(uint32_t k, uint32_t w)
     GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaStreamSynchronize(st));
     total_hashes = total;
+    timing.d2h_bytes += 8 + (uint64_t)n * 4;
     GNB_TRY(d_hashes.ensure((total + 1) * 8));
     launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
                       true, nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), st);
@@ -761,6 +770,7 @@ int gnb_session::run_level(size_t li)
     if (li > 0 && n)
     {
         GNB_CUDA(cudaMemcpyAsync(d_active.p, h_active.data(), n, cudaMemcpyHostToDevice, st));
+        timing.h2d_bytes += n;
         act = d_active.as<uint8_t>();
     }
     uint64_t active_hashes = 0;
@@ -788,6 +798,7 @@ int gnb_session::run_level(size_t li)
                              d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            timing.d2h_bytes += 8;
             GNB_CUDA(cudaStreamSynchronize(st));
             GNB_CUDA(cudaGetLastError());
             if (produced <= cap)
@@ -805,6 +816,7 @@ int gnb_session::run_level(size_t li)
         launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
         GNB_CUDA(cudaEventRecord(ev[7], st));
         F.tuples.resize(produced);
+        timing.d2h_bytes += produced * 8;
         GNB_CUDA(cudaMemcpyAsync(F.tuples.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
         GNB_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
@@ -1218,6 +1230,7 @@ extern "C" int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings)
     s->hashed_k = s->hashed_w = 0;
     s->timing.ms_count = s->timing.ms_sort = 0;
     s->timing.count_kernel_bytes = 0;
+    s->timing.d2h_bytes = 0;
     s->launches = 0;
     std::fill(s->h_active.begin(), s->h_active.end(), (uint8_t)1);
     int rc = s->run_level(0);
@@ -1404,41 +1417,74 @@ extern "C" int gnb_session_stats(gnb_session *s, uint32_t prefix_id, const char 
 // ---------------------------------------------------------------------------------------------------------------------
 // kernel test hooks
 // ---------------------------------------------------------------------------------------------------------------------
+extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const char *seqs, const uint64_t *seq_off, uint64_t n, uint64_t *hash_off,
+                                    uint64_t *hashes, uint64_t cap)
+{
+    if (!seqs || !seq_off || !hash_off || k < 1 || k > 32 || w < k || w - k + 1 > 256 || n >= kMaxReadsPerBatch || seq_off[n] >= (1ull << 32))
+        return fail(GNB_ERR_ARG, "gnb_minimisers_batch: bad arguments");
+    GNB_CUDA(cudaSetDevice(device));
+    hash_off[0] = 0;
+    if (n == 0)
+        return GNB_OK;
+    std::vector<uint32_t> off(n), len(n);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        off[i] = (uint32_t)seq_off[i];
+        len[i] = (uint32_t)(seq_off[i + 1] - seq_off[i]);
+    }
+    DevBuf d_seq, d_off, d_len, d_cnt, d_hoff, d_h, d_tmp;
+    auto   cleanup = [&]() {
+        for (DevBuf *b : {&d_seq, &d_off, &d_len, &d_cnt, &d_hoff, &d_h, &d_tmp})
+            b->release();
+    };
+    int rc = GNB_OK;
+    auto body = [&]() -> int {
+        GNB_TRY(d_seq.ensure(seq_off[n] + 64));
+        GNB_TRY(d_off.ensure(n * 4));
+        GNB_TRY(d_len.ensure(n * 4));
+        GNB_TRY(d_cnt.ensure(n * 4));
+        GNB_TRY(d_hoff.ensure((n + 1) * 8));
+        GNB_TRY(d_tmp.ensure(scan_tmp_bytes((uint32_t)n)));
+        GNB_CUDA(cudaMemcpy(d_seq.p, seqs, seq_off[n], cudaMemcpyHostToDevice));
+        GNB_CUDA(cudaMemcpy(d_off.p, off.data(), n * 4, cudaMemcpyHostToDevice));
+        GNB_CUDA(cudaMemcpy(d_len.p, len.data(), n * 4, cudaMemcpyHostToDevice));
+        launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, false,
+                          d_cnt.as<uint32_t>(), nullptr, nullptr, 0);
+        launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
+        GNB_CUDA(cudaMemcpy(hash_off, d_hoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
+        const uint64_t total = hash_off[n];
+        if (hashes && total <= cap && total > 0)
+        {
+            GNB_TRY(d_h.ensure(total * 8));
+            launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, true, nullptr,
+                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), 0);
+            GNB_CUDA(cudaMemcpy(hashes, d_h.p, total * 8, cudaMemcpyDeviceToHost));
+        }
+        GNB_CUDA(cudaGetLastError());
+        return GNB_OK;
+    };
+    rc = body();
+    cleanup();
+    return rc;
+}
+
 extern "C" int gnb_minimisers(int device, uint32_t k, uint32_t w, const char *seq, uint64_t len, uint64_t *out, uint64_t cap, uint64_t *n_out)
 {
-    if (!seq || !n_out || k < 1 || k > 32 || w < k || w - k + 1 > 256 || len >= (1ull << 31))
+    if (!seq || !n_out || k < 1 || k > 32 || w < k || len >= (1ull << 31))
         return fail(GNB_ERR_ARG, "gnb_minimisers: bad arguments");
-    GNB_CUDA(cudaSetDevice(device));
     *n_out = 0;
-    if (len < k)
-        return GNB_OK;
-    // the kernel applies the classify() rule "shorter than the window -> skipped"; the view itself shrinks the window
-    // (minimiser.hpp:298-299), so clamp w for the hook
-    const uint32_t w_eff = (uint32_t)std::min<uint64_t>(w, len);
-    uint8_t  *d_seq = nullptr;
-    uint32_t *d_meta = nullptr;
-    uint64_t *d_off = nullptr, *d_h = nullptr;
-    GNB_CUDA(cudaMalloc((void **)&d_seq, len + 64));
-    GNB_CUDA(cudaMalloc((void **)&d_meta, 16));
-    GNB_CUDA(cudaMalloc((void **)&d_off, 16));
-    GNB_CUDA(cudaMalloc((void **)&d_h, (len + 1) * 8));
-    const uint32_t meta[3] = {0, (uint32_t)len, 0};
-    const uint64_t off[2]  = {0, 0};
-    cudaMemcpy(d_seq, seq, len, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_meta, meta, 12, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_off, off, 16, cudaMemcpyHostToDevice);
-    launch_minimisers(d_seq, d_meta, d_meta + 1, nullptr, nullptr, nullptr, 1, k, w_eff, false, d_meta + 2, nullptr, nullptr, 0);
-    launch_minimisers(d_seq, d_meta, d_meta + 1, nullptr, nullptr, nullptr, 1, k, w_eff, true, nullptr, d_off, d_h, 0);
-    uint32_t    n = 0;
-    cudaError_t e = cudaMemcpy(&n, d_meta + 2, 4, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && out)
-        e = cudaMemcpy(out, d_h, std::min<uint64_t>(n, cap) * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_seq);
-    cudaFree(d_meta);
-    cudaFree(d_off);
-    cudaFree(d_h);
-    GNB_CUDA(e);
-    *n_out = n;
+    // the kernel applies the classify() rule "shorter than the window -> skipped" (GC.cpp:690); the view itself shrinks
+    // the window (minimiser.hpp:298-299), so clamp w for the hook
+    const uint32_t w_eff = (uint32_t)std::min<uint64_t>(w, std::max<uint64_t>(len, k));
+    const uint64_t so[2] = {0, len};
+    uint64_t       ho[2] = {0, 0};
+    std::vector<uint64_t> tmp(len + 1);
+    int rc = gnb_minimisers_batch(device, k, w_eff, seq, so, 1, ho, tmp.data(), tmp.size());
+    if (rc != GNB_OK)
+        return rc;
+    *n_out = ho[1];
+    if (out)
+        memcpy(out, tmp.data(), std::min<uint64_t>(ho[1], cap) * 8);
     return GNB_OK;
 }
 

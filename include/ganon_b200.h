@@ -99,6 +99,10 @@ int gnb_db_save(const gnb_db *db, const char *path); /* flat .ibf in the referen
  * (minimiser_hash.hpp:76-108, minimiser.hpp:398-472, kmer_hash.hpp:618-640, adjust_seed.hpp:33-37). */
 int gnb_minimisers(int device, uint32_t k, uint32_t w, const char *seq, uint64_t len, uint64_t *out, uint64_t cap,
                    uint64_t *n_out);
+/* K2 over many sequences: seqs = concatenated text, seq_off[n+1]; hash_off[n+1] is always filled, hashes only if the
+ * total fits in cap (call once with cap = 0 to size the buffer). */
+int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const char *seqs, const uint64_t *seq_off, uint64_t n,
+                         uint64_t *hash_off, uint64_t *hashes, uint64_t cap);
 /* K3: counting_agent::bulk_count (IBF.hpp:1027-1042) for n_reads hash lists; counts[n_reads][technical_bins] (host).
  * ibf_index selects the sub-IBF of an HIBF (0 for flat). */
 int gnb_db_bulk_count(const gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint64_t *hash_off,
@@ -126,6 +130,7 @@ typedef struct
     int                 host_threads;     /* threads for the host finishing stage (0 = hardware concurrency)         */
     int                 n_reads_chunk;    /* --n-reads (only observable in the parse-error truncation rule); 0=400   */
     int                 quiet;            /* suppress WARNING lines on stderr (--quiet)                              */
+    void               *cuda_stream;      /* cudaStream_t to run on (e.g. a framework's stream); NULL = own stream   */
 } gnb_session_config;
 
 typedef struct
@@ -155,6 +160,7 @@ typedef struct
     uint64_t n_minimisers;       /* sum of n_hashes over processed reads                                            */
     uint64_t count_kernel_bytes; /* algorithmic bytes of the IBF-count launches: sum n_hashes * h * bin_words * 8   */
     uint64_t n_kernel_launches;  /* kernels of this library launched for the batch                                  */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host for the batch                        */
 } gnb_batch_result;
 
 int  gnb_session_create(const gnb_session_config *cfg, gnb_session **out);
