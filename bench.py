@@ -356,7 +356,7 @@ def main():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_ibf_count launch from the committed ncu capture (profiles/)
-TRAFFIC_BYTES_PER_LAUNCH = {}
+TRAFFIC_BYTES_PER_LAUNCH = {"c2": 75373784000 + 10292992}  # profiles/r01_k3_ncu_summary.md (2^21 reads per launch)
 
 
 def cpu_baseline(args, wl, db, block, host_block, sess, result_text):

@@ -140,8 +140,8 @@ struct FastqIndexOut
     uint32_t *status;                              // [4]: unused, n_malformed_records, first_bad_record, n_bad_alphabet_records
 };
 size_t fastq_index_tmp_bytes(uint64_t n_bytes);
-void   launch_fastq_lines(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, uint32_t *n_lines_dev, void *tmp,
-                          size_t tmp_bytes, cudaStream_t st);
+void   launch_fastq_count(const uint8_t *blk, uint64_t n_bytes, uint32_t *n_lines_dev, void *tmp, size_t tmp_bytes, cudaStream_t st);
+void   launch_fastq_line_starts(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, void *tmp, cudaStream_t st);
 void   launch_fastq_records(const uint8_t *blk, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st);
 
 // error plumbing

@@ -796,27 +796,32 @@ size_t fastq_index_tmp_bytes(uint64_t n_bytes)
     return 2 * (tiles + 64) * sizeof(uint32_t) + scan + 512;
 }
 
-// Phase 1: line_start[0..n_lines] (capped at cap_lines entries); *n_lines_dev = number of newlines in the block.
-void launch_fastq_lines(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, uint32_t *n_lines_dev, void *tmp,
-                        size_t tmp_bytes, cudaStream_t st)
+// Phase 1a: count the newlines of the block; *n_lines_dev = total.  tmp keeps the per-tile bases for phase 1b.
+void launch_fastq_count(const uint8_t *blk, uint64_t n_bytes, uint32_t *n_lines_dev, void *tmp, size_t tmp_bytes, cudaStream_t st)
 {
     const uint32_t tiles = (uint32_t)((n_bytes + K1_TILE - 1) / K1_TILE);
     uint32_t *tile_counts = reinterpret_cast<uint32_t *>(tmp);
     uint32_t *tile_base   = tile_counts + (tiles + 64);
     char     *scan_tmp    = reinterpret_cast<char *>(tile_base + (tiles + 64));
-    size_t    scan_bytes  = tmp_bytes - 2 * (size_t)(tiles + 64) * sizeof(uint32_t);
-    scan_bytes &= ~(size_t)255;
+    uintptr_t a           = ((uintptr_t)scan_tmp + 255) & ~(uintptr_t)255;
+    size_t    scan_bytes  = tmp_bytes - (size_t)(a - (uintptr_t)tmp);
     cudaMemsetAsync(tile_counts + tiles, 0, sizeof(uint32_t), st);
     if (tiles)
         k_count_newlines<<<tiles, K1_THREADS, 0, st>>>(blk, n_bytes, tile_counts);
-    // align the scan scratch
-    uintptr_t a = ((uintptr_t)scan_tmp + 255) & ~(uintptr_t)255;
     cub::DeviceScan::ExclusiveSum((void *)a, scan_bytes, tile_counts, tile_base, (int)(tiles + 1), st);
+    cudaMemcpyAsync(n_lines_dev, tile_base + tiles, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+}
+
+// Phase 1b: line_start[0..min(n_lines, cap_lines-1)] from the tile bases left in tmp by phase 1a.
+void launch_fastq_line_starts(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, void *tmp, cudaStream_t st)
+{
+    const uint32_t tiles = (uint32_t)((n_bytes + K1_TILE - 1) / K1_TILE);
+    uint32_t *tile_counts = reinterpret_cast<uint32_t *>(tmp);
+    uint32_t *tile_base   = tile_counts + (tiles + 64);
     if (tiles)
         k_line_starts<<<tiles, K1_THREADS, 0, st>>>(blk, n_bytes, tile_base, line_start, cap_lines);
     else
         cudaMemsetAsync(line_start, 0, sizeof(uint32_t), st);
-    cudaMemcpyAsync(n_lines_dev, tile_base + tiles, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
 }
 
 // Phase 2: record spans + marker / length / alphabet validation.  out.status must be {0, 0, 0xffffffff, 0} on entry.

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -253,10 +254,12 @@ struct gnb_session
     bool        staged = false, ran = false;
     uint32_t    hashed_k = 0, hashed_w = 0; // (k, w) the device hash list was computed for
     uint32_t    max_hashes_ub = 0;
-    bool        device_index = true; // try K1 first
+    bool        use_device_index = true; // K1 first, host reader when the block is not strict 4-line FASTQ
+    const uint32_t *p_idoff = nullptr, *p_idlen = nullptr, *p_slen1 = nullptr, *p_slen2 = nullptr;
+    uint64_t    consumed1 = 0, consumed2 = 0;
 
     DevBuf d_blk1, d_blk2, d_off1, d_len1, d_off2, d_len2, d_idoff, d_idlen, d_counts, d_hash_off, d_hashes, d_active, d_tuples_a, d_tuples_b,
-        d_cursor, d_tmp, d_lines, d_status;
+        d_cursor, d_tmp, d_lines1, d_lines2, d_k1tmp1, d_k1tmp2, d_idoff2, d_idlen2, d_status;
     PinBuf h_pin;
     std::vector<uint32_t> h_counts;
     std::vector<uint8_t>  h_active;
@@ -286,7 +289,7 @@ struct gnb_session
                 f.d_segs.release();
             }
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
-                          &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines, &d_status})
+                          &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status})
             b->release();
         h_pin.release();
         for (auto &e : ev)
@@ -298,6 +301,7 @@ struct gnb_session
 
     int  build_level_tables(LevelRt &L);
     int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
+    int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines);
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
     int  finish_level(size_t li, uint32_t prefix_id);
@@ -413,6 +417,8 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
     s->tax_root = cfg->tax_root_node ? cfg->tax_root_node : "1";
     s->skip_lca = cfg->skip_lca != 0 || cfg->tax_files == nullptr; // Config.hpp:168-170
     s->n_reads_chunk = cfg->n_reads_chunk > 0 ? (uint32_t)cfg->n_reads_chunk : 400u;
+    if (const char *e = getenv("GANON_B200_HOST_INDEX"))
+        s->use_device_index = !(e[0] == '1'); // debugging aid: force the host record reader
     GNB_CUDA(cudaSetDevice(s->device));
 
     // ---- parse_hierarchy: levels in sorted label order; rel_filter / fpr_query by first appearance ----
@@ -623,8 +629,32 @@ void gnb_session::ensure_prefix(uint32_t prefix_id)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// stage: index the block(s) and copy them to the device
+// stage: copy the block(s) to the device and index the records -- on the device (K1) for strict 4-line FASTQ, on the
+// host (reads.cpp: FASTA, wrapped FASTQ, blanks, and the exact parse-error behaviour) for everything else
 // ---------------------------------------------------------------------------------------------------------------------
+int gnb_session::device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines)
+{
+    DevBuf        &blk   = side == 0 ? d_blk1 : d_blk2;
+    DevBuf        &lines = side == 0 ? d_lines1 : d_lines2;
+    const uint64_t n     = len;
+    const size_t   tb    = fastq_index_tmp_bytes(n);
+    DevBuf        &tmp   = side == 0 ? d_k1tmp1 : d_k1tmp2;
+    GNB_TRY(tmp.ensure(tb));
+    launch_fastq_count(blk.as<uint8_t>(), n, d_status.as<uint32_t>() + 8 + side, tmp.p, tmp.cap, st);
+    launches += 1;
+    uint32_t nl = 0;
+    GNB_CUDA(cudaMemcpyAsync(&nl, d_status.as<uint32_t>() + 8 + side, 4, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    (void)fin;
+    n_lines   = nl;
+    n_records = std::min<uint32_t>(nl / 4, kMaxReadsPerBatch - 1);
+    const uint32_t cap_lines = 4 * n_records + 1;
+    GNB_TRY(lines.ensure((size_t)cap_lines * 4 + 16));
+    launch_fastq_line_starts(blk.as<uint8_t>(), n, lines.as<uint32_t>(), cap_lines, tmp.p, st);
+    launches += 1;
+    return GNB_OK;
+}
+
 int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin)
 {
     GNB_CUDA(cudaSetDevice(device));
@@ -638,74 +668,178 @@ int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2,
     parse_error = false;
     if (l1 >= (1ull << 31) || len2 >= (1ull << 31))
         return fail(GNB_ERR_LIMIT, "read blocks are limited to 2 GiB");
-    timing = gnb_batch_result{};
+    timing   = gnb_batch_result{};
     launches = 0;
-    auto t0 = Clock::now();
-    index_reads_host(b1, l1, final_block, kMaxReadsPerBatch - 1, t1);
+    hashed_k = hashed_w = 0;
+    max_hashes_ub = 0;
+
+    // ---- blocks -> device (one extra byte so that a final block without trailing newline can be terminated) ----
+    GNB_CUDA(cudaEventRecord(ev[0], st));
+    GNB_TRY(d_blk1.ensure(len1 + 64));
+    if (len1)
+        GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
     if (paired)
-        index_reads_host(b2, len2, final_block, kMaxReadsPerBatch - 1, t2);
-    size_t n = t1.size();
-    if (paired)
-        n = std::min(n, t2.size());
-    // A parse error ends the file; the reference loses the chunk of --n-reads records being assembled (GC.cpp:1240-1283)
-    bool   err = false;
-    size_t err_rec = n;
-    if (t1.parse_error && t1.error_record <= n)
-        err = true, err_rec = std::min(err_rec, (size_t)t1.error_record);
-    if (paired && t2.parse_error && t2.error_record <= n)
-        err = true, err_rec = std::min(err_rec, (size_t)t2.error_record);
-    if (err)
     {
-        const uint64_t abs_rec = file_records + err_rec;
-        const uint64_t keep_abs = abs_rec / n_reads_chunk * n_reads_chunk;
-        n = keep_abs > file_records ? (size_t)(keep_abs - file_records) : 0;
-        parse_error = true;
-        if (!quiet)
-            fprintf(stderr, "Error parsing file(s): %s\n", (t1.parse_error ? t1.error_msg : t2.error_msg).c_str());
+        GNB_TRY(d_blk2.ensure(len2 + 64));
+        if (len2)
+            GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st));
     }
-    t1.truncate(n);
-    if (paired)
-        t2.truncate(n);
-    n_reads = (uint32_t)n;
+    GNB_CUDA(cudaEventRecord(ev[1], st));
+    timing.h2d_bytes = len1 + len2;
+
+    size_t n = 0;
+    bool   on_device = use_device_index && len1 > 0 && b1[0] == '@' && (!paired || (len2 > 0 && b2[0] == '@'));
+    if (on_device)
+    {
+        GNB_CUDA(cudaEventRecord(ev[8], st));
+        uint64_t e1 = len1, e2 = len2;
+        if (final_block && b1[len1 - 1] != '\n')
+        {
+            GNB_CUDA(cudaMemsetAsync(d_blk1.as<uint8_t>() + len1, '\n', 1, st));
+            e1 = len1 + 1;
+        }
+        if (paired && final_block && b2[len2 - 1] != '\n')
+        {
+            GNB_CUDA(cudaMemsetAsync(d_blk2.as<uint8_t>() + len2, '\n', 1, st));
+            e2 = len2 + 1;
+        }
+        uint32_t n1 = 0, n2 = 0, nl1 = 0, nl2 = 0;
+        GNB_TRY(device_index(0, e1, final_block, n1, nl1));
+        if (paired)
+            GNB_TRY(device_index(1, e2, final_block, n2, nl2));
+        n = paired ? std::min(n1, n2) : n1;
+        const uint32_t init_status[4] = {0, 0, 0xffffffffu, 0};
+        GNB_CUDA(cudaMemcpyAsync(d_status.p, init_status, 16, cudaMemcpyHostToDevice, st));
+        GNB_TRY(d_off1.ensure(n * 4 + 4));
+        GNB_TRY(d_len1.ensure(n * 4 + 4));
+        GNB_TRY(d_idoff.ensure(n * 4 + 4));
+        GNB_TRY(d_idlen.ensure(n * 4 + 4));
+        FastqIndexOut o1{d_idoff.as<uint32_t>(), d_idlen.as<uint32_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), d_status.as<uint32_t>()};
+        launch_fastq_records(d_blk1.as<uint8_t>(), d_lines1.as<uint32_t>(), (uint32_t)n, o1, st);
+        launches += 2;
+        if (paired)
+        {
+            GNB_TRY(d_off2.ensure(n * 4 + 4));
+            GNB_TRY(d_len2.ensure(n * 4 + 4));
+            GNB_TRY(d_idoff2.ensure(n * 4 + 4));
+            GNB_TRY(d_idlen2.ensure(n * 4 + 4));
+            FastqIndexOut o2{d_idoff2.as<uint32_t>(), d_idlen2.as<uint32_t>(), d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), d_status.as<uint32_t>()};
+            launch_fastq_records(d_blk2.as<uint8_t>(), d_lines2.as<uint32_t>(), (uint32_t)n, o2, st);
+            launches += 2;
+        }
+        GNB_CUDA(cudaEventRecord(ev[9], st));
+        // record table -> pinned host memory (needed by the finishing stage only)
+        GNB_TRY(h_pin.ensure(((size_t)n * 4 + 8) * 4 + 64));
+        uint32_t *hp = h_pin.as<uint32_t>();
+        uint32_t *h_status = hp, *h_cons = hp + 4;
+        p_idoff = hp + 8;
+        p_idlen = p_idoff + n;
+        p_slen1 = p_idlen + n;
+        p_slen2 = p_slen1 + n;
+        GNB_CUDA(cudaMemcpyAsync(h_status, d_status.p, 16, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync(h_cons, d_lines1.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st));
+        if (paired)
+            GNB_CUDA(cudaMemcpyAsync(h_cons + 1, d_lines2.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st));
+        if (n)
+        {
+            GNB_CUDA(cudaMemcpyAsync((void *)p_idoff, d_idoff.p, n * 4, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync((void *)p_idlen, d_idlen.p, n * 4, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync((void *)p_slen1, d_len1.p, n * 4, cudaMemcpyDeviceToHost, st));
+            if (paired)
+                GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(cudaGetLastError());
+        timing.d2h_bytes += 24 + (uint64_t)n * 4 * (paired ? 4 : 3);
+        consumed1 = h_cons[0];
+        consumed2 = paired ? h_cons[1] : 0;
+        // anything irregular -> the host reader decides (wrapped records, blanks, bad letters, trailing garbage)
+        const bool irregular = h_status[1] != 0 || h_status[3] != 0 || (final_block && (consumed1 != e1 || (paired && consumed2 != e2))) ||
+                               (final_block && paired && n1 != n2);
+        if (irregular)
+            on_device = false;
+        else
+        {
+            consumed1 = std::min<uint64_t>(consumed1, len1);
+            consumed2 = std::min<uint64_t>(consumed2, len2);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[8], ev[9]);
+            timing.ms_index = ms;
+        }
+    }
+    if (!on_device)
+    {
+        auto t0 = Clock::now();
+        index_reads_host(b1, l1, final_block, kMaxReadsPerBatch - 1, t1);
+        if (paired)
+            index_reads_host(b2, len2, final_block, kMaxReadsPerBatch - 1, t2);
+        n = t1.size();
+        if (paired)
+            n = std::min(n, t2.size());
+        // A parse error ends the file; the reference loses the chunk of --n-reads records being assembled (GC.cpp:1240-1283)
+        bool   err = false;
+        size_t err_rec = n;
+        if (t1.parse_error && t1.error_record <= n)
+            err = true, err_rec = std::min(err_rec, (size_t)t1.error_record);
+        if (paired && t2.parse_error && t2.error_record <= n)
+            err = true, err_rec = std::min(err_rec, (size_t)t2.error_record);
+        if (err)
+        {
+            const uint64_t abs_rec  = file_records + err_rec;
+            const uint64_t keep_abs = abs_rec / n_reads_chunk * n_reads_chunk;
+            n = keep_abs > file_records ? (size_t)(keep_abs - file_records) : 0;
+            parse_error = true;
+            if (!quiet)
+                fprintf(stderr, "Error parsing file(s): %s\n", (t1.parse_error ? t1.error_msg : t2.error_msg).c_str());
+        }
+        t1.truncate(n);
+        if (paired)
+            t2.truncate(n);
+        consumed1 = t1.consumed_for(n);
+        consumed2 = paired ? t2.consumed_for(n) : 0;
+        p_idoff = t1.id_off.data();
+        p_idlen = t1.id_len.data();
+        p_slen1 = t1.seq_len.data();
+        p_slen2 = paired ? t2.seq_len.data() : nullptr;
+        timing.ms_host_index = ms_since(t0);
+        GNB_TRY(d_blk1.ensure(len1 + t1.aux.size() + 64)); // contents are kept when the buffer is already large enough
+        if (!t1.aux.empty())
+        {
+            // ensure() may have reallocated: re-send the block
+            GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_blk1.as<uint8_t>() + len1, t1.aux.data(), t1.aux.size(), cudaMemcpyHostToDevice, st));
+        }
+        GNB_TRY(d_off1.ensure(n * 4 + 4));
+        GNB_TRY(d_len1.ensure(n * 4 + 4));
+        if (n)
+        {
+            GNB_CUDA(cudaMemcpyAsync(d_off1.p, t1.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_len1.p, t1.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+        }
+        if (paired)
+        {
+            GNB_TRY(d_blk2.ensure(len2 + t2.aux.size() + 64));
+            if (!t2.aux.empty())
+            {
+                GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st));
+                GNB_CUDA(cudaMemcpyAsync(d_blk2.as<uint8_t>() + len2, t2.aux.data(), t2.aux.size(), cudaMemcpyHostToDevice, st));
+            }
+            GNB_TRY(d_off2.ensure(n * 4 + 4));
+            GNB_TRY(d_len2.ensure(n * 4 + 4));
+            if (n)
+            {
+                GNB_CUDA(cudaMemcpyAsync(d_off2.p, t2.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
+                GNB_CUDA(cudaMemcpyAsync(d_len2.p, t2.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+            }
+        }
+        timing.h2d_bytes += t1.aux.size() + (paired ? t2.aux.size() : 0) + (uint64_t)n * 8 * (paired ? 2 : 1);
+    }
+    n_reads            = (uint32_t)n;
     timing.n_reads     = n_reads;
     timing.parse_error = parse_error ? 1 : 0;
-    timing.ms_host_index = ms_since(t0);
     file_records += n;
     if (final_block || parse_error)
         file_records = 0;
-
-    // upper bound of minimisers per read -> number of counter planes in K3
-    max_hashes_ub = 0;
-    hashed_k = hashed_w = 0;
-    GNB_CUDA(cudaEventRecord(ev[0], st));
-    const uint64_t bytes1 = len1 + t1.aux.size(), bytes2 = paired ? len2 + t2.aux.size() : 0;
-    timing.h2d_bytes = bytes1 + bytes2 + (uint64_t)n * 8 * (paired ? 2 : 1);
-    GNB_TRY(d_blk1.ensure(bytes1 + 64));
-    GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
-    if (!t1.aux.empty())
-        GNB_CUDA(cudaMemcpyAsync(d_blk1.as<uint8_t>() + len1, t1.aux.data(), t1.aux.size(), cudaMemcpyHostToDevice, st));
-    GNB_TRY(d_off1.ensure((size_t)n * 4 + 4));
-    GNB_TRY(d_len1.ensure((size_t)n * 4 + 4));
-    if (n)
-    {
-        GNB_CUDA(cudaMemcpyAsync(d_off1.p, t1.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
-        GNB_CUDA(cudaMemcpyAsync(d_len1.p, t1.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
-    }
-    if (paired)
-    {
-        GNB_TRY(d_blk2.ensure(bytes2 + 64));
-        GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st));
-        if (!t2.aux.empty())
-            GNB_CUDA(cudaMemcpyAsync(d_blk2.as<uint8_t>() + len2, t2.aux.data(), t2.aux.size(), cudaMemcpyHostToDevice, st));
-        GNB_TRY(d_off2.ensure((size_t)n * 4 + 4));
-        GNB_TRY(d_len2.ensure((size_t)n * 4 + 4));
-        if (n)
-        {
-            GNB_CUDA(cudaMemcpyAsync(d_off2.p, t2.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
-            GNB_CUDA(cudaMemcpyAsync(d_len2.p, t2.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
-        }
-    }
-    GNB_CUDA(cudaEventRecord(ev[1], st));
     GNB_TRY(d_counts.ensure((size_t)n * 4 + 4));
     GNB_TRY(d_hash_off.ensure(((size_t)n + 1) * 8));
     GNB_TRY(d_active.ensure((size_t)n + 1));
@@ -777,8 +911,7 @@ int gnb_session::run_level(size_t li)
     for (uint32_t i = 0; i < n; ++i)
         if (h_active[i] && h_counts[i] <= 65535)
             active_hashes += h_counts[i];
-    GNB_CUDA(cudaEventRecord(ev[4], st));
-    float ms_sort = 0;
+    float ms_sort = 0, ms_k3 = 0;
     for (auto &F : L.filters)
     {
         F.tuples.clear();
@@ -794,13 +927,20 @@ int gnb_session::run_level(size_t li)
         for (int attempt = 0; attempt < 2; ++attempt)
         {
             GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
+            GNB_CUDA(cudaEventRecord(ev[4], st));
             launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
                              d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
+            GNB_CUDA(cudaEventRecord(ev[5], st));
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             timing.d2h_bytes += 8;
             GNB_CUDA(cudaStreamSynchronize(st));
             GNB_CUDA(cudaGetLastError());
+            {
+                float ms1 = 0;
+                cudaEventElapsedTime(&ms1, ev[4], ev[5]);
+                ms_k3 += ms1;
+            }
             if (produced <= cap)
                 break;
             GNB_TRY(d_tuples_a.ensure(produced * 8)); // exact size is now known: run again
@@ -823,11 +963,7 @@ int gnb_session::run_level(size_t li)
         cudaEventElapsedTime(&ms, ev[6], ev[7]);
         ms_sort += ms;
     }
-    GNB_CUDA(cudaEventRecord(ev[5], st));
-    GNB_CUDA(cudaStreamSynchronize(st));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev[4], ev[5]);
-    timing.ms_count += ms - ms_sort;
+    timing.ms_count += ms_k3;
     timing.ms_sort += ms_sort;
     return GNB_OK;
 }
@@ -864,7 +1000,7 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
             if (!h_active[r])
                 continue;
             const uint32_t nh  = h_counts[r];
-            const uint32_t l1  = t1.seq_len[r], l2 = paired ? t2.seq_len[r] : 0;
+            const uint32_t l1  = p_slen1[r], l2 = paired ? p_slen2[r] : 0;
             const bool     small = l1 < L.w, big = nh > 65535;
             if (first)
             {
@@ -1005,8 +1141,8 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
                 W.n_classified++;
                 h_active[r]     = 0;
                 h_read_level[r] = (uint8_t)li;
-                const char  *id  = reinterpret_cast<const char *>(id_base + t1.id_off[r]);
-                const size_t idl = t1.id_len[r];
+                const char  *id  = reinterpret_cast<const char *>(id_base + p_idoff[r]);
+                const size_t idl = p_idlen[r];
                 uint32_t     one_node = W.m_target[m_begin];
                 uint64_t     one_count = W.m_count[m_begin];
                 if (kept == 1)
@@ -1057,7 +1193,7 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
                 W.m_count.resize(m_begin);
                 if (last && cfg.output_unclassified)
                 {
-                    W.unc_text.append(reinterpret_cast<const char *>(id_base + t1.id_off[r]), t1.id_len[r]);
+                    W.unc_text.append(reinterpret_cast<const char *>(id_base + p_idoff[r]), p_idlen[r]);
                     W.unc_text.push_back('\n');
                 }
             }
@@ -1205,8 +1341,8 @@ int gnb_session::finish(uint32_t prefix_id, gnb_batch_result *out)
 static void fill_consumed(gnb_session *s, gnb_batch_result *out)
 {
     // bytes that formed the records taken; on a parse error the rest of the file is skipped (GC.cpp:1278-1283)
-    out->consumed1 = s->parse_error ? s->len1 : s->t1.consumed_for(s->n_reads);
-    out->consumed2 = !s->paired ? 0 : s->parse_error ? s->len2 : s->t2.consumed_for(s->n_reads);
+    out->consumed1 = s->parse_error ? s->len1 : s->consumed1;
+    out->consumed2 = !s->paired ? 0 : s->parse_error ? s->len2 : s->consumed2;
 }
 
 extern "C" int gnb_session_stage(gnb_session *s, const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin, uint64_t *n_reads)

@@ -238,3 +238,42 @@ def test_parse_error_truncation_rule(golden_dbs, tmp_path):
     assert cli.main(["-r", f, "-i", golden_dbs["synth"], "-o", pre, "-u", "--quiet", "--n-reads", "400"]) == 0
     rep = dict(l.split("\t") for l in open(pre + ".rep").read().splitlines() if l.startswith("#"))
     assert int(rep["#total_unclassified"]) + int(rep["#total_classified"]) == 800
+
+
+def test_device_and_host_record_index_agree(golden_dbs, tmp_path, monkeypatch):
+    """K1 (device FASTQ index) and the host reader give identical results, including a final block without a
+    trailing newline and blocks that end in the middle of a record."""
+    args = SU.expand(SU.load_scenarios()["pe_synth_all"], golden_dbs)
+    outs = []
+    for host_index in ("0", "1"):
+        monkeypatch.setenv("GANON_B200_HOST_INDEX", host_index)
+        pre = str(tmp_path / ("o" + host_index))
+        assert cli.main(args + ["-o", pre, "--quiet"]) == 0
+        outs.append({e: _read_sorted(pre + "." + e) for e in ("all", "unc", "rep", "sta")})
+    assert outs[0] == outs[1]
+    assert outs[0]["all"] == SU.expected_lines("pe_synth_all", "all")
+    # block boundaries inside records + missing final newline, through the session API
+    fq1 = open(os.path.join(SU.GOLDEN, "reads.1.fq"), "rb").read().rstrip(b"\n")
+    fq2 = open(os.path.join(SU.GOLDEN, "reads.2.fq"), "rb").read().rstrip(b"\n")
+    db = Database.open(golden_dbs["synth"])
+    res_all = []
+    for host_index in ("0", "1"):
+        monkeypatch.setenv("GANON_B200_HOST_INDEX", host_index)
+        sess = Session([db], [0.0], [1.0], [1.0], output_all=True, output_unclassified=True)
+        lines, o1, o2, total = [], 0, 0, 0
+        step = 40000
+        while True:
+            e1, e2 = min(len(fq1), o1 + step), min(len(fq2), o2 + step + 777)
+            final = e1 == len(fq1) and e2 == len(fq2)
+            r = sess.classify(fq1[o1:e1], fq2[o2:e2], final=final)
+            lines += result_text(r, "all").decode().splitlines()
+            total += r.n_reads
+            o1 += r.consumed1
+            o2 += r.consumed2
+            if final:
+                break
+            assert r.n_reads > 0
+        res_all.append((total, sorted(lines)))
+        sess.close()
+    assert res_all[0] == res_all[1]
+    assert res_all[0][1] == SU.expected_lines("pe_synth_all", "all")
