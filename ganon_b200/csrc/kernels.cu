@@ -25,11 +25,9 @@ namespace gnb
 namespace
 {
 
-constexpr int K2_WARPS = 4;   // warps (= reads in flight) per CTA
-constexpr int K2_TILE  = 256; // k-mer positions per tile
-constexpr int K2_WMAX  = 256; // max supported (w - k + 1)
-constexpr int K2_NV    = K2_TILE + K2_WMAX;
-constexpr int K2_NB    = K2_NV + 32;
+constexpr int K2_WARPS = 8;   // warps (= reads in flight) per CTA
+constexpr int K2_TILE  = 256; // windows per tile (8 per lane)
+constexpr int K2_PER   = K2_TILE / 32;
 
 // seqan3 dna4 char_to_rank incl. IUPAC conversion (dna4.hpp:166-205): everything not listed maps to 0 ('A').
 __device__ __forceinline__ uint32_t dna4_rank(uint8_t c)
@@ -42,106 +40,196 @@ __device__ __forceinline__ uint32_t dna4_rank(uint8_t c)
     return r;
 }
 
-struct K2Smem
+// Rightmost minimum of sv[0..W) (std::ranges::min_element with less_equal, minimiser.hpp:433-435); dup = the minimum
+// occurs more than once.
+__device__ __forceinline__ uint32_t rightmost_min(const uint64_t *sv, uint32_t W, uint64_t &best, bool &dup)
 {
-    uint64_t v[K2_WARPS][K2_NV];
-    uint16_t succ[K2_WARPS][K2_TILE];
-    uint8_t  base[K2_WARPS][K2_NB];
-};
+    uint32_t idx = 0;
+    best = sv[0];
+    bool d = false;
+    for (uint32_t x = 1; x < W; ++x)
+    {
+        const uint64_t y = sv[x];
+        if (y < best)
+        {
+            best = y;
+            idx  = x;
+            d    = false;
+        }
+        else if (y == best)
+        {
+            idx = x;
+            d   = true;
+        }
+    }
+    dup |= d;
+    return idx;
+}
 
-// One mate.  Returns the number of minimisers emitted (valid in every lane).  See DESIGN.md "K2" for the successor
-// formulation of minimiser.hpp:444-472: from a tracked position p the next tracked position is the first e in
-// (p, p+W-1] with v[e] < v[p] (strictly smaller newcomer), else -- when p leaves the window at e = p+W -- the
-// RIGHTMOST minimum of v[p+1..p+W]; every change of the tracked position emits.
+// bases [b0, b0+nb) of the mate -> ranks in shared memory, then canonical k-mer values v[0..nv) (value i = k-mer at
+// base b0 + i); each lane rolls over a contiguous run (kmer_hash.hpp:618-640, minimiser_hash.hpp:91-107)
+__device__ __forceinline__ void load_values(const uint8_t *__restrict__ seq, uint32_t nv, uint32_t k, uint64_t seed, uint64_t kmask,
+                                            uint64_t *sv, uint8_t *sb, uint32_t lane)
+{
+    const uint32_t nb = nv + k - 1;
+    __syncwarp();
+    for (uint32_t i = lane; i < nb; i += 32)
+        sb[i] = (uint8_t)dna4_rank(seq[i]);
+    __syncwarp();
+    const uint32_t seg = (nv + 31) >> 5;
+    const uint32_t i0 = lane * seg, i1 = min(nv, i0 + seg);
+    if (i0 < i1)
+    {
+        uint64_t f = 0, r = 0;
+        for (uint32_t j = 0; j < k; ++j)
+        {
+            const uint64_t b = sb[i0 + j];
+            f = (f << 2) | b;                          // first base most significant
+            r = (r >> 2) | ((3 - b) << (2 * (k - 1))); // reverse complement, complement = 3 - rank (dna4.hpp:95-98)
+        }
+        sv[i0] = min(f ^ seed, r ^ seed);
+        for (uint32_t i = i0 + 1; i < i1; ++i)
+        {
+            const uint64_t b = sb[i + k - 1];
+            f = ((f << 2) | b) & kmask;
+            r = (r >> 2) | ((3 - b) << (2 * (k - 1)));
+            sv[i] = min(f ^ seed, r ^ seed);
+        }
+    }
+    __syncwarp();
+}
+
+// One mate.  Returns the number of minimisers emitted (warp-uniform).
+//
+// The reference's window (minimiser.hpp:444-472) is a sticky state machine: the tracked minimiser position `mp` only
+// moves when a strictly smaller value enters, or when it leaves the window (then the RIGHTMOST minimum of the new
+// window is taken and emitted even if the value repeats).  Whenever every window has a unique minimum, mp(i) is simply
+// that minimum, so the windows are split over the lanes: a lane seeds its state with the minimum of the window before
+// its first one and then runs the exact step rule over its 8 windows.  Any equality a lane meets (two equal minima in
+// a rescan, a newcomer equal to the current minimum) raises `tie`, and the whole mate is redone by the exact serial
+// walk below -- homopolymers, short-period repeats etc. stay bit-exact.
 template <bool WRITE>
 __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t L, uint32_t k, uint32_t w, uint64_t seed,
-                                       uint64_t *__restrict__ out, K2Smem &sm, uint32_t wib, uint32_t lane)
+                                       uint64_t *__restrict__ out, uint64_t *sv, uint8_t *sb, uint32_t lane)
 {
-    const uint32_t nk = L - k + 1;
-    const uint32_t W  = min(w - k + 1, nk);
+    const uint32_t nk   = L - k + 1;
+    const uint32_t W    = min(w - k + 1, nk);
+    const uint32_t nwin = nk - W + 1;
     const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
-    uint64_t *sv  = sm.v[wib];
-    uint16_t *ssu = sm.succ[wib];
-    uint8_t  *sb  = sm.base[wib];
 
-    uint32_t cur     = 0; // tracked position (lane 0)
     uint32_t emitted = 0;
-    bool     done    = false;
-    for (uint32_t t0 = 0; t0 < nk; t0 += K2_TILE)
+    bool     tie     = false;
+    for (uint32_t t0 = 0; t0 < nwin; t0 += K2_TILE)
     {
-        const uint32_t nv = min(nk - t0, (uint32_t)K2_TILE + W); // values needed: tile + look-ahead of W
-        const uint32_t nb = nv + k - 1;
-        __syncwarp();
-        for (uint32_t i = lane; i < nb; i += 32)
-            sb[i] = (uint8_t)dna4_rank(seq[t0 + i]);
-        __syncwarp();
-        // each lane rolls over a contiguous run of positions
+        const uint32_t nt  = min((uint32_t)K2_TILE, nwin - t0);
+        const uint32_t vlo = t0 ? t0 - 1 : 0; // the window before the tile seeds the first lane
+        const uint32_t nv  = t0 + nt + W - 1 - vlo;
+        load_values(seq + vlo, nv, k, seed, kmask, sv, sb, lane);
+        const uint32_t a = t0 + lane * K2_PER, b = min(t0 + nt, a + K2_PER);
+        uint64_t em[K2_PER];
+        uint32_t emask = 0;
+        if (a < b)
         {
-            const uint32_t seg = (nv + 31) >> 5;
-            const uint32_t i0 = lane * seg, i1 = min(nv, i0 + seg);
-            if (i0 < i1)
-            {
-                uint64_t f = 0, r = 0;
-                for (uint32_t j = 0; j < k; ++j)
-                {
-                    const uint64_t b = sb[i0 + j];
-                    f = (f << 2) | b;                          // first base most significant (kmer_hash.hpp:618-640)
-                    r = (r >> 2) | ((3 - b) << (2 * (k - 1))); // reverse complement, complement = 3 - rank
-                }
-                sv[i0] = min(f ^ seed, r ^ seed);
-                for (uint32_t i = i0 + 1; i < i1; ++i)
-                {
-                    const uint64_t b = sb[i + k - 1];
-                    f = ((f << 2) | b) & kmask;
-                    r = (r >> 2) | ((3 - b) << (2 * (k - 1)));
-                    sv[i] = min(f ^ seed, r ^ seed);
-                }
-            }
-        }
-        __syncwarp();
-        const uint32_t np = min((uint32_t)K2_TILE, nk - t0);
-        for (uint32_t p = lane; p < np; p += 32)
-        {
-            const uint64_t vp = sv[p];
-            const uint32_t hi = min(W, nk - 1 - (t0 + p)); // values after p that exist, at most W
-            uint32_t first = 0, rmin_d = 0;
-            uint64_t rmin = ~0ULL;
-            for (uint32_t d = 1; d <= hi; ++d)
-            {
-                const uint64_t x = sv[p + d];
-                if (first == 0 && d < W && x < vp)
-                    first = d;
-                if (x <= rmin) // less_equal -> last of equal minima (minimiser.hpp:433-435)
-                {
-                    rmin   = x;
-                    rmin_d = d;
-                }
-            }
-            ssu[p] = (uint16_t)(first ? first : (hi == W ? rmin_d : 0u));
-        }
-        __syncwarp();
-        if (lane == 0 && !done)
-        {
-            if (t0 == 0)
+            uint64_t cur;
+            uint32_t mp; // absolute position of the tracked minimiser
+            uint32_t first = a;
+            if (a == 0)
             { // window_first (minimiser.hpp:422-436)
-                uint32_t m = 0;
-                for (uint32_t x = 1; x < W; ++x)
-                    if (sv[x] <= sv[m])
-                        m = x;
-                cur = m;
+                mp    = rightmost_min(sv, W, cur, tie);
+                em[0] = cur;
+                emask = 1;
+                first = 1;
             }
-            while (cur < t0 + np)
+            else
+                mp = a - 1 + rightmost_min(sv + (a - 1 - vlo), W, cur, tie);
+#pragma unroll
+            for (int j = 0; j < K2_PER; ++j)
             {
-                if (WRITE)
-                    out[emitted] = sv[cur - t0];
-                ++emitted;
-                const uint32_t d = ssu[cur - t0];
-                if (d == 0)
+                const uint32_t i = a + j; // window [i, i+W-1]
+                if (i >= first && i < b)
                 {
-                    done = true;
-                    break;
+                    if (mp < i)
+                    { // the minimiser left the window: rescan, always emit (minimiser.hpp:455-461)
+                        mp    = i + rightmost_min(sv + (i - vlo), W, cur, tie);
+                        em[j] = cur;
+                        emask |= 1u << j;
+                    }
+                    else
+                    {
+                        const uint64_t x = sv[i + W - 1 - vlo];
+                        if (x < cur)
+                        { // strictly smaller newcomer (minimiser.hpp:463-468)
+                            cur   = x;
+                            mp    = i + W - 1;
+                            em[j] = x;
+                            emask |= 1u << j;
+                        }
+                        else if (x == cur)
+                            tie = true;
+                    }
                 }
-                cur += d;
+            }
+        }
+        if (__any_sync(0xffffffffu, tie))
+            break;
+        // ordered compaction of the lanes' emissions
+        const uint32_t mine = __popc(emask);
+        uint32_t       incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d)
+                incl += y;
+        }
+        if (WRITE)
+        {
+            uint32_t pos = emitted + incl - mine;
+#pragma unroll
+            for (int j = 0; j < K2_PER; ++j)
+                if ((emask >> j) & 1u)
+                    out[pos++] = em[j];
+        }
+        emitted += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (!__any_sync(0xffffffffu, tie))
+        return emitted;
+
+    // ---- exact serial walk (ties present) ----
+    emitted = 0;
+    uint32_t mp = 0;
+    uint64_t cur = 0;
+    for (uint32_t t0 = 0; t0 < nwin; t0 += K2_TILE)
+    {
+        const uint32_t nt = min((uint32_t)K2_TILE, nwin - t0);
+        const uint32_t nv = nt + W - 1;
+        load_values(seq + t0, nv, k, seed, kmask, sv, sb, lane);
+        if (lane == 0)
+        {
+            for (uint32_t i = t0; i < t0 + nt; ++i)
+            {
+                bool e = false, dummy = false;
+                if (i == 0 || mp < i)
+                {
+                    mp = i + rightmost_min(sv + (i - t0), W, cur, dummy);
+                    e  = true;
+                }
+                else
+                {
+                    const uint64_t x = sv[i + W - 1 - t0];
+                    if (x < cur)
+                    {
+                        cur = x;
+                        mp  = i + W - 1;
+                        e   = true;
+                    }
+                }
+                if (e)
+                {
+                    if (WRITE)
+                        out[emitted] = cur;
+                    ++emitted;
+                }
             }
         }
     }
@@ -166,11 +254,13 @@ template <bool WRITE>
 __global__ void __launch_bounds__(K2_WARPS * 32)
     k_minimisers(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1,
                  const uint8_t *__restrict__ blk2, const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2,
-                 uint32_t n_reads, uint32_t k, uint32_t w, uint32_t *__restrict__ counts, const uint64_t *__restrict__ hash_off,
-                 uint64_t *__restrict__ hashes)
+                 uint32_t n_reads, uint32_t k, uint32_t w, uint32_t nv_cap, uint32_t nb_cap, uint32_t *__restrict__ counts,
+                 const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes)
 {
-    __shared__ K2Smem sm;
+    extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t *sv = reinterpret_cast<uint64_t *>(k2_smem) + (size_t)wib * nv_cap;
+    uint8_t  *sb = k2_smem + (size_t)K2_WARPS * nv_cap * 8 + (size_t)wib * nb_cap;
     const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
     for (uint32_t read = blockIdx.x * K2_WARPS + wib; read < n_reads; read += gridDim.x * K2_WARPS)
     {
@@ -179,12 +269,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
         if (L1 >= w && L1 >= k) // GC.cpp:690: reads shorter than the window are skipped entirely
         {
             uint64_t *out = WRITE ? hashes + hash_off[read] : nullptr;
-            total = minimisers_of_mate<WRITE>(blk1 + off1[read], L1, k, w, seed, out, sm, wib, lane);
+            total = minimisers_of_mate<WRITE>(blk1 + off1[read], L1, k, w, seed, out, sv, sb, lane);
             if (blk2 != nullptr)
             {
                 const uint32_t L2 = len2[read];
                 if (L2 >= w && L2 >= k) // GC.cpp:695
-                    total += minimisers_of_mate<WRITE>(blk2 + off2[read], L2, k, w, seed, WRITE ? out + total : nullptr, sm, wib, lane);
+                    total += minimisers_of_mate<WRITE>(blk2 + off2[read], L2, k, w, seed, WRITE ? out + total : nullptr, sv, sb, lane);
             }
         }
         if (!WRITE && lane == 0)
@@ -200,12 +290,26 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
 {
     if (n_reads == 0)
         return;
+    const uint32_t W      = w - k + 1;
+    const uint32_t nv_cap = (K2_TILE + W + 1 + 1) & ~1u;          // values per warp
+    const uint32_t nb_cap = (nv_cap + k + 15) & ~15u;             // bases per warp
+    const size_t   smem   = (size_t)K2_WARPS * (nv_cap * 8 + nb_cap);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t want = (n_reads + K2_WARPS - 1) / K2_WARPS;
-    const uint32_t grid = want < 148u * 16u ? want : 148u * 16u; // 16 CTAs (64 warps) per SM, persistent stride
+    const uint32_t full = (uint32_t)sms * 8; // 64 warps per SM, persistent stride
+    const uint32_t grid = want < full ? want : full;
     if (write)
-        k_minimisers<true><<<grid, K2_WARPS * 32, 0, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes);
+    {
+        cudaFuncSetAttribute(k_minimisers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_minimisers<true><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes);
+    }
     else
-        k_minimisers<false><<<grid, K2_WARPS * 32, 0, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes);
+    {
+        cudaFuncSetAttribute(k_minimisers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_minimisers<false><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
