@@ -104,10 +104,11 @@ __device__ __forceinline__ void load_values(const uint8_t *__restrict__ seq, uin
 // The reference's window (minimiser.hpp:444-472) is a sticky state machine: the tracked minimiser position `mp` only
 // moves when a strictly smaller value enters, or when it leaves the window (then the RIGHTMOST minimum of the new
 // window is taken and emitted even if the value repeats).  Whenever every window has a unique minimum, mp(i) is simply
-// that minimum, so the windows are split over the lanes: a lane seeds its state with the minimum of the window before
-// its first one and then runs the exact step rule over its 8 windows.  Any equality a lane meets (two equal minima in
-// a rescan, a newcomer equal to the current minimum) raises `tie`, and the whole mate is redone by the exact serial
-// walk below -- homopolymers, short-period repeats etc. stay bit-exact.
+// that minimum R(i), and window i emits iff R(i) != R(i-1) (or i == 0).  So consecutive lanes take consecutive windows,
+// each scans its W values for the minimum (uniform work, conflict-free shared-memory reads), neighbours exchange R by
+// shuffle and the emissions are compacted in order with a ballot.  A duplicated minimum in any window raises `tie`,
+// and the whole mate is redone by the exact serial walk below -- homopolymers, short-period repeats etc. stay
+// bit-exact.
 template <bool WRITE>
 __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t L, uint32_t k, uint32_t w, uint64_t seed,
                                        uint64_t *__restrict__ out, uint64_t *sv, uint8_t *sb, uint32_t lane)
@@ -119,80 +120,38 @@ __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t
 
     uint32_t emitted = 0;
     bool     tie     = false;
-    for (uint32_t t0 = 0; t0 < nwin; t0 += K2_TILE)
+    uint32_t prev_r  = 0xffffffffu; // R of the window before the current group of 32 (lane 31's, carried)
+    for (uint32_t t0 = 0; t0 < nwin && !tie; t0 += K2_TILE)
     {
-        const uint32_t nt  = min((uint32_t)K2_TILE, nwin - t0);
-        const uint32_t vlo = t0 ? t0 - 1 : 0; // the window before the tile seeds the first lane
-        const uint32_t nv  = t0 + nt + W - 1 - vlo;
-        load_values(seq + vlo, nv, k, seed, kmask, sv, sb, lane);
-        const uint32_t a = t0 + lane * K2_PER, b = min(t0 + nt, a + K2_PER);
-        uint64_t em[K2_PER];
-        uint32_t emask = 0;
-        if (a < b)
+        const uint32_t nt = min((uint32_t)K2_TILE, nwin - t0);
+        const uint32_t nv = nt + W - 1;
+        load_values(seq + t0, nv, k, seed, kmask, sv, sb, lane);
+        for (uint32_t g = 0; g < nt; g += 32)
         {
-            uint64_t cur;
-            uint32_t mp; // absolute position of the tracked minimiser
-            uint32_t first = a;
-            if (a == 0)
-            { // window_first (minimiser.hpp:422-436)
-                mp    = rightmost_min(sv, W, cur, tie);
-                em[0] = cur;
-                emask = 1;
-                first = 1;
-            }
-            else
-                mp = a - 1 + rightmost_min(sv + (a - 1 - vlo), W, cur, tie);
-#pragma unroll
-            for (int j = 0; j < K2_PER; ++j)
+            const uint32_t i  = g + lane; // window [t0+i, t0+i+W-1]
+            const bool     on = i < nt;
+            uint64_t best = 0;
+            bool     dup  = false;
+            uint32_t r    = 0;
+            if (on)
+                r = t0 + i + rightmost_min(sv + i, W, best, dup);
+            uint32_t left = __shfl_up_sync(0xffffffffu, r, 1);
+            if (lane == 0)
+                left = prev_r;
+            prev_r = __shfl_sync(0xffffffffu, r, 31);
+            const bool     emit = on && r != left; // prev_r starts at an impossible position: window 0 always emits
+            const uint32_t mask = __ballot_sync(0xffffffffu, emit);
+            if (__any_sync(0xffffffffu, dup))
             {
-                const uint32_t i = a + j; // window [i, i+W-1]
-                if (i >= first && i < b)
-                {
-                    if (mp < i)
-                    { // the minimiser left the window: rescan, always emit (minimiser.hpp:455-461)
-                        mp    = i + rightmost_min(sv + (i - vlo), W, cur, tie);
-                        em[j] = cur;
-                        emask |= 1u << j;
-                    }
-                    else
-                    {
-                        const uint64_t x = sv[i + W - 1 - vlo];
-                        if (x < cur)
-                        { // strictly smaller newcomer (minimiser.hpp:463-468)
-                            cur   = x;
-                            mp    = i + W - 1;
-                            em[j] = x;
-                            emask |= 1u << j;
-                        }
-                        else if (x == cur)
-                            tie = true;
-                    }
-                }
+                tie = true;
+                break;
             }
+            if (WRITE && emit)
+                out[emitted + __popc(mask & ((1u << lane) - 1))] = best;
+            emitted += __popc(mask);
         }
-        if (__any_sync(0xffffffffu, tie))
-            break;
-        // ordered compaction of the lanes' emissions
-        const uint32_t mine = __popc(emask);
-        uint32_t       incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d)
-                incl += y;
-        }
-        if (WRITE)
-        {
-            uint32_t pos = emitted + incl - mine;
-#pragma unroll
-            for (int j = 0; j < K2_PER; ++j)
-                if ((emask >> j) & 1u)
-                    out[pos++] = em[j];
-        }
-        emitted += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (!__any_sync(0xffffffffu, tie))
+    if (!tie)
         return emitted;
 
     // ---- exact serial walk (ties present) ----
