@@ -126,6 +126,11 @@ void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *h
 // K3 dense (test hook): counts[n_reads][row_words*64]
 void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n_reads,
                             uint32_t max_hashes, uint16_t *counts, cudaStream_t st);
+// K3h: one traversal round of an HIBF (items = (read, sub-IBF) pairs); see kernels.cu
+void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *items, uint32_t n_items, const uint64_t *hashes, const uint64_t *hash_off,
+                       uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
+                       unsigned long long *items_cursor, uint64_t items_cap, cudaStream_t st);
+constexpr uint32_t kMergedBinFlag = 0x80000000u;
 // sort tuples by (read, node)
 size_t sort_tmp_bytes(uint64_t n);
 void   launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);

@@ -383,194 +383,237 @@ __device__ __forceinline__ uint32_t sliced_sum(const uint32_t (&P)[NP][4], uint3
     return s;
 }
 
-// MODE 0: sparse tuples; MODE 1: dense counts (test hook)
+// MODE 0: sparse tuples; MODE 1: dense counts (test hook); MODE 2: HIBF item (merged bins feed the next worklist)
+constexpr uint32_t kMergedBin = 0x80000000u; // bin_node flag: the bin is a merged bin, low bits = child IBF
+
+struct WorkOut
+{
+    uint64_t           *tuples;
+    unsigned long long *cursor;
+    uint64_t            cap;
+    uint16_t           *dense;
+    uint2              *items; // MODE 2: (read, child ibf) for merged bins that reach the threshold
+    unsigned long long *items_cursor;
+    uint64_t            items_cap;
+};
+
+// One (read, chunk) work item: gather + AND + bit-sliced count over the read's minimisers, then the epilogue.
+template <int H, int NP, bool ALIGNED, int MODE>
+__device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint32_t chunk, const uint64_t *__restrict__ hashes,
+                                           const uint64_t *__restrict__ hash_off, double rel_cutoff, const WorkOut &wo, uint64_t *s_row,
+                                           uint32_t lane)
+{
+    constexpr int  PER    = 32 / H; // minimisers whose rows are staged per round
+    const uint64_t seed_l = ibf_seed(lane % H);
+    uint64_t *const tuples = wo.tuples;
+    unsigned long long *const cursor = wo.cursor;
+    const uint64_t  cap   = wo.cap;
+    uint16_t *const dense = wo.dense;
+    const uint64_t h0 = hash_off[read];
+    const uint64_t nn = hash_off[read + 1] - h0;
+    if (nn == 0 || nn > 65535) // skipped: shorter than the window / more minimisers than the counter type holds
+        return;
+    const uint32_t n  = (uint32_t)nn;
+    const uint32_t w0 = chunk * 64 + lane * 2; // first of the lane's two bin-words inside the row
+    const bool     v0 = w0 < f.row_words, v1 = (w0 + 1) < f.row_words;
+    const uint64_t *lane_base = f.data + w0;
+
+    uint32_t P[NP][4];
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+        P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0;
+
+    for (uint32_t base = 0; base < n; base += PER)
+    {
+        __syncwarp();
+        if (lane < PER * H)
+        {
+            const uint32_t m = base + lane / H;
+            if (m < n)
+                s_row[lane] = ibf_row(hashes[h0 + m], seed_l, f.hash_shift, f.bin_size) * f.row_words;
+        }
+        __syncwarp();
+        const uint32_t cnt = min((uint32_t)PER, n - base);
+        for (uint32_t jb = 0; jb < cnt; jb += 4)
+        {
+            uint32_t x[4][4];
+            uint4    rows[4][H];
+            // issue every load of the block first (up to 4*H 128-bit loads in flight per lane)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                const bool ok = (jb + q) < cnt;
+#pragma unroll
+                for (int i = 0; i < H; ++i)
+                {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (ok)
+                    {
+                        const uint64_t *p = lane_base + s_row[(jb + q) * H + i];
+                        if (ALIGNED)
+                        {
+                            if (v0)
+                                v = ldg_stream16(p);
+                        }
+                        else
+                        {
+                            if (v0)
+                            {
+                                const uint2 a = ldg_stream8(p);
+                                v.x = a.x;
+                                v.y = a.y;
+                            }
+                            if (v1)
+                            {
+                                const uint2 b = ldg_stream8(p + 1);
+                                v.z = b.x;
+                                v.w = b.y;
+                            }
+                        }
+                    }
+                    rows[q][i] = v;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                uint4 a = rows[q][0];
+#pragma unroll
+                for (int i = 1; i < H; ++i)
+                {
+                    a.x &= rows[q][i].x;
+                    a.y &= rows[q][i].y;
+                    a.z &= rows[q][i].z;
+                    a.w &= rows[q][i].w;
+                }
+                x[q][0] = a.x;
+                x[q][1] = a.y;
+                x[q][2] = a.z;
+                x[q][3] = a.w;
+            }
+            csa_add4<NP>(P, x);
+        }
+    }
+
+    if (MODE == 1)
+    {
+        // dense dump: counts[read][bin]
+        uint16_t *o = dense + (uint64_t)read * ((uint64_t)f.row_words * 64) + (uint64_t)w0 * 64;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+        {
+            const bool valid = (r < 2) ? v0 : v1;
+            if (valid)
+                for (uint32_t b = 0; b < 32; ++b)
+                    o[r * 32 + b] = (uint16_t)sliced_get<NP>(P, r, b);
+        }
+        return;
+    }
+
+    // ---- select_matches (GC.cpp:504-541) on the lane's 128 bins ----
+    const uint32_t T = threshold_cutoff(n, rel_cutoff);
+    uint32_t       cand[4];
+    uint32_t       mine = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const bool valid = (r < 2) ? v0 : v1;
+        cand[r] = valid ? (sliced_ge<NP>(P, r, T) & f.single_mask[(uint32_t)w0 * 2 + r]) : 0u;
+        mine += __popc(cand[r]);
+    }
+    if (__any_sync(0xffffffffu, mine != 0))
+    {
+        // warp-aggregated append: one atomic per warp
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d)
+                incl += y;
+        }
+        const uint32_t     total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long start = 0;
+        if (lane == 0)
+            start = atomicAdd(cursor, (unsigned long long)total);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        uint64_t pos = start + (incl - mine);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+        {
+            uint32_t m = cand[r];
+            while (m)
+            {
+                const uint32_t b = __ffs(m) - 1;
+                m &= m - 1;
+                if (pos < cap)
+                    tuples[pos] = make_tuple64(read, f.bin_node[(uint32_t)w0 * 64 + r * 32 + b], 0, sliced_get<NP>(P, r, b));
+                ++pos;
+            }
+        }
+    }
+    // ---- nodes made of several bins: masked popcount sums per segment ----
+    if (f.seg_off != nullptr)
+    {
+        const uint32_t s0 = f.seg_off[chunk * 32 + lane], s1 = f.seg_off[chunk * 32 + lane + 1];
+        for (uint32_t s = s0; s < s1; ++s)
+        {
+            const Seg      sg  = f.segs[s];
+            uint32_t       sum = sliced_sum<NP>(P, sg.reg, sg.mask);
+            uint32_t       partial = 1;
+            if (sg.complete)
+            {
+                sum     = min(sum, n); // GC.cpp:525-526
+                partial = 0;
+                if (sum < T)
+                    sum = 0;
+            }
+            if (sum != 0)
+            {
+                const unsigned long long pos = atomicAdd(cursor, 1ULL);
+                if (pos < cap)
+                    tuples[pos] = make_tuple64(read, sg.node, partial, sum);
+            }
+        }
+    }
+
+}
+
 template <int H, int NP, bool ALIGNED, int MODE>
 __global__ void __launch_bounds__(K3_WARPS * 32)
     k_ibf_count(const IbfDev f, const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ hash_off,
-                const uint8_t *__restrict__ active, uint32_t n_reads, double rel_cutoff, uint64_t *__restrict__ tuples,
-                unsigned long long *__restrict__ cursor, uint64_t cap, uint16_t *__restrict__ dense)
+                const uint8_t *__restrict__ active, uint32_t n_reads, double rel_cutoff, const WorkOut wo)
 {
-    constexpr int PER = 32 / H; // minimisers whose rows are staged per round
     __shared__ uint64_t s_row[K3_WARPS][32];
-
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t n_items = (uint64_t)n_reads * f.n_chunks;
     const uint64_t stride  = (uint64_t)gridDim.x * K3_WARPS;
-    const uint64_t seed_l  = ibf_seed(lane % H);
-
     for (uint64_t item = (uint64_t)blockIdx.x * K3_WARPS + wib; item < n_items; item += stride)
     {
         const uint32_t read  = (uint32_t)(item / f.n_chunks);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)read * f.n_chunks);
         if (active != nullptr && active[read] == 0)
             continue;
-        const uint64_t h0 = hash_off[read];
-        const uint64_t nn = hash_off[read + 1] - h0;
-        if (nn == 0 || nn > 65535) // skipped: shorter than the window / more minimisers than the counter type holds
-            continue;
-        const uint32_t n  = (uint32_t)nn;
-        const uint32_t w0 = chunk * 64 + lane * 2; // first of the lane's two bin-words inside the row
-        const bool     v0 = w0 < f.row_words, v1 = (w0 + 1) < f.row_words;
-        const uint64_t *lane_base = f.data + w0;
+        count_item<H, NP, ALIGNED, MODE>(f, read, chunk, hashes, hash_off, rel_cutoff, wo, s_row[wib], lane);
+    }
+}
 
-        uint32_t P[NP][4];
-#pragma unroll
-        for (int j = 0; j < NP; ++j)
-            P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0;
-
-        for (uint32_t base = 0; base < n; base += PER)
-        {
-            __syncwarp();
-            if (lane < PER * H)
-            {
-                const uint32_t m = base + lane / H;
-                if (m < n)
-                    s_row[wib][lane] = ibf_row(hashes[h0 + m], seed_l, f.hash_shift, f.bin_size) * f.row_words;
-            }
-            __syncwarp();
-            const uint32_t cnt = min((uint32_t)PER, n - base);
-            for (uint32_t jb = 0; jb < cnt; jb += 4)
-            {
-                uint32_t x[4][4];
-                uint4    rows[4][H];
-                // issue every load of the block first (up to 4*H 128-bit loads in flight per lane)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                {
-                    const bool ok = (jb + q) < cnt;
-#pragma unroll
-                    for (int i = 0; i < H; ++i)
-                    {
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (ok)
-                        {
-                            const uint64_t *p = lane_base + s_row[wib][(jb + q) * H + i];
-                            if (ALIGNED)
-                            {
-                                if (v0)
-                                    v = ldg_stream16(p);
-                            }
-                            else
-                            {
-                                if (v0)
-                                {
-                                    const uint2 a = ldg_stream8(p);
-                                    v.x = a.x;
-                                    v.y = a.y;
-                                }
-                                if (v1)
-                                {
-                                    const uint2 b = ldg_stream8(p + 1);
-                                    v.z = b.x;
-                                    v.w = b.y;
-                                }
-                            }
-                        }
-                        rows[q][i] = v;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                {
-                    uint4 a = rows[q][0];
-#pragma unroll
-                    for (int i = 1; i < H; ++i)
-                    {
-                        a.x &= rows[q][i].x;
-                        a.y &= rows[q][i].y;
-                        a.z &= rows[q][i].z;
-                        a.w &= rows[q][i].w;
-                    }
-                    x[q][0] = a.x;
-                    x[q][1] = a.y;
-                    x[q][2] = a.z;
-                    x[q][3] = a.w;
-                }
-                csa_add4<NP>(P, x);
-            }
-        }
-
-        if (MODE == 1)
-        {
-            // dense dump: counts[read][bin]
-            uint16_t *o = dense + (uint64_t)read * ((uint64_t)f.row_words * 64) + (uint64_t)w0 * 64;
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-            {
-                const bool valid = (r < 2) ? v0 : v1;
-                if (valid)
-                    for (uint32_t b = 0; b < 32; ++b)
-                        o[r * 32 + b] = (uint16_t)sliced_get<NP>(P, r, b);
-            }
-            continue;
-        }
-
-        // ---- select_matches (GC.cpp:504-541) on the lane's 128 bins ----
-        const uint32_t T = threshold_cutoff(n, rel_cutoff);
-        uint32_t       cand[4];
-        uint32_t       mine = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-        {
-            const bool valid = (r < 2) ? v0 : v1;
-            cand[r] = valid ? (sliced_ge<NP>(P, r, T) & f.single_mask[(uint32_t)w0 * 2 + r]) : 0u;
-            mine += __popc(cand[r]);
-        }
-        if (__any_sync(0xffffffffu, mine != 0))
-        {
-            // warp-aggregated append: one atomic per warp
-            uint32_t incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d)
-                    incl += y;
-            }
-            const uint32_t     total = __shfl_sync(0xffffffffu, incl, 31);
-            unsigned long long start = 0;
-            if (lane == 0)
-                start = atomicAdd(cursor, (unsigned long long)total);
-            start = __shfl_sync(0xffffffffu, start, 0);
-            uint64_t pos = start + (incl - mine);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-            {
-                uint32_t m = cand[r];
-                while (m)
-                {
-                    const uint32_t b = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (pos < cap)
-                        tuples[pos] = make_tuple64(read, f.bin_node[(uint32_t)w0 * 64 + r * 32 + b], 0, sliced_get<NP>(P, r, b));
-                    ++pos;
-                }
-            }
-        }
-        // ---- nodes made of several bins: masked popcount sums per segment ----
-        if (f.seg_off != nullptr)
-        {
-            const uint32_t s0 = f.seg_off[chunk * 32 + lane], s1 = f.seg_off[chunk * 32 + lane + 1];
-            for (uint32_t s = s0; s < s1; ++s)
-            {
-                const Seg      sg  = f.segs[s];
-                uint32_t       sum = sliced_sum<NP>(P, sg.reg, sg.mask);
-                uint32_t       partial = 1;
-                if (sg.complete)
-                {
-                    sum     = min(sum, n); // GC.cpp:525-526
-                    partial = 0;
-                    if (sum < T)
-                        sum = 0;
-                }
-                if (sum != 0)
-                {
-                    const unsigned long long pos = atomicAdd(cursor, 1ULL);
-                    if (pos < cap)
-                        tuples[pos] = make_tuple64(read, sg.node, partial, sum);
-                }
-            }
-        }
+// HIBF traversal round (bulk_count_impl, HIBF.hpp:433-460, level-synchronous): one warp per (read, ibf) item, all
+// chunks of that sub-IBF in turn.  User bins reaching the threshold become tuples, merged bins become items of the
+// next round.
+template <int H, int NP>
+__global__ void __launch_bounds__(K3_WARPS * 32)
+    k_hibf_count(const IbfDev *__restrict__ table, const uint2 *__restrict__ items, uint32_t n_items, const uint64_t *__restrict__ hashes,
+                 const uint64_t *__restrict__ hash_off, double rel_cutoff, const WorkOut wo)
+{
+    __shared__ uint64_t s_row[K3_WARPS][32];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (uint32_t it = blockIdx.x * K3_WARPS + wib; it < n_items; it += gridDim.x * K3_WARPS)
+    {
+        const uint2  item = items[it];
+        const IbfDev f    = table[item.y];
+        for (uint32_t chunk = 0; chunk < f.n_chunks; ++chunk)
+            count_item<H, NP, false, 2>(f, item.x, chunk, hashes, hash_off, rel_cutoff, wo, s_row[wib], lane);
     }
 }
 
@@ -590,7 +633,8 @@ void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off
     uint64_t       want  = (items + K3_WARPS - 1) / K3_WARPS;
     const uint64_t full  = (uint64_t)sms * occ; // one resident wave, grid-stride inside
     const uint32_t grid  = (uint32_t)(want < full ? want : full);
-    kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, active, n_reads, rel_cutoff, tuples, cursor, cap, dense);
+    WorkOut wo{tuples, cursor, cap, dense, nullptr, nullptr, 0};
+    kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, active, n_reads, rel_cutoff, wo);
 }
 
 template <int H, int MODE>
@@ -641,6 +685,32 @@ void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *h
     if (n_reads == 0)
         return;
     dispatch_k3_h<0>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, nullptr, st);
+}
+
+void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *items, uint32_t n_items, const uint64_t *hashes, const uint64_t *hash_off,
+                       uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
+                       unsigned long long *items_cursor, uint64_t items_cap, cudaStream_t st)
+{
+    if (n_items == 0)
+        return;
+    WorkOut        wo{tuples, cursor, cap, nullptr, items_out, items_cursor, items_cap};
+    const uint32_t want = (n_items + K3_WARPS - 1) / K3_WARPS;
+    const uint32_t grid = want < 148u * 4u ? want : 148u * 4u;
+    const bool     small = max_hashes < 256;
+#define GNB_HIBF(HV)                                                                                                             \
+    if (small)                                                                                                                   \
+        k_hibf_count<HV, 8><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, rel_cutoff, wo);           \
+    else                                                                                                                         \
+        k_hibf_count<HV, 16><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, rel_cutoff, wo);
+    switch (hash_funs)
+    {
+    case 1: GNB_HIBF(1) break;
+    case 2: GNB_HIBF(2) break;
+    case 3: GNB_HIBF(3) break;
+    case 4: GNB_HIBF(4) break;
+    default: GNB_HIBF(5) break;
+    }
+#undef GNB_HIBF
 }
 
 void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n_reads, uint32_t max_hashes,

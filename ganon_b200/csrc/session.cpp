@@ -131,6 +131,10 @@ struct FilterRt
     DevBuf      d_single, d_bin_node, d_seg_off, d_segs;
     std::vector<double>   node_fpr;   // [n_level_targets] fpr of this filter's target for the node (0 if absent)
     std::vector<uint8_t>  node_multi; // [n_level_targets] 1: node's bins form several segments (partial tuples)
+    // HIBF: one IbfDev per sub-IBF (tables carved out of the shared device arrays above)
+    bool                  is_hibf = false;
+    std::vector<IbfDev>   ibf_table;
+    DevBuf                d_ibf_table, d_items_a, d_items_b, d_items_cursor;
     // per batch
     std::vector<uint64_t> tuples; // sorted by (read, node)
 };
@@ -265,6 +269,8 @@ struct gnb_session
     std::vector<uint8_t>  h_active;
     std::vector<uint8_t>  h_read_level;
     uint64_t              total_hashes = 0;
+    uint64_t              hibf_bytes = 0;
+    float                 hibf_ms = 0;
 
     // result storage
     std::vector<uint64_t>      r_match_off;
@@ -287,6 +293,10 @@ struct gnb_session
                 f.d_bin_node.release();
                 f.d_seg_off.release();
                 f.d_segs.release();
+                f.d_ibf_table.release();
+                f.d_items_a.release();
+                f.d_items_b.release();
+                f.d_items_cursor.release();
             }
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
                           &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status})
@@ -300,6 +310,8 @@ struct gnb_session
     }
 
     int  build_level_tables(LevelRt &L);
+    int  build_hibf_tables(LevelRt &L, FilterRt &F);
+    int  run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &produced);
     int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
     int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines);
     int  compute_hashes(uint32_t k, uint32_t w);
@@ -313,10 +325,136 @@ struct gnb_session
 // session creation: parse_hierarchy (GC.cpp:353-401), load_tax / merge_tax / validate_targets_tax (GC.cpp:988-1005,
 // 1324-1362), pre_process_lca (GC.cpp:1364-1371), bin -> node tables for K3
 // ---------------------------------------------------------------------------------------------------------------------
+// HIBF (HIBF.hpp:124-136, 176-188): per sub-IBF the same bin tables as a flat filter.  A merged bin is a "single" bin
+// whose node carries kMergedBinFlag | child; a user bin split over several technical bins becomes partial segments
+// (the host adds them with the reference's wrapping uint16 arithmetic, HIBF.hpp:437-441).
+int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
+{
+    const gnb_db &db = *F.db;
+    F.is_hibf = true;
+    F.node_fpr.assign(L.n_targets, 0.0);
+    F.node_multi.assign(L.n_targets, 0);
+    std::unordered_map<std::string, uint32_t> node_of;
+    for (uint32_t i = 0; i < L.n_targets; ++i)
+        node_of.emplace(L.node_names[i], i);
+    // select_matches(THIBF) looks at bins[0] of every target only (GC.cpp:553-556)
+    std::vector<uint32_t> node_of_user_bin(db.n_user_bins, 0xffffffffu);
+    for (size_t t = 0; t < db.target_names.size(); ++t)
+    {
+        const uint32_t node = node_of.at(db.target_names[t]);
+        F.node_fpr[node]    = db.target_fpr[t];
+        if (!db.target_bins[t].empty() && db.target_bins[t][0] < db.n_user_bins)
+            node_of_user_bin[db.target_bins[t][0]] = node;
+    }
+    std::vector<uint32_t> single, bin_node, seg_off;
+    std::vector<Seg>      segs;
+    struct Place
+    {
+        size_t single, bin_node, seg_off;
+        bool   has_seg;
+    };
+    std::vector<Place> place(db.ibfs.size());
+    F.ibf_table.resize(db.ibfs.size());
+    for (size_t i = 0; i < db.ibfs.size(); ++i)
+    {
+        const IbfHost &ibf = db.ibfs[i];
+        IbfDev        &d   = F.ibf_table[i];
+        d.data       = ibf.d_data;
+        d.bin_size   = ibf.bin_size;
+        d.hash_shift = (uint32_t)ibf.hash_shift;
+        d.hash_funs  = (uint32_t)ibf.hash_funs;
+        d.row_words  = (uint32_t)ibf.row_words();
+        d.n_chunks   = (d.row_words + 63) / 64;
+        if (d.hash_funs != F.ibf_table[0].hash_funs)
+            return fail(GNB_ERR_LIMIT, "sub-IBFs with different numbers of hash functions are not supported");
+        place[i] = Place{single.size(), bin_node.size(), seg_off.size(), false};
+        single.resize(single.size() + (size_t)d.n_chunks * 128, 0);
+        bin_node.resize(bin_node.size() + (size_t)d.n_chunks * 4096, 0);
+        uint32_t *sg = single.data() + place[i].single;
+        uint32_t *bn = bin_node.data() + place[i].bin_node;
+        std::vector<std::vector<Seg>> per_slot((size_t)d.n_chunks * 32);
+        const auto &pos = db.bin_to_user[i];
+        const auto &nxt = db.next_ibf_id[i];
+        for (uint64_t b = 0; b < ibf.bins;)
+        {
+            const int64_t fi = pos[b];
+            if (fi < 0)
+            { // merged bin
+                sg[b >> 5] |= 1u << (b & 31);
+                bn[b] = kMergedBinFlag | (uint32_t)nxt[b];
+                ++b;
+                continue;
+            }
+            uint64_t e = b + 1;
+            while (e < ibf.bins && pos[e] == fi)
+                ++e;
+            const uint32_t node = node_of_user_bin[(size_t)fi];
+            if (node != 0xffffffffu)
+            {
+                if (e - b == 1)
+                {
+                    sg[b >> 5] |= 1u << (b & 31);
+                    bn[b] = node;
+                }
+                else
+                {
+                    F.node_multi[node] = 1;
+                    std::map<uint64_t, uint32_t> regs;
+                    for (uint64_t x = b; x < e; ++x)
+                        regs[x >> 5] |= 1u << (x & 31);
+                    for (auto const &[rg, mask] : regs)
+                    {
+                        per_slot[rg >> 2].push_back(Seg{mask, node, (uint16_t)(rg & 3), 0});
+                        place[i].has_seg = true;
+                    }
+                }
+            }
+            b = e;
+        }
+        if (place[i].has_seg)
+        {
+            for (size_t sl = 0; sl < per_slot.size(); ++sl)
+            {
+                seg_off.push_back((uint32_t)segs.size());
+                segs.insert(segs.end(), per_slot[sl].begin(), per_slot[sl].end());
+            }
+            seg_off.push_back((uint32_t)segs.size());
+        }
+    }
+    GNB_TRY(F.d_single.ensure(single.size() * 4 + 4));
+    GNB_TRY(F.d_bin_node.ensure(bin_node.size() * 4 + 4));
+    GNB_TRY(F.d_seg_off.ensure(seg_off.size() * 4 + 4));
+    GNB_TRY(F.d_segs.ensure(segs.size() * sizeof(Seg) + 16));
+    GNB_CUDA(cudaMemcpy(F.d_single.p, single.data(), single.size() * 4, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(F.d_bin_node.p, bin_node.data(), bin_node.size() * 4, cudaMemcpyHostToDevice));
+    if (!seg_off.empty())
+        GNB_CUDA(cudaMemcpy(F.d_seg_off.p, seg_off.data(), seg_off.size() * 4, cudaMemcpyHostToDevice));
+    if (!segs.empty())
+        GNB_CUDA(cudaMemcpy(F.d_segs.p, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < db.ibfs.size(); ++i)
+    {
+        IbfDev &d     = F.ibf_table[i];
+        d.single_mask = F.d_single.as<uint32_t>() + place[i].single;
+        d.bin_node    = F.d_bin_node.as<uint32_t>() + place[i].bin_node;
+        d.seg_off     = place[i].has_seg ? F.d_seg_off.as<uint32_t>() + place[i].seg_off : nullptr;
+        d.segs        = F.d_segs.as<Seg>(); // seg_off entries are absolute indices into the shared array
+    }
+    GNB_TRY(F.d_ibf_table.ensure(F.ibf_table.size() * sizeof(IbfDev)));
+    GNB_CUDA(cudaMemcpy(F.d_ibf_table.p, F.ibf_table.data(), F.ibf_table.size() * sizeof(IbfDev), cudaMemcpyHostToDevice));
+    GNB_TRY(F.d_items_cursor.ensure(64));
+    F.dev = F.ibf_table[0];
+    return GNB_OK;
+}
+
 int gnb_session::build_level_tables(LevelRt &L)
 {
     for (auto &F : L.filters)
     {
+        if (F.db->is_hibf)
+        {
+            GNB_TRY(build_hibf_tables(L, F));
+            continue;
+        }
         const gnb_db  &db  = *F.db;
         const IbfHost &ibf = db.ibfs[0];
         IbfDev        &d   = F.dev;
@@ -582,8 +720,6 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
             }
             L.depth[i] = d;
         }
-        if (L.filters[0].db->is_hibf)
-            return fail(GNB_ERR_LIMIT, "HIBF classification is not available in this build");
         int rc = s->build_level_tables(L);
         if (rc != GNB_OK)
             return rc;
@@ -892,6 +1028,84 @@ int gnb_session::compute_hashes(uint32_t k, uint32_t w)
     return GNB_OK;
 }
 
+// HIBF traversal (counting_agent_type::bulk_count, HIBF.hpp:433-460, 506-523) as level-synchronous rounds over a
+// worklist of (read, sub-IBF) items; tuples accumulate in d_tuples_a across the rounds.
+int gnb_session::run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &produced_out)
+{
+    (void)act;
+    const uint32_t n = n_reads;
+    hibf_bytes = 0;
+    hibf_ms    = 0;
+    std::vector<uint2> items;
+    items.reserve(n);
+    for (uint32_t r = 0; r < n; ++r)
+        if (h_active[r] && h_counts[r] > 0 && h_counts[r] <= 65535)
+            items.push_back(make_uint2(r, 0));
+    uint64_t n_items = items.size();
+    GNB_TRY(F.d_items_a.ensure((n_items + 1024) * sizeof(uint2)));
+    GNB_TRY(F.d_items_b.ensure((n_items + 1024) * sizeof(uint2)));
+    if (n_items)
+        GNB_CUDA(cudaMemcpyAsync(F.d_items_a.p, items.data(), n_items * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    timing.h2d_bytes += n_items * sizeof(uint2);
+    GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
+    unsigned long long tuples_before = 0;
+    DevBuf *cur = &F.d_items_a, *nxt = &F.d_items_b;
+    std::vector<uint2> round_items; // only used for the byte accounting
+    while (n_items)
+    {
+        unsigned long long got_tuples = 0, got_items = 0;
+        for (int attempt = 0; attempt < 3; ++attempt)
+        {
+            const uint64_t cap = d_tuples_a.cap / 8, icap = nxt->cap / sizeof(uint2);
+            GNB_CUDA(cudaMemsetAsync(F.d_items_cursor.p, 0, 8, st));
+            GNB_CUDA(cudaMemcpyAsync(d_cursor.p, &tuples_before, 8, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaEventRecord(ev[4], st));
+            launch_hibf_round(F.d_ibf_table.as<IbfDev>(), F.dev.hash_funs, cur->as<uint2>(), (uint32_t)n_items, d_hashes.as<uint64_t>(),
+                              d_hash_off.as<uint64_t>(), std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff, d_tuples_a.as<uint64_t>(),
+                              d_cursor.as<unsigned long long>(), cap, nxt->as<uint2>(), F.d_items_cursor.as<unsigned long long>(), icap, st);
+            GNB_CUDA(cudaEventRecord(ev[5], st));
+            launches += 1;
+            GNB_CUDA(cudaMemcpyAsync(&got_tuples, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync(&got_items, F.d_items_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaStreamSynchronize(st));
+            GNB_CUDA(cudaGetLastError());
+            timing.d2h_bytes += 16;
+            float ms1 = 0;
+            cudaEventElapsedTime(&ms1, ev[4], ev[5]);
+            hibf_ms += ms1;
+            if (got_tuples <= cap && got_items <= icap)
+                break;
+            // a buffer was too small: the exact need is known now.  Tuples of earlier rounds must survive the growth.
+            if (got_tuples > cap)
+            {
+                DevBuf bigger;
+                GNB_TRY(bigger.ensure(got_tuples * 8));
+                if (tuples_before)
+                    GNB_CUDA(cudaMemcpyAsync(bigger.p, d_tuples_a.p, tuples_before * 8, cudaMemcpyDeviceToDevice, st));
+                GNB_CUDA(cudaStreamSynchronize(st));
+                d_tuples_a.release();
+                d_tuples_a = bigger;
+            }
+            if (got_items > icap)
+                GNB_TRY(nxt->ensure(got_items * sizeof(uint2)));
+        }
+        // algorithmic bytes of the round: every item reads n_hashes * h * row_words * 8 of its sub-IBF
+        {
+            round_items.resize(n_items);
+            GNB_CUDA(cudaMemcpy(round_items.data(), cur->p, n_items * sizeof(uint2), cudaMemcpyDeviceToHost));
+            for (auto const &it : round_items)
+                hibf_bytes += (uint64_t)h_counts[it.x] * F.ibf_table[it.y].hash_funs * F.ibf_table[it.y].row_words * 8;
+        }
+        tuples_before = got_tuples;
+        n_items       = got_items;
+        std::swap(cur, nxt);
+        if (n_items)
+            GNB_TRY(nxt->ensure(n_items * sizeof(uint2))); // the next round can at most... grow lazily on overflow
+    }
+    produced_out = tuples_before;
+    return GNB_OK;
+}
+
 // K3 (+ sort) for every filter of level li on the reads still active
 int gnb_session::run_level(size_t li)
 {
@@ -924,6 +1138,15 @@ int gnb_session::run_level(size_t li)
             cap = d_tuples_a.cap / 8;
         }
         unsigned long long produced = 0;
+        if (F.is_hibf)
+        {
+            uint64_t prod = 0;
+            GNB_TRY(run_hibf_filter(F, act, prod));
+            produced = prod;
+            timing.count_kernel_bytes += hibf_bytes;
+            ms_k3 += hibf_ms;
+        }
+        else
         for (int attempt = 0; attempt < 2; ++attempt)
         {
             GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
@@ -946,7 +1169,8 @@ int gnb_session::run_level(size_t li)
             GNB_TRY(d_tuples_a.ensure(produced * 8)); // exact size is now known: run again
             cap = d_tuples_a.cap / 8;
         }
-        timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.dev.row_words * 8;
+        if (!F.is_hibf)
+            timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.dev.row_words * 8;
         if (produced == 0)
             continue;
         GNB_CUDA(cudaEventRecord(ev[6], st));
@@ -1037,7 +1261,16 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
                         partial |= ((tp[c] >> 16) & 1) != 0;
                         ++c;
                     }
-                    if (partial)
+                    if (F.is_hibf)
+                    { // running sum of the counter type wraps (HIBF.hpp:437-441), then select_matches caps (GC.cpp:560-563)
+                        if (partial)
+                            sum &= 0xFFFF;
+                        if (sum < cutoff || sum == 0)
+                            continue;
+                        if (sum > nh)
+                            sum = nh;
+                    }
+                    else if (partial)
                     {
                         if (sum > nh)
                             sum = nh; // GC.cpp:525-526

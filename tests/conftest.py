@@ -33,4 +33,8 @@ def golden_dbs(tmp_path_factory):
         with gzip.open(os.path.join(GOLDEN, n + ".ibf.gz"), "rb") as fi, open(p, "wb") as fo:
             shutil.copyfileobj(fi, fo)
         out[n] = p
+    p = str(d / "synth.hibf")
+    with gzip.open(os.path.join(GOLDEN, "synth.hibf.gz"), "rb") as fi, open(p, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    out["synth_hibf"] = p
     return out

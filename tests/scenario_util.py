@@ -10,6 +10,11 @@ def load_scenarios():
         return json.load(f)
 
 
+def load_hibf_scenarios():
+    with open(os.path.join(GOLDEN, "scenarios_hibf.json")) as f:
+        return json.load(f)
+
+
 def expand(args, dbs):
     """Fill the {golden}/{tmp} placeholders; {tmp}/X.ibf -> decompressed fixture path."""
     out = []
@@ -17,6 +22,8 @@ def expand(args, dbs):
         a = a.replace("{golden}", GOLDEN)
         for n, p in dbs.items():
             a = a.replace("{tmp}/%s.ibf" % n, p)
+        if "synth_hibf" in dbs:
+            a = a.replace("{tmp}/synth.hibf", dbs["synth_hibf"])
         out.append(a)
     return out
 
@@ -35,6 +42,9 @@ def parse_args(argv):
                 v = [float(x) for x in v]
             cfg[names[a]] = v
             i += 2
+        elif a == "--hibf":
+            cfg["flags"].add(a)
+            i += 1
         else:
             cfg["flags"].add(a)
             i += 1

@@ -277,3 +277,35 @@ def test_device_and_host_record_index_agree(golden_dbs, tmp_path, monkeypatch):
         sess.close()
     assert res_all[0] == res_all[1]
     assert res_all[0][1] == SU.expected_lines("pe_synth_all", "all")
+
+
+# ------------------------------------------------------------------------------------------------------------------ HIBF
+def test_hibf_sub_ibf_counts_match_oracle(golden_dbs):
+    h = formats.read_hibf(golden_dbs["synth_hibf"])
+    db = Database.open(golden_dbs["synth_hibf"], hibf=True)
+    assert db.info().n_ibfs == len(h.ibfs) and db.info().is_hibf == 1
+    rng = np.random.default_rng(8)
+    lists = [rng.integers(0, 1 << 38, size=int(n), dtype=np.uint64) for n in (0, 1, 5, 17, 40)]
+    off = np.zeros(len(lists) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([x.size for x in lists])
+    L = _lib.lib()
+    for idx in (0, 1, len(h.ibfs) - 1):
+        i = h.ibfs[idx]
+        o = O.OracleIBF(i.bins, i.bin_size, i.hash_funs, i.data)
+        got = np.zeros((len(lists), i.technical_bins), dtype=np.uint16)
+        hs = np.concatenate(lists)
+        _lib.check(L.gnb_db_bulk_count(db.handle, idx, hs.ctypes.data, off.ctypes.data, len(lists), got.ctypes.data))
+        for j, x in enumerate(lists):
+            assert np.array_equal(got[j], o.bulk_count(x)), (idx, j)
+
+
+@pytest.mark.parametrize("name", sorted(SU.load_hibf_scenarios()))
+def test_hibf_scenarios_match_reference_outputs(name, golden_dbs, tmp_path):
+    args = SU.expand(SU.load_hibf_scenarios()[name], golden_dbs)
+    pre = str(tmp_path / name)
+    assert cli.main(args + ["-o", pre, "-t", "4", "--quiet"]) == 0
+    want_files = sorted(os.path.basename(p)[len(name) :] for p in glob.glob(os.path.join(SU.GOLDEN, "expected", name + ".*")))
+    got_files = sorted(os.path.basename(p)[len(name) :] for p in glob.glob(pre + ".*"))
+    assert got_files == want_files
+    for ext in want_files:
+        assert _read_sorted(pre + ext) == SU.expected_lines(name, ext[1:]), ext

@@ -106,3 +106,32 @@ def test_oracle_matches_reference_outputs(name, golden_dbs):
         mine = sorted(sum((O.all_lines(per_level[lab]) for lab in labels), []))
         assert mine == SU.expected_lines(name, "all")
     assert unc == SU.expected_lines(name, "unc")
+
+
+# ---- HIBF: the oracle's traversal (go_hibf_bulk_count) against `ganon-classify --hibf` outputs (make_golden_hibf.py)
+def _oracle_hibf_filter(path, rel_cutoff):
+    h = formats.read_hibf(path)
+    ibfs = [O.OracleIBF(i.bins, i.bin_size, i.hash_funs, i.data) for i in h.ibfs]
+    oh = O.OracleHIBF(ibfs, h.next_ibf_id, h.bin_to_user, len(h.bin_path))
+    tmap = {}
+    for u, paths in enumerate(h.bin_path):
+        for p in paths:
+            tmap.setdefault(formats.hibf_target_name(p), []).append(u)
+    targets = list(tmap)
+    return O.OracleFilter(oh, targets, [tmap[t] for t in targets], [h.fpr] * len(targets), rel_cutoff, h.kmer_size, h.window_size)
+
+
+@pytest.mark.parametrize("name", sorted(SU.load_hibf_scenarios()))
+def test_oracle_hibf_matches_reference_outputs(name, golden_dbs):
+    args = SU.expand(SU.load_hibf_scenarios()[name], golden_dbs)
+    cfg = SU.parse_args(args)
+    reads = []
+    for f in cfg["single"]:
+        reads += [(i, s, None) for i, s in O.parse_reads(f)]
+    for a, b in zip(cfg["paired"][0::2], cfg["paired"][1::2]):
+        reads += [(x[0], x[1], y[1]) for x, y in zip(O.parse_reads(a), O.parse_reads(b))]
+    (lab, lev), = cfg["levels"]
+    filt = _oracle_hibf_filter(lev["filters"][0][0], lev["filters"][0][1])
+    res = O.classify_level([filt], reads, lev["rel_filter"], lev["fpr_query"])
+    assert O.all_lines(res) == SU.expected_lines(name, "all")
+    assert sorted(r["id"].decode() for r in res if not r["matches"]) == SU.expected_lines(name, "unc")
