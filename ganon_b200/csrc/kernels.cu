@@ -534,7 +534,7 @@ __device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint3
         }
         const uint32_t     total = __shfl_sync(0xffffffffu, incl, 31);
         unsigned long long start = 0;
-        if (lane == 0)
+        if (MODE != 2 && lane == 0)
             start = atomicAdd(cursor, (unsigned long long)total);
         start = __shfl_sync(0xffffffffu, start, 0);
         uint64_t pos = start + (incl - mine);
@@ -546,8 +546,25 @@ __device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint3
             {
                 const uint32_t b = __ffs(m) - 1;
                 m &= m - 1;
+                const uint32_t node = f.bin_node[(uint32_t)w0 * 64 + r * 32 + b];
+                if (MODE == 2)
+                {
+                    if (node & kMergedBin)
+                    { // descend: the child IBF is queried with the full hash list (HIBF.hpp:447-451)
+                        const unsigned long long ip = atomicAdd(wo.items_cursor, 1ULL);
+                        if (ip < wo.items_cap)
+                            wo.items[ip] = make_uint2(read, node & ~kMergedBin);
+                    }
+                    else
+                    {
+                        const unsigned long long tp = atomicAdd(cursor, 1ULL);
+                        if (tp < cap)
+                            tuples[tp] = make_tuple64(read, node, 0, sliced_get<NP>(P, r, b));
+                    }
+                    continue;
+                }
                 if (pos < cap)
-                    tuples[pos] = make_tuple64(read, f.bin_node[(uint32_t)w0 * 64 + r * 32 + b], 0, sliced_get<NP>(P, r, b));
+                    tuples[pos] = make_tuple64(read, node, 0, sliced_get<NP>(P, r, b));
                 ++pos;
             }
         }
