@@ -119,6 +119,7 @@ SYMBOLS = {
     "gnb_db_target": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gnb_db_free": (None, [_P]),
     "gnb_db_create": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(_P)]),
+    "gnb_db_create_sharded": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "gnb_db_fill_random": (C.c_int, [_P, C.c_uint64, C.c_int]),
     "gnb_db_emplace": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gnb_db_set_targets": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), _P, _P, C.c_uint64]),
@@ -133,6 +134,16 @@ SYMBOLS = {
     "gnb_session_stage": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "gnb_session_run_staged": (C.c_int, [_P, C.POINTER(BatchResult)]),
     "gnb_session_finish_staged": (C.c_int, [_P, C.c_uint32, C.POINTER(BatchResult)]),
+    "gnb_session_submit": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.POINTER(BatchResult)]),
+    "gnb_session_collect": (C.c_int, [_P, C.POINTER(BatchResult)]),
+    "gnb_session_in_flight": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "gnb_session_run_level": (C.c_int, [_P, C.c_uint32]),
+    "gnb_session_level_tuples": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "gnb_session_set_level_tuples": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
+    "gnb_session_finish_level": (C.c_int, [_P, C.c_uint32]),
+    "gnb_session_collect_staged": (C.c_int, [_P, C.c_uint32, C.POINTER(BatchResult)]),
+    "gnb_host_register": (C.c_int, [_P, C.c_uint64]),
+    "gnb_host_unregister": (C.c_int, [_P]),
     "gnb_session_level_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "gnb_session_level_label": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_char_p)]),
     "gnb_session_node_name": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p)]),

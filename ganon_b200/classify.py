@@ -45,9 +45,9 @@ class Database:
         return cls(h.value)
 
     @classmethod
-    def create(cls, bins: int, bin_size_bits: int, hash_functions: int, kmer_size: int, window_size: int, device: int = 0) -> "Database":
+    def create(cls, bins: int, bin_size_bits: int, hash_functions: int, kmer_size: int, window_size: int, device: int = 0, shard: int = 0, n_shards: int = 1) -> "Database":
         h = C.c_void_p()
-        check(_lib.lib().gnb_db_create(bins, bin_size_bits, hash_functions, kmer_size, window_size, device, C.byref(h)))
+        check(_lib.lib().gnb_db_create_sharded(bins, bin_size_bits, hash_functions, kmer_size, window_size, device, shard, n_shards, C.byref(h)))
         return cls(h.value)
 
     @property
@@ -217,6 +217,7 @@ class Session:
         for i in range(n_levels.value):
             check(_lib.lib().gnb_session_level_label(self._h, i, C.byref(lab)))
             self.level_labels.append(lab.value.decode())
+        self._filters_per_level = [sum(1 for x in labels if x == l) for l in self.level_labels]
 
     @staticmethod
     def _ptr(buf, n=None):
@@ -259,6 +260,55 @@ class Session:
         res = BatchResult()
         check(_lib.lib().gnb_session_finish_staged(self._h, prefix_id, C.byref(res)))
         return res
+
+    def submit(self, block1, block2=None, final: bool = True, prefix_id: int = 0, len1: Optional[int] = None, len2: Optional[int] = None) -> BatchResult:
+        """Asynchronous classify: returns the staging info (n_reads, consumed1/2, parse_error); see collect()."""
+        p1, n1 = self._ptr(block1, len1)
+        p2, n2 = self._ptr(block2, len2)
+        info = BatchResult()
+        check(_lib.lib().gnb_session_submit(self._h, prefix_id, p1, n1, p2, n2, int(final), C.byref(info)))
+        return info
+
+    def collect(self) -> BatchResult:
+        res = BatchResult()
+        check(_lib.lib().gnb_session_collect(self._h, C.byref(res)))
+        return res
+
+    def in_flight(self) -> Tuple[int, int]:
+        n, cap = C.c_uint32(), C.c_uint32()
+        check(_lib.lib().gnb_session_in_flight(self._h, C.byref(n), C.byref(cap)))
+        return n.value, cap.value
+
+    # level-wise form (bin-sharded multi-GPU, see ganon_b200/sharded.py)
+    def run_level(self, level: int) -> None:
+        check(_lib.lib().gnb_session_run_level(self._h, level))
+
+    def level_tuples(self, level: int, filt: int):
+        import numpy as np
+
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().gnb_session_level_tuples(self._h, level, filt, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.empty(0, dtype=np.uint64)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n.value,)).copy()
+
+    def set_level_tuples(self, level: int, filt: int, tuples) -> None:
+        import numpy as np
+
+        t = np.ascontiguousarray(tuples, dtype=np.uint64)
+        check(_lib.lib().gnb_session_set_level_tuples(self._h, level, filt, t.ctypes.data, t.size))
+
+    def finish_level(self, level: int) -> None:
+        check(_lib.lib().gnb_session_finish_level(self._h, level))
+
+    def collect_staged(self, prefix_id: int = 0) -> BatchResult:
+        res = BatchResult()
+        check(_lib.lib().gnb_session_collect_staged(self._h, prefix_id, C.byref(res)))
+        return res
+
+    @property
+    def n_filters_per_level(self) -> List[int]:
+        return self._filters_per_level
 
     def node_name(self, level: int, node: int) -> str:
         s = C.c_char_p()
@@ -393,36 +443,68 @@ class GanonClassifyConfig:
 
 
 class _ReadStream:
-    """A read file (plain or gzip, by magic) consumed in blocks; the unconsumed tail is carried to the next block."""
+    """A read file (plain or gzip, by magic) consumed in blocks.  Blocks live in a ring of page-locked buffers (a block
+    must stay untouched while its batch is in flight); the unconsumed tail of a block is copied to the next one."""
 
-    def __init__(self, path: str, block_bytes: int):
+    def __init__(self, path: str, block_bytes: int, n_buffers: int):
         with open(path, "rb") as f:
             magic = f.read(2)
         self.f = gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb", buffering=0)
-        self.buf = bytearray(block_bytes)
+        self.bufs = [bytearray(block_bytes) for _ in range(n_buffers)]
+        self.pinned = []
+        self._pin()
+        self.cur = -1
         self.fill = 0
+        self.tail = b""
         self.eof = False
 
-    def load(self) -> None:
-        mv = memoryview(self.buf)
-        while self.fill < len(self.buf) and not self.eof:
-            n = self.f.readinto(mv[self.fill :])
-            if not n:
+    def _pin(self) -> None:
+        for b in self.bufs:
+            if id(b) in [i for i, _ in self.pinned]:
+                continue
+            arr = (C.c_char * len(b)).from_buffer(b)
+            if _lib.lib().gnb_host_register(C.cast(arr, C.c_void_p), len(b)) == 0:
+                self.pinned.append((id(b), arr))  # keeps the export alive: the bytearray cannot be resized while pinned
+
+    def _unpin(self) -> None:
+        for _i, arr in self.pinned:
+            _lib.lib().gnb_host_unregister(C.cast(arr, C.c_void_p))
+        self.pinned = []
+
+    @property
+    def buf(self) -> bytearray:
+        return self.bufs[self.cur]
+
+    def next_block(self) -> None:
+        """Move to the next ring buffer: tail of the previous block first, then fresh bytes from the file."""
+        self.cur = (self.cur + 1) % len(self.bufs)
+        buf = self.bufs[self.cur]
+        n = len(self.tail)
+        buf[:n] = self.tail
+        self.fill = n
+        mv = memoryview(buf)
+        while self.fill < len(buf) and not self.eof:
+            got = self.f.readinto(mv[self.fill :])
+            if not got:
                 self.eof = True
             else:
-                self.fill += n
+                self.fill += got
+        mv.release()
 
     def consume(self, n: int) -> None:
-        rest = self.fill - n
-        if rest:
-            self.buf[:rest] = self.buf[n : self.fill]
-        self.fill = rest
+        self.tail = bytes(self.buf[n : self.fill])
 
     def grow(self) -> None:
-        self.buf.extend(bytearray(len(self.buf)))
+        """Not a single complete record fitted: double the block size (the whole block becomes the tail)."""
+        self._unpin()
+        size = 2 * len(self.bufs[0])
+        self.bufs = [bytearray(size) for _ in self.bufs]
+        self._pin()
+        self.cur = -1
 
     def close(self) -> None:
         self.f.close()
+        self._unpin()
 
 
 def _parse_reads_config(cfg: GanonClassifyConfig) -> Optional[Dict[str, List[Tuple[str, str]]]]:
@@ -517,43 +599,52 @@ def run(cfg: GanonClassifyConfig) -> bool:
     out_all = level_files("all") if cfg.output_all else {}
     out_one = level_files("one") if write_one else {}
 
+    def write_result(prefix: str, res: BatchResult) -> None:
+        for li in range(len(labels)):
+            if cfg.output_all and res.all_len[li]:
+                out_all[prefix][li].write(C.string_at(res.all_text[li], res.all_len[li]))
+            if write_one and res.one_len[li]:
+                out_one[prefix][li].write(C.string_at(res.one_text[li], res.one_len[li]))
+        if cfg.output_unclassified and res.unc_len:
+            out_unc[prefix].write(C.string_at(res.unc_text, res.unc_len))
+
     t_class = time.time()
+    _n, capacity = sess.in_flight()
+    pending: List[str] = []  # prefixes of the batches in flight, oldest first
     for pid, prefix in enumerate(prefixes):
         for file1, file2 in reads_config[prefix]:
-            s1 = _ReadStream(file1, BLOCK_BYTES)
-            s2 = _ReadStream(file2, BLOCK_BYTES) if file2 else None
+            s1 = _ReadStream(file1, BLOCK_BYTES, capacity + 2)
+            s2 = _ReadStream(file2, BLOCK_BYTES, capacity + 2) if file2 else None
             try:
                 while True:
-                    s1.load()
+                    s1.next_block()
                     if s2:
-                        s2.load()
+                        s2.next_block()
                     final = s1.eof and (s2 is None or s2.eof)
-                    if s1.fill == 0 and (s2 is None or s2.fill == 0):
-                        break
-                    if s2 is not None and (s1.fill == 0 or s2.fill == 0):
-                        break  # one mate file ended early: nothing more to pair
-                    res = sess.classify(s1.buf, s2.buf if s2 else None, final=final, prefix_id=pid, len1=s1.fill, len2=s2.fill if s2 else 0)
-                    for li in range(len(labels)):
-                        if cfg.output_all and res.all_len[li]:
-                            out_all[prefix][li].write(C.string_at(res.all_text[li], res.all_len[li]))
-                        if write_one and res.one_len[li]:
-                            out_one[prefix][li].write(C.string_at(res.one_text[li], res.one_len[li]))
-                    if cfg.output_unclassified and res.unc_len:
-                        out_unc[prefix].write(C.string_at(res.unc_text, res.unc_len))
-                    if res.parse_error:
+                    if s1.fill == 0 or (s2 is not None and s2.fill == 0):
+                        break  # nothing (more) to pair
+                    info = sess.submit(s1.buf, s2.buf if s2 else None, final=final, prefix_id=pid, len1=s1.fill, len2=s2.fill if s2 else 0)
+                    pending.append(prefix)
+                    if len(pending) > capacity - 1 or info.parse_error or final or info.n_reads == 0:
+                        while len(pending) > (0 if (info.parse_error or final or info.n_reads == 0) else capacity - 1):
+                            write_result(pending.pop(0), sess.collect())
+                    if info.parse_error:
                         break  # rest of the file is skipped (GC.cpp:1278-1283)
-                    if res.n_reads == 0 and not final:
-                        # not a single complete record in the block: enlarge it
+                    if info.n_reads == 0 and not final:
+                        s1.tail = bytes(s1.buf[: s1.fill])
                         s1.grow()
                         if s2:
+                            s2.tail = bytes(s2.buf[: s2.fill])
                             s2.grow()
                         continue
-                    s1.consume(res.consumed1)
+                    s1.consume(info.consumed1)
                     if s2:
-                        s2.consume(res.consumed2)
+                        s2.consume(info.consumed2)
                     if final:
                         break
             finally:
+                while pending:
+                    write_result(pending.pop(0), sess.collect())
                 s1.close()
                 if s2:
                     s2.close()

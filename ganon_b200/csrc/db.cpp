@@ -454,7 +454,13 @@ extern "C" int gnb_db_target(const gnb_db *db, uint64_t i, const char **name, do
 extern "C" int gnb_db_create(uint64_t bins, uint64_t bin_size_bits, uint32_t hash_functions, uint32_t kmer_size, uint32_t window_size,
                              int device, gnb_db **out)
 {
-    if (!out || bins == 0 || bin_size_bits == 0 || hash_functions < 1 || hash_functions > 5 || kmer_size < 1 || kmer_size > 32 ||
+    return gnb_db_create_sharded(bins, bin_size_bits, hash_functions, kmer_size, window_size, device, 0, 1, out);
+}
+
+extern "C" int gnb_db_create_sharded(uint64_t bins, uint64_t bin_size_bits, uint32_t hash_functions, uint32_t kmer_size, uint32_t window_size,
+                                     int device, int shard, int n_shards, gnb_db **out)
+{
+    if (!out || n_shards < 1 || shard < 0 || shard >= n_shards || bins == 0 || bin_size_bits == 0 || hash_functions < 1 || hash_functions > 5 || kmer_size < 1 || kmer_size > 32 ||
         window_size < kmer_size)
         return fail(GNB_ERR_ARG, "gnb_db_create: bad arguments"); // IBF.hpp:227-236
     GNB_CUDA(cudaSetDevice(device));
@@ -471,8 +477,10 @@ extern "C" int gnb_db_create(uint64_t bins, uint64_t bin_size_bits, uint32_t has
     t.bin_size       = bin_size_bits;
     t.hash_shift     = (uint64_t)__builtin_clzll(bin_size_bits);
     t.hash_funs      = hash_functions;
-    t.w0             = 0;
-    t.w1             = t.bin_words;
+    t.w0             = t.bin_words * (uint64_t)shard / (uint64_t)n_shards;
+    t.w1             = t.bin_words * (uint64_t)(shard + 1) / (uint64_t)n_shards;
+    if (t.w1 <= t.w0)
+        return fail(GNB_ERR_ARG, "more shards than bin-words");
     GNB_CUDA(cudaMalloc((void **)&t.d_data, t.device_bytes()));
     GNB_CUDA(cudaMemset(t.d_data, 0, t.device_bytes()));
     // default map: one target per bin, "T<bin>"
@@ -492,9 +500,7 @@ extern "C" int gnb_db_fill_random(gnb_db *db, uint64_t seed, int and_terms)
         return fail(GNB_ERR_ARG, "gnb_db_fill_random: bad arguments");
     GNB_CUDA(cudaSetDevice(db->device));
     IbfHost &t = db->ibfs[0];
-    if (t.w0 != 0 || t.w1 != t.bin_words)
-        return fail(GNB_ERR_ARG, "gnb_db_fill_random: sharded handle");
-    launch_fill_random(t.d_data, t.bin_size * t.bin_words, (uint32_t)t.bin_words, t.bins, seed, and_terms, 0);
+    launch_fill_random(t.d_data, t.bin_size, (uint32_t)t.row_words(), (uint32_t)t.w0, (uint32_t)t.bin_words, t.bins, seed, and_terms, 0);
     GNB_CUDA(cudaGetLastError());
     GNB_CUDA(cudaDeviceSynchronize());
     return GNB_OK;
@@ -517,7 +523,7 @@ extern "C" int gnb_db_emplace(gnb_db *db, const uint64_t *hashes, const uint32_t
     GNB_CUDA(cudaMalloc((void **)&d_b, n * 4));
     GNB_CUDA(cudaMemcpy(d_h, hashes, n * 8, cudaMemcpyHostToDevice));
     GNB_CUDA(cudaMemcpy(d_b, bins, n * 4, cudaMemcpyHostToDevice));
-    launch_emplace(t.d_data, t.bin_size, (uint32_t)t.hash_shift, (uint32_t)t.hash_funs, (uint32_t)t.bin_words, d_h, d_b, n, 0);
+    launch_emplace(t.d_data, t.bin_size, (uint32_t)t.hash_shift, (uint32_t)t.hash_funs, (uint32_t)t.row_words(), (uint32_t)t.w0, d_h, d_b, n, 0);
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(d_h);
     cudaFree(d_b);

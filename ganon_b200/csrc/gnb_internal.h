@@ -135,8 +135,9 @@ constexpr uint32_t kMergedBinFlag = 0x80000000u;
 size_t sort_tmp_bytes(uint64_t n);
 void   launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 // build-side
-void launch_fill_random(uint64_t *data, uint64_t n_words, uint32_t row_words, uint64_t bins, uint64_t seed, int and_terms, cudaStream_t st);
-void launch_emplace(uint64_t *data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words,
+void launch_fill_random(uint64_t *data, uint64_t rows, uint32_t row_words, uint32_t w0, uint32_t total_words, uint64_t bins, uint64_t seed,
+                        int and_terms, cudaStream_t st);
+void launch_emplace(uint64_t *data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words, uint32_t w0,
                     const uint64_t *hashes, const uint32_t *bins, uint64_t n, cudaStream_t st);
 // K1: FASTQ record index on the device (strict 4-line records); see kernels.cu
 struct FastqIndexOut

@@ -760,24 +760,28 @@ void launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp
 // =====================================================================================================================
 namespace
 {
-__global__ void k_fill_random(uint64_t *__restrict__ data, uint64_t n_words, uint32_t row_words, uint64_t bins, uint64_t seed, int and_terms)
+__global__ void k_fill_random(uint64_t *__restrict__ data, uint64_t rows, uint32_t row_words, uint32_t w0, uint32_t total_words, uint64_t bins,
+                              uint64_t seed, int and_terms)
 {
+    // word (row, w) of the whole filter has index row*total_words + w; a shard holds columns [w0, w0+row_words)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride)
+    const uint64_t n      = rows * row_words;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
     {
-        uint64_t v = ~0ULL;
+        const uint64_t row = j / row_words, w = w0 + (j - row * row_words);
+        const uint64_t i   = row * total_words + w;
+        uint64_t       v   = ~0ULL;
         for (int t = 0; t < and_terms; ++t)
             v &= splitmix64(seed + i * 8 + (uint64_t)t);
-        // padding bins [bins, 64*row_words) stay zero (IBF.hpp:238-240)
-        const uint64_t w   = i % row_words;
-        const uint64_t lo  = w * 64;
+        // padding bins [bins, 64*total_words) stay zero (IBF.hpp:238-240)
+        const uint64_t lo = w * 64;
         if (lo + 64 > bins)
             v &= (lo >= bins) ? 0ULL : ((1ULL << (bins - lo)) - 1);
-        data[i] = v;
+        data[j] = v;
     }
 }
 
-__global__ void k_emplace(uint64_t *__restrict__ data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words,
+__global__ void k_emplace(uint64_t *__restrict__ data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words, uint32_t w0,
                           const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ bins, uint64_t n)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -785,24 +789,28 @@ __global__ void k_emplace(uint64_t *__restrict__ data, uint64_t bin_size, uint32
         return;
     const uint64_t m  = i / hash_funs;
     const uint32_t fn = (uint32_t)(i - m * hash_funs);
+    const uint32_t b  = bins[m];
+    const uint32_t w  = b >> 6;
+    if (w < w0 || w >= w0 + row_words) // bin lives in another shard
+        return;
     const uint64_t row = ibf_row(hashes[m], ibf_seed(fn), hash_shift, bin_size);
-    const uint32_t b   = bins[m];
-    atomicOr((unsigned long long *)(data + row * row_words + (b >> 6)), 1ULL << (b & 63));
+    atomicOr((unsigned long long *)(data + row * row_words + (w - w0)), 1ULL << (b & 63));
 }
 } // namespace
 
-void launch_fill_random(uint64_t *data, uint64_t n_words, uint32_t row_words, uint64_t bins, uint64_t seed, int and_terms, cudaStream_t st)
+void launch_fill_random(uint64_t *data, uint64_t rows, uint32_t row_words, uint32_t w0, uint32_t total_words, uint64_t bins, uint64_t seed,
+                        int and_terms, cudaStream_t st)
 {
-    k_fill_random<<<148 * 16, 256, 0, st>>>(data, n_words, row_words, bins, seed, and_terms);
+    k_fill_random<<<148 * 16, 256, 0, st>>>(data, rows, row_words, w0, total_words, bins, seed, and_terms);
 }
 
-void launch_emplace(uint64_t *data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words, const uint64_t *hashes,
-                    const uint32_t *bins, uint64_t n, cudaStream_t st)
+void launch_emplace(uint64_t *data, uint64_t bin_size, uint32_t hash_shift, uint32_t hash_funs, uint32_t row_words, uint32_t w0,
+                    const uint64_t *hashes, const uint32_t *bins, uint64_t n, cudaStream_t st)
 {
     if (n == 0)
         return;
     const uint64_t threads = n * hash_funs;
-    k_emplace<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(data, bin_size, hash_shift, hash_funs, row_words, hashes, bins, n);
+    k_emplace<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(data, bin_size, hash_shift, hash_funs, row_words, w0, hashes, bins, n);
 }
 
 // =====================================================================================================================

@@ -13,9 +13,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <thread>
 #include <unordered_map>
@@ -134,9 +136,7 @@ struct FilterRt
     // HIBF: one IbfDev per sub-IBF (tables carved out of the shared device arrays above)
     bool                  is_hibf = false;
     std::vector<IbfDev>   ibf_table;
-    DevBuf                d_ibf_table, d_items_a, d_items_b, d_items_cursor;
-    // per batch
-    std::vector<uint64_t> tuples; // sorted by (read, node)
+    DevBuf                d_ibf_table;
 };
 
 struct LevelRt
@@ -233,19 +233,49 @@ inline void append_u64(std::string &s, uint64_t v)
 
 using namespace gnb;
 
+struct BatchCtx;
+
+// Shared, read-mostly state of a classification run: configuration, levels with their device tables, accounting.
 struct gnb_session
 {
-    gnb_session_config cfg{};
-    int                device = 0;
-    bool               skip_lca = false, quiet = false;
-    std::string        tax_root = "1";
-    uint32_t           n_reads_chunk = 400;
+    gnb_session_config   cfg{};
+    int                  device = 0;
+    bool                 skip_lca = false, quiet = false;
+    std::string          tax_root = "1";
+    uint32_t             n_reads_chunk = 400;
     std::vector<LevelRt> levels;
-    cudaStream_t       st = nullptr;
-    bool               own_stream = true;
-    cudaEvent_t        ev[12]{};
-    int                n_threads = 1;
-    std::vector<Worker> workers;
+    bool                 use_device_index = true; // K1 first, host reader when the block is not strict 4-line FASTQ
+    int                  n_threads = 1;
+    uint64_t             file_records = 0; // records taken from the current file so far (parse-error truncation rule)
+    std::mutex           acc_mutex;        // guards LevelRt::rep / total
+    std::vector<std::unique_ptr<BatchCtx>> slots;
+    std::deque<int>      in_flight;        // slots with a submitted batch, oldest first
+    int                  holding = -1;     // slot whose result buffers the caller may still be reading
+    std::string          report_text, stats_text;
+
+    ~gnb_session();
+    int  build_level_tables(LevelRt &L);
+    int  build_hibf_tables(LevelRt &L, FilterRt &F);
+    void ensure_prefix(uint32_t prefix_id);
+    int  acquire_slot();
+};
+
+// One batch in flight: its own stream, device buffers, host finishing workers and result storage.  Several of these
+// overlap (H2D of batch i+1 | kernels of batch i | host finishing of batch i-1).
+struct BatchCtx
+{
+    gnb_session          *S;
+    std::vector<LevelRt> &levels;
+    gnb_session_config   &cfg;
+    int                   device;
+    bool                  skip_lca, quiet;
+    uint32_t              n_reads_chunk;
+    int                   n_threads;
+    bool                  use_device_index;
+    cudaStream_t          st = nullptr;
+    bool                  own_stream = true;
+    cudaEvent_t           ev[12]{};
+    std::vector<Worker>   workers;
 
     // staged batch
     const char *blk1 = nullptr, *blk2 = nullptr;
@@ -253,17 +283,15 @@ struct gnb_session
     bool        paired = false, final_block = false;
     RecTable    t1, t2;
     uint32_t    n_reads = 0;
-    uint64_t    file_records = 0; // records taken from the current file so far (parse-error truncation rule)
     bool        parse_error = false;
     bool        staged = false, ran = false;
     uint32_t    hashed_k = 0, hashed_w = 0; // (k, w) the device hash list was computed for
     uint32_t    max_hashes_ub = 0;
-    bool        use_device_index = true; // K1 first, host reader when the block is not strict 4-line FASTQ
     const uint32_t *p_idoff = nullptr, *p_idlen = nullptr, *p_slen1 = nullptr, *p_slen2 = nullptr;
     uint64_t    consumed1 = 0, consumed2 = 0;
 
     DevBuf d_blk1, d_blk2, d_off1, d_len1, d_off2, d_len2, d_idoff, d_idlen, d_counts, d_hash_off, d_hashes, d_active, d_tuples_a, d_tuples_b,
-        d_cursor, d_tmp, d_lines1, d_lines2, d_k1tmp1, d_k1tmp2, d_idoff2, d_idlen2, d_status;
+        d_cursor, d_tmp, d_lines1, d_lines2, d_k1tmp1, d_k1tmp2, d_idoff2, d_idlen2, d_status, d_items_a, d_items_b, d_items_cursor;
     PinBuf h_pin;
     std::vector<uint32_t> h_counts;
     std::vector<uint8_t>  h_active;
@@ -271,6 +299,7 @@ struct gnb_session
     uint64_t              total_hashes = 0;
     uint64_t              hibf_bytes = 0;
     float                 hibf_ms = 0;
+    std::vector<std::vector<std::vector<uint64_t>>> tuples; // [level][filter], sorted by (read, node)
 
     // result storage
     std::vector<uint64_t>      r_match_off;
@@ -279,27 +308,33 @@ struct gnb_session
     std::string                r_unc;
     std::vector<const char *>  r_all_p, r_one_p;
     std::vector<uint64_t>      r_all_l, r_one_l;
-    std::string                report_text, stats_text;
     gnb_batch_result           timing{};
+    gnb_batch_result           result{};
     uint64_t                   launches = 0;
 
-    ~gnb_session()
+    // asynchronous job (gnb_session_submit / gnb_session_collect)
+    std::thread job;
+    bool        busy = false;
+    int         job_rc = GNB_OK;
+    std::string job_err;
+    Clock::time_point t_submit;
+
+    BatchCtx(gnb_session *s)
+        : S(s), levels(s->levels), cfg(s->cfg), device(s->device), skip_lca(s->skip_lca), quiet(s->quiet), n_reads_chunk(s->n_reads_chunk),
+          n_threads(s->n_threads), use_device_index(s->use_device_index)
     {
+        tuples.resize(levels.size());
+        for (size_t li = 0; li < levels.size(); ++li)
+            tuples[li].resize(levels[li].filters.size());
+    }
+    ~BatchCtx()
+    {
+        if (job.joinable())
+            job.join();
         cudaSetDevice(device);
-        for (auto &l : levels)
-            for (auto &f : l.filters)
-            {
-                f.d_single.release();
-                f.d_bin_node.release();
-                f.d_seg_off.release();
-                f.d_segs.release();
-                f.d_ibf_table.release();
-                f.d_items_a.release();
-                f.d_items_b.release();
-                f.d_items_cursor.release();
-            }
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
-                          &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status})
+                          &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status,
+                          &d_items_a, &d_items_b, &d_items_cursor})
             b->release();
         h_pin.release();
         for (auto &e : ev)
@@ -308,18 +343,60 @@ struct gnb_session
         if (st && own_stream)
             cudaStreamDestroy(st);
     }
+    int init(cudaStream_t external);
 
-    int  build_level_tables(LevelRt &L);
-    int  build_hibf_tables(LevelRt &L, FilterRt &F);
-    int  run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &produced);
+    int  run_hibf_filter(size_t li, size_t fi, uint64_t &produced);
     int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
     int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines);
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
-    int  finish_level(size_t li, uint32_t prefix_id);
+    int  finish_level(size_t li);
+    void begin_finish();
+    int  collect(uint32_t prefix_id, gnb_batch_result *out);
     int  finish(uint32_t prefix_id, gnb_batch_result *out);
-    void ensure_prefix(uint32_t prefix_id);
+    void fill_timings(gnb_batch_result *t);
 };
+
+gnb_session::~gnb_session()
+{
+    slots.clear(); // joins jobs, frees per-batch buffers
+    cudaSetDevice(device);
+    for (auto &l : levels)
+        for (auto &f : l.filters)
+        {
+            f.d_single.release();
+            f.d_bin_node.release();
+            f.d_seg_off.release();
+            f.d_segs.release();
+            f.d_ibf_table.release();
+        }
+}
+
+int BatchCtx::init(cudaStream_t external)
+{
+    GNB_CUDA(cudaSetDevice(device));
+    if (external)
+    {
+        st         = external;
+        own_stream = false;
+    }
+    else
+        GNB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &e : ev)
+        GNB_CUDA(cudaEventCreate(&e));
+    workers.resize(n_threads);
+    for (auto &w : workers)
+    {
+        w.all_text.resize(levels.size());
+        w.one_text.resize(levels.size());
+        w.rep.resize(levels.size());
+        w.total.resize(levels.size());
+    }
+    GNB_TRY(d_cursor.ensure(64));
+    GNB_TRY(d_status.ensure(64));
+    GNB_TRY(d_items_cursor.ensure(64));
+    return GNB_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // session creation: parse_hierarchy (GC.cpp:353-401), load_tax / merge_tax / validate_targets_tax (GC.cpp:988-1005,
@@ -441,7 +518,6 @@ int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
     }
     GNB_TRY(F.d_ibf_table.ensure(F.ibf_table.size() * sizeof(IbfDev)));
     GNB_CUDA(cudaMemcpy(F.d_ibf_table.p, F.ibf_table.data(), F.ibf_table.size() * sizeof(IbfDev), cudaMemcpyHostToDevice));
-    GNB_TRY(F.d_items_cursor.ensure(64));
     F.dev = F.ibf_table[0];
     return GNB_OK;
 }
@@ -725,28 +801,18 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
             return rc;
     }
 
-    if (cfg->cuda_stream)
-    {
-        s->st         = (cudaStream_t)cfg->cuda_stream;
-        s->own_stream = false;
-    }
-    else
-        GNB_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
-    for (auto &e : s->ev)
-        GNB_CUDA(cudaEventCreate(&e));
     s->n_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     if (s->n_threads > 64)
         s->n_threads = 64;
-    s->workers.resize(s->n_threads);
-    for (auto &w : s->workers)
+    // batches in flight: 1 on a caller-provided stream (its events must bracket the work), else 3
+    int n_slots = cfg->cuda_stream ? 1 : 3;
+    if (const char *e = getenv("GANON_B200_SLOTS"))
+        n_slots = std::max(1, std::min(8, atoi(e)));
+    for (int i = 0; i < n_slots; ++i)
     {
-        w.all_text.resize(s->levels.size());
-        w.one_text.resize(s->levels.size());
-        w.rep.resize(s->levels.size());
-        w.total.resize(s->levels.size());
+        s->slots.emplace_back(new BatchCtx(s.get()));
+        GNB_TRY(s->slots.back()->init((cudaStream_t)cfg->cuda_stream));
     }
-    GNB_TRY(s->d_cursor.ensure(64));
-    GNB_TRY(s->d_status.ensure(64));
     *out = s.release();
     return GNB_OK;
 }
@@ -768,7 +834,7 @@ void gnb_session::ensure_prefix(uint32_t prefix_id)
 // stage: copy the block(s) to the device and index the records -- on the device (K1) for strict 4-line FASTQ, on the
 // host (reads.cpp: FASTA, wrapped FASTQ, blanks, and the exact parse-error behaviour) for everything else
 // ---------------------------------------------------------------------------------------------------------------------
-int gnb_session::device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines)
+int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines)
 {
     DevBuf        &blk   = side == 0 ? d_blk1 : d_blk2;
     DevBuf        &lines = side == 0 ? d_lines1 : d_lines2;
@@ -791,7 +857,7 @@ int gnb_session::device_index(int side, uint64_t len, bool fin, uint32_t &n_reco
     return GNB_OK;
 }
 
-int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin)
+int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin)
 {
     GNB_CUDA(cudaSetDevice(device));
     staged = ran = false;
@@ -921,9 +987,9 @@ int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2,
             err = true, err_rec = std::min(err_rec, (size_t)t2.error_record);
         if (err)
         {
-            const uint64_t abs_rec  = file_records + err_rec;
+            const uint64_t abs_rec  = S->file_records + err_rec;
             const uint64_t keep_abs = abs_rec / n_reads_chunk * n_reads_chunk;
-            n = keep_abs > file_records ? (size_t)(keep_abs - file_records) : 0;
+            n = keep_abs > S->file_records ? (size_t)(keep_abs - S->file_records) : 0;
             parse_error = true;
             if (!quiet)
                 fprintf(stderr, "Error parsing file(s): %s\n", (t1.parse_error ? t1.error_msg : t2.error_msg).c_str());
@@ -973,9 +1039,9 @@ int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2,
     n_reads            = (uint32_t)n;
     timing.n_reads     = n_reads;
     timing.parse_error = parse_error ? 1 : 0;
-    file_records += n;
+    S->file_records += n;
     if (final_block || parse_error)
-        file_records = 0;
+        S->file_records = 0;
     GNB_TRY(d_counts.ensure((size_t)n * 4 + 4));
     GNB_TRY(d_hash_off.ensure(((size_t)n + 1) * 8));
     GNB_TRY(d_active.ensure((size_t)n + 1));
@@ -986,7 +1052,7 @@ int gnb_session::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2,
 }
 
 // K2 twice (count, then write) with an exclusive scan in between
-int gnb_session::compute_hashes(uint32_t k, uint32_t w)
+int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
 {
     if (hashed_k == k && hashed_w == w)
         return GNB_OK;
@@ -1030,9 +1096,9 @@ int gnb_session::compute_hashes(uint32_t k, uint32_t w)
 
 // HIBF traversal (counting_agent_type::bulk_count, HIBF.hpp:433-460, 506-523) as level-synchronous rounds over a
 // worklist of (read, sub-IBF) items; tuples accumulate in d_tuples_a across the rounds.
-int gnb_session::run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &produced_out)
+int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
 {
-    (void)act;
+    FilterRt &F = levels[li].filters[fi];
     const uint32_t n = n_reads;
     hibf_bytes = 0;
     hibf_ms    = 0;
@@ -1042,14 +1108,14 @@ int gnb_session::run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &prod
         if (h_active[r] && h_counts[r] > 0 && h_counts[r] <= 65535)
             items.push_back(make_uint2(r, 0));
     uint64_t n_items = items.size();
-    GNB_TRY(F.d_items_a.ensure((n_items + 1024) * sizeof(uint2)));
-    GNB_TRY(F.d_items_b.ensure((n_items + 1024) * sizeof(uint2)));
+    GNB_TRY(d_items_a.ensure((n_items + 1024) * sizeof(uint2)));
+    GNB_TRY(d_items_b.ensure((n_items + 1024) * sizeof(uint2)));
     if (n_items)
-        GNB_CUDA(cudaMemcpyAsync(F.d_items_a.p, items.data(), n_items * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        GNB_CUDA(cudaMemcpyAsync(d_items_a.p, items.data(), n_items * sizeof(uint2), cudaMemcpyHostToDevice, st));
     timing.h2d_bytes += n_items * sizeof(uint2);
     GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
     unsigned long long tuples_before = 0;
-    DevBuf *cur = &F.d_items_a, *nxt = &F.d_items_b;
+    DevBuf *cur = &d_items_a, *nxt = &d_items_b;
     std::vector<uint2> round_items; // only used for the byte accounting
     while (n_items)
     {
@@ -1057,16 +1123,16 @@ int gnb_session::run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &prod
         for (int attempt = 0; attempt < 3; ++attempt)
         {
             const uint64_t cap = d_tuples_a.cap / 8, icap = nxt->cap / sizeof(uint2);
-            GNB_CUDA(cudaMemsetAsync(F.d_items_cursor.p, 0, 8, st));
+            GNB_CUDA(cudaMemsetAsync(d_items_cursor.p, 0, 8, st));
             GNB_CUDA(cudaMemcpyAsync(d_cursor.p, &tuples_before, 8, cudaMemcpyHostToDevice, st));
             GNB_CUDA(cudaEventRecord(ev[4], st));
             launch_hibf_round(F.d_ibf_table.as<IbfDev>(), F.dev.hash_funs, cur->as<uint2>(), (uint32_t)n_items, d_hashes.as<uint64_t>(),
                               d_hash_off.as<uint64_t>(), std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff, d_tuples_a.as<uint64_t>(),
-                              d_cursor.as<unsigned long long>(), cap, nxt->as<uint2>(), F.d_items_cursor.as<unsigned long long>(), icap, st);
+                              d_cursor.as<unsigned long long>(), cap, nxt->as<uint2>(), d_items_cursor.as<unsigned long long>(), icap, st);
             GNB_CUDA(cudaEventRecord(ev[5], st));
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&got_tuples, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
-            GNB_CUDA(cudaMemcpyAsync(&got_items, F.d_items_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync(&got_items, d_items_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             GNB_CUDA(cudaStreamSynchronize(st));
             GNB_CUDA(cudaGetLastError());
             timing.d2h_bytes += 16;
@@ -1107,7 +1173,7 @@ int gnb_session::run_hibf_filter(FilterRt &F, const uint8_t *act, uint64_t &prod
 }
 
 // K3 (+ sort) for every filter of level li on the reads still active
-int gnb_session::run_level(size_t li)
+int BatchCtx::run_level(size_t li)
 {
     LevelRt &L = levels[li];
     int rc = compute_hashes(L.k, L.w);
@@ -1126,9 +1192,11 @@ int gnb_session::run_level(size_t li)
         if (h_active[i] && h_counts[i] <= 65535)
             active_hashes += h_counts[i];
     float ms_sort = 0, ms_k3 = 0;
-    for (auto &F : L.filters)
+    for (size_t fi = 0; fi < L.filters.size(); ++fi)
     {
-        F.tuples.clear();
+        FilterRt              &F  = L.filters[fi];
+        std::vector<uint64_t> &Ft = tuples[li][fi];
+        Ft.clear();
         if (n == 0)
             continue;
         uint64_t cap = d_tuples_a.cap / 8;
@@ -1141,7 +1209,7 @@ int gnb_session::run_level(size_t li)
         if (F.is_hibf)
         {
             uint64_t prod = 0;
-            GNB_TRY(run_hibf_filter(F, act, prod));
+            GNB_TRY(run_hibf_filter(li, fi, prod));
             produced = prod;
             timing.count_kernel_bytes += hibf_bytes;
             ms_k3 += hibf_ms;
@@ -1179,9 +1247,9 @@ int gnb_session::run_level(size_t li)
         GNB_TRY(d_tmp.ensure(tb));
         launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
         GNB_CUDA(cudaEventRecord(ev[7], st));
-        F.tuples.resize(produced);
+        Ft.resize(produced);
         timing.d2h_bytes += produced * 8;
-        GNB_CUDA(cudaMemcpyAsync(F.tuples.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync(Ft.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
         GNB_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, ev[6], ev[7]);
@@ -1193,7 +1261,7 @@ int gnb_session::run_level(size_t li)
 }
 
 // host finishing stage for level li
-int gnb_session::finish_level(size_t li, uint32_t prefix_id)
+int BatchCtx::finish_level(size_t li)
 {
     LevelRt       &L = levels[li];
     const uint32_t n = n_reads;
@@ -1210,7 +1278,7 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
         std::vector<size_t> cur(nf);
         for (size_t f = 0; f < nf; ++f)
         {
-            const auto &tp = L.filters[f].tuples;
+            const auto &tp = tuples[li][f];
             cur[f] = std::lower_bound(tp.begin(), tp.end(), (uint64_t)r0 << kTupleReadShift) - tp.begin();
         }
         struct M
@@ -1244,7 +1312,7 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
             for (size_t f = 0; f < nf; ++f)
             {
                 const FilterRt &F  = L.filters[f];
-                const auto     &tp = F.tuples;
+                const auto     &tp = tuples[li][f];
                 size_t         &c  = cur[f];
                 if (c >= tp.size() || (uint32_t)(tp[c] >> kTupleReadShift) != r)
                     continue;
@@ -1442,13 +1510,11 @@ int gnb_session::finish_level(size_t li, uint32_t prefix_id)
         for (auto &t : th)
             t.join();
     }
-    (void)prefix_id;
     return GNB_OK;
 }
 
-int gnb_session::finish(uint32_t prefix_id, gnb_batch_result *out)
+void BatchCtx::begin_finish()
 {
-    ensure_prefix(prefix_id);
     for (auto &W : workers)
     {
         for (auto &s : W.all_text)
@@ -1461,44 +1527,56 @@ int gnb_session::finish(uint32_t prefix_id, gnb_batch_result *out)
         W.m_count.clear();
         W.n_classified = 0;
     }
-    auto t0 = Clock::now();
-    double host_ms = 0;
-    for (size_t li = 0; li < levels.size(); ++li)
-    {
-        if (!(li == 0 && ran))
-        {
-            int rc = run_level(li);
-            if (rc != GNB_OK)
-                return rc;
-        }
-        auto th = Clock::now();
-        int  rc = finish_level(li, prefix_id);
-        host_ms += ms_since(th);
-        if (rc != GNB_OK)
-            return rc;
-    }
-    // ---- merge worker state into the session ----
+    timing.ms_host_finish = 0;
+}
+
+void BatchCtx::fill_timings(gnb_batch_result *t)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess)
+        timing.ms_h2d = ms;
+    if (n_reads && hashed_k && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess)
+        timing.ms_minimiser = ms;
+    *t                   = timing;
+    t->n_reads           = n_reads;
+    t->parse_error       = parse_error ? 1 : 0;
+    t->consumed1         = parse_error ? len1 : consumed1; // a parse error skips the rest of the file (GC.cpp:1278-1283)
+    t->consumed2         = !paired ? 0 : parse_error ? len2 : consumed2;
+    t->n_kernel_launches = launches;
+    t->n_minimisers      = 0;
+    for (uint32_t i = 0; i < n_reads && i < h_counts.size(); ++i)
+        if (h_counts[i] <= 65535)
+            t->n_minimisers += h_counts[i];
+}
+
+// merge the workers' pieces into the result buffers and the session's accounting
+int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
+{
     const uint32_t n = n_reads;
     r_all.assign(levels.size(), std::string());
     r_one.assign(levels.size(), std::string());
     r_unc.clear();
     r_match_off.assign((size_t)n + 1, 0);
     uint64_t n_classified = 0;
-    for (size_t li = 0; li < levels.size(); ++li)
     {
-        LevelRt &L = levels[li];
-        for (auto &W : workers)
+        std::lock_guard<std::mutex> lock(S->acc_mutex);
+        S->ensure_prefix(prefix_id);
+        for (size_t li = 0; li < levels.size(); ++li)
         {
-            r_all[li] += W.all_text[li];
-            r_one[li] += W.one_text[li];
-            for (auto const &[node, rp] : W.rep[li])
-                L.rep[prefix_id][node].add(rp);
-            W.rep[li].clear();
-            add_totals(L.total[prefix_id], W.total[li]);
-            W.total[li] = gnb_totals{};
+            LevelRt &L = levels[li];
+            for (auto &W : workers)
+            {
+                r_all[li] += W.all_text[li];
+                r_one[li] += W.one_text[li];
+                for (auto const &[node, rp] : W.rep[li])
+                    L.rep[prefix_id][node].add(rp);
+                W.rep[li].clear();
+                add_totals(L.total[prefix_id], W.total[li]);
+                W.total[li] = gnb_totals{};
+            }
         }
+        levels[0].total[prefix_id].input_seqs += n;
     }
-    levels[0].total[prefix_id].input_seqs += n;
     // structured CSR: counts per read, then fill
     for (auto &W : workers)
     {
@@ -1522,115 +1600,226 @@ int gnb_session::finish(uint32_t prefix_id, gnb_batch_result *out)
             p += k;
         }
     }
-    timing.ms_host_finish = host_ms;
-    // device stage timings
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess)
-        timing.ms_h2d = ms;
-    if (n && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess)
-        timing.ms_minimiser = ms;
-    (void)t0;
-    if (out)
+    r_all_p.clear();
+    r_one_p.clear();
+    r_all_l.clear();
+    r_one_l.clear();
+    for (size_t li = 0; li < levels.size(); ++li)
     {
-        r_all_p.clear();
-        r_one_p.clear();
-        r_all_l.clear();
-        r_one_l.clear();
-        for (size_t li = 0; li < levels.size(); ++li)
-        {
-            r_all_p.push_back(r_all[li].data());
-            r_all_l.push_back(r_all[li].size());
-            r_one_p.push_back(r_one[li].data());
-            r_one_l.push_back(r_one[li].size());
-        }
-        *out              = timing;
-        out->n_reads      = n;
-        out->match_off    = r_match_off.data();
-        out->match_target = r_match_target.data();
-        out->match_count  = r_match_count.data();
-        out->read_level   = h_read_level.data();
-        out->n_hashes     = h_counts.data();
-        out->n_classified = n_classified;
-        out->n_levels     = (uint32_t)levels.size();
-        out->all_text     = r_all_p.data();
-        out->all_len      = r_all_l.data();
-        out->one_text     = r_one_p.data();
-        out->one_len      = r_one_l.data();
-        out->unc_text     = r_unc.data();
-        out->unc_len      = r_unc.size();
-        out->n_minimisers = 0;
-        for (uint32_t i = 0; i < n; ++i)
-            if (h_counts[i] <= 65535)
-                out->n_minimisers += h_counts[i];
-        out->n_kernel_launches = launches;
+        r_all_p.push_back(r_all[li].data());
+        r_all_l.push_back(r_all[li].size());
+        r_one_p.push_back(r_one[li].data());
+        r_one_l.push_back(r_one[li].size());
     }
+    fill_timings(&result);
+    result.match_off    = r_match_off.data();
+    result.match_target = r_match_target.data();
+    result.match_count  = r_match_count.data();
+    result.read_level   = h_read_level.data();
+    result.n_hashes     = h_counts.data();
+    result.n_classified = n_classified;
+    result.n_levels     = (uint32_t)levels.size();
+    result.all_text     = r_all_p.data();
+    result.all_len      = r_all_l.data();
+    result.one_text     = r_one_p.data();
+    result.one_len      = r_one_l.data();
+    result.unc_text     = r_unc.data();
+    result.unc_len      = r_unc.size();
+    if (out)
+        *out = result;
     staged = ran = false;
     return GNB_OK;
+}
+
+// all levels of the staged batch: K2/K3 (unless level 0 already ran), host finishing, merge
+int BatchCtx::finish(uint32_t prefix_id, gnb_batch_result *out)
+{
+    GNB_CUDA(cudaSetDevice(device));
+    begin_finish();
+    for (size_t li = 0; li < levels.size(); ++li)
+    {
+        if (!(li == 0 && ran))
+            GNB_TRY(run_level(li));
+        auto th = Clock::now();
+        GNB_TRY(finish_level(li));
+        timing.ms_host_finish += ms_since(th);
+    }
+    return collect(prefix_id, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------------
-static void fill_consumed(gnb_session *s, gnb_batch_result *out)
+// A slot that is neither in flight nor holding the result the caller may still be reading.
+int gnb_session::acquire_slot()
 {
-    // bytes that formed the records taken; on a parse error the rest of the file is skipped (GC.cpp:1278-1283)
-    out->consumed1 = s->parse_error ? s->len1 : s->consumed1;
-    out->consumed2 = !s->paired ? 0 : s->parse_error ? s->len2 : s->consumed2;
+    for (int i = 0; i < (int)slots.size(); ++i)
+    {
+        bool used = i == holding && slots.size() > 1;
+        for (int f : in_flight)
+            used |= f == i;
+        if (!used)
+            return i;
+    }
+    return -1;
+}
+
+static int sync_slot(gnb_session *s)
+{
+    if (!s->in_flight.empty())
+        return fail(GNB_ERR_ARG, "batches are in flight: call gnb_session_collect first");
+    return 0;
 }
 
 extern "C" int gnb_session_stage(gnb_session *s, const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin, uint64_t *n_reads)
 {
     if (!s || !b1)
         return fail(GNB_ERR_ARG, "gnb_session_stage: bad arguments");
-    int rc = s->stage(b1, l1, b2, l2, fin);
-    if (rc == GNB_OK && n_reads)
-        *n_reads = s->n_reads;
-    if (rc == GNB_OK)
-        GNB_CUDA(cudaStreamSynchronize(s->st));
-    return rc;
+    GNB_TRY(sync_slot(s));
+    BatchCtx &c = *s->slots[0];
+    GNB_TRY(c.stage(b1, l1, b2, l2, fin));
+    if (n_reads)
+        *n_reads = c.n_reads;
+    GNB_CUDA(cudaStreamSynchronize(c.st));
+    return GNB_OK;
 }
 
 extern "C" int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings)
 {
-    if (!s || !s->staged)
+    if (!s || !s->slots[0]->staged)
         return fail(GNB_ERR_ARG, "gnb_session_run_staged: nothing staged");
-    GNB_CUDA(cudaSetDevice(s->device));
+    BatchCtx &c = *s->slots[0];
+    GNB_CUDA(cudaSetDevice(c.device));
     // allow repeated runs on the same staged batch (benchmark): reset per-run state
-    s->hashed_k = s->hashed_w = 0;
-    s->timing.ms_count = s->timing.ms_sort = 0;
-    s->timing.count_kernel_bytes = 0;
-    s->timing.d2h_bytes = 0;
-    s->launches = 0;
-    std::fill(s->h_active.begin(), s->h_active.end(), (uint8_t)1);
-    int rc = s->run_level(0);
-    if (rc != GNB_OK)
-        return rc;
-    float ms = 0;
-    if (s->n_reads && cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess)
-        s->timing.ms_minimiser = ms;
-    s->ran = true;
+    c.hashed_k = c.hashed_w = 0;
+    c.timing.ms_count = c.timing.ms_sort = 0;
+    c.timing.count_kernel_bytes = 0;
+    c.timing.d2h_bytes = 0;
+    c.launches = 0;
+    std::fill(c.h_active.begin(), c.h_active.end(), (uint8_t)1);
+    GNB_TRY(c.run_level(0));
+    c.ran = true;
     if (timings)
-    {
-        *timings = s->timing;
-        timings->n_reads = s->n_reads;
-        timings->n_kernel_launches = s->launches;
-        timings->n_minimisers = 0;
-        for (uint32_t i = 0; i < s->n_reads; ++i)
-            if (s->h_counts[i] <= 65535)
-                timings->n_minimisers += s->h_counts[i];
-    }
+        c.fill_timings(timings);
     return GNB_OK;
 }
 
 extern "C" int gnb_session_finish_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out)
 {
-    if (!s || !s->staged)
+    if (!s || !s->slots[0]->staged)
         return fail(GNB_ERR_ARG, "gnb_session_finish_staged: nothing staged");
-    GNB_CUDA(cudaSetDevice(s->device));
-    int rc = s->finish(prefix_id, out);
-    if (rc == GNB_OK && out)
-        fill_consumed(s, out);
-    return rc;
+    return s->slots[0]->finish(prefix_id, out);
+}
+
+// Level-wise form (bin-sharded multi-GPU): run K2/K3 of one level, expose / replace its tuples, finish the level.
+extern "C" int gnb_session_run_level(gnb_session *s, uint32_t level)
+{
+    if (!s || !s->slots[0]->staged || level >= s->levels.size())
+        return fail(GNB_ERR_ARG, "gnb_session_run_level: nothing staged or bad level");
+    BatchCtx &c = *s->slots[0];
+    GNB_CUDA(cudaSetDevice(c.device));
+    if (level == 0)
+        c.begin_finish();
+    return c.run_level(level);
+}
+
+extern "C" int gnb_session_level_tuples(gnb_session *s, uint32_t level, uint32_t filter, const uint64_t **tuples, uint64_t *n)
+{
+    if (!s || !tuples || !n || level >= s->levels.size() || filter >= s->levels[level].filters.size())
+        return fail(GNB_ERR_ARG, "gnb_session_level_tuples: bad arguments");
+    auto &t = s->slots[0]->tuples[level][filter];
+    *tuples = t.data();
+    *n      = t.size();
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_set_level_tuples(gnb_session *s, uint32_t level, uint32_t filter, const uint64_t *tuples, uint64_t n)
+{
+    if (!s || (n && !tuples) || level >= s->levels.size() || filter >= s->levels[level].filters.size())
+        return fail(GNB_ERR_ARG, "gnb_session_set_level_tuples: bad arguments");
+    auto &t = s->slots[0]->tuples[level][filter];
+    t.assign(tuples, tuples + n);
+    if (!std::is_sorted(t.begin(), t.end(), [](uint64_t a, uint64_t b) { return (a >> kTupleNodeShift) < (b >> kTupleNodeShift); }))
+        std::stable_sort(t.begin(), t.end(), [](uint64_t a, uint64_t b) { return (a >> kTupleNodeShift) < (b >> kTupleNodeShift); });
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_finish_level(gnb_session *s, uint32_t level)
+{
+    if (!s || !s->slots[0]->staged || level >= s->levels.size())
+        return fail(GNB_ERR_ARG, "gnb_session_finish_level: nothing staged or bad level");
+    BatchCtx &c = *s->slots[0];
+    auto      th = Clock::now();
+    GNB_TRY(c.finish_level(level));
+    c.timing.ms_host_finish += ms_since(th);
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_collect_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out)
+{
+    if (!s || !s->slots[0]->staged)
+        return fail(GNB_ERR_ARG, "gnb_session_collect_staged: nothing staged");
+    return s->slots[0]->collect(prefix_id, out);
+}
+
+// Asynchronous form.  submit: index + copy the block to the device in the calling thread (the caller needs the consumed
+// byte counts to cut the next block), then K2/K3/host finishing run in a worker thread on the slot's own stream while the
+// caller stages the next block.  collect: results of the oldest batch, in submission order.
+extern "C" int gnb_session_submit(gnb_session *s, uint32_t prefix_id, const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin,
+                                  gnb_batch_result *staged_info)
+{
+    if (!s || !b1)
+        return fail(GNB_ERR_ARG, "gnb_session_submit: bad arguments");
+    const int slot = s->acquire_slot();
+    if (slot < 0)
+        return fail(GNB_ERR_LIMIT, "gnb_session_submit: all slots in flight, collect first");
+    BatchCtx &c = *s->slots[slot];
+    if (c.job.joinable())
+        c.job.join();
+    c.t_submit = Clock::now();
+    GNB_TRY(c.stage(b1, l1, b2, l2, fin));
+    if (staged_info)
+        c.fill_timings(staged_info);
+    c.busy   = true;
+    c.job_rc = GNB_OK;
+    c.job    = std::thread([&c, prefix_id]() {
+        c.job_rc = c.finish(prefix_id, nullptr);
+        if (c.job_rc != GNB_OK)
+            c.job_err = gnb_last_error();
+    });
+    s->in_flight.push_back(slot);
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_in_flight(const gnb_session *s, uint32_t *n, uint32_t *capacity)
+{
+    if (!s)
+        return fail(GNB_ERR_ARG, "null argument");
+    if (n)
+        *n = (uint32_t)s->in_flight.size();
+    if (capacity)
+        *capacity = (uint32_t)std::max<size_t>(1, s->slots.size() - 1);
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_collect(gnb_session *s, gnb_batch_result *out)
+{
+    if (!s || !out)
+        return fail(GNB_ERR_ARG, "gnb_session_collect: bad arguments");
+    if (s->in_flight.empty())
+        return fail(GNB_ERR_ARG, "gnb_session_collect: nothing in flight");
+    const int slot = s->in_flight.front();
+    s->in_flight.pop_front();
+    BatchCtx &c = *s->slots[slot];
+    if (c.job.joinable())
+        c.job.join();
+    c.busy     = false;
+    s->holding = slot;
+    if (c.job_rc != GNB_OK)
+        return fail(c.job_rc, c.job_err);
+    *out          = c.result;
+    out->ms_total = ms_since(c.t_submit);
+    return GNB_OK;
 }
 
 extern "C" int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin,
@@ -1638,15 +1827,28 @@ extern "C" int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const ch
 {
     if (!s || !b1 || !out)
         return fail(GNB_ERR_ARG, "gnb_session_classify: bad arguments");
-    auto t0 = Clock::now();
-    int  rc = s->stage(b1, l1, b2, l2, fin);
-    if (rc != GNB_OK)
-        return rc;
-    rc = s->finish(prefix_id, out);
-    if (rc != GNB_OK)
-        return rc;
-    fill_consumed(s, out);
+    GNB_TRY(sync_slot(s));
+    auto      t0 = Clock::now();
+    BatchCtx &c  = *s->slots[0];
+    s->holding   = 0;
+    GNB_TRY(c.stage(b1, l1, b2, l2, fin));
+    GNB_TRY(c.finish(prefix_id, out));
     out->ms_total = ms_since(t0);
+    return GNB_OK;
+}
+
+extern "C" int gnb_host_register(void *ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes)
+        return fail(GNB_ERR_ARG, "gnb_host_register: bad arguments");
+    GNB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return GNB_OK;
+}
+extern "C" int gnb_host_unregister(void *ptr)
+{
+    if (!ptr)
+        return fail(GNB_ERR_ARG, "gnb_host_unregister: bad arguments");
+    GNB_CUDA(cudaHostUnregister(ptr));
     return GNB_OK;
 }
 

@@ -83,6 +83,10 @@ void gnb_db_free(gnb_db *db);
  * IBF.hpp:222-246, emplace IBF.hpp:271-286, bin map GanonBuild.cpp:619-653).  Used by the benchmark and tests. */
 int gnb_db_create(uint64_t bins, uint64_t bin_size_bits, uint32_t hash_functions, uint32_t kmer_size,
                   uint32_t window_size, int device, gnb_db **out);
+/* the same filter, but only the bin-word columns of shard `shard` of `n_shards` are held (gnb_db_fill_random and
+ * gnb_db_emplace then produce exactly that slice of the whole filter) */
+int gnb_db_create_sharded(uint64_t bins, uint64_t bin_size_bits, uint32_t hash_functions, uint32_t kmer_size,
+                          uint32_t window_size, int device, int shard, int n_shards, gnb_db **out);
 /* word(i) = AND of `and_terms` splitmix64 draws of (seed, i, term): bit density 2^-and_terms; padding bins cleared */
 int gnb_db_fill_random(gnb_db *db, uint64_t seed, int and_terms);
 int gnb_db_emplace(gnb_db *db, const uint64_t *hashes, const uint32_t *bins, uint64_t n); /* host arrays */
@@ -179,6 +183,33 @@ int gnb_session_stage(gnb_session *s, const char *block1, uint64_t len1, const c
                       uint64_t *n_reads);
 int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings);
 int gnb_session_finish_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out);
+
+/* Asynchronous form of gnb_session_classify for streaming a file: submit indexes the block and copies it to the device
+ * in the calling thread (staged_info->n_reads / consumed1 / consumed2 / parse_error are valid on return, so the caller
+ * can cut the next block), then kernels and host finishing run in a worker thread on the slot's own CUDA stream while the
+ * next block is staged.  collect returns the oldest submitted batch (submission order).  The blocks passed to submit
+ * must stay untouched until their batch has been collected; a collected result stays valid until the next collect.
+ * gnb_session_in_flight: batches submitted and not collected, and how many may be in flight at once. */
+int gnb_session_submit(gnb_session *s, uint32_t prefix_id, const char *block1, uint64_t len1, const char *block2,
+                       uint64_t len2, int final, gnb_batch_result *staged_info);
+int gnb_session_collect(gnb_session *s, gnb_batch_result *out);
+int gnb_session_in_flight(const gnb_session *s, uint32_t *n, uint32_t *capacity);
+
+/* Level-wise form for bin-sharded multi-GPU runs (every rank holds a column shard of the filter and stages the same
+ * block): run_level = K2/K3 of one hierarchy level on this rank's shard; level_tuples exposes the sparse result of one
+ * filter -- uint64 [63:40] read | [39:17] node | [16] partial-sum flag | [15:0] count, sorted by (read, node);
+ * the caller concatenates the ranks' tuples (all-gather) and hands them back with set_level_tuples; finish_level runs
+ * the host finishing stage of that level; collect_staged merges the result after the last level. */
+int gnb_session_run_level(gnb_session *s, uint32_t level);
+int gnb_session_level_tuples(gnb_session *s, uint32_t level, uint32_t filter, const uint64_t **tuples, uint64_t *n);
+int gnb_session_set_level_tuples(gnb_session *s, uint32_t level, uint32_t filter, const uint64_t *tuples, uint64_t n);
+int gnb_session_finish_level(gnb_session *s, uint32_t level);
+int gnb_session_collect_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out);
+
+/* Page-lock / unlock a host buffer that will be passed as a read block (cudaHostRegister): faster, truly asynchronous
+ * host->device copies. */
+int gnb_host_register(void *ptr, uint64_t bytes);
+int gnb_host_unregister(void *ptr);
 
 /* Node (target / taxonomy node) names of a level, as used by match_target. */
 int gnb_session_level_count(const gnb_session *s, uint32_t *n_levels);

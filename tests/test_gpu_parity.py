@@ -309,3 +309,129 @@ def test_hibf_scenarios_match_reference_outputs(name, golden_dbs, tmp_path):
     assert got_files == want_files
     for ext in want_files:
         assert _read_sorted(pre + ext) == SU.expected_lines(name, ext[1:]), ext
+
+
+# ------------------------------------------------------------------------------------------------------------------ pipeline + shards
+def test_async_submit_collect_matches_sync(golden_dbs):
+    fq1 = open(os.path.join(SU.GOLDEN, "reads.1.fq"), "rb").read()
+    fq2 = open(os.path.join(SU.GOLDEN, "reads.2.fq"), "rb").read()
+    recs1 = [b"@" + r for r in fq1.split(b"\n@")]
+    recs1[0] = recs1[0][1:]
+    recs2 = [b"@" + r for r in fq2.split(b"\n@")]
+    recs2[0] = recs2[0][1:]
+    fix = lambda r: r if r.endswith(b"\n") else r + b"\n"
+    recs1, recs2 = [fix(r) for r in recs1], [fix(r) for r in recs2]
+    db = Database.open(golden_dbs["synth"])
+    ref = Session([db], [0.0], [1.0], [1.0], output_all=True, output_unclassified=True)
+    r = ref.classify(b"".join(recs1), b"".join(recs2), final=True)
+    want_all, want_unc = sorted(result_text(r, "all").decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines())
+    want_rep = ref.report()
+    sess = Session([db], [0.0], [1.0], [1.0], output_all=True, output_unclassified=True)
+    _n, cap = sess.in_flight()
+    assert cap >= 2
+    blocks, step = [], 90
+    for a in range(0, len(recs1), step):
+        blocks.append((b"".join(recs1[a : a + step]), b"".join(recs2[a : a + step])))
+    got_all, got_unc, pending = [], [], 0
+    for i, (b1, b2) in enumerate(blocks):
+        info = sess.submit(b1, b2, final=i == len(blocks) - 1)
+        assert info.n_reads == min(step, len(recs1) - i * step) and info.consumed1 == len(b1) and info.consumed2 == len(b2)
+        pending += 1
+        if pending == cap:
+            res = sess.collect()
+            got_all += result_text(res, "all").decode().splitlines()
+            got_unc += result_text(res, "unc").decode().splitlines()
+            pending -= 1
+    while pending:
+        res = sess.collect()
+        got_all += result_text(res, "all").decode().splitlines()
+        got_unc += result_text(res, "unc").decode().splitlines()
+        pending -= 1
+    assert sorted(got_all) == want_all and sorted(got_unc) == want_unc
+    assert sess.report() == want_rep
+    with pytest.raises(_lib.GnbError):
+        sess.collect()
+
+
+def test_column_shards_on_one_gpu_equal_the_whole(golden_dbs):
+    """Three shard handles of the same .ibf (targets of 1-3 bins straddle the shard borders): merged tuples give the
+    unsharded result."""
+    from ganon_b200.sharded import merge_tuples
+
+    fq = open(os.path.join(SU.GOLDEN, "reads.se.fq"), "rb").read()
+    whole = Session([Database.open(golden_dbs["synth"])], [0.1], [0.5], [1.0], output_all=True, output_unclassified=True)
+    r = whole.classify(fq, final=True)
+    want = (sorted(result_text(r, "all").decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), whole.report())
+    n_shards = 3
+    sessions = [Session([Database.open(golden_dbs["synth"], shard=i, n_shards=n_shards)], [0.1], [0.5], [1.0], output_all=True, output_unclassified=True) for i in range(n_shards)]
+    for s in sessions:
+        assert s.stage(fq, final=True) == r.n_reads
+        s.run_level(0)
+    parts = [s.level_tuples(0, 0) for s in sessions]
+    assert any(((p >> np.uint64(16)) & np.uint64(1)).any() for p in parts)  # partial sums exist
+    merged = merge_tuples(np.concatenate(parts))
+    for s in sessions:
+        s.set_level_tuples(0, 0, merged)
+        s.finish_level(0)
+        res = s.collect_staged()
+        got = (sorted(result_text(res, "all").decode().splitlines()), sorted(result_text(res, "unc").decode().splitlines()), s.report())
+        assert got == want
+
+
+def test_sharded_create_fill_emplace_equals_slice():
+    full = Database.create(1000, 997, 4, 19, 31)
+    full.fill_random(3, 2)
+    hs = np.arange(5000, 5400, dtype=np.uint64)
+    bs = (np.arange(400) * 7 % 1000).astype(np.uint32)
+    full.emplace(hs, bs)
+    fi = full.info()
+    whole = full.read_words(0, fi.bin_size_bits * fi.bin_words).reshape(fi.bin_size_bits, fi.bin_words)
+    for sh in range(3):
+        part = Database.create(1000, 997, 4, 19, 31, shard=sh, n_shards=3)
+        part.fill_random(3, 2)
+        part.emplace(hs, bs)
+        pi = part.info()
+        w = pi.shard_word_end - pi.shard_word_begin
+        got = part.read_words(0, pi.bin_size_bits * w).reshape(pi.bin_size_bits, w)
+        assert np.array_equal(got, whole[:, pi.shard_word_begin : pi.shard_word_end])
+
+
+def _two_gpu_worker(rank, world, port, ibf, fq_path, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from ganon_b200.sharded import ShardedSession
+
+    s = ShardedSession.open([ibf], rank, world, rank, [0.1], [0.5], [1.0], output_all=True, output_unclassified=True)
+    res = s.classify(open(fq_path, "rb").read(), final=True)
+    with open(os.path.join(out_dir, "r%d.all" % rank), "wb") as f:
+        f.write(result_text(res, "all"))
+    with open(os.path.join(out_dir, "r%d.rep" % rank), "wb") as f:
+        f.write(s.report())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_two_gpus_nccl(golden_dbs, tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    fq = os.path.join(SU.GOLDEN, "reads.se.fq")
+    whole = Session([Database.open(golden_dbs["synth"])], [0.1], [0.5], [1.0], output_all=True, output_unclassified=True)
+    r = whole.classify(open(fq, "rb").read(), final=True)
+    mp.spawn(_two_gpu_worker, args=(2, port, golden_dbs["synth"], fq, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        assert sorted(open(tmp_path / ("r%d.all" % rank)).read().splitlines()) == sorted(result_text(r, "all").decode().splitlines())
+        assert open(tmp_path / ("r%d.rep" % rank), "rb").read() == whole.report()
