@@ -257,7 +257,10 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t want = (n_reads + K2_WARPS - 1) / K2_WARPS;
-    const uint32_t full = (uint32_t)sms * 8; // 64 warps per SM, persistent stride
+    uint32_t       full = (uint32_t)sms * 8; // 64 warps per SM
+    const uint32_t fine = (want + 63) / 64;  // ~64 reads per warp: short-lived CTAs (see launch_k3)
+    if (fine > full)
+        full = fine;
     const uint32_t grid = want < full ? want : full;
     if (write)
     {
@@ -648,7 +651,12 @@ void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t items = (uint64_t)n_reads * f.n_chunks;
     uint64_t       want  = (items + K3_WARPS - 1) / K3_WARPS;
-    const uint64_t full  = (uint64_t)sms * occ; // one resident wave, grid-stride inside
+    // at least one resident wave; beyond that CTAs of ~16 items per warp, so that a CTA lives ~0.2 ms and the
+    // high-priority staging stream of the next batch (H2D + K1) gets SMs without waiting for the whole launch
+    uint64_t       full  = (uint64_t)sms * occ;
+    const uint64_t fine  = (want + 15) / 16;
+    if (fine > full)
+        full = fine;
     const uint32_t grid  = (uint32_t)(want < full ? want : full);
     WorkOut wo{tuples, cursor, cap, dense, nullptr, nullptr, 0};
     kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, active, n_reads, rel_cutoff, wo);

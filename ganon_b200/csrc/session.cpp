@@ -94,6 +94,38 @@ struct PinBuf
     }
 };
 
+// std::vector in page-locked host memory: device<->host copies into it are asynchronous and run at link speed
+template <typename T>
+struct PinnedAlloc
+{
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <typename U>
+    PinnedAlloc(const PinnedAlloc<U> &)
+    {
+    }
+    T *allocate(size_t n)
+    {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, n * sizeof(T)) != cudaSuccess)
+            throw std::bad_alloc();
+        return static_cast<T *>(p);
+    }
+    void deallocate(T *p, size_t) { cudaFreeHost(p); }
+    template <typename U>
+    bool operator==(const PinnedAlloc<U> &) const
+    {
+        return true;
+    }
+    template <typename U>
+    bool operator!=(const PinnedAlloc<U> &) const
+    {
+        return false;
+    }
+};
+template <typename T>
+using PinnedVec = std::vector<T, PinnedAlloc<T>>;
+
 struct Rep // GC.cpp:153-160
 {
     uint64_t matches = 0, seqs_lca = 0, seqs_unique = 0, discarded_matches_filter = 0, discarded_matches_fprquery = 0;
@@ -272,7 +304,9 @@ struct BatchCtx
     uint32_t              n_reads_chunk;
     int                   n_threads;
     bool                  use_device_index;
-    cudaStream_t          st = nullptr;
+    cudaStream_t          st = nullptr;    // K2 / K3 / sort / result copies
+    cudaStream_t          st_in = nullptr; // host->device block copies + K1, high priority (same as st on a caller's stream)
+    cudaEvent_t           ev_in = nullptr;
     bool                  own_stream = true;
     cudaEvent_t           ev[12]{};
     std::vector<Worker>   workers;
@@ -293,13 +327,13 @@ struct BatchCtx
     DevBuf d_blk1, d_blk2, d_off1, d_len1, d_off2, d_len2, d_idoff, d_idlen, d_counts, d_hash_off, d_hashes, d_active, d_tuples_a, d_tuples_b,
         d_cursor, d_tmp, d_lines1, d_lines2, d_k1tmp1, d_k1tmp2, d_idoff2, d_idlen2, d_status, d_items_a, d_items_b, d_items_cursor;
     PinBuf h_pin;
-    std::vector<uint32_t> h_counts;
+    PinnedVec<uint32_t>   h_counts;
     std::vector<uint8_t>  h_active;
     std::vector<uint8_t>  h_read_level;
     uint64_t              total_hashes = 0;
     uint64_t              hibf_bytes = 0;
     float                 hibf_ms = 0;
-    std::vector<std::vector<std::vector<uint64_t>>> tuples; // [level][filter], sorted by (read, node)
+    std::vector<std::vector<PinnedVec<uint64_t>>> tuples; // [level][filter], sorted by (read, node)
 
     // result storage
     std::vector<uint64_t>      r_match_off;
@@ -340,8 +374,13 @@ struct BatchCtx
         for (auto &e : ev)
             if (e)
                 cudaEventDestroy(e);
+        if (ev_in)
+            cudaEventDestroy(ev_in);
         if (st && own_stream)
+        {
             cudaStreamDestroy(st);
+            cudaStreamDestroy(st_in);
+        }
     }
     int init(cudaStream_t external);
 
@@ -377,11 +416,17 @@ int BatchCtx::init(cudaStream_t external)
     GNB_CUDA(cudaSetDevice(device));
     if (external)
     {
-        st         = external;
+        st = st_in = external;
         own_stream = false;
     }
     else
-        GNB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        GNB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        GNB_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, least));
+        GNB_CUDA(cudaStreamCreateWithPriority(&st_in, cudaStreamNonBlocking, greatest));
+    }
+    GNB_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     for (auto &e : ev)
         GNB_CUDA(cudaEventCreate(&e));
     workers.resize(n_threads);
@@ -842,17 +887,17 @@ int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records
     const size_t   tb    = fastq_index_tmp_bytes(n);
     DevBuf        &tmp   = side == 0 ? d_k1tmp1 : d_k1tmp2;
     GNB_TRY(tmp.ensure(tb));
-    launch_fastq_count(blk.as<uint8_t>(), n, d_status.as<uint32_t>() + 8 + side, tmp.p, tmp.cap, st);
+    launch_fastq_count(blk.as<uint8_t>(), n, d_status.as<uint32_t>() + 8 + side, tmp.p, tmp.cap, st_in);
     launches += 1;
     uint32_t nl = 0;
-    GNB_CUDA(cudaMemcpyAsync(&nl, d_status.as<uint32_t>() + 8 + side, 4, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(cudaMemcpyAsync(&nl, d_status.as<uint32_t>() + 8 + side, 4, cudaMemcpyDeviceToHost, st_in));
+    GNB_CUDA(cudaStreamSynchronize(st_in));
     (void)fin;
     n_lines   = nl;
     n_records = std::min<uint32_t>(nl / 4, kMaxReadsPerBatch - 1);
     const uint32_t cap_lines = 4 * n_records + 1;
     GNB_TRY(lines.ensure((size_t)cap_lines * 4 + 16));
-    launch_fastq_line_starts(blk.as<uint8_t>(), n, lines.as<uint32_t>(), cap_lines, tmp.p, st);
+    launch_fastq_line_starts(blk.as<uint8_t>(), n, lines.as<uint32_t>(), cap_lines, tmp.p, st_in);
     launches += 1;
     return GNB_OK;
 }
@@ -876,33 +921,33 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     max_hashes_ub = 0;
 
     // ---- blocks -> device (one extra byte so that a final block without trailing newline can be terminated) ----
-    GNB_CUDA(cudaEventRecord(ev[0], st));
+    GNB_CUDA(cudaEventRecord(ev[0], st_in));
     GNB_TRY(d_blk1.ensure(len1 + 64));
     if (len1)
-        GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
+        GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st_in));
     if (paired)
     {
         GNB_TRY(d_blk2.ensure(len2 + 64));
         if (len2)
-            GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st_in));
     }
-    GNB_CUDA(cudaEventRecord(ev[1], st));
+    GNB_CUDA(cudaEventRecord(ev[1], st_in));
     timing.h2d_bytes = len1 + len2;
 
     size_t n = 0;
     bool   on_device = use_device_index && len1 > 0 && b1[0] == '@' && (!paired || (len2 > 0 && b2[0] == '@'));
     if (on_device)
     {
-        GNB_CUDA(cudaEventRecord(ev[8], st));
+        GNB_CUDA(cudaEventRecord(ev[8], st_in));
         uint64_t e1 = len1, e2 = len2;
         if (final_block && b1[len1 - 1] != '\n')
         {
-            GNB_CUDA(cudaMemsetAsync(d_blk1.as<uint8_t>() + len1, '\n', 1, st));
+            GNB_CUDA(cudaMemsetAsync(d_blk1.as<uint8_t>() + len1, '\n', 1, st_in));
             e1 = len1 + 1;
         }
         if (paired && final_block && b2[len2 - 1] != '\n')
         {
-            GNB_CUDA(cudaMemsetAsync(d_blk2.as<uint8_t>() + len2, '\n', 1, st));
+            GNB_CUDA(cudaMemsetAsync(d_blk2.as<uint8_t>() + len2, '\n', 1, st_in));
             e2 = len2 + 1;
         }
         uint32_t n1 = 0, n2 = 0, nl1 = 0, nl2 = 0;
@@ -911,13 +956,13 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             GNB_TRY(device_index(1, e2, final_block, n2, nl2));
         n = paired ? std::min(n1, n2) : n1;
         const uint32_t init_status[4] = {0, 0, 0xffffffffu, 0};
-        GNB_CUDA(cudaMemcpyAsync(d_status.p, init_status, 16, cudaMemcpyHostToDevice, st));
+        GNB_CUDA(cudaMemcpyAsync(d_status.p, init_status, 16, cudaMemcpyHostToDevice, st_in));
         GNB_TRY(d_off1.ensure(n * 4 + 4));
         GNB_TRY(d_len1.ensure(n * 4 + 4));
         GNB_TRY(d_idoff.ensure(n * 4 + 4));
         GNB_TRY(d_idlen.ensure(n * 4 + 4));
         FastqIndexOut o1{d_idoff.as<uint32_t>(), d_idlen.as<uint32_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), d_status.as<uint32_t>()};
-        launch_fastq_records(d_blk1.as<uint8_t>(), d_lines1.as<uint32_t>(), (uint32_t)n, o1, st);
+        launch_fastq_records(d_blk1.as<uint8_t>(), d_lines1.as<uint32_t>(), (uint32_t)n, o1, st_in);
         launches += 2;
         if (paired)
         {
@@ -926,10 +971,10 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             GNB_TRY(d_idoff2.ensure(n * 4 + 4));
             GNB_TRY(d_idlen2.ensure(n * 4 + 4));
             FastqIndexOut o2{d_idoff2.as<uint32_t>(), d_idlen2.as<uint32_t>(), d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), d_status.as<uint32_t>()};
-            launch_fastq_records(d_blk2.as<uint8_t>(), d_lines2.as<uint32_t>(), (uint32_t)n, o2, st);
+            launch_fastq_records(d_blk2.as<uint8_t>(), d_lines2.as<uint32_t>(), (uint32_t)n, o2, st_in);
             launches += 2;
         }
-        GNB_CUDA(cudaEventRecord(ev[9], st));
+        GNB_CUDA(cudaEventRecord(ev[9], st_in));
         // record table -> pinned host memory (needed by the finishing stage only)
         GNB_TRY(h_pin.ensure(((size_t)n * 4 + 8) * 4 + 64));
         uint32_t *hp = h_pin.as<uint32_t>();
@@ -938,19 +983,19 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         p_idlen = p_idoff + n;
         p_slen1 = p_idlen + n;
         p_slen2 = p_slen1 + n;
-        GNB_CUDA(cudaMemcpyAsync(h_status, d_status.p, 16, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaMemcpyAsync(h_cons, d_lines1.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync(h_status, d_status.p, 16, cudaMemcpyDeviceToHost, st_in));
+        GNB_CUDA(cudaMemcpyAsync(h_cons, d_lines1.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st_in));
         if (paired)
-            GNB_CUDA(cudaMemcpyAsync(h_cons + 1, d_lines2.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync(h_cons + 1, d_lines2.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st_in));
         if (n)
         {
-            GNB_CUDA(cudaMemcpyAsync((void *)p_idoff, d_idoff.p, n * 4, cudaMemcpyDeviceToHost, st));
-            GNB_CUDA(cudaMemcpyAsync((void *)p_idlen, d_idlen.p, n * 4, cudaMemcpyDeviceToHost, st));
-            GNB_CUDA(cudaMemcpyAsync((void *)p_slen1, d_len1.p, n * 4, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync((void *)p_idoff, d_idoff.p, n * 4, cudaMemcpyDeviceToHost, st_in));
+            GNB_CUDA(cudaMemcpyAsync((void *)p_idlen, d_idlen.p, n * 4, cudaMemcpyDeviceToHost, st_in));
+            GNB_CUDA(cudaMemcpyAsync((void *)p_slen1, d_len1.p, n * 4, cudaMemcpyDeviceToHost, st_in));
             if (paired)
-                GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st_in));
         }
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(cudaStreamSynchronize(st_in));
         GNB_CUDA(cudaGetLastError());
         timing.d2h_bytes += 24 + (uint64_t)n * 4 * (paired ? 4 : 3);
         consumed1 = h_cons[0];
@@ -1008,30 +1053,30 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         if (!t1.aux.empty())
         {
             // ensure() may have reallocated: re-send the block
-            GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st));
-            GNB_CUDA(cudaMemcpyAsync(d_blk1.as<uint8_t>() + len1, t1.aux.data(), t1.aux.size(), cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st_in));
+            GNB_CUDA(cudaMemcpyAsync(d_blk1.as<uint8_t>() + len1, t1.aux.data(), t1.aux.size(), cudaMemcpyHostToDevice, st_in));
         }
         GNB_TRY(d_off1.ensure(n * 4 + 4));
         GNB_TRY(d_len1.ensure(n * 4 + 4));
         if (n)
         {
-            GNB_CUDA(cudaMemcpyAsync(d_off1.p, t1.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
-            GNB_CUDA(cudaMemcpyAsync(d_len1.p, t1.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_off1.p, t1.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st_in));
+            GNB_CUDA(cudaMemcpyAsync(d_len1.p, t1.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st_in));
         }
         if (paired)
         {
             GNB_TRY(d_blk2.ensure(len2 + t2.aux.size() + 64));
             if (!t2.aux.empty())
             {
-                GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st));
-                GNB_CUDA(cudaMemcpyAsync(d_blk2.as<uint8_t>() + len2, t2.aux.data(), t2.aux.size(), cudaMemcpyHostToDevice, st));
+                GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st_in));
+                GNB_CUDA(cudaMemcpyAsync(d_blk2.as<uint8_t>() + len2, t2.aux.data(), t2.aux.size(), cudaMemcpyHostToDevice, st_in));
             }
             GNB_TRY(d_off2.ensure(n * 4 + 4));
             GNB_TRY(d_len2.ensure(n * 4 + 4));
             if (n)
             {
-                GNB_CUDA(cudaMemcpyAsync(d_off2.p, t2.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st));
-                GNB_CUDA(cudaMemcpyAsync(d_len2.p, t2.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+                GNB_CUDA(cudaMemcpyAsync(d_off2.p, t2.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st_in));
+                GNB_CUDA(cudaMemcpyAsync(d_len2.p, t2.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st_in));
             }
         }
         timing.h2d_bytes += t1.aux.size() + (paired ? t2.aux.size() : 0) + (uint64_t)n * 8 * (paired ? 2 : 1);
@@ -1047,6 +1092,10 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     GNB_TRY(d_active.ensure((size_t)n + 1));
     h_active.assign(n, 1);
     h_read_level.assign(n, 0xFF);
+    // the compute stream picks up after everything staged here
+    GNB_CUDA(cudaEventRecord(ev_in, st_in));
+    if (st != st_in)
+        GNB_CUDA(cudaStreamWaitEvent(st, ev_in, 0));
     staged = true;
     return GNB_OK;
 }
@@ -1195,7 +1244,7 @@ int BatchCtx::run_level(size_t li)
     for (size_t fi = 0; fi < L.filters.size(); ++fi)
     {
         FilterRt              &F  = L.filters[fi];
-        std::vector<uint64_t> &Ft = tuples[li][fi];
+        PinnedVec<uint64_t>   &Ft = tuples[li][fi];
         Ft.clear();
         if (n == 0)
             continue;
@@ -1680,7 +1729,7 @@ extern "C" int gnb_session_stage(gnb_session *s, const char *b1, uint64_t l1, co
     GNB_TRY(c.stage(b1, l1, b2, l2, fin));
     if (n_reads)
         *n_reads = c.n_reads;
-    GNB_CUDA(cudaStreamSynchronize(c.st));
+    GNB_CUDA(cudaStreamSynchronize(c.st_in));
     return GNB_OK;
 }
 
