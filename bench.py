@@ -299,7 +299,7 @@ def main():
     h2d, d2h, n_class, n_bytes_all, r = e2e_loop(args.steps, 1)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_sort=r.ms_sort, ms_host_index=r.ms_host_index, ms_host_finish=r.ms_host_finish, ms_submit_to_collect=r.ms_total, batches_in_flight=cap)
+    last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_sort=r.ms_sort, ms_worker_job=r.ms_host_index, ms_host_finish=r.ms_host_finish, ms_host_merge=r.ms_d2h, ms_submit_to_collect=r.ms_total, batches_in_flight=cap)
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

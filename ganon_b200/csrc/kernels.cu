@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
     k_minimisers(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1,
                  const uint8_t *__restrict__ blk2, const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2,
                  uint32_t n_reads, uint32_t k, uint32_t w, uint32_t nv_cap, uint32_t nb_cap, uint32_t *__restrict__ counts,
-                 const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes)
+                 const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count)
 {
+    uint32_t warp_max = 0;
     extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t *sv = reinterpret_cast<uint64_t *>(k2_smem) + (size_t)wib * nv_cap;
@@ -238,14 +239,17 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
         }
         if (!WRITE && lane == 0)
             counts[read] = total;
+        warp_max = max(warp_max, total);
     }
+    if (!WRITE && max_count != nullptr && lane == 0 && warp_max)
+        atomicMax(max_count, warp_max);
 }
 
 } // namespace
 
 void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
                        const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, bool write, uint32_t *counts,
-                       const uint64_t *hash_off, uint64_t *hashes, cudaStream_t st)
+                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, cudaStream_t st)
 {
     if (n_reads == 0)
         return;
@@ -265,12 +269,12 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     if (write)
     {
         cudaFuncSetAttribute(k_minimisers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_minimisers<true><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes);
+        k_minimisers<true><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes, max_count);
     }
     else
     {
         cudaFuncSetAttribute(k_minimisers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_minimisers<false><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes);
+        k_minimisers<false><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes, max_count);
     }
 }
 

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -164,6 +165,7 @@ struct FilterRt
     IbfDev      dev{};
     DevBuf      d_single, d_bin_node, d_seg_off, d_segs;
     std::vector<double>   node_fpr;   // [n_level_targets] fpr of this filter's target for the node (0 if absent)
+    std::vector<uint8_t>  node_fpr_class; // [n_level_targets] index into LevelRt::fpr_classes, 255 = none
     std::vector<uint8_t>  node_multi; // [n_level_targets] 1: node's bins form several segments (partial tuples)
     // HIBF: one IbfDev per sub-IBF (tables carved out of the shared device arrays above)
     bool                  is_hibf = false;
@@ -186,6 +188,7 @@ struct LevelRt
     std::vector<int32_t>     parent;
     std::vector<uint32_t>    depth;
     int32_t                  root = -1;
+    std::vector<double>      fpr_classes; // distinct per-target fpr values (at most kMemoClasses, else empty)
     // accounting per prefix
     std::vector<std::unordered_map<uint32_t, Rep>> rep;
     std::vector<gnb_totals>                        total;
@@ -235,12 +238,18 @@ inline double fpr_query_q(uint64_t n_hashes, uint64_t count, double fpr)
     return q;
 }
 
+constexpr size_t kDenseRepNodes = 1u << 16;
+constexpr size_t kMemoClasses   = 8;
+
 struct Worker
 {
     std::unordered_map<FprKey, double, FprKeyHash> memo;
     std::vector<std::string>                       all_text, one_text; // per level
     std::string                                    unc_text;
-    std::vector<std::unordered_map<uint32_t, Rep>> rep;   // per level
+    std::vector<std::unordered_map<uint32_t, Rep>> rep;   // per level (large node tables)
+    std::vector<std::vector<Rep>>                  rep_dense;   // per level (node tables up to kDenseRepNodes)
+    std::vector<std::vector<uint32_t>>             rep_touched; // nodes with a non-zero dense entry
+    std::vector<double>                            memo_table;  // [fpr class][n < 256][count < 256], NaN = not computed
     std::vector<gnb_totals>                        total; // per level
     std::vector<uint64_t>                          m_off; // CSR pieces for the structured result
     std::vector<uint32_t>                          m_target, m_count;
@@ -345,6 +354,7 @@ struct BatchCtx
     gnb_batch_result           timing{};
     gnb_batch_result           result{};
     uint64_t                   launches = 0;
+    int                        finish_T = 0; // worker count of the last finish_level
 
     // asynchronous job (gnb_session_submit / gnb_session_collect)
     std::thread job;
@@ -435,6 +445,11 @@ int BatchCtx::init(cudaStream_t external)
         w.all_text.resize(levels.size());
         w.one_text.resize(levels.size());
         w.rep.resize(levels.size());
+        w.rep_dense.resize(levels.size());
+        w.rep_touched.resize(levels.size());
+        for (size_t li = 0; li < levels.size(); ++li)
+            if (levels[li].node_names.size() <= kDenseRepNodes)
+                w.rep_dense[li].resize(levels[li].node_names.size());
         w.total.resize(levels.size());
     }
     GNB_TRY(d_cursor.ensure(64));
@@ -844,13 +859,40 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
         int rc = s->build_level_tables(L);
         if (rc != GNB_OK)
             return rc;
+        // fpr classes for the direct-mapped --fpr-query memo
+        {
+            std::vector<double> classes;
+            bool                ok = true;
+            for (auto &F : L.filters)
+                for (double v : F.node_fpr)
+                    if (ok && std::find(classes.begin(), classes.end(), v) == classes.end())
+                    {
+                        if (classes.size() == kMemoClasses)
+                            ok = false;
+                        else
+                            classes.push_back(v);
+                    }
+            if (!ok)
+                classes.clear();
+            L.fpr_classes = classes;
+            for (auto &F : L.filters)
+            {
+                F.node_fpr_class.assign(F.node_fpr.size(), 255);
+                for (size_t i = 0; i < F.node_fpr.size(); ++i)
+                {
+                    auto it = std::find(classes.begin(), classes.end(), F.node_fpr[i]);
+                    if (it != classes.end())
+                        F.node_fpr_class[i] = (uint8_t)(it - classes.begin());
+                }
+            }
+        }
     }
 
     s->n_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     if (s->n_threads > 64)
         s->n_threads = 64;
     // batches in flight: 1 on a caller-provided stream (its events must bracket the work), else 3
-    int n_slots = cfg->cuda_stream ? 1 : 3;
+    int n_slots = cfg->cuda_stream ? 1 : 4;
     if (const char *e = getenv("GANON_B200_SLOTS"))
         n_slots = std::max(1, std::min(8, atoi(e)));
     for (int i = 0; i < n_slots; ++i)
@@ -1106,7 +1148,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     if (hashed_k == k && hashed_w == w)
         return GNB_OK;
     const uint32_t n = n_reads;
-    h_counts.assign(n, 0);
+    h_counts.resize(n);
     total_hashes = 0;
     if (n == 0)
     {
@@ -1116,27 +1158,28 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     }
     const uint8_t *b2 = paired ? d_blk2.as<uint8_t>() : nullptr;
     GNB_CUDA(cudaEventRecord(ev[2], st));
+    uint32_t *d_max = d_status.as<uint32_t>() + 12;
+    GNB_CUDA(cudaMemsetAsync(d_max, 0, 4, st));
     launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
-                      false, d_counts.as<uint32_t>(), nullptr, nullptr, st);
+                      false, d_counts.as<uint32_t>(), nullptr, nullptr, d_max, st);
     const size_t tmpb = scan_tmp_bytes(n);
     GNB_TRY(d_tmp.ensure(tmpb));
     launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
     launches += 2;
     uint64_t total = 0;
+    uint32_t mx    = 0;
     GNB_CUDA(cudaMemcpyAsync(&total, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaMemcpyAsync(&mx, d_max, 4, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaStreamSynchronize(st));
     total_hashes = total;
     timing.d2h_bytes += 8 + (uint64_t)n * 4;
     GNB_TRY(d_hashes.ensure((total + 1) * 8));
     launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
-                      true, nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), st);
+                      true, nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, st);
     launches += 1;
     GNB_CUDA(cudaEventRecord(ev[3], st));
     GNB_CUDA(cudaGetLastError());
-    uint32_t mx = 0;
-    for (uint32_t i = 0; i < n; ++i)
-        mx = std::max(mx, h_counts[i]);
     max_hashes_ub = mx;
     hashed_k = k;
     hashed_w = w;
@@ -1237,9 +1280,12 @@ int BatchCtx::run_level(size_t li)
         act = d_active.as<uint8_t>();
     }
     uint64_t active_hashes = 0;
-    for (uint32_t i = 0; i < n; ++i)
-        if (h_active[i] && h_counts[i] <= 65535)
-            active_hashes += h_counts[i];
+    if (li == 0 && max_hashes_ub <= 65535)
+        active_hashes = total_hashes;
+    else
+        for (uint32_t i = 0; i < n; ++i)
+            if (h_active[i] && h_counts[i] <= 65535)
+                active_hashes += h_counts[i];
     float ms_sort = 0, ms_k3 = 0;
     for (size_t fi = 0; fi < L.filters.size(); ++fi)
     {
@@ -1317,12 +1363,23 @@ int BatchCtx::finish_level(size_t li)
     const bool     first = li == 0, last = li + 1 == levels.size();
     const int      T = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, (n + 4095) / 4096));
     const uint8_t *id_base = reinterpret_cast<const uint8_t *>(blk1);
+    finish_T = T;
 
     auto work = [&](int tid) {
         Worker        &W  = workers[tid];
         const uint32_t r0 = (uint32_t)((uint64_t)n * tid / T), r1 = (uint32_t)((uint64_t)n * (tid + 1) / T);
         gnb_totals    &tot = W.total[li];
-        auto          &rep = W.rep[li];
+        const bool     dense = !W.rep_dense[li].empty();
+        auto rep_at = [&](uint32_t node) -> Rep & {
+            if (dense)
+            {
+                Rep &x = W.rep_dense[li][node];
+                if (!(x.matches | x.seqs_lca | x.seqs_unique | x.discarded_matches_filter | x.discarded_matches_fprquery))
+                    W.rep_touched[li].push_back(node);
+                return x;
+            }
+            return W.rep[li][node];
+        };
         const size_t   nf  = L.filters.size();
         std::vector<size_t> cur(nf);
         for (size_t f = 0; f < nf; ++f)
@@ -1334,7 +1391,10 @@ int BatchCtx::finish_level(size_t li)
         {
             uint32_t node, count;
             double   fpr;
+            uint8_t  cls;
         };
+        if (L.fpr_query < 1.0 && !L.fpr_classes.empty() && W.memo_table.size() != L.fpr_classes.size() * 65536)
+            W.memo_table.assign(L.fpr_classes.size() * 65536, std::numeric_limits<double>::quiet_NaN());
         std::vector<M> best, merged, one_filter;
         for (uint32_t r = r0; r < r1; ++r)
         {
@@ -1394,7 +1454,7 @@ int BatchCtx::finish_level(size_t li)
                         if (sum < cutoff)
                             continue;
                     }
-                    one_filter.push_back(M{node, (uint32_t)sum, F.node_fpr[node]});
+                    one_filter.push_back(M{node, (uint32_t)sum, F.node_fpr[node], F.node_fpr_class[node]});
                 }
                 // merge into best (both sorted by node): keep the strictly larger count (GC.cpp:531-539)
                 if (best.empty())
@@ -1450,27 +1510,37 @@ int BatchCtx::finish_level(size_t li)
                     {
                         if (L.fpr_query < 1.0)
                         {
-                            double   q;
-                            FprKey   key;
-                            memcpy(&key.fpr_bits, &m.fpr, 8);
-                            key.n = nh;
-                            key.c = m.count;
-                            auto it = W.memo.find(key);
-                            if (it != W.memo.end())
-                                q = it->second;
+                            double q;
+                            if (m.cls != 255 && nh < 256 && m.count < 256 && !W.memo_table.empty())
+                            {
+                                double &slot = W.memo_table[((size_t)m.cls << 16) | (nh << 8) | m.count];
+                                if (std::isnan(slot))
+                                    slot = fpr_query_q(nh, m.count, m.fpr);
+                                q = slot;
+                            }
                             else
                             {
-                                q = fpr_query_q(nh, m.count, m.fpr);
-                                W.memo.emplace(key, q);
+                                FprKey key;
+                                memcpy(&key.fpr_bits, &m.fpr, 8);
+                                key.n = nh;
+                                key.c = m.count;
+                                auto it = W.memo.find(key);
+                                if (it != W.memo.end())
+                                    q = it->second;
+                                else
+                                {
+                                    q = fpr_query_q(nh, m.count, m.fpr);
+                                    W.memo.emplace(key, q);
+                                }
                             }
                             if (q > L.fpr_query)
                             {
-                                rep[m.node].discarded_matches_fprquery++;
+                                rep_at(m.node).discarded_matches_fprquery++;
                                 tot.discarded_matches_fprquery++;
                                 continue;
                             }
                         }
-                        rep[m.node].matches++;
+                        rep_at(m.node).matches++;
                         tot.matches++;
                         W.m_target.push_back(m.node);
                         W.m_count.push_back(m.count);
@@ -1478,7 +1548,7 @@ int BatchCtx::finish_level(size_t li)
                     }
                     else
                     {
-                        rep[m.node].discarded_matches_filter++;
+                        rep_at(m.node).discarded_matches_filter++;
                         tot.discarded_matches_filter++;
                     }
                 }
@@ -1497,7 +1567,7 @@ int BatchCtx::finish_level(size_t li)
                 uint64_t     one_count = W.m_count[m_begin];
                 if (kept == 1)
                 {
-                    rep[one_node].seqs_unique++;
+                    rep_at(one_node).seqs_unique++;
                     tot.seqs_unique++;
                 }
                 else if (!skip_lca)
@@ -1505,12 +1575,12 @@ int BatchCtx::finish_level(size_t li)
                     uint32_t l = L.lca2(W.m_target[m_begin], W.m_target[m_begin + 1]);
                     for (size_t i = 2; i < kept; ++i)
                         l = L.lca2(l, W.m_target[m_begin + i]);
-                    rep[l].seqs_lca++;
+                    rep_at(l).seqs_lca++;
                     one_node  = l;
                     one_count = max_c;
                 }
                 else
-                    rep[(uint32_t)L.root].seqs_lca++;
+                    rep_at((uint32_t)L.root).seqs_lca++;
                 if (!skip_lca && cfg.output_lca)
                 {
                     std::string &o = W.one_text[li];
@@ -1593,61 +1663,139 @@ void BatchCtx::fill_timings(gnb_batch_result *t)
     t->consumed2         = !paired ? 0 : parse_error ? len2 : consumed2;
     t->n_kernel_launches = launches;
     t->n_minimisers      = 0;
-    for (uint32_t i = 0; i < n_reads && i < h_counts.size(); ++i)
-        if (h_counts[i] <= 65535)
-            t->n_minimisers += h_counts[i];
+    if (max_hashes_ub <= 65535)
+        t->n_minimisers = hashed_k ? total_hashes : 0;
+    else
+        for (uint32_t i = 0; i < n_reads && i < h_counts.size(); ++i)
+            if (h_counts[i] <= 65535)
+                t->n_minimisers += h_counts[i];
 }
 
 // merge the workers' pieces into the result buffers and the session's accounting
 int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
 {
+    auto           t_collect = Clock::now();
     const uint32_t n = n_reads;
-    r_all.assign(levels.size(), std::string());
-    r_one.assign(levels.size(), std::string());
-    r_unc.clear();
-    r_match_off.assign((size_t)n + 1, 0);
+    const int      T = (int)workers.size();
+    const size_t   NL = levels.size();
+    r_all.resize(NL);
+    r_one.resize(NL);
+    // sizes and per-worker offsets of every output piece
+    std::vector<size_t> off_all(NL * (T + 1), 0), off_one(NL * (T + 1), 0), off_unc(T + 1, 0), off_m(T + 1, 0);
     uint64_t n_classified = 0;
+    for (int w = 0; w < T; ++w)
+    {
+        for (size_t li = 0; li < NL; ++li)
+        {
+            off_all[li * (T + 1) + w + 1] = off_all[li * (T + 1) + w] + workers[w].all_text[li].size();
+            off_one[li * (T + 1) + w + 1] = off_one[li * (T + 1) + w] + workers[w].one_text[li].size();
+        }
+        off_unc[w + 1] = off_unc[w] + workers[w].unc_text.size();
+        off_m[w + 1]   = off_m[w] + workers[w].m_target.size();
+        n_classified += workers[w].n_classified;
+    }
+    for (size_t li = 0; li < NL; ++li)
+    {
+        r_all[li].resize(off_all[li * (T + 1) + T]);
+        r_one[li].resize(off_one[li * (T + 1) + T]);
+    }
+    r_unc.resize(off_unc[T]);
+    r_match_off.resize((size_t)n + 1);
+    r_match_target.resize(off_m[T]);
+    r_match_count.resize(off_m[T]);
+    // With one hierarchy level the workers' match lists, taken in worker order, already are the CSR value arrays
+    // (worker w finished the reads [n*w/Tf, n*(w+1)/Tf) in order); with several levels the lists interleave.
+    const bool csr_parallel = NL == 1 && finish_T > 0;
+    auto piece = [&](int w) {
+        Worker &W = workers[w];
+        for (size_t li = 0; li < NL; ++li)
+        {
+            if (!W.all_text[li].empty())
+                memcpy(&r_all[li][off_all[li * (T + 1) + w]], W.all_text[li].data(), W.all_text[li].size());
+            if (!W.one_text[li].empty())
+                memcpy(&r_one[li][off_one[li * (T + 1) + w]], W.one_text[li].data(), W.one_text[li].size());
+        }
+        if (!W.unc_text.empty())
+            memcpy(&r_unc[off_unc[w]], W.unc_text.data(), W.unc_text.size());
+        if (csr_parallel)
+        {
+            if (!W.m_target.empty())
+            {
+                memcpy(&r_match_target[off_m[w]], W.m_target.data(), W.m_target.size() * 4);
+                memcpy(&r_match_count[off_m[w]], W.m_count.data(), W.m_count.size() * 4);
+            }
+            if (w < finish_T)
+            {
+                const uint32_t r0 = (uint32_t)((uint64_t)n * w / finish_T), r1 = (uint32_t)((uint64_t)n * (w + 1) / finish_T);
+                uint64_t       pos = off_m[w];
+                size_t         nx  = 0;
+                for (uint32_t r = r0; r < r1; ++r)
+                {
+                    r_match_off[r] = pos;
+                    if (nx + 1 < W.m_off.size() && W.m_off[nx] == r)
+                    {
+                        pos += W.m_off[nx + 1];
+                        nx += 2;
+                    }
+                }
+            }
+        }
+    };
+    if (n < 65536)
+        for (int w = 0; w < T; ++w)
+            piece(w);
+    else
+    {
+        std::vector<std::thread> th;
+        for (int w = 0; w < T; ++w)
+            th.emplace_back(piece, w);
+        for (auto &t : th)
+            t.join();
+    }
+    if (csr_parallel)
+        r_match_off[n] = off_m[T];
+    else
+    {
+        std::fill(r_match_off.begin(), r_match_off.end(), 0);
+        for (auto &W : workers)
+            for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
+                r_match_off[W.m_off[i] + 1] = W.m_off[i + 1];
+        for (size_t i = 0; i < n; ++i)
+            r_match_off[i + 1] += r_match_off[i];
+        for (auto &W : workers)
+        {
+            size_t p = 0;
+            for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
+            {
+                const uint64_t r = W.m_off[i], k = W.m_off[i + 1];
+                std::copy(W.m_target.begin() + p, W.m_target.begin() + p + k, r_match_target.begin() + r_match_off[r]);
+                std::copy(W.m_count.begin() + p, W.m_count.begin() + p + k, r_match_count.begin() + r_match_off[r]);
+                p += k;
+            }
+        }
+    }
     {
         std::lock_guard<std::mutex> lock(S->acc_mutex);
         S->ensure_prefix(prefix_id);
-        for (size_t li = 0; li < levels.size(); ++li)
+        for (size_t li = 0; li < NL; ++li)
         {
             LevelRt &L = levels[li];
             for (auto &W : workers)
             {
-                r_all[li] += W.all_text[li];
-                r_one[li] += W.one_text[li];
                 for (auto const &[node, rp] : W.rep[li])
                     L.rep[prefix_id][node].add(rp);
                 W.rep[li].clear();
+                for (uint32_t node : W.rep_touched[li])
+                {
+                    L.rep[prefix_id][node].add(W.rep_dense[li][node]);
+                    W.rep_dense[li][node] = Rep{};
+                }
+                W.rep_touched[li].clear();
                 add_totals(L.total[prefix_id], W.total[li]);
                 W.total[li] = gnb_totals{};
             }
         }
         levels[0].total[prefix_id].input_seqs += n;
-    }
-    // structured CSR: counts per read, then fill
-    for (auto &W : workers)
-    {
-        r_unc += W.unc_text;
-        n_classified += W.n_classified;
-        for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
-            r_match_off[W.m_off[i] + 1] = W.m_off[i + 1];
-    }
-    for (size_t i = 0; i < n; ++i)
-        r_match_off[i + 1] += r_match_off[i];
-    r_match_target.assign(r_match_off[n], 0);
-    r_match_count.assign(r_match_off[n], 0);
-    for (auto &W : workers)
-    {
-        size_t p = 0;
-        for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
-        {
-            const uint64_t r = W.m_off[i], k = W.m_off[i + 1];
-            std::copy(W.m_target.begin() + p, W.m_target.begin() + p + k, r_match_target.begin() + r_match_off[r]);
-            std::copy(W.m_count.begin() + p, W.m_count.begin() + p + k, r_match_count.begin() + r_match_off[r]);
-            p += k;
-        }
     }
     r_all_p.clear();
     r_one_p.clear();
@@ -1660,6 +1808,7 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
         r_one_p.push_back(r_one[li].data());
         r_one_l.push_back(r_one[li].size());
     }
+    timing.ms_d2h = (float)ms_since(t_collect); // host merge of the workers' pieces (no device copy happens here)
     fill_timings(&result);
     result.match_off    = r_match_off.data();
     result.match_target = r_match_target.data();
@@ -1832,7 +1981,9 @@ extern "C" int gnb_session_submit(gnb_session *s, uint32_t prefix_id, const char
     c.busy   = true;
     c.job_rc = GNB_OK;
     c.job    = std::thread([&c, prefix_id]() {
+        auto tj  = Clock::now();
         c.job_rc = c.finish(prefix_id, nullptr);
+        c.result.ms_host_index = ms_since(tj); // async form: wall time of the worker job
         if (c.job_rc != GNB_OK)
             c.job_err = gnb_last_error();
     });
@@ -2069,7 +2220,7 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         GNB_CUDA(cudaMemcpy(d_off.p, off.data(), n * 4, cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_len.p, len.data(), n * 4, cudaMemcpyHostToDevice));
         launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, false,
-                          d_cnt.as<uint32_t>(), nullptr, nullptr, 0);
+                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, 0);
         launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
         GNB_CUDA(cudaMemcpy(hash_off, d_hoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
         const uint64_t total = hash_off[n];
@@ -2077,7 +2228,7 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         {
             GNB_TRY(d_h.ensure(total * 8));
             launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, true, nullptr,
-                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), 0);
+                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, 0);
             GNB_CUDA(cudaMemcpy(hashes, d_h.p, total * 8, cudaMemcpyDeviceToHost));
         }
         GNB_CUDA(cudaGetLastError());
