@@ -114,13 +114,15 @@ GNB_HD uint32_t threshold_cutoff(uint32_t n_hashes, double rel_cutoff)
 // ---------------------------------------------------------------------------------------------------------------
 // K2: counts pass (write=false -> counts[n_reads]) and write pass (write=true -> hashes at hash_off).
 void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2,
-                       const uint32_t *off2, const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, bool write,
-                       uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, cudaStream_t st);
+                       const uint32_t *off2, const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, int mode,
+                       uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count,
+                       cudaStream_t st);
+void launch_hash_upper_bounds(const uint32_t *len1, const uint32_t *len2, uint32_t n, uint32_t w, uint32_t *ub, cudaStream_t st);
 // exclusive scan of counts (values > 65535 are kept in the offsets; K3 skips such reads) -> hash_off[n+1]
 void   launch_scan_counts(const uint32_t *counts, uint64_t *hash_off, uint32_t n_reads, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t scan_tmp_bytes(uint32_t n_reads);
 // K3 sparse: tuples of (read, node, count) for nodes reaching the cutoff (+ partial sums of multi-segment nodes)
-void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active,
+void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint32_t *counts, const uint8_t *active,
                       uint32_t n_reads, uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor,
                       uint64_t cap, cudaStream_t st);
 // K3 dense (test hook): counts[n_reads][row_words*64]
@@ -128,7 +130,7 @@ void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint6
                             uint32_t max_hashes, uint16_t *counts, cudaStream_t st);
 // K3h: one traversal round of an HIBF (items = (read, sub-IBF) pairs); see kernels.cu
 void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *items, uint32_t n_items, const uint64_t *hashes, const uint64_t *hash_off,
-                       uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
+                       const uint32_t *counts, uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
                        unsigned long long *items_cursor, uint64_t items_cap, cudaStream_t st);
 constexpr uint32_t kMergedBinFlag = 0x80000000u;
 // sort tuples by (read, node)

@@ -209,14 +209,17 @@ __device__ __forceinline__ bool dna15_valid(uint8_t c)
     return i < 26 && ((ok >> i) & 1u);
 }
 
-template <bool WRITE>
+template <int KMODE> // 0: count only, 1: write at hash_off, 2: write at hash_off and count (single pass)
 __global__ void __launch_bounds__(K2_WARPS * 32)
     k_minimisers(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1,
                  const uint8_t *__restrict__ blk2, const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2,
                  uint32_t n_reads, uint32_t k, uint32_t w, uint32_t nv_cap, uint32_t nb_cap, uint32_t *__restrict__ counts,
-                 const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count)
+                 const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count,
+                 unsigned long long *__restrict__ sum_count)
 {
+    constexpr bool WRITE = KMODE != 0;
     uint32_t warp_max = 0;
+    uint64_t warp_sum = 0;
     extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t *sv = reinterpret_cast<uint64_t *>(k2_smem) + (size_t)wib * nv_cap;
@@ -237,19 +240,42 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
                     total += minimisers_of_mate<WRITE>(blk2 + off2[read], L2, k, w, seed, WRITE ? out + total : nullptr, sv, sb, lane);
             }
         }
-        if (!WRITE && lane == 0)
+        if (KMODE != 1 && lane == 0)
             counts[read] = total;
         warp_max = max(warp_max, total);
+        warp_sum += total;
     }
-    if (!WRITE && max_count != nullptr && lane == 0 && warp_max)
-        atomicMax(max_count, warp_max);
+    if (KMODE != 1 && lane == 0 && warp_max)
+    {
+        if (max_count != nullptr)
+            atomicMax(max_count, warp_max);
+        if (sum_count != nullptr)
+            atomicAdd(sum_count, (unsigned long long)warp_sum);
+    }
+}
+
+// upper bound of the minimisers of a read (pair): every window could emit (GC.cpp:690-700)
+__global__ void k_hash_upper_bounds(const uint32_t *__restrict__ len1, const uint32_t *__restrict__ len2, uint32_t n, uint32_t w, uint32_t *__restrict__ ub)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t a = len1[i];
+    uint32_t       u = 0;
+    if (a >= w)
+    {
+        u = a - w + 1;
+        if (len2 != nullptr && len2[i] >= w)
+            u += len2[i] - w + 1;
+    }
+    ub[i] = u;
 }
 
 } // namespace
 
 void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
-                       const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, bool write, uint32_t *counts,
-                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, cudaStream_t st)
+                       const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, int mode, uint32_t *counts,
+                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count, cudaStream_t st)
 {
     if (n_reads == 0)
         return;
@@ -266,16 +292,25 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     if (fine > full)
         full = fine;
     const uint32_t grid = want < full ? want : full;
-    if (write)
-    {
-        cudaFuncSetAttribute(k_minimisers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_minimisers<true><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes, max_count);
+#define GNB_K2(M)                                                                                                                     \
+    {                                                                                                                                 \
+        cudaFuncSetAttribute(k_minimisers<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                \
+        k_minimisers<M><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, \
+                                                            hash_off, hashes, max_count, sum_count);                                  \
     }
+    if (mode == 0)
+        GNB_K2(0)
+    else if (mode == 1)
+        GNB_K2(1)
     else
-    {
-        cudaFuncSetAttribute(k_minimisers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_minimisers<false><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, hash_off, hashes, max_count);
-    }
+        GNB_K2(2)
+#undef GNB_K2
+}
+
+void launch_hash_upper_bounds(const uint32_t *len1, const uint32_t *len2, uint32_t n, uint32_t w, uint32_t *ub, cudaStream_t st)
+{
+    if (n)
+        k_hash_upper_bounds<<<(n + 255) / 256, 256, 0, st>>>(len1, len2, n, w, ub);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -407,8 +442,8 @@ struct WorkOut
 // One (read, chunk) work item: gather + AND + bit-sliced count over the read's minimisers, then the epilogue.
 template <int H, int NP, bool ALIGNED, int MODE>
 __device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint32_t chunk, const uint64_t *__restrict__ hashes,
-                                           const uint64_t *__restrict__ hash_off, double rel_cutoff, const WorkOut &wo, uint64_t *s_row,
-                                           uint32_t lane)
+                                           const uint64_t *__restrict__ hash_off, const uint32_t *__restrict__ counts, double rel_cutoff,
+                                           const WorkOut &wo, uint64_t *s_row, uint32_t lane)
 {
     constexpr int  PER    = 32 / H; // minimisers whose rows are staged per round
     const uint64_t seed_l = ibf_seed(lane % H);
@@ -417,7 +452,7 @@ __device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint3
     const uint64_t  cap   = wo.cap;
     uint16_t *const dense = wo.dense;
     const uint64_t h0 = hash_off[read];
-    const uint64_t nn = hash_off[read + 1] - h0;
+    const uint64_t nn = counts != nullptr ? (uint64_t)counts[read] : hash_off[read + 1] - h0; // upper-bound vs exact layout
     if (nn == 0 || nn > 65535) // skipped: shorter than the window / more minimisers than the counter type holds
         return;
     const uint32_t n  = (uint32_t)nn;
@@ -605,7 +640,7 @@ __device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint3
 
 template <int H, int NP, bool ALIGNED, int MODE>
 __global__ void __launch_bounds__(K3_WARPS * 32)
-    k_ibf_count(const IbfDev f, const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ hash_off,
+    k_ibf_count(const IbfDev f, const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ hash_off, const uint32_t *__restrict__ counts,
                 const uint8_t *__restrict__ active, uint32_t n_reads, double rel_cutoff, const WorkOut wo)
 {
     __shared__ uint64_t s_row[K3_WARPS][32];
@@ -618,7 +653,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         const uint32_t chunk = (uint32_t)(item - (uint64_t)read * f.n_chunks);
         if (active != nullptr && active[read] == 0)
             continue;
-        count_item<H, NP, ALIGNED, MODE>(f, read, chunk, hashes, hash_off, rel_cutoff, wo, s_row[wib], lane);
+        count_item<H, NP, ALIGNED, MODE>(f, read, chunk, hashes, hash_off, counts, rel_cutoff, wo, s_row[wib], lane);
     }
 }
 
@@ -628,7 +663,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
 template <int H, int NP>
 __global__ void __launch_bounds__(K3_WARPS * 32)
     k_hibf_count(const IbfDev *__restrict__ table, const uint2 *__restrict__ items, uint32_t n_items, const uint64_t *__restrict__ hashes,
-                 const uint64_t *__restrict__ hash_off, double rel_cutoff, const WorkOut wo)
+                 const uint64_t *__restrict__ hash_off, const uint32_t *__restrict__ counts, double rel_cutoff, const WorkOut wo)
 {
     __shared__ uint64_t s_row[K3_WARPS][32];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -637,12 +672,12 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         const uint2  item = items[it];
         const IbfDev f    = table[item.y];
         for (uint32_t chunk = 0; chunk < f.n_chunks; ++chunk)
-            count_item<H, NP, false, 2>(f, item.x, chunk, hashes, hash_off, rel_cutoff, wo, s_row[wib], lane);
+            count_item<H, NP, false, 2>(f, item.x, chunk, hashes, hash_off, counts, rel_cutoff, wo, s_row[wib], lane);
     }
 }
 
 template <int H, int NP, bool ALIGNED, int MODE>
-void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint32_t *counts, const uint8_t *active, uint32_t n_reads,
                double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint16_t *dense, cudaStream_t st)
 {
     auto     kern  = k_ibf_count<H, NP, ALIGNED, MODE>;
@@ -663,17 +698,17 @@ void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off
         full = fine;
     const uint32_t grid  = (uint32_t)(want < full ? want : full);
     WorkOut wo{tuples, cursor, cap, dense, nullptr, nullptr, 0};
-    kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, active, n_reads, rel_cutoff, wo);
+    kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, counts, active, n_reads, rel_cutoff, wo);
 }
 
 template <int H, int MODE>
-void dispatch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+void dispatch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint32_t *counts, const uint8_t *active, uint32_t n_reads,
                  uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap,
                  uint16_t *dense, cudaStream_t st)
 {
     const bool aligned = (f.row_words % 2 == 0) && (((uintptr_t)f.data & 15) == 0);
     const bool small   = max_hashes < 256; // 8 planes hold counts up to 255
-#define GNB_K3(NPV, AL) launch_k3<H, NPV, AL, MODE>(f, hashes, hash_off, active, n_reads, rel_cutoff, tuples, cursor, cap, dense, st)
+#define GNB_K3(NPV, AL) launch_k3<H, NPV, AL, MODE>(f, hashes, hash_off, counts, active, n_reads, rel_cutoff, tuples, cursor, cap, dense, st)
     if (small)
     {
         if (aligned)
@@ -692,32 +727,32 @@ void dispatch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_o
 }
 
 template <int MODE>
-void dispatch_k3_h(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+void dispatch_k3_h(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint32_t *counts, const uint8_t *active, uint32_t n_reads,
                    uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap,
                    uint16_t *dense, cudaStream_t st)
 {
     switch (f.hash_funs)
     {
-    case 1: dispatch_k3<1, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
-    case 2: dispatch_k3<2, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
-    case 3: dispatch_k3<3, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
-    case 4: dispatch_k3<4, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
-    default: dispatch_k3<5, MODE>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 1: dispatch_k3<1, MODE>(f, hashes, hash_off, counts, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 2: dispatch_k3<2, MODE>(f, hashes, hash_off, counts, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 3: dispatch_k3<3, MODE>(f, hashes, hash_off, counts, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    case 4: dispatch_k3<4, MODE>(f, hashes, hash_off, counts, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
+    default: dispatch_k3<5, MODE>(f, hashes, hash_off, counts, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, dense, st); break;
     }
 }
 
 } // namespace
 
-void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint8_t *active, uint32_t n_reads,
+void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, const uint32_t *counts, const uint8_t *active, uint32_t n_reads,
                       uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, cudaStream_t st)
 {
     if (n_reads == 0)
         return;
-    dispatch_k3_h<0>(f, hashes, hash_off, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, nullptr, st);
+    dispatch_k3_h<0>(f, hashes, hash_off, counts, active, n_reads, max_hashes, rel_cutoff, tuples, cursor, cap, nullptr, st);
 }
 
 void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *items, uint32_t n_items, const uint64_t *hashes, const uint64_t *hash_off,
-                       uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
+                       const uint32_t *counts, uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
                        unsigned long long *items_cursor, uint64_t items_cap, cudaStream_t st)
 {
     if (n_items == 0)
@@ -728,9 +763,9 @@ void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *ite
     const bool     small = max_hashes < 256;
 #define GNB_HIBF(HV)                                                                                                             \
     if (small)                                                                                                                   \
-        k_hibf_count<HV, 8><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, rel_cutoff, wo);           \
+        k_hibf_count<HV, 8><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, counts, rel_cutoff, wo);           \
     else                                                                                                                         \
-        k_hibf_count<HV, 16><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, rel_cutoff, wo);
+        k_hibf_count<HV, 16><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, counts, rel_cutoff, wo);
     switch (hash_funs)
     {
     case 1: GNB_HIBF(1) break;
@@ -747,7 +782,7 @@ void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint6
 {
     if (n_reads == 0)
         return;
-    dispatch_k3_h<1>(f, hashes, hash_off, nullptr, n_reads, max_hashes, 0.0, nullptr, nullptr, 0, counts, st);
+    dispatch_k3_h<1>(f, hashes, hash_off, nullptr, nullptr, n_reads, max_hashes, 0.0, nullptr, nullptr, 0, counts, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

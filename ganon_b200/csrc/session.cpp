@@ -340,6 +340,7 @@ struct BatchCtx
     std::vector<uint8_t>  h_active;
     std::vector<uint8_t>  h_read_level;
     uint64_t              total_hashes = 0;
+    bool                  d_counts_valid = false;
     uint64_t              hibf_bytes = 0;
     float                 hibf_ms = 0;
     std::vector<std::vector<PinnedVec<uint64_t>>> tuples; // [level][filter], sorted by (read, node)
@@ -1156,30 +1157,65 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
         hashed_w = w;
         return GNB_OK;
     }
-    const uint8_t *b2 = paired ? d_blk2.as<uint8_t>() : nullptr;
+    const uint8_t  *b2   = paired ? d_blk2.as<uint8_t>() : nullptr;
+    const uint32_t *l2   = paired ? d_len2.as<uint32_t>() : nullptr;
+    uint32_t       *d_max = d_status.as<uint32_t>() + 12;
+    unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(d_status.as<uint32_t>() + 14);
     GNB_CUDA(cudaEventRecord(ev[2], st));
-    uint32_t *d_max = d_status.as<uint32_t>() + 12;
-    GNB_CUDA(cudaMemsetAsync(d_max, 0, 4, st));
-    launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
-                      false, d_counts.as<uint32_t>(), nullptr, nullptr, d_max, st);
-    const size_t tmpb = scan_tmp_bytes(n);
-    GNB_TRY(d_tmp.ensure(tmpb));
+    GNB_CUDA(cudaMemsetAsync(d_max, 0, 16, st));
+    // One pass: every read gets room for its upper bound of minimisers (one per window), so the offsets are known
+    // before K2 runs; K2 writes the hashes and the real counts.  If that layout would be too large (very long
+    // reads) fall back to count -> scan -> write with exact offsets.
+    GNB_TRY(d_tmp.ensure(scan_tmp_bytes(n)));
+    launch_hash_upper_bounds(d_len1.as<uint32_t>(), l2, n, w, d_counts.as<uint32_t>(), st);
     launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
     launches += 2;
+    uint64_t total_ub = 0;
+    GNB_CUDA(cudaMemcpyAsync(&total_ub, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    timing.d2h_bytes += 8;
     uint64_t total = 0;
     uint32_t mx    = 0;
-    GNB_CUDA(cudaMemcpyAsync(&total, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaMemcpyAsync(&mx, d_max, 4, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
-    total_hashes = total;
-    timing.d2h_bytes += 8 + (uint64_t)n * 4;
-    GNB_TRY(d_hashes.ensure((total + 1) * 8));
-    launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
-                      true, nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, st);
-    launches += 1;
-    GNB_CUDA(cudaEventRecord(ev[3], st));
+    struct
+    {
+        uint32_t           mx, pad;
+        unsigned long long sum;
+    } agg{};
+    if (total_ub * 8 <= (6ull << 30))
+    {
+        GNB_TRY(d_hashes.ensure((total_ub + 1) * 8));
+        launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 2,
+                          d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), d_max, d_sum, st);
+        launches += 1;
+        GNB_CUDA(cudaEventRecord(ev[3], st));
+        GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        d_counts_valid = true;
+        total = agg.sum;
+        mx    = agg.mx;
+    }
+    else
+    {
+        launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 0,
+                          d_counts.as<uint32_t>(), nullptr, nullptr, d_max, d_sum, st);
+        launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
+        launches += 2;
+        GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        total = agg.sum;
+        mx    = agg.mx;
+        GNB_TRY(d_hashes.ensure((total + 1) * 8));
+        launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 1,
+                          nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, nullptr, st);
+        launches += 1;
+        GNB_CUDA(cudaEventRecord(ev[3], st));
+        d_counts_valid = true; // exact layout: counts equal the offset differences
+    }
     GNB_CUDA(cudaGetLastError());
+    timing.d2h_bytes += 16 + (uint64_t)n * 4;
+    total_hashes  = total;
     max_hashes_ub = mx;
     hashed_k = k;
     hashed_w = w;
@@ -1219,7 +1255,7 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
             GNB_CUDA(cudaMemcpyAsync(d_cursor.p, &tuples_before, 8, cudaMemcpyHostToDevice, st));
             GNB_CUDA(cudaEventRecord(ev[4], st));
             launch_hibf_round(F.d_ibf_table.as<IbfDev>(), F.dev.hash_funs, cur->as<uint2>(), (uint32_t)n_items, d_hashes.as<uint64_t>(),
-                              d_hash_off.as<uint64_t>(), std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff, d_tuples_a.as<uint64_t>(),
+                              d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff, d_tuples_a.as<uint64_t>(),
                               d_cursor.as<unsigned long long>(), cap, nxt->as<uint2>(), d_items_cursor.as<unsigned long long>(), icap, st);
             GNB_CUDA(cudaEventRecord(ev[5], st));
             launches += 1;
@@ -1314,7 +1350,7 @@ int BatchCtx::run_level(size_t li)
         {
             GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
             GNB_CUDA(cudaEventRecord(ev[4], st));
-            launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
+            launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
                              d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
             GNB_CUDA(cudaEventRecord(ev[5], st));
             launches += 1;
@@ -2219,16 +2255,16 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         GNB_CUDA(cudaMemcpy(d_seq.p, seqs, seq_off[n], cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_off.p, off.data(), n * 4, cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_len.p, len.data(), n * 4, cudaMemcpyHostToDevice));
-        launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, false,
-                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, 0);
+        launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, 0,
+                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, 0);
         launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
         GNB_CUDA(cudaMemcpy(hash_off, d_hoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
         const uint64_t total = hash_off[n];
         if (hashes && total <= cap && total > 0)
         {
             GNB_TRY(d_h.ensure(total * 8));
-            launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, true, nullptr,
-                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, 0);
+            launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, 1, nullptr,
+                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, nullptr, 0);
             GNB_CUDA(cudaMemcpy(hashes, d_h.p, total * 8, cudaMemcpyDeviceToHost));
         }
         GNB_CUDA(cudaGetLastError());
