@@ -99,6 +99,132 @@ __device__ __forceinline__ void load_values(const uint8_t *__restrict__ seq, uin
     __syncwarp();
 }
 
+// ---- fast path (k <= 31): packed 2-bit bases, doubling-tree window minimum -----------------------------------------
+// rank table of dna4_rank packed 2 bits per letter 'a'..'z'
+__device__ __forceinline__ uint32_t dna4_rank_fast(uint8_t c)
+{
+    // c:1 y:1 s:1 b:1 | g:2 k:2 | t:3 u:3 ; everything else 0
+    constexpr uint64_t T = (1ull << (2 * ('c' - 'a'))) | (1ull << (2 * ('y' - 'a'))) | (1ull << (2 * ('s' - 'a'))) | (1ull << (2 * ('b' - 'a'))) |
+                           (2ull << (2 * ('g' - 'a'))) | (2ull << (2 * ('k' - 'a'))) | (3ull << (2 * ('t' - 'a'))) | (3ull << (2 * ('u' - 'a')));
+    const uint32_t i = (uint32_t)(c | 0x20) - 'a';
+    const uint32_t lo = (uint32_t)T, hi = (uint32_t)(T >> 32);
+    const uint32_t w = i < 16 ? lo : hi;
+    return i < 26 ? (w >> ((i & 15) * 2)) & 3u : 0u;
+}
+
+// keys: (canonical k-mer value << 1) | dup-flag; comb = minimum by value, equal values set the flag.
+__device__ __forceinline__ uint64_t key_comb(uint64_t a, uint64_t b)
+{
+    const uint64_t m = a < b ? a : b;
+    return ((a ^ b) < 2) ? (m | 1ull) : m;
+}
+
+// bases [0, nv+k-1) of `seq` -> 2-bit packed big-endian words (REDUX.OR over the warp) -> keys lev0[0..nv)
+__device__ __forceinline__ void load_keys(const uint8_t *__restrict__ seq, uint32_t nv, uint32_t k, uint64_t seed, uint64_t kmask, uint64_t *sp,
+                                          uint64_t *lev0, uint32_t lane)
+{
+    const uint32_t nb = nv + k - 1;
+    const uint32_t ng = (nb + 31) >> 5;
+    __syncwarp();
+    for (uint32_t t = 0; t < ng; ++t)
+    {
+        const uint32_t i  = t * 32 + lane;
+        const uint32_t r  = i < nb ? dna4_rank_fast(seq[i]) : 0u;
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? r << (30 - 2 * lane) : 0u);
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? r << (62 - 2 * lane) : 0u);
+        if (lane == 0)
+            sp[t] = ((uint64_t)hi << 32) | lo;
+    }
+    if (lane == 0)
+        sp[ng] = 0;
+    __syncwarp();
+    const uint32_t sh = 64 - 2 * k;
+    for (uint32_t i = lane; i < nv; i += 32)
+    {
+        const uint32_t j = i >> 5, o = (i & 31) * 2;
+        const uint64_t a = sp[j], b = sp[j + 1];
+        const uint64_t x = (a << o) | ((b >> 1) >> (63 - o)); // k-mer in the top 2k bits, first base most significant
+        const uint64_t f = x >> sh;
+        uint64_t       z = __brevll(~x);                      // complement, reverse: bases in reverse order, bit pairs swapped
+        z = ((z >> 1) & 0x5555555555555555ull) | ((z & 0x5555555555555555ull) << 1);
+        const uint64_t rc = z & kmask;
+        const uint64_t fs = f ^ seed, rs = rc ^ seed;
+        lev0[i] = (fs < rs ? fs : rs) << 1;
+    }
+    __syncwarp();
+}
+
+// Exact for every input: windows with a duplicated minimum make the caller fall back to the serial walk.
+// Per tile: keys -> min-with-dup-flag over 2,4,8,... consecutive values (in shared memory) -> window minimum as the
+// fold over the binary digits of W -> window i emits iff the previous minimum left the window (v[i-1] == m(i-1)) or
+// the newcomer is smaller (v[i+W-1] < m(i-1)).
+template <bool WRITE>
+__device__ __forceinline__ bool minimisers_fast(const uint8_t *__restrict__ seq, uint32_t nwin, uint32_t W, uint32_t k, uint64_t seed,
+                                                uint64_t kmask, uint64_t *__restrict__ out, uint64_t *sp, uint64_t *lev, uint32_t nv_cap,
+                                                uint32_t lane, uint32_t &emitted_out)
+{
+    const uint32_t lmax = 31 - __clz(W); // levels 0..lmax
+    uint32_t emitted = 0;
+    uint64_t prev    = 0; // window minimum key of the window before the current group (carried in every lane)
+    for (uint32_t t0 = 0; t0 < nwin; t0 += K2_TILE)
+    {
+        const uint32_t nt   = min((uint32_t)K2_TILE, nwin - t0);
+        const uint32_t base = t0 ? 1u : 0u; // one extra value in front: v[i-1] of the tile's first window
+        const uint32_t nv   = nt + W - 1 + base;
+        load_keys(seq + t0 - base, nv, k, seed, kmask, sp, lev, lane);
+        for (uint32_t l = 1; l <= lmax; ++l)
+        {
+            const uint64_t *src = lev + (size_t)(l - 1) * nv_cap;
+            uint64_t       *dst = lev + (size_t)l * nv_cap;
+            const uint32_t  h   = 1u << (l - 1);
+            for (uint32_t i = lane; i + 2 * h <= nv; i += 32)
+                dst[i] = key_comb(src[i], src[i + h]);
+            __syncwarp();
+        }
+        for (uint32_t g = 0; g < nt; g += 32)
+        {
+            const uint32_t i  = g + lane;
+            const bool     on = i < nt;
+            uint64_t       acc = ~0ull;
+            if (on)
+            {
+                uint32_t pos = i + base;
+                for (int l = (int)lmax; l >= 0; --l)
+                    if ((W >> l) & 1u)
+                    {
+                        const uint64_t term = lev[(size_t)l * nv_cap + pos];
+                        acc = acc == ~0ull ? term : key_comb(acc, term);
+                        pos += 1u << l;
+                    }
+            }
+            if (__any_sync(0xffffffffu, on && (acc & 1ull)))
+                return false; // tie inside a window
+            uint64_t left = __shfl_up_sync(0xffffffffu, acc, 1);
+            if (lane == 0)
+                left = prev;
+            const uint32_t last = min(31u, nt - 1 - g);
+            prev = __shfl_sync(0xffffffffu, acc, last);
+            bool emit = false;
+            if (on)
+            {
+                if (t0 + i == 0)
+                    emit = true;
+                else
+                {
+                    const uint64_t gone = lev[i + base - 1], come = lev[i + base + W - 1]; // keys (value << 1)
+                    emit = (gone >> 1) == (left >> 1) || (come >> 1) < (left >> 1);
+                }
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, emit);
+            if (WRITE && emit)
+                out[emitted + __popc(mask & ((1u << lane) - 1))] = acc >> 1;
+            emitted += __popc(mask);
+        }
+    }
+    emitted_out = emitted;
+    return true;
+}
+
 // One mate.  Returns the number of minimisers emitted (warp-uniform).
 //
 // The reference's window (minimiser.hpp:444-472) is a sticky state machine: the tracked minimiser position `mp` only
@@ -111,7 +237,7 @@ __device__ __forceinline__ void load_values(const uint8_t *__restrict__ seq, uin
 // bit-exact.
 template <bool WRITE>
 __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t L, uint32_t k, uint32_t w, uint64_t seed,
-                                       uint64_t *__restrict__ out, uint64_t *sv, uint8_t *sb, uint32_t lane)
+                                       uint64_t *__restrict__ out, uint64_t *sv, uint8_t *sb, uint64_t *sp, uint32_t nv_cap, uint32_t lane)
 {
     const uint32_t nk   = L - k + 1;
     const uint32_t W    = min(w - k + 1, nk);
@@ -120,8 +246,15 @@ __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t
 
     uint32_t emitted = 0;
     bool     tie     = false;
+    if (k <= 31)
+    {
+        if (minimisers_fast<WRITE>(seq, nwin, W, k, seed, kmask, out, sp, sv, nv_cap, lane, emitted))
+            return emitted;
+        tie     = true; // a window with a duplicated minimum: exact serial walk below
+        emitted = 0;
+    }
     uint32_t prev_r  = 0xffffffffu; // R of the window before the current group of 32 (lane 31's, carried)
-    for (uint32_t t0 = 0; t0 < nwin && !tie; t0 += K2_TILE)
+    for (uint32_t t0 = 0; k > 31 && t0 < nwin && !tie; t0 += K2_TILE)
     {
         const uint32_t nt = min((uint32_t)K2_TILE, nwin - t0);
         const uint32_t nv = nt + W - 1;
@@ -222,8 +355,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
     uint64_t warp_sum = 0;
     extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint64_t *sv = reinterpret_cast<uint64_t *>(k2_smem) + (size_t)wib * nv_cap;
-    uint8_t  *sb = k2_smem + (size_t)K2_WARPS * nv_cap * 8 + (size_t)wib * nb_cap;
+    // per warp: n_lev key arrays of nv_cap (level 0 doubles as the value array of the generic path), packed words, ranks
+    const uint32_t n_lev  = 32 - __clz(w - k + 1);
+    const uint32_t sp_cap = (nb_cap >> 5) + 2;
+    const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
+    uint8_t  *wbase = k2_smem + (size_t)wib * per_w;
+    uint64_t *sv = reinterpret_cast<uint64_t *>(wbase);
+    uint64_t *sp = sv + (size_t)n_lev * nv_cap;
+    uint8_t  *sb = reinterpret_cast<uint8_t *>(sp + sp_cap);
     const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
     for (uint32_t read = blockIdx.x * K2_WARPS + wib; read < n_reads; read += gridDim.x * K2_WARPS)
     {
@@ -232,12 +371,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
         if (L1 >= w && L1 >= k) // GC.cpp:690: reads shorter than the window are skipped entirely
         {
             uint64_t *out = WRITE ? hashes + hash_off[read] : nullptr;
-            total = minimisers_of_mate<WRITE>(blk1 + off1[read], L1, k, w, seed, out, sv, sb, lane);
+            total = minimisers_of_mate<WRITE>(blk1 + off1[read], L1, k, w, seed, out, sv, sb, sp, nv_cap, lane);
             if (blk2 != nullptr)
             {
                 const uint32_t L2 = len2[read];
                 if (L2 >= w && L2 >= k) // GC.cpp:695
-                    total += minimisers_of_mate<WRITE>(blk2 + off2[read], L2, k, w, seed, WRITE ? out + total : nullptr, sv, sb, lane);
+                    total += minimisers_of_mate<WRITE>(blk2 + off2[read], L2, k, w, seed, WRITE ? out + total : nullptr, sv, sb, sp, nv_cap, lane);
             }
         }
         if (KMODE != 1 && lane == 0)
@@ -280,9 +419,13 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     if (n_reads == 0)
         return;
     const uint32_t W      = w - k + 1;
-    const uint32_t nv_cap = (K2_TILE + W + 1 + 1) & ~1u;          // values per warp
-    const uint32_t nb_cap = (nv_cap + k + 15) & ~15u;             // bases per warp
-    const size_t   smem   = (size_t)K2_WARPS * (nv_cap * 8 + nb_cap);
+    const uint32_t nv_cap = (K2_TILE + W + 2 + 1) & ~1u;          // values per warp and level
+    const uint32_t nb_cap = (nv_cap + k + 15) & ~15u;             // bases per warp (multiple of 16: keeps 8-byte alignment)
+    uint32_t       n_lev  = 0;
+    while ((1u << n_lev) <= W)
+        ++n_lev;                                                   // levels 0..floor(log2 W)
+    const uint32_t sp_cap = (nb_cap >> 5) + 2;
+    const size_t   smem   = (size_t)K2_WARPS * (((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
