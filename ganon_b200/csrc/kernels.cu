@@ -154,6 +154,116 @@ __device__ __forceinline__ void load_keys(const uint8_t *__restrict__ seq, uint3
     __syncwarp();
 }
 
+// ---- fastest path (k <= 26, W <= 24): position-tagged keys, window minima by warp shuffles on the FP64 min unit ---
+// Keys (value << 9) | tag are < 2^62, i.e. finite non-negative IEEE doubles whose order equals their integer order,
+// so a 64-bit minimum is a single DMNMX.  tag = 511 - p makes the minimum the RIGHTMOST minimal value (R), tag = p the
+// leftmost (L); R != L in some window means a duplicated minimum -> the caller falls back to the exact serial walk.
+__device__ __forceinline__ uint64_t dmin64(uint64_t a, uint64_t b)
+{
+    return (uint64_t)__double_as_longlong(fmin(__longlong_as_double((long long)a), __longlong_as_double((long long)b)));
+}
+__device__ __forceinline__ uint64_t shfl_down64(uint64_t v, uint32_t d)
+{
+    return (uint64_t)__double_as_longlong(__shfl_down_sync(0xffffffffu, __longlong_as_double((long long)v), d));
+}
+
+template <bool WRITE>
+__device__ __forceinline__ bool minimisers_shfl(const uint8_t *__restrict__ seq, uint32_t nwin, uint32_t W, uint32_t k, uint64_t seed,
+                                                uint64_t kmask, uint64_t *__restrict__ out, uint64_t *sp, uint64_t *sv, uint32_t lane,
+                                                uint32_t &emitted_out)
+{
+    constexpr int LMAX = 4; // W <= 24 < 32
+    const uint32_t G  = 32 - (W - 1); // windows finished per group of 32 positions
+    const uint32_t sh = 64 - 2 * k;
+    const uint32_t span = 32 - k + 1; // k-mers available from one 32-base word pair
+    uint32_t emitted = 0;
+    uint32_t prev_r  = 0xffffffffu; // global position of the previous window's minimum
+    for (uint32_t t0 = 0; t0 < nwin; t0 += K2_TILE)
+    {
+        const uint32_t nt = min((uint32_t)K2_TILE, nwin - t0);
+        const uint32_t nv = nt + W - 1;
+        const uint32_t nb = nv + k - 1;
+        const uint32_t ng = (nb + 31) >> 5;
+        const uint8_t *sq = seq + t0;
+        __syncwarp();
+        for (uint32_t t = 0; t < ng; ++t)
+        {
+            const uint32_t i  = t * 32 + lane;
+            const uint32_t r  = i < nb ? dna4_rank_fast(sq[i]) : 0u;
+            const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? r << (30 - 2 * lane) : 0u);
+            const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? r << (62 - 2 * lane) : 0u);
+            if (lane == 0)
+                sp[t] = ((uint64_t)hi << 32) | lo;
+        }
+        if (lane == 0)
+            sp[ng] = 0;
+        __syncwarp();
+        // canonical values (<< 9) of a contiguous run of positions per lane
+        {
+            const uint32_t rl = (nv + 31) >> 5;
+            const uint32_t i0 = lane * rl, i1 = min(nv, i0 + rl);
+            uint64_t x = 0, z = 0;
+            for (uint32_t i = i0, d = span; i < i1; ++i, ++d)
+            {
+                if (d >= span)
+                { // (re)load the 32 bases starting at position i
+                    const uint32_t j = i >> 5, o = (i & 31) * 2;
+                    const uint64_t a = sp[j], b = sp[j + 1];
+                    x = (a << o) | ((b >> 1) >> (63 - o));
+                    z = __brevll(~x);
+                    z = ((z >> 1) & 0x5555555555555555ull) | ((z & 0x5555555555555555ull) << 1); // comp(base t) at bits 2t+1..2t
+                    d = 0;
+                }
+                const uint64_t f  = ((x << (2 * d)) >> sh) ^ seed;
+                const uint64_t rc = ((z >> (2 * d)) & kmask) ^ seed;
+                sv[i] = dmin64(f, rc) << 9;
+            }
+        }
+        __syncwarp();
+        for (uint32_t g = 0; g < nt; g += G)
+        {
+            const uint32_t p  = g + lane; // tile-local position held by this lane
+            const uint64_t u  = p < nv ? sv[p] : 0x3ffffffffffffe00ull; // beyond the tile: larger than any key
+            uint64_t lvR[LMAX + 1], lvL[LMAX + 1];
+            lvR[0] = u | (uint64_t)(511 - p);
+            lvL[0] = u | (uint64_t)p;
+#pragma unroll
+            for (int l = 1; l <= LMAX; ++l)
+            {
+                lvR[l] = dmin64(lvR[l - 1], shfl_down64(lvR[l - 1], 1u << (l - 1)));
+                lvL[l] = dmin64(lvL[l - 1], shfl_down64(lvL[l - 1], 1u << (l - 1)));
+            }
+            uint64_t accR = ~0ull >> 2, accL = ~0ull >> 2;
+            uint32_t off = 0;
+#pragma unroll
+            for (int l = LMAX; l >= 0; --l)
+                if ((W >> l) & 1u) // warp-uniform
+                {
+                    accR = dmin64(accR, off ? shfl_down64(lvR[l], off) : lvR[l]);
+                    accL = dmin64(accL, off ? shfl_down64(lvL[l], off) : lvL[l]);
+                    off += 1u << l;
+                }
+            const bool     on = lane < G && p < nt; // window index p (tile-local)
+            const uint32_t R  = 511u - (uint32_t)(accR & 511u), Lm = (uint32_t)(accL & 511u);
+            if (__any_sync(0xffffffffu, on && R != Lm))
+                return false; // duplicated minimum inside a window
+            const uint32_t rg   = t0 + R;
+            uint32_t       left = __shfl_up_sync(0xffffffffu, rg, 1);
+            if (lane == 0)
+                left = prev_r;
+            const uint32_t last = min(G, nt - g) - 1;
+            prev_r = __shfl_sync(0xffffffffu, rg, last);
+            const bool     emit = on && rg != left; // prev_r starts impossible: the first window always emits
+            const uint32_t mask = __ballot_sync(0xffffffffu, emit);
+            if (WRITE && emit)
+                out[emitted + __popc(mask & ((1u << lane) - 1))] = accR >> 9;
+            emitted += __popc(mask);
+        }
+    }
+    emitted_out = emitted;
+    return true;
+}
+
 // Exact for every input: windows with a duplicated minimum make the caller fall back to the serial walk.
 // Per tile: keys -> min-with-dup-flag over 2,4,8,... consecutive values (in shared memory) -> window minimum as the
 // fold over the binary digits of W -> window i emits iff the previous minimum left the window (v[i-1] == m(i-1)) or
@@ -246,7 +356,14 @@ __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t
 
     uint32_t emitted = 0;
     bool     tie     = false;
-    if (k <= 31)
+    if (k <= 26 && W <= 24)
+    {
+        if (minimisers_shfl<WRITE>(seq, nwin, W, k, seed, kmask, out, sp, sv, lane, emitted))
+            return emitted;
+        tie     = true;
+        emitted = 0;
+    }
+    else if (k <= 31)
     {
         if (minimisers_fast<WRITE>(seq, nwin, W, k, seed, kmask, out, sp, sv, nv_cap, lane, emitted))
             return emitted;
@@ -356,7 +473,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
     extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // per warp: n_lev key arrays of nv_cap (level 0 doubles as the value array of the generic path), packed words, ranks
-    const uint32_t n_lev  = 32 - __clz(w - k + 1);
+    const uint32_t n_lev  = (k <= 26 && w - k + 1 <= 24) ? 1u : 32 - __clz(w - k + 1);
     const uint32_t sp_cap = (nb_cap >> 5) + 2;
     const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
     uint8_t  *wbase = k2_smem + (size_t)wib * per_w;
@@ -364,7 +481,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
     uint64_t *sp = sv + (size_t)n_lev * nv_cap;
     uint8_t  *sb = reinterpret_cast<uint8_t *>(sp + sp_cap);
     const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
-    for (uint32_t read = blockIdx.x * K2_WARPS + wib; read < n_reads; read += gridDim.x * K2_WARPS)
+    const uint32_t wpc = blockDim.x >> 5; // warps per CTA (chosen at launch from the shared-memory need)
+    for (uint32_t read = blockIdx.x * wpc + wib; read < n_reads; read += gridDim.x * wpc)
     {
         uint32_t       total = 0;
         const uint32_t L1    = len1[read];
@@ -424,12 +542,18 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     uint32_t       n_lev  = 0;
     while ((1u << n_lev) <= W)
         ++n_lev;                                                   // levels 0..floor(log2 W)
+    if (k <= 26 && W <= 24)
+        n_lev = 1;                                                 // shuffle path: values only
     const uint32_t sp_cap = (nb_cap >> 5) + 2;
-    const size_t   smem   = (size_t)K2_WARPS * (((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap);
+    const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
+    uint32_t       wpc    = K2_WARPS;
+    while (wpc > 1 && wpc * per_w > 200 * 1024)
+        wpc >>= 1;
+    const size_t   smem   = (size_t)wpc * per_w;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t want = (n_reads + K2_WARPS - 1) / K2_WARPS;
+    const uint32_t want = (n_reads + wpc - 1) / wpc;
     uint32_t       full = (uint32_t)sms * 8; // 64 warps per SM
     const uint32_t fine = (want + 63) / 64;  // ~64 reads per warp: short-lived CTAs (see launch_k3)
     if (fine > full)
@@ -438,7 +562,7 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
 #define GNB_K2(M)                                                                                                                     \
     {                                                                                                                                 \
         cudaFuncSetAttribute(k_minimisers<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                \
-        k_minimisers<M><<<grid, K2_WARPS * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, \
+        k_minimisers<M><<<grid, wpc * 32, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, nv_cap, nb_cap, counts, \
                                                             hash_off, hashes, max_count, sum_count);                                  \
     }
     if (mode == 0)
