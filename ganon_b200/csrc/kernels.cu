@@ -154,27 +154,114 @@ __device__ __forceinline__ void load_keys(const uint8_t *__restrict__ seq, uint3
     __syncwarp();
 }
 
-// ---- fastest path (k <= 26, W <= 24): position-tagged keys, window minima by warp shuffles on the FP64 min unit ---
-// Keys (value << 9) | tag are < 2^62, i.e. finite non-negative IEEE doubles whose order equals their integer order,
-// so a 64-bit minimum is a single DMNMX.  tag = 511 - p makes the minimum the RIGHTMOST minimal value (R), tag = p the
-// leftmost (L); R != L in some window means a duplicated minimum -> the caller falls back to the exact serial walk.
-__device__ __forceinline__ uint64_t dmin64(uint64_t a, uint64_t b)
+// ---- fastest path (k <= 26, 8 <= W <= 255): position-tagged keys, a run of C consecutive windows per lane ------------
+// Keys (value << 9) | tag are totally ordered: tag = 511 - p makes the minimum the RIGHTMOST minimal value (R), tag = p
+// the leftmost (L); R != L in some window means a duplicated minimum -> the caller falls back to the exact serial walk.
+// A lane owns windows [lane*C, lane*C + C): they share the values at offsets [C-1, W), so the lane takes the minimum of
+// that shared part once, suffix minima over the C-1 values in front and prefix minima over the C-1 values behind, and
+// every window is the minimum of three terms: (W + 3C - 4) 64-bit minima for C windows instead of C*(W-1).
+// Values are stored residue-major (position p at (p % C) * pitch + p / C) so that the lanes' reads are conflict-free.
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+template <bool WRITE, int C>
+__device__ __forceinline__ bool window_runs(const uint64_t *sv, uint32_t pitch, uint32_t nv, uint32_t nt, uint32_t W, uint32_t t0, uint32_t lane,
+                                            uint32_t &prev_r, uint32_t &emitted, uint64_t *__restrict__ out)
 {
-    return (uint64_t)__double_as_longlong(fmin(__longlong_as_double((long long)a), __longlong_as_double((long long)b)));
-}
-__device__ __forceinline__ uint64_t shfl_down64(uint64_t v, uint32_t d)
-{
-    return (uint64_t)__double_as_longlong(__shfl_down_sync(0xffffffffu, __longlong_as_double((long long)v), d));
+    constexpr uint64_t BIG = 0x3ffffffffffffe00ull; // larger than any key, tag bits clear
+    const uint32_t i = lane * C;                    // first window (tile-local) of this lane
+    auto key = [&](uint32_t t, uint64_t &kr, uint64_t &kl) {
+        const uint32_t p = i + t;
+        const uint64_t u = p < nv ? sv[(p % C) * pitch + p / C] : BIG;
+        kr = u | (uint64_t)(511u - (p & 511u));
+        kl = u | (uint64_t)(p & 511u);
+    };
+    // shared part
+    uint64_t mR, mL;
+    key(C - 1, mR, mL);
+    for (uint32_t t = C; t < W; ++t)
+    {
+        uint64_t a, b;
+        key(t, a, b);
+        mR = umin64(mR, a);
+        mL = umin64(mL, b);
+    }
+    // suffix minima of the values in front: sufR[j] = min over offsets [j, C-1)
+    uint64_t sufR[C], sufL[C];
+    sufR[C - 1] = sufL[C - 1] = ~0ull;
+#pragma unroll
+    for (int j = C - 2; j >= 0; --j)
+    {
+        uint64_t a, b;
+        key((uint32_t)j, a, b);
+        sufR[j] = umin64(sufR[j + 1], a);
+        sufL[j] = umin64(sufL[j + 1], b);
+    }
+    // windows in order, extending the prefix minimum of the values behind
+    uint64_t preR = ~0ull, preL = ~0ull;
+    uint32_t R[C];
+    uint64_t val[C];
+    bool     tie = false;
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+    {
+        if (j > 0)
+        {
+            uint64_t a, b;
+            key(W + (uint32_t)j - 1, a, b);
+            preR = umin64(preR, a);
+            preL = umin64(preL, b);
+        }
+        const uint64_t wr = umin64(umin64(sufR[j], mR), preR), wl = umin64(umin64(sufL[j], mL), preL);
+        const bool     on = i + j < nt;
+        R[j]   = 511u - (uint32_t)(wr & 511u);
+        val[j] = wr >> 9;
+        tie |= on && R[j] != (uint32_t)(wl & 511u);
+    }
+    if (__any_sync(0xffffffffu, tie))
+        return false;
+    // emissions: window j emits iff its minimum sits elsewhere than the previous window's
+    const uint32_t my_last = i < nt ? R[min((uint32_t)C, nt - i) - 1] + t0 : 0u;
+    uint32_t       left    = __shfl_up_sync(0xffffffffu, my_last, 1);
+    if (lane == 0)
+        left = prev_r;
+    const uint32_t last_lane = (nt - 1) / C;
+    prev_r = __shfl_sync(0xffffffffu, my_last, last_lane);
+    uint32_t emask = 0;
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+    {
+        const uint32_t rg = R[j] + t0;
+        if (i + j < nt && rg != left)
+            emask |= 1u << j;
+        left = rg;
+    }
+    const uint32_t mine = __popc(emask);
+    uint32_t       incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += y;
+    }
+    if (WRITE)
+    {
+        uint32_t pos = emitted + incl - mine;
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            if ((emask >> j) & 1u)
+                out[pos++] = val[j];
+    }
+    emitted += __shfl_sync(0xffffffffu, incl, 31);
+    return true;
 }
 
 template <bool WRITE>
-__device__ __forceinline__ bool minimisers_shfl(const uint8_t *__restrict__ seq, uint32_t nwin, uint32_t W, uint32_t k, uint64_t seed,
+__device__ __forceinline__ bool minimisers_runs(const uint8_t *__restrict__ seq, uint32_t nwin, uint32_t W, uint32_t k, uint64_t seed,
                                                 uint64_t kmask, uint64_t *__restrict__ out, uint64_t *sp, uint64_t *sv, uint32_t lane,
                                                 uint32_t &emitted_out)
 {
-    constexpr int LMAX = 4; // W <= 24 < 32
-    const uint32_t G  = 32 - (W - 1); // windows finished per group of 32 positions
-    const uint32_t sh = 64 - 2 * k;
+    const uint32_t sh   = 64 - 2 * k;
     const uint32_t span = 32 - k + 1; // k-mers available from one 32-base word pair
     uint32_t emitted = 0;
     uint32_t prev_r  = 0xffffffffu; // global position of the previous window's minimum
@@ -184,6 +271,8 @@ __device__ __forceinline__ bool minimisers_shfl(const uint8_t *__restrict__ seq,
         const uint32_t nv = nt + W - 1;
         const uint32_t nb = nv + k - 1;
         const uint32_t ng = (nb + 31) >> 5;
+        const uint32_t C  = (nt + 31) >> 5;      // windows per lane, 1..8
+        const uint32_t pitch = (nv + C - 1) / C; // values per residue class
         const uint8_t *sq = seq + t0;
         __syncwarp();
         for (uint32_t t = 0; t < ng; ++t)
@@ -216,49 +305,24 @@ __device__ __forceinline__ bool minimisers_shfl(const uint8_t *__restrict__ seq,
                 }
                 const uint64_t f  = ((x << (2 * d)) >> sh) ^ seed;
                 const uint64_t rc = ((z >> (2 * d)) & kmask) ^ seed;
-                sv[i] = dmin64(f, rc) << 9;
+                sv[(i % C) * pitch + i / C] = umin64(f, rc) << 9;
             }
         }
         __syncwarp();
-        for (uint32_t g = 0; g < nt; g += G)
+        bool ok;
+        switch (C)
         {
-            const uint32_t p  = g + lane; // tile-local position held by this lane
-            const uint64_t u  = p < nv ? sv[p] : 0x3ffffffffffffe00ull; // beyond the tile: larger than any key
-            uint64_t lvR[LMAX + 1], lvL[LMAX + 1];
-            lvR[0] = u | (uint64_t)(511 - p);
-            lvL[0] = u | (uint64_t)p;
-#pragma unroll
-            for (int l = 1; l <= LMAX; ++l)
-            {
-                lvR[l] = dmin64(lvR[l - 1], shfl_down64(lvR[l - 1], 1u << (l - 1)));
-                lvL[l] = dmin64(lvL[l - 1], shfl_down64(lvL[l - 1], 1u << (l - 1)));
-            }
-            uint64_t accR = ~0ull >> 2, accL = ~0ull >> 2;
-            uint32_t off = 0;
-#pragma unroll
-            for (int l = LMAX; l >= 0; --l)
-                if ((W >> l) & 1u) // warp-uniform
-                {
-                    accR = dmin64(accR, off ? shfl_down64(lvR[l], off) : lvR[l]);
-                    accL = dmin64(accL, off ? shfl_down64(lvL[l], off) : lvL[l]);
-                    off += 1u << l;
-                }
-            const bool     on = lane < G && p < nt; // window index p (tile-local)
-            const uint32_t R  = 511u - (uint32_t)(accR & 511u), Lm = (uint32_t)(accL & 511u);
-            if (__any_sync(0xffffffffu, on && R != Lm))
-                return false; // duplicated minimum inside a window
-            const uint32_t rg   = t0 + R;
-            uint32_t       left = __shfl_up_sync(0xffffffffu, rg, 1);
-            if (lane == 0)
-                left = prev_r;
-            const uint32_t last = min(G, nt - g) - 1;
-            prev_r = __shfl_sync(0xffffffffu, rg, last);
-            const bool     emit = on && rg != left; // prev_r starts impossible: the first window always emits
-            const uint32_t mask = __ballot_sync(0xffffffffu, emit);
-            if (WRITE && emit)
-                out[emitted + __popc(mask & ((1u << lane) - 1))] = accR >> 9;
-            emitted += __popc(mask);
+        case 1: ok = window_runs<WRITE, 1>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        case 2: ok = window_runs<WRITE, 2>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        case 3: ok = window_runs<WRITE, 3>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        case 4: ok = window_runs<WRITE, 4>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        case 5: ok = window_runs<WRITE, 5>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        case 6: ok = window_runs<WRITE, 6>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        case 7: ok = window_runs<WRITE, 7>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        default: ok = window_runs<WRITE, 8>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
         }
+        if (!ok)
+            return false; // duplicated minimum inside a window
     }
     emitted_out = emitted;
     return true;
@@ -356,9 +420,9 @@ __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t
 
     uint32_t emitted = 0;
     bool     tie     = false;
-    if (k <= 26 && W <= 24)
+    if (k <= 26 && W >= 8)
     {
-        if (minimisers_shfl<WRITE>(seq, nwin, W, k, seed, kmask, out, sp, sv, lane, emitted))
+        if (minimisers_runs<WRITE>(seq, nwin, W, k, seed, kmask, out, sp, sv, lane, emitted))
             return emitted;
         tie     = true;
         emitted = 0;
@@ -473,7 +537,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
     extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // per warp: n_lev key arrays of nv_cap (level 0 doubles as the value array of the generic path), packed words, ranks
-    const uint32_t n_lev  = (k <= 26 && w - k + 1 <= 24) ? 1u : 32 - __clz(w - k + 1);
+    const uint32_t n_lev  = (k <= 26 && w - k + 1 >= 8) ? 1u : 32 - __clz(w - k + 1);
     const uint32_t sp_cap = (nb_cap >> 5) + 2;
     const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
     uint8_t  *wbase = k2_smem + (size_t)wib * per_w;
@@ -542,8 +606,8 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     uint32_t       n_lev  = 0;
     while ((1u << n_lev) <= W)
         ++n_lev;                                                   // levels 0..floor(log2 W)
-    if (k <= 26 && W <= 24)
-        n_lev = 1;                                                 // shuffle path: values only
+    if (k <= 26 && W >= 8)
+        n_lev = 1;                                                 // run-per-lane path: values only
     const uint32_t sp_cap = (nb_cap >> 5) + 2;
     const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
     uint32_t       wpc    = K2_WARPS;
