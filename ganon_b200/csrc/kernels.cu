@@ -26,8 +26,7 @@ namespace
 {
 
 constexpr int K2_WARPS = 8;   // warps (= reads in flight) per CTA
-constexpr int K2_TILE  = 256; // windows per tile (8 per lane)
-constexpr int K2_PER   = K2_TILE / 32;
+constexpr int K2_TILE  = 128; // windows per tile (up to 4 consecutive windows per lane)
 
 // seqan3 dna4 char_to_rank incl. IUPAC conversion (dna4.hpp:166-205): everything not listed maps to 0 ('A').
 __device__ __forceinline__ uint32_t dna4_rank(uint8_t c)
@@ -154,7 +153,7 @@ __device__ __forceinline__ void load_keys(const uint8_t *__restrict__ seq, uint3
     __syncwarp();
 }
 
-// ---- fastest path (k <= 26, 8 <= W <= 255): position-tagged keys, a run of C consecutive windows per lane ------------
+// ---- fastest path (k <= 26, 4 <= W <= 255): position-tagged keys, a run of C consecutive windows per lane ------------
 // Keys (value << 9) | tag are totally ordered: tag = 511 - p makes the minimum the RIGHTMOST minimal value (R), tag = p
 // the leftmost (L); R != L in some window means a duplicated minimum -> the caller falls back to the exact serial walk.
 // A lane owns windows [lane*C, lane*C + C): they share the values at offsets [C-1, W), so the lane takes the minimum of
@@ -275,14 +274,26 @@ __device__ __forceinline__ bool minimisers_runs(const uint8_t *__restrict__ seq,
         const uint32_t pitch = (nv + C - 1) / C; // values per residue class
         const uint8_t *sq = seq + t0;
         __syncwarp();
-        for (uint32_t t = 0; t < ng; ++t)
+        // bases -> 2-bit packed words; the byte loads of six words are issued together (memory-level parallelism)
+        for (uint32_t tb = 0; tb < ng; tb += 6)
         {
-            const uint32_t i  = t * 32 + lane;
-            const uint32_t r  = i < nb ? dna4_rank_fast(sq[i]) : 0u;
-            const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? r << (30 - 2 * lane) : 0u);
-            const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? r << (62 - 2 * lane) : 0u);
-            if (lane == 0)
-                sp[t] = ((uint64_t)hi << 32) | lo;
+            uint8_t c[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+            {
+                const uint32_t i = (tb + q) * 32 + lane;
+                c[q] = i < nb ? sq[i] : (uint8_t)'A';
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                if (tb + q < ng)
+                {
+                    const uint32_t r  = dna4_rank_fast(c[q]);
+                    const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? r << (30 - 2 * lane) : 0u);
+                    const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? r << (62 - 2 * lane) : 0u);
+                    if (lane == 0)
+                        sp[tb + q] = ((uint64_t)hi << 32) | lo;
+                }
         }
         if (lane == 0)
             sp[ng] = 0;
@@ -315,11 +326,7 @@ __device__ __forceinline__ bool minimisers_runs(const uint8_t *__restrict__ seq,
         case 1: ok = window_runs<WRITE, 1>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
         case 2: ok = window_runs<WRITE, 2>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
         case 3: ok = window_runs<WRITE, 3>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
-        case 4: ok = window_runs<WRITE, 4>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
-        case 5: ok = window_runs<WRITE, 5>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
-        case 6: ok = window_runs<WRITE, 6>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
-        case 7: ok = window_runs<WRITE, 7>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
-        default: ok = window_runs<WRITE, 8>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
+        default: ok = window_runs<WRITE, 4>(sv, pitch, nv, nt, W, t0, lane, prev_r, emitted, out); break;
         }
         if (!ok)
             return false; // duplicated minimum inside a window
@@ -420,7 +427,7 @@ __device__ uint32_t minimisers_of_mate(const uint8_t *__restrict__ seq, uint32_t
 
     uint32_t emitted = 0;
     bool     tie     = false;
-    if (k <= 26 && W >= 8)
+    if (k <= 26 && W >= 4)
     {
         if (minimisers_runs<WRITE>(seq, nwin, W, k, seed, kmask, out, sp, sv, lane, emitted))
             return emitted;
@@ -524,7 +531,7 @@ __device__ __forceinline__ bool dna15_valid(uint8_t c)
 }
 
 template <int KMODE> // 0: count only, 1: write at hash_off, 2: write at hash_off and count (single pass)
-__global__ void __launch_bounds__(K2_WARPS * 32)
+__global__ void __launch_bounds__(K2_WARPS * 32, 4)
     k_minimisers(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1,
                  const uint8_t *__restrict__ blk2, const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2,
                  uint32_t n_reads, uint32_t k, uint32_t w, uint32_t nv_cap, uint32_t nb_cap, uint32_t *__restrict__ counts,
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
     extern __shared__ __align__(16) uint8_t k2_smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // per warp: n_lev key arrays of nv_cap (level 0 doubles as the value array of the generic path), packed words, ranks
-    const uint32_t n_lev  = (k <= 26 && w - k + 1 >= 8) ? 1u : 32 - __clz(w - k + 1);
+    const uint32_t n_lev  = (k <= 26 && w - k + 1 >= 4) ? 1u : 32 - __clz(w - k + 1);
     const uint32_t sp_cap = (nb_cap >> 5) + 2;
     const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
     uint8_t  *wbase = k2_smem + (size_t)wib * per_w;
@@ -606,7 +613,7 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     uint32_t       n_lev  = 0;
     while ((1u << n_lev) <= W)
         ++n_lev;                                                   // levels 0..floor(log2 W)
-    if (k <= 26 && W >= 8)
+    if (k <= 26 && W >= 4)
         n_lev = 1;                                                 // run-per-lane path: values only
     const uint32_t sp_cap = (nb_cap >> 5) + 2;
     const size_t   per_w  = ((size_t)n_lev * nv_cap + sp_cap) * 8 + nb_cap;
