@@ -25,7 +25,7 @@ def test_minimisers_seqan3_kats():
     assert minimisers(b"A" * 19, 19, 19).tolist() == [min(0 ^ O.adjust_seed(19), (4**19 - 1) ^ O.adjust_seed(19))]
 
 
-@pytest.mark.parametrize("k,w", [(19, 31), (10, 10), (4, 8), (32, 40), (21, 63), (5, 260)])
+@pytest.mark.parametrize("k,w", [(19, 31), (10, 10), (4, 8), (32, 40), (21, 63), (5, 260), (28, 35), (31, 31), (27, 29), (26, 33), (12, 14)])
 def test_minimisers_random_and_adversarial(k, w):
     rng = np.random.default_rng(k * 1000 + w)
     seqs = []
