@@ -3,8 +3,8 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|tiny] [--impl reference]
 
-One "step" = one pass of the hot path (K2 minimisers -> K3 IBF count -> sort of the sparse matches) over one batch of
-synthetic 150 bp reads.  `value` = reads/s with the FASTQ batch already in HBM; `e2e` = the same metric through the
+One "step" = one pass of the hot path (K2 minimisers -> K3 IBF count -> sort of the sparse matches -> K4 rel-filter /
+fpr-query / LCA / output lines) over one batch of synthetic 150 bp reads.  `value` = reads/s with the FASTQ batch already in HBM; `e2e` = the same metric through the
 C-ABI call gnb_session_classify with HOST (pinned) FASTQ buffers: record indexing, H2D, kernels, D2H and the host
 finishing stage (rel-filter, fpr-query, formatting of the `.all` lines) inside the timed region.
 N > 1: one process per GPU (torchrun), database replicated, reads sharded -- no data-path collective ("weak").
@@ -252,13 +252,14 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     t0 = time.perf_counter()
-    ms_count = ms_min = ms_sort = 0.0
+    ms_count = ms_min = ms_sort = ms_fin = 0.0
     k3_bytes = launches = minimisers = 0
     for i in range(args.steps):
         r = sessions[(args.warmup + i) % pool].run_staged()
         ms_count += r.ms_count
         ms_min += r.ms_minimiser
         ms_sort += r.ms_sort
+        ms_fin += r.ms_finish_device
         k3_bytes += r.count_kernel_bytes
         launches += r.n_kernel_launches
         minimisers += r.n_minimisers
@@ -278,21 +279,32 @@ def main():
     e2e_sess = Session([db], [REL_CUTOFF], [REL_FILTER], [FPR_QUERY], output_all=True, device=dev)
     _n, cap = e2e_sess.in_flight()
 
+    e2e_prof = {}
+
     def e2e_loop(n_steps, first):
         h2d = d2h = n_class = n_lines = pending = 0
         last = None
+        t_sub = t_col = s_h2d = s_idx = s_job = 0.0
         for i in range(n_steps):
             h1, h2 = host[(first + i) % pool]
+            ta = time.perf_counter()
             e2e_sess.submit(h1, h2, final=True)
+            t_sub += time.perf_counter() - ta
             pending += 1
             while pending >= cap or (i == n_steps - 1 and pending):
+                ta = time.perf_counter()
                 r = e2e_sess.collect()
+                t_col += time.perf_counter() - ta
                 pending -= 1
                 h2d += r.h2d_bytes
                 d2h += r.d2h_bytes
                 n_class += r.n_classified  # the step's result, read on the host
                 n_lines += r.all_len[0]
+                s_h2d += r.ms_h2d
+                s_idx += r.ms_index
+                s_job += r.ms_host_index
                 last = r
+        e2e_prof.update(mean_submit_call_ms=t_sub * 1e3 / n_steps, mean_collect_call_ms=t_col * 1e3 / n_steps, mean_h2d_ms=s_h2d / n_steps, mean_index_ms=s_idx / n_steps, mean_worker_job_ms=s_job / n_steps)
         return h2d, d2h, n_class, n_lines, last
 
     e2e_loop(max(3, cap + 1), 0)
@@ -301,7 +313,7 @@ def main():
     h2d, d2h, n_class, n_bytes_all, r = e2e_loop(args.steps, 1)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_sort=r.ms_sort, ms_worker_job=r.ms_host_index, ms_host_finish=r.ms_host_finish, ms_host_merge=r.ms_d2h, ms_submit_to_collect=r.ms_total, batches_in_flight=cap)
+    last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_sort=r.ms_sort, ms_worker_job=r.ms_host_index, ms_finish_device=r.ms_finish_device, levels_on_device=r.levels_on_device, ms_finish_total=r.ms_host_finish, ms_host_merge=r.ms_d2h, ms_submit_to_collect=r.ms_total, batches_in_flight=cap, **e2e_prof)
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,7 +367,7 @@ def main():
                 "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload),
                 "algorithmic_bytes_per_launch": k3_bytes / max(1, args.steps),
                 "ms_per_launch": ms_count / max(1, args.steps),
-                "other_kernels_ms_per_step": {"k_minimisers(x2)+scan": ms_min / args.steps, "radix_sort": ms_sort / args.steps},
+                "other_kernels_ms_per_step": {"k_minimisers(x2)+scan": ms_min / args.steps, "radix_sort": ms_sort / args.steps, "k_finish(select+scan+write)": ms_fin / args.steps},
             },
             "cpu_baseline": cpu,
             "e2e": {"value": world * args.steps * R * units / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "last_step_breakdown_ms": last, "classified_reads_per_step": n_class // args.steps},

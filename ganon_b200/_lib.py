@@ -101,6 +101,8 @@ class BatchResult(C.Structure):
         ("n_kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("ms_finish_device", C.c_float),
+        ("levels_on_device", C.c_uint32),
     ]
 
 

@@ -136,6 +136,55 @@ constexpr uint32_t kMergedBinFlag = 0x80000000u;
 // sort tuples by (read, node)
 size_t sort_tmp_bytes(uint64_t n);
 void   launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
+// K4: the finishing stage of one hierarchy level on the device (levels with a single filter): cross-run sums, rel-filter,
+// --fpr-query, unique / LCA, report accounting and the text of .all/.one/.unc (GC.cpp:504-541, 579-627, 766-803, 1289-1322)
+struct FinishSizes // per read; exclusive-scanned into offsets
+{
+    unsigned long long kept, all_bytes, one_bytes, unc_bytes;
+};
+enum
+{
+    kFtProcessed = 0, kFtSkippedBig, kFtSkippedSmall, kFtLength, kFtKmers, kFtClassified, kFtKmersMatches, kFtKmersClassified, kFtMatches,
+    kFtUnique, kFtDiscFilter, kFtDiscFpr, kFtActiveHashesNext, kFtAmbiguous, kFinishTotals = 16
+};
+struct FinishParams
+{
+    // batch
+    const uint64_t *tuples;  // sorted by (read, node)
+    uint64_t        n_tuples;
+    uint64_t       *entries; // scratch, same size as tuples: accepted (node, status, count) per read at the read's tuple range
+    uint32_t       *tuple_start; // [n_reads] first tuple of the read, 0xFFFFFFFF = none
+    const uint32_t *n_hashes, *len1, *len2, *id_off, *id_len;
+    const uint8_t  *blk1;
+    uint8_t        *active, *read_level;
+    uint32_t        n_reads;
+    // per-read outputs of pass A
+    uint32_t    *n_acc;
+    FinishSizes *sizes, *offs; // offs = exclusive scan of sizes, [n_reads + 1]
+    uint2       *one;          // (node, count) of the .one line
+    unsigned long long *totals; // [kFinishTotals]
+    // outputs of pass B
+    uint64_t *match_off; // [n_reads + 1]
+    uint32_t *match_target, *match_count;
+    char     *all_text, *one_text, *unc_text;
+    // level
+    const double   *node_fpr;
+    const uint32_t *node_class;   // index of the node's fpr among the level's distinct fpr values
+    unsigned long long *fpr_memo; // direct-mapped cache of --fpr-query values: [slot] = (key, bits of q)
+    uint32_t        fpr_memo_mask;
+    const int32_t  *parent;
+    const uint32_t *depth, *name_off;
+    const char     *names;
+    unsigned long long *rep; // [n_nodes][5]: matches, seqs_lca, seqs_unique, discarded_matches_filter, discarded_matches_fprquery
+    int32_t  root;
+    double   rel_cutoff, rel_filter, fpr_query, fpr_band;
+    uint32_t w, level;
+    uint8_t  is_hibf, skip_lca, output_lca, output_all, output_unc, first, last;
+};
+void   launch_finish_select(const FinishParams &p, cudaStream_t st);                         // boundaries + pass A
+size_t finish_scan_tmp_bytes(uint32_t n_reads);
+void   launch_finish_scan(const FinishParams &p, void *tmp, size_t tmp_bytes, cudaStream_t st); // sizes -> offs
+void   launch_finish_write(const FinishParams &p, cudaStream_t st);                          // pass B
 // build-side
 void launch_fill_random(uint64_t *data, uint64_t rows, uint32_t row_words, uint32_t w0, uint32_t total_words, uint64_t bins, uint64_t seed,
                         int and_terms, cudaStream_t st);

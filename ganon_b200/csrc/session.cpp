@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +34,20 @@ namespace
 
 using Clock = std::chrono::steady_clock;
 inline double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+// GANON_B200_TRACE=1: wall-clock phase marks of every batch on stderr (pipeline debugging)
+inline bool trace_on()
+{
+    static const bool on = [] { const char *e = getenv("GANON_B200_TRACE"); return e && e[0] == '1'; }();
+    return on;
+}
+inline void trace_mark(const void *ctx, const char *what)
+{
+    if (!trace_on())
+        return;
+    static const Clock::time_point t0 = Clock::now();
+    fprintf(stderr, "[gnb-trace] %p %-18s %9.3f ms\n", ctx, what, ms_since(t0));
+}
 
 struct DevBuf
 {
@@ -192,6 +207,10 @@ struct LevelRt
     // accounting per prefix
     std::vector<std::unordered_map<uint32_t, Rep>> rep;
     std::vector<gnb_totals>                        total;
+    // K4 (finishing stage on the device; levels with one filter): node tables and per-prefix report accumulators in HBM
+    bool                device_finish = false;
+    DevBuf              d_node_fpr, d_node_class, d_fpr_memo, d_parent, d_depth, d_name_off, d_names;
+    std::vector<DevBuf> d_rep; // [prefix] -> unsigned long long [n_nodes][5]
 
     uint32_t lca2(uint32_t u, uint32_t v) const
     {
@@ -239,6 +258,7 @@ inline double fpr_query_q(uint64_t n_hashes, uint64_t count, double fpr)
 }
 
 constexpr size_t kDenseRepNodes = 1u << 16;
+constexpr size_t kFprMemoSlots  = 1u << 20; // K4's --fpr-query cache: 16 MiB per level
 constexpr size_t kMemoClasses   = 8;
 
 struct Worker
@@ -293,8 +313,20 @@ struct gnb_session
     std::deque<int>      in_flight;        // slots with a submitted batch, oldest first
     int                  holding = -1;     // slot whose result buffers the caller may still be reading
     std::string          report_text, stats_text;
+    double               fpr_band = 4e-9;   // |q - fpr_query| <= band: the device's --fpr-query value is not trusted (K4)
+    bool                 any_device_finish = false, all_device_finish = false;
+    DevBuf               d_rep_scratch;     // report accumulators of runs whose accounting is discarded (gnb_session_run_staged)
+    // Batches in flight take turns on the GPU for K3 .. K4 in submission order: without it the block scheduler lets the
+    // K3 grid of a younger batch starve the small sort / K4 kernels of an older one and the pipeline stalls in collect.
+    std::mutex              chain_mu;
+    std::condition_variable chain_cv;
+    uint64_t                chain_recorded = 0; // highest sequence number whose "kernels done" event has been recorded
+    uint64_t                next_seq       = 1;
 
     ~gnb_session();
+    int  build_finish_tables(LevelRt &L);
+    int  device_rep(size_t li, uint32_t prefix_id, unsigned long long **out);
+    int  drain_device_rep();
     int  build_level_tables(LevelRt &L);
     int  build_hibf_tables(LevelRt &L, FilterRt &F);
     void ensure_prefix(uint32_t prefix_id);
@@ -344,6 +376,34 @@ struct BatchCtx
     uint64_t              hibf_bytes = 0;
     float                 hibf_ms = 0;
     std::vector<std::vector<PinnedVec<uint64_t>>> tuples; // [level][filter], sorted by (read, node)
+    // K4: finishing stage on the device
+    struct LevelOut
+    {
+        bool       on_device = false;
+        PinBuf     h_moff, h_mt, h_mc, h_all, h_one;
+        uint64_t   n_matches = 0, all_len = 0, one_len = 0;
+        gnb_totals total{};
+    };
+    std::vector<LevelOut> lv;
+    PinBuf     h_unc, h_rlevel;
+    uint64_t   unc_len_dev = 0;
+    bool       unc_on_device = false;
+    DevBuf     d_tstart, d_nacc, d_sizes, d_offs, d_one, d_ftotals, d_read_level, d_moff, d_mt, d_mc, d_all, d_one_txt, d_unc;
+    PinBuf     h_fin; // offs[n] + totals of one K4 pass
+    uint64_t   n_tuples_dev = 0;       // sorted tuples of the level just run, in d_tuples_b (single-filter levels)
+    bool       tuples_on_device = false, keep_on_device = false;
+    bool       active_on_device = false; // d_active / d_read_level are authoritative (else h_active / h_read_level)
+    bool       host_records_valid = false;
+    uint64_t   next_active_hashes = 0;
+    float      ms_finish_dev = 0;
+    uint32_t   levels_on_device = 0;
+    // turn taking (asynchronous form only; seq == 0: not chained)
+    uint64_t    seq = 0;
+    cudaEvent_t ev_done = nullptr, prev_done = nullptr;
+    bool        turn_taken = false, done_signalled = false;
+    int         wait_turn();
+    void        wait_turn_noexcept() { (void)wait_turn(); }
+    void        signal_done();
 
     // result storage
     std::vector<uint64_t>      r_match_off;
@@ -371,6 +431,7 @@ struct BatchCtx
         tuples.resize(levels.size());
         for (size_t li = 0; li < levels.size(); ++li)
             tuples[li].resize(levels[li].filters.size());
+        lv.resize(levels.size());
     }
     ~BatchCtx()
     {
@@ -379,14 +440,23 @@ struct BatchCtx
         cudaSetDevice(device);
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
                           &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status,
-                          &d_items_a, &d_items_b, &d_items_cursor})
+                          &d_items_a, &d_items_b, &d_items_cursor, &d_tstart, &d_nacc, &d_sizes, &d_offs, &d_one, &d_ftotals, &d_read_level, &d_moff,
+                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc})
             b->release();
         h_pin.release();
+        h_unc.release();
+        h_rlevel.release();
+        h_fin.release();
+        for (auto &o : lv)
+            for (PinBuf *b : {&o.h_moff, &o.h_mt, &o.h_mc, &o.h_all, &o.h_one})
+                b->release();
         for (auto &e : ev)
             if (e)
                 cudaEventDestroy(e);
         if (ev_in)
             cudaEventDestroy(ev_in);
+        if (ev_done)
+            cudaEventDestroy(ev_done);
         if (st && own_stream)
         {
             cudaStreamDestroy(st);
@@ -401,6 +471,9 @@ struct BatchCtx
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
     int  finish_level(size_t li);
+    int  finish_level_device(size_t li, unsigned long long *rep, bool fetch, bool &done);
+    int  to_host_state(size_t li);
+    int  fetch_host_records();
     void begin_finish();
     int  collect(uint32_t prefix_id, gnb_batch_result *out);
     int  finish(uint32_t prefix_id, gnb_batch_result *out);
@@ -420,6 +493,118 @@ gnb_session::~gnb_session()
             f.d_segs.release();
             f.d_ibf_table.release();
         }
+    for (auto &l : levels)
+    {
+        for (DevBuf *b : {&l.d_node_fpr, &l.d_node_class, &l.d_fpr_memo, &l.d_parent, &l.d_depth, &l.d_name_off, &l.d_names})
+            b->release();
+        for (auto &b : l.d_rep)
+            b.release();
+    }
+    d_rep_scratch.release();
+}
+
+// K4 tables of a level with one filter: per-node fpr, taxonomy parent / depth, names
+int gnb_session::build_finish_tables(LevelRt &L)
+{
+    L.device_finish = false;
+    if (L.filters.size() != 1)
+        return GNB_OK; // the cross-filter merge (GC.cpp:531-539) stays in the host finishing stage
+    if (const char *e = getenv("GANON_B200_HOST_FINISH"))
+        if (e[0] == '1')
+            return GNB_OK;
+    const size_t          nn = L.node_names.size();
+    std::vector<double>   fpr(nn, 0.0);
+    const FilterRt       &F = L.filters[0];
+    for (size_t i = 0; i < F.node_fpr.size() && i < nn; ++i)
+        fpr[i] = F.node_fpr[i];
+    std::vector<uint32_t> off(nn + 1, 0);
+    std::string           pool;
+    for (size_t i = 0; i < nn; ++i)
+    {
+        off[i] = (uint32_t)pool.size();
+        pool += L.node_names[i];
+    }
+    off[nn] = (uint32_t)pool.size();
+    // classes of equal fpr (keys of the --fpr-query cache)
+    std::vector<uint32_t> cls(nn, 0);
+    {
+        std::unordered_map<uint64_t, uint32_t> ids;
+        for (size_t i = 0; i < nn; ++i)
+        {
+            uint64_t bits;
+            memcpy(&bits, &fpr[i], 8);
+            cls[i] = ids.emplace(bits, (uint32_t)ids.size()).first->second;
+        }
+    }
+    GNB_TRY(L.d_node_class.ensure(nn * 4));
+    GNB_CUDA(cudaMemcpy(L.d_node_class.p, cls.data(), nn * 4, cudaMemcpyHostToDevice));
+    GNB_TRY(L.d_fpr_memo.ensure(kFprMemoSlots * 16));
+    GNB_CUDA(cudaMemset(L.d_fpr_memo.p, 0xFF, kFprMemoSlots * 16));
+    GNB_TRY(L.d_node_fpr.ensure(nn * 8));
+    GNB_TRY(L.d_parent.ensure(nn * 4));
+    GNB_TRY(L.d_depth.ensure(nn * 4));
+    GNB_TRY(L.d_name_off.ensure((nn + 1) * 4));
+    GNB_TRY(L.d_names.ensure(pool.size() + 1));
+    GNB_CUDA(cudaMemcpy(L.d_node_fpr.p, fpr.data(), nn * 8, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(L.d_parent.p, L.parent.data(), nn * 4, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(L.d_depth.p, L.depth.data(), nn * 4, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(L.d_name_off.p, off.data(), (nn + 1) * 4, cudaMemcpyHostToDevice));
+    if (!pool.empty())
+        GNB_CUDA(cudaMemcpy(L.d_names.p, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+    L.device_finish = true;
+    return GNB_OK;
+}
+
+// report accumulators of (level, prefix) in HBM, zeroed on first use
+int gnb_session::device_rep(size_t li, uint32_t prefix_id, unsigned long long **out)
+{
+    std::lock_guard<std::mutex> lock(acc_mutex);
+    LevelRt &L = levels[li];
+    if (L.d_rep.size() <= prefix_id)
+        L.d_rep.resize(prefix_id + 1);
+    DevBuf &b = L.d_rep[prefix_id];
+    if (!b.p)
+    {
+        const size_t bytes = L.node_names.size() * 5 * 8;
+        GNB_TRY(b.ensure(bytes));
+        GNB_CUDA(cudaMemset(b.p, 0, bytes));
+    }
+    *out = b.as<unsigned long long>();
+    return GNB_OK;
+}
+
+// fold the device accumulators into LevelRt::rep (called with no batch in flight)
+int gnb_session::drain_device_rep()
+{
+    GNB_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(acc_mutex);
+    std::vector<unsigned long long> h;
+    for (auto &L : levels)
+        for (size_t pf = 0; pf < L.d_rep.size(); ++pf)
+        {
+            DevBuf &b = L.d_rep[pf];
+            if (!b.p)
+                continue;
+            const size_t nn = L.node_names.size();
+            h.resize(nn * 5);
+            GNB_CUDA(cudaDeviceSynchronize());
+            GNB_CUDA(cudaMemcpy(h.data(), b.p, nn * 5 * 8, cudaMemcpyDeviceToHost));
+            GNB_CUDA(cudaMemset(b.p, 0, nn * 5 * 8));
+            ensure_prefix((uint32_t)pf);
+            for (size_t i = 0; i < nn; ++i)
+            {
+                const unsigned long long *x = &h[i * 5];
+                if (!(x[0] | x[1] | x[2] | x[3] | x[4]))
+                    continue;
+                Rep &r = L.rep[pf][(uint32_t)i];
+                r.matches += x[0];
+                r.seqs_lca += x[1];
+                r.seqs_unique += x[2];
+                r.discarded_matches_filter += x[3];
+                r.discarded_matches_fprquery += x[4];
+            }
+        }
+    return GNB_OK;
 }
 
 int BatchCtx::init(cudaStream_t external)
@@ -438,6 +623,7 @@ int BatchCtx::init(cudaStream_t external)
         GNB_CUDA(cudaStreamCreateWithPriority(&st_in, cudaStreamNonBlocking, greatest));
     }
     GNB_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    GNB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     for (auto &e : ev)
         GNB_CUDA(cudaEventCreate(&e));
     workers.resize(n_threads);
@@ -860,6 +1046,9 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
         int rc = s->build_level_tables(L);
         if (rc != GNB_OK)
             return rc;
+        rc = s->build_finish_tables(L);
+        if (rc != GNB_OK)
+            return rc;
         // fpr classes for the direct-mapped --fpr-query memo
         {
             std::vector<double> classes;
@@ -889,6 +1078,14 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
         }
     }
 
+    s->all_device_finish = true;
+    for (auto const &L : s->levels)
+    {
+        s->any_device_finish |= L.device_finish;
+        s->all_device_finish &= L.device_finish;
+    }
+    if (const char *e = getenv("GANON_B200_FPR_BAND"))
+        s->fpr_band = atof(e); // tests widen the band to force the host path for ambiguous --fpr-query values
     s->n_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     if (s->n_threads > 64)
         s->n_threads = 64;
@@ -950,6 +1147,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     GNB_CUDA(cudaSetDevice(device));
     staged = ran = false;
     blk1 = b1;
+    trace_mark(this, "stage.begin");
     len1 = l1;
     blk2 = b2;
     len2 = b2 ? l2 : 0;
@@ -1030,17 +1228,20 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         GNB_CUDA(cudaMemcpyAsync(h_cons, d_lines1.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st_in));
         if (paired)
             GNB_CUDA(cudaMemcpyAsync(h_cons + 1, d_lines2.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st_in));
-        if (n)
+        // the host finishing stage needs the record table; with K4 on every level it is fetched only on demand
+        host_records_valid = !S->all_device_finish;
+        if (n && host_records_valid)
         {
             GNB_CUDA(cudaMemcpyAsync((void *)p_idoff, d_idoff.p, n * 4, cudaMemcpyDeviceToHost, st_in));
             GNB_CUDA(cudaMemcpyAsync((void *)p_idlen, d_idlen.p, n * 4, cudaMemcpyDeviceToHost, st_in));
             GNB_CUDA(cudaMemcpyAsync((void *)p_slen1, d_len1.p, n * 4, cudaMemcpyDeviceToHost, st_in));
             if (paired)
                 GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st_in));
+            timing.d2h_bytes += (uint64_t)n * 4 * (paired ? 4 : 3);
         }
         GNB_CUDA(cudaStreamSynchronize(st_in));
         GNB_CUDA(cudaGetLastError());
-        timing.d2h_bytes += 24 + (uint64_t)n * 4 * (paired ? 4 : 3);
+        timing.d2h_bytes += 24;
         consumed1 = h_cons[0];
         consumed2 = paired ? h_cons[1] : 0;
         // anything irregular -> the host reader decides (wrapped records, blanks, bad letters, trailing garbage)
@@ -1106,6 +1307,18 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             GNB_CUDA(cudaMemcpyAsync(d_off1.p, t1.seq_off.data(), n * 4, cudaMemcpyHostToDevice, st_in));
             GNB_CUDA(cudaMemcpyAsync(d_len1.p, t1.seq_len.data(), n * 4, cudaMemcpyHostToDevice, st_in));
         }
+        host_records_valid = true;
+        if (S->any_device_finish)
+        { // K4 writes the read ids of the output lines
+            GNB_TRY(d_idoff.ensure(n * 4 + 4));
+            GNB_TRY(d_idlen.ensure(n * 4 + 4));
+            if (n)
+            {
+                GNB_CUDA(cudaMemcpyAsync(d_idoff.p, t1.id_off.data(), n * 4, cudaMemcpyHostToDevice, st_in));
+                GNB_CUDA(cudaMemcpyAsync(d_idlen.p, t1.id_len.data(), n * 4, cudaMemcpyHostToDevice, st_in));
+                timing.h2d_bytes += (uint64_t)n * 8;
+            }
+        }
         if (paired)
         {
             GNB_TRY(d_blk2.ensure(len2 + t2.aux.size() + 64));
@@ -1124,6 +1337,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         }
         timing.h2d_bytes += t1.aux.size() + (paired ? t2.aux.size() : 0) + (uint64_t)n * 8 * (paired ? 2 : 1);
     }
+    trace_mark(this, "stage.indexed");
     n_reads            = (uint32_t)n;
     timing.n_reads     = n_reads;
     timing.parse_error = parse_error ? 1 : 0;
@@ -1135,6 +1349,8 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     GNB_TRY(d_active.ensure((size_t)n + 1));
     h_active.assign(n, 1);
     h_read_level.assign(n, 0xFF);
+    tuples_on_device = active_on_device = false;
+    n_tuples_dev = next_active_hashes = 0;
     // the compute stream picks up after everything staged here
     GNB_CUDA(cudaEventRecord(ev_in, st_in));
     if (st != st_in)
@@ -1173,6 +1389,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     uint64_t total_ub = 0;
     GNB_CUDA(cudaMemcpyAsync(&total_ub, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaStreamSynchronize(st));
+    trace_mark(this, "k2.scan_done");
     timing.d2h_bytes += 8;
     uint64_t total = 0;
     uint32_t mx    = 0;
@@ -1192,6 +1409,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
         GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         GNB_CUDA(cudaStreamSynchronize(st));
         d_counts_valid = true;
+        trace_mark(this, "k2.done");
         total = agg.sum;
         mx    = agg.mx;
     }
@@ -1232,6 +1450,12 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     hibf_ms    = 0;
     std::vector<uint2> items;
     items.reserve(n);
+    if (active_on_device && li > 0 && n)
+    {
+        GNB_CUDA(cudaMemcpyAsync(h_active.data(), d_active.p, n, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        timing.d2h_bytes += n;
+    }
     for (uint32_t r = 0; r < n; ++r)
         if (h_active[r] && h_counts[r] > 0 && h_counts[r] <= 65535)
             items.push_back(make_uint2(r, 0));
@@ -1300,6 +1524,37 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     return GNB_OK;
 }
 
+// K3 of this batch starts after the last kernel of the batch submitted before it
+int BatchCtx::wait_turn()
+{
+    if (seq == 0 || turn_taken)
+        return GNB_OK;
+    turn_taken = true;
+    if (seq > 1)
+    {
+        {
+            std::unique_lock<std::mutex> lock(S->chain_mu);
+            S->chain_cv.wait(lock, [&] { return S->chain_recorded + 1 >= seq; });
+        }
+        if (prev_done)
+            GNB_CUDA(cudaStreamWaitEvent(st, prev_done, 0));
+    }
+    return GNB_OK;
+}
+
+void BatchCtx::signal_done()
+{
+    if (seq == 0 || done_signalled)
+        return;
+    done_signalled = true;
+    cudaEventRecord(ev_done, st);
+    {
+        std::lock_guard<std::mutex> lock(S->chain_mu);
+        S->chain_recorded = std::max(S->chain_recorded, seq);
+    }
+    S->chain_cv.notify_all();
+}
+
 // K3 (+ sort) for every filter of level li on the reads still active
 int BatchCtx::run_level(size_t li)
 {
@@ -1311,13 +1566,21 @@ int BatchCtx::run_level(size_t li)
     const uint8_t *act = nullptr;
     if (li > 0 && n)
     {
-        GNB_CUDA(cudaMemcpyAsync(d_active.p, h_active.data(), n, cudaMemcpyHostToDevice, st));
-        timing.h2d_bytes += n;
+        if (!active_on_device)
+        {
+            GNB_CUDA(cudaMemcpyAsync(d_active.p, h_active.data(), n, cudaMemcpyHostToDevice, st));
+            timing.h2d_bytes += n;
+        }
         act = d_active.as<uint8_t>();
     }
+    const bool stay = keep_on_device && L.device_finish && L.filters.size() == 1; // K4 consumes the tuples in HBM
+    tuples_on_device = false;
+    n_tuples_dev     = 0;
     uint64_t active_hashes = 0;
     if (li == 0 && max_hashes_ub <= 65535)
         active_hashes = total_hashes;
+    else if (li > 0 && active_on_device)
+        active_hashes = next_active_hashes;
     else
         for (uint32_t i = 0; i < n; ++i)
             if (h_active[i] && h_counts[i] <= 65535)
@@ -1328,6 +1591,8 @@ int BatchCtx::run_level(size_t li)
         FilterRt              &F  = L.filters[fi];
         PinnedVec<uint64_t>   &Ft = tuples[li][fi];
         Ft.clear();
+        if (stay)
+            tuples_on_device = true;
         if (n == 0)
             continue;
         uint64_t cap = d_tuples_a.cap / 8;
@@ -1337,6 +1602,7 @@ int BatchCtx::run_level(size_t li)
             cap = d_tuples_a.cap / 8;
         }
         unsigned long long produced = 0;
+        GNB_TRY(wait_turn());
         if (F.is_hibf)
         {
             uint64_t prod = 0;
@@ -1357,6 +1623,7 @@ int BatchCtx::run_level(size_t li)
             GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             timing.d2h_bytes += 8;
             GNB_CUDA(cudaStreamSynchronize(st));
+            trace_mark(this, "k3.done");
             GNB_CUDA(cudaGetLastError());
             {
                 float ms1 = 0;
@@ -1378,10 +1645,16 @@ int BatchCtx::run_level(size_t li)
         GNB_TRY(d_tmp.ensure(tb));
         launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
         GNB_CUDA(cudaEventRecord(ev[7], st));
-        Ft.resize(produced);
-        timing.d2h_bytes += produced * 8;
-        GNB_CUDA(cudaMemcpyAsync(Ft.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
+        if (stay)
+            n_tuples_dev = produced;
+        else
+        {
+            Ft.resize(produced);
+            timing.d2h_bytes += produced * 8;
+            GNB_CUDA(cudaMemcpyAsync(Ft.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
+        }
         GNB_CUDA(cudaStreamSynchronize(st));
+        trace_mark(this, "sort.done");
         float ms = 0;
         cudaEventElapsedTime(&ms, ev[6], ev[7]);
         ms_sort += ms;
@@ -1668,6 +1941,236 @@ int BatchCtx::finish_level(size_t li)
     return GNB_OK;
 }
 
+// The record table (ids, sequence lengths) in host memory: with K4 on every level it is only needed when a level falls
+// back to the host finishing stage.
+int BatchCtx::fetch_host_records()
+{
+    if (host_records_valid)
+        return GNB_OK;
+    const size_t n = n_reads;
+    if (n)
+    {
+        GNB_CUDA(cudaMemcpyAsync((void *)p_idoff, d_idoff.p, n * 4, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync((void *)p_idlen, d_idlen.p, n * 4, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync((void *)p_slen1, d_len1.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (paired)
+            GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        timing.d2h_bytes += (uint64_t)n * 4 * (paired ? 4 : 3);
+    }
+    host_records_valid = true;
+    return GNB_OK;
+}
+
+// Everything the host finishing stage of level li reads, brought to the host (after K4 declined the level).
+int BatchCtx::to_host_state(size_t li)
+{
+    GNB_TRY(fetch_host_records());
+    const size_t n = n_reads;
+    if (tuples_on_device)
+    {
+        PinnedVec<uint64_t> &Ft = tuples[li][0];
+        Ft.resize(n_tuples_dev);
+        if (n_tuples_dev)
+        {
+            GNB_CUDA(cudaMemcpyAsync(Ft.data(), d_tuples_b.p, n_tuples_dev * 8, cudaMemcpyDeviceToHost, st));
+            timing.d2h_bytes += n_tuples_dev * 8;
+        }
+        tuples_on_device = false;
+    }
+    if (active_on_device && n)
+    {
+        GNB_CUDA(cudaMemcpyAsync(h_active.data(), d_active.p, n, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemcpyAsync(h_read_level.data(), d_read_level.p, n, cudaMemcpyDeviceToHost, st));
+        timing.d2h_bytes += 2 * n;
+    }
+    GNB_CUDA(cudaStreamSynchronize(st));
+    active_on_device = false;
+    return GNB_OK;
+}
+
+// K4: finishing stage of level li on the device.  done = false: the level has to go through the host finishing stage
+// (an --fpr-query value inside the guard band, very long reads, or nothing staged for the device).
+// rep: report accumulators to add to; fetch: copy the level's result to the host.
+int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch, bool &done)
+{
+    done             = false;
+    LevelRt       &L = levels[li];
+    const uint32_t n = n_reads;
+    if (!L.device_finish || !tuples_on_device || max_hashes_ub > 4096 || n_tuples_dev >= 0xFFFFFFFFull)
+        return GNB_OK;
+    const bool first = li == 0, last = li + 1 == levels.size();
+    LevelOut  &O     = lv[li];
+    if (n == 0)
+    {
+        O.on_device = true;
+        O.n_matches = O.all_len = O.one_len = 0;
+        O.total     = gnb_totals{};
+        GNB_TRY(O.h_moff.ensure(8));
+        O.h_moff.as<uint64_t>()[0] = 0;
+        if (last)
+        {
+            unc_on_device = true;
+            unc_len_dev   = 0;
+        }
+        done = true;
+        return GNB_OK;
+    }
+    GNB_CUDA(cudaEventRecord(ev[10], st));
+    GNB_TRY(d_read_level.ensure(n));
+    if (first)
+        GNB_CUDA(cudaMemsetAsync(d_read_level.p, 0xFF, n, st));
+    else if (!active_on_device)
+    {
+        GNB_CUDA(cudaMemcpyAsync(d_active.p, h_active.data(), n, cudaMemcpyHostToDevice, st));
+        GNB_CUDA(cudaMemcpyAsync(d_read_level.p, h_read_level.data(), n, cudaMemcpyHostToDevice, st));
+        timing.h2d_bytes += 2ull * n;
+    }
+    GNB_TRY(d_tstart.ensure((size_t)n * 4));
+    GNB_TRY(d_nacc.ensure((size_t)n * 4));
+    GNB_TRY(d_sizes.ensure(((size_t)n + 1) * sizeof(FinishSizes)));
+    GNB_TRY(d_offs.ensure(((size_t)n + 1) * sizeof(FinishSizes)));
+    GNB_TRY(d_one.ensure((size_t)n * 8));
+    GNB_TRY(d_ftotals.ensure(kFinishTotals * 8));
+    GNB_TRY(d_moff.ensure(((size_t)n + 1) * 8));
+    GNB_TRY(d_tuples_a.ensure(n_tuples_dev * 8 + 8));
+    GNB_TRY(d_tmp.ensure(finish_scan_tmp_bytes(n)));
+    GNB_TRY(h_fin.ensure(sizeof(FinishSizes) + kFinishTotals * 8));
+
+    FinishParams P{};
+    P.tuples      = d_tuples_b.as<uint64_t>();
+    P.n_tuples    = n_tuples_dev;
+    P.entries     = d_tuples_a.as<uint64_t>();
+    P.tuple_start = d_tstart.as<uint32_t>();
+    P.n_hashes    = d_counts.as<uint32_t>();
+    P.len1        = d_len1.as<uint32_t>();
+    P.len2        = paired ? d_len2.as<uint32_t>() : nullptr;
+    P.id_off      = d_idoff.as<uint32_t>();
+    P.id_len      = d_idlen.as<uint32_t>();
+    P.blk1        = d_blk1.as<uint8_t>();
+    P.active      = d_active.as<uint8_t>();
+    P.read_level  = d_read_level.as<uint8_t>();
+    P.n_reads     = n;
+    P.n_acc       = d_nacc.as<uint32_t>();
+    P.sizes       = d_sizes.as<FinishSizes>();
+    P.offs        = d_offs.as<FinishSizes>();
+    P.one         = d_one.as<uint2>();
+    P.totals      = d_ftotals.as<unsigned long long>();
+    P.match_off   = d_moff.as<uint64_t>();
+    P.node_fpr    = L.d_node_fpr.as<double>();
+    P.node_class  = L.d_node_class.as<uint32_t>();
+    P.fpr_memo    = L.d_fpr_memo.as<unsigned long long>();
+    P.fpr_memo_mask = (uint32_t)(kFprMemoSlots - 1);
+    P.parent      = L.d_parent.as<int32_t>();
+    P.depth       = L.d_depth.as<uint32_t>();
+    P.name_off    = L.d_name_off.as<uint32_t>();
+    P.names       = L.d_names.as<char>();
+    P.rep         = rep;
+    P.root        = L.root;
+    P.rel_cutoff  = L.filters[0].rel_cutoff;
+    P.rel_filter  = L.rel_filter;
+    P.fpr_query   = L.fpr_query;
+    P.fpr_band    = S->fpr_band;
+    P.w           = L.w;
+    P.level       = (uint32_t)li;
+    P.is_hibf     = L.filters[0].is_hibf;
+    P.skip_lca    = skip_lca;
+    P.output_lca  = cfg.output_lca != 0;
+    P.output_all  = cfg.output_all != 0;
+    P.output_unc  = cfg.output_unclassified != 0;
+    P.first       = first;
+    P.last        = last;
+    launch_finish_select(P, st);
+    launch_finish_scan(P, d_tmp.p, d_tmp.cap, st);
+    launches += 3;
+    FinishSizes        *h_tot = h_fin.as<FinishSizes>();
+    unsigned long long *h_ft  = reinterpret_cast<unsigned long long *>(h_tot + 1);
+    GNB_CUDA(cudaMemcpyAsync(h_tot, d_offs.as<FinishSizes>() + n, sizeof(FinishSizes), cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaMemcpyAsync(h_ft, d_ftotals.p, kFinishTotals * 8, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    trace_mark(this, "k4.select_done");
+    GNB_CUDA(cudaGetLastError());
+    timing.d2h_bytes += sizeof(FinishSizes) + kFinishTotals * 8;
+    if (h_ft[kFtAmbiguous])
+        return GNB_OK; // nothing outside the scratch buffers was touched: the host stage takes the level
+    const FinishSizes T = *h_tot;
+    GNB_TRY(d_mt.ensure(T.kept * 4 + 4));
+    GNB_TRY(d_mc.ensure(T.kept * 4 + 4));
+    GNB_TRY(d_all.ensure(T.all_bytes + 1));
+    GNB_TRY(d_one_txt.ensure(T.one_bytes + 1));
+    GNB_TRY(d_unc.ensure(T.unc_bytes + 1));
+    P.match_target = d_mt.as<uint32_t>();
+    P.match_count  = d_mc.as<uint32_t>();
+    P.all_text     = d_all.as<char>();
+    P.one_text     = d_one_txt.as<char>();
+    P.unc_text     = d_unc.as<char>();
+    launch_finish_write(P, st);
+    launches += 1;
+    GNB_CUDA(cudaEventRecord(ev[11], st));
+    if (last)
+        signal_done(); // the next batch may start K3 while this one's result travels to the host
+    if (fetch)
+    {
+        GNB_TRY(O.h_moff.ensure(((size_t)n + 1) * 8));
+        GNB_TRY(O.h_mt.ensure(T.kept * 4 + 4));
+        GNB_TRY(O.h_mc.ensure(T.kept * 4 + 4));
+        GNB_TRY(O.h_all.ensure(T.all_bytes + 1));
+        GNB_TRY(O.h_one.ensure(T.one_bytes + 1));
+        GNB_CUDA(cudaMemcpyAsync(O.h_moff.p, d_moff.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (T.kept)
+        {
+            GNB_CUDA(cudaMemcpyAsync(O.h_mt.p, d_mt.p, T.kept * 4, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync(O.h_mc.p, d_mc.p, T.kept * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (T.all_bytes)
+            GNB_CUDA(cudaMemcpyAsync(O.h_all.p, d_all.p, T.all_bytes, cudaMemcpyDeviceToHost, st));
+        if (T.one_bytes)
+            GNB_CUDA(cudaMemcpyAsync(O.h_one.p, d_one_txt.p, T.one_bytes, cudaMemcpyDeviceToHost, st));
+        timing.d2h_bytes += ((uint64_t)n + 1) * 8 + T.kept * 8 + T.all_bytes + T.one_bytes;
+        if (last)
+        {
+            GNB_TRY(h_unc.ensure(T.unc_bytes + 1));
+            if (T.unc_bytes)
+                GNB_CUDA(cudaMemcpyAsync(h_unc.p, d_unc.p, T.unc_bytes, cudaMemcpyDeviceToHost, st));
+            timing.d2h_bytes += T.unc_bytes;
+        }
+    }
+    GNB_CUDA(cudaStreamSynchronize(st));
+    trace_mark(this, "k4.write_d2h_done");
+    GNB_CUDA(cudaGetLastError());
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev[10], ev[11]) == cudaSuccess)
+        ms_finish_dev += ms;
+    O.on_device = true;
+    O.n_matches = T.kept;
+    O.all_len   = T.all_bytes;
+    O.one_len   = T.one_bytes;
+    gnb_totals &t = O.total;
+    t             = gnb_totals{};
+    t.seqs_processed             = h_ft[kFtProcessed];
+    t.seqs_skipped_big           = h_ft[kFtSkippedBig];
+    t.seqs_skipped_small         = h_ft[kFtSkippedSmall];
+    t.length_processed           = h_ft[kFtLength];
+    t.kmers_processed            = h_ft[kFtKmers];
+    t.seqs_classified            = h_ft[kFtClassified];
+    t.kmers_matches              = h_ft[kFtKmersMatches];
+    t.kmers_from_classified_seqs = h_ft[kFtKmersClassified];
+    t.matches                    = h_ft[kFtMatches];
+    t.seqs_unique                = h_ft[kFtUnique];
+    t.discarded_matches_filter   = h_ft[kFtDiscFilter];
+    t.discarded_matches_fprquery = h_ft[kFtDiscFpr];
+    next_active_hashes           = h_ft[kFtActiveHashesNext];
+    if (last)
+    {
+        unc_on_device = true;
+        unc_len_dev   = T.unc_bytes;
+    }
+    active_on_device = true;
+    levels_on_device += 1;
+    done = true;
+    return GNB_OK;
+}
+
 void BatchCtx::begin_finish()
 {
     for (auto &W : workers)
@@ -1683,6 +2186,17 @@ void BatchCtx::begin_finish()
         W.n_classified = 0;
     }
     timing.ms_host_finish = 0;
+    for (auto &o : lv)
+    {
+        o.on_device = false;
+        o.n_matches = o.all_len = o.one_len = 0;
+        o.total = gnb_totals{};
+    }
+    unc_on_device    = false;
+    unc_len_dev      = 0;
+    finish_T         = 0;
+    ms_finish_dev    = 0;
+    levels_on_device = 0;
 }
 
 void BatchCtx::fill_timings(gnb_batch_result *t)
@@ -1736,12 +2250,25 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
         r_one[li].resize(off_one[li * (T + 1) + T]);
     }
     r_unc.resize(off_unc[T]);
-    r_match_off.resize((size_t)n + 1);
-    r_match_target.resize(off_m[T]);
-    r_match_count.resize(off_m[T]);
+    uint64_t dev_matches = 0;
+    bool     any_dev     = false;
+    for (auto const &o : lv)
+        if (o.on_device)
+        {
+            dev_matches += o.n_matches;
+            n_classified += o.total.seqs_classified;
+            any_dev = true;
+        }
+    const bool csr_device = NL == 1 && lv[0].on_device; // the level's CSR in pinned memory is the result
+    if (!csr_device)
+    {
+        r_match_off.resize((size_t)n + 1);
+        r_match_target.resize(off_m[T] + dev_matches);
+        r_match_count.resize(off_m[T] + dev_matches);
+    }
     // With one hierarchy level the workers' match lists, taken in worker order, already are the CSR value arrays
     // (worker w finished the reads [n*w/Tf, n*(w+1)/Tf) in order); with several levels the lists interleave.
-    const bool csr_parallel = NL == 1 && finish_T > 0;
+    const bool csr_parallel = NL == 1 && finish_T > 0 && !any_dev;
     auto piece = [&](int w) {
         Worker &W = workers[w];
         for (size_t li = 0; li < NL; ++li)
@@ -1788,7 +2315,9 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
         for (auto &t : th)
             t.join();
     }
-    if (csr_parallel)
+    if (csr_device)
+        ;
+    else if (csr_parallel)
         r_match_off[n] = off_m[T];
     else
     {
@@ -1796,8 +2325,28 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
         for (auto &W : workers)
             for (size_t i = 0; i + 1 < W.m_off.size(); i += 2)
                 r_match_off[W.m_off[i] + 1] = W.m_off[i + 1];
+        for (auto const &o : lv) // a read is classified at one level only
+            if (o.on_device && o.n_matches)
+            {
+                const uint64_t *mo = o.h_moff.as<uint64_t>();
+                for (size_t i = 0; i < n; ++i)
+                    if (mo[i + 1] != mo[i])
+                        r_match_off[i + 1] = mo[i + 1] - mo[i];
+            }
         for (size_t i = 0; i < n; ++i)
             r_match_off[i + 1] += r_match_off[i];
+        for (auto const &o : lv)
+            if (o.on_device && o.n_matches)
+            {
+                const uint64_t *mo = o.h_moff.as<uint64_t>();
+                const uint32_t *mt = o.h_mt.as<uint32_t>(), *mc = o.h_mc.as<uint32_t>();
+                for (size_t i = 0; i < n; ++i)
+                    if (mo[i + 1] != mo[i])
+                    {
+                        std::copy(mt + mo[i], mt + mo[i + 1], r_match_target.begin() + r_match_off[i]);
+                        std::copy(mc + mo[i], mc + mo[i + 1], r_match_count.begin() + r_match_off[i]);
+                    }
+            }
         for (auto &W : workers)
         {
             size_t p = 0;
@@ -1830,6 +2379,8 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
                 add_totals(L.total[prefix_id], W.total[li]);
                 W.total[li] = gnb_totals{};
             }
+            if (lv[li].on_device)
+                add_totals(L.total[prefix_id], lv[li].total);
         }
         levels[0].total[prefix_id].input_seqs += n;
     }
@@ -1843,12 +2394,19 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
         r_all_l.push_back(r_all[li].size());
         r_one_p.push_back(r_one[li].data());
         r_one_l.push_back(r_one[li].size());
+        if (lv[li].on_device)
+        {
+            r_all_p.back() = lv[li].h_all.as<char>();
+            r_all_l.back() = lv[li].all_len;
+            r_one_p.back() = lv[li].h_one.as<char>();
+            r_one_l.back() = lv[li].one_len;
+        }
     }
     timing.ms_d2h = (float)ms_since(t_collect); // host merge of the workers' pieces (no device copy happens here)
     fill_timings(&result);
-    result.match_off    = r_match_off.data();
-    result.match_target = r_match_target.data();
-    result.match_count  = r_match_count.data();
+    result.match_off    = csr_device ? lv[0].h_moff.as<uint64_t>() : r_match_off.data();
+    result.match_target = csr_device ? lv[0].h_mt.as<uint32_t>() : r_match_target.data();
+    result.match_count  = csr_device ? lv[0].h_mc.as<uint32_t>() : r_match_count.data();
     result.read_level   = h_read_level.data();
     result.n_hashes     = h_counts.data();
     result.n_classified = n_classified;
@@ -1857,8 +2415,11 @@ int BatchCtx::collect(uint32_t prefix_id, gnb_batch_result *out)
     result.all_len      = r_all_l.data();
     result.one_text     = r_one_p.data();
     result.one_len      = r_one_l.data();
-    result.unc_text     = r_unc.data();
-    result.unc_len      = r_unc.size();
+    result.unc_text     = unc_on_device ? h_unc.as<char>() : r_unc.data();
+    result.unc_len      = unc_on_device ? unc_len_dev : r_unc.size();
+    result.ms_finish_device = ms_finish_dev;
+    result.levels_on_device = levels_on_device;
+    trace_mark(this, "job.end");
     if (out)
         *out = result;
     staged = ran = false;
@@ -1870,13 +2431,41 @@ int BatchCtx::finish(uint32_t prefix_id, gnb_batch_result *out)
 {
     GNB_CUDA(cudaSetDevice(device));
     begin_finish();
+    keep_on_device = true;
+    struct TurnGuard
+    {
+        BatchCtx *c;
+        ~TurnGuard()
+        {
+            c->wait_turn_noexcept();
+            c->signal_done();
+        }
+    } turn_guard{this};
+    trace_mark(this, "job.begin");
     for (size_t li = 0; li < levels.size(); ++li)
     {
         if (!(li == 0 && ran))
             GNB_TRY(run_level(li));
-        auto th = Clock::now();
-        GNB_TRY(finish_level(li));
+        auto th   = Clock::now();
+        bool done = false;
+        if (levels[li].device_finish && tuples_on_device)
+        {
+            unsigned long long *rep = nullptr;
+            GNB_TRY(S->device_rep(li, prefix_id, &rep));
+            GNB_TRY(finish_level_device(li, rep, true, done));
+        }
+        if (!done)
+        {
+            GNB_TRY(to_host_state(li));
+            GNB_TRY(finish_level(li));
+        }
         timing.ms_host_finish += ms_since(th);
+    }
+    if (active_on_device && n_reads)
+    { // classified level of every read for the structured result
+        GNB_CUDA(cudaMemcpyAsync(h_read_level.data(), d_read_level.p, n_reads, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        timing.d2h_bytes += n_reads;
     }
     return collect(prefix_id, out);
 }
@@ -1911,6 +2500,7 @@ extern "C" int gnb_session_stage(gnb_session *s, const char *b1, uint64_t l1, co
         return fail(GNB_ERR_ARG, "gnb_session_stage: bad arguments");
     GNB_TRY(sync_slot(s));
     BatchCtx &c = *s->slots[0];
+    c.seq       = 0;
     GNB_TRY(c.stage(b1, l1, b2, l2, fin));
     if (n_reads)
         *n_reads = c.n_reads;
@@ -1931,10 +2521,28 @@ extern "C" int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings)
     c.timing.d2h_bytes = 0;
     c.launches = 0;
     std::fill(c.h_active.begin(), c.h_active.end(), (uint8_t)1);
+    c.keep_on_device = true;
+    c.ms_finish_dev  = 0;
     GNB_TRY(c.run_level(0));
     c.ran = true;
+    if (s->levels[0].device_finish && c.tuples_on_device)
+    { // K4 of the first level belongs to the pass; its report counters go to a scratch accumulator
+        const size_t bytes = s->levels[0].node_names.size() * 5 * 8;
+        if (!s->d_rep_scratch.p)
+        {
+            GNB_TRY(s->d_rep_scratch.ensure(bytes));
+            GNB_CUDA(cudaMemset(s->d_rep_scratch.p, 0, bytes));
+        }
+        bool done = false;
+        GNB_TRY(c.finish_level_device(0, s->d_rep_scratch.as<unsigned long long>(), false, done));
+        c.active_on_device = false; // finish_staged starts over from the staged state
+        c.levels_on_device = 0;
+    }
     if (timings)
+    {
         c.fill_timings(timings);
+        timings->ms_finish_device = c.ms_finish_dev;
+    }
     return GNB_OK;
 }
 
@@ -1954,6 +2562,7 @@ extern "C" int gnb_session_run_level(gnb_session *s, uint32_t level)
     GNB_CUDA(cudaSetDevice(c.device));
     if (level == 0)
         c.begin_finish();
+    c.keep_on_device = false; // the tuples are exchanged between ranks on the host
     return c.run_level(level);
 }
 
@@ -1984,6 +2593,7 @@ extern "C" int gnb_session_finish_level(gnb_session *s, uint32_t level)
         return fail(GNB_ERR_ARG, "gnb_session_finish_level: nothing staged or bad level");
     BatchCtx &c = *s->slots[0];
     auto      th = Clock::now();
+    GNB_TRY(c.fetch_host_records());
     GNB_TRY(c.finish_level(level));
     c.timing.ms_host_finish += ms_since(th);
     return GNB_OK;
@@ -2016,6 +2626,15 @@ extern "C" int gnb_session_submit(gnb_session *s, uint32_t prefix_id, const char
         c.fill_timings(staged_info);
     c.busy   = true;
     c.job_rc = GNB_OK;
+    c.seq            = s->next_seq++;
+    c.turn_taken     = false;
+    c.done_signalled = false;
+    c.prev_done      = s->in_flight.empty() ? nullptr : s->slots[s->in_flight.back()]->ev_done;
+    if (!c.prev_done)
+    { // nothing to wait for: this batch opens a new chain
+        std::lock_guard<std::mutex> lock(s->chain_mu);
+        s->chain_recorded = std::max(s->chain_recorded, c.seq - 1);
+    }
     c.job    = std::thread([&c, prefix_id]() {
         auto tj  = Clock::now();
         c.job_rc = c.finish(prefix_id, nullptr);
@@ -2067,6 +2686,7 @@ extern "C" int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const ch
     auto      t0 = Clock::now();
     BatchCtx &c  = *s->slots[0];
     s->holding   = 0;
+    c.seq        = 0;
     GNB_TRY(c.stage(b1, l1, b2, l2, fin));
     GNB_TRY(c.finish(prefix_id, out));
     out->ms_total = ms_since(t0);
@@ -2138,6 +2758,10 @@ extern "C" int gnb_session_report(gnb_session *s, uint32_t prefix_id, const char
 {
     if (!s || !text || !len)
         return fail(GNB_ERR_ARG, "null argument");
+    for (auto &c : s->slots) // the accumulators in HBM are folded in once no batch is running
+        if (c->job.joinable())
+            c->job.join();
+    GNB_TRY(s->drain_device_rep());
     std::string &o = s->report_text;
     o.clear();
     for (auto const &L : s->levels)

@@ -165,6 +165,8 @@ typedef struct
     uint64_t count_kernel_bytes; /* algorithmic bytes of the IBF-count launches: sum n_hashes * h * bin_words * 8   */
     uint64_t n_kernel_launches;  /* kernels of this library launched for the batch                                  */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host for the batch                        */
+    float    ms_finish_device;   /* K4 (finishing stage kernels: select, scan, write) of the batch                  */
+    uint32_t levels_on_device;   /* hierarchy levels of the batch finished by K4 (the others by the host stage)     */
 } gnb_batch_result;
 
 int  gnb_session_create(const gnb_session_config *cfg, gnb_session **out);

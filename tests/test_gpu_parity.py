@@ -113,8 +113,26 @@ def _read_sorted(path):
         return sorted(l.rstrip("\n") for l in f)
 
 
+FINISH_MODES = {
+    # K4 on the device for every single-filter level (the default)
+    "device": {},
+    # the host finishing stage for every level
+    "host": {"GANON_B200_HOST_FINISH": "1"},
+    # K4 first; every --fpr-query value counts as "too close to the threshold", so levels with --fpr-query < 1 are
+    # handed to the host finishing stage after the device pass (the path a borderline libm value takes)
+    "fallback": {"GANON_B200_FPR_BAND": "2"},
+}
+
+
+@pytest.fixture(params=sorted(FINISH_MODES))
+def finish_mode(request, monkeypatch):
+    for k, v in FINISH_MODES[request.param].items():
+        monkeypatch.setenv(k, v)
+    return request.param
+
+
 @pytest.mark.parametrize("name", sorted(SU.load_scenarios()))
-def test_golden_scenarios_match_reference_outputs(name, golden_dbs, tmp_path):
+def test_golden_scenarios_match_reference_outputs(name, golden_dbs, tmp_path, finish_mode):
     """The `ganon-classify` drop-in on the arguments the reference binary was run with; every output file the
     reference wrote must exist with identical (sorted) lines, and no extra file may appear."""
     args = SU.expand(SU.load_scenarios()[name], golden_dbs)
@@ -127,7 +145,7 @@ def test_golden_scenarios_match_reference_outputs(name, golden_dbs, tmp_path):
         assert _read_sorted(pre + ext) == SU.expected_lines(name, ext[1:]), ext
 
 
-def test_session_matches_oracle_multibin_targets_and_blocks():
+def test_session_matches_oracle_multibin_targets_and_blocks(finish_mode):
     """Synthetic DB whose targets span 1..5 bins (crossing 32-bin registers, lanes and 4096-bin chunks), paired
     reads, fed in several blocks; structured result and text vs the oracle."""
     rng = np.random.default_rng(3)
@@ -191,6 +209,13 @@ def test_session_matches_oracle_multibin_targets_and_blocks():
             # structured CSR agrees with the text
             nm = res.match_off[res.n_reads]
             assert nm == len(result_text(res, "all").decode().splitlines())
+            lines = result_text(res, "all").decode().splitlines()
+            for i in range(res.n_reads):  # CSR rows are the read's lines, in order
+                for j in range(res.match_off[i], res.match_off[i + 1]):
+                    assert lines[j].split("\t")[1:] == [names[res.match_target[j]], str(res.match_count[j])]
+                assert (res.read_level[i] == 0) == (res.match_off[i + 1] > res.match_off[i])
+            want_dev = {"device": 1, "host": 0, "fallback": 1 if fq >= 1.0 else 0}[finish_mode]
+            assert res.levels_on_device == want_dev, (finish_mode, fq)
         assert n_hashes == [r["n_hashes"] for r in want]
         assert sorted(got_all) == O.all_lines(want), (cutoff, relf, fq)
         assert sorted(got_unc) == sorted(r["id"].decode() for r in want if not r["matches"])
@@ -300,7 +325,7 @@ def test_hibf_sub_ibf_counts_match_oracle(golden_dbs):
 
 
 @pytest.mark.parametrize("name", sorted(SU.load_hibf_scenarios()))
-def test_hibf_scenarios_match_reference_outputs(name, golden_dbs, tmp_path):
+def test_hibf_scenarios_match_reference_outputs(name, golden_dbs, tmp_path, finish_mode):
     args = SU.expand(SU.load_hibf_scenarios()[name], golden_dbs)
     pre = str(tmp_path / name)
     assert cli.main(args + ["-o", pre, "-t", "4", "--quiet"]) == 0
