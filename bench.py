@@ -187,7 +187,7 @@ def write_sample(wl_name, b1, b2, n_reads, tag):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ganon_b200", choices=["ganon_b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GANON_B200_WORKLOAD", "c2"), choices=sorted(WORKLOADS))

@@ -1143,14 +1143,14 @@ void launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp
 // =====================================================================================================================
 // K4: finishing stage of one hierarchy level on the device (levels with one filter).
 //   k_tuple_starts    first tuple of every read in the sorted tuple list
-//   k_finish_select   warp per read.  Pass 1: runs of equal (read, node) are summed (partial sums of targets spread over
+//   k_finish_select   thread per read.  Pass 1: runs of equal (read, node) are summed (partial sums of targets spread over
 //                     several registers / chunks / technical bins), capped and compared with the cutoff exactly as
 //                     select_matches does (GC.cpp:504-541, 543-577; HIBF running sum wraps at 16 bits, HIBF.hpp:437-441);
 //                     max / min of the accepted counts.  Pass 2: rel-filter threshold (GC.cpp:757-758, 579-587) and
 //                     --fpr-query (GC.cpp:588-601) per accepted match, LCA of the kept targets (GC.cpp:615-627), sizes of
 //                     the read's .all/.one/.unc lines, per-batch totals (struct Total GC.cpp:162-177).
 //                     No side effect outside the batch's scratch: the host may still discard the pass (see below).
-//   k_finish_write    warp per read, after the exclusive scan of the sizes: report counters (struct Rep GC.cpp:153-160,
+//   k_finish_write    thread per read, after the exclusive scan of the sizes: report counters (struct Rep GC.cpp:153-160,
 //                     atomics on the run's accumulators), CSR of the kept matches, text lines (GC.cpp:1289-1322),
 //                     active mask / classified level of the read for the next hierarchy level (GC.cpp:811-830).
 // --fpr-query compares a libm double with the threshold.  The device evaluates the same expression with CUDA's
@@ -1159,7 +1159,7 @@ void launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp
 // =====================================================================================================================
 namespace
 {
-constexpr int      K4_WARPS = 8;
+constexpr int      K4_THREADS = 256;
 constexpr uint32_t kNoTuple = 0xFFFFFFFFu, kNoNode = 0xFFFFFFFFu, kFull = 0xFFFFFFFFu;
 
 __global__ void k_tuple_starts(const uint64_t *__restrict__ tuples, uint64_t n, uint32_t *__restrict__ start)
@@ -1228,43 +1228,39 @@ __device__ __forceinline__ uint32_t dec_digits(uint32_t v)
     return v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6 : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
 }
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+// One thread per read (grid-stride): a read has few tuples, and what bounds the pass is the chain of dependent loads
+// per read (record -> first tuple -> tuples -> fpr cache -> names), so the more reads in flight the better.
+__global__ void __launch_bounds__(K4_THREADS) k_finish_select(const FinishParams p)
 {
-    return __reduce_add_sync(kFull, v);
-}
-
-__global__ void __launch_bounds__(K4_WARPS * 32) k_finish_select(const FinishParams p)
-{
-    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    unsigned long long acc = 0; // lane i accumulates totals[i]
+    const uint32_t lane   = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long acc = 0; // lane i of every warp accumulates totals[i]
     bool               ambiguous = false;
-#define K4_ADD(idx, v)                        \
-    do                                        \
-    {                                         \
-        if (lane == (idx))                    \
-            acc += (unsigned long long)(v);   \
-    } while (0)
-    for (uint32_t r = warp; r < p.n_reads; r += n_warps)
+    // the loop bound is warp-uniform so that the warp reductions below see all lanes
+    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < p.n_reads; r0 += stride)
     {
-        const bool  act = p.first ? true : p.active[r] != 0;
-        FinishSizes sz{0, 0, 0, 0};
-        uint32_t    nacc = 0;
-        uint2       one  = make_uint2(0, 0);
+        const uint32_t r     = r0 + lane;
+        const bool     inb   = r < p.n_reads;
+        const bool     act   = inb && (p.first ? true : p.active[r] != 0);
+        FinishSizes    sz{0, 0, 0, 0};
+        uint32_t       nacc = 0;
+        uint2          one  = make_uint2(0, 0);
+        uint32_t       c_small = 0, c_big = 0, c_proc = 0, c_len = 0, c_kmers = 0, c_class = 0, c_kmatch = 0, c_kclass = 0, c_match = 0, c_uniq = 0,
+                 c_dfilter = 0, c_dfpr = 0, c_next = 0;
         if (act)
         {
             const uint32_t nh = p.n_hashes[r], l1 = p.len1[r], l2 = p.len2 ? p.len2[r] : 0;
             if (p.first)
             {
                 if (l1 < p.w)
-                    K4_ADD(kFtSkippedSmall, 1);
+                    c_small = 1;
                 else if (nh > 65535)
-                    K4_ADD(kFtSkippedBig, 1);
+                    c_big = 1;
                 else
                 {
-                    K4_ADD(kFtProcessed, 1);
-                    K4_ADD(kFtLength, (unsigned long long)l1 + l2);
-                    K4_ADD(kFtKmers, nh);
+                    c_proc  = 1;
+                    c_len   = l1 + l2;
+                    c_kmers = nh;
                 }
             }
             const uint32_t start = p.tuple_start[r];
@@ -1273,135 +1269,107 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k_finish_select(const FinishPar
             if (start != kNoTuple)
             {
                 // ---- pass 1: sum runs of equal (read, node), cap, cutoff ----
-                const uint32_t cutoff    = threshold_cutoff(nh, p.rel_cutoff);
-                uint32_t       prev_node = kNoNode;
-                for (uint64_t base = start;; base += 32)
-                {
-                    const uint64_t i    = base + lane;
-                    const uint64_t t    = i < p.n_tuples ? p.tuples[i] : ~0ull;
-                    const bool     mine = i < p.n_tuples && (uint32_t)(t >> kTupleReadShift) == r;
-                    const uint32_t mb   = __ballot_sync(kFull, mine);
-                    if (!mb)
-                        break;
-                    const uint32_t node = (uint32_t)(t >> kTupleNodeShift) & (kMaxNodes - 1);
-                    uint32_t       pn   = __shfl_up_sync(kFull, node, 1);
-                    if (lane == 0)
-                        pn = prev_node;
-                    bool     ok  = false;
-                    uint32_t cnt = 0;
-                    if (mine && node != pn)
+                const uint32_t cutoff = threshold_cutoff(nh, p.rel_cutoff);
+                uint64_t       run_key = ~0ull, sum = 0;
+                bool           partial = false;
+                auto           flush   = [&]() {
+                    if (run_key == ~0ull)
+                        return;
+                    bool ok = true;
+                    if (p.is_hibf)
                     {
-                        uint64_t sum     = t & 0xFFFF;
-                        bool     partial = ((t >> 16) & 1) != 0;
-                        for (uint64_t j = i + 1; j < p.n_tuples; ++j)
-                        {
-                            const uint64_t u = p.tuples[j];
-                            if ((u >> kTupleNodeShift) != (t >> kTupleNodeShift))
-                                break;
-                            sum += u & 0xFFFF;
-                            partial |= ((u >> 16) & 1) != 0;
-                        }
-                        ok = true;
-                        if (p.is_hibf)
-                        {
-                            if (partial)
-                                sum &= 0xFFFF;
-                            if (sum < cutoff || sum == 0)
-                                ok = false;
-                            if (sum > nh)
-                                sum = nh;
-                        }
-                        else if (partial)
-                        {
-                            if (sum > nh)
-                                sum = nh;
-                            if (sum < cutoff)
-                                ok = false;
-                        }
-                        cnt = (uint32_t)sum;
+                        if (partial)
+                            sum &= 0xFFFF;
+                        if (sum < cutoff || sum == 0)
+                            ok = false;
+                        if (sum > nh)
+                            sum = nh;
                     }
-                    prev_node          = __shfl_sync(kFull, node, 31);
-                    const uint32_t okb = __ballot_sync(kFull, ok);
+                    else if (partial)
+                    {
+                        if (sum > nh)
+                            sum = nh;
+                        if (sum < cutoff)
+                            ok = false;
+                    }
                     if (ok)
-                        p.entries[(uint64_t)start + nacc + __popc(okb & lt)] = ((uint64_t)node << 32) | cnt;
-                    nacc += __popc(okb);
-                    max_c = max(max_c, __reduce_max_sync(kFull, ok ? cnt : 0u));
-                    min_c = min(min_c, __reduce_min_sync(kFull, ok ? cnt : 0xFFFFFFFFu));
-                    if (mb != kFull)
+                    {
+                        const uint32_t node = (uint32_t)run_key & (kMaxNodes - 1), cnt = (uint32_t)sum;
+                        p.entries[(uint64_t)start + nacc++] = ((uint64_t)node << 32) | cnt;
+                        max_c = max(max_c, cnt);
+                        min_c = min(min_c, cnt);
+                    }
+                };
+                for (uint64_t i = start; i < p.n_tuples; ++i)
+                {
+                    const uint64_t t = p.tuples[i];
+                    if ((uint32_t)(t >> kTupleReadShift) != r)
                         break;
+                    const uint64_t key = t >> kTupleNodeShift; // (read, node)
+                    if (key != run_key)
+                    {
+                        flush();
+                        run_key = key;
+                        sum     = 0;
+                        partial = false;
+                    }
+                    sum += t & 0xFFFF;
+                    partial |= ((t >> 16) & 1) != 0;
                 }
-                __syncwarp();
+                flush();
                 // ---- pass 2: rel-filter, fpr-query, LCA, sizes ----
                 if (nacc)
                 {
                     const uint64_t thr_ceil         = (uint64_t)ceil(__dmul_rn((double)(max_c - min_c), p.rel_filter));
                     const double   threshold_filter = (double)((uint64_t)max_c - thr_ceil);
-                    uint32_t       n_filter = 0, n_fpr = 0;
-                    for (uint32_t base = 0; base < nacc; base += 32)
+                    for (uint32_t j = 0; j < nacc; ++j)
                     {
-                        const uint32_t idx   = base + lane;
-                        const bool     valid = idx < nacc;
-                        uint64_t       e     = valid ? p.entries[(uint64_t)start + idx] : 0;
+                        const uint64_t e    = p.entries[(uint64_t)start + j];
                         const uint32_t node = (uint32_t)(e >> 32), cnt = (uint32_t)(e & 0xFFFF);
                         uint32_t       status = 0;
-                        if (valid)
+                        if ((double)cnt >= threshold_filter)
                         {
-                            if ((double)cnt >= threshold_filter)
+                            if (p.fpr_query < 1.0)
                             {
-                                if (p.fpr_query < 1.0)
-                                {
-                                    const double q = dev_fpr_query_cached(p, node, nh, cnt);
-                                    if (fabs(q - p.fpr_query) <= p.fpr_band)
-                                        ambiguous = true;
-                                    if (q > p.fpr_query)
-                                        status = 2;
-                                }
+                                const double q = dev_fpr_query_cached(p, node, nh, cnt);
+                                if (fabs(q - p.fpr_query) <= p.fpr_band)
+                                    ambiguous = true;
+                                if (q > p.fpr_query)
+                                    status = 2;
                             }
-                            else
-                                status = 1;
-                            p.entries[(uint64_t)start + idx] = e | ((uint64_t)status << 16);
                         }
-                        const bool     keep = valid && status == 0;
-                        const uint32_t kb   = __ballot_sync(kFull, keep);
-                        n_filter += __popc(__ballot_sync(kFull, valid && status == 1));
-                        n_fpr += __popc(__ballot_sync(kFull, valid && status == 2));
-                        if (p.output_all)
-                            all_bytes += warp_sum(keep ? idl + 1 + (p.name_off[node + 1] - p.name_off[node]) + 1 + dec_digits(cnt) + 1 : 0u);
-                        if (kb)
+                        else
+                            status = 1;
+                        if (status)
+                            p.entries[(uint64_t)start + j] = e | ((uint64_t)status << 16);
+                        if (status == 1)
+                            ++c_dfilter;
+                        else if (status == 2)
+                            ++c_dfpr;
+                        else
                         {
-                            const uint32_t nk = __popc(kb);
-                            if (kept == 0 && nk == 1)
+                            if (p.output_all)
+                                all_bytes += idl + 1 + (p.name_off[node + 1] - p.name_off[node]) + 1 + dec_digits(cnt) + 1;
+                            if (kept == 0)
                             {
-                                const int src = __ffs(kb) - 1;
-                                one_node      = __shfl_sync(kFull, node, src);
-                                one_cnt       = __shfl_sync(kFull, cnt, src);
+                                one_node = node;
+                                one_cnt  = cnt;
                             }
                             else if (!p.skip_lca)
-                            {
-                                uint32_t x = keep ? node : kNoNode;
-#pragma unroll
-                                for (int off = 16; off > 0; off >>= 1)
-                                {
-                                    const uint32_t y = __shfl_xor_sync(kFull, x, off);
-                                    x = x == kNoNode ? y : y == kNoNode ? x : dev_lca2(p.parent, p.depth, p.root, x, y);
-                                }
-                                one_node = one_node == kNoNode ? x : dev_lca2(p.parent, p.depth, p.root, one_node, x);
-                            }
-                            kept += nk;
+                                one_node = dev_lca2(p.parent, p.depth, p.root, one_node, node);
+                            ++kept;
                         }
                     }
-                    K4_ADD(kFtMatches, kept);
-                    K4_ADD(kFtDiscFilter, n_filter);
-                    K4_ADD(kFtDiscFpr, n_fpr);
+                    c_match = kept;
                 }
             }
             if (kept > 0)
             {
-                K4_ADD(kFtClassified, 1);
-                K4_ADD(kFtKmersClassified, nh);
-                K4_ADD(kFtKmersMatches, max_c);
+                c_class  = 1;
+                c_kclass = nh;
+                c_kmatch = max_c;
                 if (kept == 1)
-                    K4_ADD(kFtUnique, 1);
+                    c_uniq = 1;
                 else
                 {
                     if (p.skip_lca)
@@ -1418,23 +1386,53 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k_finish_select(const FinishPar
             {
                 if (p.last && p.output_unc)
                     sz.unc_bytes = idl + 1;
-                K4_ADD(kFtActiveHashesNext, nh <= 65535 ? nh : 0);
+                c_next = nh <= 65535 ? nh : 0;
             }
         }
-        if (lane == 0)
+        if (inb)
         {
             p.sizes[r] = sz;
             p.n_acc[r] = nacc;
             p.one[r]   = one;
         }
-    }
+#define K4_ADD(idx, v)                                         \
+    do                                                         \
+    {                                                          \
+        const uint32_t s_ = __reduce_add_sync(kFull, (v));     \
+        if (lane == (idx))                                     \
+            acc += s_;                                         \
+    } while (0)
+        if (p.first)
+        {
+            K4_ADD(kFtSkippedSmall, c_small);
+            K4_ADD(kFtSkippedBig, c_big);
+            K4_ADD(kFtProcessed, c_proc);
+            K4_ADD(kFtLength, c_len);
+            K4_ADD(kFtKmers, c_kmers);
+        }
+        K4_ADD(kFtClassified, c_class);
+        K4_ADD(kFtKmersMatches, c_kmatch);
+        K4_ADD(kFtKmersClassified, c_kclass);
+        K4_ADD(kFtMatches, c_match);
+        K4_ADD(kFtUnique, c_uniq);
+        K4_ADD(kFtDiscFilter, c_dfilter);
+        K4_ADD(kFtDiscFpr, c_dfpr);
+        K4_ADD(kFtActiveHashesNext, c_next);
 #undef K4_ADD
-    if (warp == 0 && lane == 0)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
         p.sizes[p.n_reads] = FinishSizes{0, 0, 0, 0};
     if (__any_sync(kFull, ambiguous) && lane == kFtAmbiguous)
         acc += 1;
+    __shared__ unsigned long long s_acc[kFinishTotals];
+    if (threadIdx.x < kFinishTotals)
+        s_acc[threadIdx.x] = 0;
+    __syncthreads();
     if (lane < kFinishTotals && acc)
-        atomicAdd(&p.totals[lane], acc);
+        atomicAdd(&s_acc[lane], acc);
+    __syncthreads();
+    if (threadIdx.x < kFinishTotals && s_acc[threadIdx.x])
+        atomicAdd(&p.totals[threadIdx.x], s_acc[threadIdx.x]);
 }
 
 struct FinishSizesAdd
@@ -1464,82 +1462,55 @@ __device__ __forceinline__ char *put_line(char *o, const uint8_t *id, uint32_t i
     return o;
 }
 
-__global__ void __launch_bounds__(K4_WARPS * 32) k_finish_write(const FinishParams p)
+__global__ void __launch_bounds__(K4_THREADS) k_finish_write(const FinishParams p)
 {
-    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    if (warp == 0 && lane == 0)
+    const uint32_t stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
         p.match_off[p.n_reads] = p.offs[p.n_reads].kept;
-    for (uint32_t r = warp; r < p.n_reads; r += n_warps)
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += stride)
     {
         const FinishSizes o = p.offs[r];
-        if (lane == 0)
-            p.match_off[r] = o.kept;
-        const bool act = p.first ? true : p.active[r] != 0;
+        p.match_off[r]      = o.kept;
+        const bool act      = p.first ? true : p.active[r] != 0;
         if (!act)
             continue;
         const uint32_t nacc  = p.n_acc[r];
         const uint32_t start = nacc ? p.tuple_start[r] : 0;
         const uint8_t *id    = p.blk1 + p.id_off[r];
         const uint32_t idl   = p.id_len[r];
-        uint32_t       kept = 0, bytes = 0;
-        for (uint32_t base = 0; base < nacc; base += 32)
+        uint32_t       kept  = 0;
+        char          *out   = p.all_text + o.all_bytes;
+        for (uint32_t j = 0; j < nacc; ++j)
         {
-            const uint32_t idx   = base + lane;
-            const bool     valid = idx < nacc;
-            const uint64_t e     = valid ? p.entries[(uint64_t)start + idx] : 0;
+            const uint64_t e    = p.entries[(uint64_t)start + j];
             const uint32_t node = (uint32_t)(e >> 32), cnt = (uint32_t)(e & 0xFFFF), status = (uint32_t)(e >> 16) & 3;
-            if (valid)
-                atomicAdd(&p.rep[(uint64_t)node * 5 + (status == 0 ? 0 : status == 1 ? 3 : 4)], 1ull);
-            const bool     keep = valid && status == 0;
-            const uint32_t kb   = __ballot_sync(kFull, keep);
-            if (!kb)
+            atomicAdd(&p.rep[(uint64_t)node * 5 + (status == 0 ? 0 : status == 1 ? 3 : 4)], 1ull);
+            if (status)
                 continue;
-            if (keep)
-            {
-                const uint64_t j   = o.kept + kept + __popc(kb & lt);
-                p.match_target[j] = node;
-                p.match_count[j]  = cnt;
-            }
+            p.match_target[o.kept + kept] = node;
+            p.match_count[o.kept + kept]  = cnt;
+            ++kept;
             if (p.output_all)
-            {
-                const uint32_t nl  = keep ? p.name_off[node + 1] - p.name_off[node] : 0;
-                const uint32_t len = keep ? idl + 1 + nl + 1 + dec_digits(cnt) + 1 : 0;
-                uint32_t       pos = len; // inclusive warp scan
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1)
-                {
-                    const uint32_t y = __shfl_up_sync(kFull, pos, off);
-                    if (lane >= (uint32_t)off)
-                        pos += y;
-                }
-                if (keep)
-                    put_line(p.all_text + o.all_bytes + bytes + (pos - len), id, idl, p.names + p.name_off[node], nl, cnt);
-                bytes += __shfl_sync(kFull, pos, 31);
-            }
-            kept += __popc(kb);
+                out = put_line(out, id, idl, p.names + p.name_off[node], p.name_off[node + 1] - p.name_off[node], cnt);
         }
-        if (lane == 0)
+        if (kept > 0)
         {
-            if (kept > 0)
+            const uint2 one = p.one[r];
+            atomicAdd(&p.rep[(uint64_t)one.x * 5 + (kept == 1 ? 2 : 1)], 1ull);
+            if (!p.skip_lca && p.output_lca)
+                put_line(p.one_text + o.one_bytes, id, idl, p.names + p.name_off[one.x], p.name_off[one.x + 1] - p.name_off[one.x], one.y);
+            p.active[r]     = 0;
+            p.read_level[r] = (uint8_t)p.level;
+        }
+        else
+        {
+            p.active[r] = 1;
+            if (p.last && p.output_unc)
             {
-                const uint2 one = p.one[r];
-                atomicAdd(&p.rep[(uint64_t)one.x * 5 + (kept == 1 ? 2 : 1)], 1ull);
-                if (!p.skip_lca && p.output_lca)
-                    put_line(p.one_text + o.one_bytes, id, idl, p.names + p.name_off[one.x], p.name_off[one.x + 1] - p.name_off[one.x], one.y);
-                p.active[r]     = 0;
-                p.read_level[r] = (uint8_t)p.level;
-            }
-            else
-            {
-                p.active[r] = 1;
-                if (p.last && p.output_unc)
-                {
-                    char *u = p.unc_text + o.unc_bytes;
-                    for (uint32_t i = 0; i < idl; ++i)
-                        u[i] = (char)id[i];
-                    u[idl] = '\n';
-                }
+                char *u = p.unc_text + o.unc_bytes;
+                for (uint32_t i = 0; i < idl; ++i)
+                    u[i] = (char)id[i];
+                u[idl] = '\n';
             }
         }
     }
@@ -1552,8 +1523,8 @@ void launch_finish_select(const FinishParams &p, cudaStream_t st)
     cudaMemsetAsync(p.totals, 0, kFinishTotals * 8, st);
     if (p.n_tuples)
         k_tuple_starts<<<(unsigned)((p.n_tuples + 255) / 256), 256, 0, st>>>(p.tuples, p.n_tuples, p.tuple_start);
-    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.n_reads + K4_WARPS - 1) / K4_WARPS, 148u * 8);
-    k_finish_select<<<std::max(1u, blocks), K4_WARPS * 32, 0, st>>>(p);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.n_reads + K4_THREADS - 1) / K4_THREADS, 148u * 8);
+    k_finish_select<<<std::max(1u, blocks), K4_THREADS, 0, st>>>(p);
 }
 
 size_t finish_scan_tmp_bytes(uint32_t n_reads)
@@ -1570,8 +1541,8 @@ void launch_finish_scan(const FinishParams &p, void *tmp, size_t tmp_bytes, cuda
 
 void launch_finish_write(const FinishParams &p, cudaStream_t st)
 {
-    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.n_reads + K4_WARPS - 1) / K4_WARPS, 148u * 8);
-    k_finish_write<<<std::max(1u, blocks), K4_WARPS * 32, 0, st>>>(p);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.n_reads + K4_THREADS - 1) / K4_THREADS, 148u * 8);
+    k_finish_write<<<std::max(1u, blocks), K4_THREADS, 0, st>>>(p);
 }
 
 // =====================================================================================================================
