@@ -33,6 +33,8 @@ WORKLOADS = {
     "c2": dict(bins=4096, bin_size=1 << 24, h=4, k=19, w=31, paired=False, reads_per_step=1 << 21, genome_len=10000, desc="8 GiB flat IBF, 4096 bins, k=19 w=31 h=4, 150 bp single-end"),
     # BASELINE.json configs[2]: 64 GiB flat IBF, 65536 bins, paired
     "c3": dict(bins=65536, bin_size=1 << 23, h=4, k=19, w=31, paired=True, reads_per_step=1 << 18, genome_len=4000, desc="64 GiB flat IBF, 65536 bins, k=19 w=31 h=4, 150 bp paired"),
+    # BASELINE.json configs[4]: 256 GiB flat IBF, 65536 bins, bin-sharded over the GPUs (--shard-db; 32 GiB per GPU at N=8)
+    "c5": dict(bins=65536, bin_size=1 << 25, h=4, k=19, w=31, paired=True, reads_per_step=1 << 18, genome_len=4000, desc="256 GiB flat IBF, 65536 bins, k=19 w=31 h=4, 150 bp paired"),
     # small stand-in used by the tests of this file
     "tiny": dict(bins=256, bin_size=1 << 16, h=4, k=19, w=31, paired=False, reads_per_step=1 << 14, genome_len=3000, desc="2 MiB flat IBF, 256 bins (bench self-test)"),
 }
@@ -103,12 +105,13 @@ def target_hashes_for_density(wl, density=0.5):
     return int(-np.log(1 - density) * wl["bin_size"] / wl["h"])
 
 
-def build_database(wl, device):
-    """Flat IBF in HBM: random background bits (density 0.5) OR planted genomes (one per bin)."""
+def build_database(wl, device, shard=0, n_shards=1):
+    """Flat IBF in HBM: random background bits (density 0.5) OR planted genomes (one per bin).  With n_shards > 1 only
+    the bin-word columns of `shard` are created (the same bits as that slice of the whole filter)."""
     from ganon_b200 import synth
     from ganon_b200.classify import Database, minimisers_batch
 
-    db = Database.create(wl["bins"], wl["bin_size"], wl["h"], wl["k"], wl["w"], device=device)
+    db = Database.create(wl["bins"], wl["bin_size"], wl["h"], wl["k"], wl["w"], device=device, shard=shard, n_shards=n_shards)
     db.fill_random(DB_SEED, 1)
     genomes = synth.random_genomes(DB_SEED, wl["bins"], wl["genome_len"])
     step = 1024
@@ -194,6 +197,7 @@ def main():
     ap.add_argument("--reads-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=4, help="distinct read batches cycled through the steps")
+    ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (every rank classifies the same reads on its columns; tuples all-gathered over NCCL): strong scaling")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.reads_per_step:
@@ -222,6 +226,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from ganon_b200.classify import Session, result_text
 
+    if args.shard_db:
+        return sharded_arm(args, wl, rank, local_rank, world)
     dev = local_rank
     R = wl["reads_per_step"]
     t_setup = time.perf_counter()
@@ -374,6 +380,147 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity": parity,
+            "setup_s": t_setup,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def sharded_arm(args, wl, rank, local_rank, world):
+    """--shard-db: the filter is split by bin-word columns over the ranks; every rank stages the same
+    batch, runs K2 + K3 on its columns, the sparse tuples are all-gathered in HBM (NCCL) and sorted + finished (K4) on
+    every rank.  Total work is fixed as N grows ("strong")."""
+    import torch
+    import torch.distributed as dist
+
+    from ganon_b200.sharded import ShardedSession
+
+    dev = local_rank
+    R = wl["reads_per_step"]
+    units = 2 if wl["paired"] else 1
+    t_setup = time.perf_counter()
+    db, genomes = build_database(wl, dev, shard=rank, n_shards=world)
+    info = db.info()
+    pool = max(1, min(args.pool, args.steps + args.warmup))
+    blocks = [make_batch(wl, genomes, i, R) for i in range(pool)]  # the same reads on every rank
+    host = [(pinned(b1), pinned(b2) if b2 is not None else None) for b1, b2 in blocks]
+    stream = torch.cuda.Stream()
+    mk = lambda: ShardedSession([db], [REL_CUTOFF], [REL_FILTER], [FPR_QUERY], output_all=True, device=dev, cuda_stream=stream.cuda_stream)
+    sessions = [mk() for _ in range(pool)]
+    for s, (h1, h2) in zip(sessions, host):
+        assert s.stage(h1, h2, final=True) == R
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(max(args.warmup, pool)):
+            sessions[i % pool].run_levels(prefix_id=1)
+        sampler = ClockSampler(dev)
+        sampler.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        ms_count = ms_min = ms_sort = ms_fin = 0.0
+        k3_bytes = launches = minimisers = exchanged = 0
+        for i in range(args.steps):
+            s = sessions[(args.warmup + i) % pool]
+            s.run_levels(prefix_id=1)
+            r = s.staged_timings()
+            ms_count += r.ms_count
+            ms_min += r.ms_minimiser
+            ms_sort += r.ms_sort
+            ms_fin += r.ms_finish_device
+            k3_bytes += r.count_kernel_bytes
+            launches += r.n_kernel_launches
+            minimisers += r.n_minimisers
+            exchanged += s.last_exchanged_bytes
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([dev_ms, wall_ms, ms_count], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, ms_count_max = float(t[0]), float(t[1]), float(t[2])
+        barrier()
+
+        # e2e: host FASTQ blocks through ShardedSession.classify on every rank (H2D of the block, kernels, exchange,
+        # K4, result read back), synchronous per step
+        e2e = mk()
+        for i in range(3):
+            e2e.classify(host[i % pool][0], host[i % pool][1], final=True)
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = n_class = 0
+        for i in range(args.steps):
+            h1, h2 = host[(1 + i) % pool]
+            r = e2e.classify(h1, h2, final=True)
+            h2d += r.h2d_bytes
+            d2h += r.d2h_bytes
+            n_class += r.n_classified
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_sort=r.ms_sort, ms_finish_device=r.ms_finish_device, levels_on_device=r.levels_on_device)
+        if world > 1:
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t[0])
+    clocks = sampler.stop()
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (k3_bytes / 1e9) / (ms_count / 1e3) if ms_count > 0 else 0.0
+        line = {
+            "metric": METRIC,
+            "value": args.steps * R * units / (dev_ms / 1e3),
+            "unit": "reads/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "u64",
+            "data": "synthetic",
+            "config": {
+                "workload": args.workload + ": " + wl["desc"],
+                "reads_per_step": R * units,
+                "db_bytes_per_gpu": int(info.device_bytes),
+                "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY),
+                "parallelism": "bin-sharded x%d (bin-word columns %d..%d of %d on rank 0); every rank classifies the same reads, sparse tuples all-gathered in HBM over NCCL, K4 on every rank" % (world, info.shard_word_begin, info.shard_word_end, info.bin_words),
+                "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, filter shard gathered at random" % (pool, blocks[0][0].size * units >> 20),
+                "timing": "CUDA events on the launch stream around the K steps (max over ranks); wall %.1f ms" % wall_ms,
+                "minimisers_per_read": minimisers / max(1, args.steps * R * units),
+                "exchanged_tuple_bytes_per_step": exchanged // max(1, args.steps),
+            },
+            "roofline": {
+                "kernel": "k_ibf_count",
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "peak_source": peak_src,
+                "traffic": None,
+                "algorithmic_bytes_per_launch": k3_bytes / max(1, args.steps),
+                "ms_per_launch": ms_count / max(1, args.steps),
+                "ms_per_launch_max_over_ranks": ms_count_max / max(1, args.steps),
+                "note": "per GPU (rank 0): its shard's share of every row",
+                "other_kernels_ms_per_step": {"k_minimisers(x2)+scan": ms_min / args.steps, "radix_sort": ms_sort / args.steps, "k_finish(select+scan+write)": ms_fin / args.steps},
+            },
+            "cpu_baseline": None,
+            "e2e": {"value": args.steps * R * units / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "last_step_breakdown_ms": last, "classified_reads_per_step": n_class // args.steps, "note": "per rank: every rank copies the same block"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity": None,
             "setup_s": t_setup,
         }
         print(json.dumps(line))

@@ -144,6 +144,11 @@ SYMBOLS = {
     "gnb_session_set_level_tuples": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
     "gnb_session_finish_level": (C.c_int, [_P, C.c_uint32]),
     "gnb_session_collect_staged": (C.c_int, [_P, C.c_uint32, C.POINTER(BatchResult)]),
+    "gnb_session_run_level_device": (C.c_int, [_P, C.c_uint32]),
+    "gnb_session_level_tuples_device": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "gnb_session_set_level_tuples_device": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64]),
+    "gnb_session_finish_level_device": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "gnb_session_staged_timings": (C.c_int, [_P, C.POINTER(BatchResult)]),
     "gnb_host_register": (C.c_int, [_P, C.c_uint64]),
     "gnb_host_unregister": (C.c_int, [_P]),
     "gnb_session_level_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),

@@ -301,6 +301,27 @@ class Session:
     def finish_level(self, level: int) -> None:
         check(_lib.lib().gnb_session_finish_level(self._h, level))
 
+    # device form of the level-wise API (tuples stay in HBM; see ganon_b200/sharded.py)
+    def run_level_device(self, level: int) -> None:
+        check(_lib.lib().gnb_session_run_level_device(self._h, level))
+
+    def level_tuples_device(self, level: int) -> Tuple[int, int]:
+        """(device pointer, count) of the level's sorted tuples."""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().gnb_session_level_tuples_device(self._h, level, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def set_level_tuples_device(self, level: int, dev_ptr: int, n: int) -> None:
+        check(_lib.lib().gnb_session_set_level_tuples_device(self._h, level, C.c_void_p(dev_ptr), n))
+
+    def finish_level_device(self, level: int, prefix_id: int = 0) -> None:
+        check(_lib.lib().gnb_session_finish_level_device(self._h, level, prefix_id))
+
+    def staged_timings(self) -> BatchResult:
+        res = BatchResult()
+        check(_lib.lib().gnb_session_staged_timings(self._h, C.byref(res)))
+        return res
+
     def collect_staged(self, prefix_id: int = 0) -> BatchResult:
         res = BatchResult()
         check(_lib.lib().gnb_session_collect_staged(self._h, prefix_id, C.byref(res)))

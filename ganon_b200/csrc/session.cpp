@@ -2593,9 +2593,106 @@ extern "C" int gnb_session_finish_level(gnb_session *s, uint32_t level)
         return fail(GNB_ERR_ARG, "gnb_session_finish_level: nothing staged or bad level");
     BatchCtx &c = *s->slots[0];
     auto      th = Clock::now();
-    GNB_TRY(c.fetch_host_records());
+    GNB_TRY(c.to_host_state(level)); // record table; active mask if an earlier level was finished by K4
     GNB_TRY(c.finish_level(level));
     c.timing.ms_host_finish += ms_since(th);
+    return GNB_OK;
+}
+
+// Device form of the level-wise API: the tuples of a single-filter level stay in HBM, the ranks exchange them with a
+// device collective (NCCL all-gather) and K4 finishes the level on every rank.
+extern "C" int gnb_session_run_level_device(gnb_session *s, uint32_t level)
+{
+    if (!s || !s->slots[0]->staged || level >= s->levels.size())
+        return fail(GNB_ERR_ARG, "gnb_session_run_level_device: nothing staged or bad level");
+    BatchCtx &c = *s->slots[0];
+    GNB_CUDA(cudaSetDevice(c.device));
+    if (level == 0)
+    { // a staged batch may be run again (benchmark): start from the staged state
+        c.begin_finish();
+        c.hashed_k = c.hashed_w = 0;
+        c.timing.ms_count = c.timing.ms_sort = 0;
+        c.timing.count_kernel_bytes = 0;
+        c.launches         = 0;
+        c.active_on_device = false;
+        std::fill(c.h_active.begin(), c.h_active.end(), (uint8_t)1);
+    }
+    c.keep_on_device = true;
+    GNB_TRY(c.run_level(level));
+    if (!c.tuples_on_device)
+        return fail(GNB_ERR_ARG, "gnb_session_run_level_device: the level has several filters (use gnb_session_run_level)");
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_level_tuples_device(gnb_session *s, uint32_t level, const uint64_t **dev_tuples, uint64_t *n)
+{
+    if (!s || !dev_tuples || !n || level >= s->levels.size() || !s->slots[0]->tuples_on_device)
+        return fail(GNB_ERR_ARG, "gnb_session_level_tuples_device: bad arguments or no tuples in device memory");
+    BatchCtx &c = *s->slots[0];
+    *dev_tuples = c.n_tuples_dev ? c.d_tuples_b.as<uint64_t>() : nullptr;
+    *n          = c.n_tuples_dev;
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_set_level_tuples_device(gnb_session *s, uint32_t level, const uint64_t *dev_tuples, uint64_t n)
+{
+    if (!s || (n && !dev_tuples) || level >= s->levels.size() || !s->slots[0]->staged)
+        return fail(GNB_ERR_ARG, "gnb_session_set_level_tuples_device: bad arguments");
+    BatchCtx &c = *s->slots[0];
+    GNB_CUDA(cudaSetDevice(c.device));
+    if (n)
+    {
+        GNB_TRY(c.d_tuples_a.ensure(n * 8));
+        GNB_TRY(c.d_tuples_b.ensure(n * 8));
+        GNB_TRY(c.d_tmp.ensure(sort_tmp_bytes(n)));
+        GNB_CUDA(cudaMemcpyAsync(c.d_tuples_a.p, dev_tuples, n * 8, cudaMemcpyDeviceToDevice, c.st));
+        launch_sort_tuples(c.d_tuples_a.as<uint64_t>(), c.d_tuples_b.as<uint64_t>(), n, c.d_tmp.p, c.d_tmp.cap, c.st);
+        c.launches += 4;
+        GNB_CUDA(cudaStreamSynchronize(c.st));
+        GNB_CUDA(cudaGetLastError());
+    }
+    c.n_tuples_dev     = n;
+    c.tuples_on_device = true;
+    return GNB_OK;
+}
+
+// K4 on the (exchanged) tuples of the level; the host finishing stage takes over if K4 declines (see finish_level_device)
+extern "C" int gnb_session_finish_level_device(gnb_session *s, uint32_t level, uint32_t prefix_id)
+{
+    if (!s || !s->slots[0]->staged || level >= s->levels.size())
+        return fail(GNB_ERR_ARG, "gnb_session_finish_level_device: nothing staged or bad level");
+    BatchCtx &c = *s->slots[0];
+    GNB_CUDA(cudaSetDevice(c.device));
+    auto th   = Clock::now();
+    bool done = false;
+    if (s->levels[level].device_finish && c.tuples_on_device)
+    {
+        unsigned long long *rep = nullptr;
+        GNB_TRY(s->device_rep(level, prefix_id, &rep));
+        GNB_TRY(c.finish_level_device(level, rep, true, done));
+    }
+    if (!done)
+    {
+        GNB_TRY(c.to_host_state(level));
+        GNB_TRY(c.finish_level(level));
+    }
+    c.timing.ms_host_finish += ms_since(th);
+    if (level + 1 == s->levels.size() && c.active_on_device && c.n_reads)
+    {
+        GNB_CUDA(cudaMemcpyAsync(c.h_read_level.data(), c.d_read_level.p, c.n_reads, cudaMemcpyDeviceToHost, c.st));
+        GNB_CUDA(cudaStreamSynchronize(c.st));
+    }
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_staged_timings(gnb_session *s, gnb_batch_result *timings)
+{
+    if (!s || !timings || !s->slots[0]->staged)
+        return fail(GNB_ERR_ARG, "gnb_session_staged_timings: nothing staged");
+    BatchCtx &c = *s->slots[0];
+    c.fill_timings(timings);
+    timings->ms_finish_device = c.ms_finish_dev;
+    timings->levels_on_device = c.levels_on_device;
     return GNB_OK;
 }
 

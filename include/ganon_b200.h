@@ -207,6 +207,18 @@ int gnb_session_level_tuples(gnb_session *s, uint32_t level, uint32_t filter, co
 int gnb_session_set_level_tuples(gnb_session *s, uint32_t level, uint32_t filter, const uint64_t *tuples, uint64_t n);
 int gnb_session_finish_level(gnb_session *s, uint32_t level);
 int gnb_session_collect_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_result *out);
+/* The same exchange without leaving HBM (levels with one filter): run_level_device keeps the sorted tuples on the
+ * device, level_tuples_device exposes them (device pointer, valid until the next call on the session),
+ * set_level_tuples_device takes the concatenation of all ranks' tuples from device memory (any order; the work that
+ * produced it must be complete, e.g. the NCCL all-gather synchronised) and sorts it, finish_level_device runs K4 on it
+ * (rel-filter, fpr-query, LCA, accounting under prefix_id, output text) or, if K4 declines the level, the host
+ * finishing stage.  collect_staged then returns the batch result as usual. */
+int gnb_session_run_level_device(gnb_session *s, uint32_t level);
+int gnb_session_level_tuples_device(gnb_session *s, uint32_t level, const uint64_t **dev_tuples, uint64_t *n);
+int gnb_session_set_level_tuples_device(gnb_session *s, uint32_t level, const uint64_t *dev_tuples, uint64_t n);
+int gnb_session_finish_level_device(gnb_session *s, uint32_t level, uint32_t prefix_id);
+/* device timings / byte counts of the staged batch so far (level-wise forms; the batch stays staged) */
+int gnb_session_staged_timings(gnb_session *s, gnb_batch_result *timings);
 
 /* Page-lock / unlock a host buffer that will be passed as a read block (cudaHostRegister): faster, truly asynchronous
  * host->device copies. */

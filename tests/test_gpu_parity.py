@@ -403,6 +403,36 @@ def test_column_shards_on_one_gpu_equal_the_whole(golden_dbs):
         assert got == want
 
 
+def test_column_shards_device_exchange_equals_the_whole(golden_dbs):
+    """The same three shards with the exchange inside HBM: device tuples concatenated with torch (what the NCCL
+    all-gather yields), sorted by the library, finished by K4 on every shard session."""
+    import torch
+
+    from ganon_b200.sharded import _DeviceWords
+
+    fq = open(os.path.join(SU.GOLDEN, "reads.se.fq"), "rb").read()
+    whole = Session([Database.open(golden_dbs["synth"])], [0.1], [0.5], [1e-3], output_all=True, output_unclassified=True)
+    r = whole.classify(fq, final=True)
+    want = (sorted(result_text(r, "all").decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), whole.report())
+    n_shards = 3
+    sessions = [Session([Database.open(golden_dbs["synth"], shard=i, n_shards=n_shards)], [0.1], [0.5], [1e-3], output_all=True, output_unclassified=True) for i in range(n_shards)]
+    parts = []
+    for s in sessions:
+        assert s.stage(fq, final=True) == r.n_reads
+        s.run_level_device(0)
+        ptr, n = s.level_tuples_device(0)
+        parts.append(torch.as_tensor(_DeviceWords(ptr, n), device="cuda").clone() if n else torch.empty(0, dtype=torch.int64, device="cuda"))
+    merged = torch.cat(parts)
+    torch.cuda.synchronize()
+    for s in sessions:
+        s.set_level_tuples_device(0, merged.data_ptr(), merged.numel())
+        s.finish_level_device(0)
+        res = s.collect_staged()
+        assert res.levels_on_device == 1
+        got = (sorted(result_text(res, "all").decode().splitlines()), sorted(result_text(res, "unc").decode().splitlines()), s.report())
+        assert got == want
+
+
 def test_sharded_create_fill_emplace_equals_slice():
     full = Database.create(1000, 997, 4, 19, 31)
     full.fill_random(3, 2)
