@@ -33,6 +33,13 @@ WORKLOADS = {
     "c2": dict(bins=4096, bin_size=1 << 24, h=4, k=19, w=31, paired=False, reads_per_step=1 << 21, genome_len=10000, desc="8 GiB flat IBF, 4096 bins, k=19 w=31 h=4, 150 bp single-end"),
     # BASELINE.json configs[2]: 64 GiB flat IBF, 65536 bins, paired
     "c3": dict(bins=65536, bin_size=1 << 23, h=4, k=19, w=31, paired=True, reads_per_step=1 << 18, genome_len=4000, desc="64 GiB flat IBF, 65536 bins, k=19 w=31 h=4, 150 bp paired"),
+    # BASELINE.json configs[3]: 3-level HIBF, top 1024 bins (256 merged) -> 256 children of 64 bins (4 merged each) -> 1024
+    # grandchildren of 64 bins; 16 + 16 + 8 = 40 GiB; 81 376 user bins, some split over two technical bins
+    "c4": dict(hibf=True, top_bins=1024, top_rows=1 << 27, child_bins=64, child_rows=1 << 23, child_merged=4, grand_bins=64, grand_rows=1 << 20, h=4, k=19, w=31,
+               paired=False, reads_per_step=1 << 21, genome_len=3000, desc="3-level HIBF, 1024-bin top level, 40 GiB, k=19 w=31 h=4, 150 bp single-end"),
+    # the same shape at 1/64 of the rows (self-test of the generator)
+    "c4tiny": dict(hibf=True, top_bins=1024, top_rows=1 << 21, child_bins=64, child_rows=1 << 17, child_merged=4, grand_bins=64, grand_rows=1 << 14, h=4, k=19, w=31,
+                   paired=False, reads_per_step=1 << 16, genome_len=3000, desc="3-level HIBF, 1024-bin top level, 640 MiB (bench self-test)"),
     # BASELINE.json configs[4]: 256 GiB flat IBF, 65536 bins, bin-sharded over the GPUs (--shard-db; 32 GiB per GPU at N=8)
     "c5": dict(bins=65536, bin_size=1 << 25, h=4, k=19, w=31, paired=True, reads_per_step=1 << 18, genome_len=4000, desc="256 GiB flat IBF, 65536 bins, k=19 w=31 h=4, 150 bp paired"),
     # small stand-in used by the tests of this file
@@ -105,12 +112,86 @@ def target_hashes_for_density(wl, density=0.5):
     return int(-np.log(1 - density) * wl["bin_size"] / wl["h"])
 
 
+def hibf_layout(wl):
+    """Synthetic 3-level HIBF in the raptor layout: per sub-IBF its technical bins, next_ibf_id and
+    ibf_bin_to_filename_position rows; returns also, per user bin, the chain [(ibf, [bins])] from its own IBF up to the
+    top level (the user bin's content is inserted along the whole chain, as raptor's merged bins hold their subtree)."""
+    bins, rows, nxt, pos = [], [], [], []
+    chains = []  # per user bin
+
+    def new_ibf(n_bins, n_rows):
+        bins.append(n_bins)
+        rows.append(n_rows)
+        nxt.append([len(bins) - 1] * n_bins)
+        pos.append([0] * n_bins)
+        return len(bins) - 1
+
+    def user_bin(ibf, bs, up):
+        u = len(chains)
+        for b in bs:
+            pos[ibf][b] = u
+        chains.append([(ibf, bs)] + up)
+
+    top = new_ibf(wl["top_bins"], wl["top_rows"])
+    b = 0
+    while b < wl["top_bins"]:
+        if b % 4 == 0:  # merged bin -> child IBF
+            c = new_ibf(wl["child_bins"], wl["child_rows"])
+            nxt[top][b], pos[top][b] = c, -1
+            up_c = [(top, [b])]
+            for cb in range(wl["child_merged"]):
+                g = new_ibf(wl["grand_bins"], wl["grand_rows"])
+                nxt[c][cb], pos[c][cb] = g, -1
+                for gb in range(wl["grand_bins"]):
+                    user_bin(g, [gb], [(c, [cb])] + up_c)
+            cb = wl["child_merged"]
+            user_bin(c, [cb, cb + 1], up_c)  # a user bin split over two technical bins
+            for cb in range(wl["child_merged"] + 2, wl["child_bins"]):
+                user_bin(c, [cb], up_c)
+            b += 1
+        elif b % 4 == 1 and (b // 4) % 8 == 0:
+            user_bin(top, [b, b + 1], [])  # split
+            b += 2
+        else:
+            user_bin(top, [b], [])
+            b += 1
+    return bins, rows, nxt, pos, chains
+
+
+def build_database_hibf(wl, device):
+    from ganon_b200 import synth
+    from ganon_b200.classify import Database, minimisers_batch
+
+    bins, rows, nxt, pos, chains = hibf_layout(wl)
+    names = ["U%d" % u for u in range(len(chains))]
+    db = Database.create_hibf(bins, rows, wl["h"], wl["k"], wl["w"], nxt, pos, names, fpr=0.05, device=device)
+    db.fill_random(DB_SEED, 1)
+    genomes = synth.random_genomes(DB_SEED, len(chains), wl["genome_len"])
+    per_ibf = {}  # ibf -> ([hashes], [bins])
+    step = 2048
+    for g0 in range(0, len(chains), step):
+        gs = [genomes[i].tobytes() for i in range(g0, min(g0 + step, len(chains)))]
+        hoff, hashes = minimisers_batch(gs, wl["k"], wl["w"], device=device)
+        for j in range(len(gs)):
+            hs = hashes[int(hoff[j]) : int(hoff[j + 1])]
+            for ibf, bs in chains[g0 + j]:
+                hl, bl = per_ibf.setdefault(ibf, ([], []))
+                hl.append(hs)
+                bl.append(np.asarray(bs, dtype=np.uint32)[np.arange(hs.size) % len(bs)])  # split bins share the content
+    for ibf, (hl, bl) in per_ibf.items():
+        db.emplace(np.concatenate(hl), np.concatenate(bl), ibf_index=ibf)
+    return db, genomes
+
+
 def build_database(wl, device, shard=0, n_shards=1):
     """Flat IBF in HBM: random background bits (density 0.5) OR planted genomes (one per bin).  With n_shards > 1 only
     the bin-word columns of `shard` are created (the same bits as that slice of the whole filter)."""
     from ganon_b200 import synth
     from ganon_b200.classify import Database, minimisers_batch
 
+    if wl.get("hibf"):
+        assert n_shards == 1, "bin-block sharding is implemented for flat IBFs"
+        return build_database_hibf(wl, device)
     db = Database.create(wl["bins"], wl["bin_size"], wl["h"], wl["k"], wl["w"], device=device, shard=shard, n_shards=n_shards)
     db.fill_random(DB_SEED, 1)
     genomes = synth.random_genomes(DB_SEED, wl["bins"], wl["genome_len"])
@@ -145,9 +226,9 @@ def pinned(arr):
 # ----------------------------------------------------------------------------------------------------------------------
 # reference CPU arm: the unmodified ganon-classify (oracle/_ref) on a bounded sample, all host threads
 # ----------------------------------------------------------------------------------------------------------------------
-def run_reference_binary(ibf_path, fq1, fq2, out_prefix, threads):
+def run_reference_binary(ibf_path, fq1, fq2, out_prefix, threads, hibf=False):
     reads = ["-p", fq1 + "," + fq2] if fq2 else ["-r", fq1]
-    cmd = [REF_BIN] + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", out_prefix, "-t", str(threads), "--verbose"]
+    cmd = [REF_BIN] + (["--hibf"] if hibf else []) + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", out_prefix, "-t", str(threads), "--verbose"]
     t0 = time.perf_counter()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     wall = time.perf_counter() - t0
@@ -164,9 +245,9 @@ def reference_threads():
 
 def ensure_ibf_file(wl_name, db):
     os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, "%s_seed%d.ibf" % (wl_name, DB_SEED))
     i = db.info()
-    want = i.bin_size_bits * i.bin_words * 8
+    path = os.path.join(CACHE, "%s_seed%d.%s" % (wl_name, DB_SEED, "hibf" if i.is_hibf else "ibf"))
+    want = i.device_bytes if i.is_hibf else i.bin_size_bits * i.bin_words * 8
     if not (os.path.exists(path) and os.path.getsize(path) > want):
         free = shutil.disk_usage(CACHE).free
         if free < want * 1.1:
@@ -358,12 +439,12 @@ def main():
                 "db_bytes": int(info.device_bytes),
                 "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY),
                 "parallelism": "replicated db, reads sharded x%d" % world if world > 1 else "1 gpu",
-                "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, 8+ GiB filter gathered at random" % (pool, blocks[0][0].size * (2 if wl["paired"] else 1) >> 20),
+                "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, %d GiB filter gathered at random" % (pool, blocks[0][0].size * (2 if wl["paired"] else 1) >> 20, int(info.device_bytes) >> 30),
                 "timing": "CUDA events on the launch stream around the K steps (max over ranks); wall %.1f ms" % wall_ms,
                 "minimisers_per_read": minimisers / max(1, args.steps * R * units),
             },
             "roofline": {
-                "kernel": "k_ibf_count",
+                "kernel": "k_hibf_count" if wl.get("hibf") else "k_ibf_count",
                 "bound": "hbm",
                 "achieved": achieved,
                 "peak": peak,
@@ -547,7 +628,7 @@ def cpu_baseline(args, wl, db, block, host_block, sess, result_text):
     p1, p2 = write_sample(args.workload, s1, s2, n, "sample")
     out = os.path.join(CACHE, "ref_out")
     threads = reference_threads()
-    t = run_reference_binary(ibf, p1, p2, out, threads)
+    t = run_reference_binary(ibf, p1, p2, out, threads, hibf=bool(wl.get("hibf")))
     units = 2 if wl["paired"] else 1
     cpu = {"value": n * units / t["classify_s"], "unit": "reads/s", "cores": threads, "kind": "reference", "sample": "%d reads of batch 0; reference's own classifying+printing time %.2f s (filter load %.1f s excluded)" % (n * units, t["classify_s"], t["load_s"])}
     # parity: the same reads through the C ABI
@@ -579,7 +660,7 @@ def reference_arm(args, wl):
     for i in range(args.warmup + args.steps):
         b1, b2 = make_batch(wl, genomes, i % 2, n)
         p1, p2 = write_sample(args.workload, b1, b2, n, "ref%d" % (i % 2))
-        t = run_reference_binary(ibf, p1, p2, os.path.join(CACHE, "ref_arm_out"), threads)
+        t = run_reference_binary(ibf, p1, p2, os.path.join(CACHE, "ref_arm_out"), threads, hibf=bool(wl.get("hibf")))
         if i >= args.warmup:
             times.append(t["classify_s"])
     total = sum(times)

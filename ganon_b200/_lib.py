@@ -127,6 +127,8 @@ SYMBOLS = {
     "gnb_db_set_targets": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), _P, _P, C.c_uint64]),
     "gnb_db_read_words": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "gnb_db_save": (C.c_int, [_P, C.c_char_p]),
+    "gnb_db_create_hibf": (C.c_int, [C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64, C.POINTER(C.c_char_p), C.c_double, C.c_int, C.POINTER(_P)]),
+    "gnb_db_emplace_ibf": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64]),
     "gnb_minimisers": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "gnb_minimisers_batch": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64, _P, _P, C.c_uint64]),
     "gnb_db_bulk_count": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64, _P]),

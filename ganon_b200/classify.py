@@ -50,6 +50,22 @@ class Database:
         check(_lib.lib().gnb_db_create_sharded(bins, bin_size_bits, hash_functions, kmer_size, window_size, device, shard, n_shards, C.byref(h)))
         return cls(h.value)
 
+    @classmethod
+    def create_hibf(cls, bins: Sequence[int], bin_size_bits: Sequence[int], hash_functions: int, kmer_size: int, window_size: int, next_ibf: Sequence[Sequence[int]],
+                    bin_to_user: Sequence[Sequence[int]], user_bin_names: Sequence[str], fpr: float = 0.05, device: int = 0) -> "Database":
+        """An HIBF in HBM: per sub-IBF the technical bins, rows, next_ibf_id and ibf_bin_to_filename_position rows (raptor layout)."""
+        import numpy as np
+
+        b = np.ascontiguousarray(bins, dtype=np.uint64)
+        s = np.ascontiguousarray(bin_size_bits, dtype=np.uint64)
+        nx = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.int64) for v in next_ibf]), dtype=np.int64)
+        bu = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.int64) for v in bin_to_user]), dtype=np.int64)
+        assert nx.size == bu.size == int(b.sum())
+        names = (C.c_char_p * len(user_bin_names))(*[n.encode() for n in user_bin_names])
+        h = C.c_void_p()
+        check(_lib.lib().gnb_db_create_hibf(b.size, b.ctypes.data, s.ctypes.data, hash_functions, kmer_size, window_size, nx.ctypes.data, bu.ctypes.data, len(user_bin_names), names, fpr, device, C.byref(h)))
+        return cls(h.value)
+
     @property
     def handle(self) -> C.c_void_p:
         return self._h
@@ -70,13 +86,13 @@ class Database:
     def fill_random(self, seed: int, and_terms: int = 1) -> None:
         check(_lib.lib().gnb_db_fill_random(self._h, seed, and_terms))
 
-    def emplace(self, hashes, bins) -> None:
+    def emplace(self, hashes, bins, ibf_index: int = 0) -> None:
         import numpy as np
 
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         bins = np.ascontiguousarray(bins, dtype=np.uint32)
         assert hashes.size == bins.size
-        check(_lib.lib().gnb_db_emplace(self._h, hashes.ctypes.data, bins.ctypes.data, hashes.size))
+        check(_lib.lib().gnb_db_emplace_ibf(self._h, ibf_index, hashes.ctypes.data, bins.ctypes.data, hashes.size))
 
     def set_targets(self, names: Sequence[str], bin_target, target_hashes, max_hashes_bin: int) -> None:
         import numpy as np

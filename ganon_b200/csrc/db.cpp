@@ -496,11 +496,14 @@ extern "C" int gnb_db_create_sharded(uint64_t bins, uint64_t bin_size_bits, uint
 
 extern "C" int gnb_db_fill_random(gnb_db *db, uint64_t seed, int and_terms)
 {
-    if (!db || db->is_hibf || and_terms < 0 || and_terms > 16)
+    if (!db || and_terms < 0 || and_terms > 16)
         return fail(GNB_ERR_ARG, "gnb_db_fill_random: bad arguments");
     GNB_CUDA(cudaSetDevice(db->device));
-    IbfHost &t = db->ibfs[0];
-    launch_fill_random(t.d_data, t.bin_size, (uint32_t)t.row_words(), (uint32_t)t.w0, (uint32_t)t.bin_words, t.bins, seed, and_terms, 0);
+    for (size_t i = 0; i < db->ibfs.size(); ++i)
+    { // sub-IBF i of an HIBF draws from seed + i
+        IbfHost &t = db->ibfs[i];
+        launch_fill_random(t.d_data, t.bin_size, (uint32_t)t.row_words(), (uint32_t)t.w0, (uint32_t)t.bin_words, t.bins, seed + i, and_terms, 0);
+    }
     GNB_CUDA(cudaGetLastError());
     GNB_CUDA(cudaDeviceSynchronize());
     return GNB_OK;
@@ -508,12 +511,19 @@ extern "C" int gnb_db_fill_random(gnb_db *db, uint64_t seed, int and_terms)
 
 extern "C" int gnb_db_emplace(gnb_db *db, const uint64_t *hashes, const uint32_t *bins, uint64_t n)
 {
-    if (!db || db->is_hibf || (n && (!hashes || !bins)))
+    if (!db || db->is_hibf)
+        return fail(GNB_ERR_ARG, "gnb_db_emplace: bad arguments");
+    return gnb_db_emplace_ibf(db, 0, hashes, bins, n);
+}
+
+extern "C" int gnb_db_emplace_ibf(gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint32_t *bins, uint64_t n)
+{
+    if (!db || ibf_index >= db->ibfs.size() || (n && (!hashes || !bins)))
         return fail(GNB_ERR_ARG, "gnb_db_emplace: bad arguments");
     if (n == 0)
         return GNB_OK;
     GNB_CUDA(cudaSetDevice(db->device));
-    IbfHost &t = db->ibfs[0];
+    IbfHost &t = db->ibfs[ibf_index];
     for (uint64_t i = 0; i < n; ++i)
         if (bins[i] >= t.bins)
             return fail(GNB_ERR_ARG, "gnb_db_emplace: bin out of range"); // IBF.hpp:274
@@ -563,10 +573,157 @@ extern "C" int gnb_db_read_words(const gnb_db *db, uint64_t ibf_index, uint64_t 
     return GNB_OK;
 }
 
+namespace
+{
+// seqan3 IBF serialize (IBF.hpp:561-571) + sdsl::bit_vector (int_vector.hpp:2029-2035), bitvector streamed from HBM
+bool write_ibf_body(FILE *fp, const gnb::IbfHost &t, std::vector<uint64_t> &buf)
+{
+    auto put = [&](const void *p, size_t n) { return fwrite(p, 1, n, fp) == n; };
+    bool ok  = put(&t.bins, 8) && put(&t.technical_bins, 8) && put(&t.bin_size, 8) && put(&t.hash_shift, 8) && put(&t.bin_words, 8) && put(&t.hash_funs, 8);
+    uint8_t  width  = 1;
+    float    growth = 1.5f;
+    uint64_t n_bits = t.technical_bins * t.bin_size;
+    ok &= put(&width, 1) && put(&growth, 4) && put(&n_bits, 8);
+    const uint64_t total = t.bin_size * t.bin_words;
+    const uint64_t step  = 8u << 20; // words
+    buf.resize(std::min(step, std::max<uint64_t>(total, 1)));
+    for (uint64_t o = 0; ok && o < total; o += step)
+    {
+        const uint64_t m = std::min(step, total - o);
+        if (cudaMemcpy(buf.data(), t.d_data + o, m * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return false;
+        ok &= put(buf.data(), m * 8);
+    }
+    return ok;
+}
+} // namespace
+
+// raptor 3.0.1 index layout as read by load_filter(THIBF) GC.cpp:875-938 (see gnb_db_open)
+static int save_hibf(const gnb_db *db, const char *path)
+{
+    FILE *fp = fopen(path, "wb");
+    if (!fp)
+        return fail(GNB_ERR_IO, std::string("cannot write ") + path);
+    auto put = [&](const void *p, size_t n) { return fwrite(p, 1, n, fp) == n; };
+    auto put_str = [&](const std::string &x) {
+        uint64_t l = x.size();
+        return put(&l, 8) && put(x.data(), l);
+    };
+    uint32_t version = 1;
+    uint64_t window = db->window_size, shape_size = db->kmer_size, shape_bits = db->kmer_size >= 64 ? ~0ull : ((1ull << db->kmer_size) - 1);
+    uint8_t  parts = 1, compressed = 0, is_hibf = 1;
+    bool     ok = put(&version, 4) && put(&window, 8) && put(&shape_size, 8) && put(&shape_bits, 8) && put(&parts, 1) && put(&compressed, 1);
+    // bin_path: one file per user bin, named after the target
+    std::vector<std::string> names(db->n_user_bins);
+    for (auto const &[u, name] : db->bin_map)
+        if (u < names.size() && names[u].empty())
+            names[u] = name;
+    uint64_t n = names.size();
+    ok &= put(&n, 8);
+    for (auto const &nm : names)
+    {
+        uint64_t one = 1;
+        ok &= put(&one, 8) && put_str("/db/" + nm + ".minimiser");
+    }
+    ok &= put(&db->max_fp, 8) && put(&is_hibf, 1);
+    n = db->ibfs.size();
+    ok &= put(&n, 8);
+    cudaSetDevice(db->device);
+    std::vector<uint64_t> buf;
+    for (size_t i = 0; ok && i < db->ibfs.size(); ++i)
+        ok &= write_ibf_body(fp, db->ibfs[i], buf);
+    auto put_vv = [&](const std::vector<std::vector<int64_t>> &vv) {
+        uint64_t m = vv.size();
+        bool     o = put(&m, 8);
+        for (auto const &v : vv)
+        {
+            uint64_t l = v.size();
+            o &= put(&l, 8) && (l == 0 || put(v.data(), l * 8));
+        }
+        return o;
+    };
+    ok &= put_vv(db->next_ibf_id);
+    n = names.size();
+    ok &= put(&n, 8);
+    for (auto const &nm : names)
+        ok &= put_str(nm);
+    ok &= put_vv(db->bin_to_user);
+    ok &= fclose(fp) == 0;
+    return ok ? GNB_OK : fail(GNB_ERR_IO, std::string("short write to ") + path);
+}
+
+extern "C" int gnb_db_create_hibf(uint64_t n_ibfs, const uint64_t *bins, const uint64_t *bin_size_bits, uint32_t hash_functions, uint32_t kmer_size,
+                                  uint32_t window_size, const int64_t *next_ibf, const int64_t *bin_to_user, uint64_t n_user_bins,
+                                  const char *const *user_bin_names, double fpr, int device, gnb_db **out)
+{
+    if (!out || n_ibfs == 0 || !bins || !bin_size_bits || !next_ibf || !bin_to_user || !user_bin_names || n_user_bins == 0 || hash_functions < 1 ||
+        hash_functions > 5 || kmer_size < 1 || kmer_size > 32 || window_size < kmer_size)
+        return fail(GNB_ERR_ARG, "gnb_db_create_hibf: bad arguments");
+    GNB_CUDA(cudaSetDevice(device));
+    std::unique_ptr<gnb_db> db(new gnb_db);
+    db->is_hibf     = true;
+    db->device      = device;
+    db->kmer_size   = kmer_size;
+    db->window_size = window_size;
+    db->max_fp      = fpr;
+    db->n_user_bins = n_user_bins;
+    db->ibfs.resize(n_ibfs);
+    db->next_ibf_id.resize(n_ibfs);
+    db->bin_to_user.resize(n_ibfs);
+    uint64_t off = 0;
+    int      rc  = GNB_OK;
+    for (uint64_t i = 0; i < n_ibfs && rc == GNB_OK; ++i)
+    {
+        IbfHost &t = db->ibfs[i];
+        if (bins[i] == 0 || bin_size_bits[i] == 0)
+        {
+            rc = fail(GNB_ERR_ARG, "gnb_db_create_hibf: empty sub-IBF");
+            break;
+        }
+        t.bins           = bins[i];
+        t.bin_words      = (bins[i] + 63) >> 6;
+        t.technical_bins = t.bin_words << 6;
+        t.bin_size       = bin_size_bits[i];
+        t.hash_shift     = (uint64_t)__builtin_clzll(bin_size_bits[i]);
+        t.hash_funs      = hash_functions;
+        t.w0             = 0;
+        t.w1             = t.bin_words;
+        db->next_ibf_id[i].assign(next_ibf + off, next_ibf + off + bins[i]);
+        db->bin_to_user[i].assign(bin_to_user + off, bin_to_user + off + bins[i]);
+        for (uint64_t b = 0; b < bins[i]; ++b)
+        {
+            const int64_t fi = bin_to_user[off + b], nx = next_ibf[off + b];
+            if (fi >= (int64_t)n_user_bins || (fi < 0 && (nx < 0 || nx >= (int64_t)n_ibfs)))
+                rc = fail(GNB_ERR_ARG, "gnb_db_create_hibf: table entry out of range");
+        }
+        off += bins[i];
+        if (rc == GNB_OK && cudaMalloc((void **)&t.d_data, t.device_bytes()) != cudaSuccess)
+            rc = fail(GNB_ERR_CUDA, "gnb_db_create_hibf: out of device memory");
+        if (rc == GNB_OK)
+            cudaMemsetAsync(t.d_data, 0, t.device_bytes(), 0);
+    }
+    if (rc == GNB_OK && cudaDeviceSynchronize() != cudaSuccess)
+        rc = fail(GNB_ERR_CUDA, "gnb_db_create_hibf: memset failed");
+    if (rc != GNB_OK)
+    {
+        std::string keep = g_err;
+        gnb_db_free(db.release());
+        g_err = keep;
+        return rc;
+    }
+    for (uint64_t u = 0; u < n_user_bins; ++u)
+        db->bin_map.emplace_back(u, user_bin_names[u] ? user_bin_names[u] : "");
+    db->derive_targets();
+    *out = db.release();
+    return GNB_OK;
+}
+
 extern "C" int gnb_db_save(const gnb_db *db, const char *path)
 {
-    if (!db || db->is_hibf || !path)
+    if (!db || !path)
         return fail(GNB_ERR_ARG, "gnb_db_save: bad arguments");
+    if (db->is_hibf)
+        return save_hibf(db, path);
     const IbfHost &t = db->ibfs[0];
     if (t.w0 != 0 || t.w1 != t.bin_words)
         return fail(GNB_ERR_ARG, "gnb_db_save: sharded handle");
@@ -598,25 +755,9 @@ extern "C" int gnb_db_save(const gnb_db *db, const char *path)
         uint64_t l = name.size();
         ok &= put(&b, 8) && put(&l, 8) && put(name.data(), l);
     }
-    ok &= put(&t.bins, 8) && put(&t.technical_bins, 8) && put(&t.bin_size, 8) && put(&t.hash_shift, 8) && put(&t.bin_words, 8) && put(&t.hash_funs, 8);
-    uint8_t  width = 1;
-    float    growth = 1.5f;
-    uint64_t n_bits = t.technical_bins * t.bin_size;
-    ok &= put(&width, 1) && put(&growth, 4) && put(&n_bits, 8);
     cudaSetDevice(db->device);
-    const uint64_t total = t.bin_size * t.bin_words;
-    const uint64_t step  = 8u << 20; // words
-    std::vector<uint64_t> buf(std::min(step, total));
-    for (uint64_t o = 0; ok && o < total; o += step)
-    {
-        const uint64_t m = std::min(step, total - o);
-        if (cudaMemcpy(buf.data(), t.d_data + o, m * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
-        {
-            fclose(fp);
-            return fail(GNB_ERR_CUDA, "gnb_db_save: device read failed");
-        }
-        ok &= put(buf.data(), m * 8);
-    }
+    std::vector<uint64_t> buf;
+    ok &= write_ibf_body(fp, t, buf);
     ok &= fclose(fp) == 0;
     return ok ? GNB_OK : fail(GNB_ERR_IO, std::string("short write to ") + path);
 }

@@ -131,7 +131,9 @@ void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint6
 // K3h: one traversal round of an HIBF (items = (read, sub-IBF) pairs); see kernels.cu
 void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *items, uint32_t n_items, const uint64_t *hashes, const uint64_t *hash_off,
                        const uint32_t *counts, uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
-                       unsigned long long *items_cursor, uint64_t items_cap, cudaStream_t st);
+                       unsigned long long *items_cursor, uint64_t items_cap, unsigned long long *bytes, uint32_t lanes_per_item, cudaStream_t st);
+// first worklist of the traversal, built on the device: (read, 0) for every active read with 1..65535 minimisers
+void launch_hibf_seed_items(const uint8_t *active, const uint32_t *counts, uint32_t n_reads, uint2 *items, unsigned long long *cursor, cudaStream_t st);
 constexpr uint32_t kMergedBinFlag = 0x80000000u;
 // sort tuples by (read, node)
 size_t sort_tmp_bytes(uint64_t n);

@@ -775,6 +775,7 @@ struct WorkOut
     uint2              *items; // MODE 2: (read, child ibf) for merged bins that reach the threshold
     unsigned long long *items_cursor;
     uint64_t            items_cap;
+    unsigned long long *bytes; // MODE 2: algorithmic bytes of the round (sum over items of n_hashes * h * row_words * 8)
 };
 
 // One (read, chunk) work item: gather + AND + bit-sliced count over the read's minimisers, then the epilogue.
@@ -1005,13 +1006,240 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
 {
     __shared__ uint64_t s_row[K3_WARPS][32];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned long long bytes = 0;
     for (uint32_t it = blockIdx.x * K3_WARPS + wib; it < n_items; it += gridDim.x * K3_WARPS)
     {
         const uint2  item = items[it];
         const IbfDev f    = table[item.y];
+        bytes += (unsigned long long)counts[item.x] * f.hash_funs * f.row_words * 8;
         for (uint32_t chunk = 0; chunk < f.n_chunks; ++chunk)
             count_item<H, NP, false, 2>(f, item.x, chunk, hashes, hash_off, counts, rel_cutoff, wo, s_row[wib], lane);
     }
+    if (lane == 0 && bytes && wo.bytes)
+        atomicAdd(wo.bytes, bytes);
+}
+
+// Sub-IBFs of an HIBF are narrow (raptor's t_max: 64 .. ~2048 technical bins = 1 .. 32 words per row), so a whole warp
+// per (read, ibf) item leaves most lanes idle and -- worse -- leaves one short dependent-load chain per warp.  Here an
+// item takes G lanes (lane `sub` owns words 2*sub, 2*sub+1 of the row, as in count_item) and a warp works on 32/G items
+// at once: every lane hashes its item's minimisers itself, gathers its 16 bytes of the h rows, ANDs and counts in its
+// own bit-sliced planes; no cross-lane traffic until the warp-aggregated append of the results.
+template <int H, int NP, int G>
+__global__ void __launch_bounds__(K3_WARPS * 32)
+    k_hibf_count_narrow(const IbfDev *__restrict__ table, const uint2 *__restrict__ items, uint32_t n_items, const uint64_t *__restrict__ hashes,
+                        const uint64_t *__restrict__ hash_off, const uint32_t *__restrict__ counts, double rel_cutoff, const WorkOut wo)
+{
+    constexpr uint32_t IPW  = 32 / G; // items per warp
+    const uint32_t     lane = threadIdx.x & 31, lt = (1u << lane) - 1, sub = lane % G;
+    const uint32_t     warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long bytes = 0;
+    for (uint32_t base = warp * IPW; base < n_items; base += n_warps * IPW)
+    {
+        const uint32_t it   = base + lane / G;
+        const bool     have = it < n_items;
+        const uint2    item = have ? items[it] : make_uint2(0, 0);
+        const IbfDev  *fp   = table + item.y;
+        const uint32_t row_words = fp->row_words, hash_shift = fp->hash_shift;
+        const uint64_t bin_size = fp->bin_size;
+        uint32_t       n  = 0;
+        uint64_t       h0 = 0;
+        if (have)
+        {
+            const uint32_t nn = counts[item.x];
+            if (nn > 0 && nn <= 65535)
+            {
+                n  = nn;
+                h0 = hash_off[item.x];
+            }
+        }
+        const uint32_t w0 = sub * 2;
+        const bool     v0 = n != 0 && w0 < row_words, v1 = n != 0 && (w0 + 1) < row_words;
+        const bool     al = (row_words & 1) == 0; // 16-byte loads stay aligned
+        const uint64_t *lane_base = fp->data + w0;
+        if (sub == 0)
+            bytes += (unsigned long long)n * H * row_words * 8;
+
+        uint32_t P[NP][4];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+            P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0;
+        if (v0)
+            for (uint32_t m = 0; m < n; m += 4)
+            {
+                uint4 rows[4][H];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    const bool     ok = (m + q) < n;
+                    const uint64_t x  = ok ? hashes[h0 + m + q] : 0;
+#pragma unroll
+                    for (int i = 0; i < H; ++i)
+                    {
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (ok)
+                        {
+                            const uint64_t *p = lane_base + ibf_row(x, ibf_seed(i), hash_shift, bin_size) * row_words;
+                            if (al)
+                                v = ldg_stream16(p);
+                            else
+                            {
+                                const uint2 a = ldg_stream8(p);
+                                v.x = a.x;
+                                v.y = a.y;
+                                if (v1)
+                                {
+                                    const uint2 b = ldg_stream8(p + 1);
+                                    v.z = b.x;
+                                    v.w = b.y;
+                                }
+                            }
+                        }
+                        rows[q][i] = v;
+                    }
+                }
+                uint32_t x4[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    uint4 a = rows[q][0];
+#pragma unroll
+                    for (int i = 1; i < H; ++i)
+                    {
+                        a.x &= rows[q][i].x;
+                        a.y &= rows[q][i].y;
+                        a.z &= rows[q][i].z;
+                        a.w &= rows[q][i].w;
+                    }
+                    x4[q][0] = a.x;
+                    x4[q][1] = a.y;
+                    x4[q][2] = a.z;
+                    x4[q][3] = a.w;
+                }
+                csa_add4<NP>(P, x4);
+            }
+
+        // ---- epilogue: bins reaching the threshold -> tuples (user bins) / items of the next round (merged bins) ----
+        const uint32_t T = threshold_cutoff(n, rel_cutoff);
+        uint32_t       cand[4];
+        uint32_t       nt = 0, ni = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+        {
+            const bool valid = (r < 2) ? v0 : v1;
+            cand[r] = valid ? (sliced_ge<NP>(P, r, T) & fp->single_mask[w0 * 2 + r]) : 0u;
+            uint32_t mm = cand[r];
+            while (mm)
+            {
+                const uint32_t b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (fp->bin_node[w0 * 64 + r * 32 + b] & kMergedBin)
+                    ++ni;
+                else
+                    ++nt;
+            }
+        }
+        uint32_t s0 = 0, s1 = 0;
+        if (v0 && fp->seg_off != nullptr)
+        {
+            s0 = fp->seg_off[sub];
+            s1 = fp->seg_off[sub + 1];
+            for (uint32_t sI = s0; sI < s1; ++sI)
+            {
+                const Seg sg = fp->segs[sI];
+                uint32_t  sum = sliced_sum<NP>(P, sg.reg, sg.mask);
+                if (sg.complete)
+                    sum = min(sum, n) < T ? 0 : min(sum, n);
+                nt += sum != 0;
+            }
+        }
+        if (!__any_sync(0xffffffffu, (nt | ni) != 0))
+            continue;
+        uint32_t it_incl = nt, ii_incl = ni;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, it_incl, d), b = __shfl_up_sync(0xffffffffu, ii_incl, d);
+            if (lane >= (uint32_t)d)
+            {
+                it_incl += a;
+                ii_incl += b;
+            }
+        }
+        const uint32_t     tot_t = __shfl_sync(0xffffffffu, it_incl, 31), tot_i = __shfl_sync(0xffffffffu, ii_incl, 31);
+        unsigned long long bt = 0, bi = 0;
+        if (lane == 0)
+        {
+            if (tot_t)
+                bt = atomicAdd(wo.cursor, (unsigned long long)tot_t);
+            if (tot_i)
+                bi = atomicAdd(wo.items_cursor, (unsigned long long)tot_i);
+        }
+        bt = __shfl_sync(0xffffffffu, bt, 0) + (it_incl - nt);
+        bi = __shfl_sync(0xffffffffu, bi, 0) + (ii_incl - ni);
+        (void)lt;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+        {
+            uint32_t mm = cand[r];
+            while (mm)
+            {
+                const uint32_t b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t node = fp->bin_node[w0 * 64 + r * 32 + b];
+                if (node & kMergedBin)
+                {
+                    if (bi < wo.items_cap)
+                        wo.items[bi] = make_uint2(item.x, node & ~kMergedBin);
+                    ++bi;
+                }
+                else
+                {
+                    if (bt < wo.cap)
+                        wo.tuples[bt] = make_tuple64(item.x, node, 0, sliced_get<NP>(P, r, b));
+                    ++bt;
+                }
+            }
+        }
+        for (uint32_t sI = s0; sI < s1; ++sI)
+        {
+            const Seg sg = fp->segs[sI];
+            uint32_t  sum = sliced_sum<NP>(P, sg.reg, sg.mask), partial = 1;
+            if (sg.complete)
+            {
+                sum     = min(sum, n) < T ? 0 : min(sum, n);
+                partial = 0;
+            }
+            if (sum != 0)
+            {
+                if (bt < wo.cap)
+                    wo.tuples[bt] = make_tuple64(item.x, sg.node, partial, sum);
+                ++bt;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+    if (lane == 0 && bytes && wo.bytes)
+        atomicAdd(wo.bytes, bytes);
+}
+
+// first round of the traversal: one item (read, top-level IBF) per active read with 1..65535 minimisers
+__global__ void k_hibf_seed_items(const uint8_t *__restrict__ active, const uint32_t *__restrict__ counts, uint32_t n_reads, uint2 *__restrict__ items,
+                                  unsigned long long *__restrict__ cursor)
+{
+    const uint32_t r    = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool     take = r < n_reads && (active == nullptr || active[r] != 0) && counts[r] > 0 && counts[r] <= 65535;
+    const uint32_t m    = __ballot_sync(0xffffffffu, take);
+    if (!m)
+        return;
+    unsigned long long base = 0;
+    if (lane == 0)
+        base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take)
+        items[base + __popc(m & ((1u << lane) - 1))] = make_uint2(r, 0);
 }
 
 template <int H, int NP, bool ALIGNED, int MODE>
@@ -1035,7 +1263,7 @@ void launch_k3(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off
     if (fine > full)
         full = fine;
     const uint32_t grid  = (uint32_t)(want < full ? want : full);
-    WorkOut wo{tuples, cursor, cap, dense, nullptr, nullptr, 0};
+    WorkOut wo{tuples, cursor, cap, dense, nullptr, nullptr, 0, nullptr};
     kern<<<grid, K3_WARPS * 32, 0, st>>>(f, hashes, hash_off, counts, active, n_reads, rel_cutoff, wo);
 }
 
@@ -1091,14 +1319,45 @@ void launch_ibf_count(const IbfDev &f, const uint64_t *hashes, const uint64_t *h
 
 void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *items, uint32_t n_items, const uint64_t *hashes, const uint64_t *hash_off,
                        const uint32_t *counts, uint32_t max_hashes, double rel_cutoff, uint64_t *tuples, unsigned long long *cursor, uint64_t cap, uint2 *items_out,
-                       unsigned long long *items_cursor, uint64_t items_cap, cudaStream_t st)
+                       unsigned long long *items_cursor, uint64_t items_cap, unsigned long long *bytes, uint32_t lanes_per_item, cudaStream_t st)
 {
     if (n_items == 0)
         return;
-    WorkOut        wo{tuples, cursor, cap, nullptr, items_out, items_cursor, items_cap};
+    WorkOut        wo{tuples, cursor, cap, nullptr, items_out, items_cursor, items_cap, bytes};
+    const bool     small = max_hashes < 256;
+    if (lanes_per_item >= 1 && lanes_per_item <= 16)
+    { // narrow sub-IBFs: G lanes per item
+        const uint64_t threads = (uint64_t)n_items * lanes_per_item;
+        const uint32_t want_n  = (uint32_t)((threads + K3_WARPS * 32 - 1) / (K3_WARPS * 32));
+        const uint32_t grid_n  = want_n < 148u * 8u ? want_n : 148u * 8u;
+#define GNB_NARROW(HV, GV)                                                                                                                                        \
+    if (small)                                                                                                                                                    \
+        k_hibf_count_narrow<HV, 8, GV><<<grid_n, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, counts, rel_cutoff, wo);                    \
+    else                                                                                                                                                          \
+        k_hibf_count_narrow<HV, 16, GV><<<grid_n, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, counts, rel_cutoff, wo);
+#define GNB_NARROW_G(HV)                  \
+    switch (lanes_per_item)               \
+    {                                     \
+    case 1: GNB_NARROW(HV, 1) break;      \
+    case 2: GNB_NARROW(HV, 2) break;      \
+    case 4: GNB_NARROW(HV, 4) break;      \
+    case 8: GNB_NARROW(HV, 8) break;      \
+    default: GNB_NARROW(HV, 16) break;    \
+    }
+        switch (hash_funs)
+        {
+        case 1: GNB_NARROW_G(1) break;
+        case 2: GNB_NARROW_G(2) break;
+        case 3: GNB_NARROW_G(3) break;
+        case 4: GNB_NARROW_G(4) break;
+        default: GNB_NARROW_G(5) break;
+        }
+#undef GNB_NARROW_G
+#undef GNB_NARROW
+        return;
+    }
     const uint32_t want = (n_items + K3_WARPS - 1) / K3_WARPS;
     const uint32_t grid = want < 148u * 4u ? want : 148u * 4u;
-    const bool     small = max_hashes < 256;
 #define GNB_HIBF(HV)                                                                                                             \
     if (small)                                                                                                                   \
         k_hibf_count<HV, 8><<<grid, K3_WARPS * 32, 0, st>>>(table, items, n_items, hashes, hash_off, counts, rel_cutoff, wo);           \
@@ -1113,6 +1372,13 @@ void launch_hibf_round(const IbfDev *table, uint32_t hash_funs, const uint2 *ite
     default: GNB_HIBF(5) break;
     }
 #undef GNB_HIBF
+}
+
+void launch_hibf_seed_items(const uint8_t *active, const uint32_t *counts, uint32_t n_reads, uint2 *items, unsigned long long *cursor, cudaStream_t st)
+{
+    if (n_reads == 0)
+        return;
+    k_hibf_seed_items<<<(n_reads + 255) / 256, 256, 0, st>>>(active, counts, n_reads, items, cursor);
 }
 
 void launch_ibf_count_dense(const IbfDev &f, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n_reads, uint32_t max_hashes,

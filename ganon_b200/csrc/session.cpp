@@ -185,6 +185,7 @@ struct FilterRt
     // HIBF: one IbfDev per sub-IBF (tables carved out of the shared device arrays above)
     bool                  is_hibf = false;
     std::vector<IbfDev>   ibf_table;
+    std::vector<uint32_t> round_lanes; // [depth] lanes per item of the traversal round (1..16), 0 = whole warp (wide sub-IBFs)
     DevBuf                d_ibf_table;
 };
 
@@ -762,6 +763,45 @@ int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
         d.bin_node    = F.d_bin_node.as<uint32_t>() + place[i].bin_node;
         d.seg_off     = place[i].has_seg ? F.d_seg_off.as<uint32_t>() + place[i].seg_off : nullptr;
         d.segs        = F.d_segs.as<Seg>(); // seg_off entries are absolute indices into the shared array
+    }
+    // lanes per item of every traversal round: round d visits the sub-IBFs at depth d
+    {
+        std::vector<int> depth(db.ibfs.size(), -1);
+        std::vector<size_t> queue{0};
+        depth[0] = 0;
+        for (size_t qi = 0; qi < queue.size(); ++qi)
+        {
+            const size_t i = queue[qi];
+            for (uint64_t b = 0; b < db.ibfs[i].bins; ++b)
+                if (db.bin_to_user[i][b] < 0)
+                {
+                    const size_t c = (size_t)db.next_ibf_id[i][b];
+                    if (depth[c] < 0)
+                    {
+                        depth[c] = depth[i] + 1;
+                        queue.push_back(c);
+                    }
+                }
+        }
+        std::vector<uint32_t> max_rw;
+        for (size_t i = 0; i < db.ibfs.size(); ++i)
+            if (depth[i] >= 0)
+            {
+                if (max_rw.size() <= (size_t)depth[i])
+                    max_rw.resize(depth[i] + 1, 0);
+                max_rw[depth[i]] = std::max(max_rw[depth[i]], F.ibf_table[i].row_words);
+            }
+        F.round_lanes.clear();
+        for (uint32_t rw : max_rw)
+        {
+            uint32_t need = (rw + 1) / 2, g = 1;
+            while (g < need)
+                g <<= 1;
+            F.round_lanes.push_back(g <= 16 ? g : 0);
+        }
+        if (const char *e = getenv("GANON_B200_HIBF_WIDE"))
+            if (e[0] == '1')
+                F.round_lanes.assign(F.round_lanes.size(), 0); // debugging aid: the warp-per-item kernel for every round
     }
     GNB_TRY(F.d_ibf_table.ensure(F.ibf_table.size() * sizeof(IbfDev)));
     GNB_CUDA(cudaMemcpy(F.d_ibf_table.p, F.ibf_table.data(), F.ibf_table.size() * sizeof(IbfDev), cudaMemcpyHostToDevice));
@@ -1448,29 +1488,24 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     const uint32_t n = n_reads;
     hibf_bytes = 0;
     hibf_ms    = 0;
-    std::vector<uint2> items;
-    items.reserve(n);
-    if (active_on_device && li > 0 && n)
-    {
-        GNB_CUDA(cudaMemcpyAsync(h_active.data(), d_active.p, n, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaStreamSynchronize(st));
-        timing.d2h_bytes += n;
-    }
-    for (uint32_t r = 0; r < n; ++r)
-        if (h_active[r] && h_counts[r] > 0 && h_counts[r] <= 65535)
-            items.push_back(make_uint2(r, 0));
-    uint64_t n_items = items.size();
-    GNB_TRY(d_items_a.ensure((n_items + 1024) * sizeof(uint2)));
-    GNB_TRY(d_items_b.ensure((n_items + 1024) * sizeof(uint2)));
-    if (n_items)
-        GNB_CUDA(cudaMemcpyAsync(d_items_a.p, items.data(), n_items * sizeof(uint2), cudaMemcpyHostToDevice, st));
-    timing.h2d_bytes += n_items * sizeof(uint2);
+    // worklist of round 0 on the device: d_status[8..9] = item cursor of the seeding, d_status[10..11] = bytes of all rounds
+    unsigned long long *d_seed  = reinterpret_cast<unsigned long long *>(d_status.as<uint32_t>() + 8);
+    unsigned long long *d_bytes = reinterpret_cast<unsigned long long *>(d_status.as<uint32_t>() + 10);
+    GNB_TRY(d_items_a.ensure(((uint64_t)n + 1024) * sizeof(uint2)));
+    GNB_TRY(d_items_b.ensure(((uint64_t)n + 1024) * sizeof(uint2)));
+    GNB_CUDA(cudaMemsetAsync(d_seed, 0, 16, st));
+    launch_hibf_seed_items(li > 0 ? d_active.as<uint8_t>() : nullptr, d_counts.as<uint32_t>(), n, d_items_a.as<uint2>(), d_seed, st);
+    launches += 1;
+    unsigned long long n_items = 0;
+    GNB_CUDA(cudaMemcpyAsync(&n_items, d_seed, 8, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    timing.d2h_bytes += 8;
     unsigned long long tuples_before = 0;
     DevBuf *cur = &d_items_a, *nxt = &d_items_b;
-    std::vector<uint2> round_items; // only used for the byte accounting
-    while (n_items)
+    for (size_t round = 0; n_items; ++round)
     {
+        const uint32_t lanes = round < F.round_lanes.size() ? F.round_lanes[round] : 0;
         unsigned long long got_tuples = 0, got_items = 0;
         for (int attempt = 0; attempt < 3; ++attempt)
         {
@@ -1478,9 +1513,10 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
             GNB_CUDA(cudaMemsetAsync(d_items_cursor.p, 0, 8, st));
             GNB_CUDA(cudaMemcpyAsync(d_cursor.p, &tuples_before, 8, cudaMemcpyHostToDevice, st));
             GNB_CUDA(cudaEventRecord(ev[4], st));
+            // bytes are accumulated by the attempt that fits (an overflowing attempt is repeated in full)
             launch_hibf_round(F.d_ibf_table.as<IbfDev>(), F.dev.hash_funs, cur->as<uint2>(), (uint32_t)n_items, d_hashes.as<uint64_t>(),
                               d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff, d_tuples_a.as<uint64_t>(),
-                              d_cursor.as<unsigned long long>(), cap, nxt->as<uint2>(), d_items_cursor.as<unsigned long long>(), icap, st);
+                              d_cursor.as<unsigned long long>(), cap, nxt->as<uint2>(), d_items_cursor.as<unsigned long long>(), icap, attempt == 0 ? d_bytes : nullptr, lanes, st);
             GNB_CUDA(cudaEventRecord(ev[5], st));
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&got_tuples, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1507,18 +1543,17 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
             if (got_items > icap)
                 GNB_TRY(nxt->ensure(got_items * sizeof(uint2)));
         }
-        // algorithmic bytes of the round: every item reads n_hashes * h * row_words * 8 of its sub-IBF
-        {
-            round_items.resize(n_items);
-            GNB_CUDA(cudaMemcpy(round_items.data(), cur->p, n_items * sizeof(uint2), cudaMemcpyDeviceToHost));
-            for (auto const &it : round_items)
-                hibf_bytes += (uint64_t)h_counts[it.x] * F.ibf_table[it.y].hash_funs * F.ibf_table[it.y].row_words * 8;
-        }
         tuples_before = got_tuples;
         n_items       = got_items;
         std::swap(cur, nxt);
         if (n_items)
-            GNB_TRY(nxt->ensure(n_items * sizeof(uint2))); // the next round can at most... grow lazily on overflow
+            GNB_TRY(nxt->ensure(n_items * sizeof(uint2))); // grows lazily on overflow
+    }
+    {
+        unsigned long long b = 0;
+        GNB_CUDA(cudaMemcpyAsync(&b, d_bytes, 8, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaStreamSynchronize(st));
+        hibf_bytes = b;
     }
     produced_out = tuples_before;
     return GNB_OK;

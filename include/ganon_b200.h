@@ -94,7 +94,18 @@ int gnb_db_emplace(gnb_db *db, const uint64_t *hashes, const uint32_t *bins, uin
 int gnb_db_set_targets(gnb_db *db, uint64_t n_targets, const char *const *names, const uint32_t *bin_target,
                        const uint64_t *target_hashes, uint64_t max_hashes_bin);
 int gnb_db_read_words(const gnb_db *db, uint64_t ibf_index, uint64_t word_offset, uint64_t n_words, uint64_t *out);
-int gnb_db_save(const gnb_db *db, const char *path); /* flat .ibf in the reference layout (save_filter GanonBuild.cpp:251-288) */
+/* flat: .ibf in the reference layout (save_filter GanonBuild.cpp:251-288); HIBF: raptor 3.0.1 index layout as read by
+ * load_filter(THIBF) GC.cpp:875-938 (one path "/db/<target>.minimiser" per user bin) */
+int gnb_db_save(const gnb_db *db, const char *path);
+/* An HIBF directly in HBM (tests / benchmark; raptor, the HIBF builder, is not part of the reference tree): n_ibfs
+ * sub-IBFs (0 = top level) of bins[i] technical bins x bin_size_bits[i] rows, tables in the layout of HIBF.hpp:124-136,
+ * 176-188 flattened over the sub-IBFs' bins -- next_ibf[j]: child IBF of a merged bin (else the IBF's own index),
+ * bin_to_user[j]: user bin, or < 0 for a merged bin.  Target names = user_bin_names; per-target fpr = fpr (GC.cpp:932).
+ * gnb_db_fill_random fills every sub-IBF (seed + index); gnb_db_emplace_ibf inserts into one sub-IBF. */
+int gnb_db_create_hibf(uint64_t n_ibfs, const uint64_t *bins, const uint64_t *bin_size_bits, uint32_t hash_functions,
+                       uint32_t kmer_size, uint32_t window_size, const int64_t *next_ibf, const int64_t *bin_to_user,
+                       uint64_t n_user_bins, const char *const *user_bin_names, double fpr, int device, gnb_db **out);
+int gnb_db_emplace_ibf(gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint32_t *bins, uint64_t n);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Test hooks for single kernels.
