@@ -697,6 +697,14 @@ __device__ __forceinline__ uint4 ldg_stream16(const uint64_t *p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+// plain 8-byte load as a volatile asm: keeps the issue order written in the source (used to software-pipeline the
+// minimiser fetch ahead of the row gathers)
+__device__ __forceinline__ uint64_t ldg_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint2 ldg_stream8(const uint64_t *p)
 {
     uint2 v;
@@ -959,7 +967,14 @@ __device__ __forceinline__ void count_item(const IbfDev &f, uint32_t read, uint3
             const Seg      sg  = f.segs[s];
             uint32_t       sum = sliced_sum<NP>(P, sg.reg, sg.mask);
             uint32_t       partial = 1;
-            if (sg.complete)
+            if (sg.complete == 2)
+            { // HIBF user bin split inside this register: u16 running sum, then the threshold (HIBF.hpp:437-458)
+                sum &= 0xFFFF;
+                partial = 0;
+                if (sum < T)
+                    sum = 0;
+            }
+            else if (sg.complete)
             {
                 sum     = min(sum, n); // GC.cpp:525-526
                 partial = 0;
@@ -1025,7 +1040,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
 // at once: every lane hashes its item's minimisers itself, gathers its 16 bytes of the h rows, ANDs and counts in its
 // own bit-sliced planes; no cross-lane traffic until the warp-aggregated append of the results.
 template <int H, int NP, int G>
-__global__ void __launch_bounds__(K3_WARPS * 32)
+__global__ void __launch_bounds__(K3_WARPS * 32, 2)
     k_hibf_count_narrow(const IbfDev *__restrict__ table, const uint2 *__restrict__ items, uint32_t n_items, const uint64_t *__restrict__ hashes,
                         const uint64_t *__restrict__ hash_off, const uint32_t *__restrict__ counts, double rel_cutoff, const WorkOut wo)
 {
@@ -1039,8 +1054,11 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         const bool     have = it < n_items;
         const uint2    item = have ? items[it] : make_uint2(0, 0);
         const IbfDev  *fp   = table + item.y;
+        // every field up front: the loads overlap with the gather loop instead of forming a chain in the epilogue
         const uint32_t row_words = fp->row_words, hash_shift = fp->hash_shift;
         const uint64_t bin_size = fp->bin_size;
+        const uint32_t *const f_single = fp->single_mask, *const f_bin_node = fp->bin_node, *const f_seg_off = fp->seg_off;
+        const Seg *const      f_segs = fp->segs;
         uint32_t       n  = 0;
         uint64_t       h0 = 0;
         if (have)
@@ -1064,14 +1082,27 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         for (int j = 0; j < NP; ++j)
             P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0;
         if (v0)
+        {
+            // the four minimisers of the next block are fetched while the rows of the current one are in flight
+            uint64_t xn[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                xn[q] = (uint32_t)q < n ? ldg_u64(hashes + h0 + q) : 0;
             for (uint32_t m = 0; m < n; m += 4)
             {
-                uint4 rows[4][H];
+                uint4    rows[4][H];
+                uint64_t xc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    xc[q] = xn[q];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    xn[q] = (m + 4 + q) < n ? ldg_u64(hashes + h0 + m + 4 + q) : 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                 {
                     const bool     ok = (m + q) < n;
-                    const uint64_t x  = ok ? hashes[h0 + m + q] : 0;
+                    const uint64_t x  = xc[q];
 #pragma unroll
                     for (int i = 0; i < H; ++i)
                     {
@@ -1117,6 +1148,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
                 }
                 csa_add4<NP>(P, x4);
             }
+        }
 
         // ---- epilogue: bins reaching the threshold -> tuples (user bins) / items of the next round (merged bins) ----
         const uint32_t T = threshold_cutoff(n, rel_cutoff);
@@ -1126,28 +1158,30 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         for (int r = 0; r < 4; ++r)
         {
             const bool valid = (r < 2) ? v0 : v1;
-            cand[r] = valid ? (sliced_ge<NP>(P, r, T) & fp->single_mask[w0 * 2 + r]) : 0u;
+            cand[r] = valid ? (sliced_ge<NP>(P, r, T) & f_single[w0 * 2 + r]) : 0u;
             uint32_t mm = cand[r];
             while (mm)
             {
                 const uint32_t b = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (fp->bin_node[w0 * 64 + r * 32 + b] & kMergedBin)
+                if (f_bin_node[w0 * 64 + r * 32 + b] & kMergedBin)
                     ++ni;
                 else
                     ++nt;
             }
         }
         uint32_t s0 = 0, s1 = 0;
-        if (v0 && fp->seg_off != nullptr)
+        if (v0 && f_seg_off != nullptr)
         {
-            s0 = fp->seg_off[sub];
-            s1 = fp->seg_off[sub + 1];
+            s0 = f_seg_off[sub];
+            s1 = f_seg_off[sub + 1];
             for (uint32_t sI = s0; sI < s1; ++sI)
             {
-                const Seg sg = fp->segs[sI];
+                const Seg sg = f_segs[sI];
                 uint32_t  sum = sliced_sum<NP>(P, sg.reg, sg.mask);
-                if (sg.complete)
+                if (sg.complete == 2)
+                    sum = (sum & 0xFFFF) < T ? 0 : (sum & 0xFFFF);
+                else if (sg.complete)
                     sum = min(sum, n) < T ? 0 : min(sum, n);
                 nt += sum != 0;
             }
@@ -1185,7 +1219,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
             {
                 const uint32_t b = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const uint32_t node = fp->bin_node[w0 * 64 + r * 32 + b];
+                const uint32_t node = f_bin_node[w0 * 64 + r * 32 + b];
                 if (node & kMergedBin)
                 {
                     if (bi < wo.items_cap)
@@ -1202,9 +1236,14 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         }
         for (uint32_t sI = s0; sI < s1; ++sI)
         {
-            const Seg sg = fp->segs[sI];
+            const Seg sg = f_segs[sI];
             uint32_t  sum = sliced_sum<NP>(P, sg.reg, sg.mask), partial = 1;
-            if (sg.complete)
+            if (sg.complete == 2)
+            {
+                sum     = (sum & 0xFFFF) < T ? 0 : (sum & 0xFFFF);
+                partial = 0;
+            }
+            else if (sg.complete)
             {
                 sum     = min(sum, n) < T ? 0 : min(sum, n);
                 partial = 0;

@@ -723,13 +723,17 @@ int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
                 }
                 else
                 {
-                    F.node_multi[node] = 1;
                     std::map<uint64_t, uint32_t> regs;
                     for (uint64_t x = b; x < e; ++x)
                         regs[x >> 5] |= 1u << (x & 31);
+                    // a run inside one 32-bin register is decided on the device (complete = 2: the HIBF rule -- running
+                    // sum of the counter type, then the threshold, HIBF.hpp:437-458); a longer run yields partial sums
+                    const uint16_t complete = regs.size() == 1 ? 2 : 0;
+                    if (!complete)
+                        F.node_multi[node] = 1;
                     for (auto const &[rg, mask] : regs)
                     {
-                        per_slot[rg >> 2].push_back(Seg{mask, node, (uint16_t)(rg & 3), 0});
+                        per_slot[rg >> 2].push_back(Seg{mask, node, (uint16_t)(rg & 3), complete});
                         place[i].has_seg = true;
                     }
                 }
