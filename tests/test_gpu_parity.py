@@ -336,6 +336,96 @@ def test_hibf_scenarios_match_reference_outputs(name, golden_dbs, tmp_path, fini
         assert _read_sorted(pre + ext) == SU.expected_lines(name, ext[1:]), ext
 
 
+def test_hibf_created_in_hbm_matches_oracle(tmp_path, finish_mode):
+    """gnb_db_create_hibf / emplace_ibf / save -> reopen: a 3-level HIBF whose sub-IBFs take every traversal kernel
+    (1, 2 and 4 lanes per item, and a 2100-bin sub-IBF on the warp-per-item path), with user bins split inside a
+    32-bin register, across registers and across bin-words; results vs the oracle's HIBF restatement."""
+    rng = np.random.default_rng(21)
+    k, w, h = 19, 31, 3
+    bins, rows, nxt, pos, chains = [], [], [], [], []
+
+    def new_ibf(nb, nr):
+        bins.append(nb)
+        rows.append(nr)
+        nxt.append([len(bins) - 1] * nb)
+        pos.append([0] * nb)
+        return len(bins) - 1
+
+    def fill(ibf, first, up, runs):
+        b = first
+        for r in runs:
+            if b + r > bins[ibf]:
+                break
+            u = len(chains)
+            for x in range(b, b + r):
+                pos[ibf][x] = u
+            chains.append([(ibf, list(range(b, b + r)))] + up)
+            b += r
+        while b < bins[ibf]:
+            u = len(chains)
+            pos[ibf][b] = u
+            chains.append([(ibf, [b])] + up)
+            b += 1
+
+    top = new_ibf(200, 4001)
+    c1, c2 = new_ibf(64, 3001), new_ibf(2100, 1009)
+    g1 = new_ibf(130, 2003)
+    nxt[top][0], pos[top][0] = c1, -1
+    nxt[top][1], pos[top][1] = c2, -1
+    nxt[c1][5], pos[c1][5] = g1, -1
+    fill(top, 2, [], [1, 2, 3, 1, 40, 1, 1, 70])  # runs inside a register, across registers and across words
+    fill(c1, 0, [(top, [0])], [2, 3])  # bins 0..4, bin 5 is merged
+    fill(c1, 6, [(top, [0])], [1, 30, 1])
+    fill(c2, 0, [(top, [1])], [1] * 50 + [3, 33, 1, 65])
+    fill(g1, 0, [(c1, [5]), (top, [0])], [1, 1, 2, 64, 1])
+    names = ["u%d" % u for u in range(len(chains))]
+    db = Database.create_hibf(bins, rows, h, k, w, nxt, pos, names, fpr=0.01)
+    db.fill_random(9, 3)
+    genomes = [bytes(rng.choice(list(b"ACGT"), size=700).astype(np.uint8)) for _ in names]
+    per = {}
+    for u, g in enumerate(genomes):
+        hs = np.unique(O.minimiser_hash(g, k, w))
+        for ibf, bs in chains[u]:
+            a, b_ = per.setdefault(ibf, ([], []))
+            a.append(hs)
+            b_.append(np.asarray(bs, dtype=np.uint32)[np.arange(hs.size) % len(bs)])
+    for ibf, (a, b_) in per.items():
+        db.emplace(np.concatenate(a), np.concatenate(b_), ibf_index=ibf)
+    path = str(tmp_path / "made.hibf")
+    db.save(path)
+    f = formats.read_hibf(path)
+    assert [i.bins for i in f.ibfs] == bins and f.next_ibf_id == nxt and f.bin_to_user == pos
+    assert [formats.hibf_target_name(p[0]) for p in f.bin_path] == names
+    for i, ib in enumerate(f.ibfs):
+        assert np.array_equal(ib.data, db.read_words(0, ib.bin_size * ib.bin_words, ibf_index=i))
+    ohibf = O.OracleHIBF([O.OracleIBF(i.bins, i.bin_size, i.hash_funs, i.data) for i in f.ibfs], nxt, pos, len(names))
+    reads = []
+    for i in range(500):
+        if i % 5 == 4:
+            s = bytes(rng.choice(list(b"ACGT"), size=150).astype(np.uint8))
+        else:
+            g = genomes[int(rng.integers(0, len(names)))]
+            p0 = int(rng.integers(0, len(g) - 150))
+            s = bytearray(g[p0 : p0 + 150])
+            for _ in range(int(rng.integers(0, 4))):
+                s[int(rng.integers(0, 150))] = ord("ACGT"[int(rng.integers(0, 4))])
+            s = bytes(s)
+        reads.append((b"r%d" % i, s, None))
+    fq = b"".join(b"@%s\n%s\n+\n%s\n" % (i, a, b"F" * len(a)) for i, a, _ in reads)
+    reopened = Database.open(path, hibf=True)
+    for cutoff, relf, fpq in [(0.05, 1.0, 1.0), (0.4, 0.3, 1e-4)]:
+        filt = O.OracleFilter(ohibf, names, [[u] for u in range(len(names))], [0.01] * len(names), cutoff, k, w)
+        want = O.all_lines(O.classify_level([filt], reads, relf, fpq))
+        assert len(want) > 300
+        for d in (db, reopened):
+            sess = Session([d], [cutoff], [relf], [fpq], output_all=True)
+            res = sess.classify(fq, final=True)
+            assert sorted(result_text(res, "all").decode().splitlines()) == want, (cutoff, relf, fpq)
+            sess.close()
+    db.close()
+    reopened.close()
+
+
 # ------------------------------------------------------------------------------------------------------------------ pipeline + shards
 def test_async_submit_collect_matches_sync(golden_dbs):
     fq1 = open(os.path.join(SU.GOLDEN, "reads.1.fq"), "rb").read()
