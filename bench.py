@@ -251,6 +251,12 @@ def ensure_ibf_file(wl_name, db):
     if not (os.path.exists(path) and os.path.getsize(path) > want):
         free = shutil.disk_usage(CACHE).free
         if free < want * 1.1:
+            # make room: the copies written for other workloads are only a cache
+            for f in os.listdir(CACHE):
+                if f.endswith((".ibf", ".hibf")) and not f.startswith(wl_name + "_seed"):
+                    os.remove(os.path.join(CACHE, f))
+            free = shutil.disk_usage(CACHE).free
+        if free < want * 1.1:
             raise RuntimeError("not enough disk for the reference's copy of the database (%d GiB needed)" % (want >> 30))
         db.save(path)
     return path
