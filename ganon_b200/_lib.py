@@ -106,6 +106,19 @@ class BatchResult(C.Structure):
     ]
 
 
+class ReassignResult(C.Structure):
+    _fields_ = [
+        ("n_groups", C.c_uint32),
+        ("group_label", C.POINTER(C.c_char_p)),
+        ("one_text", C.POINTER(C.c_void_p)),
+        ("one_len", C.POINTER(C.c_uint64)),
+        ("iterations", C.POINTER(C.c_uint32)),
+        ("reassigned_reads", C.POINTER(C.c_uint64)),
+        ("rep_text", C.c_void_p),
+        ("rep_len", C.c_uint64),
+    ]
+
+
 class Totals(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("input_seqs", "seqs_processed", "seqs_skipped_big", "seqs_skipped_small", "length_processed", "kmers_processed", "seqs_classified", "kmers_matches", "kmers_from_classified_seqs", "matches", "seqs_unique", "discarded_matches_filter", "discarded_matches_fprquery")]
 
@@ -159,6 +172,8 @@ SYMBOLS = {
     "gnb_session_report": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gnb_session_stats": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gnb_session_totals": (C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(Totals)]),
+    "gnb_session_keep_matches": (C.c_int, [_P, C.c_int]),
+    "gnb_session_reassign": (C.c_int, [_P, C.c_uint32, C.c_double, C.c_uint32, C.POINTER(ReassignResult)]),
 }
 
 _LIB = None

@@ -362,6 +362,22 @@ class Session:
         check(_lib.lib().gnb_session_stats(self._h, prefix_id, prefix_name.encode(), C.byref(p), C.byref(n)))
         return C.string_at(p, n.value)
 
+    def keep_matches(self, enable: bool = True) -> None:
+        """Keep the matches of every classified read in HBM for `reassign` (call before the first batch)."""
+        check(_lib.lib().gnb_session_keep_matches(self._h, int(enable)))
+
+    def reassign(self, prefix_id: int = 0, threshold: float = 0.0, max_iter: int = 10):
+        """EM reassignment (src/ganon/reassign.py) on the kept matches: ({group label: `.one` bytes}, new `.rep` bytes,
+        {group label: (iterations, reads with several matches)})."""
+        r = _lib.ReassignResult()
+        check(_lib.lib().gnb_session_reassign(self._h, prefix_id, float(threshold), int(max_iter), C.byref(r)))
+        ones, info = {}, {}
+        for g in range(r.n_groups):
+            lab = r.group_label[g].decode()
+            ones[lab] = C.string_at(r.one_text[g], r.one_len[g]) if r.one_len[g] else b""
+            info[lab] = (r.iterations[g], r.reassigned_reads[g])
+        return ones, (C.string_at(r.rep_text, r.rep_len) if r.rep_len else b""), info
+
     def totals(self, prefix_id: int = 0, level: int = -1) -> Totals:
         t = Totals()
         check(_lib.lib().gnb_session_totals(self._h, prefix_id, level, C.byref(t)))
@@ -418,6 +434,10 @@ class GanonClassifyConfig:
     quiet: bool = False
     # not in the reference: which GPU to use
     device: int = 0
+    # not in the reference binary: the EM step of `ganon classify` (src/ganon/reassign.py) from the matches in HBM
+    reassign_em: bool = False
+    em_max_iter: int = 10
+    em_threshold: List[float] = field(default_factory=lambda: [0.0])
 
     def _err(self, msg: str) -> bool:
         print(msg, file=sys.stderr)
@@ -619,6 +639,11 @@ def run(cfg: GanonClassifyConfig) -> bool:
     labels = sess.level_labels
     multi = len(labels) > 1 and not cfg.output_single
     write_one = cfg.output_lca and not cfg.skip_lca
+    if cfg.reassign_em:
+        if write_one:
+            print("--reassign-em writes the .one file itself: it cannot be combined with --output-lca", file=sys.stderr)
+            return False
+        sess.keep_matches(True)
     prefixes = list(reads_config)
     out_rep = {p: open(cfg.output_prefix + p + ".rep", "wb") for p in prefixes}
     out_unc = {p: open(cfg.output_prefix + p + ".unc", "wb") for p in prefixes} if cfg.output_unclassified else {}
@@ -688,7 +713,17 @@ def run(cfg: GanonClassifyConfig) -> bool:
     t_class = time.time() - t_class
 
     for pid, prefix in enumerate(prefixes):
-        out_rep[prefix].write(sess.report(pid))
+        if cfg.reassign_em:
+            # reassign.py: `.one` (one per hierarchy label unless there is a single `.all`) and the new `.rep`
+            ones, new_rep, info = sess.reassign(pid, cfg.em_threshold[0], cfg.em_max_iter)
+            for lab, text in ones.items():
+                with open(cfg.output_prefix + prefix + ("." + lab if lab else "") + ".one", "wb") as fh:
+                    fh.write(text)
+                if not cfg.quiet:
+                    print(" - %d iteration(s), %d reassigned reads%s" % (info[lab][0], info[lab][1], " [" + lab + "]" if lab else ""), file=sys.stderr)
+            out_rep[prefix].write(new_rep)
+        else:
+            out_rep[prefix].write(sess.report(pid))
         out_rep[prefix].close()
         if cfg.output_stats:
             with open(cfg.output_prefix + prefix + ".sta", "wb") as fh:

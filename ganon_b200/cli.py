@@ -33,6 +33,10 @@ _OPTS = {
     "verbose": (None, "bool", "verbose"),
     "quiet": (None, "bool", "quiet"),
     "device": (None, "int", "device"),  # extension: GPU ordinal
+    # extension: `ganon classify --multiple-matches em` without the round trip through the .all file (src/ganon/reassign.py)
+    "reassign-em": (None, "bool", "reassign_em"),
+    "em-max-iter": (None, "int", "em_max_iter"),
+    "em-threshold": (None, "floats", "em_threshold"),
     "help": ("h", "flag", None),
     "version": ("v", "flag", None),
 }
@@ -64,6 +68,11 @@ Usage:
       --n-batches arg         (accepted for compatibility)
       --n-reads arg           Number of reads for each batch. Default: 400
       --device arg            CUDA device ordinal. Default: 0
+      --reassign-em           EM reassignment of reads with several matches from the matches kept on the GPU
+                              (what `ganon classify --multiple-matches em` does from the .all file): writes prefix.one
+                              and the reassigned prefix.rep
+      --em-max-iter arg       Max. number of EM iterations, 0 = until convergence. Default: 10
+      --em-threshold arg      Convergence threshold of the EM. Default: 0
       --verbose               Verbose output mode
       --quiet                 Quiet output mode
   -h, --help                  Print help

@@ -187,6 +187,37 @@ void   launch_finish_select(const FinishParams &p, cudaStream_t st);            
 size_t finish_scan_tmp_bytes(uint32_t n_reads);
 void   launch_finish_scan(const FinishParams &p, void *tmp, size_t tmp_bytes, cudaStream_t st); // sizes -> offs
 void   launch_finish_write(const FinishParams &p, cudaStream_t st);                          // pass B
+// EM reassignment of multi-matching reads from the matches kept in HBM (src/ganon/reassign.py)
+struct EmSizes
+{
+    unsigned long long reads, id_bytes; // per read of a batch: 1 / id length if the level classified it
+};
+struct EmStoreDev // matches of all classified reads of a run (one EM group), CSR over reads
+{
+    uint64_t *off;    // [n_reads + 1] into tgt / cnt
+    uint32_t *tgt;    // run-wide target id (by name)
+    uint32_t *cnt;
+    uint64_t *id_off; // [n_reads + 1] into ids
+    char     *ids;
+};
+size_t em_scan_tmp_bytes(uint32_t n_reads);
+// per read of the batch: {kept > 0, id_len} -> exclusive scan -> offs [n_reads + 1]
+void launch_em_sizes(const FinishSizes *sizes, const uint32_t *id_len, uint32_t n_reads, EmSizes *es, EmSizes *offs, void *tmp, size_t tmp_bytes, cudaStream_t st);
+// append the batch's classified reads (level-local CSR match_off/match_target/match_count) to the store
+void launch_em_append(const FinishSizes *sizes, const EmSizes *offs, const uint64_t *match_off, const uint32_t *match_target, const uint32_t *match_count,
+                      uint64_t n_matches, const uint32_t *id_off, const uint32_t *id_len, const uint8_t *blk, uint32_t n_reads, const uint32_t *node_to_target,
+                      EmStoreDev store, uint64_t base_reads, uint64_t base_matches, uint64_t base_ids, cudaStream_t st);
+// first position of every target in the store (the reference numbers targets by first appearance in the .all file)
+void launch_em_first_pos(EmStoreDev store, uint64_t n_matches, unsigned long long *first_pos, cudaStream_t st);
+// weights of reads with exactly one match
+void launch_em_initial(EmStoreDev store, uint64_t n_reads, unsigned long long *initial, cudaStream_t st);
+// one EM iteration: counts (preset to the initial weights) += 1 at the top match of every multi-matching read
+void launch_em_assign(EmStoreDev store, uint64_t n_reads, const unsigned long long *weight, unsigned long long *counts, cudaStream_t st);
+// `.one` lines: sizes pass (out == nullptr: line_len[r]) and write pass (line_off = exclusive scan of line_len)
+void launch_em_one(EmStoreDev store, uint64_t n_reads, const unsigned long long *weight, const uint32_t *name_off, const char *names, uint64_t *line_len,
+                   const uint64_t *line_off, char *out, unsigned long long *n_multi, cudaStream_t st);
+size_t em_scan64_tmp_bytes(uint64_t n);
+void   launch_scan64(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 // build-side
 void launch_fill_random(uint64_t *data, uint64_t rows, uint32_t row_words, uint32_t w0, uint32_t total_words, uint64_t bins, uint64_t seed,
                         int and_terms, cudaStream_t st);

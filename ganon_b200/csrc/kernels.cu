@@ -1851,6 +1851,171 @@ void launch_finish_write(const FinishParams &p, cudaStream_t st)
 }
 
 // =====================================================================================================================
+// EM reassignment (src/ganon/reassign.py) on the matches of the whole run kept in HBM.
+// Probabilities of one iteration share a denominator (reassign.py:106-107, 125-128), so "highest probability" is
+// "highest integer weight": the device compares the counts themselves; the host keeps the double-precision
+// probabilities only for the convergence test (|old - new| summed in the reference's target order).
+// =====================================================================================================================
+namespace
+{
+__global__ void k_em_sizes(const FinishSizes *__restrict__ sizes, const uint32_t *__restrict__ id_len, uint32_t n, EmSizes *__restrict__ es)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n)
+        return;
+    const bool cls = r < n && sizes[r].kept != 0;
+    es[r]          = EmSizes{cls ? 1ull : 0ull, cls ? (unsigned long long)id_len[r] : 0ull};
+}
+struct EmSizesAdd
+{
+    __host__ __device__ __forceinline__ EmSizes operator()(const EmSizes &a, const EmSizes &b) const { return EmSizes{a.reads + b.reads, a.id_bytes + b.id_bytes}; }
+};
+__global__ void k_em_append_reads(const FinishSizes *__restrict__ sizes, const EmSizes *__restrict__ offs, const uint64_t *__restrict__ match_off,
+                                  const uint32_t *__restrict__ id_off, const uint32_t *__restrict__ id_len, const uint8_t *__restrict__ blk, uint32_t n, EmStoreDev st,
+                                  uint64_t base_reads, uint64_t base_matches, uint64_t base_ids)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0)
+    { // sentinels of the grown store
+        st.off[base_reads + offs[n].reads]    = base_matches + match_off[n];
+        st.id_off[base_reads + offs[n].reads] = base_ids + offs[n].id_bytes;
+    }
+    if (r >= n || sizes[r].kept == 0)
+        return;
+    const uint64_t j = base_reads + offs[r].reads;
+    st.off[j]        = base_matches + match_off[r];
+    const uint64_t o = base_ids + offs[r].id_bytes;
+    st.id_off[j]     = o;
+    const uint8_t *id = blk + id_off[r];
+    for (uint32_t i = 0; i < id_len[r]; ++i)
+        st.ids[o + i] = (char)id[i];
+}
+__global__ void k_em_append_matches(const uint32_t *__restrict__ mt, const uint32_t *__restrict__ mc, uint64_t n, const uint32_t *__restrict__ map, uint32_t *__restrict__ dt,
+                                    uint32_t *__restrict__ dc)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    dt[i] = map[mt[i]];
+    dc[i] = mc[i];
+}
+__global__ void k_em_first_pos(const uint32_t *__restrict__ tgt, uint64_t n, unsigned long long *__restrict__ first_pos)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n)
+        atomicMin(&first_pos[tgt[i]], (unsigned long long)i);
+}
+__global__ void k_em_initial(EmStoreDev st, uint64_t n_reads, unsigned long long *__restrict__ initial)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads)
+        return;
+    const uint64_t a = st.off[r];
+    if (st.off[r + 1] - a == 1)
+        atomicAdd(&initial[st.tgt[a]], 1ull);
+}
+// get_top_match (reassign.py:229-241): first match unless a later one has a strictly higher, non-zero weight
+__device__ __forceinline__ uint64_t em_top(const EmStoreDev &st, uint64_t a, uint64_t b, const unsigned long long *__restrict__ weight)
+{
+    uint64_t           best = a;
+    unsigned long long bw   = 0;
+    for (uint64_t i = a; i < b; ++i)
+    {
+        const unsigned long long w = weight[st.tgt[i]];
+        if (w > bw)
+        {
+            bw   = w;
+            best = i;
+        }
+    }
+    return best;
+}
+__global__ void k_em_assign(EmStoreDev st, uint64_t n_reads, const unsigned long long *__restrict__ weight, unsigned long long *__restrict__ counts)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads)
+        return;
+    const uint64_t a = st.off[r], b = st.off[r + 1];
+    if (b - a > 1)
+        atomicAdd(&counts[st.tgt[em_top(st, a, b, weight)]], 1ull);
+}
+__global__ void k_em_one(EmStoreDev st, uint64_t n_reads, const unsigned long long *__restrict__ weight, const uint32_t *__restrict__ name_off, const char *__restrict__ names,
+                         uint64_t *__restrict__ line_len, const uint64_t *__restrict__ line_off, char *__restrict__ out, unsigned long long *__restrict__ n_multi)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads)
+    {
+        if (r == n_reads && out == nullptr)
+            line_len[r] = 0;
+        return;
+    }
+    const uint64_t a = st.off[r], b = st.off[r + 1];
+    const uint64_t m = b - a == 1 ? a : em_top(st, a, b, weight);
+    const uint32_t t = st.tgt[m], k = st.cnt[m];
+    const uint32_t idl = (uint32_t)(st.id_off[r + 1] - st.id_off[r]), nl = name_off[t + 1] - name_off[t];
+    if (out == nullptr)
+    {
+        line_len[r] = idl + 1 + nl + 1 + dec_digits(k) + 1;
+        if (b - a > 1)
+            atomicAdd(n_multi, 1ull);
+        return;
+    }
+    put_line(out + line_off[r], reinterpret_cast<const uint8_t *>(st.ids + st.id_off[r]), idl, names + name_off[t], nl, k);
+}
+} // namespace
+
+size_t em_scan_tmp_bytes(uint32_t n_reads)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveScan(nullptr, bytes, (const EmSizes *)nullptr, (EmSizes *)nullptr, EmSizesAdd{}, EmSizes{0, 0}, (int)(n_reads + 1));
+    return bytes + 256;
+}
+void launch_em_sizes(const FinishSizes *sizes, const uint32_t *id_len, uint32_t n_reads, EmSizes *es, EmSizes *offs, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    k_em_sizes<<<(n_reads + 1 + 255) / 256, 256, 0, st>>>(sizes, id_len, n_reads, es);
+    cub::DeviceScan::ExclusiveScan(tmp, tmp_bytes, (const EmSizes *)es, offs, EmSizesAdd{}, EmSizes{0, 0}, (int)(n_reads + 1), st);
+}
+void launch_em_append(const FinishSizes *sizes, const EmSizes *offs, const uint64_t *match_off, const uint32_t *match_target, const uint32_t *match_count,
+                      uint64_t n_matches, const uint32_t *id_off, const uint32_t *id_len, const uint8_t *blk, uint32_t n_reads, const uint32_t *node_to_target,
+                      EmStoreDev store, uint64_t base_reads, uint64_t base_matches, uint64_t base_ids, cudaStream_t st)
+{
+    k_em_append_reads<<<(n_reads + 255) / 256, 256, 0, st>>>(sizes, offs, match_off, id_off, id_len, blk, n_reads, store, base_reads, base_matches, base_ids);
+    if (n_matches)
+        k_em_append_matches<<<(unsigned)((n_matches + 255) / 256), 256, 0, st>>>(match_target, match_count, n_matches, node_to_target, store.tgt + base_matches,
+                                                                                    store.cnt + base_matches);
+}
+void launch_em_first_pos(EmStoreDev store, uint64_t n_matches, unsigned long long *first_pos, cudaStream_t st)
+{
+    if (n_matches)
+        k_em_first_pos<<<(unsigned)((n_matches + 255) / 256), 256, 0, st>>>(store.tgt, n_matches, first_pos);
+}
+void launch_em_initial(EmStoreDev store, uint64_t n_reads, unsigned long long *initial, cudaStream_t st)
+{
+    if (n_reads)
+        k_em_initial<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(store, n_reads, initial);
+}
+void launch_em_assign(EmStoreDev store, uint64_t n_reads, const unsigned long long *weight, unsigned long long *counts, cudaStream_t st)
+{
+    if (n_reads)
+        k_em_assign<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(store, n_reads, weight, counts);
+}
+void launch_em_one(EmStoreDev store, uint64_t n_reads, const unsigned long long *weight, const uint32_t *name_off, const char *names, uint64_t *line_len,
+                   const uint64_t *line_off, char *out, unsigned long long *n_multi, cudaStream_t st)
+{
+    k_em_one<<<(unsigned)((n_reads + 1 + 255) / 256), 256, 0, st>>>(store, n_reads, weight, name_off, names, line_len, line_off, out, n_multi);
+}
+size_t em_scan64_tmp_bytes(uint64_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)n);
+    return bytes + 256;
+}
+void launch_scan64(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int64_t)n, st);
+}
+
+// =====================================================================================================================
 // build-side helpers
 // =====================================================================================================================
 namespace

@@ -142,6 +142,43 @@ struct PinnedAlloc
 template <typename T>
 using PinnedVec = std::vector<T, PinnedAlloc<T>>;
 
+// Matches of every classified read of a run (one EM group) kept in HBM for gnb_session_reassign.
+struct EmStore
+{
+    DevBuf   off, tgt, cnt, id_off, ids;
+    uint64_t n_reads = 0, n_matches = 0, id_bytes = 0;
+    // grow a buffer keeping its contents (rare: capacities double)
+    static int grow(DevBuf &b, size_t used, size_t need)
+    {
+        if (need <= b.cap)
+            return GNB_OK;
+        DevBuf nb;
+        GNB_TRY(nb.ensure(std::max(need, b.cap * 2)));
+        GNB_CUDA(cudaDeviceSynchronize()); // appends of earlier batches may still be writing the old buffer
+        if (used && b.p)
+            GNB_CUDA(cudaMemcpy(nb.p, b.p, std::min(used, b.cap), cudaMemcpyDeviceToDevice));
+        b.release();
+        b = nb;
+        return GNB_OK;
+    }
+    int reserve(uint64_t add_reads, uint64_t add_matches, uint64_t add_ids)
+    {
+        GNB_TRY(grow(off, (n_reads + 1) * 8, (n_reads + add_reads + 1) * 8));
+        GNB_TRY(grow(id_off, (n_reads + 1) * 8, (n_reads + add_reads + 1) * 8));
+        GNB_TRY(grow(tgt, n_matches * 4, (n_matches + add_matches) * 4 + 4));
+        GNB_TRY(grow(cnt, n_matches * 4, (n_matches + add_matches) * 4 + 4));
+        GNB_TRY(grow(ids, id_bytes, id_bytes + add_ids + 1));
+        return GNB_OK;
+    }
+    EmStoreDev dev() const { return EmStoreDev{off.as<uint64_t>(), tgt.as<uint32_t>(), cnt.as<uint32_t>(), id_off.as<uint64_t>(), ids.as<char>()}; }
+    void release()
+    {
+        for (DevBuf *b : {&off, &tgt, &cnt, &id_off, &ids})
+            b->release();
+        n_reads = n_matches = id_bytes = 0;
+    }
+};
+
 struct Rep // GC.cpp:153-160
 {
     uint64_t matches = 0, seqs_lca = 0, seqs_unique = 0, discarded_matches_filter = 0, discarded_matches_fprquery = 0;
@@ -212,6 +249,9 @@ struct LevelRt
     bool                device_finish = false;
     DevBuf              d_node_fpr, d_node_class, d_fpr_memo, d_parent, d_depth, d_name_off, d_names;
     std::vector<DevBuf> d_rep; // [prefix] -> unsigned long long [n_nodes][5]
+    // EM reassignment: run-wide target ids (by name, as the reference keys its dictionaries) of this level's nodes
+    std::vector<uint32_t> em_map;
+    DevBuf                d_em_map;
 
     uint32_t lca2(uint32_t u, uint32_t v) const
     {
@@ -317,6 +357,29 @@ struct gnb_session
     double               fpr_band = 4e-9;   // |q - fpr_query| <= band: the device's --fpr-query value is not trusted (K4)
     bool                 any_device_finish = false, all_device_finish = false;
     DevBuf               d_rep_scratch;     // report accumulators of runs whose accounting is discarded (gnb_session_run_staged)
+    // EM reassignment (gnb_session_keep_matches / gnb_session_reassign)
+    bool                     keep_matches = false;
+    std::mutex               em_mutex;
+    std::vector<std::string> em_names; // run-wide targets
+    DevBuf                   d_em_name_off, d_em_names;
+    std::vector<std::vector<EmStore>> em; // [prefix][group]
+    size_t em_groups() const { return cfg.output_single || levels.size() == 1 ? 1 : levels.size(); }
+    size_t em_group_of(size_t li) const { return em_groups() == 1 ? 0 : li; }
+    EmStore &em_store(uint32_t prefix_id, size_t li)
+    {
+        if (em.size() <= prefix_id)
+            em.resize(prefix_id + 1);
+        if (em[prefix_id].size() < em_groups())
+            em[prefix_id].resize(em_groups());
+        return em[prefix_id][em_group_of(li)];
+    }
+    int build_em_tables();
+    // results of the last gnb_session_reassign
+    std::vector<std::string>  em_one, em_label;
+    std::vector<const char *> em_one_p, em_label_p;
+    std::vector<uint64_t>     em_one_l, em_reassigned;
+    std::vector<uint32_t>     em_iterations;
+    std::string               em_rep;
     // Batches in flight take turns on the GPU for K3 .. K4 in submission order: without it the block scheduler lets the
     // K3 grid of a younger batch starve the small sort / K4 kernels of an older one and the pipeline stalls in collect.
     std::mutex              chain_mu;
@@ -398,6 +461,12 @@ struct BatchCtx
     uint64_t   next_active_hashes = 0;
     float      ms_finish_dev = 0;
     uint32_t   levels_on_device = 0;
+    // EM: matches of the batch appended to the run's store
+    uint32_t    cur_prefix = 0;
+    bool        em_account = false; // this pass's results count (false for gnb_session_run_staged's scratch pass)
+    DevBuf      d_em_sizes, d_em_offs;
+    int         em_append_device(size_t li, const FinishParams &P, uint64_t n_kept);
+    int         em_append_host(size_t li, const std::vector<size_t> &off_before, const std::vector<size_t> &tgt_before);
     // turn taking (asynchronous form only; seq == 0: not chained)
     uint64_t    seq = 0;
     cudaEvent_t ev_done = nullptr, prev_done = nullptr;
@@ -442,7 +511,7 @@ struct BatchCtx
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
                           &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status,
                           &d_items_a, &d_items_b, &d_items_cursor, &d_tstart, &d_nacc, &d_sizes, &d_offs, &d_one, &d_ftotals, &d_read_level, &d_moff,
-                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc})
+                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc, &d_em_sizes, &d_em_offs})
             b->release();
         h_pin.release();
         h_unc.release();
@@ -502,6 +571,13 @@ gnb_session::~gnb_session()
             b.release();
     }
     d_rep_scratch.release();
+    for (auto &l : levels)
+        l.d_em_map.release();
+    d_em_name_off.release();
+    d_em_names.release();
+    for (auto &p : em)
+        for (auto &e : p)
+            e.release();
 }
 
 // K4 tables of a level with one filter: per-node fpr, taxonomy parent / depth, names
@@ -553,6 +629,44 @@ int gnb_session::build_finish_tables(LevelRt &L)
     if (!pool.empty())
         GNB_CUDA(cudaMemcpy(L.d_names.p, pool.data(), pool.size(), cudaMemcpyHostToDevice));
     L.device_finish = true;
+    return GNB_OK;
+}
+
+// EM reassignment: run-wide target ids keyed by name (the reference's dictionaries are keyed by the target string, so a
+// name shared by two levels of an --output-single run is one target), names in HBM for the `.one` lines
+int gnb_session::build_em_tables()
+{
+    std::unordered_map<std::string, uint32_t> id_of;
+    em_names.clear();
+    for (auto &L : levels)
+    {
+        L.em_map.assign(L.node_names.size(), 0);
+        for (size_t i = 0; i < L.node_names.size(); ++i)
+        {
+            auto it = id_of.find(L.node_names[i]);
+            if (it == id_of.end())
+            {
+                it = id_of.emplace(L.node_names[i], (uint32_t)em_names.size()).first;
+                em_names.push_back(L.node_names[i]);
+            }
+            L.em_map[i] = it->second;
+        }
+        GNB_TRY(L.d_em_map.ensure(L.em_map.size() * 4 + 4));
+        GNB_CUDA(cudaMemcpy(L.d_em_map.p, L.em_map.data(), L.em_map.size() * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<uint32_t> off(em_names.size() + 1, 0);
+    std::string           pool;
+    for (size_t i = 0; i < em_names.size(); ++i)
+    {
+        off[i] = (uint32_t)pool.size();
+        pool += em_names[i];
+    }
+    off[em_names.size()] = (uint32_t)pool.size();
+    GNB_TRY(d_em_name_off.ensure(off.size() * 4));
+    GNB_TRY(d_em_names.ensure(pool.size() + 1));
+    GNB_CUDA(cudaMemcpy(d_em_name_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    if (!pool.empty())
+        GNB_CUDA(cudaMemcpy(d_em_names.p, pool.data(), pool.size(), cudaMemcpyHostToDevice));
     return GNB_OK;
 }
 
@@ -2146,6 +2260,8 @@ int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch
     launch_finish_write(P, st);
     launches += 1;
     GNB_CUDA(cudaEventRecord(ev[11], st));
+    if (S->keep_matches && em_account)
+        GNB_TRY(em_append_device(li, P, T.kept)); // before the turn is passed on: the store keeps submission order
     if (last)
         signal_done(); // the next batch may start K3 while this one's result travels to the host
     if (fetch)
@@ -2207,6 +2323,79 @@ int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch
     active_on_device = true;
     levels_on_device += 1;
     done = true;
+    return GNB_OK;
+}
+
+// EM: the level's classified reads (ids + kept matches, targets as run-wide ids) go to the run's store in HBM
+int BatchCtx::em_append_device(size_t li, const FinishParams &P, uint64_t n_kept)
+{
+    const uint32_t n = n_reads;
+    GNB_TRY(d_em_sizes.ensure(((size_t)n + 1) * sizeof(EmSizes)));
+    GNB_TRY(d_em_offs.ensure(((size_t)n + 1) * sizeof(EmSizes)));
+    GNB_TRY(d_tmp.ensure(em_scan_tmp_bytes(n)));
+    launch_em_sizes(P.sizes, P.id_len, n, d_em_sizes.as<EmSizes>(), d_em_offs.as<EmSizes>(), d_tmp.p, d_tmp.cap, st);
+    EmSizes tot{};
+    GNB_CUDA(cudaMemcpyAsync(&tot, d_em_offs.as<EmSizes>() + n, sizeof(EmSizes), cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    launches += 3;
+    if (tot.reads == 0)
+        return GNB_OK;
+    std::lock_guard<std::mutex> lock(S->em_mutex);
+    EmStore &E = S->em_store(cur_prefix, li);
+    GNB_TRY(E.reserve(tot.reads, n_kept, tot.id_bytes));
+    launch_em_append(P.sizes, d_em_offs.as<EmSizes>(), P.match_off, P.match_target, P.match_count, n_kept, P.id_off, P.id_len, P.blk1, n,
+                     levels[li].d_em_map.as<uint32_t>(), E.dev(), E.n_reads, E.n_matches, E.id_bytes, st);
+    launches += 2;
+    E.n_reads += tot.reads;
+    E.n_matches += n_kept;
+    E.id_bytes += tot.id_bytes;
+    GNB_CUDA(cudaGetLastError());
+    return GNB_OK;
+}
+
+// the same for a level finished by the host stage: the workers' new (read, kept) pairs and match lists of this level
+int BatchCtx::em_append_host(size_t li, const std::vector<size_t> &off_before, const std::vector<size_t> &tgt_before)
+{
+    std::vector<uint64_t> off, id_off;
+    std::vector<uint32_t> tgt, cnt;
+    std::string           ids;
+    const auto           &map = levels[li].em_map;
+    const char           *base = blk1;
+    std::lock_guard<std::mutex> lock(S->em_mutex);
+    EmStore &E = S->em_store(cur_prefix, li);
+    for (size_t w = 0; w < workers.size(); ++w)
+    {
+        const Worker &W = workers[w];
+        size_t        p = tgt_before[w];
+        for (size_t i = off_before[w]; i + 1 < W.m_off.size(); i += 2)
+        {
+            const uint64_t r = W.m_off[i], k = W.m_off[i + 1];
+            off.push_back(E.n_matches + tgt.size());
+            id_off.push_back(E.id_bytes + ids.size());
+            ids.append(base + p_idoff[r], p_idlen[r]);
+            for (uint64_t j = 0; j < k; ++j)
+            {
+                tgt.push_back(map[W.m_target[p + j]]);
+                cnt.push_back(W.m_count[p + j]);
+            }
+            p += k;
+        }
+    }
+    if (off.empty())
+        return GNB_OK;
+    GNB_TRY(E.reserve(off.size(), tgt.size(), ids.size()));
+    off.push_back(E.n_matches + tgt.size()); // sentinels
+    id_off.push_back(E.id_bytes + ids.size());
+    GNB_CUDA(cudaMemcpyAsync(E.off.as<uint64_t>() + E.n_reads, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    GNB_CUDA(cudaMemcpyAsync(E.id_off.as<uint64_t>() + E.n_reads, id_off.data(), id_off.size() * 8, cudaMemcpyHostToDevice, st));
+    GNB_CUDA(cudaMemcpyAsync(E.tgt.as<uint32_t>() + E.n_matches, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, st));
+    GNB_CUDA(cudaMemcpyAsync(E.cnt.as<uint32_t>() + E.n_matches, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!ids.empty())
+        GNB_CUDA(cudaMemcpyAsync(E.ids.as<char>() + E.id_bytes, ids.data(), ids.size(), cudaMemcpyHostToDevice, st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    E.n_reads += off.size() - 1;
+    E.n_matches += tgt.size();
+    E.id_bytes += ids.size();
     return GNB_OK;
 }
 
@@ -2471,6 +2660,8 @@ int BatchCtx::finish(uint32_t prefix_id, gnb_batch_result *out)
     GNB_CUDA(cudaSetDevice(device));
     begin_finish();
     keep_on_device = true;
+    cur_prefix     = prefix_id;
+    em_account     = true;
     struct TurnGuard
     {
         BatchCtx *c;
@@ -2496,7 +2687,18 @@ int BatchCtx::finish(uint32_t prefix_id, gnb_batch_result *out)
         if (!done)
         {
             GNB_TRY(to_host_state(li));
+            std::vector<size_t> off_before, tgt_before;
+            for (auto const &W : workers)
+            {
+                off_before.push_back(W.m_off.size());
+                tgt_before.push_back(W.m_target.size());
+            }
             GNB_TRY(finish_level(li));
+            if (S->keep_matches)
+            {
+                GNB_TRY(wait_turn()); // keeps the store in submission order
+                GNB_TRY(em_append_host(li, off_before, tgt_before));
+            }
         }
         timing.ms_host_finish += ms_since(th);
     }
@@ -2572,7 +2774,8 @@ extern "C" int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings)
             GNB_TRY(s->d_rep_scratch.ensure(bytes));
             GNB_CUDA(cudaMemset(s->d_rep_scratch.p, 0, bytes));
         }
-        bool done = false;
+        bool done    = false;
+        c.em_account = false;
         GNB_TRY(c.finish_level_device(0, s->d_rep_scratch.as<unsigned long long>(), false, done));
         c.active_on_device = false; // finish_staged starts over from the staged state
         c.levels_on_device = 0;
@@ -2704,6 +2907,8 @@ extern "C" int gnb_session_finish_level_device(gnb_session *s, uint32_t level, u
     GNB_CUDA(cudaSetDevice(c.device));
     auto th   = Clock::now();
     bool done = false;
+    c.cur_prefix = prefix_id;
+    c.em_account = true;
     if (s->levels[level].device_finish && c.tuples_on_device)
     {
         unsigned long long *rep = nullptr;
@@ -2940,6 +3145,223 @@ extern "C" int gnb_session_report(gnb_session *s, uint32_t prefix_id, const char
     o.push_back('\n');
     *text = o.data();
     *len  = o.size();
+    return GNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// EM reassignment of multi-matching reads (src/ganon/reassign.py; run by `ganon classify --multiple-matches em` on the
+// `.all` / `.rep` files, src/ganon/classify.py:76-88) from the matches kept in HBM
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int gnb_session_keep_matches(gnb_session *s, int enable)
+{
+    if (!s)
+        return fail(GNB_ERR_ARG, "null argument");
+    if (!s->in_flight.empty())
+        return fail(GNB_ERR_ARG, "gnb_session_keep_matches: batches are in flight");
+    if (enable && s->em_names.empty())
+    {
+        GNB_CUDA(cudaSetDevice(s->device));
+        GNB_TRY(s->build_em_tables());
+    }
+    s->keep_matches = enable != 0;
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double threshold, uint32_t max_iter, gnb_reassign_result *out)
+{
+    if (!s || !out)
+        return fail(GNB_ERR_ARG, "null argument");
+    if (!s->keep_matches)
+        return fail(GNB_ERR_ARG, "gnb_session_reassign: call gnb_session_keep_matches before the first batch");
+    // the report of the run: joins the workers, folds the accumulators in HBM into LevelRt::rep
+    const char *rep_text = nullptr;
+    uint64_t    rep_len  = 0;
+    GNB_TRY(gnb_session_report(s, prefix_id, &rep_text, &rep_len));
+    GNB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->slots[0]->st;
+    const size_t NG = s->em_groups(), NT = s->em_names.size();
+    s->em_one.assign(NG, "");
+    s->em_label.assign(NG, "");
+    s->em_iterations.assign(NG, 0);
+    s->em_reassigned.assign(NG, 0);
+    s->em_rep.clear();
+    DevBuf d_first, d_initial, d_weight, d_counts, d_len, d_loff, d_text, d_tmp, d_multi;
+    auto   cleanup = [&]() {
+        for (DevBuf *b : {&d_first, &d_initial, &d_weight, &d_counts, &d_len, &d_loff, &d_text, &d_tmp, &d_multi})
+            b->release();
+    };
+    int rc = [&]() -> int {
+        GNB_TRY(d_first.ensure(NT * 8 + 8));
+        GNB_TRY(d_initial.ensure(NT * 8 + 8));
+        GNB_TRY(d_weight.ensure(NT * 8 + 8));
+        GNB_TRY(d_counts.ensure(NT * 8 + 8));
+        GNB_TRY(d_multi.ensure(8));
+        std::vector<unsigned long long> first(NT), initial(NT), counts(NT);
+        for (size_t g = 0; g < NG; ++g)
+        {
+            if (NG > 1)
+                s->em_label[g] = s->levels[g].label;
+            static EmStore empty;
+            EmStore &E = (prefix_id < s->em.size() && g < s->em[prefix_id].size()) ? s->em[prefix_id][g] : empty;
+            std::vector<uint32_t> order; // targets present in the group's `.all`, in order of first appearance
+            if (E.n_reads)
+            {
+                const EmStoreDev D = E.dev();
+                GNB_CUDA(cudaMemsetAsync(d_first.p, 0xFF, NT * 8, st));
+                GNB_CUDA(cudaMemsetAsync(d_initial.p, 0, NT * 8, st));
+                launch_em_first_pos(D, E.n_matches, d_first.as<unsigned long long>(), st);
+                launch_em_initial(D, E.n_reads, d_initial.as<unsigned long long>(), st);
+                GNB_CUDA(cudaMemcpyAsync(first.data(), d_first.p, NT * 8, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaMemcpyAsync(initial.data(), d_initial.p, NT * 8, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaStreamSynchronize(st));
+                for (uint32_t t = 0; t < NT; ++t)
+                    if (first[t] != ~0ull)
+                        order.push_back(t);
+                std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; });
+                // reassign.py:94-107: total weight = reads with matches, first probabilities from the unique matches
+                const double total = (double)E.n_reads;
+                uint64_t     uniq  = 0;
+                for (uint32_t t : order)
+                    uniq += initial[t];
+                const double        denom0 = uniq ? (double)uniq : 1.0;
+                std::vector<double> prob(NT, 0.0);
+                for (uint32_t t : order)
+                    prob[t] = (double)initial[t] / denom0;
+                // the device compares integer weights: one denominator per iteration makes that the same order
+                GNB_CUDA(cudaMemcpyAsync(d_weight.p, d_initial.p, NT * 8, cudaMemcpyDeviceToDevice, st));
+                uint32_t it = 0;
+                while (true)
+                { // reassign.py:110-141
+                    GNB_CUDA(cudaMemcpyAsync(d_counts.p, d_initial.p, NT * 8, cudaMemcpyDeviceToDevice, st));
+                    launch_em_assign(D, E.n_reads, d_weight.as<unsigned long long>(), d_counts.as<unsigned long long>(), st);
+                    GNB_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, NT * 8, cudaMemcpyDeviceToHost, st));
+                    GNB_CUDA(cudaMemcpyAsync(d_weight.p, d_counts.p, NT * 8, cudaMemcpyDeviceToDevice, st));
+                    GNB_CUDA(cudaStreamSynchronize(st));
+                    double diff = 0;
+                    for (uint32_t t : order)
+                    {
+                        const double np = (double)counts[t] / total;
+                        diff += std::fabs(prob[t] - np);
+                        prob[t] = np;
+                    }
+                    if (diff <= threshold)
+                        break;
+                    if (max_iter > 0 && it == max_iter - 1)
+                        break;
+                    ++it;
+                }
+                s->em_iterations[g] = it + 1;
+                // `.one` (reassign.py:149-179): the unique match, or the top match under the final probabilities
+                GNB_TRY(d_len.ensure((E.n_reads + 1) * 8));
+                GNB_TRY(d_loff.ensure((E.n_reads + 1) * 8));
+                GNB_TRY(d_tmp.ensure(em_scan64_tmp_bytes(E.n_reads + 1)));
+                GNB_CUDA(cudaMemsetAsync(d_multi.p, 0, 8, st));
+                launch_em_one(D, E.n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(), nullptr,
+                              nullptr, d_multi.as<unsigned long long>(), st);
+                launch_scan64(d_len.as<uint64_t>(), d_loff.as<uint64_t>(), E.n_reads + 1, d_tmp.p, d_tmp.cap, st);
+                uint64_t           bytes = 0;
+                unsigned long long multi = 0;
+                GNB_CUDA(cudaMemcpyAsync(&bytes, d_loff.as<uint64_t>() + E.n_reads, 8, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaMemcpyAsync(&multi, d_multi.p, 8, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaStreamSynchronize(st));
+                s->em_reassigned[g] = multi;
+                GNB_TRY(d_text.ensure(bytes + 1));
+                launch_em_one(D, E.n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(),
+                              d_loff.as<uint64_t>(), d_text.as<char>(), nullptr, st);
+                s->em_one[g].resize(bytes);
+                if (bytes)
+                    GNB_CUDA(cudaMemcpyAsync(&s->em_one[g][0], d_text.p, bytes, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaStreamSynchronize(st));
+                GNB_CUDA(cudaGetLastError());
+            }
+            // new `.rep` rows of the group (reassign.py:188-214): the report's rows of targets present in the `.all`,
+            // lca column = redistributed count of the last iteration - unique
+            std::vector<uint8_t> present(NT, 0);
+            for (uint32_t t : order)
+                present[t] = 1;
+            for (size_t li = 0; li < s->levels.size(); ++li)
+            {
+                const LevelRt &L = s->levels[li];
+                if ((NG > 1 && li != g) || prefix_id >= L.rep.size())
+                    continue;
+                std::vector<uint32_t> nodes;
+                for (auto const &kv : L.rep[prefix_id])
+                    nodes.push_back(kv.first);
+                std::sort(nodes.begin(), nodes.end());
+                for (uint32_t node : nodes)
+                {
+                    const Rep &r = L.rep[prefix_id].at(node);
+                    if (!(r.matches || r.seqs_lca || r.seqs_unique))
+                        continue;
+                    const uint32_t t = L.em_map[node];
+                    if (!present[t])
+                        continue;
+                    std::string &o = s->em_rep;
+                    o += L.label;
+                    o.push_back('\t');
+                    o += L.node_names[node];
+                    o.push_back('\t');
+                    append_u64(o, r.matches);
+                    o.push_back('\t');
+                    append_u64(o, r.seqs_unique);
+                    o.push_back('\t');
+                    const long long lca = (long long)counts[t] - (long long)r.seqs_unique;
+                    if (lca < 0)
+                    {
+                        o.push_back('-');
+                        append_u64(o, (uint64_t)(-lca));
+                    }
+                    else
+                        append_u64(o, (uint64_t)lca);
+                    o.push_back('\t');
+                    if (L.has_tax)
+                        o += L.node_rank[node];
+                    o.push_back('\t');
+                    if (L.has_tax)
+                        o += L.node_tax_name[node];
+                    o.push_back('\n');
+                }
+            }
+        }
+        return GNB_OK;
+    }();
+    cleanup();
+    if (rc != GNB_OK)
+        return rc;
+    // the '#' lines of the report follow the rows (reassign.py:219-220)
+    {
+        const std::string rep(rep_text, rep_len);
+        size_t            pos = 0;
+        while (pos < rep.size())
+        {
+            size_t e = rep.find('\n', pos);
+            if (e == std::string::npos)
+                e = rep.size();
+            if (rep[pos] == '#')
+            {
+                s->em_rep.append(rep, pos, e - pos);
+                s->em_rep.push_back('\n');
+            }
+            pos = e + 1;
+        }
+    }
+    s->em_one_p.clear();
+    s->em_label_p.clear();
+    s->em_one_l.clear();
+    for (size_t g = 0; g < NG; ++g)
+    {
+        s->em_one_p.push_back(s->em_one[g].data());
+        s->em_one_l.push_back(s->em_one[g].size());
+        s->em_label_p.push_back(s->em_label[g].c_str());
+    }
+    out->n_groups         = (uint32_t)NG;
+    out->group_label      = s->em_label_p.data();
+    out->one_text         = s->em_one_p.data();
+    out->one_len          = s->em_one_l.data();
+    out->iterations       = s->em_iterations.data();
+    out->reassigned_reads = s->em_reassigned.data();
+    out->rep_text         = s->em_rep.data();
+    out->rep_len          = s->em_rep.size();
     return GNB_OK;
 }
 

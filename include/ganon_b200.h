@@ -246,6 +246,29 @@ int gnb_session_node_name(const gnb_session *s, uint32_t level, uint32_t node, c
 int gnb_session_report(gnb_session *s, uint32_t prefix_id, const char **text, uint64_t *len);
 int gnb_session_stats(gnb_session *s, uint32_t prefix_id, const char *prefix_name, const char **text, uint64_t *len);
 
+/* EM reassignment of reads with several matches (`ganon classify --multiple-matches em`, the default: src/ganon/
+ * classify.py:76-88 runs src/ganon/reassign.py on the `.all` / `.rep` files the binary wrote).  Here the matches of the
+ * run stay in HBM: gnb_session_keep_matches(s, 1) before the first batch makes every batch append its classified reads
+ * (ids, targets, counts) to a store on the device; gnb_session_reassign runs the iterations there (reassign.py:72-141:
+ * initial weights from unique matches, each multi-matching read to its most probable target, until the summed change of
+ * the probabilities is <= threshold or max_iter iterations; 0 = until convergence) and returns the `.one` lines
+ * (reassign.py:149-179) per EM group -- one group per hierarchy level, or a single one for one level / --output-single,
+ * as the reference finds its `.all` files (reassign.py:37-60) -- and the new `.rep` (reassign.py:188-220).
+ * Reads are told apart by position in the input, not by id (the reference merges reads that share an id). */
+typedef struct
+{
+    uint32_t           n_groups;
+    const char *const *group_label;      /* hierarchy label of the group; "" for the single group                  */
+    const char *const *one_text;         /* [n_groups] readid \t target \t count                                   */
+    const uint64_t    *one_len;
+    const uint32_t    *iterations;       /* [n_groups] iterations run                                               */
+    const uint64_t    *reassigned_reads; /* [n_groups] reads with several matches                                   */
+    const char        *rep_text;         /* new `.rep`: label, target, matches, unique, reassigned - unique, rank, name */
+    uint64_t           rep_len;
+} gnb_reassign_result;
+int gnb_session_keep_matches(gnb_session *s, int enable);
+int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double threshold, uint32_t max_iter, gnb_reassign_result *out);
+
 typedef struct
 {
     uint64_t input_seqs, seqs_processed, seqs_skipped_big, seqs_skipped_small, length_processed, kmers_processed,

@@ -304,6 +304,39 @@ def test_device_and_host_record_index_agree(golden_dbs, tmp_path, monkeypatch):
     assert res_all[0][1] == SU.expected_lines("pe_synth_all", "all")
 
 
+# ------------------------------------------------------------------------------------------------------------------ EM reassignment
+EM_SCENARIOS = ["pe_real4_all", "se_synth_all", "pe_synth_all", "pe_two_filters", "pe_three_filters", "hier_two_levels", "hier_two_levels_single", "se_synth"]
+EM_CASES = [(n, "device") for n in EM_SCENARIOS] + [(n, m) for n in ("pe_synth_all", "hier_two_levels", "hier_two_levels_single") for m in ("host", "fallback")]
+
+
+@pytest.mark.parametrize("name,mode", EM_CASES)
+def test_em_reassign_in_hbm_matches_restatement(name, mode, golden_dbs, tmp_path, monkeypatch):
+    """`--reassign-em` (matches kept in HBM, iterations on the device) against the restatement of src/ganon/reassign.py
+    (pinned to the reference module by tests/test_reassign_cpu.py) run on the `.all` / `.rep` files of the same run.
+    Single- and multi-filter levels, two hierarchy levels with split and single output files; K4 and host finishing."""
+    from oracle import reassign_oracle as RO
+
+    for k, v in FINISH_MODES[mode].items():
+        monkeypatch.setenv(k, v)
+    args = SU.expand(SU.load_scenarios()[name], golden_dbs)
+    plain = str(tmp_path / "plain")
+    assert cli.main(args + ["-o", plain, "-t", "4", "--quiet"]) == 0
+    rep = open(plain + ".rep").read()
+    have = [os.path.basename(p)[len("plain") + 1 :] for p in glob.glob(plain + ".*all")]
+    labels = RO.all_files_of(rep, have)
+    texts = {h: open(plain + ("." + h if h else "") + ".all").read() for h in labels}
+    for threshold, max_iter in [(0, 10), (0, 1), (0.05, 0)]:
+        em = str(tmp_path / ("em_%s_%s" % (threshold, max_iter)))
+        assert cli.main(args + ["-o", em, "-t", "4", "--quiet", "--reassign-em", "--em-max-iter", str(max_iter), "--em-threshold", str(threshold)]) == 0
+        ones, new_rep = RO.reassign_texts(rep, texts, threshold, max_iter)
+        assert open(em + ".rep").read() == new_rep
+        for h, one in ones.items():
+            assert open(em + ("." + h if len(ones) > 1 else "") + ".one").read() == one, h
+        for h in labels:  # the .all files of the EM run are the plain run's
+            suffix = ("." + h if h else "") + ".all"
+            assert open(em + suffix).read() == open(plain + suffix).read()
+
+
 # ------------------------------------------------------------------------------------------------------------------ HIBF
 def test_hibf_sub_ibf_counts_match_oracle(golden_dbs):
     h = formats.read_hibf(golden_dbs["synth_hibf"])
