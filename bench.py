@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--reads-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=4, help="distinct read batches cycled through the steps")
+    ap.add_argument("--em", action="store_true", help="also time the EM reassignment (SURVEY 8f.1) on the matches of the e2e batches kept in HBM, next to the CPU restatement of src/ganon/reassign.py on the same .all text")
     ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (every rank classifies the same reads on its columns; tuples all-gathered over NCCL): strong scaling")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -413,6 +414,33 @@ def main():
         e2e_ms = float(t[0])
     clocks = sampler.stop()
 
+    # ------------------------------------------------------------------ EM reassignment from the matches kept in HBM (--em)
+    em_line = None
+    if args.em and rank == 0:
+        # a looser cutoff than the classification default so that many reads have several candidate targets
+        em_sess = Session([db], [0.25], [1.0], [1.0], output_all=True, device=dev)
+        em_sess.keep_matches(True)
+        texts = []
+        for h1, h2 in host[:1]:  # one batch: the CPU leg below is pure Python
+            r = em_sess.classify(h1, h2, final=True)
+            texts.append(result_text(r, "all"))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ones, new_rep, em_info = em_sess.reassign(0, 0.0, 10)
+        em_ms = (time.perf_counter() - t0) * 1e3
+        all_text = b"".join(texts).decode()
+        n_lines = all_text.count("\n")
+        from oracle import reassign_oracle as RO  # the checker, timed as the CPU leg of this row
+
+        rep_text = em_sess.report(0).decode()
+        t0 = time.perf_counter()
+        o_ones, o_rep = RO.reassign_texts(rep_text, {"": all_text}, 0.0, 10)
+        port_s = time.perf_counter() - t0
+        em_line = {"reads_with_matches": ones[""].count(b"\n"), "match_lines": n_lines, "iterations": em_info[""][0], "reads_with_several_matches": em_info[""][1],
+                   "gpu_ms": em_ms, "cpu_port_s": port_s, "cpu_port_kind": "oracle/reassign_oracle.py (restatement of src/ganon/reassign.py, 1 thread, from the .all text)",
+                   "identical": ones[""].decode() == o_ones[""] and new_rep.decode() == o_rep, "thresholds": "rel-cutoff 0.25 rel-filter 1 fpr-query 1"}
+        em_sess.close()
+
     # ------------------------------------------------------------------ CPU baseline + parity on a bounded sample (rank 0, N=1)
     cpu = None
     parity = None
@@ -469,6 +497,8 @@ def main():
             "parity": parity,
             "setup_s": t_setup,
         }
+        if em_line is not None:
+            line["em_reassign"] = em_line
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
