@@ -49,6 +49,31 @@ inline void trace_mark(const void *ctx, const char *what)
     fprintf(stderr, "[gnb-trace] %p %-18s %9.3f ms\n", ctx, what, ms_since(t0));
 }
 
+// Host wait for a stream.  Default: cudaStreamSynchronize (spins: lowest latency).  GANON_B200_SYNC=block: wait on an
+// event created with cudaEventBlockingSync, so that the waiting thread sleeps -- several ranks per node with a few
+// threads each would otherwise keep more spinning threads than the host has cores.
+inline cudaError_t stream_wait(cudaStream_t st)
+{
+    static const bool block = [] { const char *e = getenv("GANON_B200_SYNC"); return e && e[0] == 'b'; }();
+    if (!block)
+        return cudaStreamSynchronize(st);
+    thread_local cudaEvent_t ev     = nullptr;
+    thread_local int         ev_dev = -1;
+    int                      dev    = 0;
+    cudaGetDevice(&dev);
+    if (!ev || ev_dev != dev)
+    {
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess)
+            return e;
+        ev_dev = dev;
+    }
+    cudaError_t e = cudaEventRecord(ev, st);
+    if (e != cudaSuccess)
+        return e;
+    return cudaEventSynchronize(ev);
+}
+
 struct DevBuf
 {
     void  *p   = nullptr;
@@ -1289,7 +1314,7 @@ int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records
     launches += 1;
     uint32_t nl = 0;
     GNB_CUDA(cudaMemcpyAsync(&nl, d_status.as<uint32_t>() + 8 + side, 4, cudaMemcpyDeviceToHost, st_in));
-    GNB_CUDA(cudaStreamSynchronize(st_in));
+    GNB_CUDA(stream_wait(st_in));
     (void)fin;
     n_lines   = nl;
     n_records = std::min<uint32_t>(nl / 4, kMaxReadsPerBatch - 1);
@@ -1397,7 +1422,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
                 GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st_in));
             timing.d2h_bytes += (uint64_t)n * 4 * (paired ? 4 : 3);
         }
-        GNB_CUDA(cudaStreamSynchronize(st_in));
+        GNB_CUDA(stream_wait(st_in));
         GNB_CUDA(cudaGetLastError());
         timing.d2h_bytes += 24;
         consumed1 = h_cons[0];
@@ -1546,7 +1571,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     launches += 2;
     uint64_t total_ub = 0;
     GNB_CUDA(cudaMemcpyAsync(&total_ub, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     trace_mark(this, "k2.scan_done");
     timing.d2h_bytes += 8;
     uint64_t total = 0;
@@ -1565,7 +1590,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
         GNB_CUDA(cudaEventRecord(ev[3], st));
         GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
         GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(stream_wait(st));
         d_counts_valid = true;
         trace_mark(this, "k2.done");
         total = agg.sum;
@@ -1579,7 +1604,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
         launches += 2;
         GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
         GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(stream_wait(st));
         total = agg.sum;
         mx    = agg.mx;
         GNB_TRY(d_hashes.ensure((total + 1) * 8));
@@ -1617,7 +1642,7 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     unsigned long long n_items = 0;
     GNB_CUDA(cudaMemcpyAsync(&n_items, d_seed, 8, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     timing.d2h_bytes += 8;
     unsigned long long tuples_before = 0;
     DevBuf *cur = &d_items_a, *nxt = &d_items_b;
@@ -1639,7 +1664,7 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&got_tuples, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             GNB_CUDA(cudaMemcpyAsync(&got_items, d_items_cursor.p, 8, cudaMemcpyDeviceToHost, st));
-            GNB_CUDA(cudaStreamSynchronize(st));
+            GNB_CUDA(stream_wait(st));
             GNB_CUDA(cudaGetLastError());
             timing.d2h_bytes += 16;
             float ms1 = 0;
@@ -1654,7 +1679,7 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
                 GNB_TRY(bigger.ensure(got_tuples * 8));
                 if (tuples_before)
                     GNB_CUDA(cudaMemcpyAsync(bigger.p, d_tuples_a.p, tuples_before * 8, cudaMemcpyDeviceToDevice, st));
-                GNB_CUDA(cudaStreamSynchronize(st));
+                GNB_CUDA(stream_wait(st));
                 d_tuples_a.release();
                 d_tuples_a = bigger;
             }
@@ -1670,7 +1695,7 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     {
         unsigned long long b = 0;
         GNB_CUDA(cudaMemcpyAsync(&b, d_bytes, 8, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(stream_wait(st));
         hibf_bytes = b;
     }
     produced_out = tuples_before;
@@ -1775,7 +1800,7 @@ int BatchCtx::run_level(size_t li)
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             timing.d2h_bytes += 8;
-            GNB_CUDA(cudaStreamSynchronize(st));
+            GNB_CUDA(stream_wait(st));
             trace_mark(this, "k3.done");
             GNB_CUDA(cudaGetLastError());
             {
@@ -1806,7 +1831,7 @@ int BatchCtx::run_level(size_t li)
             timing.d2h_bytes += produced * 8;
             GNB_CUDA(cudaMemcpyAsync(Ft.data(), d_tuples_b.p, produced * 8, cudaMemcpyDeviceToHost, st));
         }
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(stream_wait(st));
         trace_mark(this, "sort.done");
         float ms = 0;
         cudaEventElapsedTime(&ms, ev[6], ev[7]);
@@ -2108,7 +2133,7 @@ int BatchCtx::fetch_host_records()
         GNB_CUDA(cudaMemcpyAsync((void *)p_slen1, d_len1.p, n * 4, cudaMemcpyDeviceToHost, st));
         if (paired)
             GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(stream_wait(st));
         timing.d2h_bytes += (uint64_t)n * 4 * (paired ? 4 : 3);
     }
     host_records_valid = true;
@@ -2137,7 +2162,7 @@ int BatchCtx::to_host_state(size_t li)
         GNB_CUDA(cudaMemcpyAsync(h_read_level.data(), d_read_level.p, n, cudaMemcpyDeviceToHost, st));
         timing.d2h_bytes += 2 * n;
     }
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     active_on_device = false;
     return GNB_OK;
 }
@@ -2240,7 +2265,7 @@ int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch
     unsigned long long *h_ft  = reinterpret_cast<unsigned long long *>(h_tot + 1);
     GNB_CUDA(cudaMemcpyAsync(h_tot, d_offs.as<FinishSizes>() + n, sizeof(FinishSizes), cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaMemcpyAsync(h_ft, d_ftotals.p, kFinishTotals * 8, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     trace_mark(this, "k4.select_done");
     GNB_CUDA(cudaGetLastError());
     timing.d2h_bytes += sizeof(FinishSizes) + kFinishTotals * 8;
@@ -2290,7 +2315,7 @@ int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch
             timing.d2h_bytes += T.unc_bytes;
         }
     }
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     trace_mark(this, "k4.write_d2h_done");
     GNB_CUDA(cudaGetLastError());
     float ms = 0;
@@ -2336,7 +2361,7 @@ int BatchCtx::em_append_device(size_t li, const FinishParams &P, uint64_t n_kept
     launch_em_sizes(P.sizes, P.id_len, n, d_em_sizes.as<EmSizes>(), d_em_offs.as<EmSizes>(), d_tmp.p, d_tmp.cap, st);
     EmSizes tot{};
     GNB_CUDA(cudaMemcpyAsync(&tot, d_em_offs.as<EmSizes>() + n, sizeof(EmSizes), cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     launches += 3;
     if (tot.reads == 0)
         return GNB_OK;
@@ -2392,7 +2417,7 @@ int BatchCtx::em_append_host(size_t li, const std::vector<size_t> &off_before, c
     GNB_CUDA(cudaMemcpyAsync(E.cnt.as<uint32_t>() + E.n_matches, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, st));
     if (!ids.empty())
         GNB_CUDA(cudaMemcpyAsync(E.ids.as<char>() + E.id_bytes, ids.data(), ids.size(), cudaMemcpyHostToDevice, st));
-    GNB_CUDA(cudaStreamSynchronize(st));
+    GNB_CUDA(stream_wait(st));
     E.n_reads += off.size() - 1;
     E.n_matches += tgt.size();
     E.id_bytes += ids.size();
@@ -2705,7 +2730,7 @@ int BatchCtx::finish(uint32_t prefix_id, gnb_batch_result *out)
     if (active_on_device && n_reads)
     { // classified level of every read for the structured result
         GNB_CUDA(cudaMemcpyAsync(h_read_level.data(), d_read_level.p, n_reads, cudaMemcpyDeviceToHost, st));
-        GNB_CUDA(cudaStreamSynchronize(st));
+        GNB_CUDA(stream_wait(st));
         timing.d2h_bytes += n_reads;
     }
     return collect(prefix_id, out);
@@ -2745,7 +2770,7 @@ extern "C" int gnb_session_stage(gnb_session *s, const char *b1, uint64_t l1, co
     GNB_TRY(c.stage(b1, l1, b2, l2, fin));
     if (n_reads)
         *n_reads = c.n_reads;
-    GNB_CUDA(cudaStreamSynchronize(c.st_in));
+    GNB_CUDA(stream_wait(c.st_in));
     return GNB_OK;
 }
 
@@ -2890,7 +2915,7 @@ extern "C" int gnb_session_set_level_tuples_device(gnb_session *s, uint32_t leve
         GNB_CUDA(cudaMemcpyAsync(c.d_tuples_a.p, dev_tuples, n * 8, cudaMemcpyDeviceToDevice, c.st));
         launch_sort_tuples(c.d_tuples_a.as<uint64_t>(), c.d_tuples_b.as<uint64_t>(), n, c.d_tmp.p, c.d_tmp.cap, c.st);
         c.launches += 4;
-        GNB_CUDA(cudaStreamSynchronize(c.st));
+        GNB_CUDA(stream_wait(c.st));
         GNB_CUDA(cudaGetLastError());
     }
     c.n_tuples_dev     = n;
@@ -2924,7 +2949,7 @@ extern "C" int gnb_session_finish_level_device(gnb_session *s, uint32_t level, u
     if (level + 1 == s->levels.size() && c.active_on_device && c.n_reads)
     {
         GNB_CUDA(cudaMemcpyAsync(c.h_read_level.data(), c.d_read_level.p, c.n_reads, cudaMemcpyDeviceToHost, c.st));
-        GNB_CUDA(cudaStreamSynchronize(c.st));
+        GNB_CUDA(stream_wait(c.st));
     }
     return GNB_OK;
 }
@@ -3213,7 +3238,7 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                 launch_em_initial(D, E.n_reads, d_initial.as<unsigned long long>(), st);
                 GNB_CUDA(cudaMemcpyAsync(first.data(), d_first.p, NT * 8, cudaMemcpyDeviceToHost, st));
                 GNB_CUDA(cudaMemcpyAsync(initial.data(), d_initial.p, NT * 8, cudaMemcpyDeviceToHost, st));
-                GNB_CUDA(cudaStreamSynchronize(st));
+                GNB_CUDA(stream_wait(st));
                 for (uint32_t t = 0; t < NT; ++t)
                     if (first[t] != ~0ull)
                         order.push_back(t);
@@ -3236,7 +3261,7 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                     launch_em_assign(D, E.n_reads, d_weight.as<unsigned long long>(), d_counts.as<unsigned long long>(), st);
                     GNB_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, NT * 8, cudaMemcpyDeviceToHost, st));
                     GNB_CUDA(cudaMemcpyAsync(d_weight.p, d_counts.p, NT * 8, cudaMemcpyDeviceToDevice, st));
-                    GNB_CUDA(cudaStreamSynchronize(st));
+                    GNB_CUDA(stream_wait(st));
                     double diff = 0;
                     for (uint32_t t : order)
                     {
@@ -3263,7 +3288,7 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                 unsigned long long multi = 0;
                 GNB_CUDA(cudaMemcpyAsync(&bytes, d_loff.as<uint64_t>() + E.n_reads, 8, cudaMemcpyDeviceToHost, st));
                 GNB_CUDA(cudaMemcpyAsync(&multi, d_multi.p, 8, cudaMemcpyDeviceToHost, st));
-                GNB_CUDA(cudaStreamSynchronize(st));
+                GNB_CUDA(stream_wait(st));
                 s->em_reassigned[g] = multi;
                 GNB_TRY(d_text.ensure(bytes + 1));
                 launch_em_one(D, E.n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(),
@@ -3271,7 +3296,7 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                 s->em_one[g].resize(bytes);
                 if (bytes)
                     GNB_CUDA(cudaMemcpyAsync(&s->em_one[g][0], d_text.p, bytes, cudaMemcpyDeviceToHost, st));
-                GNB_CUDA(cudaStreamSynchronize(st));
+                GNB_CUDA(stream_wait(st));
                 GNB_CUDA(cudaGetLastError());
             }
             // new `.rep` rows of the group (reassign.py:188-214): the report's rows of targets present in the `.all`,
