@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--reads-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=4, help="distinct read batches cycled through the steps")
+    ap.add_argument("--cli", action="store_true", help="also time the drop-in command line (bin/ganon-classify) on a FASTQ file of the pool's batches and the saved database")
     ap.add_argument("--em", action="store_true", help="also time the EM reassignment (SURVEY 8f.1) on the matches of the e2e batches kept in HBM, next to the CPU restatement of src/ganon/reassign.py on the same .all text")
     ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (every rank classifies the same reads on its columns; tuples all-gathered over NCCL): strong scaling")
     args = ap.parse_args()
@@ -441,6 +442,35 @@ def main():
                    "identical": ones[""].decode() == o_ones[""] and new_rep.decode() == o_rep, "thresholds": "rel-cutoff 0.25 rel-filter 1 fpr-query 1"}
         em_sess.close()
 
+    # ------------------------------------------------------------------ the drop-in command line on files (--cli)
+    cli_line = None
+    if args.cli and rank == 0 and world == 1:
+        ibf_path = ensure_ibf_file(args.workload, db)
+        fq1 = os.path.join(CACHE, "%s_cli.1.fq" % args.workload)
+        fq2 = os.path.join(CACHE, "%s_cli.2.fq" % args.workload) if wl["paired"] else None
+        reps = 4  # the pool's batches four times over: long enough for the fixed costs (buffers, first allocations) to amortise
+        with open(fq1, "wb") as f1:
+            for _ in range(reps):
+                for b1, _b2 in blocks:
+                    b1.tofile(f1)
+        if fq2:
+            with open(fq2, "wb") as f2:
+                for _ in range(reps):
+                    for _b1, b2 in blocks:
+                        b2.tofile(f2)
+        n_cli = reps * pool * R * (2 if wl["paired"] else 1)
+        reads = ["-p", fq1 + "," + fq2] if fq2 else ["-r", fq1]
+        cmd = [sys.executable, os.path.join(ROOT, "bin", "ganon-classify")] + (["--hibf"] if wl.get("hibf") else []) + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", os.path.join(CACHE, "cli_out"), "--verbose", "--device", str(dev)]
+        t0 = time.perf_counter()
+        pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        wall = time.perf_counter() - t0
+        mc = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+        ml = re.search(r"loading filter\(s\)\s+elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+        cs = float(mc.group(1)) if mc else None
+        cli_line = {"rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
+                    "reads_per_s": n_cli / cs if cs else None, "all_bytes": os.path.getsize(os.path.join(CACHE, "cli_out.all")) if os.path.exists(os.path.join(CACHE, "cli_out.all")) else None,
+                    "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
+
     # ------------------------------------------------------------------ CPU baseline + parity on a bounded sample (rank 0, N=1)
     cpu = None
     parity = None
@@ -499,6 +529,8 @@ def main():
         }
         if em_line is not None:
             line["em_reassign"] = em_line
+        if cli_line is not None:
+            line["cli"] = cli_line
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -26,7 +26,10 @@ from . import _lib
 from ._lib import BatchResult, DbInfo, SessionConfig, Totals, check
 
 VERSION = "ganon-b200 0.1.0 (ganon-classify 2.4.1 compatible)"
-BLOCK_BYTES = int(os.environ.get("GANON_B200_BLOCK_BYTES", str(256 << 20)))
+# bytes of a read file per batch.  64 MiB (~200 k reads of 150 bp): measured on B200 with the 8 GiB workload, 33.5 M reads
+# from a 10.6 GB FASTQ take 0.73 s with 64 MiB blocks and 1.17 s with 256 MiB ones (page-locking the ring of buffers is
+# a fixed cost of ~0.5 ms per MiB, and the parallel file reads hide behind the staging only with smaller blocks)
+BLOCK_BYTES = int(os.environ.get("GANON_B200_BLOCK_BYTES", str(64 << 20)))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -499,21 +502,42 @@ class GanonClassifyConfig:
         return True
 
 
+_IO_THREADS = int(os.environ.get("GANON_B200_IO_THREADS", str(min(16, os.cpu_count() or 8))))
+_IO_SLICE = 4 << 20
+_HEADROOM = 1 << 20
+
+
 class _ReadStream:
-    """A read file (plain or gzip, by magic) consumed in blocks.  Blocks live in a ring of page-locked buffers (a block
-    must stay untouched while its batch is in flight); the unconsumed tail of a block is copied to the next one."""
+    """A read file (plain or gzip, by magic) consumed in blocks (reader of GC.cpp:1220-1287).
+
+    Blocks live in a ring of page-locked buffers (a block must stay untouched while its batch is in flight).  Every
+    buffer has a headroom in front of the file bytes: the unconsumed tail of the previous block (less than one record) is
+    copied right-aligned into it, so the file bytes themselves never move and the NEXT buffer can be filled while the
+    current block is being staged.  Plain files are read with parallel preads (page-cache copies are what bounds a
+    single reader thread); gzip files are inflated by the prefetch thread (zlib releases the GIL)."""
 
     def __init__(self, path: str, block_bytes: int, n_buffers: int):
+        from concurrent.futures import ThreadPoolExecutor
+
         with open(path, "rb") as f:
             magic = f.read(2)
-        self.f = gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb", buffering=0)
-        self.bufs = [bytearray(block_bytes) for _ in range(n_buffers)]
+        self.gz = magic == b"\x1f\x8b"
+        self.f = gzip.open(path, "rb") if self.gz else open(path, "rb", buffering=0)
+        self.size = None if self.gz else os.fstat(self.f.fileno()).st_size
+        self.pos = 0  # plain files: next file offset to read
+        self.block_bytes = block_bytes
+        self.head = _HEADROOM
+        self.bufs = [bytearray(self.head + block_bytes) for _ in range(n_buffers)]
         self.pinned = []
         self._pin()
+        self.pool = ThreadPoolExecutor(max_workers=max(1, _IO_THREADS))
         self.cur = -1
-        self.fill = 0
+        self.fill = 0  # bytes of the current block (tail + fresh)
+        self.start = 0  # offset of the current block inside its buffer
         self.tail = b""
         self.eof = False
+        self._raw_eof = False
+        self._next = None  # (buffer index, future -> fresh byte count)
 
     def _pin(self) -> None:
         for b in self.bufs:
@@ -529,37 +553,139 @@ class _ReadStream:
         self.pinned = []
 
     @property
-    def buf(self) -> bytearray:
-        return self.bufs[self.cur]
+    def buf(self):
+        """(address, length)-style view of the current block for Session.submit."""
+        b = self.bufs[self.cur]
+        arr = (C.c_char * len(b)).from_buffer(b)
+        return (C.addressof(arr) + self.start, self.fill)
+
+    def block_bytes_view(self) -> memoryview:
+        return memoryview(self.bufs[self.cur])[self.start : self.start + self.fill]
+
+    def _read_fresh(self, idx: int) -> int:
+        """Fill bufs[idx][head : head + block_bytes] from the file; returns the byte count (runs in the pool)."""
+        buf = self.bufs[idx]
+        mv = memoryview(buf)
+        try:
+            if self.gz:
+                got_total = 0
+                while got_total < self.block_bytes:
+                    got = self.f.readinto(mv[self.head + got_total : self.head + self.block_bytes])
+                    if not got:
+                        self._raw_eof = True
+                        break
+                    got_total += got
+                return got_total
+            want = min(self.block_bytes, self.size - self.pos)
+            if want <= 0:
+                self._raw_eof = True
+                return 0
+            fd, base, off0 = self.f.fileno(), self.head, self.pos
+            futs = []
+            for o in range(0, want, _IO_SLICE):
+                n = min(_IO_SLICE, want - o)
+                futs.append(self.pool.submit(self._pread, fd, mv[base + o : base + o + n], off0 + o))
+            for fu in futs:
+                fu.result()
+            self.pos += want
+            if self.pos >= self.size:
+                self._raw_eof = True
+            return want
+        finally:
+            mv.release()
+
+    @staticmethod
+    def _pread(fd: int, view: memoryview, offset: int) -> None:
+        done = 0
+        while done < len(view):
+            got = os.preadv(fd, [view[done:]], offset + done)
+            if got <= 0:
+                raise IOError("short read")
+            done += got
+
+    def _schedule(self, idx: int) -> None:
+        import threading
+
+        box = {}
+
+        def work():
+            try:
+                box["n"] = self._read_fresh(idx)
+            except BaseException as e:  # surfaced by next_block
+                box["err"] = e
+
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+        self._next = (idx, t, box)
 
     def next_block(self) -> None:
-        """Move to the next ring buffer: tail of the previous block first, then fresh bytes from the file."""
-        self.cur = (self.cur + 1) % len(self.bufs)
-        buf = self.bufs[self.cur]
+        """Move to the next ring buffer: its file bytes were prefetched; the tail of the previous block goes in front."""
+        idx = (self.cur + 1) % len(self.bufs)
+        if self._next is None or self._next[0] != idx:
+            if not self._raw_eof:
+                self._schedule(idx)
+        fresh = 0
+        if self._next is not None and self._next[0] == idx:
+            _i, t, box = self._next
+            t.join()
+            self._next = None
+            if "err" in box:
+                raise box["err"]
+            fresh = box["n"]
+        self.cur = idx
+        buf = self.bufs[idx]
         n = len(self.tail)
-        buf[:n] = self.tail
-        self.fill = n
-        mv = memoryview(buf)
-        while self.fill < len(buf) and not self.eof:
-            got = self.f.readinto(mv[self.fill :])
-            if not got:
-                self.eof = True
-            else:
-                self.fill += got
-        mv.release()
+        if n > self.head:
+            # a tail longer than the headroom (a record of more than 1 MiB): rebuild the buffers with more room in front
+            self._wait_idle()
+            data = bytes(self.tail) + bytes(buf[self.head : self.head + fresh])
+            self._unpin()
+            self.head = 2 * n
+            self.bufs = [bytearray(self.head + max(self.block_bytes, len(data))) for _ in self.bufs]
+            self._pin()
+            self.cur = 0
+            buf = self.bufs[0]
+            buf[self.head - n : self.head - n + len(data)] = data
+        else:
+            buf[self.head - n : self.head] = self.tail
+        self.start = self.head - n
+        self.fill = n + fresh
+        self.tail = b""
+        self.eof = self._raw_eof
+        if not self._raw_eof:
+            self._schedule((self.cur + 1) % len(self.bufs))  # overlaps with the staging of this block
+
+    def _wait_idle(self) -> None:
+        if self._next is not None:
+            self._next[1].join()
 
     def consume(self, n: int) -> None:
-        self.tail = bytes(self.buf[n : self.fill])
+        b = self.bufs[self.cur]
+        self.tail = bytes(b[self.start + n : self.start + self.fill])
+
+    def whole_block_to_tail(self) -> None:
+        self.consume(0)
 
     def grow(self) -> None:
-        """Not a single complete record fitted: double the block size (the whole block becomes the tail)."""
+        """Not a single complete record fitted: double the block size (the whole block became the tail)."""
+        self._wait_idle()
+        pending = None
+        if self._next is not None:
+            _i, _t, box = self._next
+            pending = bytes(self.bufs[self._next[0]][self.head : self.head + box.get("n", 0)])
+            self._next = None
+        if pending:
+            self.tail = self.tail + pending  # bytes already taken from the file stay in order
         self._unpin()
-        size = 2 * len(self.bufs[0])
-        self.bufs = [bytearray(size) for _ in self.bufs]
+        self.block_bytes *= 2
+        self.head = max(self.head, 2 * len(self.tail))
+        self.bufs = [bytearray(self.head + self.block_bytes) for _ in self.bufs]
         self._pin()
         self.cur = -1
 
     def close(self) -> None:
+        self._wait_idle()
+        self.pool.shutdown(wait=True)
         self.f.close()
         self._unpin()
 
@@ -661,42 +787,74 @@ def run(cfg: GanonClassifyConfig) -> bool:
     out_all = level_files("all") if cfg.output_all else {}
     out_one = level_files("one") if write_one else {}
 
+    # writer thread (the reference has one per output kind, GC.cpp:1289-1322): the text of a batch is copied out of the
+    # library's result buffers (valid until the next collect) and written while the next batches are staged
+    import queue
+    import threading
+
+    wq: "queue.Queue" = queue.Queue(maxsize=16)
+    werr: List[BaseException] = []
+
+    def writer() -> None:
+        while True:
+            item = wq.get()
+            if item is None:
+                return
+            try:
+                item[0].write(item[1])
+            except BaseException as e:  # reported after the run
+                werr.append(e)
+
+    wthread = threading.Thread(target=writer, daemon=True)
+    wthread.start()
+
     def write_result(prefix: str, res: BatchResult) -> None:
         for li in range(len(labels)):
             if cfg.output_all and res.all_len[li]:
-                out_all[prefix][li].write(C.string_at(res.all_text[li], res.all_len[li]))
+                wq.put((out_all[prefix][li], C.string_at(res.all_text[li], res.all_len[li])))
             if write_one and res.one_len[li]:
-                out_one[prefix][li].write(C.string_at(res.one_text[li], res.one_len[li]))
+                wq.put((out_one[prefix][li], C.string_at(res.one_text[li], res.one_len[li])))
         if cfg.output_unclassified and res.unc_len:
-            out_unc[prefix].write(C.string_at(res.unc_text, res.unc_len))
+            wq.put((out_unc[prefix], C.string_at(res.unc_text, res.unc_len)))
 
     t_class = time.time()
     _n, capacity = sess.in_flight()
     pending: List[str] = []  # prefixes of the batches in flight, oldest first
+    prof = {"open": 0.0, "read_wait": 0.0, "submit": 0.0, "collect": 0.0, "blocks": 0}
     for pid, prefix in enumerate(prefixes):
         for file1, file2 in reads_config[prefix]:
+            tp = time.time()
             s1 = _ReadStream(file1, BLOCK_BYTES, capacity + 2)
             s2 = _ReadStream(file2, BLOCK_BYTES, capacity + 2) if file2 else None
+            prof["open"] += time.time() - tp
             try:
                 while True:
+                    tp = time.time()
                     s1.next_block()
                     if s2:
                         s2.next_block()
+                    prof["read_wait"] += time.time() - tp
+                    prof["blocks"] += 1
                     final = s1.eof and (s2 is None or s2.eof)
                     if s1.fill == 0 or (s2 is not None and s2.fill == 0):
                         break  # nothing (more) to pair
-                    info = sess.submit(s1.buf, s2.buf if s2 else None, final=final, prefix_id=pid, len1=s1.fill, len2=s2.fill if s2 else 0)
+                    tp = time.time()
+                    info = sess.submit(s1.buf, s2.buf if s2 else None, final=final, prefix_id=pid)
+                    prof["submit"] += time.time() - tp
                     pending.append(prefix)
                     if len(pending) > capacity - 1 or info.parse_error or final or info.n_reads == 0:
                         while len(pending) > (0 if (info.parse_error or final or info.n_reads == 0) else capacity - 1):
-                            write_result(pending.pop(0), sess.collect())
+                            tp = time.time()
+                            res_ = sess.collect()
+                            prof["collect"] += time.time() - tp
+                            write_result(pending.pop(0), res_)
                     if info.parse_error:
                         break  # rest of the file is skipped (GC.cpp:1278-1283)
                     if info.n_reads == 0 and not final:
-                        s1.tail = bytes(s1.buf[: s1.fill])
+                        s1.whole_block_to_tail()
                         s1.grow()
                         if s2:
-                            s2.tail = bytes(s2.buf[: s2.fill])
+                            s2.whole_block_to_tail()
                             s2.grow()
                         continue
                     s1.consume(info.consumed1)
@@ -710,6 +868,11 @@ def run(cfg: GanonClassifyConfig) -> bool:
                 s1.close()
                 if s2:
                     s2.close()
+    wq.put(None)
+    wthread.join()
+    if werr:
+        print("ERROR: writing output files (%s)" % werr[0], file=sys.stderr)
+        return False
     t_class = time.time() - t_class
 
     for pid, prefix in enumerate(prefixes):
@@ -735,6 +898,8 @@ def run(cfg: GanonClassifyConfig) -> bool:
                 seen.add(id(fh))
                 fh.close()
 
+    if cfg.verbose and not cfg.quiet:
+        print("host pipeline (s): open+pin %.3f, waiting for file blocks %.3f, staging (H2D + record index) %.3f, waiting for results %.3f; %d blocks of <= %d MiB" % (prof["open"], prof["read_wait"], prof["submit"], prof["collect"], prof["blocks"], BLOCK_BYTES >> 20), file=sys.stderr)
     if not cfg.quiet:
         _print_stats(cfg, sess, prefixes, labels, t_class, t_load, time.time() - t_start)
     sess.close()
