@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import gzip
+import zlib
 import os
 import sys
 import time
@@ -502,6 +503,81 @@ class GanonClassifyConfig:
         return True
 
 
+class _BgzfReader:
+    """Blocked gzip (BGZF: what bcl2fastq / BCL Convert, bgzip and htslib write): every <= 64 KiB block is an independent
+    gzip member whose compressed size sits in a 'BC' extra field and whose inflated size in the trailer, so the blocks
+    of a chunk are inflated in parallel (zlib releases the GIL) straight to their places in the output buffer.  A plain
+    single-member .gz has no such structure and stays on one thread (gzip module)."""
+
+    CHUNK = 8 << 20  # compressed bytes looked at per readinto round
+
+    def __init__(self, path: str, pool):
+        self.f = open(path, "rb", buffering=0)
+        self.size = os.fstat(self.f.fileno()).st_size
+        self.pos = 0
+        self.pool = pool
+        self.carry = b""  # inflated bytes that did not fit the caller's buffer
+
+    @staticmethod
+    def is_bgzf(path: str) -> bool:
+        with open(path, "rb") as f:
+            h = f.read(18)
+        return len(h) == 18 and h[:4] == b"\x1f\x8b\x08\x04" and h[10:12] == b"\x06\x00" and h[12:14] == b"BC" and h[14:16] == b"\x02\x00"
+
+    @staticmethod
+    def _inflate(raw: bytes, a: int, b: int) -> bytes:
+        # block = 18-byte header (FEXTRA with the BC subfield first, as every BGZF writer emits), deflate data, CRC32, ISIZE
+        xlen = raw[a + 10] | (raw[a + 11] << 8)
+        return zlib.decompress(raw[a + 12 + xlen : b - 8], wbits=-15)
+
+    def readinto(self, mv) -> int:
+        room = len(mv)
+        done = 0
+        if self.carry:
+            n = min(room, len(self.carry))
+            mv[:n] = self.carry[:n]
+            self.carry = self.carry[n:]
+            done = n
+            if done == room:
+                return done
+        while done < room and self.pos < self.size:
+            raw = os.pread(self.f.fileno(), min(self.CHUNK, self.size - self.pos), self.pos)
+            # block boundaries of the chunk
+            spans, a, out = [], 0, 0
+            while a + 18 <= len(raw):
+                if raw[a : a + 4] != b"\x1f\x8b\x08\x04" or raw[a + 12 : a + 14] != b"BC":
+                    raise IOError("not a BGZF block at offset %d" % (self.pos + a))
+                bsize = (raw[a + 16] | (raw[a + 17] << 8)) + 1
+                if a + bsize > len(raw):
+                    break
+                isize = int.from_bytes(raw[a + bsize - 4 : a + bsize], "little")
+                if spans and out + isize > room - done:
+                    break  # the caller's buffer is full: the rest of the chunk is looked at again next time
+                spans.append((a, a + bsize, out, isize))
+                out += isize
+                a += bsize
+            if not spans:
+                raise IOError("truncated BGZF block at offset %d" % self.pos)
+            self.pos += a
+            # groups of blocks per task keep the per-task overhead small
+            step = max(1, len(spans) // (4 * 16) + 1)
+            groups = [spans[i : i + step] for i in range(0, len(spans), step)]
+
+            def work(g):
+                return b"".join(self._inflate(raw, x, y) for x, y, _o, _n in g)
+
+            for g, data in zip(groups, self.pool.map(work, groups)):
+                n = min(len(data), room - done)
+                mv[done : done + n] = data[:n]
+                done += n
+                if n < len(data):
+                    self.carry += data[n:]
+        return done
+
+    def close(self) -> None:
+        self.f.close()
+
+
 _IO_THREADS = int(os.environ.get("GANON_B200_IO_THREADS", str(min(16, os.cpu_count() or 8))))
 _IO_SLICE = 4 << 20
 _HEADROOM = 1 << 20
@@ -522,7 +598,11 @@ class _ReadStream:
         with open(path, "rb") as f:
             magic = f.read(2)
         self.gz = magic == b"\x1f\x8b"
-        self.f = gzip.open(path, "rb") if self.gz else open(path, "rb", buffering=0)
+        self.pool = ThreadPoolExecutor(max_workers=max(1, _IO_THREADS))
+        if self.gz and _BgzfReader.is_bgzf(path):
+            self.f = _BgzfReader(path, self.pool)
+        else:
+            self.f = gzip.open(path, "rb") if self.gz else open(path, "rb", buffering=0)
         self.size = None if self.gz else os.fstat(self.f.fileno()).st_size
         self.pos = 0  # plain files: next file offset to read
         self.block_bytes = block_bytes
@@ -530,7 +610,6 @@ class _ReadStream:
         self.bufs = [bytearray(self.head + block_bytes) for _ in range(n_buffers)]
         self.pinned = []
         self._pin()
-        self.pool = ThreadPoolExecutor(max_workers=max(1, _IO_THREADS))
         self.cur = -1
         self.fill = 0  # bytes of the current block (tail + fresh)
         self.start = 0  # offset of the current block inside its buffer

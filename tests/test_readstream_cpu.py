@@ -78,3 +78,46 @@ def test_missing_final_newline_and_empty_tail(tmp_path):
     finally:
         s.close()
     assert got == data
+
+
+def _bgzf(data: bytes, rng) -> bytes:
+    """BGZF as bgzip writes it: gzip members of <= 64 KiB with the BC extra field, then the empty EOF block."""
+    import struct
+    import zlib
+
+    out, pos = [], 0
+    while pos <= len(data):
+        n = int(rng.integers(1, 65000)) if pos < len(data) else 0
+        chunk = data[pos : pos + n]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 18 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + body + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        if pos == len(data):
+            break
+        pos += n
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("block", [3000, 100000, 1 << 20])
+def test_bgzf_blocks_are_inflated_in_parallel_and_in_order(tmp_path, monkeypatch, block):
+    rng = np.random.default_rng(block)
+    data = b"".join(_fastq(3000, rng))
+    raw = _bgzf(data, rng)
+    p = str(tmp_path / "r.fq.gz")
+    open(p, "wb").write(raw)
+    assert gzip.open(p, "rb").read() == data  # a valid multi-member gzip for everyone else
+    assert K._BgzfReader.is_bgzf(p)
+    monkeypatch.setattr(K._BgzfReader, "CHUNK", 150000)
+    s = K._ReadStream(p, block, 5)
+    assert isinstance(s.f, K._BgzfReader)
+    try:
+        got, _ = _consume(s, 3000)
+    finally:
+        s.close()
+    assert got == data
+    # a plain .gz keeps the gzip module
+    q = str(tmp_path / "plain.fq.gz")
+    with gzip.open(q, "wb") as f:
+        f.write(data[:5000])
+    assert not K._BgzfReader.is_bgzf(q)
