@@ -46,3 +46,39 @@ def test_fastq_block_and_reads():
     assert recs[0] == b"@r000000005/1" and recs[1] == m1[0].tobytes() and recs[2] == b"+" and recs[3] == b"I" * 150
     assert len(recs) == 401 and recs[-1] == b""
     reads = O.parse_reads.__wrapped__ if hasattr(O.parse_reads, "__wrapped__") else None  # noqa: F841
+
+
+def test_bench_hibf_layout_is_a_consistent_tree():
+    """The synthetic 3-level HIBF of bench.py (workload c4): tables in the raptor layout, every user bin reachable from
+    the top level through merged bins, chains list the bins that must hold a user bin's content."""
+    import bench
+
+    wl = dict(bench.WORKLOADS["c4tiny"])
+    bins, rows, nxt, pos, chains = bench.hibf_layout(wl)
+    n_ibf = len(bins)
+    assert n_ibf == 1 + 256 + 256 * wl["child_merged"] and bins[0] == wl["top_bins"]
+    assert sum(b * r for b, r in zip(bins, rows)) // 8 == (wl["top_bins"] * wl["top_rows"] + 256 * wl["child_bins"] * wl["child_rows"] + 1024 * wl["grand_bins"] * wl["grand_rows"]) // 8
+    seen_users, seen_ibfs = set(), {0}
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        assert len(nxt[i]) == len(pos[i]) == bins[i]
+        for b in range(bins[i]):
+            if pos[i][b] < 0:
+                c = nxt[i][b]
+                assert c not in seen_ibfs and 0 < c < n_ibf
+                seen_ibfs.add(c)
+                stack.append(c)
+            else:
+                assert nxt[i][b] == i
+                seen_users.add(pos[i][b])
+    assert seen_ibfs == set(range(n_ibf)) and seen_users == set(range(len(chains)))
+    for u, chain in enumerate(chains):
+        leaf, leaf_bins = chain[0]
+        assert all(pos[leaf][b] == u for b in leaf_bins)
+        child = leaf
+        for parent, pb in chain[1:]:  # the merged bins above point down the chain
+            assert len(pb) == 1 and pos[parent][pb[0]] < 0 and nxt[parent][pb[0]] == child
+            child = parent
+        assert child == 0
+    assert any(len(c[0][1]) == 2 for c in chains)  # split user bins exist
