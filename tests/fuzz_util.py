@@ -173,6 +173,85 @@ def run_case(seed, tmp):
     return ok, desc + (" all=%d unc=%d" % (len(want_all), len(want_unc)))
 
 
+def make_hibf(rng, path, k, w):
+    """A random HIBF in the raptor layout: up to 3 levels, sub-IBFs of 1..200 bins, merged bins, user bins split over
+    1..4 technical bins (also across 64-bin words), names that go through the reference's mangling (GC.cpp:916-928)."""
+    hf = rng.randint(1, 5)
+    ibfs, nxt, pos, genomes, bin_path = [], [], [], [], []
+
+    def user_bin():
+        u = len(genomes)
+        genomes.append(_seq(rng, rng.choice((200, 400, 900))))
+        name = ["GCF_%06d|||%d" % (u, rng.randrange(9)), "s__Sp---nr---%d" % u, "plain%d" % u][u % 3]
+        bin_path.append(["/x/y/%s.minimiser" % name] + (["/x/extra%d.fa" % u] if rng.random() < 0.2 else []))
+        return u
+
+    def make_ibf(depth, n_bins, bin_size):
+        idx = len(ibfs)
+        ibfs.append(None)
+        nxt.append(None)
+        pos.append(None)
+        o = O.OracleIBF(n_bins, bin_size, hf)
+        my_nxt, my_pos, contained = [idx] * n_bins, [0] * n_bins, []
+        b = 0
+        while b < n_bins:
+            if depth < 2 and rng.random() < (0.12 if depth == 0 else 0.06) and len(ibfs) < 12:
+                child, hs = make_ibf(depth + 1, rng.choice((1, 5, 20, 64, 70, 130)), rng.choice((1009, 4099, 20011)))
+                for h in hs:
+                    o.emplace(int(h), b)
+                my_nxt[b], my_pos[b] = child, -1
+                contained.extend(hs)
+                b += 1
+            else:
+                nb = min(rng.choice((1, 1, 1, 2, 3, 4)), n_bins - b)
+                u = user_bin()
+                hs = sorted(set(int(x) for x in O.minimiser_hash(genomes[u], k, w)))
+                for i, h in enumerate(hs):
+                    o.emplace(h, b + i % nb)
+                for j in range(nb):
+                    my_pos[b + j] = u
+                contained.extend(hs)
+                b += nb
+        ibfs[idx] = formats.IBF(n_bins, bin_size, hf, o.data.copy())
+        nxt[idx], pos[idx] = my_nxt, my_pos
+        return idx, contained
+
+    make_ibf(0, rng.choice((3, 40, 64, 66, 130)), rng.choice((4099, 20011, 65537)))
+    db = formats.HIBFFile(w, k, ibfs, nxt, ["f%d" % i for i in range(len(genomes))], pos, bin_path, fpr=rng.choice((0.05, 0.01, 0.3)))
+    formats.write_hibf(path, db)
+    return db, {i: g for i, g in enumerate(genomes)}
+
+
+def run_hibf_case(seed, tmp):
+    """`ganon-classify --hibf` against the oracle's HIBF traversal on one random case: (ok, description)."""
+    rng = random.Random(seed)
+    k = rng.choice((12, 19, 19, 21, 31))
+    w = k + rng.choice((0, 4, 12))
+    path = os.path.join(tmp, "h%d.hibf" % seed)
+    db, genomes = make_hibf(rng, path, k, w)
+    cut, relf, fprq = rng.choice((0.0, 0.05, 0.3, 0.75)), rng.choice((0.0, 0.2, 1.0)), rng.choice((1.0, 0.5, 1e-3))
+    reads1 = make_reads(rng, genomes, 100, w)
+    f1 = os.path.join(tmp, "h%d.fq" % seed)
+    write_fastq(f1, reads1)
+    out = os.path.join(tmp, "h%d_ref" % seed)
+    pr = subprocess.run([REF_BIN, "--hibf", "-r", f1, "-i", path, "-c", str(cut), "-d", str(relf), "-f", str(fprq), "-a", "-u", "-o", out, "-t", "2", "--quiet"],
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    desc = "hibf seed %d k=%d w=%d ibfs=%d user bins=%d cut=%s relf=%s fprq=%s" % (seed, k, w, len(db.ibfs), len(genomes), cut, relf, fprq)
+    if pr.returncode != 0:
+        return False, desc + " reference failed: " + pr.stderr[-200:]
+    oh = O.OracleHIBF([O.OracleIBF(i.bins, i.bin_size, i.hash_funs, i.data) for i in db.ibfs], db.next_ibf_id, db.bin_to_user, len(db.bin_path))
+    tmap = {}
+    for u, paths in enumerate(db.bin_path):
+        for p_ in paths:
+            tmap.setdefault(formats.hibf_target_name(p_), []).append(u)
+    targets = list(tmap)
+    filt = O.OracleFilter(oh, targets, [tmap[t] for t in targets], [db.fpr] * len(targets), cut, k, w)
+    res = O.classify_level([filt], [(a[0], a[1], None) for a in reads1], relf, fprq)
+    want_all, want_unc = read_sorted(out + ".all"), read_sorted(out + ".unc")
+    ok = O.all_lines(res) == want_all and sorted(r["id"].decode() for r in res if not r["matches"]) == want_unc
+    return ok, desc + (" all=%d unc=%d" % (len(want_all), len(want_unc)))
+
+
 if __name__ == "__main__":
     import tempfile
 
@@ -181,7 +260,7 @@ if __name__ == "__main__":
     bad = 0
     with tempfile.TemporaryDirectory() as tmp:
         for seed in range(first, first + n):
-            ok, desc = run_case(seed, tmp)
+            ok, desc = (run_hibf_case if os.environ.get("FUZZ_HIBF") else run_case)(seed, tmp)
             if not ok:
                 bad += 1
                 print("MISMATCH", desc)

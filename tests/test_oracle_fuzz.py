@@ -16,6 +16,13 @@ def test_oracle_matches_reference_on_random_cases(seed, tmp_path):
     assert ok, desc
 
 
+@pytest.mark.skipif(not os.path.exists(F.REF_BIN), reason="oracle/_ref/ganon-classify is not built")
+@pytest.mark.parametrize("seed", range(500, 505))
+def test_oracle_hibf_matches_reference_on_random_cases(seed, tmp_path):
+    ok, desc = F.run_hibf_case(seed, str(tmp_path))
+    assert ok, desc
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(200, 216))
 def test_dropin_matches_oracle_on_random_cases(seed, tmp_path):
