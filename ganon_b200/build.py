@@ -8,9 +8,13 @@ reference's (pinned against the reference binary by tests/test_build_config_cpu.
 """
 from __future__ import annotations
 
+import gzip
 import math
-from dataclasses import dataclass
-from typing import Dict, Iterable, List, Optional, Tuple
+import os
+import sys
+import time
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 MIB_BITS = 8388608  # bits per "megabyte" of --filter-size
 
@@ -106,6 +110,8 @@ def choose_ibf_params(hashes_count: Dict[str, int], max_fp: float = 0.05, filter
     (filter size or false positive) and (number of bins), each relative to its minimum over the simulations."""
     counts = list(hashes_count.values())
     largest = max(counts) if counts else 0
+    if largest == 0:
+        return IBFParams()
     sims: List[Tuple[int, int, int, float]] = []  # (n_hashes, n_bins, filter_size_bits, fp)
     min_filter = min_bins = 0
     min_fp = 1.0
@@ -188,3 +194,249 @@ def bin_layout(hashes_count: Dict[str, int], params: IBFParams) -> List[Tuple[st
                 break
             out.append((target, first, min(first + per_bin, count) - 1))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# `ganon-build` (GanonBuild::run, GanonBuild.cpp:752-923): input table -> minimisers per target -> parameters -> filter
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class GanonBuildConfig:
+    """Field for field GanonBuild::Config (src/ganon-build/include/ganon-build/Config.hpp:14-31)."""
+
+    input_file: str = ""
+    output_file: str = ""
+    tmp_output_folder: str = ""
+    max_fp: float = 0.05
+    filter_size: float = 0.0
+    kmer_size: int = 19
+    window_size: int = 31
+    hash_functions: int = 0
+    mode: str = "avg"
+    min_length: int = 0
+    threads: int = 1
+    verbose: bool = False
+    quiet: bool = False
+    device: int = 0  # not in the reference
+
+    def _err(self, msg: str) -> bool:
+        if not self.quiet:
+            print(msg, file=sys.stderr)
+        return False
+
+    def validate(self) -> bool:
+        """Config::validate (Config.hpp:33-107): same checks, same messages."""
+        if not self.input_file:
+            return self._err("--input-file is mandatory")
+        if not os.path.exists(self.input_file):
+            return self._err("--input-file not found: " + self.input_file)
+        if os.path.getsize(self.input_file) == 0:
+            return self._err("--input-file is empty: " + self.input_file)
+        if not self.output_file:
+            return self._err("--output-file is mandatory")
+        if self.tmp_output_folder and not os.path.exists(self.tmp_output_folder):
+            return self._err("--tmp-output-folder not found")
+        if self.hash_functions > 5:
+            return self._err("--hash-functions must be <=5")
+        if self.filter_size == 0 and self.max_fp == 0:
+            return self._err("--max-fp or --filter-size is mandatory")
+        if self.filter_size > 0:
+            self.max_fp = 0
+        if self.window_size < self.kmer_size:
+            return self._err("--window-size has to be >= --kmer-size")
+        if self.mode not in ("avg", "smaller", "smallest", "faster", "fastest"):
+            return self._err("Invalid --mode")
+        if self.kmer_size > 32:
+            return self._err("--kmer-size has to be <= 32")
+        return True
+
+
+def parse_input_table(path: str, quiet: bool = False) -> Tuple[Dict[str, List[str]], int]:
+    """`parse_input_file` (GanonBuild.cpp:86-137): tab-separated `file [<tab> target]`; the target defaults to the file
+    name.  Returns ({target: [files]}, number of missing / empty files).  Targets keep the order of first appearance
+    (the reference keeps them in a hash map; the order only decides which bins a target gets)."""
+    targets: Dict[str, List[str]] = {}
+    invalid = 0
+    with open(path) as fh:
+        for line in fh.read().split("\n"):
+            if not line:
+                continue
+            fields = line.split("\t")
+            f = fields[0]
+            if not os.path.exists(f) or os.path.getsize(f) == 0:
+                if not quiet:
+                    print("WARNING: input file not found/empty: " + f, file=sys.stderr)
+                invalid += 1
+                continue
+            if len(fields) == 1:
+                targets.setdefault(os.path.basename(f), []).append(f)
+            elif len(fields) == 2:
+                targets.setdefault(fields[1], []).append(f)
+    return targets, invalid
+
+
+def read_sequences(path: str) -> List[bytes]:
+    """Sequences of a FASTA / FASTQ file, plain or gzip (what seqan3::sequence_file_input yields to count_hashes,
+    GanonBuild.cpp:205-226; whitespace inside FASTA sequences is skipped)."""
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    data = gzip.open(path, "rb").read() if magic == b"\x1f\x8b" else open(path, "rb").read()
+    out: List[bytes] = []
+    if data[:1] == b">":
+        for rec in data.split(b"\n>"):
+            nl = rec.find(b"\n")
+            if nl < 0:
+                continue
+            out.append(rec[nl + 1 :].replace(b"\n", b"").replace(b"\r", b"").replace(b" ", b""))
+    elif data[:1] == b"@":
+        lines = data.split(b"\n")
+        for i in range(1, len(lines), 4):
+            out.append(lines[i].rstrip(b"\r"))
+    return out
+
+
+class GpuBackend:
+    """The device side of the build: K2 over the sequences of a target, filter creation and insertion in HBM."""
+
+    def __init__(self, device: int = 0):
+        from . import classify as _c
+
+        self._c = _c
+        self.device = device
+        self.db = None
+
+    def minimisers(self, seqs: Sequence[bytes], k: int, w: int):
+        import numpy as np
+
+        if not seqs:
+            return np.empty(0, dtype=np.uint64)
+        _off, hashes = self._c.minimisers_batch(list(seqs), k, w, device=self.device)
+        return hashes
+
+    def create(self, n_bins: int, bin_size_bits: int, hash_functions: int, k: int, w: int) -> None:
+        self.db = self._c.Database.create(n_bins, bin_size_bits, hash_functions, k, w, device=self.device)
+
+    def emplace(self, hashes, bins) -> None:
+        self.db.emplace(hashes, bins)
+
+    def words(self):
+        i = self.db.info()
+        return self.db.read_words(0, i.bin_size_bits * i.bin_words)
+
+    def close(self) -> None:
+        if self.db is not None:
+            self.db.close()
+
+
+def run_build(cfg: GanonBuildConfig, backend=None) -> bool:
+    """GanonBuild::run.  Deterministic where the reference is not: targets are laid out in order of first appearance in
+    the input table and a target's distinct minimisers in increasing order, so equal inputs give equal files."""
+    import numpy as np
+
+    from . import formats
+
+    if not cfg.validate():
+        return False
+    t0 = time.time()
+    targets, invalid = parse_input_table(cfg.input_file, cfg.quiet)
+    if not targets:
+        print("No valid input files", file=sys.stderr)
+        return False
+    own = backend is None
+    be = backend or GpuBackend(cfg.device)
+    try:
+        # count_hashes (GanonBuild.cpp:184-249): distinct minimisers per target over all its files and sequences
+        hashes: Dict[str, "np.ndarray"] = {}
+        n_seq = n_skipped = n_bp = 0
+        for target, files in targets.items():
+            parts = []
+            for f in files:
+                seqs = []
+                for s in read_sequences(f):
+                    if len(s) < cfg.min_length:
+                        n_skipped += 1
+                        continue
+                    n_seq += 1
+                    n_bp += len(s)
+                    seqs.append(s)
+                parts.append(np.unique(be.minimisers(seqs, cfg.kmer_size, cfg.window_size)))
+            # the reference counts per file and adds up (a hash shared by two files of a target counts twice) and appends
+            # every file's set to the target's .min file: keep the per-file sets concatenated
+            hashes[target] = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
+        counts = {t: int(h.size) for t, h in hashes.items()}
+        params = choose_ibf_params(counts, cfg.max_fp, cfg.filter_size, cfg.hash_functions, cfg.mode)
+        if params.n_bins == 0:
+            print("No valid sequences to build", file=sys.stderr)
+            return False
+        layout = bin_layout(counts, params)
+        be.create(params.n_bins, params.bin_size_bits, params.hash_functions, cfg.kmer_size, cfg.window_size)
+        hs, bs = [], []
+        for binno, (target, first, last) in enumerate(layout):
+            hs.append(hashes[target][first : last + 1])
+            bs.append(np.full(last + 1 - first, binno, dtype=np.uint32))
+        be.emplace(np.concatenate(hs), np.concatenate(bs))
+        db = formats.IBFFile(formats.IBF(params.n_bins, params.bin_size_bits, params.hash_functions, be.words()), cfg.kmer_size, cfg.window_size,
+                             params.max_hashes_bin, [(t, c) for t, c in counts.items()], [(b, t) for b, (t, _f, _l) in enumerate(layout)],
+                             max_fp=params.max_fp, true_max_fp=params.true_max_fp, true_avg_fp=params.true_avg_fp)
+        formats.write_ibf(cfg.output_file, db)
+    finally:
+        if own:
+            be.close()
+    if not cfg.quiet:
+        e = sys.stderr
+        print("ganon-build processed %d sequences / %d files (%g Mbp) in %g seconds" % (n_seq, sum(len(f) for f in targets.values()), n_bp / 1e6, time.time() - t0), file=e)
+        print(" - max. false positive: %g (avg.: %g)" % (params.true_max_fp, params.true_avg_fp), file=e)
+        print(" - filter size: %gMB" % (params.filter_bits / float(MIB_BITS)), file=e)
+        print(" - bins assigned: %d / hash functions: %d / max. hashes per bin: %d" % (params.n_bins, params.hash_functions, params.max_hashes_bin), file=e)
+        if n_skipped or invalid:
+            print(" - %d invalid files skipped, %d sequences shorter than --min-length skipped" % (invalid, n_skipped), file=e)
+    return True
+
+
+_BUILD_OPTS = {
+    "input-file": ("i", str, "input_file"), "output-file": ("o", str, "output_file"), "kmer-size": ("k", int, "kmer_size"), "window-size": ("w", int, "window_size"),
+    "hash-functions": ("s", int, "hash_functions"), "max-fp": ("p", float, "max_fp"), "filter-size": ("f", float, "filter_size"), "mode": ("j", str, "mode"),
+    "min-length": ("y", int, "min_length"), "tmp-output-folder": ("m", str, "tmp_output_folder"), "threads": ("t", int, "threads"), "device": (None, int, "device"),
+    "verbose": (None, bool, "verbose"), "quiet": (None, bool, "quiet"),
+}
+
+
+def build_main(argv: Optional[List[str]] = None) -> int:
+    """`ganon-build` command line (src/ganon-build/CommandLineParser.cpp:15-85; exit codes of main.cpp)."""
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv:
+        print("Try 'ganon-build -h/--help' for more information.", file=sys.stderr)
+        return 1
+    cfg = GanonBuildConfig()
+    short = {v[0]: k for k, v in _BUILD_OPTS.items() if v[0]}
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a in ("-h", "--help"):
+            print("ganon-build (B200): " + ", ".join("--" + k for k in _BUILD_OPTS), file=sys.stderr)
+            return 0
+        if a in ("-v", "--version"):
+            from .classify import VERSION
+
+            print("version: " + VERSION, file=sys.stderr)
+            return 0
+        name, inline = (a[2:].partition("=")[0], a[2:].partition("=")[2] if "=" in a else None) if a.startswith("--") else (short.get(a[1:2]), a[2:] or None) if a.startswith("-") else (None, None)
+        if name not in _BUILD_OPTS:
+            print("Option '%s' does not exist" % a, file=sys.stderr)
+            return 1
+        _s, kind, attr = _BUILD_OPTS[name]
+        if kind is bool:
+            setattr(cfg, attr, True)
+        else:
+            if inline is None:
+                i += 1
+                if i >= len(argv):
+                    print("Option '%s' is missing an argument" % name, file=sys.stderr)
+                    return 1
+                inline = argv[i]
+            try:
+                setattr(cfg, attr, kind(inline))
+            except ValueError:
+                print("Argument '%s' failed to parse" % inline, file=sys.stderr)
+                return 1
+        i += 1
+    return 0 if run_build(cfg) else 1

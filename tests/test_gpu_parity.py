@@ -459,6 +459,34 @@ def test_hibf_created_in_hbm_matches_oracle(tmp_path, finish_mode):
     reopened.close()
 
 
+# ------------------------------------------------------------------------------------------------------------------ build drop-in
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on hardware")
+def test_build_dropin_on_gpu_writes_the_oracle_backend_file(tmp_path):
+    """`ganon-build` drop-in with K2 and the insertion on the device against the same orchestration with the oracle
+    standing in for the device (tests/test_build_cpu.py pins that one to the reference builder): identical files."""
+    import json
+
+    from ganon_b200 import build as B
+    from tests.build_util import OracleBackend
+
+    cases = [c for c in json.load(open(os.path.join(SU.GOLDEN, "build_cases.json"))) if c["genomes"]]
+    for ci, c in enumerate(cases[:6]):
+        d = tmp_path / ("c%d" % ci)
+        d.mkdir()
+        tsv = str(d / "in.tsv")
+        with open(tsv, "w") as t:
+            for name, seq in c["genomes"].items():
+                p = str(d / (name + ".fa"))
+                open(p, "w").write(">%s\n%s\n" % (name, seq))
+                t.write("%s\t%s\n" % (p, name))
+        pr = c["params"]
+        mk = lambda out: B.GanonBuildConfig(input_file=tsv, output_file=out, kmer_size=pr["k"], window_size=pr["w"], max_fp=pr["max_fp"], filter_size=pr["filter_size"],
+                                            hash_functions=pr["hash_functions"], mode=pr["mode"], quiet=True)
+        assert B.run_build(mk(str(d / "gpu.ibf")))
+        assert B.run_build(mk(str(d / "cpu.ibf")), backend=OracleBackend())
+        assert open(str(d / "gpu.ibf"), "rb").read() == open(str(d / "cpu.ibf"), "rb").read()
+
+
 # ------------------------------------------------------------------------------------------------------------------ pipeline + shards
 def test_async_submit_collect_matches_sync(golden_dbs):
     fq1 = open(os.path.join(SU.GOLDEN, "reads.1.fq"), "rb").read()
