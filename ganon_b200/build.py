@@ -439,4 +439,10 @@ def build_main(argv: Optional[List[str]] = None) -> int:
                 print("Argument '%s' failed to parse" % inline, file=sys.stderr)
                 return 1
         i += 1
-    return 0 if run_build(cfg) else 1
+    from ._lib import GnbError
+
+    try:
+        return 0 if run_build(cfg) else 1
+    except GnbError as e:  # no device, out of memory ...: there is no CPU fallback
+        print("ERROR: " + e.msg, file=sys.stderr)
+        return 1

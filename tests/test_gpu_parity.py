@@ -482,7 +482,14 @@ def test_build_dropin_on_gpu_writes_the_oracle_backend_file(tmp_path):
         pr = c["params"]
         mk = lambda out: B.GanonBuildConfig(input_file=tsv, output_file=out, kmer_size=pr["k"], window_size=pr["w"], max_fp=pr["max_fp"], filter_size=pr["filter_size"],
                                             hash_functions=pr["hash_functions"], mode=pr["mode"], quiet=True)
-        assert B.run_build(mk(str(d / "gpu.ibf")))
+        # the device leg through the command line, in its own process
+        import subprocess
+        import sys
+
+        argv = [sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin", "ganon-build"), "-i", tsv, "-o", str(d / "gpu.ibf"), "-k", str(pr["k"]),
+                "-w", str(pr["w"]), "-s", str(pr["hash_functions"]), "-j", pr["mode"], "--quiet"] + (["-f", str(pr["filter_size"])] if pr["filter_size"] else ["-p", str(pr["max_fp"])])
+        done = subprocess.run(argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert done.returncode == 0, done.stderr[-500:]
         assert B.run_build(mk(str(d / "cpu.ibf")), backend=OracleBackend())
         assert open(str(d / "gpu.ibf"), "rb").read() == open(str(d / "cpu.ibf"), "rb").read()
 
