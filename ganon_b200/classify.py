@@ -442,6 +442,7 @@ class GanonClassifyConfig:
     reassign_em: bool = False
     em_max_iter: int = 10
     em_threshold: List[float] = field(default_factory=lambda: [0.0])
+    em_write_one: bool = True  # reassign.py --skip-one: only the new .rep is written
 
     def _err(self, msg: str) -> bool:
         print(msg, file=sys.stderr)
@@ -959,8 +960,9 @@ def run(cfg: GanonClassifyConfig) -> bool:
             # reassign.py: `.one` (one per hierarchy label unless there is a single `.all`) and the new `.rep`
             ones, new_rep, info = sess.reassign(pid, cfg.em_threshold[0], cfg.em_max_iter)
             for lab, text in ones.items():
-                with open(cfg.output_prefix + prefix + ("." + lab if lab else "") + ".one", "wb") as fh:
-                    fh.write(text)
+                if cfg.em_write_one:
+                    with open(cfg.output_prefix + prefix + ("." + lab if lab else "") + ".one", "wb") as fh:
+                        fh.write(text)
                 if not cfg.quiet:
                     print(" - %d iteration(s), %d reassigned reads%s" % (info[lab][0], info[lab][1], " [" + lab + "]" if lab else ""), file=sys.stderr)
             out_rep[prefix].write(new_rep)
@@ -1036,7 +1038,9 @@ def _print_stats(cfg, sess: Session, prefixes, labels, t_class: float, t_load: f
 def classify(cfg) -> bool:
     """Drop-in for ``ganon.classify.classify(cfg)`` up to the ganon-classify call (src/ganon/classify.py:7-64): the
     same selection of .hibf/.ibf/.tax per --db-prefix and the same argument mapping; reassign/report stay the
-    reference's (they consume the files written here)."""
+    reference's (they consume the files written here).  With ``cfg.reassign_in_memory`` set and --multiple-matches em
+    the EM step (src/ganon/classify.py:76-88 -> reassign.py) runs on the matches kept in HBM instead: `.one` is written if
+    --output-one, `.all` only if --output-all, and the caller skips its own reassign() call."""
     filter_files, tax_files, hibf = [], [], False
     for db_prefix in cfg.db_prefix:
         if os.path.isfile(db_prefix + ".hibf") and os.path.getsize(db_prefix + ".hibf") > 0:
@@ -1063,7 +1067,11 @@ def classify(cfg) -> bool:
         fpr_query=[float(x) for x in (g("fpr_query") or [1e-5])],
         skip_lca=mm != "lca",
         output_lca=mm == "lca" and bool(g("output_one")),
-        output_all=bool(g("output_all")) or mm == "em",
+        output_all=bool(g("output_all")) or (mm == "em" and not g("reassign_in_memory")),
+        reassign_em=mm == "em" and bool(g("reassign_in_memory")),
+        em_write_one=bool(g("output_one")),
+        em_max_iter=int(g("max_iter", 10) or 10) if g("max_iter", 10) is not None else 10,
+        em_threshold=[float(g("threshold", 0) or 0)],
         output_unclassified=bool(g("output_unclassified")),
         output_stats=bool(g("output_stats")),
         output_single=bool(g("output_single")),
