@@ -1070,7 +1070,7 @@ def classify(cfg) -> bool:
         output_all=bool(g("output_all")) or (mm == "em" and not g("reassign_in_memory")),
         reassign_em=mm == "em" and bool(g("reassign_in_memory")),
         em_write_one=bool(g("output_one")),
-        em_max_iter=int(g("max_iter", 10) or 10) if g("max_iter", 10) is not None else 10,
+        em_max_iter=10 if g("max_iter") is None else int(g("max_iter")),  # 0 = until convergence
         em_threshold=[float(g("threshold", 0) or 0)],
         output_unclassified=bool(g("output_unclassified")),
         output_stats=bool(g("output_stats")),
