@@ -99,3 +99,29 @@ def test_graft_entry_build_imports():
     import __graft_entry__ as G
 
     assert callable(G.build) and callable(G.smoke)
+
+
+def test_classify_wrapper_argument_mapping(tmp_path, monkeypatch):
+    """ganon_b200.classify.classify(cfg) maps ganon's Config like src/ganon/classify.py:29-64; with reassign_in_memory the EM
+    step of classify.py:76-88 is folded into the run."""
+    import types
+
+    from ganon_b200 import classify as K
+
+    (tmp_path / "db.ibf").write_bytes(b"x")
+    (tmp_path / "db.tax").write_bytes(b"x")
+    seen = {}
+    monkeypatch.setattr(K, "run", lambda c: seen.setdefault("cfg", c) is not None)
+    base = dict(db_prefix=[str(tmp_path / "db")], single_reads=["r.fq"], paired_reads=[], batch_reads=[], output_prefix="out", hierarchy_labels=None, rel_cutoff=[0.5],
+                rel_filter=[0.2], fpr_query=[1e-3], output_one=True, output_all=False, output_unclassified=True, output_stats=False, output_single=False, threads=3,
+                verbose=False, quiet=True, hibf=False)
+    assert K.classify(types.SimpleNamespace(multiple_matches="em", **base))
+    c = seen.pop("cfg")
+    assert c.ibf == [str(tmp_path / "db.ibf")] and c.tax == [str(tmp_path / "db.tax")] and c.skip_lca and c.output_all and not c.output_lca and not c.reassign_em
+    assert (c.rel_cutoff, c.rel_filter, c.fpr_query, c.threads) == ([0.5], [0.2], [1e-3], 3)
+    assert K.classify(types.SimpleNamespace(multiple_matches="em", reassign_in_memory=True, max_iter=0, threshold=0.01, **base))
+    c = seen.pop("cfg")
+    assert c.reassign_em and not c.output_all and c.em_write_one and c.em_max_iter == 0 and c.em_threshold == [0.01]
+    assert K.classify(types.SimpleNamespace(multiple_matches="lca", **base))
+    c = seen.pop("cfg")
+    assert not c.skip_lca and c.output_lca and not c.output_all and not c.reassign_em
