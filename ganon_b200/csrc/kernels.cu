@@ -15,6 +15,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "gnb_internal.h"
+#include "k2_thread.cuh"
 
 namespace gnb
 {
@@ -582,6 +583,71 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 4)
     }
 }
 
+// ---- K2t: one thread per read (k2_thread.cuh; switch GANON_B200_K2=thread) -------------------------------------------------
+// Written after the GPU budget of round 1 was spent: the per-thread core is checked against the oracle on the CPU
+// (tests/test_k2t_cpu.py), the kernel has not run on hardware yet, so it is off unless the switch is set.
+template <int KMODE> // as k_minimisers
+__global__ void __launch_bounds__(k2t::kThreads)
+    k_minimisers_thread(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1, const uint8_t *__restrict__ blk2,
+                        const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2, uint32_t n_reads, uint32_t k, uint32_t w, uint32_t *__restrict__ counts,
+                        const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count, unsigned long long *__restrict__ sum_count)
+{
+    constexpr bool WRITE = KMODE != 0;
+    extern __shared__ __align__(16) uint64_t k2t_smem[]; // [256] character table, then the rings [W][kThreads]: slot-major, a warp's lanes side by side
+    k2t::LutEntry *lut = reinterpret_cast<k2t::LutEntry *>(k2t_smem);
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t W = w - k + 1;
+    const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
+    const uint64_t mask = (1ull << (2 * k)) - 1; // k <= 29
+    const uint32_t lut_s  = (uint32_t)__cvta_generic_to_shared(k2t_smem);
+    const uint32_t ring_s = lut_s + k2t::kLutBytes + tid * 8;
+    constexpr uint32_t kStride = k2t::kThreads * 8;
+    for (uint32_t c = tid; c < 256; c += k2t::kThreads)
+        lut[c] = k2t::lut_entry(c, k);
+    __syncthreads();
+    uint32_t           my_max = 0;
+    unsigned long long my_sum = 0;
+    for (uint32_t first = blockIdx.x * k2t::kThreads; first < n_reads; first += gridDim.x * k2t::kThreads)
+    {
+        const uint32_t read = first + tid;
+        if (read >= n_reads)
+            continue;
+        uint32_t       total = 0;
+        const uint32_t L1    = len1[read];
+        if (L1 >= w) // GC.cpp:690: reads shorter than the window are skipped entirely
+        {
+            uint64_t *out = WRITE ? hashes + hash_off[read] : nullptr;
+            total         = k2t::mate<WRITE>(blk1 + off1[read], L1, k, W, seed, mask, lut_s, out, ring_s, kStride);
+            if (blk2 != nullptr)
+            {
+                const uint32_t L2 = len2[read];
+                if (L2 >= w) // GC.cpp:695
+                    total += k2t::mate<WRITE>(blk2 + off2[read], L2, k, W, seed, mask, lut_s, WRITE ? out + total : nullptr, ring_s, kStride);
+            }
+        }
+        if (KMODE != 1)
+            counts[read] = total;
+        my_max = max(my_max, total);
+        my_sum += total;
+    }
+    if (KMODE != 1)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+        {
+            my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
+            my_sum += __shfl_xor_sync(0xffffffffu, my_sum, d);
+        }
+        if (lane == 0 && my_max)
+        {
+            if (max_count != nullptr)
+                atomicMax(max_count, my_max);
+            if (sum_count != nullptr)
+                atomicAdd(sum_count, my_sum);
+        }
+    }
+}
+
 // upper bound of the minimisers of a read (pair): every window could emit (GC.cpp:690-700)
 __global__ void k_hash_upper_bounds(const uint32_t *__restrict__ len1, const uint32_t *__restrict__ len2, uint32_t n, uint32_t w, uint32_t *__restrict__ ub)
 {
@@ -608,6 +674,24 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
     if (n_reads == 0)
         return;
     const uint32_t W      = w - k + 1;
+    static const bool thread_path = [] { const char *e = getenv("GANON_B200_K2"); return e && e[0] == 't'; }();
+    if (thread_path && k <= k2t::kMaxK && W <= k2t::kMaxW)
+    { // K2t: one thread per read, CTAs of 128 reads (k2_thread.cuh)
+        int dev_t = 0, sms_t = 148;
+        cudaGetDevice(&dev_t);
+        cudaDeviceGetAttribute(&sms_t, cudaDevAttrMultiProcessorCount, dev_t);
+        const size_t   smem_t = k2t::kLutBytes + (size_t)W * k2t::kThreads * 8; // <= 34 KiB
+        const uint32_t want_t = (n_reads + k2t::kThreads - 1) / k2t::kThreads;
+        const uint32_t cap_t  = (uint32_t)sms_t * 128;         // short-lived CTAs: the tail of the grid stays small
+        const uint32_t grid_t = want_t < cap_t ? want_t : cap_t;
+        if (mode == 0)
+            k_minimisers_thread<0><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count);
+        else if (mode == 1)
+            k_minimisers_thread<1><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count);
+        else
+            k_minimisers_thread<2><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count);
+        return;
+    }
     const uint32_t nv_cap = (K2_TILE + W + 2 + 1) & ~1u;          // values per warp and level
     const uint32_t nb_cap = (nv_cap + k + 15) & ~15u;             // bases per warp (multiple of 16: keeps 8-byte alignment)
     uint32_t       n_lev  = 0;

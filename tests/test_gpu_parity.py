@@ -42,6 +42,22 @@ def test_minimisers_random_and_adversarial(k, w):
         assert minimisers(s, k, w).tolist() == O.minimiser_hash(s, k, w).tolist(), (k, w, len(s), s[:40])
 
 
+@pytest.mark.xfail(strict=False, reason="K2t was written after the GPU budget of round 1 was spent: its per-thread core is pinned on the CPU (test_k2t_cpu.py), the kernel has not run on hardware")
+def test_thread_per_read_minimiser_kernel_passes_the_k2_and_scenario_tests():
+    """GANON_B200_K2=thread (k2_thread.cuh) is read once per process: re-run the K2 tests, the golden scenarios (single,
+    paired, FASTA, several levels) and the oracle session test of this file in a child process with the switch set."""
+    import subprocess
+    import sys
+
+    if os.environ.get("GANON_B200_K2", "").startswith("t"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, GANON_B200_K2="thread")
+    sel = "minimisers_seqan3 or minimisers_random or (golden_scenarios and device) or session_matches_oracle or device_and_host_record_index"
+    done = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", sel, "-p", "no:cacheprovider"], env=env,
+                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert done.returncode == 0, done.stdout[-2000:]
+
+
 # ------------------------------------------------------------------------------------------------------------------ K3
 def _random_db(rng, bins, bin_size, h, density_terms=2, k=19, w=31):
     db = Database.create(bins, bin_size, h, k, w)
