@@ -318,3 +318,84 @@ def classify_level(filters: Sequence[OracleFilter], reads: Sequence[Tuple[bytes,
 def all_lines(results) -> List[str]:
     """The `.all` file content (unordered in the reference -> compare sorted)."""
     return sorted("%s\t%s\t%d" % (r["id"].decode(), t, c) for r in results for t, c in r["matches"])
+
+
+# ---- taxonomy + LCA (A7): utils/LCA.hpp:38-174, GanonClassify.cpp:615-627, 988-1005, 1324-1371 ---------------------------
+def load_tax(path: str) -> Dict[str, str]:
+    """``load_tax`` GanonClassify.cpp:988-1005: node <tab> parent <tab> rank <tab> name; later lines replace earlier ones.
+    Only the parent matters for the LCA."""
+    tax: Dict[str, str] = {}
+    with open(path) as f:
+        for line in f:
+            fields = line.rstrip("\n").split("\t")
+            tax[fields[0]] = fields[1]
+    return tax
+
+
+def merge_tax(taxes: Sequence[Dict[str, str]]) -> Dict[str, str]:
+    """``merge_tax`` GanonClassify.cpp:1324-1342: the first filter's entry of a node wins (map::insert)."""
+    merged = dict(taxes[0])
+    for t in taxes[1:]:
+        for node, parent in t.items():
+            merged.setdefault(node, parent)
+    return merged
+
+
+def validate_targets_tax(tax: Dict[str, str], filters: Sequence["OracleFilter"], root: str = "1") -> Dict[str, str]:
+    """``validate_targets_tax`` GanonClassify.cpp:1344-1362: targets without a tax entry hang under the root node."""
+    for f in filters:
+        for t in f.targets:
+            tax.setdefault(t, root)
+    return tax
+
+
+class OracleLCA:
+    """``pre_process_lca`` (GanonClassify.cpp:1364-1371: one edge parent -> node per tax entry, Euler walk from the root)
+    and ``LCA::getLCA`` (utils/LCA.hpp:150-174: pairwise fold over the targets).  The reference answers the pairwise
+    query with an Euler tour + sparse-table RMQ (LCA.hpp:60-148); the lowest common ancestor of two nodes of a tree is
+    unique, so this restatement walks parent pointers with the depths of the same depth-first search instead."""
+
+    def __init__(self, tax: Dict[str, str], root: str = "1"):
+        children: Dict[str, List[str]] = {}
+        for node, parent in tax.items():
+            children.setdefault(parent, []).append(node)
+        self.parent: Dict[str, str] = {}
+        self.depth: Dict[str, int] = {root: 0}
+        stack = [root]
+        while stack:  # depthFirstSearch LCA.hpp:60-82 (only nodes reachable from the root get a first appearance)
+            cur = stack.pop()
+            for ch in children.get(cur, []):
+                if ch not in self.depth:
+                    self.depth[ch] = self.depth[cur] + 1
+                    self.parent[ch] = cur
+                    stack.append(ch)
+
+    def pair(self, u: str, v: str) -> str:
+        du, dv = self.depth[u], self.depth[v]
+        while du > dv:
+            u, du = self.parent[u], du - 1
+        while dv > du:
+            v, dv = self.parent[v], dv - 1
+        while u != v:
+            u, v = self.parent[u], self.parent[v]
+        return u
+
+    def get_lca(self, targets: Sequence[str]) -> str:
+        assert len(targets) > 1  # LCA.hpp:168
+        lca = self.pair(targets[0], targets[1])
+        for t in targets[2:]:
+            lca = self.pair(lca, t)
+        return lca
+
+
+def one_lines(results, lca: Optional[OracleLCA]) -> List[str]:
+    """The `.one` file (--output-lca) of a level: the single match of a read, or the LCA of its matches with the read's
+    maximum count (GanonClassify.cpp:770-786, 615-627).  Compare sorted."""
+    out = []
+    for r in results:
+        m = r["matches"]
+        if len(m) == 1:
+            out.append("%s\t%s\t%d" % (r["id"].decode(), m[0][0], m[0][1]))
+        elif len(m) > 1:
+            out.append("%s\t%s\t%d" % (r["id"].decode(), lca.get_lca([t for t, _ in m]), r["max"]))
+    return sorted(out)

@@ -1,0 +1,276 @@
+"""The reference's own known-answer tests for the classify path, restated in tests/refkat_util.py from
+tests/ganon-classify/GanonClassify.test.cpp and tests/utils/LCA.test.cpp, against
+
+  * the oracle (CPU): filters built by the `ganon-build` drop-in with the oracle as the device (pinned to the reference
+    builder in tests/test_build_cpu.py), classification by oracle/ -- this pins the oracle to the reference's KATs;
+  * the unmodified reference binaries where oracle/_ref exists (CPU, build container only): the restated inputs really
+    produce the asserted numbers, and the drop-in-built filter classifies like the reference-built one;
+  * the drop-in command line on the GPU (`-m gpu`): same numbers, output-file rules, .rep cross-consistency, batch == non-batch,
+    and the LCA KATs through K4.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ganon_b200 import build as B
+from ganon_b200 import formats
+from oracle import oracle as O
+from tests import refkat_util as K
+from tests import scenario_util as SU
+from tests.build_util import OracleBackend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CLASSIFY = os.path.join(ROOT, "oracle", "_ref", "ganon-classify")
+REF_BUILD = os.path.join(ROOT, "oracle", "_ref", "ganon-build")
+CASE_IDS = [c["name"] for c in K.CASES]
+# the GPU legs below were written after the GPU budget of round 1 was spent; remove the marker once they have run on a B200
+not_yet_on_hardware = pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on hardware")
+
+
+@pytest.fixture(scope="module")
+def kat(tmp_path_factory):
+    """Inputs of all cases + the five filters, built by ganon_b200.build.run_build with the oracle as the device."""
+    d = str(tmp_path_factory.mktemp("refkats"))
+    paths = K.write_inputs(d)
+    ibf = {}
+    for b, (k, w, _refs) in K.BUILDS.items():
+        out = os.path.join(d, b + ".ibf")
+        cfg = B.GanonBuildConfig(input_file=paths["tsv"][b], output_file=out, kmer_size=k, window_size=w, max_fp=0.01, quiet=True)
+        assert B.run_build(cfg, backend=OracleBackend())
+        ibf[b] = out
+    return dict(dir=d, paths=paths, ibf=ibf)
+
+
+def _check(case, all_map, one_map):
+    for read, want in case["all"].items():
+        assert all_map.get(read, {}) == want, (case["name"], case["ref"], read, all_map.get(read))
+    if case["all"]:
+        assert set(all_map) == set(case["all"]), (case["name"], sorted(all_map))
+    if case["one"] is not None:
+        assert one_map == case["one"], (case["name"], case["ref"], one_map)
+
+
+# ------------------------------------------------------------------------------------------------------------------ LCA.test.cpp
+def test_lca_known_answers_oracle():
+    kats = json.load(open(os.path.join(SU.GOLDEN, "lca_kats.json")))
+    for name, t in kats.items():
+        lca = O.OracleLCA({node: parent for node, parent in t["edges"]}, "1")
+        for want, nodes in t["cases"]:
+            assert lca.get_lca(nodes) == want, (name, nodes)
+
+
+# ------------------------------------------------------------------------------------------------------------------ oracle
+def _oracle_run(case, kat):
+    """The case through oracle/: levels in sorted label order, reads left unclassified go on to the next level
+    (GanonClassify.cpp:1528-1537), `.one` via the restated LCA."""
+    argv = K.argv_of(case, kat["paths"], kat["ibf"])
+    cfg = SU.parse_args(argv)
+    reads = []
+    for f in cfg["single"]:
+        reads += [(i, s, None) for i, s in O.parse_reads(f)]
+    for a, b in zip(cfg["paired"][0::2], cfg["paired"][1::2]):
+        reads += [(x[0], x[1], y[1]) for x, y in zip(O.parse_reads(a), O.parse_reads(b))]
+    taxes = cfg["tax"]
+    all_map, one_map = {}, {}
+    ibf_index = {p: i for i, p in enumerate(cfg["ibf"])}
+    for _lab, lev in cfg["levels"]:
+        filters = [O.OracleFilter.from_ibf_file(formats.read_ibf(p), c) for p, c in lev["filters"]]
+        res = O.classify_level(filters, reads, lev["rel_filter"], lev["fpr_query"])
+        for line in O.all_lines(res):
+            rid, t, c = line.split("\t")
+            all_map.setdefault(rid, {})[t] = int(c)
+        if taxes:
+            tax = O.validate_targets_tax(O.merge_tax([O.load_tax(taxes[ibf_index[p]]) for p, _ in lev["filters"]]), filters)
+            for line in O.one_lines(res, O.OracleLCA(tax, "1")):
+                rid, t, c = line.split("\t")
+                one_map.setdefault(rid, {})[t] = int(c)
+        reads = [r for r, x in zip(reads, res) if not x["matches"]]
+    return all_map, (one_map if taxes else None)
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in K.CASES if c["all"] or c["one"]])
+def test_reference_kats_oracle(name, kat):
+    case = K.CASES[CASE_IDS.index(name)]
+    all_map, one_map = _oracle_run(case, kat)
+    _check(case, all_map, one_map if case["one"] is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------------------------ reference binaries
+needs_ref = pytest.mark.skipif(not (os.path.exists(REF_CLASSIFY) and os.path.exists(REF_BUILD)), reason="oracle/_ref not built (only in the build container)")
+
+
+@pytest.fixture(scope="module")
+def ref_ibf(kat):
+    out = {}
+    for b, (k, w, _refs) in K.BUILDS.items():
+        p = os.path.join(kat["dir"], b + ".ref.ibf")
+        pr = subprocess.run([REF_BUILD, "-i", kat["paths"]["tsv"][b], "-o", p, "-k", str(k), "-w", str(w), "-p", "0.01", "--quiet"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert pr.returncode == 0, pr.stderr
+        out[b] = p
+    return out
+
+
+def _files_check(case, pre):
+    for ext in case["absent"]:
+        assert not os.path.exists(pre + ext), (case["name"], ext)
+    for ext in case["present"]:
+        assert os.path.getsize(pre + ext) > 0, (case["name"], ext)
+
+
+def _maps_of(case, pre):
+    all_map = K.parse_matches(pre + ".all") if "--output-all" in case["flags"] and os.path.exists(pre + ".all") else {}
+    one_map = K.parse_matches(pre + ".one") if case["one"] is not None else None
+    return all_map, one_map
+
+
+@needs_ref
+@pytest.mark.parametrize("name", CASE_IDS)
+def test_reference_kats_reference_binary(name, kat, ref_ibf):
+    """The unmodified ganon-build + ganon-classify on the restated inputs give the numbers their own test asserts, and the
+    reference classifier gives the same `.all` on the filter written by the drop-in builder."""
+    case = K.CASES[CASE_IDS.index(name)]
+    outs = []
+    for tag, ibfs in (("ref", ref_ibf), ("mine", kat["ibf"])):
+        pre = os.path.join(kat["dir"], "%s_%s" % (tag, name))
+        pr = subprocess.run([REF_CLASSIFY] + K.argv_of(case, kat["paths"], ibfs) + ["-o", pre, "-t", "4", "--quiet"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert pr.returncode == 0, pr.stderr
+        _files_check(case, pre)
+        all_map, one_map = _maps_of(case, pre)
+        _check(case, all_map, one_map)
+        if not case["labels"] or "--output-single" in case["flags"]:
+            K.sanity_check(pre, case["flags"], bool(case["tax"]))
+        outs.append(all_map)
+    assert outs[0] == outs[1]
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@not_yet_on_hardware
+@pytest.mark.parametrize("name", CASE_IDS)
+def test_reference_kats_dropin(name, kat):
+    from ganon_b200 import cli
+
+    case = K.CASES[CASE_IDS.index(name)]
+    pre = os.path.join(kat["dir"], "gpu_" + name)
+    assert cli.main(K.argv_of(case, kat["paths"], kat["ibf"]) + ["-o", pre, "-t", "4", "--quiet"]) == 0
+    _files_check(case, pre)
+    all_map, one_map = _maps_of(case, pre)
+    _check(case, all_map, one_map)
+    if not case["labels"] or "--output-single" in case["flags"]:
+        K.sanity_check(pre, case["flags"], bool(case["tax"]))
+
+
+def _run_dropin(args):
+    from ganon_b200 import cli
+
+    return cli.main(args)
+
+
+def _run_reference(args):
+    return subprocess.run([REF_CLASSIFY] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).returncode
+
+
+def _sorted_lines(p):
+    with open(p) as f:
+        return sorted(f.read().splitlines())
+
+
+def _batch_reads_kats(kat, run, tag):
+    """--batch-reads (GanonClassify.test.cpp:364-507): results per prefix equal the un-batched runs after sorting; an empty
+    prefix behaves like --single/--paired-reads; with several hierarchy labels every prefix gets its own files."""
+    R, d = kat["paths"]["reads"], os.path.join(kat["dir"], "batch_" + tag)
+    os.makedirs(d, exist_ok=True)
+    base = ["-i", kat["ibf"]["b1"], "-c", "0", "-d", "1", "--output-all", "--output-lca", "--output-unclassified", "--output-stats", "-t", "4", "--quiet"]
+    tax = ["-x", kat["paths"]["tax"]["tax1"]]
+    # :364-423
+    assert run(base + tax + ["-p", R["readA"] + "," + R["readT"], "-o", os.path.join(d, "nb_paired")]) == 0
+    assert run(base + tax + ["-r", R["readC"], "-o", os.path.join(d, "nb_single")]) == 0
+    tsv = os.path.join(d, "batch.tsv")
+    open(tsv, "w").write("batch_paired\t%s\t%s\nbatch_single\t%s\n" % (R["readA"], R["readT"], R["readC"]))
+    pre = os.path.join(d, "batch")
+    assert run(base + tax + ["-b", tsv, "-o", pre]) == 0
+    for ext in ("all", "one", "unc", "rep"):
+        assert _sorted_lines(os.path.join(d, "nb_paired." + ext)) == _sorted_lines(pre + "batch_paired." + ext), ext
+        assert _sorted_lines(os.path.join(d, "nb_single." + ext)) == _sorted_lines(pre + "batch_single." + ext), ext
+    # :426-457
+    tsv2 = os.path.join(d, "batch_noprefix.tsv")
+    open(tsv2, "w").write("\t%s\n\t%s\n\t%s\t%s\n" % (R["readC"], R["readG"], R["readA"], R["readT"]))
+    pre2 = os.path.join(d, "batch_noprefix")
+    assert run(base + ["-b", tsv2, "-o", pre2]) == 0
+    got = K.parse_matches(pre2 + ".all")
+    assert got == {"readA": {"A": 10, "T": 10}, "readC": {"C": 5, "G": 5}, "readG": {"C": 5, "G": 5}}
+    # :459-507
+    tsv3 = os.path.join(d, "batch_h.tsv")
+    open(tsv3, "w").write("batchA\t%s\nbatchB\t%s\nbatchC\t%s\t%s\n" % (R["readC"], R["readG"], R["readA"], R["readT"]))
+    pre3 = os.path.join(d, "batch_h")
+    args = ["-i", kat["ibf"]["b1"] + "," + kat["ibf"]["b1"], "-x", kat["paths"]["tax"]["tax1"] + "," + kat["paths"]["tax"]["tax1"], "-y", "DB1,DB2", "-c", "0", "-d", "1",
+            "--output-all", "--output-lca", "--output-unclassified", "--output-stats", "-t", "4", "--quiet", "-b", tsv3, "-o", pre3]
+    assert run(args) == 0
+    for b in ("batchA", "batchB", "batchC"):
+        for ext in (".DB1.all", ".DB2.all", ".DB1.one", ".DB2.one", ".unc", ".rep"):
+            assert os.path.exists(pre3 + b + ext), b + ext
+
+
+def _lca_kats_through_classify(tmp_path, run):
+    """tests/utils/LCA.test.cpp through a whole classification: every node of the test taxonomy is a target with its own
+    random sequence, a read is the concatenation of one fragment per listed node, so its matches are exactly those targets
+    and the `.one` line must name the expected LCA (on the GPU: K4's parent / depth walk over the taxonomy in HBM)."""
+    kats = json.load(open(os.path.join(SU.GOLDEN, "lca_kats.json")))
+    k = w = 12
+    for name, t in kats.items():
+        rng = np.random.default_rng(len(name))
+        d = tmp_path / name
+        d.mkdir()
+        nodes = [n for n, _p in t["edges"] if n != "1"]
+        seqs = {n: bytes(rng.choice(list(b"ACGT"), size=40).astype(np.uint8)).decode() for n in nodes}
+        tsv = str(d / "in.tsv")
+        with open(tsv, "w") as f:
+            for n in nodes:
+                p = str(d / ("n_%s.fa" % n))
+                open(p, "w").write(">%s\n%s\n" % (n, seqs[n]))
+                f.write("%s\t%s\n" % (p, n))
+        ibf = str(d / "db.ibf")
+        assert B.run_build(B.GanonBuildConfig(input_file=tsv, output_file=ibf, kmer_size=k, window_size=w, max_fp=0.0001, quiet=True), backend=OracleBackend())
+        tax = str(d / "db.tax")
+        with open(tax, "w") as f:
+            for n, p in t["edges"]:
+                f.write("%s\t%s\trank\tname-%s\n" % (n, p, n))
+        fa = str(d / "reads.fa")
+        with open(fa, "w") as f:
+            for i, (_want, vals) in enumerate(t["cases"]):
+                f.write(">q%d\n%s\n" % (i, "".join(seqs[v][5:25] for v in vals)))
+        pre = str(d / "out")
+        # a fragment gives 9 of a read's 29..129 minimisers; --rel-cutoff 0.06 keeps those (threshold 2..8) and drops the
+        # stray hits of the junction k-mers (1..3 in these tiny filters)
+        assert run(["-i", ibf, "-x", tax, "-r", fa, "-c", "0.06", "-d", "1", "--output-all", "--output-lca", "-o", pre, "-t", "2", "--quiet"]) == 0
+        all_map, one_map = K.parse_matches(pre + ".all"), K.parse_matches(pre + ".one")
+        for i, (want, vals) in enumerate(t["cases"]):
+            q = "q%d" % i
+            assert set(all_map[q]) == set(vals), (name, q, all_map[q])
+            assert list(one_map[q]) == [want], (name, q, one_map[q])
+            assert one_map[q][want] == max(all_map[q].values())  # the read's maximum count (GanonClassify.cpp:615-627)
+
+
+@needs_ref
+def test_reference_kats_batch_reads_reference_binary(kat):
+    _batch_reads_kats(kat, _run_reference, "ref")
+
+
+@pytest.mark.gpu
+@not_yet_on_hardware
+def test_reference_kats_batch_reads_dropin(kat):
+    _batch_reads_kats(kat, _run_dropin, "gpu")
+
+
+@needs_ref
+def test_lca_known_answers_through_reference_binary(tmp_path):
+    _lca_kats_through_classify(tmp_path, _run_reference)
+
+
+@pytest.mark.gpu
+@not_yet_on_hardware
+def test_lca_known_answers_through_k4(tmp_path):
+    _lca_kats_through_classify(tmp_path, _run_dropin)
