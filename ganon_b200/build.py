@@ -95,8 +95,13 @@ def real_fp(counts: Iterable[int], max_hashes_bin: int, bin_size_bits: int, hash
     n = 0
     for c in counts:
         n_bins_target = _u64(math.ceil(c / float(max_hashes_bin)))
-        n_hashes_bin = _u64(math.ceil(c / float(n_bins_target)))
-        fp = 1.0 - math.pow(1.0 - bloom_fp(bin_size_bits, hash_functions, n_hashes_bin), n_bins_target)
+        if n_bins_target == 0:
+            # a target without hashes (every sequence shorter than --min-length): the reference evaluates pow(x, 0) = 1,
+            # i.e. a rate of 0 that still counts in the average
+            fp = 0.0
+        else:
+            n_hashes_bin = _u64(math.ceil(c / float(n_bins_target)))
+            fp = 1.0 - math.pow(1.0 - bloom_fp(bin_size_bits, hash_functions, n_hashes_bin), n_bins_target)
         highest = max(highest, fp)
         total += fp
         n += 1
@@ -187,6 +192,8 @@ def bin_layout(hashes_count: Dict[str, int], params: IBFParams) -> List[Tuple[st
     out: List[Tuple[str, int, int]] = []
     for target, count in hashes_count.items():
         n_bins_target = _u64(math.ceil(count / float(params.max_hashes_bin)))
+        if n_bins_target == 0:
+            continue  # no hashes, no bins (the loop below would not run in the reference either)
         per_bin = min(_u64(math.ceil(count / float(n_bins_target))), params.max_hashes_bin)
         for i in range(n_bins_target):
             first = i * per_bin

@@ -38,3 +38,16 @@ for name, cases in CASES.items():
 with open(os.path.join(HERE, "lca_kats.json"), "w") as f:
     json.dump(out, f, separators=(",", ":"))
 print({k: (len(v["edges"]), len(v["cases"])) for k, v in out.items()})
+
+# ---- tests/ganon-build/GanonBuild.test.cpp: the literal sequences its sections build filters from (:118-128 `seqs`,
+# :521-532 `seqs2` for --min-length, :562-570 `seqs3` = the ones of seqs2 that are at least 50 bp long)
+import re
+
+src = open("/root/reference/tests/ganon-build/GanonBuild.test.cpp").read()
+seqsets = {}
+for m in re.finditer(r"aux::sequences_type\s+(\w+)\s*\{(.*?)\};", src, re.S):
+    seqsets[m.group(1)] = re.findall(r'"([ACGT]+)"_dna4', m.group(2))
+assert [len(seqsets[k]) for k in ("seqs", "seqs2", "seqs3")] == [10, 10, 7]
+with open(os.path.join(HERE, "build_kats.json"), "w") as f:
+    json.dump(seqsets, f, separators=(",", ":"))
+print({k: len(v) for k, v in seqsets.items()})
