@@ -1450,7 +1450,10 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         n = t1.size();
         if (paired)
             n = std::min(n, t2.size());
-        // A parse error ends the file; the reference loses the chunk of --n-reads records being assembled (GC.cpp:1240-1283)
+        // A parse error ends the file; the reference loses the chunk of --n-reads records being assembled (GC.cpp:1240-1283).
+        // Its reader looks one record ahead (seqan3::views::chunk and std::views::take advance the file before they report
+        // their end), so record e fails inside the chunk that holds record e - 1: that chunk goes too, even when it is
+        // complete (tests/test_reader_cpu.py: differential against the reference binary).
         bool   err = false;
         size_t err_rec = n;
         if (t1.parse_error && t1.error_record <= n)
@@ -1460,7 +1463,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         if (err)
         {
             const uint64_t abs_rec  = S->file_records + err_rec;
-            const uint64_t keep_abs = abs_rec / n_reads_chunk * n_reads_chunk;
+            const uint64_t keep_abs = abs_rec == 0 ? 0 : (abs_rec - 1) / n_reads_chunk * n_reads_chunk;
             n = keep_abs > S->file_records ? (size_t)(keep_abs - S->file_records) : 0;
             parse_error = true;
             if (!quiet)
@@ -3162,12 +3165,17 @@ extern "C" int gnb_session_report(gnb_session *s, uint32_t prefix_id, const char
             o.push_back('\n');
         }
     }
+    // the reference creates a prefix's totals when its first batch of reads is queued (GC.cpp:1256, 1272): a prefix
+    // without a single parsed read (empty file, parse error in the first chunk) gets no totals lines
     const gnb_totals t = sum_levels(s, prefix_id);
-    o += "#total_classified\t";
-    append_u64(o, t.seqs_classified);
-    o += "\n#total_unclassified\t";
-    append_u64(o, t.input_seqs - t.seqs_classified);
-    o.push_back('\n');
+    if (t.input_seqs > 0)
+    {
+        o += "#total_classified\t";
+        append_u64(o, t.seqs_classified);
+        o += "\n#total_unclassified\t";
+        append_u64(o, t.input_seqs - t.seqs_classified);
+        o.push_back('\n');
+    }
     *text = o.data();
     *len  = o.size();
     return GNB_OK;

@@ -281,6 +281,23 @@ def test_parse_error_truncation_rule(golden_dbs, tmp_path):
     assert int(rep["#total_unclassified"]) + int(rep["#total_classified"]) == 800
 
 
+@pytest.mark.xfail(strict=False, reason="rule corrected after the GPU budget of round 1 was spent (CPU differential against the reference binary, tests/test_reader_cpu.py): not yet run on hardware")
+@pytest.mark.parametrize("bad_at,kept", [(0, 0), (1, 0), (399, 0), (400, 0), (401, 400), (800, 400), (801, 800)])
+def test_parse_error_chunk_rule_at_chunk_boundaries(golden_dbs, tmp_path, bad_at, kept):
+    """The reference's reader looks one record ahead: record e fails inside the chunk that holds record e - 1, so
+    floor((e - 1) / n_reads) * n_reads records survive (numbers confirmed with the reference binary on the CPU); a run
+    without a single parsed read writes a `.rep` without totals."""
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 10, b"I" * 40) for i in range(1000)]
+    recs[bad_at] = b"@bad\nACGTXXXX\n+\nIIIIIIII\n"
+    f = str(tmp_path / "bad.fq")
+    open(f, "wb").write(b"".join(recs))
+    pre = str(tmp_path / "o")
+    assert cli.main(["-r", f, "-i", golden_dbs["synth"], "-o", pre, "-u", "--quiet", "--n-reads", "400"]) == 0
+    rep = dict(l.split("\t") for l in open(pre + ".rep").read().splitlines() if l.startswith("#"))
+    assert int(rep.get("#total_unclassified", 0)) + int(rep.get("#total_classified", 0)) == kept
+    assert bool(rep) == (kept > 0)
+
+
 def test_device_and_host_record_index_agree(golden_dbs, tmp_path, monkeypatch):
     """K1 (device FASTQ index) and the host reader give identical results, including a final block without a
     trailing newline and blocks that end in the middle of a record."""
