@@ -1,0 +1,106 @@
+"""Flag grammar, validation order, messages and accept / reject decisions of the `ganon-classify` drop-in
+(ganon_b200/cli.py, GanonClassifyConfig.validate) against the UNMODIFIED reference binary on random command lines
+(CommandLineParser.cpp:15-45, Config.hpp:71-245): whenever the reference rejects a command line the drop-in must reject
+it with exactly the same text on stderr, and whenever the reference runs it the drop-in's validation must pass.  No GPU
+involved: the comparison stops where the reference would start loading filters.  1500 further seeds were run in round 1
+without a mismatch."""
+import contextlib
+import io
+import os
+import random
+import subprocess
+
+import pytest
+
+from ganon_b200 import cli
+from tests import fuzz_util as F
+
+pytestmark = pytest.mark.skipif(not os.path.exists(F.REF_BIN), reason="oracle/_ref not built (only in the build container)")
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("clifuzz"))
+    rng = random.Random(5)
+    p = {k: os.path.join(d, v) for k, v in dict(ibf="d.ibf", ibf2="e.ibf", r1="r1.fq", r2="r2.fq", empty="empty.fq", tax="t.tax", batch="b.tsv", missing="missing", out="out").items()}
+    F.make_db(rng, p["ibf"], 12, 16)
+    F.make_db(rng, p["ibf2"], 12, 16)
+    open(p["r1"], "w").write("@a\nACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIII\n")
+    open(p["r2"], "w").write("@a\nACGTACGTACGTACGTACGA\n+\nIIIIIIIIIIIIIIIIIIII\n")
+    open(p["empty"], "w").close()
+    open(p["tax"], "w").write("1\t0\troot\troot\n")
+    open(p["batch"], "w").write("p\t%s\n" % p["r1"])
+    return p
+
+
+def _pick(rng, pool, lo, hi):
+    return [rng.choice(pool) for _ in range(rng.randint(lo, hi))]
+
+
+def _argv(rng, p):
+    tame = rng.random() < 0.5  # half of the command lines use only well-formed values, so that many are accepted
+    a = []
+    if rng.random() < (0.9 if tame else 0.7):
+        a += ["-r", ",".join(_pick(rng, [p["r1"], p["r2"]] if tame else [p["r1"], p["r2"], p["r1"], p["missing"], p["empty"]], 1, 3))]
+    if rng.random() < 0.3:
+        n = rng.choice((2, 4)) if tame else rng.randint(1, 4)
+        a += ["-p", ",".join(_pick(rng, [p["r1"], p["r2"]] if tame else [p["r1"], p["r2"], p["missing"]], n, n))]
+    if rng.random() < (0.0 if tame else 0.1):
+        a += ["-b", rng.choice([p["batch"], p["missing"]])]
+    n_ibf = rng.randint(1, 3)
+    if rng.random() < (1.0 if tame else 0.9):
+        a += ["-i", ",".join(_pick(rng, [p["ibf"], p["ibf2"]] if tame else [p["ibf"], p["ibf2"], p["ibf"], p["missing"]], n_ibf, n_ibf))]
+    if rng.random() < 0.3:
+        n = n_ibf if tame else rng.randint(1, 3)
+        a += ["-x", ",".join(_pick(rng, [p["tax"]] if tame else [p["tax"], p["tax"], p["missing"]], n, n))]
+    labels = None
+    if rng.random() < 0.5:
+        n = rng.choice((1, n_ibf)) if tame else rng.randint(1, 4)
+        labels = _pick(rng, ["a", "b", "c"], n, n)
+        a += ["-y", ",".join(labels)]
+    n_lab = len(set(labels)) if labels else 1
+    good, wild = ["0", "0.5", "1", "0.25"], ["0", "0.5", "1", "1.5", "-0.1", "0.25"]
+    if rng.random() < 0.5:
+        n = rng.choice((1, n_ibf)) if tame else rng.randint(1, 4)
+        a += ["-c", ",".join(_pick(rng, good if tame else wild, n, n))]
+    if rng.random() < 0.5:
+        n = rng.choice((1, n_lab)) if tame else rng.randint(1, 4)
+        a += ["-d", ",".join(_pick(rng, good if tame else wild, n, n))]
+    if rng.random() < 0.4:
+        n = rng.choice((1, n_lab)) if tame else rng.randint(1, 4)
+        a += ["-f", ",".join(_pick(rng, good + ["1e-5"] if tame else wild + ["1e-5"], n, n))]
+    if rng.random() < (1.0 if tame else 0.9):
+        a += ["-o", p["out"]]
+    if rng.random() < 0.3:
+        a += ["-t", rng.choice(["0", "1", "4"])]
+    if rng.random() < 0.2:
+        a += ["--n-reads", rng.choice(["0", "1", "400"])]
+    if rng.random() < 0.2:
+        a += ["--n-batches", rng.choice(["0", "5", "1000"]) if not a or "-r" not in a else "1000"]  # the reference deadlocks with a one-batch queue and several files
+    for fl in ("--skip-lca", "-a", "-u", "-l", "-s", "-z"):
+        if rng.random() < 0.2:
+            a.append(fl)
+    return a + ["--quiet"]
+
+
+@pytest.mark.parametrize("first", range(0, 400, 50))
+def test_validation_matches_the_reference_binary(files, first):
+    accepted = 0
+    for seed in range(first, first + 50):
+        a = _argv(random.Random(seed), files)
+        try:
+            pr = subprocess.run([F.REF_BIN] + a, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=20)
+        except subprocess.TimeoutExpired:  # seen with --n-batches 0 / 1 and several read files: the reference's queue deadlocks
+            continue
+        err = io.StringIO()
+        with contextlib.redirect_stderr(err):
+            try:
+                ok = cli.parse(a).validate()
+            except cli.CliError as e:
+                ok = False
+                err.write(str(e))
+        assert ok == (pr.returncode == 0), (seed, a, pr.stderr, err.getvalue())
+        if not ok:
+            assert err.getvalue().strip() == pr.stderr.strip(), (seed, a)
+        accepted += ok
+    assert accepted >= 5  # both outcomes are exercised
