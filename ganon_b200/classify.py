@@ -1062,9 +1062,10 @@ def classify(cfg) -> bool:
         tax=tax_files,
         output_prefix=g("output_prefix", "") or "",
         hierarchy_labels=list(g("hierarchy_labels") or ["H1"]),
-        rel_cutoff=[float(x) for x in (g("rel_cutoff") or [0.75])],
-        rel_filter=[float(x) for x in (g("rel_filter") or [0.1])],
-        fpr_query=[float(x) for x in (g("fpr_query") or [1e-5])],
+        # an empty value leaves the flag out and with it the binary's default (Config.hpp:36-38), classify.py:40-48
+        rel_cutoff=[float(x) for x in (g("rel_cutoff") or [0.2])],
+        rel_filter=[float(x) for x in (g("rel_filter") or [0.0])],
+        fpr_query=[float(x) for x in (g("fpr_query") or [1.0])],
         skip_lca=mm != "lca",
         output_lca=mm == "lca" and bool(g("output_one")),
         output_all=bool(g("output_all")) or (mm == "em" and not g("reassign_in_memory")),
