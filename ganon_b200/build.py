@@ -316,8 +316,15 @@ class GpuBackend:
 
         if not seqs:
             return np.empty(0, dtype=np.uint64)
-        _off, hashes = self._c.minimisers_batch(list(seqs), k, w, device=self.device)
-        return hashes
+        # K2 applies ganon-classify's rule "shorter than the window: skipped" (GC.cpp:690); the builder hashes every sequence
+        # with seqan3's view, which shrinks the window to a sequence shorter than it (minimiser.hpp:298-299; the reference
+        # builder counts 1 minimiser for 25 bp at k=19, w=31).  Those rare sequences go through the single-sequence hook,
+        # which clamps the window; both run on the device.
+        full = [s for s in seqs if len(s) >= w]
+        parts = [self._c.minimisers(s, k, w, device=self.device) for s in seqs if k <= len(s) < w]
+        if full:
+            parts.append(self._c.minimisers_batch(full, k, w, device=self.device)[1])
+        return np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
 
     def create(self, n_bins: int, bin_size_bits: int, hash_functions: int, k: int, w: int) -> None:
         self.db = self._c.Database.create(n_bins, bin_size_bits, hash_functions, k, w, device=self.device)

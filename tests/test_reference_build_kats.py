@@ -191,3 +191,37 @@ def test_build_sections_on_gpu(sec, tmp_path):
     a, b = formats.read_ibf(cfg.output_file), formats.read_ibf(ref.output_file)
     assert (a.ibf.bins, a.ibf.bin_size, a.ibf.hash_funs, a.max_hashes_bin) == (b.ibf.bins, b.ibf.bin_size, b.ibf.hash_funs, b.max_hashes_bin)
     assert np.array_equal(np.asarray(a.ibf.data), np.asarray(b.ibf.data))
+
+
+# ---- not in the reference's test file: sequences shorter than the window -------------------------------------------------
+SHORT = ["ACGTTGCAAGCTTGCAATGCATGCA", "ACGTTGCAAGCTTGCAATGCATGCAACGTTGCAAGCTTGCAATGCATGCATTTT", "ACGTACGTACGTACGTAC", "TTGCAAGCTTGCAATGCAT"]  # 25, 54, 18 (< k), 19 bp
+
+
+def _short_case(tmp, backend_factory):
+    prefix = os.path.join(tmp, "short")
+    cfg = default_config(prefix, kmer_size=19, window_size=31, hash_functions=0)
+    write_seqtarget(prefix, SHORT, ["A", "B", "C", "D"])
+    backend = backend_factory()
+    try:
+        assert B.run_build(cfg, backend=backend)
+    finally:
+        backend.close()
+    return cfg
+
+
+def test_sequences_shorter_than_the_window_count_like_the_reference(tmp_path):
+    """seqan3's minimiser view shrinks the window to a sequence shorter than it (minimiser.hpp:298-299): the reference builder
+    counts one minimiser for 19..30 bp at k=19, w=31 and none below k -- unlike ganon-classify, which skips such reads."""
+    cfg = _short_case(str(tmp_path), OracleBackend)
+    assert dict(formats.read_ibf(cfg.output_file).hashes_count) == {"A": 1, "B": 4, "C": 0, "D": 1}
+    same_parameters_as_reference(cfg, str(tmp_path))
+
+
+@pytest.mark.gpu
+@not_yet_on_hardware
+def test_sequences_shorter_than_the_window_on_gpu(tmp_path):
+    (tmp_path / "gpu").mkdir()
+    (tmp_path / "cpu").mkdir()
+    a = formats.read_ibf(_short_case(str(tmp_path / "gpu"), lambda: B.GpuBackend(0)).output_file)
+    b = formats.read_ibf(_short_case(str(tmp_path / "cpu"), OracleBackend).output_file)
+    assert a.hashes_count == b.hashes_count and np.array_equal(np.asarray(a.ibf.data), np.asarray(b.ibf.data))

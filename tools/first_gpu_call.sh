@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 # 1. the legs marked "not yet run on hardware", without the expected-failure marker, each in its own process
 python -m pytest tests -m gpu -q -x --runxfail -p no:cacheprovider \
-    -k "thread_per_read or reference_kats or lca_known_answers or build_sections_on_gpu or build_dropin or chunk_rule" > gpurun_out/new_legs.log 2>&1
+    -k "thread_per_read or reference_kats or lca_known_answers or build_sections_on_gpu or build_dropin or chunk_rule or shorter_than_the_window" > gpurun_out/new_legs.log 2>&1
 echo "new legs rc=$?" | tee -a gpurun_out/new_legs.log
 # 2. the whole GPU suite as the driver runs it
 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
