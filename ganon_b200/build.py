@@ -11,6 +11,7 @@ from __future__ import annotations
 import gzip
 import math
 import os
+import re
 import sys
 import time
 from dataclasses import dataclass, field
@@ -281,23 +282,79 @@ def parse_input_table(path: str, quiet: bool = False) -> Tuple[Dict[str, List[st
     return targets, invalid
 
 
-def read_sequences(path: str) -> List[bytes]:
-    """Sequences of a FASTA / FASTQ file, plain or gzip (what seqan3::sequence_file_input yields to count_hashes,
-    GanonBuild.cpp:205-226; whitespace inside FASTA sequences is skipped)."""
+_WS = b" \t\n\v\f\r"
+_WS_DIGITS = _WS + b"0123456789"
+_LEGAL = b"ABCDGHKMNRSTVWYUabcdghkmnrstvwyu"  # dna15 + U (nucleotide_base.hpp:147-168)
+_NEXT_ID = re.compile(rb"[>;]")
+
+
+def read_sequences(path: str) -> Optional[List[bytes]]:
+    """Sequences of a FASTA / FASTQ file, plain or gzip, as seqan3::sequence_file_input<dna4_traits> yields them to
+    count_hashes (GanonBuild.cpp:205-226); None = parse error, the reference then drops the whole file (its hashes are
+    counted after the loop over the records, GanonBuild.cpp:239-247).  The record rules are those of the library's host
+    reader (csrc/reads.cpp: format_fasta.hpp:150-330, format_fastq.hpp:105-267), which tests/test_reader_cpu.py pins against
+    the reference binary; tests/test_build_cpu.py pins this restatement against the reference builder."""
     with open(path, "rb") as f:
         magic = f.read(2)
     data = gzip.open(path, "rb").read() if magic == b"\x1f\x8b" else open(path, "rb").read()
     out: List[bytes] = []
-    if data[:1] == b">":
-        for rec in data.split(b"\n>"):
-            nl = rec.find(b"\n")
+    n, p = len(data), 0
+    if data[:1] in (b">", b";"):
+        while p < n:
+            if data[p : p + 1] not in (b">", b";"):
+                return None  # "Expected to be on beginning of ID"
+            nl = data.find(b"\n", p)
+            if nl < 0 or nl + 1 >= n:
+                return None  # ID line without newline / "No sequence information given!"
+            m = _NEXT_ID.search(data, nl + 1)
+            e = m.start() if m else n
+            seq = data[nl + 1 : e].translate(None, _WS_DIGITS)  # blanks and digits inside the sequence are skipped
+            if seq.translate(None, _LEGAL):
+                return None  # "Encountered an unexpected letter"
+            out.append(seq)
+            p = e
+    else:
+        while p < n:
+            if data[p : p + 1] != b"@":
+                return None  # "Expected '@' on beginning of ID line"
+            nl = data.find(b"\n", p)
             if nl < 0:
-                continue
-            out.append(rec[nl + 1 :].replace(b"\n", b"").replace(b"\r", b"").replace(b" ", b""))
-    elif data[:1] == b"@":
-        lines = data.split(b"\n")
-        for i in range(1, len(lines), 4):
-            out.append(lines[i].rstrip(b"\r"))
+                return None
+            e = data.find(b"+", nl + 1)  # letters up to the first '+', blanks skipped
+            if e < 0:
+                return None
+            seq = data[nl + 1 : e].translate(None, _WS)
+            if seq.translate(None, _LEGAL):
+                return None
+            nl3 = data.find(b"\n", e)
+            if nl3 < 0:
+                return None
+            q, need = nl3 + 1, len(seq)
+            if q + need <= n and data.find(b"\n", q, q + need) < 0:
+                q, need = q + need, 0
+            while need and q < n:  # qualities: `need` characters that are not blanks, over as many lines as it takes
+                end = data.find(b"\n", q)
+                end = n if end < 0 else end + 1
+                line = data[q:end]
+                ns = len(line.translate(None, _WS))
+                if ns < need:
+                    need -= ns
+                    q = end
+                    continue
+                for idx in range(len(line)):
+                    if line[idx] not in _WS:
+                        need -= 1
+                        if need == 0:
+                            q += idx + 1
+                            break
+            if need:
+                return None  # "File ended before expected number of qualities could be read."
+            if q < n:
+                if data[q : q + 1] != b"\n":
+                    return None  # "Qualitites longer than sequence."
+                q += 1
+            out.append(seq)
+            p = q
     return out
 
 
@@ -365,7 +422,11 @@ def run_build(cfg: GanonBuildConfig, backend=None) -> bool:
             parts = []
             for f in files:
                 seqs = []
-                for s in read_sequences(f):
+                records = read_sequences(f)
+                if records is None:
+                    print("Error parsing file [%s]." % f, file=sys.stderr)
+                    continue
+                for s in records:
                     if len(s) < cfg.min_length:
                         n_skipped += 1
                         continue
