@@ -116,7 +116,7 @@ def dress(rng, recs, fmt, style):
                 out.append(eol)
         else:
             seq = _wrap(rng, s, eol) if style.get("wrap") else s
-            qual = bytes(rng.choice(b"!#5?IJ~") for _ in range(len(s)))
+            qual = bytes(rng.choice(b"!#5?IJ~@+>" if style.get("odd_quals") else b"!#5?IJ~") for _ in range(len(s)))
             qual = _wrap(rng, qual, eol) if style.get("wrap") else qual
             plus = b"+" + (rid if style.get("plus_id") and rng.random() < 0.5 else b"")
             if style.get("blanks") and len(seq) > 4 and rng.random() < 0.3:
@@ -126,6 +126,10 @@ def dress(rng, recs, fmt, style):
     data = b"".join(out)
     if style.get("no_final_newline"):
         data = data.rstrip(b"\r\n")
+    elif style.get("trailing_newlines"):
+        data += eol * rng.choice((1, 2))
+    if style.get("leading_blank"):
+        data = eol + data
     return data
 
 
@@ -138,6 +142,7 @@ def _lines(path):
 
 
 STYLES = ["wrap", "blanks", "blank_lines", "crlf", "lower", "semicolon", "id_blanks", "plus_id", "no_final_newline"]
+RARE_STYLES = ["odd_quals", "trailing_newlines", "leading_blank", "empty_seq"]  # drawn with a lower probability
 
 
 def differential_case(L, seed, tmp, ref_bin):
@@ -151,11 +156,15 @@ def differential_case(L, seed, tmp, ref_bin):
     recs = F.make_reads(rng, genomes, rng.choice((1, 7, 60)), w)
     fmt = rng.choice(("fasta", "fastq"))
     style = {s: rng.random() < 0.35 for s in STYLES}
+    style.update({s: rng.random() < 0.12 for s in RARE_STYLES})
+    if style["empty_seq"] and recs:
+        j = rng.randrange(len(recs))
+        recs[j] = (recs[j][0], b"")
     bad_at = None
     if rng.random() < 0.35 and recs:  # an illegal letter somewhere: parse error
         bad_at = rng.randrange(len(recs))
         rid, s = recs[bad_at]
-        p = rng.randrange(len(s))
+        p = rng.randrange(max(1, len(s)))
         recs[bad_at] = (rid, s[:p] + rng.choice((b"X", b"E", b"*", b"-", b"Z", b"@")) + s[p + 1 :])
     data = dress(rng, recs, fmt, style)
     path = os.path.join(tmp, "r%d.%s" % (seed, "fa" if fmt == "fasta" else "fq"))
@@ -164,9 +173,12 @@ def differential_case(L, seed, tmp, ref_bin):
     n_reads = rng.choice((1, 3, 400))
     cutoff = rng.choice((0.0, 0.2, 0.6))
     out = os.path.join(tmp, "r%d_ref" % seed)
-    pr = subprocess.run([ref_bin, "-r", path, "-i", ibf, "-c", str(cutoff), "-d", "1", "-a", "-u", "-o", out, "-t", "2", "--quiet", "--n-reads", str(n_reads)],
-                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    desc = "seed %d %s k=%d w=%d reads=%d n_reads=%d bad_at=%s style=%s" % (seed, fmt, k, w, len(recs), n_reads, bad_at, [s for s in STYLES if style[s]])
+    try:
+        pr = subprocess.run([ref_bin, "-r", path, "-i", ibf, "-c", str(cutoff), "-d", "1", "-a", "-u", "-o", out, "-t", "2", "--quiet", "--n-reads", str(n_reads)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=8)
+    except subprocess.TimeoutExpired:
+        return None, "seed %d: the reference binary hangs on this input (%s, %s)" % (seed, fmt, [s for s in STYLES + RARE_STYLES if style[s]])
+    desc = "seed %d %s k=%d w=%d reads=%d n_reads=%d bad_at=%s style=%s" % (seed, fmt, k, w, len(recs), n_reads, bad_at, [s for s in STYLES + RARE_STYLES if style[s]])
     if pr.returncode < 0 or "free():" in pr.stderr or "corrupted" in pr.stderr:
         return None, desc + " reference crashed: " + pr.stderr[-120:].strip()  # seen with CRLF + wrapped FASTA: heap corruption inside the reference
     if pr.returncode != 0:
