@@ -268,4 +268,32 @@ K2T_D uint32_t mate(const uint8_t *p, uint32_t L, uint32_t k, uint32_t W, uint64
     return WRITE ? (uint32_t)(op - out) : n;
 }
 
+// One read (pair) of a batch: the rules of GanonClassify.cpp:690-700 -- a read shorter than the window is skipped entirely, a
+// second mate shorter than the window contributes nothing, hashes(read1) ++ hashes(read2).  KMODE 0: count only; 1: write at
+// hash_off[read]; 2: write at hash_off[read] and count (single pass over upper-bound offsets).  Returns the read's total.
+template <int KMODE>
+K2T_D uint32_t read_pair(uint32_t read, const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
+                         const uint32_t *len2, uint32_t k, uint32_t w, uint64_t seed, uint64_t mask, saddr_t lut, saddr_t ring, uint32_t stride_bytes,
+                         uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes)
+{
+    constexpr bool WRITE = KMODE != 0;
+    const uint32_t W     = w - k + 1;
+    uint32_t       total = 0;
+    const uint32_t L1    = len1[read];
+    if (L1 >= w)
+    {
+        uint64_t *out = WRITE ? hashes + hash_off[read] : nullptr;
+        total         = mate<WRITE>(blk1 + off1[read], L1, k, W, seed, mask, lut, out, ring, stride_bytes);
+        if (blk2 != nullptr)
+        {
+            const uint32_t L2 = len2[read];
+            if (L2 >= w)
+                total += mate<WRITE>(blk2 + off2[read], L2, k, W, seed, mask, lut, WRITE ? out + total : nullptr, ring, stride_bytes);
+        }
+    }
+    if (KMODE != 1)
+        counts[read] = total;
+    return total;
+}
+
 } // namespace k2t

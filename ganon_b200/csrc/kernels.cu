@@ -592,11 +592,9 @@ __global__ void __launch_bounds__(k2t::kThreads)
                         const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2, uint32_t n_reads, uint32_t k, uint32_t w, uint32_t *__restrict__ counts,
                         const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count, unsigned long long *__restrict__ sum_count)
 {
-    constexpr bool WRITE = KMODE != 0;
     extern __shared__ __align__(16) uint64_t k2t_smem[]; // [256] character table, then the rings [W][kThreads]: slot-major, a warp's lanes side by side
     k2t::LutEntry *lut = reinterpret_cast<k2t::LutEntry *>(k2t_smem);
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t W = w - k + 1;
     const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
     const uint64_t mask = (1ull << (2 * k)) - 1; // k <= 29
     const uint32_t lut_s  = (uint32_t)__cvta_generic_to_shared(k2t_smem);
@@ -612,21 +610,7 @@ __global__ void __launch_bounds__(k2t::kThreads)
         const uint32_t read = first + tid;
         if (read >= n_reads)
             continue;
-        uint32_t       total = 0;
-        const uint32_t L1    = len1[read];
-        if (L1 >= w) // GC.cpp:690: reads shorter than the window are skipped entirely
-        {
-            uint64_t *out = WRITE ? hashes + hash_off[read] : nullptr;
-            total         = k2t::mate<WRITE>(blk1 + off1[read], L1, k, W, seed, mask, lut_s, out, ring_s, kStride);
-            if (blk2 != nullptr)
-            {
-                const uint32_t L2 = len2[read];
-                if (L2 >= w) // GC.cpp:695
-                    total += k2t::mate<WRITE>(blk2 + off2[read], L2, k, W, seed, mask, lut_s, WRITE ? out + total : nullptr, ring_s, kStride);
-            }
-        }
-        if (KMODE != 1)
-            counts[read] = total;
+        const uint32_t total = k2t::read_pair<KMODE>(read, blk1, off1, len1, blk2, off2, len2, k, w, seed, mask, lut_s, ring_s, kStride, counts, hash_off, hashes);
         my_max = max(my_max, total);
         my_sum += total;
     }

@@ -36,3 +36,36 @@ extern "C" long k2t_host_minimisers(const uint8_t *seq, uint32_t L, uint32_t k, 
     free(raw);
     return rc;
 }
+
+// A whole batch through k2t::read_pair, the per-thread body of the kernel: blocks with records at arbitrary offsets, optional
+// mates, the three kernel modes.  mode 0: counts only; 1: hashes at hash_off; 2: hashes at hash_off (upper bounds) and counts.
+extern "C" long k2t_host_batch(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2, const uint32_t *len2,
+                               uint32_t n_reads, uint32_t k, uint32_t w, int mode, uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes)
+{
+    if (k < 1 || k > k2t::kMaxK || w < k || w - k + 1 > k2t::kMaxW)
+        return -1;
+    const uint32_t W = w - k + 1;
+    const uint32_t T = k2t::kThreads;
+    uint64_t      *ring = (uint64_t *)malloc((size_t)W * T * 8);
+    memset(ring, 0xA5, (size_t)W * T * 8);
+    const uint64_t seed = 0x8F3F73B5CF1C9ADEull >> (64 - 2 * k);
+    const uint64_t mask = (1ull << (2 * k)) - 1;
+    k2t::LutEntry  lut[256];
+    for (uint32_t c = 0; c < 256; ++c)
+        lut[c] = k2t::lut_entry(c, k);
+    unsigned long long sum = 0;
+    for (uint32_t read = 0; read < n_reads; ++read)
+    {
+        const k2t::saddr_t ring_s = (k2t::saddr_t)(ring + read % T); // the slot column of thread read % T
+        uint32_t           total;
+        if (mode == 0)
+            total = k2t::read_pair<0>(read, blk1, off1, len1, blk2, off2, len2, k, w, seed, mask, (k2t::saddr_t)lut, ring_s, T * 8, counts, hash_off, hashes);
+        else if (mode == 1)
+            total = k2t::read_pair<1>(read, blk1, off1, len1, blk2, off2, len2, k, w, seed, mask, (k2t::saddr_t)lut, ring_s, T * 8, counts, hash_off, hashes);
+        else
+            total = k2t::read_pair<2>(read, blk1, off1, len1, blk2, off2, len2, k, w, seed, mask, (k2t::saddr_t)lut, ring_s, T * 8, counts, hash_off, hashes);
+        sum += total;
+    }
+    free(ring);
+    return (long)sum;
+}

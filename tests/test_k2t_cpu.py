@@ -25,12 +25,16 @@ def k2t(tmp_path_factory):
     lib.k2t_host_minimisers.restype = ctypes.c_long
     lib.k2t_host_minimisers.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64]
 
+    lib.k2t_host_batch.restype = ctypes.c_long
+    lib.k2t_host_batch.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+
     def run(seq, k, w, misalign=0, stride=1, lane=0):
         out = np.empty(len(seq) + 1, dtype=np.uint64)
         n = lib.k2t_host_minimisers(seq, len(seq), k, w, misalign, stride, lane, out.ctypes.data, out.size)
         assert n >= 0, (n, k, w, len(seq))
         return out[:n]
 
+    run.batch = lib.k2t_host_batch
     return run
 
 
@@ -84,3 +88,54 @@ def test_every_byte_value_decodes_like_dna4(k2t):
     for c in range(1, 256):  # ctypes c_char_p stops at NUL
         seq = b"ACGTTGCA" + bytes([c]) * 3 + b"GATTACA"
         assert k2t(seq, k, w).tolist() == O.minimiser_hash(seq, k, w).tolist(), c
+
+
+def _block(rng, seqs):
+    """A FASTQ block like the ones K1 indexes: (bytes with 64 bytes of slack on both sides, offsets, lengths)."""
+    parts, off, ln, pos = [b"#" * 64], [], [], 64
+    for i, s in enumerate(seqs):
+        head = b"@r%d some text\n" % i
+        parts += [head, s, b"\n+\n", b"I" * len(s), b"\n"]
+        off.append(pos + len(head))
+        ln.append(len(s))
+        pos += len(head) + 2 * len(s) + 4
+    parts.append(b"#" * 64)
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy(), np.asarray(off, dtype=np.uint32), np.asarray(ln, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("k,w", [(19, 31), (4, 8), (29, 60), (12, 12)])
+def test_batches_follow_the_classify_rules(k2t, k, w, paired):
+    """k2t::read_pair (the per-thread body of the kernel) over whole batches, in the kernel's three modes, against the hash lists
+    ganon-classify builds (GanonClassify.cpp:690-700: read shorter than the window skipped, short mate ignored, mate 1 ++ mate 2)."""
+    rng = np.random.default_rng(k * 100 + w + paired)
+    n = 300
+    lens = lambda: [int(rng.choice([w - 1, w, w + 1, 10, 75, 150, 151, 260])) for _ in range(n)]
+    mk = lambda L: bytes(rng.choice(list(b"ACGTN"), size=max(L, 1)).astype(np.uint8))
+    s1 = [mk(L) for L in lens()]
+    s2 = [mk(L) for L in lens()] if paired else None
+    b1, o1, l1 = _block(rng, s1)
+    b2, o2, l2 = _block(rng, s2) if paired else (None, None, None)
+    want = [O.read_hashes(a, s2[i] if paired else None, k, w) for i, a in enumerate(s1)]
+    want = [np.empty(0, dtype=np.uint64) if h is None else h for h in want]
+    ptr = lambda a: a.ctypes.data if a is not None else None
+    # mode 0: counts
+    counts = np.full(n, 77, dtype=np.uint32)
+    total = k2t.batch(ptr(b1), ptr(o1), ptr(l1), ptr(b2), ptr(o2), ptr(l2), n, k, w, 0, ptr(counts), None, None)
+    assert counts.tolist() == [h.size for h in want] and total == sum(h.size for h in want)
+    # mode 1: exact offsets
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(counts)
+    hashes = np.zeros(int(off[-1]) + 1, dtype=np.uint64)
+    k2t.batch(ptr(b1), ptr(o1), ptr(l1), ptr(b2), ptr(o2), ptr(l2), n, k, w, 1, None, ptr(off), ptr(hashes))
+    assert hashes[: int(off[-1])].tolist() == np.concatenate(want).tolist()
+    # mode 2: upper-bound offsets (one slot per window, k_hash_upper_bounds), counts written alongside
+    ub = np.asarray([max(a - w + 1, 0) + (max(int(l2[i]) - w + 1, 0) if paired else 0) for i, a in enumerate(l1.tolist())], dtype=np.uint64)
+    off2 = np.zeros(n + 1, dtype=np.uint64)
+    off2[1:] = np.cumsum(ub)
+    hashes2 = np.zeros(int(off2[-1]) + 1, dtype=np.uint64)
+    counts2 = np.full(n, 99, dtype=np.uint32)
+    k2t.batch(ptr(b1), ptr(o1), ptr(l1), ptr(b2), ptr(o2), ptr(l2), n, k, w, 2, ptr(counts2), ptr(off2), ptr(hashes2))
+    assert counts2.tolist() == counts.tolist()
+    for i in range(n):
+        assert hashes2[int(off2[i]) : int(off2[i]) + int(counts2[i])].tolist() == want[i].tolist(), i
