@@ -8,6 +8,10 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x --runxfail -p no:cacheprovider \
     -k "thread_per_read or reference_kats or lca_known_answers or build_sections_on_gpu or build_dropin or chunk_rule or shorter_than_the_window" > gpurun_out/new_legs.log 2>&1
 echo "new legs rc=$?" | tee -a gpurun_out/new_legs.log
+# 1b. memcheck of the thread-per-read kernel on the K2 tests (out-of-bounds shared / global accesses show up here first)
+GANON_B200_K2=thread timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider \
+    -k "minimisers_seqan3 or (minimisers_random and 19-31) or (minimisers_random and 4-8)" > gpurun_out/memcheck_k2thread.log 2>&1
+echo "memcheck rc=$?" | tee -a gpurun_out/memcheck_k2thread.log
 # 2. the whole GPU suite as the driver runs it
 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest -m gpu rc=$?" | tee -a gpurun_out/pytest_gpu.log
@@ -20,7 +24,7 @@ GANON_B200_K2=thread ncu --metrics gpu__time_duration.sum --clock-control none -
     python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_launches.log 2>&1
 GANON_B200_K2=thread ncu --set full --clock-control none --import-source on -k regex:k_minimisers_thread -c 1 -o gpurun_out/k2thread_full \
     python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/new_legs.log gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/new_legs.log gpurun_out/memcheck_k2thread.log gpurun_out/pytest_gpu.log
 python - <<'PY'
 import json
 for n in ("k2warp", "k2thread"):
