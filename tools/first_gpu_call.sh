@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 # 1. the legs marked "not yet run on hardware", without the expected-failure marker, each in its own process
-python -m pytest tests -m gpu -q -x --runxfail -p no:cacheprovider \
+python -m pytest tests -m gpu -q --runxfail -p no:cacheprovider \
     -k "thread_per_read or reference_kats or lca_known_answers or build_sections_on_gpu or build_dropin or chunk_rule or shorter_than_the_window" > gpurun_out/new_legs.log 2>&1
 echo "new legs rc=$?" | tee -a gpurun_out/new_legs.log
 # 1b. memcheck of the thread-per-read kernel on the K2 tests (out-of-bounds shared / global accesses show up here first)
