@@ -41,17 +41,56 @@ class IBFParams:
         return self.technical_bins * self.bin_size_bits
 
 
+# The reference computes in IEEE doubles and never traps: log(0) = -inf, x / 0 = +-inf or nan, and a non-finite value cast to
+# uint64_t comes out as 2^63 with the x86-64 code gcc emits.  Degenerate requests (--max-fp 1, filters of a few bits) rely on
+# that to end in "No valid sequences to build" instead of an exception, so the helpers below follow the same rules.
 def _u64(x: float) -> int:
-    """C++ conversion of a non-negative double to uint64_t (truncation)."""
+    """C++ conversion of a double to uint64_t: truncation; non-finite or out-of-range values give 2^63 (cvttsd2si)."""
+    if x != x or x in (math.inf, -math.inf) or x >= 18446744073709551616.0:
+        return 1 << 63
+    if x <= -1.0:
+        return int(x) % (1 << 64)
     return int(x)
+
+
+def _log(x: float) -> float:
+    return math.log(x) if x > 0 else (-math.inf if x == 0 else math.nan)
+
+
+def _exp(x: float) -> float:
+    try:
+        return math.exp(x)
+    except OverflowError:
+        return math.inf
+
+
+def _div(a: float, b: float) -> float:
+    if b != 0:
+        return a / b
+    if a == 0 or a != a:
+        return math.nan
+    return math.copysign(math.inf, a) * math.copysign(1.0, b)
+
+
+def _pow(a: float, b: float) -> float:
+    try:
+        return math.pow(a, b)
+    except OverflowError:
+        return math.inf
+    except ValueError:
+        return math.nan
+
+
+def _ceil(x: float) -> float:
+    return float(math.ceil(x)) if math.isfinite(x) else x
 
 
 def bin_bits_for_fp(max_fp: float, n_hashes: int, hash_functions: int = 0) -> int:
     """Bits of one bin for `n_hashes` elements at false-positive rate `max_fp` (GanonBuild.cpp:290-305): with the optimal
     number of hash functions when none is given, else for that number."""
     if hash_functions == 0:
-        return _u64(math.ceil((n_hashes * math.log(max_fp)) / math.log(1.0 / math.pow(2, math.log(2)))))
-    return _u64(math.ceil(n_hashes * (-hash_functions / math.log(1 - math.exp(math.log(max_fp) / hash_functions)))))
+        return _u64(_ceil(_div(n_hashes * _log(max_fp), _log(1.0 / math.pow(2, math.log(2))))))
+    return _u64(_ceil(n_hashes * _div(-hash_functions, _log(1 - _exp(_div(_log(max_fp), hash_functions))))))
 
 
 def pick_hash_functions(bin_size_bits: int, n_hashes: int, requested: int, limit: int = 5) -> int:
@@ -59,7 +98,7 @@ def pick_hash_functions(bin_size_bits: int, n_hashes: int, requested: int, limit
     clamped to 1..limit (0 and values above the limit become the limit)."""
     h = requested
     if h == 0:
-        h = int(math.log(2) * (bin_size_bits / float(n_hashes))) & 0xFF  # static_cast<uint8_t>
+        h = _u64(math.log(2) * _div(bin_size_bits, float(n_hashes))) & 0xFF  # static_cast<uint8_t>
     if h > limit or h == 0:
         h = limit
     return h
@@ -67,7 +106,7 @@ def pick_hash_functions(bin_size_bits: int, n_hashes: int, requested: int, limit
 
 def split_bins(counts: Iterable[int], n_hashes: int) -> int:
     """Bins needed when no bin holds more than n_hashes elements (GanonBuild.cpp:336-347)."""
-    return sum(_u64(math.ceil(c / float(n_hashes))) for c in counts)
+    return sum(_u64(_ceil(_div(c, float(n_hashes)))) for c in counts)
 
 
 def padded_bins(n_bins: int) -> int:
@@ -77,16 +116,16 @@ def padded_bins(n_bins: int) -> int:
 
 def bloom_fp(bin_size_bits: int, hash_functions: int, n_hashes: int) -> float:
     """Theoretical false-positive rate of one bin (GanonBuild.cpp:373-380)."""
-    return math.pow(1 - math.exp(-hash_functions / (bin_size_bits / float(n_hashes))), hash_functions)
+    return _pow(1 - _exp(_div(-hash_functions, _div(bin_size_bits, float(n_hashes)))), hash_functions)
 
 
 def split_correction(max_split_bins: int, max_fp: float, hash_functions: int, n_hashes: int) -> float:
     """Growth of a bin that keeps the rate of a target spread over `max_split_bins` bins at max_fp
     (multiple testing; GanonBuild.cpp:350-362)."""
-    target_fpr = 1.0 - math.exp(math.log(1.0 - max_fp) / max_split_bins)
+    target_fpr = 1.0 - _exp(_div(_log(1.0 - max_fp), max_split_bins))
     grown = bin_bits_for_fp(target_fpr, n_hashes, hash_functions)
     base = bin_bits_for_fp(max_fp, n_hashes, hash_functions)
-    return float(grown) / base  # ZeroDivisionError where the reference divides by an integer zero -> inf: handled by the caller
+    return _div(float(grown), base)
 
 
 def real_fp(counts: Iterable[int], max_hashes_bin: int, bin_size_bits: int, hash_functions: int) -> Tuple[float, float]:
@@ -102,7 +141,7 @@ def real_fp(counts: Iterable[int], max_hashes_bin: int, bin_size_bits: int, hash
             fp = 0.0
         else:
             n_hashes_bin = _u64(math.ceil(c / float(n_bins_target)))
-            fp = 1.0 - math.pow(1.0 - bloom_fp(bin_size_bits, hash_functions, n_hashes_bin), n_bins_target)
+            fp = 1.0 - _pow(1.0 - bloom_fp(bin_size_bits, hash_functions, n_hashes_bin), n_bins_target)
         highest = max(highest, fp)
         total += fp
         n += 1
@@ -127,7 +166,7 @@ def choose_ibf_params(hashes_count: Dict[str, int], max_fp: float = 0.05, filter
         cap = n - 1
         bins = split_bins(counts, cap)
         if filter_size:
-            bits = _u64((filter_size / float(padded_bins(bins))) * MIB_BITS)
+            bits = _u64(_div(filter_size, float(padded_bins(bins))) * MIB_BITS)
             h = pick_hash_functions(bits, cap, hash_functions, max_hash_functions)
         elif hash_functions == 0:
             bits = bin_bits_for_fp(max_fp, cap)
@@ -138,20 +177,15 @@ def choose_ibf_params(hashes_count: Dict[str, int], max_fp: float = 0.05, filter
         most_splits = _u64(math.ceil(largest / float(cap)))
         fp, filter_bits = 0.0, 0
         if filter_size:
-            fp = 1 - math.pow(1.0 - bloom_fp(bits, h, cap), most_splits)
+            fp = 1 - _pow(1.0 - bloom_fp(bits, h, cap), most_splits)
             min_fp = min(min_fp, fp)
         else:
             per_split = _u64(math.ceil(largest / float(most_splits)))
             approx = min(bloom_fp(bits, h, per_split), max_fp)
-            try:
-                rate = split_correction(most_splits, approx, h, cap)
-            except ZeroDivisionError:
-                rate = math.inf
-            if math.isinf(rate) or math.isnan(rate):
-                break
+            rate = split_correction(most_splits, approx, h, cap)
             bits = _u64(bits * rate)
-            filter_bits = bits * padded_bins(bins)
-            if filter_bits == 0:
+            filter_bits = (bits * padded_bins(bins)) & 0xFFFFFFFFFFFFFFFF
+            if filter_bits == 0 or math.isinf(rate):  # GanonBuild.cpp:541-542
                 break
             if filter_bits < min_filter or min_filter == 0:
                 min_filter = filter_bits
@@ -168,9 +202,10 @@ def choose_ibf_params(hashes_count: Dict[str, int], max_fp: float = 0.05, filter
     best = IBFParams()
     best_score = 0.0
     for cap, bins, filter_bits, fp in sims:
-        var_ratio = fp / min_fp if filter_size else filter_bits / float(min_filter)
-        bins_ratio = bins / float(min_bins)
-        score = (1 + math.pow(tilt, 2)) * ((var_ratio * bins_ratio) / ((w_var * var_ratio) + (w_bins * bins_ratio)))
+        # (0 / 0 = nan when every simulated rate underflows to 0: the first simulation then wins, as in the reference)
+        var_ratio = _div(fp, min_fp) if filter_size else _div(filter_bits, float(min_filter))
+        bins_ratio = _div(bins, float(min_bins))
+        score = (1 + math.pow(tilt, 2)) * _div(var_ratio * bins_ratio, (w_var * var_ratio) + (w_bins * bins_ratio))
         if score < best_score or best_score == 0:
             best_score = score
             if filter_size:
