@@ -776,17 +776,21 @@ def _parse_reads_config(cfg: GanonClassifyConfig) -> Optional[Dict[str, List[Tup
     if cfg.batch_reads:
         for bf in cfg.batch_reads:
             with open(bf) as fh:
-                for line in fh.read().split("\n"):
-                    if line == "":
-                        continue
+                lines = fh.read().split("\n")
+                if lines and lines[-1] == "":
+                    lines.pop()  # std::getline: the text after the last newline is a line only if it is not empty
+                for line in lines:
                     fields = line.split("\t")
-                    if len(fields) <= 1:
+                    if fields[-1] == "":
+                        fields.pop()  # getline on the fields: nothing follows a trailing tab, and an empty line has no field
+                    if len(fields) <= 1:  # this includes blank lines
                         print("ERROR: invalid --batch-reads file (prefix <tab> file1 [<tab> file2])", file=sys.stderr)
                         return None
-                    for p in fields[1:3]:
+                    for p in fields[1:3] if len(fields) == 3 else fields[1:2]:
                         if not os.path.exists(p) or os.path.getsize(p) == 0:
                             print("ERROR: file not found/empty: " + p, file=sys.stderr)
                             return None
+                    # exactly three fields make a pair; with four or more only the first file is used
                     rc.setdefault(fields[0], []).append((fields[1], fields[2] if len(fields) == 3 else ""))
     else:
         for f in cfg.single_reads:

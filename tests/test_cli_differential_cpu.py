@@ -104,3 +104,39 @@ def test_validation_matches_the_reference_binary(files, first):
             assert err.getvalue().strip() == pr.stderr.strip(), (seed, a)
         accepted += ok
     assert accepted >= 5  # both outcomes are exercised
+
+
+BATCH_FILES = {
+    # name: (content with {r1} {r2} {missing} {empty}, valid?)
+    "blank_line_in_the_middle": "p\t{r1}\n\nq\t{r2}\n",
+    "blank_line_at_the_end": "p\t{r1}\n\n",
+    "one_field": "p\n",
+    "only_a_tab": "\t\n",
+    "trailing_tab_single": "p\t{r1}\t\n",
+    "missing_second_file": "p\t{r1}\t{missing}\n",
+    "empty_first_file": "p\t{empty}\n",
+    "four_fields_use_the_first_file": "p\t{r1}\t{missing}\textra\n",
+    "empty_prefix": "\t{r1}\n",
+    "no_final_newline": "p\t{r1}\t{r2}",
+}
+
+
+@pytest.mark.parametrize("name", sorted(BATCH_FILES))
+def test_batch_reads_files_are_read_like_the_reference(files, name, tmp_path):
+    """parse_reads_config (GanonClassify.cpp:289-351): std::getline semantics for lines and tab-separated fields.  A batch file the
+    reference rejects must be rejected with the same message; one it accepts must get past this step (it then fails later for
+    lack of a GPU, which the reference binary does not need)."""
+    from ganon_b200 import classify as K
+
+    bf = str(tmp_path / "b.tsv")
+    open(bf, "w").write(BATCH_FILES[name].format(**files))
+    a = ["-b", bf, "-i", files["ibf"], "-o", str(tmp_path / "out"), "--quiet"]
+    pr = subprocess.run([F.REF_BIN] + a, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    cfg = cli.parse(a)
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err):
+        assert cfg.validate()
+        rc = K._parse_reads_config(cfg)
+    assert (rc is not None) == (pr.returncode == 0), (name, pr.stderr, err.getvalue())
+    if rc is None:
+        assert err.getvalue().strip() == pr.stderr.strip()
