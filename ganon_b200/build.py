@@ -304,6 +304,8 @@ def parse_input_table(path: str, quiet: bool = False) -> Tuple[Dict[str, List[st
             if not line:
                 continue
             fields = line.split("\t")
+            if len(fields) > 1 and fields[-1] == "":
+                fields.pop()  # std::getline on the fields: nothing follows a trailing tab
             f = fields[0]
             if not os.path.exists(f) or os.path.getsize(f) == 0:
                 if not quiet:

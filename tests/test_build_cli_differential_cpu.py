@@ -103,3 +103,18 @@ def test_builder_options_match_the_reference(files, first):
         assert (x.max_fp, x.true_max_fp) == (y.max_fp, y.true_max_fp) and x.true_avg_fp == pytest.approx(y.true_avg_fp, rel=1e-12, nan_ok=True), (seed, a)
         assert sorted(x.hashes_count) == sorted(y.hashes_count), (seed, a)
     assert accepted >= 3
+
+
+@pytest.mark.parametrize("table", ["{fa}\tA\t\n", "{fa}\t\n", "{fa}\tA\tseqid\n{fa2}\tB\n", "{fa}\n{fa2}\tB", "{missing}\tA\n{fa}\tB\n"])
+def test_input_tables_are_read_like_the_reference(files, table, tmp_path):
+    """parse_input_file (GanonBuild.cpp:86-137): a trailing tab adds no field, a line with three fields names no target, a file
+    that does not exist is skipped; same targets and hash counts as the reference builder."""
+    fa, fa2 = os.path.join(files["dir"], "g0.fa"), os.path.join(files["dir"], "g1.fa")
+    tsv = str(tmp_path / "in.tsv")
+    open(tsv, "w").write(table.format(fa=fa, fa2=fa2, missing=files["missing"]))
+    ref_out, out = str(tmp_path / "ref.ibf"), str(tmp_path / "mine.ibf")
+    pr = subprocess.run([REF_BUILD, "-i", tsv, "-o", ref_out, "-k", "19", "-w", "31", "-p", "0.05", "--quiet"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    ok = B.run_build(B.GanonBuildConfig(input_file=tsv, output_file=out, quiet=True), backend=OracleBackend())
+    assert bool(ok) == (pr.returncode == 0), pr.stderr
+    if ok:
+        assert sorted(formats.read_ibf(out).hashes_count) == sorted(formats.read_ibf(ref_out).hashes_count)
