@@ -3,7 +3,7 @@ g++ (tests/native/reads_host.cpp), checked on hand-written inputs, for independe
 oracle/_ref exists -- differentially against the UNMODIFIED reference binary on randomly formatted FASTA / FASTQ files
 (wrapped lines, blanks, digits, CRLF, `;` headers, blanks before ids, missing final newline, illegal letters with the
 chunk-loss rule of GanonClassify.cpp:1220-1287).  tests/reader_util.py holds the machinery; `python -m tests.reader_util N`
-runs a long campaign (round 1: 950 seeds, no mismatch; one input made the reference itself crash)."""
+runs a long campaign (round 1: 2850 seeds, no mismatch; a dozen inputs made the reference itself crash or hang)."""
 import os
 import subprocess
 
