@@ -546,7 +546,7 @@ def main():
                 "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, %d GiB filter gathered at random" % (pool, blocks[0][0].size * (2 if wl["paired"] else 1) >> 20, int(info.device_bytes) >> 30),
                 "timing": "CUDA events on the launch stream around the K steps (max over ranks); wall %.1f ms" % wall_ms,
                 "minimisers_per_read": minimisers / max(1, args.steps * R * units),
-                "k2_kernel": "thread per read (k2_thread.cuh)" if os.environ.get("GANON_B200_K2", "").startswith("t") else "warp per read",
+                "k2_kernel": "warp per read" if os.environ.get("GANON_B200_K2", "").startswith("w") else "thread per read (k2_thread.cuh)",
             },
             "roofline": {
                 "kernel": "k_hibf_count" if wl.get("hibf") else "k_ibf_count",
@@ -689,7 +689,7 @@ def sharded_arm(args, wl, rank, local_rank, world):
                 "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, filter shard gathered at random" % (pool, blocks[0][0].size * units >> 20),
                 "timing": "CUDA events on the launch stream around the K steps (max over ranks); wall %.1f ms" % wall_ms,
                 "minimisers_per_read": minimisers / max(1, args.steps * R * units),
-                "k2_kernel": "thread per read (k2_thread.cuh)" if os.environ.get("GANON_B200_K2", "").startswith("t") else "warp per read",
+                "k2_kernel": "warp per read" if os.environ.get("GANON_B200_K2", "").startswith("w") else "thread per read (k2_thread.cuh)",
                 "exchanged_tuple_bytes_per_step": exchanged // max(1, args.steps),
             },
             "roofline": {

@@ -147,3 +147,4 @@ def planted_hashes(genomes: np.ndarray, minimiser_fn: Callable[[bytes], np.ndarr
         bs.append(b[np.arange(u.size) % b.size])
         counts.append(int(u.size))
     return np.concatenate(hs), np.concatenate(bs), counts
+

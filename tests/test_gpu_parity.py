@@ -42,16 +42,17 @@ def test_minimisers_random_and_adversarial(k, w):
         assert minimisers(s, k, w).tolist() == O.minimiser_hash(s, k, w).tolist(), (k, w, len(s), s[:40])
 
 
-@pytest.mark.xfail(strict=False, reason="K2t was written after the GPU budget of round 1 was spent: its per-thread core is pinned on the CPU (test_k2t_cpu.py), the kernel has not run on hardware")
-def test_thread_per_read_minimiser_kernel_passes_the_k2_and_scenario_tests():
-    """GANON_B200_K2=thread (k2_thread.cuh) is read once per process: re-run the K2 tests, the golden scenarios (single,
-    paired, FASTA, several levels) and the oracle session test of this file in a child process with the switch set."""
+def test_warp_per_read_minimiser_kernel_passes_the_k2_and_scenario_tests():
+    """The thread-per-read kernel (k2_thread.cuh) is the default for k <= 29, w-k+1 <= 32; GANON_B200_K2=warp (read once
+    per process) keeps the warp-per-read kernel, which still serves every other (k, w): re-run the K2 tests, the golden
+    scenarios (single, paired, FASTA, several levels) and the oracle session test of this file in a child process with
+    the switch set, so that both kernels stay pinned."""
     import subprocess
     import sys
 
-    if os.environ.get("GANON_B200_K2", "").startswith("t"):
+    if os.environ.get("GANON_B200_K2", "").startswith("w"):
         pytest.skip("already inside the child run")
-    env = dict(os.environ, GANON_B200_K2="thread")
+    env = dict(os.environ, GANON_B200_K2="warp")
     sel = "minimisers_seqan3 or minimisers_random or (golden_scenarios and device) or session_matches_oracle or device_and_host_record_index"
     done = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", sel, "-p", "no:cacheprovider"], env=env,
                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
@@ -281,7 +282,6 @@ def test_parse_error_truncation_rule(golden_dbs, tmp_path):
     assert int(rep["#total_unclassified"]) + int(rep["#total_classified"]) == 800
 
 
-@pytest.mark.xfail(strict=False, reason="rule corrected after the GPU budget of round 1 was spent (CPU differential against the reference binary, tests/test_reader_cpu.py): not yet run on hardware")
 @pytest.mark.parametrize("bad_at,kept", [(0, 0), (1, 0), (399, 0), (400, 0), (401, 400), (800, 400), (801, 800)])
 def test_parse_error_chunk_rule_at_chunk_boundaries(golden_dbs, tmp_path, bad_at, kept):
     """The reference's reader looks one record ahead: record e fails inside the chunk that holds record e - 1, so
@@ -493,7 +493,6 @@ def test_hibf_created_in_hbm_matches_oracle(tmp_path, finish_mode):
 
 
 # ------------------------------------------------------------------------------------------------------------------ build drop-in
-@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on hardware")
 def test_build_dropin_on_gpu_writes_the_oracle_backend_file(tmp_path):
     """`ganon-build` drop-in with K2 and the insertion on the device against the same orchestration with the oracle
     standing in for the device (tests/test_build_cpu.py pins that one to the reference builder): identical files."""

@@ -27,7 +27,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BUILD = os.path.join(ROOT, "oracle", "_ref", "ganon-build")
 REF_DATA = "/root/reference/tests/ganon-build/data"
 SEQS = json.load(open(os.path.join(SU.GOLDEN, "build_kats.json")))
-not_yet_on_hardware = pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on hardware")
 
 
 def default_config(prefix, **kw):
@@ -177,7 +176,6 @@ def test_build_modes_on_the_reference_test_genomes(tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 @pytest.mark.parametrize("sec", SECTIONS, ids=[s[0] for s in SECTIONS])
 def test_build_sections_on_gpu(sec, tmp_path):
     """The same sections with K2 and the insertion on the device; the file must equal the oracle-backend one byte for byte
@@ -218,7 +216,6 @@ def test_sequences_shorter_than_the_window_count_like_the_reference(tmp_path):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_sequences_shorter_than_the_window_on_gpu(tmp_path):
     (tmp_path / "gpu").mkdir()
     (tmp_path / "cpu").mkdir()

@@ -27,7 +27,6 @@ REF_CLASSIFY = os.path.join(ROOT, "oracle", "_ref", "ganon-classify")
 REF_BUILD = os.path.join(ROOT, "oracle", "_ref", "ganon-build")
 CASE_IDS = [c["name"] for c in K.CASES]
 # the GPU legs below were written after the GPU budget of round 1 was spent; remove the marker once they have run on a B200
-not_yet_on_hardware = pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on hardware")
 
 
 @pytest.fixture(scope="module")
@@ -148,7 +147,6 @@ def test_reference_kats_reference_binary(name, kat, ref_ibf):
 
 # ------------------------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@not_yet_on_hardware
 @pytest.mark.parametrize("name", CASE_IDS)
 def test_reference_kats_dropin(name, kat):
     from ganon_b200 import cli
@@ -260,7 +258,6 @@ def test_reference_kats_batch_reads_reference_binary(kat):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_reference_kats_batch_reads_dropin(kat):
     _batch_reads_kats(kat, _run_dropin, "gpu")
 
@@ -271,6 +268,5 @@ def test_lca_known_answers_through_reference_binary(tmp_path):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_lca_known_answers_through_k4(tmp_path):
     _lca_kats_through_classify(tmp_path, _run_dropin)
