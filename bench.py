@@ -1,13 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the ganon-classify hot path on B200 (contract: see the task prompt; numbers: BASELINE.md).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|tiny] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5|tiny] [--impl reference]
+
+Default workload: c3 = BASELINE.json configs[2] (64 GiB flat IBF, 65 536 bins, paired 150 bp reads), the configuration the
+north-star targets are quoted on.  N = 1: the c3 line, with c2 (configs[1]) and c4 (configs[3], HIBF) as sub-records under
+"extra".  N > 1 (torchrun): the c3 filter bin-sharded over the ranks ("strong" scaling; the N = 1 line is the same
+workload on one shard), with the replicated-database / read-sharded arm as a sub-record.
 
 One "step" = one pass of the hot path (K2 minimisers -> K3 IBF count -> sort of the sparse matches -> K4 rel-filter /
 fpr-query / LCA / output lines) over one batch of synthetic 150 bp reads.  `value` = reads/s with the FASTQ batch already in HBM; `e2e` = the same metric through the
 C-ABI call gnb_session_classify with HOST (pinned) FASTQ buffers: record indexing, H2D, kernels, D2H and the host
 finishing stage (rel-filter, fpr-query, formatting of the `.all` lines) inside the timed region.
-N > 1: one process per GPU (torchrun), database replicated, reads sharded -- no data-path collective ("weak").
+`--impl reference`: the unmodified reference binary (oracle/_ref/ganon-classify, all host threads), ONE invocation over
+steps x n reads of the same workload, on a database file written on the CPU by oracle/synthdb (the same bits the GPU arm
+generates in HBM) -- that process never loads libganon_b200.so.
 """
 from __future__ import annotations
 
@@ -30,13 +37,13 @@ sys.path.insert(0, ROOT)
 METRIC = "reads_per_sec_150bp"
 WORKLOADS = {
     # BASELINE.json configs[1]: 8 GiB flat IBF, 4096 bins, k=19 w=31 h=4, single-end 150 bp
-    "c2": dict(bins=4096, bin_size=1 << 24, h=4, k=19, w=31, paired=False, reads_per_step=1 << 21, genome_len=10000, desc="8 GiB flat IBF, 4096 bins, k=19 w=31 h=4, 150 bp single-end"),
+    "c2": dict(bins=4096, bin_size=1 << 24, h=4, k=19, w=31, paired=False, reads_per_step=1 << 21, cpu_sample=1 << 20, ref_reads_per_step=1 << 19, genome_len=10000, desc="8 GiB flat IBF, 4096 bins, k=19 w=31 h=4, 150 bp single-end"),
     # BASELINE.json configs[2]: 64 GiB flat IBF, 65536 bins, paired
-    "c3": dict(bins=65536, bin_size=1 << 23, h=4, k=19, w=31, paired=True, reads_per_step=1 << 18, genome_len=4000, desc="64 GiB flat IBF, 65536 bins, k=19 w=31 h=4, 150 bp paired"),
+    "c3": dict(bins=65536, bin_size=1 << 23, h=4, k=19, w=31, paired=True, reads_per_step=1 << 18, cpu_sample=1 << 17, ref_reads_per_step=1 << 15, genome_len=4000, desc="64 GiB flat IBF, 65536 bins, k=19 w=31 h=4, 150 bp paired"),
     # BASELINE.json configs[3]: 3-level HIBF, top 1024 bins (256 merged) -> 256 children of 64 bins (4 merged each) -> 1024
     # grandchildren of 64 bins; 16 + 16 + 8 = 40 GiB; 81 376 user bins, some split over two technical bins
     "c4": dict(hibf=True, top_bins=1024, top_rows=1 << 27, child_bins=64, child_rows=1 << 23, child_merged=4, grand_bins=64, grand_rows=1 << 20, h=4, k=19, w=31,
-               paired=False, reads_per_step=1 << 21, genome_len=3000, desc="3-level HIBF, 1024-bin top level, 40 GiB, k=19 w=31 h=4, 150 bp single-end"),
+               paired=False, reads_per_step=1 << 21, cpu_sample=1 << 18, ref_reads_per_step=1 << 16, genome_len=3000, desc="3-level HIBF, 1024-bin top level, 40 GiB, k=19 w=31 h=4, 150 bp single-end"),
     # the same shape at 1/64 of the rows (self-test of the generator)
     "c4tiny": dict(hibf=True, top_bins=1024, top_rows=1 << 21, child_bins=64, child_rows=1 << 17, child_merged=4, grand_bins=64, grand_rows=1 << 14, h=4, k=19, w=31,
                    paired=False, reads_per_step=1 << 16, genome_len=3000, desc="3-level HIBF, 1024-bin top level, 640 MiB (bench self-test)"),
@@ -49,6 +56,7 @@ REL_CUTOFF, REL_FILTER, FPR_QUERY = 0.75, 0.1, 1e-5  # ganon CLI defaults (src/g
 DB_SEED, READ_SEED = 1, 2
 CACHE = os.environ.get("GANON_B200_BENCH_DIR", "/tmp/ganon_b200_bench")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ganon-classify")
+REF_FLAGS = "g++ -std=c++20 -O3 -DNDEBUG -mavx2 -mbmi2 -mpopcnt (oracle/Makefile; built where /root/reference exists, so not -march=native of the bench box)"
 
 
 def measured_peak_gbs():
@@ -311,6 +319,41 @@ def write_sample(wl_name, b1, b2, n_reads, tag):
     return p1, p2
 
 
+def db_file_matches_hbm(db, path, windows=32, words=1 << 14, seed=7):
+    """Spot check that the cached database file holds the bits that are in HBM: `windows` random runs of 64-bit words of
+    the flat filter's payload (the file may have been written on the CPU by oracle/synthdb in the reference arm)."""
+    i = db.info()
+    if i.is_hibf:
+        return None
+    n_words = i.bin_size_bits * i.bin_words
+    off0 = os.path.getsize(path) - n_words * 8  # the payload is the tail of the file (formats.py)
+    rng = np.random.default_rng(seed)
+    ok = True
+    with open(path, "rb") as f:
+        for _ in range(windows):
+            w0 = int(rng.integers(0, max(1, n_words - words)))
+            n = int(min(words, n_words - w0))
+            f.seek(off0 + w0 * 8)
+            want = np.frombuffer(f.read(n * 8), dtype="<u8")
+            ok = ok and bool((db.read_words(w0, n) == want).all())
+    return {"windows": windows, "words_per_window": words, "identical": ok}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from a committed `ncu --set full`
+# capture: (bytes, reads per launch of that capture, file under profiles/).  Only attached to a line whose launch has the
+# same shape; otherwise "traffic" is null.
+TRAFFIC_CAPTURES = {
+    "c2": (75373784000 + 10292992, 1 << 21, "profiles/r01_k3_ncu_summary.md"),
+}
+
+
+def traffic_for(wl_name, reads_per_launch):
+    cap = TRAFFIC_CAPTURES.get(wl_name)
+    if cap and cap[1] == reads_per_launch:
+        return cap[0], cap[2]
+    return None, None
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -318,17 +361,18 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ganon_b200", choices=["ganon_b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("GANON_B200_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("GANON_B200_WORKLOAD", ""), choices=[""] + sorted(WORKLOADS), help="default: c3 with c2 / c4 as sub-records (N = 1), c3 bin-sharded (N > 1)")
+    ap.add_argument("--extras", default=None, help="comma list of workloads measured as sub-records of the line (default: c2,c4 at N = 1 when --workload is not given; 'none' to skip)")
     ap.add_argument("--reads-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=4, help="distinct read batches cycled through the steps")
-    ap.add_argument("--cli", action="store_true", help="also time the drop-in command line (bin/ganon-classify) on a FASTQ file of the pool's batches and the saved database")
+    ap.add_argument("--cli", action="store_true", help="also time the drop-in command line (bin/ganon-classify) on a FASTQ file of the pool's batches and the saved database (always on for the c2 sub-record of the default run)")
     ap.add_argument("--em", action="store_true", help="also time the EM reassignment (SURVEY 8f.1) on the matches of the e2e batches kept in HBM, next to the CPU restatement of src/ganon/reassign.py on the same .all text")
-    ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (every rank classifies the same reads on its columns; tuples all-gathered over NCCL): strong scaling")
+    ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (the default for N > 1)")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: replicated database, reads sharded (weak scaling) as the headline instead of the bin-sharded arm")
     args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.reads_per_step:
-        wl["reads_per_step"] = args.reads_per_step
+    explicit = bool(args.workload)
+    wl_name = args.workload or "c3"
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -338,7 +382,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        return reference_arm(args, wl)
+        return reference_arm(args, wl_name)
 
     import torch
     import torch.distributed as dist
@@ -351,12 +395,49 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = dict(rank=rank, local_rank=local_rank, world=world, numa=bind_to_gpu_numa(local_rank) if world > 1 else "single process: unbound")
+
+    if args.extras is None:
+        extras = ["c2", "c4"] if (world == 1 and not explicit) else []
+    else:
+        extras = [e for e in args.extras.split(",") if e and e != "none"]
+
+    if world > 1 and not args.replicas:
+        line = sharded_arm(args, wl_name, ctx)
+        if not explicit:
+            # the other way to use N GPUs (the database fits one GPU): replicas, reads sharded, no data-path collective
+            sub = measure(args, "c2", ctx, cpu=False, cli=False, em=False)
+            if rank == 0:
+                line.setdefault("extra", {})["replicas_c2"] = sub
+    else:
+        line = measure(args, wl_name, ctx, cpu=not args.no_cpu_baseline, cli=args.cli, em=args.em)
+        for e in extras:
+            try:
+                sub = measure(args, e, ctx, cpu=not args.no_cpu_baseline, cli=(e == "c2"), em=False)
+            except Exception as ex:  # a sub-record must not take the headline with it
+                sub = {"error": str(ex)[:300]}
+            if rank == 0:
+                line.setdefault("extra", {})[e] = sub
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure(args, wl_name, ctx, cpu, cli, em):
+    """One workload on every rank's own GPU: database replicated, reads sharded over the ranks (no data-path collective).
+    Returns the bench line (rank 0; None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
     from ganon_b200.classify import Session, result_text
 
-    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single process: unbound"
-    if args.shard_db:
-        return sharded_arm(args, wl, rank, local_rank, world)
-    dev = local_rank
+    rank, world, dev = ctx["rank"], ctx["world"], ctx["local_rank"]
+    wl = dict(WORKLOADS[wl_name])
+    if args.reads_per_step:
+        wl["reads_per_step"] = args.reads_per_step
     R = wl["reads_per_step"]
     t_setup = time.perf_counter()
     db, genomes = build_database(wl, dev)
@@ -453,10 +534,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
     clocks = sampler.stop()
+    e2e_sess.close()
 
     # ------------------------------------------------------------------ EM reassignment from the matches kept in HBM (--em)
     em_line = None
-    if args.em and rank == 0:
+    if em and rank == 0:
         # a looser cutoff than the classification default so that many reads have several candidate targets
         em_sess = Session([db], [0.25], [1.0], [1.0], output_all=True, device=dev)
         em_sess.keep_matches(True)
@@ -481,48 +563,28 @@ def main():
                    "identical": ones[""].decode() == o_ones[""] and new_rep.decode() == o_rep, "thresholds": "rel-cutoff 0.25 rel-filter 1 fpr-query 1"}
         em_sess.close()
 
+    # ------------------------------------------------------------------ CPU baseline + parity on a bounded sample (rank 0, N=1)
+    cpu_line = parity = file_check = None
+    if rank == 0 and world == 1 and cpu:
+        try:
+            cpu_line, parity, file_check = cpu_baseline(wl_name, wl, db, blocks[0], sessions[0], result_text)
+        except Exception as e:  # the bench line must still be printed
+            cpu_line = {"value": None, "unit": "reads/s", "cores": reference_threads(), "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
+
     # ------------------------------------------------------------------ the drop-in command line on files (--cli)
     cli_line = None
-    if args.cli and rank == 0 and world == 1:
-        ibf_path = ensure_ibf_file(args.workload, db)
-        fq1 = os.path.join(CACHE, "%s_cli.1.fq" % args.workload)
-        fq2 = os.path.join(CACHE, "%s_cli.2.fq" % args.workload) if wl["paired"] else None
-        reps = 4  # the pool's batches four times over: long enough for the fixed costs (buffers, first allocations) to amortise
-        with open(fq1, "wb") as f1:
-            for _ in range(reps):
-                for b1, _b2 in blocks:
-                    b1.tofile(f1)
-        if fq2:
-            with open(fq2, "wb") as f2:
-                for _ in range(reps):
-                    for _b1, b2 in blocks:
-                        b2.tofile(f2)
-        n_cli = reps * pool * R * (2 if wl["paired"] else 1)
-        reads = ["-p", fq1 + "," + fq2] if fq2 else ["-r", fq1]
-        cmd = [sys.executable, os.path.join(ROOT, "bin", "ganon-classify")] + (["--hibf"] if wl.get("hibf") else []) + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", os.path.join(CACHE, "cli_out"), "--verbose", "--device", str(dev)]
-        t0 = time.perf_counter()
-        pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-        wall = time.perf_counter() - t0
-        mc = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
-        ml = re.search(r"loading filter\(s\)\s+elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
-        cs = float(mc.group(1)) if mc else None
-        cli_line = {"rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
-                    "reads_per_s": n_cli / cs if cs else None, "all_bytes": os.path.getsize(os.path.join(CACHE, "cli_out.all")) if os.path.exists(os.path.join(CACHE, "cli_out.all")) else None,
-                    "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
-
-    # ------------------------------------------------------------------ CPU baseline + parity on a bounded sample (rank 0, N=1)
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cli and rank == 0 and world == 1:
         try:
-            cpu, parity = cpu_baseline(args, wl, db, blocks[0], host[0], sessions[0], result_text)
-        except Exception as e:  # the bench line must still be printed
-            cpu = {"value": None, "unit": "reads/s", "cores": reference_threads(), "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
+            cli_line = cli_leg(wl_name, wl, db, blocks, pool, R, dev)
+        except Exception as e:
+            cli_line = {"error": str(e)[:300]}
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = (k3_bytes / 1e9) / (ms_count / 1e3) if ms_count > 0 else 0.0
         units = 2 if wl["paired"] else 1  # reads per record
+        traffic, traffic_src = traffic_for(wl_name, R * units)
         line = {
             "metric": METRIC,
             "value": world * args.steps * R * units / (dev_ms / 1e3),
@@ -532,17 +594,18 @@ def main():
             "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True,
-            "scaling": "weak",
+            # N = 1 is the one-shard end of the bin-sharded strong-scaling series; replicas scale weakly
+            "scaling": "weak" if world > 1 else "strong",
             "vs_baseline": None,
             "dtype": "u64",
             "data": "synthetic",
             "config": {
-                "workload": args.workload + ": " + wl["desc"],
+                "workload": wl_name + ": " + wl["desc"],
                 "reads_per_step_per_gpu": R * units,
                 "db_bytes": int(info.device_bytes),
                 "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY),
                 "parallelism": "replicated db, reads sharded x%d" % world if world > 1 else "1 gpu",
-                "host_placement": numa,
+                "host_placement": ctx["numa"],
                 "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, %d GiB filter gathered at random" % (pool, blocks[0][0].size * (2 if wl["paired"] else 1) >> 20, int(info.device_bytes) >> 30),
                 "timing": "CUDA events on the launch stream around the K steps (max over ranks); wall %.1f ms" % wall_ms,
                 "minimisers_per_read": minimisers / max(1, args.steps * R * units),
@@ -556,30 +619,33 @@ def main():
                 "unit": "GB/s",
                 "frac": achieved / peak,
                 "peak_source": peak_src,
-                "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload),
+                "traffic": traffic,
+                "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": k3_bytes / max(1, args.steps),
                 "ms_per_launch": ms_count / max(1, args.steps),
-                "other_kernels_ms_per_step": {"k_minimisers(x2)+scan": ms_min / args.steps, "radix_sort": ms_sort / args.steps, "k_finish(select+scan+write)": ms_fin / args.steps},
+                "other_kernels_ms_per_step": {"k_minimisers+scan": ms_min / args.steps, "radix_sort": ms_sort / args.steps, "k_finish(select+scan+write)": ms_fin / args.steps},
             },
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu_line,
             "e2e": {"value": world * args.steps * R * units / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "last_step_breakdown_ms": last, "classified_reads_per_step": n_class // args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity": parity,
+            "db_file_check": file_check,
             "setup_s": t_setup,
         }
         if em_line is not None:
             line["em_reassign"] = em_line
         if cli_line is not None:
             line["cli"] = cli_line
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    for s in sessions:
+        s.close()
+    db.close()
+    del host, blocks
+    torch.cuda.empty_cache()
+    return line
 
 
-def sharded_arm(args, wl, rank, local_rank, world):
+def sharded_arm(args, wl_name, ctx):
     """--shard-db: the filter is split by bin-word columns over the ranks; every rank stages the same
     batch, runs K2 + K3 on its columns, the sparse tuples are all-gathered in HBM (NCCL) and sorted + finished (K4) on
     every rank.  Total work is fixed as N grows ("strong")."""
@@ -588,7 +654,10 @@ def sharded_arm(args, wl, rank, local_rank, world):
 
     from ganon_b200.sharded import ShardedSession
 
-    dev = local_rank
+    rank, world, dev = ctx["rank"], ctx["world"], ctx["local_rank"]
+    wl = dict(WORKLOADS[wl_name])
+    if args.reads_per_step:
+        wl["reads_per_step"] = args.reads_per_step
     R = wl["reads_per_step"]
     units = 2 if wl["paired"] else 1
     t_setup = time.perf_counter()
@@ -664,6 +733,7 @@ def sharded_arm(args, wl, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t[0])
     clocks = sampler.stop()
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = (k3_bytes / 1e9) / (ms_count / 1e3) if ms_count > 0 else 0.0
@@ -681,7 +751,7 @@ def sharded_arm(args, wl, rank, local_rank, world):
             "dtype": "u64",
             "data": "synthetic",
             "config": {
-                "workload": args.workload + ": " + wl["desc"],
+                "workload": wl_name + ": " + wl["desc"],
                 "reads_per_step": R * units,
                 "db_bytes_per_gpu": int(info.device_bytes),
                 "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY),
@@ -714,66 +784,149 @@ def sharded_arm(args, wl, rank, local_rank, world):
             "parity": None,
             "setup_s": t_setup,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        return line
+    return None
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_ibf_count launch from the committed ncu capture (profiles/)
-TRAFFIC_BYTES_PER_LAUNCH = {"c2": 75373784000 + 10292992}  # profiles/r01_k3_ncu_summary.md (2^21 reads per launch)
+
+def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
+    """bin/ganon-classify file to file: the pool's batches (four times over) as a FASTQ file, the saved database."""
+    ibf_path = ensure_ibf_file(wl_name, db)
+    fq1 = os.path.join(CACHE, "%s_cli.1.fq" % wl_name)
+    fq2 = os.path.join(CACHE, "%s_cli.2.fq" % wl_name) if wl["paired"] else None
+    reps = 4  # long enough for the fixed costs (buffers, first allocations) to amortise
+    with open(fq1, "wb") as f1:
+        for _ in range(reps):
+            for b1, _b2 in blocks:
+                b1.tofile(f1)
+    if fq2:
+        with open(fq2, "wb") as f2:
+            for _ in range(reps):
+                for _b1, b2 in blocks:
+                    b2.tofile(f2)
+    n_cli = reps * pool * R * (2 if wl["paired"] else 1)
+    reads = ["-p", fq1 + "," + fq2] if fq2 else ["-r", fq1]
+    cmd = [sys.executable, os.path.join(ROOT, "bin", "ganon-classify")] + (["--hibf"] if wl.get("hibf") else []) + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", os.path.join(CACHE, "cli_out"), "--verbose", "--device", str(dev)]
+    t0 = time.perf_counter()
+    pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    wall = time.perf_counter() - t0
+    mc = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+    ml = re.search(r"loading filter\(s\)\s+elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+    cs = float(mc.group(1)) if mc else None
+    out = {"rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
+           "reads_per_s": n_cli / cs if cs else None, "all_bytes": os.path.getsize(os.path.join(CACHE, "cli_out.all")) if os.path.exists(os.path.join(CACHE, "cli_out.all")) else None,
+           "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
+    for p in (fq1, fq2, os.path.join(CACHE, "cli_out.all")):
+        if p and os.path.exists(p):
+            os.remove(p)
+    return out
 
 
-def cpu_baseline(args, wl, db, block, host_block, sess, result_text):
-    """Reference ganon-classify (all host threads) on one batch; also a bit-exact parity check of that batch."""
+def cpu_baseline(wl_name, wl, db, block, sess, result_text):
+    """Reference ganon-classify (all host threads) on a sample of batch 0; also a bit-exact parity check of that sample
+    and a spot check of the database file against HBM."""
     if not os.path.exists(REF_BIN):
         raise RuntimeError("oracle/_ref/ganon-classify is not built")
-    ibf = ensure_ibf_file(args.workload, db)
-    n = min(wl["reads_per_step"], 1 << 20)
+    ibf = ensure_ibf_file(wl_name, db)
+    file_check = db_file_matches_hbm(db, ibf)
+    n = min(wl["reads_per_step"], wl.get("cpu_sample", 1 << 20))
     b1, b2 = block
     rec1 = b1.size // wl["reads_per_step"]
     s1 = b1[: n * rec1]
     s2 = b2[: n * (b2.size // wl["reads_per_step"])] if b2 is not None else None
-    p1, p2 = write_sample(args.workload, s1, s2, n, "sample")
+    p1, p2 = write_sample(wl_name, s1, s2, n, "sample")
     out = os.path.join(CACHE, "ref_out")
     threads = reference_threads()
     t = run_reference_binary(ibf, p1, p2, out, threads, hibf=bool(wl.get("hibf")))
     units = 2 if wl["paired"] else 1
-    cpu = {"value": n * units / t["classify_s"], "unit": "reads/s", "cores": threads, "kind": "reference", "sample": "%d reads of batch 0; reference's own classifying+printing time %.2f s (filter load %.1f s excluded)" % (n * units, t["classify_s"], t["load_s"])}
+    cpu = {"value": n * units / t["classify_s"], "unit": "reads/s", "cores": threads, "kind": "reference", "flags": REF_FLAGS,
+           "sample": "%d reads of batch 0; reference's own classifying+printing time %.2f s (filter load %.1f s excluded)" % (n * units, t["classify_s"], t["load_s"])}
     # parity: the same reads through the C ABI
     r = sess.classify(s1, s2, final=True)
     mine = sorted(result_text(r, "all").decode().splitlines())
     with open(out + ".all") as f:
         ref = sorted(l.rstrip("\n") for l in f)
-    parity = {"reads": n * units, "all_lines": len(ref), "identical": mine == ref}
-    return cpu, parity
+    parity = {"reads": n * units, "all_lines": len(ref), "identical": mine == ref, "against": "unmodified reference binary on the same reads and database file"}
+    for p in (p1, p2, out + ".all"):
+        if p and os.path.exists(p):
+            os.remove(p)
+    return cpu, parity, file_check
 
 
-def reference_arm(args, wl):
-    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample per step."""
-    import torch
+# ----------------------------------------------------------------------------------------------------------------------
+# --impl reference: this process never imports ganon_b200._lib / loads libganon_b200.so
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_db_file(wl_name, wl):
+    """The workload's database as a file, written on the CPU by oracle/synthdb (flat IBFs).  A copy left in the cache by
+    an earlier run (either arm) is reused: both writers produce the same bits (db_file_check in the GPU arm's line)."""
+    from ganon_b200 import synth  # numpy only
 
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, "%s_seed%d.%s" % (wl_name, DB_SEED, "hibf" if wl.get("hibf") else "ibf"))
+    genomes = None
+    if wl.get("hibf"):
+        if not os.path.exists(path):
+            raise RuntimeError("no CPU writer for the synthetic HIBF: run the GPU arm with --workload %s once (it saves the file)" % wl_name)
+        return path, None, "cached copy saved by the GPU arm"
+    genomes = synth.random_genomes(DB_SEED, wl["bins"], wl["genome_len"])
+    want = wl["bin_size"] * ((wl["bins"] + 63) // 64) * 8
+    if os.path.exists(path) and os.path.getsize(path) > want:
+        return path, genomes, "cached copy"
+    free = shutil.disk_usage(CACHE).free
+    if free < want * 1.1:
+        for f in os.listdir(CACHE):
+            if f.endswith((".ibf", ".hibf")) and not f.startswith(wl_name + "_seed"):
+                os.remove(os.path.join(CACHE, f))
+    tool = os.path.join(ROOT, "oracle", "synthdb")
+    if not os.path.exists(tool):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "synthdb"])
+    gfile = os.path.join(CACHE, "%s_genomes.bin" % wl_name)
+    genomes.tofile(gfile)
+    t0 = time.perf_counter()
+    out = subprocess.run([tool, path, gfile, str(wl["bins"]), str(wl["bin_size"]), str(wl["h"]), str(wl["k"]), str(wl["w"]), str(wl["genome_len"]), str(DB_SEED), str(target_hashes_for_density(wl)), str(reference_threads())],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    os.remove(gfile)
+    if out.returncode != 0:
+        raise RuntimeError("oracle/synthdb failed: " + out.stderr[-300:])
+    return path, genomes, "written by oracle/synthdb in %.0f s (words xor sum planted: %s)" % (time.perf_counter() - t0, out.stdout.strip())
+
+
+def reference_arm(args, wl_name):
+    """--impl reference: the reference's own CPU implementation (unmodified binary), all host threads: one invocation over
+    steps x n reads of the workload, filter load paid once, its own classifying+printing time / steps."""
+    wl = dict(WORKLOADS[wl_name])
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ganon-classify missing (build it with make -C oracle ref where /root/reference exists)"}))
         return 0
-    if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "the synthetic database is generated on the GPU; no CUDA device here"}))
+    try:
+        ibf, genomes, how = reference_db_file(wl_name, wl)
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": str(e)[:300]}))
         return 0
-    db, genomes = build_database(wl, 0)  # data generation only; the timed path below is the unmodified binary
-    ibf = ensure_ibf_file(args.workload, db)
-    db.close()
-    n = min(wl["reads_per_step"], 1 << 19)
+    if genomes is None:
+        from ganon_b200 import synth
+
+        genomes = synth.random_genomes(DB_SEED, len(hibf_layout(wl)[4]), wl["genome_len"])
+    n = min(wl["reads_per_step"], wl.get("ref_reads_per_step", 1 << 19))  # records per step: a bounded sample of the workload
     threads = reference_threads()
     units = 2 if wl["paired"] else 1
-    times = []
-    for i in range(args.warmup + args.steps):
-        b1, b2 = make_batch(wl, genomes, i % 2, n)
-        p1, p2 = write_sample(args.workload, b1, b2, n, "ref%d" % (i % 2))
-        t = run_reference_binary(ibf, p1, p2, os.path.join(CACHE, "ref_arm_out"), threads, hibf=bool(wl.get("hibf")))
-        if i >= args.warmup:
-            times.append(t["classify_s"])
-    total = sum(times)
+    p1 = os.path.join(CACHE, "%s_refarm.1.fq" % wl_name)
+    p2 = os.path.join(CACHE, "%s_refarm.2.fq" % wl_name) if wl["paired"] else None
+    f1 = open(p1, "wb")
+    f2 = open(p2, "wb") if p2 else None
+    for i in range(args.steps):
+        b1, b2 = make_batch(wl, genomes, i, n)  # same generator and seeds as the GPU arm's batches
+        b1.tofile(f1)
+        if f2:
+            b2.tofile(f2)
+    f1.close()
+    if f2:
+        f2.close()
+    t = run_reference_binary(ibf, p1, p2, os.path.join(CACHE, "ref_arm_out"), threads, hibf=bool(wl.get("hibf")))
+    for p in (p1, p2, os.path.join(CACHE, "ref_arm_out.all")):
+        if p and os.path.exists(p):
+            os.remove(p)
+    total = t["classify_s"]
     value = args.steps * n * units / total
     line = {
         "impl": "reference",
@@ -785,14 +938,19 @@ def reference_arm(args, wl):
         "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY)},
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": "each step = unmodified ganon-classify --threads %d on %d reads (its own classifying+printing time; filter load excluded)" % (threads, n * units)},
+        "config": {"workload": wl_name + ": " + wl["desc"], "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY),
+                   "reads_per_step": n * units, "database_file": how, "invocations": 1,
+                   "timing": "the binary's own classifying+printing time over steps x n reads / steps; filter load %.1f s paid once and excluded; no separate warm-up pass (one process)" % t["load_s"]},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "reference", "flags": REF_FLAGS,
+                         "sample": "one run of the unmodified ganon-classify --threads %d over %d steps x %d reads (wall %.1f s incl. filter load)" % (threads, args.steps, n * units, t["wall_s"])},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    with open("/proc/self/maps") as f:  # evidence for the record: no product library in this process
+        line["native_so_loaded"] = sorted({ln.split("/")[-1].strip() for ln in f if "ganon_b200" in ln and ".so" in ln})
     print(json.dumps(line))
     return 0
 

@@ -46,6 +46,45 @@ static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static uint64_t  g_xor, g_sum;
 static int       g_failed;
 
+typedef struct
+{
+    const char *genomes;
+    uint64_t    glen, g0, g1, n, cap;
+    unsigned    h, k, w;
+    plant_t    *out;
+} plant_job;
+
+static void *plant_worker(void *arg)
+{
+    plant_job *J = (plant_job *)arg;
+    uint64_t  *mins = (uint64_t *)malloc((J->glen + 1) * 8);
+    go_ibf     ibf;
+    memset(&ibf, 0, sizeof ibf);
+    ibf.bins = g_bins, ibf.technical_bins = g_bin_words * 64, ibf.bin_size = g_bin_size, ibf.bin_words = g_bin_words, ibf.hash_funs = J->h;
+    ibf.hash_shift = (uint64_t)__builtin_clzll(g_bin_size);
+    const uint64_t kseed = go_adjust_seed(J->k);
+    J->cap = (J->g1 - J->g0) * (J->glen / 4 + 16) * J->h + 16;
+    J->out = (plant_t *)malloc(J->cap * sizeof(plant_t));
+    for (uint64_t g = J->g0; g < J->g1; ++g)
+    {
+        const size_t nm = go_minimiser_hash(J->genomes + g * J->glen, J->glen, J->k, J->w, kseed, mins);
+        for (size_t i = 0; i < nm; ++i)
+            for (unsigned fn = 0; fn < J->h; ++fn)
+            {
+                if (J->n == J->cap)
+                {
+                    J->cap *= 2;
+                    J->out = (plant_t *)realloc(J->out, J->cap * sizeof(plant_t));
+                }
+                J->out[J->n].widx = go_ibf_row(&ibf, mins[i], fn) * g_bin_words + g / 64;
+                J->out[J->n].mask = (uint64_t)1 << (g % 64);
+                ++J->n;
+            }
+    }
+    free(mins);
+    return NULL;
+}
+
 static void *fill_worker(void *arg)
 {
     (void)arg;
@@ -122,56 +161,53 @@ int main(int argc, char **argv)
     g_chunk_words = (uint64_t)1 << 22; /* 32 MiB */
     g_n_chunks    = (g_n_words + g_chunk_words - 1) / g_chunk_words;
 
-    /* ---- planted bits ---- */
+    /* ---- planted bits: genomes split over the threads, each with its own list ---- */
     FILE *gf = fopen(gpath, "rb");
     if (!gf)
     {
         perror(gpath);
         return 1;
     }
-    char     *genome = (char *)malloc(glen + 1);
-    uint64_t *mins = (uint64_t *)malloc((glen + 1) * 8);
-    uint64_t  cap = bins * (glen / 4 + 16) * h, n_pl = 0;
-    g_plants = (plant_t *)malloc(cap * sizeof(plant_t));
-    go_ibf ibf;
-    memset(&ibf, 0, sizeof ibf);
-    ibf.bins = bins, ibf.technical_bins = g_bin_words * 64, ibf.bin_size = bin_size, ibf.bin_words = g_bin_words, ibf.hash_funs = h;
-    ibf.hash_shift = (uint64_t)__builtin_clzll(bin_size);
-    const uint64_t kseed = go_adjust_seed(k);
-    for (uint64_t g = 0; g < bins; ++g)
+    char *genomes = (char *)malloc(bins * glen + 1);
+    if (fread(genomes, 1, bins * glen, gf) != bins * glen)
     {
-        if (fread(genome, 1, glen, gf) != glen)
-        {
-            fprintf(stderr, "synthdb: genomes file too short\n");
-            return 1;
-        }
-        const size_t nm = go_minimiser_hash(genome, glen, k, w, kseed, mins);
-        for (size_t i = 0; i < nm; ++i)
-            for (unsigned fn = 0; fn < h; ++fn)
-            {
-                if (n_pl == cap)
-                {
-                    cap *= 2;
-                    g_plants = (plant_t *)realloc(g_plants, cap * sizeof(plant_t));
-                }
-                g_plants[n_pl].widx = go_ibf_row(&ibf, mins[i], fn) * g_bin_words + g / 64;
-                g_plants[n_pl].mask = (uint64_t)1 << (g % 64);
-                ++n_pl;
-            }
+        fprintf(stderr, "synthdb: genomes file too short\n");
+        return 1;
     }
     fclose(gf);
+    plant_job *jobs = (plant_job *)calloc((size_t)threads, sizeof(plant_job));
+    pthread_t *pth = (pthread_t *)malloc((size_t)threads * sizeof(pthread_t));
+    for (int t = 0; t < threads; ++t)
+    {
+        jobs[t].genomes = genomes, jobs[t].glen = glen, jobs[t].h = h, jobs[t].k = k, jobs[t].w = w;
+        jobs[t].g0 = bins * (uint64_t)t / (uint64_t)threads, jobs[t].g1 = bins * (uint64_t)(t + 1) / (uint64_t)threads;
+        pthread_create(&pth[t], NULL, plant_worker, &jobs[t]);
+    }
+    uint64_t n_pl = 0;
+    for (int t = 0; t < threads; ++t)
+    {
+        pthread_join(pth[t], NULL);
+        n_pl += jobs[t].n;
+    }
+    free(genomes);
+    free(pth);
     /* bucket by chunk (counting sort) */
     g_starts = (uint64_t *)calloc(g_n_chunks + 2, 8);
-    for (uint64_t j = 0; j < n_pl; ++j)
-        g_starts[g_plants[j].widx / g_chunk_words + 1]++;
+    for (int t = 0; t < threads; ++t)
+        for (uint64_t j = 0; j < jobs[t].n; ++j)
+            g_starts[jobs[t].out[j].widx / g_chunk_words + 1]++;
     for (uint64_t c = 0; c < g_n_chunks; ++c)
         g_starts[c + 1] += g_starts[c];
     plant_t  *sorted = (plant_t *)malloc((n_pl + 1) * sizeof(plant_t));
     uint64_t *cur = (uint64_t *)malloc((g_n_chunks + 1) * 8);
     memcpy(cur, g_starts, (g_n_chunks + 1) * 8);
-    for (uint64_t j = 0; j < n_pl; ++j)
-        sorted[cur[g_plants[j].widx / g_chunk_words]++] = g_plants[j];
-    free(g_plants);
+    for (int t = 0; t < threads; ++t)
+    {
+        for (uint64_t j = 0; j < jobs[t].n; ++j)
+            sorted[cur[jobs[t].out[j].widx / g_chunk_words]++] = jobs[t].out[j];
+        free(jobs[t].out);
+    }
+    free(jobs);
     free(cur);
     g_plants = sorted;
 
@@ -214,16 +250,16 @@ int main(int argc, char **argv)
         fwrite(name, 1, (size_t)n, f);
     }
     w64(f, bins);
-    w64(f, ibf.technical_bins);
+    w64(f, g_bin_words * 64);
     w64(f, bin_size);
-    w64(f, ibf.hash_shift);
+    w64(f, (uint64_t)__builtin_clzll(bin_size));
     w64(f, g_bin_words);
     w64(f, h);
     const uint8_t width = 1;
     const float   growth = 1.5f;
     fwrite(&width, 1, 1, f);
     fwrite(&growth, 4, 1, f);
-    w64(f, ibf.technical_bins * bin_size);
+    w64(f, g_bin_words * 64 * bin_size);
     fflush(f);
     g_data_off = (uint64_t)ftello(f);
     fclose(f);

@@ -82,3 +82,62 @@ def test_bench_hibf_layout_is_a_consistent_tree():
             child = parent
         assert child == 0
     assert any(len(c[0][1]) == 2 for c in chains)  # split user bins exist
+
+
+def _synthdb(tmp_path, bins, bin_size, glen, h=4, k=19, w=31, threads=3):
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "synthdb"])
+    g = synth.random_genomes(1, bins, glen)
+    gfile, out = str(tmp_path / "g.bin"), str(tmp_path / "t.ibf")
+    g.tofile(gfile)
+    done = subprocess.run([os.path.join(root, "oracle", "synthdb"), out, gfile, str(bins), str(bin_size), str(h), str(k), str(w), str(glen), "1", "1234", str(threads)],
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert done.returncode == 0, done.stderr
+    return g, out, [int(x) for x in done.stdout.split()]
+
+
+def test_cpu_database_writer_equals_the_numpy_statement_of_the_device_generators(tmp_path):
+    """oracle/synthdb (the reference arm's database writer) = random_words (gnb_db_fill_random) OR emplace of every
+    genome's minimisers into its bin -- the filter bench.build_database creates in HBM -- in the reference's .ibf layout."""
+    from ganon_b200 import formats
+
+    for bins, bin_size, glen in ((200, 50021, 3000), (70, 1 << 15, 500), (64, 1 << 23, 400)):  # the last one spans several 32 MiB chunks
+        h, k, w = 4, 19, 31
+        g, path, (n_words, xor, total, _planted) = _synthdb(tmp_path, bins, bin_size, glen)
+        f = formats.read_ibf(path)
+        bw = (bins + 63) // 64
+        want = synth.random_words(1, 1, bin_size, bw, bins)
+        hs, bb = [], []
+        for i in range(bins):
+            u = O.minimiser_hash(g[i].tobytes(), k, w)
+            hs.append(u)
+            bb.append(np.full(u.size, i, np.uint32))
+        synth.emplace_numpy(want, bw, bin_size, h, np.concatenate(hs), np.concatenate(bb))
+        assert n_words == want.size and np.array_equal(f.ibf.data, want)
+        assert xor == int(np.bitwise_xor.reduce(want)) and total == int(want.sum(dtype=np.uint64))
+        assert (f.kmer_size, f.window_size, f.ibf.hash_funs, f.max_hashes_bin) == (k, w, h, 1234)
+        assert f.bin_map == [(b, "T%d" % b) for b in range(bins)] and f.hashes_count == [("T%d" % b, 1234) for b in range(bins)]
+
+
+def test_reference_arm_runs_without_the_product_library(tmp_path):
+    """bench.py --impl reference: one invocation of the unmodified binary on a database written on the CPU; the process
+    reports which libganon_b200 objects it mapped -- none."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    import pytest
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "ganon-classify")):
+        pytest.skip("oracle/_ref/ganon-classify not built")
+    env = dict(os.environ, GANON_B200_BENCH_DIR=str(tmp_path))
+    done = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "2"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert done.returncode == 0, done.stderr[-2000:]
+    line = json.loads(done.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["native_so_loaded"] == [] and line["value"] > 0
+    assert line["config"]["invocations"] == 1 and line["e2e"]["h2d_bytes_per_step"] == 0
