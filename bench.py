@@ -402,9 +402,9 @@ def main():
     else:
         extras = [e for e in args.extras.split(",") if e and e != "none"]
 
-    if world > 1 and not args.replicas:
+    if (world > 1 and not args.replicas) or args.shard_db:
         line = sharded_arm(args, wl_name, ctx)
-        if not explicit:
+        if not explicit and world > 1:
             # the other way to use N GPUs (the database fits one GPU): replicas, reads sharded, no data-path collective
             sub = measure(args, "c2", ctx, cpu=False, cli=False, em=False)
             if rank == 0:
@@ -646,13 +646,15 @@ def measure(args, wl_name, ctx, cpu, cli, em):
 
 
 def sharded_arm(args, wl_name, ctx):
-    """--shard-db: the filter is split by bin-word columns over the ranks; every rank stages the same
-    batch, runs K2 + K3 on its columns, the sparse tuples are all-gathered in HBM (NCCL) and sorted + finished (K4) on
-    every rank.  Total work is fixed as N grows ("strong")."""
+    """N > 1 default: the filter is split by bin-word columns over the ranks.  Every rank sees the same
+    batch, runs K2 + K3 on its columns; the sparse tuples are exchanged in HBM inside the library (NCCL) and sorted +
+    finished (K4) on every rank.  Total work is fixed as N grows ("strong").  e2e: submit / collect with sliced ingest
+    (each rank copies 1/N of the FASTQ block over its own PCIe link, slices all-gathered over NVLink)."""
     import torch
     import torch.distributed as dist
 
-    from ganon_b200.sharded import ShardedSession
+    from ganon_b200.classify import Session, result_text
+    from ganon_b200.sharded import ShardedSession, make_comm
 
     rank, world, dev = ctx["rank"], ctx["world"], ctx["local_rank"]
     wl = dict(WORKLOADS[wl_name])
@@ -663,12 +665,13 @@ def sharded_arm(args, wl_name, ctx):
     t_setup = time.perf_counter()
     db, genomes = build_database(wl, dev, shard=rank, n_shards=world)
     info = db.info()
+    comm = make_comm(dev)
     pool = max(1, min(args.pool, args.steps + args.warmup))
     blocks = [make_batch(wl, genomes, i, R) for i in range(pool)]  # the same reads on every rank
     host = [(pinned(b1), pinned(b2) if b2 is not None else None) for b1, b2 in blocks]
     stream = torch.cuda.Stream()
-    mk = lambda: ShardedSession([db], [REL_CUTOFF], [REL_FILTER], [FPR_QUERY], output_all=True, device=dev, cuda_stream=stream.cuda_stream)
-    sessions = [mk() for _ in range(pool)]
+    mk = lambda **kw: ShardedSession([db], [REL_CUTOFF], [REL_FILTER], [FPR_QUERY], output_all=True, device=dev, comm=comm, **kw)
+    sessions = [mk(cuda_stream=stream.cuda_stream) for _ in range(pool)]
     for s, (h1, h2) in zip(sessions, host):
         assert s.stage(h1, h2, final=True) == R
     t_setup = time.perf_counter() - t_setup
@@ -678,61 +681,98 @@ def sharded_arm(args, wl_name, ctx):
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        for i in range(max(args.warmup, pool)):
-            sessions[i % pool].run_levels(prefix_id=1)
-        sampler = ClockSampler(dev)
-        sampler.start()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        t0 = time.perf_counter()
-        ms_count = ms_min = ms_sort = ms_fin = 0.0
-        k3_bytes = launches = minimisers = exchanged = 0
-        for i in range(args.steps):
-            s = sessions[(args.warmup + i) % pool]
-            s.run_levels(prefix_id=1)
-            r = s.staged_timings()
-            ms_count += r.ms_count
-            ms_min += r.ms_minimiser
-            ms_sort += r.ms_sort
-            ms_fin += r.ms_finish_device
-            k3_bytes += r.count_kernel_bytes
-            launches += r.n_kernel_launches
-            minimisers += r.n_minimisers
-            exchanged += s.last_exchanged_bytes
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        dev_ms = ev0.elapsed_time(ev1)
-        t = torch.tensor([dev_ms, wall_ms, ms_count], device="cuda", dtype=torch.float64)
+    def reduce_(t, op):
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, ms_count_max = float(t[0]), float(t[1]), float(t[2])
-        barrier()
+            dist.all_reduce(t, op=op)
 
-        # e2e: host FASTQ blocks through ShardedSession.classify on every rank (H2D of the block, kernels, exchange,
-        # K4, result read back), synchronous per step
-        e2e = mk()
-        for i in range(3):
-            e2e.classify(host[i % pool][0], host[i % pool][1], final=True)
-        barrier()
-        t0 = time.perf_counter()
-        h2d = d2h = n_class = 0
-        for i in range(args.steps):
-            h1, h2 = host[(1 + i) % pool]
-            r = e2e.classify(h1, h2, final=True)
-            h2d += r.h2d_bytes
-            d2h += r.d2h_bytes
-            n_class += r.n_classified
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_sort=r.ms_sort, ms_finish_device=r.ms_finish_device, levels_on_device=r.levels_on_device)
-        if world > 1:
-            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t[0])
+    # ------------------------------------------------------------------ value: inputs resident in HBM
+    for i in range(max(args.warmup, pool)):
+        sessions[i % pool].run_staged()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    ms_count = ms_min = ms_sort = ms_fin = ms_xch = 0.0
+    k3_bytes = launches = minimisers = exchanged = 0
+    for i in range(args.steps):
+        r = sessions[(args.warmup + i) % pool].run_staged()
+        ms_count += r.ms_count
+        ms_min += r.ms_minimiser
+        ms_sort += r.ms_sort
+        ms_fin += r.ms_finish_device
+        ms_xch += r.ms_exchange
+        k3_bytes += r.count_kernel_bytes
+        launches += r.n_kernel_launches
+        minimisers += r.n_minimisers
+        exchanged += r.exchanged_bytes
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms, wall_ms, ms_count, ms_xch], device="cuda", dtype=torch.float64)
+    reduce_(t, dist.ReduceOp.MAX)
+    dev_ms, wall_ms, ms_count_max, ms_xch_max = (float(x) for x in t)
+    barrier()
+
+    # ------------------------------------------------------------------ e2e: host FASTQ blocks through submit / collect
+    e2e = mk(sliced_ingest=True)
+    _n, cap = e2e.in_flight()
+    e2e_prof = {}
+
+    def e2e_loop(n_steps, first):
+        h2d = d2h = n_class = pending = 0
+        last = None
+        s_xch = 0.0
+        for i in range(n_steps):
+            h1, h2 = host[(first + i) % pool]
+            e2e.submit(h1, h2, final=True)
+            pending += 1
+            while pending >= cap or (i == n_steps - 1 and pending):
+                r = e2e.collect()
+                pending -= 1
+                h2d += r.h2d_bytes
+                d2h += r.d2h_bytes
+                n_class += r.n_classified
+                s_xch += r.ms_exchange
+                last = r
+        e2e_prof.update(mean_exchange_ms=s_xch / n_steps)
+        return h2d, d2h, n_class, last
+
+    e2e_loop(max(3, cap + 1), 0)
+    barrier()
+    t0 = time.perf_counter()
+    h2d, d2h, n_class, r = e2e_loop(args.steps, 1)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    last = dict(ms_h2d=r.ms_h2d, ms_index=r.ms_index, ms_minimiser=r.ms_minimiser, ms_count=r.ms_count, ms_exchange=r.ms_exchange, ms_sort=r.ms_sort, ms_finish_device=r.ms_finish_device,
+                levels_on_device=r.levels_on_device, ms_submit_to_collect=r.ms_total, batches_in_flight=cap, **e2e_prof)
+    t = torch.tensor([e2e_ms, float(h2d)], device="cuda", dtype=torch.float64)
+    tm = t.clone()
+    reduce_(tm, dist.ReduceOp.MAX)
+    reduce_(t, dist.ReduceOp.SUM)
+    e2e_ms, h2d_all = float(tm[0]), int(t[1])
     clocks = sampler.stop()
+
+    # ------------------------------------------------------------------ parity: the sharded result of batch 0 against the
+    # unsharded session on one GPU (which the N = 1 line checks against the reference binary), or -- when the whole
+    # filter does not fit one GPU -- against the oracle on a sample (rows of the filter regenerated on the CPU)
+    res = e2e.classify(host[0][0], host[0][1], final=True)  # collective: every rank
+    mine = result_text(res, "all")
+    parity = None
+    if rank == 0:
+        full_bytes = wl["bin_size"] * ((wl["bins"] + 63) // 64) * 8
+        free, _total = torch.cuda.mem_get_info(dev)
+        try:
+            if full_bytes + (12 << 30) < free and not os.environ.get("GANON_B200_BENCH_ORACLE_PARITY"):
+                parity = parity_against_unsharded(wl, dev, host[0], mine, R * units)
+            else:
+                parity = parity_against_oracle_sample(wl, dev, genomes, blocks[0], mine)
+        except Exception as ex:
+            parity = {"identical": None, "error": str(ex)[:300]}
+    e2e.close()
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -755,12 +795,16 @@ def sharded_arm(args, wl_name, ctx):
                 "reads_per_step": R * units,
                 "db_bytes_per_gpu": int(info.device_bytes),
                 "thresholds": "rel-cutoff %.2f rel-filter %.2f fpr-query %g" % (REL_CUTOFF, REL_FILTER, FPR_QUERY),
-                "parallelism": "bin-sharded x%d (bin-word columns %d..%d of %d on rank 0); every rank classifies the same reads, sparse tuples all-gathered in HBM over NCCL, K4 on every rank" % (world, info.shard_word_begin, info.shard_word_end, info.bin_words),
+                "parallelism": "bin-sharded x%d (bin-word columns %d..%d of %d on rank 0); every rank classifies the same reads on its columns, sparse tuples exchanged in HBM inside libganon_b200 (NCCL %d), K4 on every rank" % (world, info.shard_word_begin, info.shard_word_end, info.bin_words, comm.nccl_version()),
+                "host_placement": ctx["numa"],
                 "l2": "inputs larger than L2: %d distinct %d MB FASTQ batches cycled, filter shard gathered at random" % (pool, blocks[0][0].size * units >> 20),
                 "timing": "CUDA events on the launch stream around the K steps (max over ranks); wall %.1f ms" % wall_ms,
                 "minimisers_per_read": minimisers / max(1, args.steps * R * units),
                 "k2_kernel": "warp per read" if os.environ.get("GANON_B200_K2", "").startswith("w") else "thread per read (k2_thread.cuh)",
                 "exchanged_tuple_bytes_per_step": exchanged // max(1, args.steps),
+                "exchange_ms_per_step": ms_xch / args.steps,
+                "exchange_ms_per_step_max_over_ranks": ms_xch_max / args.steps,
+                "exchange_share_of_step": (ms_xch_max / args.steps) / (dev_ms / args.steps),
             },
             "roofline": {
                 "kernel": "k_ibf_count",
@@ -771,22 +815,112 @@ def sharded_arm(args, wl_name, ctx):
                 "frac": achieved / peak,
                 "peak_source": peak_src,
                 "traffic": None,
+                "traffic_source": None,
                 "algorithmic_bytes_per_launch": k3_bytes / max(1, args.steps),
                 "ms_per_launch": ms_count / max(1, args.steps),
                 "ms_per_launch_max_over_ranks": ms_count_max / max(1, args.steps),
                 "note": "per GPU (rank 0): its shard's share of every row",
-                "other_kernels_ms_per_step": {"k_minimisers(x2)+scan": ms_min / args.steps, "radix_sort": ms_sort / args.steps, "k_finish(select+scan+write)": ms_fin / args.steps},
+                "other_kernels_ms_per_step": {"k_minimisers+scan": ms_min / args.steps, "tuple_exchange": ms_xch / args.steps, "radix_sort": ms_sort / args.steps, "k_finish(select+scan+write)": ms_fin / args.steps},
             },
             "cpu_baseline": None,
-            "e2e": {"value": args.steps * R * units / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "last_step_breakdown_ms": last, "classified_reads_per_step": n_class // args.steps, "note": "per rank: every rank copies the same block"},
+            "e2e": {"value": args.steps * R * units / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d_all // args.steps, "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
+                    "last_step_breakdown_ms": last, "classified_reads_per_step": n_class // args.steps, "note": "sliced ingest: h2d bytes summed over the ranks (each copies 1/N of the block); d2h of rank 0 (every rank reads the full result back)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "parity": None,
+            "parity": parity,
             "setup_s": t_setup,
         }
-        return line
-    return None
+    for s in sessions:
+        s.close()
+    db.close()
+    comm.close()
+    del host, blocks
+    torch.cuda.empty_cache()
+    return line
 
+
+def parity_against_unsharded(wl, dev, host_block, sharded_all_text, n_reads):
+    from ganon_b200.classify import Session, result_text
+
+    db, _g = build_database(wl, dev)
+    s = Session([db], [REL_CUTOFF], [REL_FILTER], [FPR_QUERY], output_all=True, device=dev)
+    r = s.classify(host_block[0], host_block[1], final=True)
+    want = result_text(r, "all")
+    out = {"reads": n_reads, "all_lines": want.count(b"\n"), "identical": sorted(want.splitlines()) == sorted(sharded_all_text.splitlines()),
+           "byte_identical": want == sharded_all_text, "against": "the unsharded session (whole filter on rank 0's GPU) on the same batch; that path is checked against the reference binary in the N = 1 line"}
+    s.close()
+    db.close()
+    return out
+
+
+def parity_against_oracle_sample(wl, dev, genomes, block, sharded_all_text, n_sample=192):
+    """The whole filter fits neither one GPU nor (for the reference binary) the host: check the first n_sample records of
+    the batch against the oracle (oracle/ganon_oracle.c, the pinned CPU restatement).  The oracle reads the filter through
+    a sparse anonymous mapping of its full size in which only the rows those reads touch are materialised, regenerated on
+    the CPU with the numpy statements of the device generators (ganon_b200/synth.py: background words + planted bits)."""
+    import ctypes as C
+    import mmap
+
+    from ganon_b200 import synth
+    from ganon_b200.classify import minimisers_batch
+    from oracle import oracle as O
+
+    k, w, h, bins, bin_size = wl["k"], wl["w"], wl["h"], wl["bins"], wl["bin_size"]
+    bw = (bins + 63) // 64
+    b1, b2 = block
+    rec1 = b1.size // wl["reads_per_step"]
+    rec2 = b2.size // wl["reads_per_step"] if b2 is not None else 0
+
+    def records(b, rec):
+        out = []
+        for i in range(n_sample):
+            lines = bytes(b[i * rec : (i + 1) * rec]).split(b"\n")
+            out.append((lines[0][1:], lines[1]))
+        return out
+
+    r1 = records(b1, rec1)
+    r2 = records(b2, rec2) if b2 is not None else None
+    reads = [(r1[i][0], r1[i][1], r2[i][1] if r2 else None) for i in range(n_sample)]
+    hashes = [O.read_hashes(s1, s2, k, w) for _id, s1, s2 in reads]
+    allh = np.unique(np.concatenate([x for x in hashes if x is not None]))
+    need = np.unique(synth.ibf_rows(allh, h, bin_size).reshape(-1))
+    n_words = bin_size * bw
+    libc = C.CDLL(None, use_errno=True)
+    libc.mmap.restype = C.c_void_p
+    libc.mmap.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_long]
+    MAP_NORESERVE = 0x4000
+    addr = libc.mmap(None, n_words * 8, mmap.PROT_READ | mmap.PROT_WRITE, mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS | MAP_NORESERVE, -1, 0)
+    if addr in (None, C.c_void_p(-1).value):
+        raise RuntimeError("sparse mapping of the filter failed (errno %d)" % C.get_errno())
+    data = np.ctypeslib.as_array((C.c_uint64 * n_words).from_address(addr))
+    try:
+        for r in need.tolist():
+            data[r * bw : (r + 1) * bw] = synth.random_words(DB_SEED, 1, bin_size, bw, bins, row0=r, rows=1)
+        # planted bits on those rows: every genome's minimisers (K2 on the GPU -- data generation, as in build_database)
+        step = 4096
+        for g0 in range(0, bins, step):
+            gs = [genomes[i].tobytes() for i in range(g0, min(g0 + step, bins))]
+            hoff, hs = minimisers_batch(gs, k, w, device=dev)
+            gbin = np.repeat(np.arange(g0, g0 + len(gs), dtype=np.uint64), np.diff(hoff).astype(np.int64))
+            rows = synth.ibf_rows(hs, h, bin_size)
+            for i in range(h):
+                sel = np.isin(rows[i], need)
+                if sel.any():
+                    idx = (rows[i][sel] * np.uint64(bw) + (gbin[sel] >> np.uint64(6))).astype(np.int64)
+                    np.bitwise_or.at(data, idx, np.uint64(1) << (gbin[sel] & np.uint64(63)))
+        oibf = O.OracleIBF(bins, bin_size, h, data)
+        n_t = target_hashes_for_density(wl)
+        fpr = O.lib().go_target_fpr(bin_size, h, n_t, n_t)
+        filt = O.OracleFilter(oibf, ["T%d" % b for b in range(bins)], [[b] for b in range(bins)], [fpr] * bins, REL_CUTOFF, k, w)
+        want = O.all_lines(O.classify_level([filt], reads, REL_FILTER, FPR_QUERY))
+    finally:
+        del data
+        libc.munmap.argtypes = [C.c_void_p, C.c_size_t]
+        libc.munmap(addr, n_words * 8)
+    ids = {r[0] for r in reads}
+    mine = sorted(ln for ln in sharded_all_text.decode().splitlines() if ln.split("\t", 1)[0].encode() in ids)
+    return {"reads": n_sample * (2 if b2 is not None else 1), "all_lines": len(want), "identical": mine == want, "rows_materialised": int(need.size),
+            "against": "oracle (CPU restatement, pinned to the reference) on the first %d records of batch 0; filter rows regenerated on the CPU" % n_sample}
 
 
 def cli_leg(wl_name, wl, db, blocks, pool, R, dev):

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libganon_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 GNB_OK = 0
+GNB_COMM_ID_BYTES = 256
 STATUS = {0: "GNB_OK", -1: "GNB_ERR_ARG", -2: "GNB_ERR_IO", -3: "GNB_ERR_FORMAT", -4: "GNB_ERR_CUDA", -5: "GNB_ERR_CONFIG", -6: "GNB_ERR_PARSE", -7: "GNB_ERR_LIMIT"}
 
 
@@ -65,6 +66,8 @@ class SessionConfig(C.Structure):
         ("n_reads_chunk", C.c_int),
         ("quiet", C.c_int),
         ("cuda_stream", C.c_void_p),
+        ("comm", C.c_void_p),
+        ("sliced_ingest", C.c_int),
     ]
 
 
@@ -103,6 +106,8 @@ class BatchResult(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("ms_finish_device", C.c_float),
         ("levels_on_device", C.c_uint32),
+        ("ms_exchange", C.c_float),
+        ("exchanged_bytes", C.c_uint64),
     ]
 
 
@@ -142,6 +147,10 @@ SYMBOLS = {
     "gnb_db_save": (C.c_int, [_P, C.c_char_p]),
     "gnb_db_create_hibf": (C.c_int, [C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64, C.POINTER(C.c_char_p), C.c_double, C.c_int, C.POINTER(_P)]),
     "gnb_db_emplace_ibf": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64]),
+    "gnb_comm_unique_id": (C.c_int, [_P, C.c_uint64]),
+    "gnb_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "gnb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gnb_comm_free": (None, [_P]),
     "gnb_minimisers": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "gnb_minimisers_batch": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64, _P, _P, C.c_uint64]),
     "gnb_db_bulk_count": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64, _P]),

@@ -170,6 +170,39 @@ def minimisers(seq: bytes, k: int, w: int, device: int = 0):
     return out[: n.value].copy()
 
 
+class Comm:
+    """This process's place in a bin-sharded multi-GPU run (gnb_comm): one process per GPU, NCCL inside the library.
+    `unique_id()` on one rank, the bytes carried to the others by the caller, then `Comm(id, rank, n_ranks, device)` on
+    every rank (collective)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(_lib.GNB_COMM_ID_BYTES)
+        check(_lib.lib().gnb_comm_unique_id(buf, _lib.GNB_COMM_ID_BYTES))
+        return buf.raw
+
+    def __init__(self, unique_id: bytes, rank: int, n_ranks: int, device: int):
+        assert len(unique_id) == _lib.GNB_COMM_ID_BYTES
+        h = C.c_void_p()
+        check(_lib.lib().gnb_comm_create(C.c_char_p(unique_id), rank, n_ranks, device, C.byref(h)))
+        self._h = h
+        self.rank, self.n_ranks, self.device = rank, n_ranks, device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        check(_lib.lib().gnb_comm_info(self._h, None, None, None, C.byref(v)))
+        return v.value
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().gnb_comm_free(self._h)
+            self._h = C.c_void_p()
+
+
 class Session:
     """One classification run over all hierarchy levels (gnb_session)."""
 
@@ -192,6 +225,8 @@ class Session:
         n_reads: int = 400,
         quiet: bool = True,
         cuda_stream: int = 0,
+        comm: Optional["Comm"] = None,
+        sliced_ingest: bool = False,
     ):
         n = len(dbs)
         labels = list(hierarchy_labels) if hierarchy_labels else ["H1"] * n
@@ -226,7 +261,10 @@ class Session:
             n_reads,
             int(quiet),
             C.c_void_p(cuda_stream) if cuda_stream else None,
+            comm.handle if comm is not None else None,
+            int(sliced_ingest),
         )
+        self._keep["comm"] = comm
         h = C.c_void_p()
         check(_lib.lib().gnb_session_create(C.byref(cfg), C.byref(h)))
         self._h = h

@@ -24,6 +24,7 @@
 #include <thread>
 #include <unordered_map>
 
+#include "comm.h"
 #include "db.h"
 #include "reads.h"
 
@@ -372,6 +373,9 @@ struct gnb_session
     uint32_t             n_reads_chunk = 400;
     std::vector<LevelRt> levels;
     bool                 use_device_index = true; // K1 first, host reader when the block is not strict 4-line FASTQ
+    gnb_comm            *comm = nullptr;          // bin-sharded run (NULL or one rank: no exchange)
+    bool                 sliced_ingest = false;   // with comm: every rank copies 1/n of a read block, slices all-gathered
+    bool                 sharded() const { return comm && comm->n_ranks > 1; }
     int                  n_threads = 1;
     uint64_t             file_records = 0; // records taken from the current file so far (parse-error truncation rule)
     std::mutex           acc_mutex;        // guards LevelRt::rep / total
@@ -438,7 +442,7 @@ struct BatchCtx
     cudaStream_t          st_in = nullptr; // host->device block copies + K1, high priority (same as st on a caller's stream)
     cudaEvent_t           ev_in = nullptr;
     bool                  own_stream = true;
-    cudaEvent_t           ev[12]{};
+    cudaEvent_t           ev[14]{};
     std::vector<Worker>   workers;
 
     // staged batch
@@ -457,6 +461,15 @@ struct BatchCtx
     DevBuf d_blk1, d_blk2, d_off1, d_len1, d_off2, d_len2, d_idoff, d_idlen, d_counts, d_hash_off, d_hashes, d_active, d_tuples_a, d_tuples_b,
         d_cursor, d_tmp, d_lines1, d_lines2, d_k1tmp1, d_k1tmp2, d_idoff2, d_idlen2, d_status, d_items_a, d_items_b, d_items_cursor;
     PinBuf h_pin;
+    // bin-sharded runs: tuple counts of all ranks, the gathered tuple list, host copies of sliced blocks (on demand)
+    DevBuf d_xch, d_gather;
+    PinBuf h_xch;
+    std::vector<char> h_blk1_copy, h_blk2_copy;
+    bool   host_block_valid = true; // blk1 / blk2 point at the whole block in host memory
+    float  ms_exchange_acc = 0;
+    bool   exchange_timed = false;
+    int    exchange_tuples(unsigned long long &produced);
+    int    ensure_host_block(cudaStream_t stream);
     PinnedVec<uint32_t>   h_counts;
     std::vector<uint8_t>  h_active;
     std::vector<uint8_t>  h_read_level;
@@ -536,9 +549,10 @@ struct BatchCtx
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
                           &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status,
                           &d_items_a, &d_items_b, &d_items_cursor, &d_tstart, &d_nacc, &d_sizes, &d_offs, &d_one, &d_ftotals, &d_read_level, &d_moff,
-                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc, &d_em_sizes, &d_em_offs})
+                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc, &d_em_sizes, &d_em_offs, &d_xch, &d_gather})
             b->release();
         h_pin.release();
+        h_xch.release();
         h_unc.release();
         h_rlevel.release();
         h_fin.release();
@@ -1261,6 +1275,31 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
         }
     }
 
+    // bin-sharded run: every database must be this rank's column shard of a flat IBF
+    s->comm          = cfg->comm;
+    s->sliced_ingest = cfg->comm && cfg->sliced_ingest != 0;
+    if (s->comm)
+    {
+        if (s->comm->device != s->device)
+            return fail(GNB_ERR_ARG, "gnb_session_create: the communicator was created for another device");
+        const uint64_t N = (uint64_t)s->comm->n_ranks, r = (uint64_t)s->comm->rank;
+        for (auto const &L : s->levels)
+            for (auto const &F : L.filters)
+            {
+                if (F.db->is_hibf)
+                {
+                    if (N > 1)
+                        return fail(GNB_ERR_CONFIG, "bin-sharded runs need flat .ibf databases (an HIBF descends per read; replicate it instead)");
+                    continue;
+                }
+                const gnb::IbfHost &I = F.db->ibfs[0];
+                if (I.w0 != r * I.bin_words / N || I.w1 != (r + 1) * I.bin_words / N)
+                    return fail(GNB_ERR_ARG, "gnb_session_create: a database is not shard `rank` of `n_ranks` (open it with gnb_db_open(..., shard = rank, n_shards = n_ranks))");
+            }
+        if (cfg->cuda_stream && N > 1 && s->sliced_ingest)
+            return fail(GNB_ERR_ARG, "gnb_session_create: sliced ingest runs on the library's own streams (cuda_stream must be NULL)");
+    }
+
     s->all_device_finish = true;
     for (auto const &L : s->levels)
     {
@@ -1346,30 +1385,79 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
 
     // ---- blocks -> device (one extra byte so that a final block without trailing newline can be terminated) ----
     GNB_CUDA(cudaEventRecord(ev[0], st_in));
-    GNB_TRY(d_blk1.ensure(len1 + 64));
-    if (len1)
-        GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st_in));
-    if (paired)
+    const bool sliced = S->sharded() && S->sliced_ingest;
+    host_block_valid  = !sliced;
+    char first1 = 0, last1 = 0, first2 = 0, last2 = 0; // first / last byte of the blocks (host decisions below)
+    if (!sliced)
     {
-        GNB_TRY(d_blk2.ensure(len2 + 64));
+        GNB_TRY(d_blk1.ensure(len1 + 64));
+        if (len1)
+            GNB_CUDA(cudaMemcpyAsync(d_blk1.p, blk1, len1, cudaMemcpyHostToDevice, st_in));
+        if (paired)
+        {
+            GNB_TRY(d_blk2.ensure(len2 + 64));
+            if (len2)
+                GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st_in));
+        }
+        timing.h2d_bytes = len1 + len2;
+        if (len1)
+            first1 = b1[0], last1 = b1[len1 - 1];
         if (len2)
-            GNB_CUDA(cudaMemcpyAsync(d_blk2.p, blk2, len2, cudaMemcpyHostToDevice, st_in));
+            first2 = b2[0], last2 = b2[len2 - 1];
+    }
+    else
+    {
+        // Bin-sharded run: every rank needs the whole block, but each one brings only its 1/n over its own PCIe link and
+        // the slices are all-gathered over NVLink (ingest communicator, used in submission order on the ingest stream).
+        const uint64_t N = (uint64_t)S->comm->n_ranks, r = (uint64_t)S->comm->rank;
+        auto bring = [&](DevBuf &d, const char *h, uint64_t len) -> int {
+            const uint64_t slice = (((len + N - 1) / N) + 15) & ~15ull;
+            GNB_TRY(d.ensure(slice * N + 64));
+            if (len == 0)
+                return GNB_OK;
+            const uint64_t lo = std::min(len, r * slice), hi = std::min(len, (r + 1) * slice);
+            if (hi > lo)
+                GNB_CUDA(cudaMemcpyAsync(d.as<char>() + lo, h + lo, hi - lo, cudaMemcpyHostToDevice, st_in));
+            timing.h2d_bytes += hi - lo;
+            GNB_TRY(comm_all_gather(S->comm->nccl_in, d.as<char>() + r * slice, d.p, slice, st_in));
+            return GNB_OK;
+        };
+        GNB_TRY(bring(d_blk1, blk1, len1));
+        if (paired)
+            GNB_TRY(bring(d_blk2, blk2, len2));
+        GNB_TRY(h_xch.ensure(64 + N * 8));
+        char *ends = h_xch.as<char>();
+        if (len1)
+        {
+            GNB_CUDA(cudaMemcpyAsync(ends + 0, d_blk1.p, 1, cudaMemcpyDeviceToHost, st_in));
+            GNB_CUDA(cudaMemcpyAsync(ends + 1, d_blk1.as<char>() + len1 - 1, 1, cudaMemcpyDeviceToHost, st_in));
+        }
+        if (len2)
+        {
+            GNB_CUDA(cudaMemcpyAsync(ends + 2, d_blk2.p, 1, cudaMemcpyDeviceToHost, st_in));
+            GNB_CUDA(cudaMemcpyAsync(ends + 3, d_blk2.as<char>() + len2 - 1, 1, cudaMemcpyDeviceToHost, st_in));
+        }
+        GNB_CUDA(stream_wait(st_in));
+        if (len1)
+            first1 = ends[0], last1 = ends[1];
+        if (len2)
+            first2 = ends[2], last2 = ends[3];
+        timing.d2h_bytes += 4;
     }
     GNB_CUDA(cudaEventRecord(ev[1], st_in));
-    timing.h2d_bytes = len1 + len2;
 
     size_t n = 0;
-    bool   on_device = use_device_index && len1 > 0 && b1[0] == '@' && (!paired || (len2 > 0 && b2[0] == '@'));
+    bool   on_device = use_device_index && len1 > 0 && first1 == '@' && (!paired || (len2 > 0 && first2 == '@'));
     if (on_device)
     {
         GNB_CUDA(cudaEventRecord(ev[8], st_in));
         uint64_t e1 = len1, e2 = len2;
-        if (final_block && b1[len1 - 1] != '\n')
+        if (final_block && last1 != '\n')
         {
             GNB_CUDA(cudaMemsetAsync(d_blk1.as<uint8_t>() + len1, '\n', 1, st_in));
             e1 = len1 + 1;
         }
-        if (paired && final_block && b2[len2 - 1] != '\n')
+        if (paired && final_block && last2 != '\n')
         {
             GNB_CUDA(cudaMemsetAsync(d_blk2.as<uint8_t>() + len2, '\n', 1, st_in));
             e2 = len2 + 1;
@@ -1444,9 +1532,10 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     if (!on_device)
     {
         auto t0 = Clock::now();
-        index_reads_host(b1, l1, final_block, kMaxReadsPerBatch - 1, t1);
+        GNB_TRY(ensure_host_block(st_in)); // sliced ingest: the host reader needs the whole block
+        index_reads_host(blk1, l1, final_block, kMaxReadsPerBatch - 1, t1);
         if (paired)
-            index_reads_host(b2, len2, final_block, kMaxReadsPerBatch - 1, t2);
+            index_reads_host(blk2, len2, final_block, kMaxReadsPerBatch - 1, t2);
         n = t1.size();
         if (paired)
             n = std::min(n, t2.size());
@@ -1542,6 +1631,31 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     if (st != st_in)
         GNB_CUDA(cudaStreamWaitEvent(st, ev_in, 0));
     staged = true;
+    return GNB_OK;
+}
+
+// Sliced ingest (bin-sharded runs): this rank's host memory holds only its slice of the block.  The host reader, the host
+// finishing stage and the host-side EM append read record ids / sequences from host memory: fetch the gathered block
+// from the device once per batch when one of them runs (not on the K1 + K4 path).
+int BatchCtx::ensure_host_block(cudaStream_t stream)
+{
+    if (host_block_valid)
+        return GNB_OK;
+    h_blk1_copy.resize(len1 + 1);
+    if (len1)
+        GNB_CUDA(cudaMemcpyAsync(h_blk1_copy.data(), d_blk1.p, len1, cudaMemcpyDeviceToHost, stream));
+    if (paired)
+    {
+        h_blk2_copy.resize(len2 + 1);
+        if (len2)
+            GNB_CUDA(cudaMemcpyAsync(h_blk2_copy.data(), d_blk2.p, len2, cudaMemcpyDeviceToHost, stream));
+    }
+    GNB_CUDA(stream_wait(stream));
+    timing.d2h_bytes += len1 + len2;
+    blk1 = h_blk1_copy.data();
+    if (paired)
+        blk2 = h_blk2_copy.data();
+    host_block_valid = true;
     return GNB_OK;
 }
 
@@ -1818,6 +1932,8 @@ int BatchCtx::run_level(size_t li)
         }
         if (!F.is_hibf)
             timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.dev.row_words * 8;
+        if (S->sharded())
+            GNB_TRY(exchange_tuples(produced)); // d_tuples_a now holds the lists of all ranks
         if (produced == 0)
             continue;
         GNB_CUDA(cudaEventRecord(ev[6], st));
@@ -1840,8 +1956,53 @@ int BatchCtx::run_level(size_t li)
         cudaEventElapsedTime(&ms, ev[6], ev[7]);
         ms_sort += ms;
     }
+    timing.ms_exchange += ms_exchange_acc;
+    ms_exchange_acc = 0;
     timing.ms_count += ms_k3;
     timing.ms_sort += ms_sort;
+    return GNB_OK;
+}
+
+// Bin-sharded run: this rank's K3 saw only its bin-word columns, so d_tuples_a holds the candidates of
+// its own bins -- finished counts for targets inside the shard, partial sums (flag bit 16) for targets that straddle a
+// shard boundary.  Every rank needs all of them (K4 then adds the partial sums, applies cap / cutoff / rel-filter /
+// fpr-query / LCA exactly as on one GPU and produces the identical result everywhere).  Two collectives on the compute
+// stream, inside this batch's GPU turn, hence in the same order on every rank: an all-gather of the list lengths
+// (8 bytes per rank; the host needs them to size the buffers) and one grouped launch of n_ranks broadcasts that moves the
+// lists themselves (a few bytes per read, against 2 * bins bytes per read for the count vectors a dense allreduce
+// would move).  On return d_tuples_a holds the concatenation in rank order and `produced` its length.
+int BatchCtx::exchange_tuples(unsigned long long &produced)
+{
+    gnb_comm    *cm = S->comm;
+    const size_t N  = (size_t)cm->n_ranks;
+    GNB_TRY(d_xch.ensure(N * 8));
+    GNB_TRY(h_xch.ensure(N * 8));
+    GNB_CUDA(cudaEventRecord(ev[12], st));
+    // d_cursor holds this rank's `produced` (the last K3 attempt fitted: produced <= capacity)
+    GNB_TRY(comm_all_gather(cm->nccl, d_cursor.p, d_xch.p, 8, st));
+    GNB_CUDA(cudaMemcpyAsync(h_xch.p, d_xch.p, N * 8, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(stream_wait(st));
+    const uint64_t *cnt   = h_xch.as<uint64_t>();
+    uint64_t        total = 0;
+    for (size_t r = 0; r < N; ++r)
+        total += cnt[r];
+    if (cnt[cm->rank] != produced)
+        return fail(GNB_ERR_CUDA, "sharded exchange: tuple count mismatch on this rank");
+    timing.d2h_bytes += N * 8;
+    if (total)
+    {
+        GNB_TRY(d_gather.ensure(total * 8));
+        GNB_TRY(comm_all_gather_v(cm, d_tuples_a.as<uint64_t>(), d_gather.as<uint64_t>(), cnt, st));
+        std::swap(d_tuples_a, d_gather);
+    }
+    GNB_CUDA(cudaEventRecord(ev[13], st));
+    GNB_CUDA(stream_wait(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[12], ev[13]);
+    ms_exchange_acc += ms;
+    timing.exchanged_bytes += total * 8;
+    produced = total;
+    trace_mark(this, "exchange.done");
     return GNB_OK;
 }
 
@@ -1852,6 +2013,7 @@ int BatchCtx::finish_level(size_t li)
     const uint32_t n = n_reads;
     const bool     first = li == 0, last = li + 1 == levels.size();
     const int      T = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, (n + 4095) / 4096));
+    GNB_TRY(ensure_host_block(st));
     const uint8_t *id_base = reinterpret_cast<const uint8_t *>(blk1);
     finish_T = T;
 
@@ -2785,8 +2947,8 @@ extern "C" int gnb_session_run_staged(gnb_session *s, gnb_batch_result *timings)
     GNB_CUDA(cudaSetDevice(c.device));
     // allow repeated runs on the same staged batch (benchmark): reset per-run state
     c.hashed_k = c.hashed_w = 0;
-    c.timing.ms_count = c.timing.ms_sort = 0;
-    c.timing.count_kernel_bytes = 0;
+    c.timing.ms_count = c.timing.ms_sort = c.timing.ms_exchange = 0;
+    c.timing.count_kernel_bytes = c.timing.exchanged_bytes = 0;
     c.timing.d2h_bytes = 0;
     c.launches = 0;
     std::fill(c.h_active.begin(), c.h_active.end(), (uint8_t)1);
@@ -2881,8 +3043,8 @@ extern "C" int gnb_session_run_level_device(gnb_session *s, uint32_t level)
     { // a staged batch may be run again (benchmark): start from the staged state
         c.begin_finish();
         c.hashed_k = c.hashed_w = 0;
-        c.timing.ms_count = c.timing.ms_sort = 0;
-        c.timing.count_kernel_bytes = 0;
+        c.timing.ms_count = c.timing.ms_sort = c.timing.ms_exchange = 0;
+        c.timing.count_kernel_bytes = c.timing.exchanged_bytes = 0;
         c.launches         = 0;
         c.active_on_device = false;
         std::fill(c.h_active.begin(), c.h_active.end(), (uint8_t)1);

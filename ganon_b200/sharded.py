@@ -1,8 +1,11 @@
 """Bin-block sharded classification over several GPUs: one process per GPU, every rank holds the
-bin-word columns [r*bw/N, (r+1)*bw/N) of every database row, stages the same read block, runs K2 + K3 on its columns,
-and the sparse per-read tuples are all-gathered (torch.distributed; NCCL on GPUs -- inside HBM, followed by the sort and
-K4 on every rank -- or gloo with host arrays in the CPU tests).  Every rank then holds the identical finished result,
-so no second exchange is needed; rank 0 writes the output.
+bin-word columns [r*bw/N, (r+1)*bw/N) of every database row, sees the same read block, runs K2 + K3 on its columns,
+and the sparse per-read tuples are all-gathered inside HBM by the library itself (NCCL C API, csrc/comm.cpp), followed
+by the sort and K4 on every rank.  Every rank then holds the identical finished result, so no second exchange is
+needed; rank 0 writes the output.  This module only creates the communicator (torch.distributed carries the NCCL id).
+
+merge_tuples / gather_tuples_device are the host-array and torch forms of the same exchange for the level-wise C-ABI
+calls (gnb_session_run_level .. gnb_session_finish_level): used by the CPU tests (gloo) and the single-GPU shard tests.
 
 What crosses the link per batch is the tuple list -- 8 bytes per (read, target) candidate, typically < 1 per read --
 not the per-bin count vectors (128 KiB/read at 65 536 bins) the reference layout would suggest.
@@ -13,7 +16,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .classify import Database, Session
+from .classify import Comm, Database, Session
 
 TUPLE_KEY_SHIFT = 17  # (read, node) = bits [17, 64) of a tuple
 
@@ -79,56 +82,30 @@ def gather_tuples_device(ptr: int, n: int, device: int, group=None):
     return merged
 
 
-class ShardedSession:
-    """Session over column shards; `classify` has the semantics of Session.classify on every rank."""
+def make_comm(device: int, group=None) -> Comm:
+    """The library's communicator for this process, with torch.distributed as the plumbing that carries the id: rank 0
+    draws it (gnb_comm_unique_id), broadcast_object_list hands it to the other ranks, gnb_comm_create is collective."""
+    import torch.distributed as dist
 
-    def __init__(self, dbs: Sequence[Database], *args, group=None, exchange: str = "auto", **kwargs):
-        self.group = group
-        self.exchange = exchange  # "auto": in HBM over NCCL when the backend is nccl; "host": numpy + all_gather (gloo tests)
-        self.device = int(kwargs.get("device", 0))
-        self.sess = Session(dbs, *args, **kwargs)
-        self.level_labels = self.sess.level_labels
+    if not (dist.is_available() and dist.is_initialized()):
+        return Comm(Comm.unique_id(), 0, 1, device)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return Comm(box[0], rank, world, device)
+
+
+class ShardedSession(Session):
+    """Session over this rank's column shards.  The tuple exchange between the ranks happens inside libganon_b200
+    (NCCL, see include/ganon_b200.h): every entry point of Session -- classify, stage / run_staged / finish_staged,
+    submit / collect -- works unchanged, provided all ranks make the same calls on the same blocks; every rank gets
+    the complete result.  sliced_ingest: each rank copies only its 1/n of a block to its GPU (all-gathered over NVLink)."""
+
+    def __init__(self, dbs: Sequence[Database], *args, comm: Optional[Comm] = None, group=None, sliced_ingest: bool = False, **kwargs):
+        self.comm = comm if comm is not None else make_comm(int(kwargs.get("device", 0)), group)
+        super().__init__(dbs, *args, comm=self.comm, sliced_ingest=sliced_ingest, **kwargs)
 
     @classmethod
-    def open(cls, paths: Sequence[str], rank: int, world: int, device: int, *args, group=None, **kwargs) -> "ShardedSession":
+    def open(cls, paths: Sequence[str], rank: int, world: int, device: int, *args, group=None, comm: Optional[Comm] = None, **kwargs) -> "ShardedSession":
         dbs = [Database.open(p, device=device, shard=rank, n_shards=world) for p in paths]
-        return cls(dbs, *args, group=group, device=device, **kwargs)
-
-    def _device_exchange(self) -> bool:
-        if self.exchange == "host":
-            return False
-        import torch.distributed as dist
-
-        return not (dist.is_available() and dist.is_initialized()) or dist.get_backend(self.group) == "nccl"
-
-    def run_levels(self, prefix_id: int = 0):
-        """K2/K3 per level on this rank's columns, tuple exchange, finishing stage; the batch must be staged."""
-        s = self.sess
-        exchanged = 0
-        on_device = self._device_exchange()
-        for li, nf in enumerate(s.n_filters_per_level):
-            if on_device and nf == 1:
-                # tuples never leave HBM: NCCL all-gather, sort + K4 on every rank
-                s.run_level_device(li)
-                ptr, n = s.level_tuples_device(li)
-                merged = gather_tuples_device(ptr, n, self.device, self.group)
-                exchanged += merged.numel() * 8
-                s.set_level_tuples_device(li, merged.data_ptr() if merged.numel() else 0, merged.numel())
-                s.finish_level_device(li, prefix_id)
-                continue
-            s.run_level(li)
-            for fi in range(nf):
-                merged = merge_tuples(s.level_tuples(li, fi), self.group)
-                exchanged += merged.size * 8
-                s.set_level_tuples(li, fi, merged)
-            s.finish_level(li)
-        self.last_exchanged_bytes = exchanged
-
-    def classify(self, block1, block2=None, final: bool = True, prefix_id: int = 0, len1=None, len2=None):
-        s = self.sess
-        s.stage(block1, block2, final=final, len1=len1, len2=len2)
-        self.run_levels(prefix_id)
-        return s.collect_staged(prefix_id)
-
-    def __getattr__(self, name):
-        return getattr(self.sess, name)
+        return cls(dbs, *args, group=group, comm=comm, device=device, **kwargs)

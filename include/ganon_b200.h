@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 1
+#define GNB_ABI_VERSION 2
 
 typedef enum
 {
@@ -41,6 +41,7 @@ typedef enum
 
 typedef struct gnb_db      gnb_db;      /* one database (flat IBF or HIBF) resident in HBM        */
 typedef struct gnb_session gnb_session; /* one classification run: all hierarchy levels + reports */
+typedef struct gnb_comm    gnb_comm;    /* this process's place in a bin-sharded multi-GPU run    */
 
 const char *gnb_last_error(void);
 int         gnb_abi_version(void);
@@ -52,7 +53,7 @@ int         gnb_device_count(int *n_devices);
  * IBFConfig.hpp:18-40, IBF.hpp:561-571, sdsl int_vector.hpp:2029-2035, HIBF.hpp:163-169,293-298): the header is parsed
  * by hand, the bitvector is streamed file -> pinned staging -> HBM in chunks (never a second full host copy).
  * shard/n_shards: bin-block (column) sharding for multi-GPU; shard s keeps bin-words [s*bw/n, (s+1)*bw/n) of every
- * row.  n_shards = 1 loads everything.
+ * row (n_shards <= bin_words: a shard is at least one 64-bin word wide).  n_shards = 1 loads everything.
  * ---------------------------------------------------------------------------------------------------------------- */
 typedef struct
 {
@@ -108,6 +109,24 @@ int gnb_db_create_hibf(uint64_t n_ibfs, const uint64_t *bins, const uint64_t *bi
 int gnb_db_emplace_ibf(gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint32_t *bins, uint64_t n);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Bin-sharded runs over several GPUs (one process per GPU).  The reference has no multi-device form: GanonClassify::run
+ * (GC.cpp:1676) is one process whose threads share the filter in host RAM (load_filter GC.cpp:949-965); a database larger
+ * than one GPU's HBM is split here by bin-word columns (gnb_db_open(..., shard, n_shards)), every rank classifies the
+ * same reads on its columns and the sparse per-read tuples -- not the per-bin count vectors -- are exchanged inside HBM.
+ * The exchange (NCCL, found at run time: the copy already loaded in the process, else $GANON_B200_NCCL, else the
+ * system's libnccl.so.2) lives inside the library: a session created with gnb_session_config.comm set behaves on every
+ * rank like the unsharded session (classify / stage+run / submit+collect), provided all ranks make the same calls in the
+ * same order on the same blocks.  Every rank returns the identical, complete result.
+ * gnb_comm_unique_id: called on one rank; the GNB_COMM_ID_BYTES bytes are carried to the other ranks by the caller
+ * (torch.distributed, MPI, a pipe ...).  gnb_comm_create: collective over all ranks.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define GNB_COMM_ID_BYTES 256
+int  gnb_comm_unique_id(void *id, uint64_t cap);
+int  gnb_comm_create(const void *id, int rank, int n_ranks, int device, gnb_comm **out);
+int  gnb_comm_info(const gnb_comm *c, int *rank, int *n_ranks, int *device, int *nccl_version);
+void gnb_comm_free(gnb_comm *c);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Test hooks for single kernels.
  * ---------------------------------------------------------------------------------------------------------------- */
 /* K2: seqan3::views::minimiser_hash(ungapped{k}, window_size{w}, adjust_seed(k)) of one sequence, emitted order
@@ -146,6 +165,11 @@ typedef struct
     int                 n_reads_chunk;    /* --n-reads (only observable in the parse-error truncation rule); 0=400   */
     int                 quiet;            /* suppress WARNING lines on stderr (--quiet)                              */
     void               *cuda_stream;      /* cudaStream_t to run on (e.g. a framework's stream); NULL = own stream   */
+    gnb_comm           *comm;             /* bin-sharded run: dbs[] are this rank's column shards; NULL = one GPU   */
+    int                 sliced_ingest;    /* with comm: each rank copies only bytes [r*S, (r+1)*S), S = ceil(len/n  */
+                                          /* rounded up to 16), of a read block to its GPU and the slices are       */
+                                          /* all-gathered over NVLink; the other bytes of the block are never read   */
+                                          /* on this rank (they need not be valid memory contents)                   */
 } gnb_session_config;
 
 typedef struct
@@ -178,6 +202,8 @@ typedef struct
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host for the batch                        */
     float    ms_finish_device;   /* K4 (finishing stage kernels: select, scan, write) of the batch                  */
     uint32_t levels_on_device;   /* hierarchy levels of the batch finished by K4 (the others by the host stage)     */
+    float    ms_exchange;        /* bin-sharded runs: tuple exchange between the ranks (counts + lists), device time  */
+    uint64_t exchanged_bytes;    /* tuples of all ranks received by this one                                         */
 } gnb_batch_result;
 
 int  gnb_session_create(const gnb_session_config *cfg, gnb_session **out);

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
     exported = set(re.findall(r" T (gnb_[a-z0-9_]+)", out))
     assert set(declared) <= exported
-    assert L.gnb_abi_version() == 1
+    assert L.gnb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -641,7 +641,67 @@ def test_sharded_create_fill_emplace_equals_slice():
         assert np.array_equal(got, whole[:, pi.shard_word_begin : pi.shard_word_end])
 
 
-def _two_gpu_worker(rank, world, port, ibf, fq_path, out_dir):
+def _sharded_cases(golden_dbs):
+    """(name, database paths, labels, cutoffs, rel_filter, fpr_query, reads1, reads2) run sharded and unsharded."""
+    g = SU.GOLDEN
+    return [
+        ("se", [golden_dbs["synth"]], None, [0.1], [0.5], [1.0], os.path.join(g, "reads.se.fq"), None),
+        ("pe_fpr", [golden_dbs["synth"]], None, [0.0], [1.0], [1e-3], os.path.join(g, "reads.1.fq"), os.path.join(g, "reads.2.fq")),
+        ("fasta_host_reader", [golden_dbs["synth"]], None, [0.1], [0.5], [1.0], os.path.join(g, "reads.fa"), None),
+        # (a column shard cannot be narrower than one 64-bin word, so the one-word real4 fixtures cannot be split)
+        ("two_levels", [golden_dbs["synth"], golden_dbs["synth"]], ["A", "B"], [0.6, 0.1], [0.2, 0.5], [1.0, 1.0], os.path.join(g, "reads.se.fq"), None),
+        ("two_filters_one_level", [golden_dbs["synth"], golden_dbs["synth"]], ["A", "A"], [0.3, 0.1], [0.5], [1.0], os.path.join(g, "reads.se.fq"), None),
+    ]
+
+
+def _cut_blocks(fq1, fq2, n_blocks):
+    """Whole FASTQ / FASTA records grouped into n_blocks consecutive blocks (mates cut at the same record)."""
+    def recs(b):
+        mark = b[:1]
+        out = [mark + r for r in b.split(b"\n" + mark)]
+        out[0] = out[0][1:]
+        return [r if r.endswith(b"\n") else r + b"\n" for r in out]
+
+    r1 = recs(fq1)
+    r2 = recs(fq2) if fq2 is not None else None
+    step = (len(r1) + n_blocks - 1) // n_blocks
+    return [(b"".join(r1[a : a + step]), b"".join(r2[a : a + step]) if r2 is not None else None) for a in range(0, len(r1), step)]
+
+
+def _run_case(make_session, fq1, fq2):
+    """The three forms of the public call on one session factory: synchronous classify, stage + run + finish, and the
+    pipelined submit / collect over several blocks.  Returns their (.all lines sorted, .unc lines sorted, report)."""
+    out = []
+    s = make_session()
+    r = s.classify(fq1, fq2, final=True)
+    out.append((sorted(b"".join(result_text(r, "all", lv) for lv in range(len(s.level_labels))).decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), s.report()))
+    s.close()
+    s = make_session()
+    s.stage(fq1, fq2, final=True)
+    s.run_staged()
+    r = s.finish_staged()
+    out.append((sorted(b"".join(result_text(r, "all", lv) for lv in range(len(s.level_labels))).decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), s.report()))
+    s.close()
+    s = make_session()
+    _n, cap = s.in_flight()
+    blocks = _cut_blocks(fq1, fq2, 5)
+    alls, uncs, pending = [], [], 0
+    for i, (b1, b2) in enumerate(blocks):
+        s.submit(b1, b2, final=i == len(blocks) - 1)
+        pending += 1
+        while pending >= cap or (i == len(blocks) - 1 and pending):
+            r = s.collect()
+            alls += b"".join(result_text(r, "all", lv) for lv in range(len(s.level_labels))).decode().splitlines()
+            uncs += result_text(r, "unc").decode().splitlines()
+            pending -= 1
+    out.append((sorted(alls), sorted(uncs), s.report()))
+    s.close()
+    return out
+
+
+def _two_gpu_worker(rank, world, port, cases, out_dir):
+    import pickle
+
     import torch
     import torch.distributed as dist
 
@@ -649,19 +709,33 @@ def _two_gpu_worker(rank, world, port, ibf, fq_path, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    from ganon_b200.sharded import ShardedSession
+    from ganon_b200.sharded import ShardedSession, make_comm
 
-    s = ShardedSession.open([ibf], rank, world, rank, [0.1], [0.5], [1.0], output_all=True, output_unclassified=True)
-    res = s.classify(open(fq_path, "rb").read(), final=True)
-    with open(os.path.join(out_dir, "r%d.all" % rank), "wb") as f:
-        f.write(result_text(res, "all"))
-    with open(os.path.join(out_dir, "r%d.rep" % rank), "wb") as f:
-        f.write(s.report())
+    comm = make_comm(rank)
+    assert comm.n_ranks == world and comm.nccl_version() > 20000
+    results = {}
+    for name, paths, labels, cutoff, rel_filter, fpr, p1, p2 in cases:
+        fq1 = open(p1, "rb").read()
+        fq2 = open(p2, "rb").read() if p2 else None
+        dbs = [Database.open(p, device=rank, shard=rank, n_shards=world) for p in paths]
+        for sliced in (False, True):
+            mk = lambda: ShardedSession(dbs, cutoff, rel_filter, fpr, hierarchy_labels=labels, output_all=True, output_unclassified=True, device=rank, comm=comm, sliced_ingest=sliced)
+            results[(name, sliced)] = _run_case(mk, fq1, fq2)
+        for d in dbs:
+            d.close()
+    with open(os.path.join(out_dir, "r%d.pkl" % rank), "wb") as f:
+        pickle.dump(results, f)
     dist.barrier()
+    comm.close()
     dist.destroy_process_group()
 
 
 def test_sharded_two_gpus_nccl(golden_dbs, tmp_path):
+    """Bin-sharded sessions over 2 GPUs with the exchange inside the library (NCCL): every form of the public call, with
+    and without sliced ingest, single / paired / FASTA (host reader) input, two hierarchy levels, two filters on one level
+    (host finishing stage) -- each rank's result equals the unsharded session's."""
+    import pickle
+
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -673,10 +747,18 @@ def test_sharded_two_gpus_nccl(golden_dbs, tmp_path):
     with socket.socket() as so:
         so.bind(("127.0.0.1", 0))
         port = so.getsockname()[1]
-    fq = os.path.join(SU.GOLDEN, "reads.se.fq")
-    whole = Session([Database.open(golden_dbs["synth"])], [0.1], [0.5], [1.0], output_all=True, output_unclassified=True)
-    r = whole.classify(open(fq, "rb").read(), final=True)
-    mp.spawn(_two_gpu_worker, args=(2, port, golden_dbs["synth"], fq, str(tmp_path)), nprocs=2, join=True)
+    cases = _sharded_cases(golden_dbs)
+    want = {}
+    for name, paths, labels, cutoff, rel_filter, fpr, p1, p2 in cases:
+        fq1 = open(p1, "rb").read()
+        fq2 = open(p2, "rb").read() if p2 else None
+        dbs = [Database.open(p) for p in paths]
+        want[name] = _run_case(lambda: Session(dbs, cutoff, rel_filter, fpr, hierarchy_labels=labels, output_all=True, output_unclassified=True), fq1, fq2)
+        assert want[name][0] == want[name][1] == want[name][2], name  # the three forms agree unsharded
+        assert want[name][0][0], name  # and the case classifies something
+    mp.spawn(_two_gpu_worker, args=(2, port, cases, str(tmp_path)), nprocs=2, join=True)
     for rank in range(2):
-        assert sorted(open(tmp_path / ("r%d.all" % rank)).read().splitlines()) == sorted(result_text(r, "all").decode().splitlines())
-        assert open(tmp_path / ("r%d.rep" % rank), "rb").read() == whole.report()
+        got = pickle.load(open(tmp_path / ("r%d.pkl" % rank), "rb"))
+        for (name, sliced), forms in got.items():
+            for form, res in zip(("classify", "staged", "pipelined"), forms):
+                assert res == want[name][0], (rank, name, sliced, form)
