@@ -289,21 +289,29 @@ def reference_threads():
     return max(1, os.cpu_count() or 1)
 
 
+def make_room(need_bytes, keep=()):
+    """The scratch directory holds database copies for the reference binary (up to 64 GiB each) that are only a cache:
+    when the disk is short, delete the ones not named in `keep`, largest first (the GPU boxes have ~80 GB free)."""
+    os.makedirs(CACHE, exist_ok=True)
+    want = int(need_bytes * 1.05) + (2 << 30)
+    if shutil.disk_usage(CACHE).free >= want:
+        return
+    cand = [os.path.join(CACHE, f) for f in os.listdir(CACHE) if f.endswith((".ibf", ".hibf", ".part")) and os.path.join(CACHE, f) not in keep]
+    for p in sorted(cand, key=os.path.getsize, reverse=True):
+        os.remove(p)
+        if shutil.disk_usage(CACHE).free >= want:
+            return
+    if shutil.disk_usage(CACHE).free < need_bytes:
+        raise RuntimeError("not enough disk in %s (%d GiB needed)" % (CACHE, need_bytes >> 30))
+
+
 def ensure_ibf_file(wl_name, db):
     os.makedirs(CACHE, exist_ok=True)
     i = db.info()
     path = os.path.join(CACHE, "%s_seed%d.%s" % (wl_name, DB_SEED, "hibf" if i.is_hibf else "ibf"))
     want = i.device_bytes if i.is_hibf else i.bin_size_bits * i.bin_words * 8
     if not (os.path.exists(path) and os.path.getsize(path) > want):
-        free = shutil.disk_usage(CACHE).free
-        if free < want * 1.1:
-            # make room: the copies written for other workloads are only a cache
-            for f in os.listdir(CACHE):
-                if f.endswith((".ibf", ".hibf")) and not f.startswith(wl_name + "_seed"):
-                    os.remove(os.path.join(CACHE, f))
-            free = shutil.disk_usage(CACHE).free
-        if free < want * 1.1:
-            raise RuntimeError("not enough disk for the reference's copy of the database (%d GiB needed)" % (want >> 30))
+        make_room(want)
         db.save(path)
     return path
 
@@ -344,6 +352,8 @@ def db_file_matches_hbm(db, path, windows=32, words=1 << 14, seed=7):
 # same shape; otherwise "traffic" is null.
 TRAFFIC_CAPTURES = {
     "c2": (75373784000 + 10292992, 1 << 21, "profiles/r01_k3_ncu_summary.md"),
+    "c3": (301541113000 + 4524544, 1 << 19, "profiles/r02_k3_c3_ncu_summary.md"),
+    "c3": (301541113000 + 4524544, 1 << 19, "profiles/r02_k3_c3_ncu_summary.md"),
 }
 
 
@@ -929,6 +939,7 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
     fq1 = os.path.join(CACHE, "%s_cli.1.fq" % wl_name)
     fq2 = os.path.join(CACHE, "%s_cli.2.fq" % wl_name) if wl["paired"] else None
     reps = 4  # long enough for the fixed costs (buffers, first allocations) to amortise
+    make_room(reps * sum(b1.size + (b2.size if b2 is not None else 0) for b1, b2 in blocks) * 1.5, keep=(ibf_path,))
     with open(fq1, "wb") as f1:
         for _ in range(reps):
             for b1, _b2 in blocks:
@@ -1006,11 +1017,7 @@ def reference_db_file(wl_name, wl):
     want = wl["bin_size"] * ((wl["bins"] + 63) // 64) * 8
     if os.path.exists(path) and os.path.getsize(path) > want:
         return path, genomes, "cached copy"
-    free = shutil.disk_usage(CACHE).free
-    if free < want * 1.1:
-        for f in os.listdir(CACHE):
-            if f.endswith((".ibf", ".hibf")) and not f.startswith(wl_name + "_seed"):
-                os.remove(os.path.join(CACHE, f))
+    make_room(want + genomes.size)
     tool = os.path.join(ROOT, "oracle", "synthdb")
     if not os.path.exists(tool):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "synthdb"])

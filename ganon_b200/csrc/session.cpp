@@ -576,6 +576,7 @@ struct BatchCtx
 
     int  run_hibf_filter(size_t li, size_t fi, uint64_t &produced);
     int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
+    size_t hold_back(size_t n) const;
     int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines);
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
@@ -1364,6 +1365,21 @@ int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records
     return GNB_OK;
 }
 
+// A parse error later in the file retracts the --n-reads chunk being assembled, and the chunk before it when the failing
+// record opens a chunk (see the host-reader branch of stage()): floor((e - 1) / c) * c records survive, e = records before
+// the failing one.  A block that does not end the file therefore hands on only floor((end - 1) / c) * c records (absolute
+// count, end = complete records seen so far) and leaves the rest -- fewer than 2c records -- unconsumed for the next
+// block: whatever e >= end turns out to be, nothing already classified has to be taken back.  Blocks holding fewer than 2c
+// records (records of > ~80 kB in a 64 MiB block) are passed on whole.
+size_t BatchCtx::hold_back(size_t n) const
+{
+    const uint64_t c = n_reads_chunk ? n_reads_chunk : 400;
+    if (final_block || n < 2 * c)
+        return n;
+    const uint64_t end = S->file_records + n;
+    return (size_t)((end - 1) / c * c - S->file_records);
+}
+
 int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin)
 {
     GNB_CUDA(cudaSetDevice(device));
@@ -1467,6 +1483,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         if (paired)
             GNB_TRY(device_index(1, e2, final_block, n2, nl2));
         n = paired ? std::min(n1, n2) : n1;
+        n = hold_back(n);
         const uint32_t init_status[4] = {0, 0, 0xffffffffu, 0};
         GNB_CUDA(cudaMemcpyAsync(d_status.p, init_status, 16, cudaMemcpyHostToDevice, st_in));
         GNB_TRY(d_off1.ensure(n * 4 + 4));
@@ -1558,6 +1575,8 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             if (!quiet)
                 fprintf(stderr, "Error parsing file(s): %s\n", (t1.parse_error ? t1.error_msg : t2.error_msg).c_str());
         }
+        if (!err)
+            n = hold_back(n);
         t1.truncate(n);
         if (paired)
             t2.truncate(n);
