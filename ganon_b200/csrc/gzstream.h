@@ -1,0 +1,45 @@
+// Read files as a byte stream for the record reader (A0, parse_reads GC.cpp:1220-1287).  seqan3 opens read files through
+// its transparent decompression layer (seqan3/io/detail/misc_input.hpp: magic-header detection, then zlib's inflate on one
+// thread, or its BGZF stream); here plain files are read with parallel preads and gzip files -- single-member, multi-member
+// or BGZF alike -- are inflated by all host threads at once:
+//   * the compressed stream is cut into chunks; in every chunk but the first a thread looks for the next deflate block
+//     that starts with a valid dynamic-Huffman header (bit-granular search, RFC 1951 3.2.7) and decodes from there with an
+//     UNKNOWN 32 KiB history: output symbols are 16 bits wide, a back-reference that reaches before the chunk's start
+//     yields a marker naming the history position it wants (the two-pass scheme of pugz / rapidgzip);
+//   * a chunk's decoder stops at the block boundary where the next chunk's decoder started (a candidate it runs past
+//     was a false positive and is dropped: the predecessor simply keeps decoding through it);
+//   * the histories are then propagated chunk by chunk (32 KiB each, sequential), markers are replaced in parallel, and
+//     the CRC-32 / ISIZE trailer of every gzip member is verified from per-chunk CRCs (crc32_combine).
+// Any structural error or CRC mismatch is reported (GNB_ERR_IO), as zlib would.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+
+namespace gnb
+{
+
+class ThreadPool;
+
+class ByteSource
+{
+  public:
+    virtual ~ByteSource() = default;
+    // next bytes of the (decompressed) stream: > 0 bytes written to dst, 0 at the end, < 0 = gnb_status (message in error())
+    virtual int64_t read(char *dst, size_t cap) = 0;
+    // plain files only: the stream position can be set (sliced ingest re-reads from the consumed position)
+    virtual bool    seekable() const { return false; }
+    virtual int64_t read_at(char *dst, size_t cap, uint64_t offset) { (void)dst, (void)cap, (void)offset; return -1; }
+    virtual uint64_t size() const { return 0; }
+    virtual bool    is_gzip() const { return false; }
+    const std::string &error() const { return err_; }
+
+  protected:
+    std::string err_;
+};
+
+// plain or gzip by magic number (1f 8b), like seqan3's make_secondary_istream
+std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int threads, std::string &err);
+
+} // namespace gnb

@@ -257,6 +257,17 @@ int gnb_session_finish_level_device(gnb_session *s, uint32_t level, uint32_t pre
 /* device timings / byte counts of the staged batch so far (level-wise forms; the batch stays staged) */
 int gnb_session_staged_timings(gnb_session *s, gnb_batch_result *timings);
 
+/* Read files as the record reader sees them (parse_reads GC.cpp:1220-1287 opens them through seqan3's transparent
+ * decompression, seqan3/io/detail/misc_input.hpp): plain, or gzip by magic number -- single-member, multi-member and BGZF
+ * alike are inflated by `io_threads` host threads at once (0 = all, at most 16; csrc/gzstream.h), CRC-32 and length of every
+ * member verified.  gnb_reads_file_read: the next bytes of the decompressed stream (> 0), 0 at the end, < 0 = gnb_status.
+ * No device is involved. */
+typedef struct gnb_reads_file gnb_reads_file;
+int     gnb_reads_file_open(const char *path, int io_threads, gnb_reads_file **out);
+int64_t gnb_reads_file_read(gnb_reads_file *f, void *dst, uint64_t cap);
+int     gnb_reads_file_is_gzip(const gnb_reads_file *f);
+void    gnb_reads_file_close(gnb_reads_file *f);
+
 /* Page-lock / unlock a host buffer that will be passed as a read block (cudaHostRegister): faster, truly asynchronous
  * host->device copies. */
 int gnb_host_register(void *ptr, uint64_t bytes);
