@@ -961,10 +961,103 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
     out = {"rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
            "reads_per_s": n_cli / cs if cs else None, "all_bytes": os.path.getsize(os.path.join(CACHE, "cli_out.all")) if os.path.exists(os.path.join(CACHE, "cli_out.all")) else None,
            "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
+    # the same reads as ordinary single-member gzip files (what sequencers / archives deliver): the library inflates them
+    # with all host threads (csrc/gzstream.cpp)
+    try:
+        gz1 = fq1 + ".gz"
+        gz2 = fq2 + ".gz" if fq2 else None
+        t0 = time.perf_counter()
+        write_single_member_gzip(gz1, [b1 for b1, _b2 in blocks])
+        if gz2:
+            write_single_member_gzip(gz2, [b2 for _b1, b2 in blocks])
+        t_gz = time.perf_counter() - t0
+        n_gz = pool * R * (2 if wl["paired"] else 1)
+        reads_gz = ["-p", gz1 + "," + gz2] if gz2 else ["-r", gz1]
+        cmd_gz = [c for c in cmd]
+        i = cmd_gz.index("-p" if fq2 else "-r")
+        cmd_gz[i : i + 2] = reads_gz
+        t0 = time.perf_counter()
+        pr = subprocess.run(cmd_gz, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        wall = time.perf_counter() - t0
+        mc = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+        cs = float(mc.group(1)) if mc else None
+        out["gz"] = {"rc": pr.returncode, "reads": n_gz, "gz_bytes": os.path.getsize(gz1) + (os.path.getsize(gz2) if gz2 else 0), "fastq_bytes": sum(b1.size + (b2.size if b2 is not None else 0) for b1, b2 in blocks),
+                     "classify_s": cs, "wall_s": wall, "reads_per_s": n_gz / cs if cs else None, "compress_s": t_gz, "host_threads": reference_threads(),
+                     "kind": "single-member gzip (one deflate stream per file, level 6)", "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
+        for p in (gz1, gz2):
+            if p and os.path.exists(p):
+                os.remove(p)
+    except Exception as e:
+        out["gz"] = {"error": str(e)[:300]}
     for p in (fq1, fq2, os.path.join(CACHE, "cli_out.all")):
         if p and os.path.exists(p):
             os.remove(p)
     return out
+
+
+def write_single_member_gzip(path, arrays, level=6, piece=8 << 20):
+    """One gzip member whose deflate stream is compressed in pieces on all host threads (each piece ends with a full flush,
+    the way pigz -i writes): an ordinary .gz for every reader, made quickly."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    views = []
+    for a in arrays:
+        mv = memoryview(np.ascontiguousarray(a)).cast("B")
+        views += [mv[o : o + piece] for o in range(0, len(mv), piece)]
+
+    def comp(iv):
+        i, v = iv
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return co.compress(v) + co.flush(zlib.Z_FINISH if i == len(views) - 1 else zlib.Z_FULL_FLUSH), zlib.crc32(v), len(v)
+
+    crc = 0
+    total = 0
+    with ThreadPoolExecutor(reference_threads()) as ex, open(path, "wb") as f:
+        f.write(b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03")
+        for data, c, n in ex.map(comp, enumerate(views)):
+            f.write(data)
+            crc = _crc32_combine(crc, c, n)
+            total += n
+        f.write(struct.pack("<II", crc & 0xFFFFFFFF, total & 0xFFFFFFFF))
+
+
+def _crc32_combine(crc1, crc2, len2):
+    """zlib's crc32_combine (not exposed by Python): CRC of a concatenation from the CRCs of its parts."""
+
+    def times(mat, vec):
+        s = 0
+        i = 0
+        while vec:
+            if vec & 1:
+                s ^= mat[i]
+            vec >>= 1
+            i += 1
+        return s
+
+    def square(mat):
+        return [times(mat, mat[n]) for n in range(32)]
+
+    if len2 <= 0:
+        return crc1
+    odd = [0xEDB88320] + [1 << n for n in range(31)]
+    even = square(odd)
+    odd = square(even)
+    while True:
+        even = square(odd)
+        if len2 & 1:
+            crc1 = times(even, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+        odd = square(even)
+        if len2 & 1:
+            crc1 = times(odd, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+    return crc1 ^ crc2
 
 
 def cpu_baseline(wl_name, wl, db, block, sess, result_text):

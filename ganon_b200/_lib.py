@@ -111,6 +111,16 @@ class BatchResult(C.Structure):
     ]
 
 
+class OutputFds(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("all_fd", C.POINTER(C.c_int)), ("one_fd", C.POINTER(C.c_int)), ("unc_fd", C.c_int)]
+
+
+class FilesResult(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_records", "n_classified", "n_blocks", "bytes_read1", "bytes_read2")] + [("parse_error", C.c_int), ("is_gzip", C.c_int)] + [
+        (n, C.c_double) for n in ("ms_open", "ms_read_wait", "ms_submit", "ms_collect", "ms_write")
+    ]
+
+
 class ReassignResult(C.Structure):
     _fields_ = [
         ("n_groups", C.c_uint32),
@@ -177,6 +187,7 @@ SYMBOLS = {
     "gnb_reads_file_read": (C.c_int64, [_P, _P, C.c_uint64]),
     "gnb_reads_file_is_gzip": (C.c_int, [_P]),
     "gnb_reads_file_close": (None, [_P]),
+    "gnb_session_classify_files": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_char_p, C.POINTER(OutputFds), C.c_uint64, C.c_int, C.POINTER(FilesResult)]),
     "gnb_host_register": (C.c_int, [_P, C.c_uint64]),
     "gnb_host_unregister": (C.c_int, [_P]),
     "gnb_session_level_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),

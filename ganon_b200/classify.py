@@ -332,6 +332,12 @@ class Session:
         check(_lib.lib().gnb_session_collect(self._h, C.byref(res)))
         return res
 
+    def classify_files(self, prefix_id: int, file1: str, file2: Optional[str] = None, fds: Optional["_lib.OutputFds"] = None, block_bytes: int = 0, io_threads: int = 0) -> "_lib.FilesResult":
+        """One read file (or pair) start to end inside the library (gnb_session_classify_files); text goes to `fds`."""
+        res = _lib.FilesResult()
+        check(_lib.lib().gnb_session_classify_files(self._h, prefix_id, file1.encode(), file2.encode() if file2 else None, C.byref(fds) if fds is not None else None, block_bytes, io_threads, C.byref(res)))
+        return res
+
     def in_flight(self) -> Tuple[int, int]:
         n, cap = C.c_uint32(), C.c_uint32()
         check(_lib.lib().gnb_session_in_flight(self._h, C.byref(n), C.byref(cap)))
@@ -542,270 +548,7 @@ class GanonClassifyConfig:
         return True
 
 
-class _BgzfReader:
-    """Blocked gzip (BGZF: what bcl2fastq / BCL Convert, bgzip and htslib write): every <= 64 KiB block is an independent
-    gzip member whose compressed size sits in a 'BC' extra field and whose inflated size in the trailer, so the blocks
-    of a chunk are inflated in parallel (zlib releases the GIL) straight to their places in the output buffer.  A plain
-    single-member .gz has no such structure and stays on one thread (gzip module)."""
-
-    CHUNK = 8 << 20  # compressed bytes looked at per readinto round
-
-    def __init__(self, path: str, pool):
-        self.f = open(path, "rb", buffering=0)
-        self.size = os.fstat(self.f.fileno()).st_size
-        self.pos = 0
-        self.pool = pool
-        self.carry = b""  # inflated bytes that did not fit the caller's buffer
-
-    @staticmethod
-    def is_bgzf(path: str) -> bool:
-        with open(path, "rb") as f:
-            h = f.read(18)
-        return len(h) == 18 and h[:4] == b"\x1f\x8b\x08\x04" and h[10:12] == b"\x06\x00" and h[12:14] == b"BC" and h[14:16] == b"\x02\x00"
-
-    @staticmethod
-    def _inflate(raw: bytes, a: int, b: int) -> bytes:
-        # block = 18-byte header (FEXTRA with the BC subfield first, as every BGZF writer emits), deflate data, CRC32, ISIZE
-        xlen = raw[a + 10] | (raw[a + 11] << 8)
-        return zlib.decompress(raw[a + 12 + xlen : b - 8], wbits=-15)
-
-    def readinto(self, mv) -> int:
-        room = len(mv)
-        done = 0
-        if self.carry:
-            n = min(room, len(self.carry))
-            mv[:n] = self.carry[:n]
-            self.carry = self.carry[n:]
-            done = n
-            if done == room:
-                return done
-        while done < room and self.pos < self.size:
-            raw = os.pread(self.f.fileno(), min(self.CHUNK, self.size - self.pos), self.pos)
-            # block boundaries of the chunk
-            spans, a, out = [], 0, 0
-            while a + 18 <= len(raw):
-                if raw[a : a + 4] != b"\x1f\x8b\x08\x04" or raw[a + 12 : a + 14] != b"BC":
-                    raise IOError("not a BGZF block at offset %d" % (self.pos + a))
-                bsize = (raw[a + 16] | (raw[a + 17] << 8)) + 1
-                if a + bsize > len(raw):
-                    break
-                isize = int.from_bytes(raw[a + bsize - 4 : a + bsize], "little")
-                if spans and out + isize > room - done:
-                    break  # the caller's buffer is full: the rest of the chunk is looked at again next time
-                spans.append((a, a + bsize, out, isize))
-                out += isize
-                a += bsize
-            if not spans:
-                raise IOError("truncated BGZF block at offset %d" % self.pos)
-            self.pos += a
-            # groups of blocks per task keep the per-task overhead small
-            step = max(1, len(spans) // (4 * 16) + 1)
-            groups = [spans[i : i + step] for i in range(0, len(spans), step)]
-
-            def work(g):
-                return b"".join(self._inflate(raw, x, y) for x, y, _o, _n in g)
-
-            for g, data in zip(groups, self.pool.map(work, groups)):
-                n = min(len(data), room - done)
-                mv[done : done + n] = data[:n]
-                done += n
-                if n < len(data):
-                    self.carry += data[n:]
-        return done
-
-    def close(self) -> None:
-        self.f.close()
-
-
-_IO_THREADS = int(os.environ.get("GANON_B200_IO_THREADS", str(min(16, os.cpu_count() or 8))))
-_IO_SLICE = 4 << 20
-_HEADROOM = 1 << 20
-
-
-class _ReadStream:
-    """A read file (plain or gzip, by magic) consumed in blocks (reader of GC.cpp:1220-1287).
-
-    Blocks live in a ring of page-locked buffers (a block must stay untouched while its batch is in flight).  Every
-    buffer has a headroom in front of the file bytes: the unconsumed tail of the previous block (less than one record) is
-    copied right-aligned into it, so the file bytes themselves never move and the NEXT buffer can be filled while the
-    current block is being staged.  Plain files are read with parallel preads (page-cache copies are what bounds a
-    single reader thread); gzip files are inflated by the prefetch thread (zlib releases the GIL)."""
-
-    def __init__(self, path: str, block_bytes: int, n_buffers: int):
-        from concurrent.futures import ThreadPoolExecutor
-
-        with open(path, "rb") as f:
-            magic = f.read(2)
-        self.gz = magic == b"\x1f\x8b"
-        self.pool = ThreadPoolExecutor(max_workers=max(1, _IO_THREADS))
-        if self.gz and _BgzfReader.is_bgzf(path):
-            self.f = _BgzfReader(path, self.pool)
-        else:
-            self.f = gzip.open(path, "rb") if self.gz else open(path, "rb", buffering=0)
-        self.size = None if self.gz else os.fstat(self.f.fileno()).st_size
-        self.pos = 0  # plain files: next file offset to read
-        self.block_bytes = block_bytes
-        self.head = _HEADROOM
-        self.bufs = [bytearray(self.head + block_bytes) for _ in range(n_buffers)]
-        self.pinned = []
-        self._pin()
-        self.cur = -1
-        self.fill = 0  # bytes of the current block (tail + fresh)
-        self.start = 0  # offset of the current block inside its buffer
-        self.tail = b""
-        self.eof = False
-        self._raw_eof = False
-        self._next = None  # (buffer index, future -> fresh byte count)
-
-    def _pin(self) -> None:
-        for b in self.bufs:
-            if id(b) in [i for i, _ in self.pinned]:
-                continue
-            arr = (C.c_char * len(b)).from_buffer(b)
-            if _lib.lib().gnb_host_register(C.cast(arr, C.c_void_p), len(b)) == 0:
-                self.pinned.append((id(b), arr))  # keeps the export alive: the bytearray cannot be resized while pinned
-
-    def _unpin(self) -> None:
-        for _i, arr in self.pinned:
-            _lib.lib().gnb_host_unregister(C.cast(arr, C.c_void_p))
-        self.pinned = []
-
-    @property
-    def buf(self):
-        """(address, length)-style view of the current block for Session.submit."""
-        b = self.bufs[self.cur]
-        arr = (C.c_char * len(b)).from_buffer(b)
-        return (C.addressof(arr) + self.start, self.fill)
-
-    def block_bytes_view(self) -> memoryview:
-        return memoryview(self.bufs[self.cur])[self.start : self.start + self.fill]
-
-    def _read_fresh(self, idx: int) -> int:
-        """Fill bufs[idx][head : head + block_bytes] from the file; returns the byte count (runs in the pool)."""
-        buf = self.bufs[idx]
-        mv = memoryview(buf)
-        try:
-            if self.gz:
-                got_total = 0
-                while got_total < self.block_bytes:
-                    got = self.f.readinto(mv[self.head + got_total : self.head + self.block_bytes])
-                    if not got:
-                        self._raw_eof = True
-                        break
-                    got_total += got
-                return got_total
-            want = min(self.block_bytes, self.size - self.pos)
-            if want <= 0:
-                self._raw_eof = True
-                return 0
-            fd, base, off0 = self.f.fileno(), self.head, self.pos
-            futs = []
-            for o in range(0, want, _IO_SLICE):
-                n = min(_IO_SLICE, want - o)
-                futs.append(self.pool.submit(self._pread, fd, mv[base + o : base + o + n], off0 + o))
-            for fu in futs:
-                fu.result()
-            self.pos += want
-            if self.pos >= self.size:
-                self._raw_eof = True
-            return want
-        finally:
-            mv.release()
-
-    @staticmethod
-    def _pread(fd: int, view: memoryview, offset: int) -> None:
-        done = 0
-        while done < len(view):
-            got = os.preadv(fd, [view[done:]], offset + done)
-            if got <= 0:
-                raise IOError("short read")
-            done += got
-
-    def _schedule(self, idx: int) -> None:
-        import threading
-
-        box = {}
-
-        def work():
-            try:
-                box["n"] = self._read_fresh(idx)
-            except BaseException as e:  # surfaced by next_block
-                box["err"] = e
-
-        t = threading.Thread(target=work, daemon=True)
-        t.start()
-        self._next = (idx, t, box)
-
-    def next_block(self) -> None:
-        """Move to the next ring buffer: its file bytes were prefetched; the tail of the previous block goes in front."""
-        idx = (self.cur + 1) % len(self.bufs)
-        if self._next is None or self._next[0] != idx:
-            if not self._raw_eof:
-                self._schedule(idx)
-        fresh = 0
-        if self._next is not None and self._next[0] == idx:
-            _i, t, box = self._next
-            t.join()
-            self._next = None
-            if "err" in box:
-                raise box["err"]
-            fresh = box["n"]
-        self.cur = idx
-        buf = self.bufs[idx]
-        n = len(self.tail)
-        if n > self.head:
-            # a tail longer than the headroom (a record of more than 1 MiB): rebuild the buffers with more room in front
-            self._wait_idle()
-            data = bytes(self.tail) + bytes(buf[self.head : self.head + fresh])
-            self._unpin()
-            self.head = 2 * n
-            self.bufs = [bytearray(self.head + max(self.block_bytes, len(data))) for _ in self.bufs]
-            self._pin()
-            self.cur = 0
-            buf = self.bufs[0]
-            buf[self.head - n : self.head - n + len(data)] = data
-        else:
-            buf[self.head - n : self.head] = self.tail
-        self.start = self.head - n
-        self.fill = n + fresh
-        self.tail = b""
-        self.eof = self._raw_eof
-        if not self._raw_eof:
-            self._schedule((self.cur + 1) % len(self.bufs))  # overlaps with the staging of this block
-
-    def _wait_idle(self) -> None:
-        if self._next is not None:
-            self._next[1].join()
-
-    def consume(self, n: int) -> None:
-        b = self.bufs[self.cur]
-        self.tail = bytes(b[self.start + n : self.start + self.fill])
-
-    def whole_block_to_tail(self) -> None:
-        self.consume(0)
-
-    def grow(self) -> None:
-        """Not a single complete record fitted: double the block size (the whole block became the tail)."""
-        self._wait_idle()
-        pending = None
-        if self._next is not None:
-            _i, _t, box = self._next
-            pending = bytes(self.bufs[self._next[0]][self.head : self.head + box.get("n", 0)])
-            self._next = None
-        if pending:
-            self.tail = self.tail + pending  # bytes already taken from the file stay in order
-        self._unpin()
-        self.block_bytes *= 2
-        self.head = max(self.head, 2 * len(self.tail))
-        self.bufs = [bytearray(self.head + self.block_bytes) for _ in self.bufs]
-        self._pin()
-        self.cur = -1
-
-    def close(self) -> None:
-        self._wait_idle()
-        self.pool.shutdown(wait=True)
-        self.f.close()
-        self._unpin()
+IO_THREADS = int(os.environ.get("GANON_B200_IO_THREADS", "0"))  # 0 = all host threads (at most 16)
 
 
 def _parse_reads_config(cfg: GanonClassifyConfig) -> Optional[Dict[str, List[Tuple[str, str]]]]:
@@ -909,91 +652,35 @@ def run(cfg: GanonClassifyConfig) -> bool:
     out_all = level_files("all") if cfg.output_all else {}
     out_one = level_files("one") if write_one else {}
 
-    # writer thread (the reference has one per output kind, GC.cpp:1289-1322): the text of a batch is copied out of the
-    # library's result buffers (valid until the next collect) and written while the next batches are staged
-    import queue
-    import threading
-
-    wq: "queue.Queue" = queue.Queue(maxsize=16)
-    werr: List[BaseException] = []
-
-    def writer() -> None:
-        while True:
-            item = wq.get()
-            if item is None:
-                return
-            try:
-                item[0].write(item[1])
-            except BaseException as e:  # reported after the run
-                werr.append(e)
-
-    wthread = threading.Thread(target=writer, daemon=True)
-    wthread.start()
-
-    def write_result(prefix: str, res: BatchResult) -> None:
-        for li in range(len(labels)):
-            if cfg.output_all and res.all_len[li]:
-                wq.put((out_all[prefix][li], C.string_at(res.all_text[li], res.all_len[li])))
-            if write_one and res.one_len[li]:
-                wq.put((out_one[prefix][li], C.string_at(res.one_text[li], res.one_len[li])))
-        if cfg.output_unclassified and res.unc_len:
-            wq.put((out_unc[prefix], C.string_at(res.unc_text, res.unc_len)))
-
+    # reader -> classify -> writer (GC.cpp:1220-1322) runs inside the library per file (pair): block ring in page-locked
+    # memory, parallel preads / parallel inflate, batches in flight on the GPU, a writer thread on the files opened here
     t_class = time.time()
-    _n, capacity = sess.in_flight()
-    pending: List[str] = []  # prefixes of the batches in flight, oldest first
-    prof = {"open": 0.0, "read_wait": 0.0, "submit": 0.0, "collect": 0.0, "blocks": 0}
-    for pid, prefix in enumerate(prefixes):
-        for file1, file2 in reads_config[prefix]:
-            tp = time.time()
-            s1 = _ReadStream(file1, BLOCK_BYTES, capacity + 2)
-            s2 = _ReadStream(file2, BLOCK_BYTES, capacity + 2) if file2 else None
-            prof["open"] += time.time() - tp
-            try:
-                while True:
-                    tp = time.time()
-                    s1.next_block()
-                    if s2:
-                        s2.next_block()
-                    prof["read_wait"] += time.time() - tp
-                    prof["blocks"] += 1
-                    final = s1.eof and (s2 is None or s2.eof)
-                    if s1.fill == 0 or (s2 is not None and s2.fill == 0):
-                        break  # nothing (more) to pair
-                    tp = time.time()
-                    info = sess.submit(s1.buf, s2.buf if s2 else None, final=final, prefix_id=pid)
-                    prof["submit"] += time.time() - tp
-                    pending.append(prefix)
-                    if len(pending) > capacity - 1 or info.parse_error or final or info.n_reads == 0:
-                        while len(pending) > (0 if (info.parse_error or final or info.n_reads == 0) else capacity - 1):
-                            tp = time.time()
-                            res_ = sess.collect()
-                            prof["collect"] += time.time() - tp
-                            write_result(pending.pop(0), res_)
-                    if info.parse_error:
-                        break  # rest of the file is skipped (GC.cpp:1278-1283)
-                    if info.n_reads == 0 and not final:
-                        s1.whole_block_to_tail()
-                        s1.grow()
-                        if s2:
-                            s2.whole_block_to_tail()
-                            s2.grow()
-                        continue
-                    s1.consume(info.consumed1)
-                    if s2:
-                        s2.consume(info.consumed2)
-                    if final:
-                        break
-            finally:
-                while pending:
-                    write_result(pending.pop(0), sess.collect())
-                s1.close()
-                if s2:
-                    s2.close()
-    wq.put(None)
-    wthread.join()
-    if werr:
-        print("ERROR: writing output files (%s)" % werr[0], file=sys.stderr)
+    prof = {"open": 0.0, "read_wait": 0.0, "submit": 0.0, "collect": 0.0, "write": 0.0, "blocks": 0}
+    n_lv = len(labels)
+    try:
+        for pid, prefix in enumerate(prefixes):
+            for fh in set(out_all.get(prefix, []) + out_one.get(prefix, []) + ([out_unc[prefix]] if prefix in out_unc else [])):
+                fh.flush()
+            all_fd = (C.c_int * n_lv)(*[out_all[prefix][li].fileno() if cfg.output_all else -1 for li in range(n_lv)])
+            one_fd = (C.c_int * n_lv)(*[out_one[prefix][li].fileno() if write_one else -1 for li in range(n_lv)])
+            fds = _lib.OutputFds(n_lv, all_fd, one_fd, out_unc[prefix].fileno() if cfg.output_unclassified else -1)
+            for file1, file2 in reads_config[prefix]:
+                fr = sess.classify_files(pid, file1, file2 or None, fds, BLOCK_BYTES, IO_THREADS)
+                prof["open"] += fr.ms_open / 1e3
+                prof["read_wait"] += fr.ms_read_wait / 1e3
+                prof["submit"] += fr.ms_submit / 1e3
+                prof["collect"] += fr.ms_collect / 1e3
+                prof["write"] += fr.ms_write / 1e3
+                prof["blocks"] += fr.n_blocks
+    except _lib.GnbError as e:
+        print("ERROR: %s" % e.msg, file=sys.stderr)
+        for group in (list(out_unc.values()), *(v for v in out_all.values()), *(v for v in out_one.values()), list(out_rep.values())):
+            for fh in group:
+                if not fh.closed:
+                    fh.close()
+        sess.close()
+        for d in dbs:
+            d.close()
         return False
     t_class = time.time() - t_class
 
@@ -1022,7 +709,7 @@ def run(cfg: GanonClassifyConfig) -> bool:
                 fh.close()
 
     if cfg.verbose and not cfg.quiet:
-        print("host pipeline (s): open+pin %.3f, waiting for file blocks %.3f, staging (H2D + record index) %.3f, waiting for results %.3f; %d blocks of <= %d MiB" % (prof["open"], prof["read_wait"], prof["submit"], prof["collect"], prof["blocks"], BLOCK_BYTES >> 20), file=sys.stderr)
+        print("host pipeline (s): open+pin %.3f, waiting for file blocks %.3f, staging (H2D + record index) %.3f, waiting for results %.3f, writer thread %.3f; %d blocks of <= %d MiB" % (prof["open"], prof["read_wait"], prof["submit"], prof["collect"], prof["write"], prof["blocks"], BLOCK_BYTES >> 20), file=sys.stderr)
     if not cfg.quiet:
         _print_stats(cfg, sess, prefixes, labels, t_class, t_load, time.time() - t_start)
     sess.close()

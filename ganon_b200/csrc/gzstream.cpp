@@ -426,6 +426,7 @@ struct Chunk
     size_t                n_out = 0;
     uint64_t              start_bit = 0, end_bit = 0;
     bool                  ok = false, eos = false, found = false;
+    bool                  ran_out = false; // failed because the buffered data ended (not an error if the file goes on)
     std::string           err;
     std::vector<MemberEnd> ends;
     std::vector<uint8_t>  bytes; // markers resolved
@@ -481,9 +482,10 @@ void decode_chunk(BitIn in, bool at_header, const uint64_t *cands, size_t n_cand
     c.start_bit = in.pos;
     size_t ci   = 0;
     auto   fail = [&](const char *m) {
-        c.ok  = false;
-        c.err = m;
-        c.n_out = o;
+        c.ok      = false;
+        c.err     = m;
+        c.n_out   = o;
+        c.ran_out = strncmp(m, "unexpected end", 14) == 0 || strncmp(m, "truncated", 9) == 0 || strstr(m, "edge of the buffered") != nullptr;
     };
     auto room = [&](size_t need) {
         if (o + need > cap)
@@ -894,6 +896,7 @@ class GzSource : public ByteSource
         uint64_t    buf_valid = 0; // compressed bytes in buf (without padding)
         bool        file_done = false;
         const uint64_t wave_bytes = chunk_bytes_ * wave_chunks_;
+        uint64_t       look_ahead = 0; // extra waves of compressed data kept buffered (grows if one deflate block needs it)
         for (;;)
         {
             // ---- keep two waves of compressed data buffered: the last chunk's decoder runs into the next wave ----
@@ -906,7 +909,7 @@ class GzSource : public ByteSource
                     file_off += drop;
                     start_bit -= drop * 8;
                 }
-                const uint64_t want = std::min<uint64_t>(2 * wave_bytes, size_ - file_off);
+                const uint64_t want = std::min<uint64_t>((2 + look_ahead) * wave_bytes, size_ - file_off);
                 buf.resize(want + 64);
                 if (want > buf_valid)
                 {
@@ -968,16 +971,19 @@ class GzSource : public ByteSource
                 const size_t first = std::upper_bound(cands.begin(), cands.end(), chunks[i].start_bit) - cands.begin();
                 decode_chunk(in, at_header && i == 0, cands.data() + first, cands.size() - first, wave_end_bit, last_data, chunks[i]);
             });
-            at_header = false;
             // ---- the chain of chunks that really follow one another ----
             std::vector<size_t> chain;
+            bool                need_more = false;
             {
                 size_t i = 0;
                 for (;;)
                 {
                     if (!chunks[i].ok)
                     {
-                        err = chunks[i].err.empty() ? "gzip decoding failed" : chunks[i].err;
+                        if (chunks[i].ran_out && !file_done)
+                            need_more = true; // a block reaches beyond the buffered data: buffer more and redo the wave
+                        else
+                            err = chunks[i].err.empty() ? "gzip decoding failed" : chunks[i].err;
                         break;
                     }
                     chain.push_back(i);
@@ -994,8 +1000,17 @@ class GzSource : public ByteSource
                     i = j;
                 }
             }
+            if (need_more)
+            {
+                look_ahead = look_ahead ? look_ahead * 2 : 2;
+                for (auto &c : chunks)
+                    if (c.sym.capacity())
+                        sym_pool_.emplace_back(std::move(c.sym));
+                continue;
+            }
             if (!err.empty())
                 break;
+            at_header = false;
             // ---- histories: window before chunk k = last 32 KiB of everything before it (sequential, 32 KiB each) ----
             std::vector<std::vector<uint8_t>> win(chain.size());
             for (size_t k = 0; k < chain.size(); ++k)

@@ -3243,6 +3243,16 @@ extern "C" int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const ch
     return GNB_OK;
 }
 
+namespace gnb
+{
+void session_ingest_mode(const gnb_session *s, int *sliced, int *rank, int *n_ranks)
+{
+    *sliced  = s->sharded() && s->sliced_ingest ? 1 : 0;
+    *rank    = s->comm ? s->comm->rank : 0;
+    *n_ranks = s->comm ? s->comm->n_ranks : 1;
+}
+} // namespace gnb
+
 extern "C" int gnb_host_register(void *ptr, uint64_t bytes)
 {
     if (!ptr || !bytes)

@@ -268,6 +268,29 @@ int64_t gnb_reads_file_read(gnb_reads_file *f, void *dst, uint64_t cap);
 int     gnb_reads_file_is_gzip(const gnb_reads_file *f);
 void    gnb_reads_file_close(gnb_reads_file *f);
 
+/* One read file (file2 NULL / "") or one pair of files, start to end: the reader / classify / writer loop of the reference
+ * (parse_reads GC.cpp:1220-1287 -> classify GC.cpp:630-832 -> write_classified / write_unclassified GC.cpp:1289-1322)
+ * with the block ring, the prefetch and the writer thread inside the library: file blocks (plain: parallel preads; gzip:
+ * parallel inflate, see gnb_reads_file_*) in page-locked buffers -> gnb_session_submit -> batches in flight ->
+ * gnb_session_collect -> text written to the given file descriptors (-1 = discard; every rank of a bin-sharded run holds
+ * the full result, so only one passes descriptors).  A parse error ends the file as in the reference (GC.cpp:1278-1283;
+ * parse_error is set, the call succeeds).  block_bytes 0 = 64 MiB, io_threads 0 = all (at most 16). */
+typedef struct
+{
+    uint32_t   n_levels; /* entries of all_fd / one_fd                                 */
+    const int *all_fd;   /* [n_levels] `.all` lines of every hierarchy level, or NULL  */
+    const int *one_fd;   /* [n_levels] `.one` lines, or NULL                           */
+    int        unc_fd;   /* `.unc` lines                                               */
+} gnb_output_fds;
+typedef struct
+{
+    uint64_t n_records, n_classified, n_blocks, bytes_read1, bytes_read2;
+    int      parse_error, is_gzip;
+    double   ms_open, ms_read_wait, ms_submit, ms_collect, ms_write; /* host pipeline: where the calling thread waited */
+} gnb_files_result;
+int gnb_session_classify_files(gnb_session *s, uint32_t prefix_id, const char *file1, const char *file2, const gnb_output_fds *out,
+                               uint64_t block_bytes, int io_threads, gnb_files_result *res);
+
 /* Page-lock / unlock a host buffer that will be passed as a read block (cudaHostRegister): faster, truly asynchronous
  * host->device copies. */
 int gnb_host_register(void *ptr, uint64_t bytes);

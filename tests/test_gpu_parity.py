@@ -754,11 +754,12 @@ def test_sharded_two_gpus_nccl(golden_dbs, tmp_path):
         fq2 = open(p2, "rb").read() if p2 else None
         dbs = [Database.open(p) for p in paths]
         want[name] = _run_case(lambda: Session(dbs, cutoff, rel_filter, fpr, hierarchy_labels=labels, output_all=True, output_unclassified=True), fq1, fq2)
-        assert want[name][0] == want[name][1] == want[name][2], name  # the three forms agree unsharded
-        assert want[name][0][0], name  # and the case classifies something
+        assert want[name][0][0], name  # the case classifies something
     mp.spawn(_two_gpu_worker, args=(2, port, cases, str(tmp_path)), nprocs=2, join=True)
     for rank in range(2):
         got = pickle.load(open(tmp_path / ("r%d.pkl" % rank), "rb"))
         for (name, sliced), forms in got.items():
             for form, res in zip(("classify", "staged", "pipelined"), forms):
                 assert res == want[name][0], (rank, name, sliced, form)
+    for name in want:
+        assert want[name][0] == want[name][1] == want[name][2], name  # the three forms agree unsharded as well

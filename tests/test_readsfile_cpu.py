@@ -1,0 +1,141 @@
+"""The library's read-file byte stream (gnb_reads_file_*, csrc/gzstream.cpp; reader side of GC.cpp:1220-1287): plain files
+by parallel preads, gzip files -- single-member, multi-member, BGZF-like, stored / fixed / dynamic blocks -- by the
+chunk-parallel inflater.  Whatever the chunk size and thread count, the consumer sees exactly the bytes zlib produces;
+damaged files give an error, never wrong bytes."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+from ganon_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def read_all(path, threads=0, cap=1 << 20):
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.gnb_reads_file_open(str(path).encode(), threads, C.byref(h))
+    assert rc == 0, L.gnb_last_error()
+    out = []
+    buf = C.create_string_buffer(cap)
+    try:
+        while True:
+            n = L.gnb_reads_file_read(h, buf, cap)
+            if n < 0:
+                return None, L.gnb_last_error().decode()
+            if n == 0:
+                break
+            out.append(buf.raw[:n])
+    finally:
+        L.gnb_reads_file_close(h)
+    return b"".join(out), None
+
+
+def read_all_with_chunk(path, threads, chunk):
+    """GANON_B200_GZ_CHUNK is read when a file is opened: run in this process with the variable set."""
+    old = os.environ.get("GANON_B200_GZ_CHUNK")
+    try:
+        if chunk:
+            os.environ["GANON_B200_GZ_CHUNK"] = str(chunk)
+        else:
+            os.environ.pop("GANON_B200_GZ_CHUNK", None)
+        return read_all(path, threads)
+    finally:
+        if old is None:
+            os.environ.pop("GANON_B200_GZ_CHUNK", None)
+        else:
+            os.environ["GANON_B200_GZ_CHUNK"] = old
+
+
+@pytest.fixture(scope="module")
+def fastq():
+    rng = np.random.default_rng(1)
+    g = synth.random_genomes(3, 32, 3000)
+    m1, _, _ = synth.reads_from_genomes(5, g, 40000)
+    fq = synth.fastq_block(m1)
+    rec = fq.size // 40000
+    fq = fq.reshape(40000, rec).copy()
+    fq[:, rec - 151 : rec - 1] = rng.choice(np.frombuffer(b"FFFFFFF:,#", dtype=np.uint8), size=(40000, 150))
+    return fq.tobytes()
+
+
+def test_plain_and_gzip_variants(tmp_path, fastq):
+    rng = np.random.default_rng(2)
+    cases = {}
+    (tmp_path / "plain.fq").write_bytes(fastq)
+    cases["plain.fq"] = fastq
+    for lvl in (1, 6, 9):
+        with gzip.open(tmp_path / ("l%d.fq.gz" % lvl), "wb", compresslevel=lvl) as f:
+            f.write(fastq)
+        cases["l%d.fq.gz" % lvl] = fastq
+    with open(tmp_path / "members.fq.gz", "wb") as f:  # concatenated members
+        for a in range(0, len(fastq), 1_700_000):
+            f.write(gzip.compress(fastq[a : a + 1_700_000], 6))
+    cases["members.fq.gz"] = fastq
+    with open(tmp_path / "bgzf_like.fq.gz", "wb") as f:  # <= 64 KiB members, as bgzip / bcl2fastq write
+        for a in range(0, len(fastq), 65280):
+            f.write(gzip.compress(fastq[a : a + 65280], 6))
+    cases["bgzf_like.fq.gz"] = fastq
+    # incompressible bytes (stored blocks), text, a run of zeros (long matches, distance 1), tiny tail (fixed block)
+    blob = rng.integers(0, 256, size=700_000, dtype=np.uint8).tobytes() + fastq[:900_000] + bytes(500_000) + b"tail"
+    with gzip.open(tmp_path / "mix.gz", "wb") as f:
+        f.write(blob)
+    cases["mix.gz"] = blob
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)  # fixed Huffman blocks only
+    (tmp_path / "fixed.gz").write_bytes(co.compress(fastq[:300_000]) + co.flush())
+    cases["fixed.gz"] = fastq[:300_000]
+    (tmp_path / "empty.gz").write_bytes(gzip.compress(b""))
+    cases["empty.gz"] = b""
+    (tmp_path / "small.gz").write_bytes(gzip.compress(b"@r\nACGT\n+\nIIII\n"))
+    cases["small.gz"] = b"@r\nACGT\n+\nIIII\n"
+    (tmp_path / "garbage_after.gz").write_bytes(gzip.compress(fastq[:100_000]) + b"\0" * 37)  # gzip ignores trailing padding
+    cases["garbage_after.gz"] = fastq[:100_000]
+    for name, want in cases.items():
+        for threads, chunk in ((1, None), (4, None), (4, 65536), (3, 20000), (2, 4096)):
+            got, err = read_all_with_chunk(tmp_path / name, threads, chunk)
+            assert err is None, (name, threads, chunk, err)
+            assert got == want, (name, threads, chunk, len(got), len(want))
+
+
+def test_damaged_gzip_files_are_errors(tmp_path, fastq):
+    z = gzip.compress(fastq[:2_000_000], 6)
+    rng = np.random.default_rng(3)
+    bad = 0
+    (tmp_path / "trunc.gz").write_bytes(z[: len(z) // 2])
+    got, err = read_all_with_chunk(tmp_path / "trunc.gz", 3, 65536)
+    assert got is None and err
+    (tmp_path / "crc.gz").write_bytes(z[:-8] + bytes([z[-8] ^ 1]) + z[-7:])
+    got, err = read_all_with_chunk(tmp_path / "crc.gz", 3, 65536)
+    assert got is None and "CRC" in err
+    for k in range(12):  # a flipped bit in the deflate data: an error, or (if the flip is harmless to the structure) a CRC failure
+        pos = int(rng.integers(64, len(z) - 16))
+        b = bytearray(z)
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        (tmp_path / "flip.gz").write_bytes(bytes(b))
+        got, err = read_all_with_chunk(tmp_path / "flip.gz", 3, 32768)
+        try:
+            want = zlib.decompress(bytes(b), 31)
+        except zlib.error:
+            want = None
+        if want is None:
+            assert got is None and err, k
+            bad += 1
+        else:
+            assert got == want, k
+    assert bad >= 8
+
+
+def test_bytes_match_gzip_command_on_a_real_gzip_file(tmp_path, fastq):
+    """A file written by the gzip program (not Python's zlib binding): header with file name, its block splitting."""
+    p = tmp_path / "reads.fq"
+    p.write_bytes(fastq)
+    subprocess.check_call(["gzip", "-6", "-k", str(p)])
+    for threads, chunk in ((1, None), (4, 100000), (4, 30000)):
+        got, err = read_all_with_chunk(str(p) + ".gz", threads, chunk)
+        assert err is None and got == fastq
