@@ -961,6 +961,8 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
     out = {"rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
            "reads_per_s": n_cli / cs if cs else None, "all_bytes": os.path.getsize(os.path.join(CACHE, "cli_out.all")) if os.path.exists(os.path.join(CACHE, "cli_out.all")) else None,
            "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
+    mh = re.search(r"host pipeline \(s\): ([^\n]*)", pr.stderr)
+    out["host_pipeline_s"] = mh.group(1) if mh else None
     # the same reads as ordinary single-member gzip files (what sequencers / archives deliver): the library inflates them
     # with all host threads (csrc/gzstream.cpp)
     try:
@@ -984,6 +986,8 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
         out["gz"] = {"rc": pr.returncode, "reads": n_gz, "gz_bytes": os.path.getsize(gz1) + (os.path.getsize(gz2) if gz2 else 0), "fastq_bytes": sum(b1.size + (b2.size if b2 is not None else 0) for b1, b2 in blocks),
                      "classify_s": cs, "wall_s": wall, "reads_per_s": n_gz / cs if cs else None, "compress_s": t_gz, "host_threads": reference_threads(),
                      "kind": "single-member gzip (one deflate stream per file, level 6)", "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
+        mh = re.search(r"host pipeline \(s\): ([^\n]*)", pr.stderr)
+        out["gz"]["host_pipeline_s"] = mh.group(1) if mh else None
         for p in (gz1, gz2):
             if p and os.path.exists(p):
                 os.remove(p)

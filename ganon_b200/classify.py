@@ -480,8 +480,9 @@ class GanonClassifyConfig:
     n_reads: int = 400
     verbose: bool = False
     quiet: bool = False
-    # not in the reference: which GPU to use
+    # not in the reference: which GPU to use, or several GPUs with every .ibf bin-sharded over them (one process per GPU)
     device: int = 0
+    devices: List[int] = field(default_factory=list)
     # not in the reference binary: the EM step of `ganon classify` (src/ganon/reassign.py) from the matches in HBM
     reassign_em: bool = False
     em_max_iter: int = 10
@@ -582,9 +583,66 @@ def _parse_reads_config(cfg: GanonClassifyConfig) -> Optional[Dict[str, List[Tup
 
 
 def run(cfg: GanonClassifyConfig) -> bool:
-    """GanonClassify::run (GC.cpp:1676-1691) -> ganon_classify<TFilter> (GC.cpp:1375-1674)."""
+    """GanonClassify::run (GC.cpp:1676-1691) -> ganon_classify<TFilter> (GC.cpp:1375-1674).  With several --devices the
+    databases are bin-sharded: this process is rank 0 (it writes every output file), one helper process per further GPU
+    runs the same loop on its column shards; the library exchanges the sparse matches between them (NCCL)."""
     if not cfg.validate():
         return False
+    if len(set(cfg.devices)) != len(cfg.devices):
+        print("--devices lists a device twice", file=sys.stderr)
+        return False
+    if len(cfg.devices) > 1:
+        if cfg.hibf:
+            print("--devices needs flat .ibf databases (an HIBF descends per read: use one GPU)", file=sys.stderr)
+            return False
+        return _run_sharded(cfg)
+    if cfg.devices:
+        cfg.device = cfg.devices[0]
+    return _run_rank(cfg, 0, 1, None)
+
+
+def _helper_rank(cfg: GanonClassifyConfig, rank: int, n_ranks: int, uid: bytes) -> None:
+    cfg.quiet = True
+    ok = _run_rank(cfg, rank, n_ranks, uid)
+    sys.exit(0 if ok else 1)
+
+
+def _run_sharded(cfg: GanonClassifyConfig) -> bool:
+    import multiprocessing as mp
+    import threading
+
+    n = len(cfg.devices)
+    uid = Comm.unique_id()
+    ctx = mp.get_context("spawn")
+    helpers = [ctx.Process(target=_helper_rank, args=(cfg, r, n, uid), daemon=True) for r in range(1, n)]
+    for h in helpers:
+        h.start()
+    stop = threading.Event()
+
+    def watchdog() -> None:  # a helper that dies leaves the other ranks waiting in a collective: end the run instead
+        while not stop.wait(0.5):
+            for r, h in enumerate(helpers, 1):
+                if h.exitcode not in (None, 0):
+                    print("ERROR: the process of device %d ended with exit code %d" % (cfg.devices[r], h.exitcode), file=sys.stderr)
+                    os._exit(1)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    try:
+        ok = _run_rank(cfg, 0, n, uid)
+    finally:
+        stop.set()
+    for h in helpers:
+        h.join(timeout=60 if ok else 1)
+        if h.is_alive():
+            h.terminate()
+            ok = False
+    return ok and all(h.exitcode == 0 for h in helpers)
+
+
+def _run_rank(cfg: GanonClassifyConfig, rank: int, n_ranks: int, uid: Optional[bytes]) -> bool:
+    """The run of one process on one GPU; rank 0 (the only rank of an unsharded run) owns the output files."""
+    writer = rank == 0
+    device = cfg.devices[rank] if n_ranks > 1 else cfg.device
     t_start = time.time()
     reads_config = _parse_reads_config(cfg)
     if reads_config is None:
@@ -599,7 +657,8 @@ def run(cfg: GanonClassifyConfig) -> bool:
     dbs: List[Database] = []
     try:
         for path in cfg.ibf:
-            dbs.append(Database.open(path, hibf=cfg.hibf, device=cfg.device))
+            dbs.append(Database.open(path, hibf=cfg.hibf, device=device, shard=rank, n_shards=n_ranks))
+        comm = Comm(uid, rank, n_ranks, device) if n_ranks > 1 else None
     except _lib.GnbError as e:
         print("ERROR: loading ibf or tax files (%s)" % e.msg, file=sys.stderr)
         return False
@@ -618,10 +677,12 @@ def run(cfg: GanonClassifyConfig) -> bool:
             output_all=cfg.output_all,
             output_unclassified=cfg.output_unclassified,
             output_single=cfg.output_single,
-            device=cfg.device,
+            device=device,
             host_threads=cfg.threads if cfg.threads > 1 else 0,
             n_reads=cfg.n_reads,
             quiet=cfg.quiet,
+            comm=comm,
+            sliced_ingest=comm is not None,
         )
     except _lib.GnbError as e:
         print(e.msg, file=sys.stderr)
@@ -636,16 +697,18 @@ def run(cfg: GanonClassifyConfig) -> bool:
             return False
         sess.keep_matches(True)
     prefixes = list(reads_config)
-    out_rep = {p: open(cfg.output_prefix + p + ".rep", "wb") for p in prefixes}
-    out_unc = {p: open(cfg.output_prefix + p + ".unc", "wb") for p in prefixes} if cfg.output_unclassified else {}
+    # every rank of a sharded run holds the complete result; only rank 0 writes it
+    open_out = (lambda path: open(path, "wb")) if writer else (lambda path: open(os.devnull, "wb"))
+    out_rep = {p: open_out(cfg.output_prefix + p + ".rep") for p in prefixes}
+    out_unc = {p: open_out(cfg.output_prefix + p + ".unc") for p in prefixes} if cfg.output_unclassified else {}
 
     def level_files(ext: str) -> Dict[str, List]:
         files: Dict[str, List] = {}
         for p in prefixes:
             if multi:
-                files[p] = [open(cfg.output_prefix + p + "." + lab + "." + ext, "wb") for lab in labels]
+                files[p] = [open_out(cfg.output_prefix + p + "." + lab + "." + ext) for lab in labels]
             else:
-                fh = open(cfg.output_prefix + p + "." + ext, "wb")
+                fh = open_out(cfg.output_prefix + p + "." + ext)
                 files[p] = [fh] * len(labels)
         return files
 
@@ -665,7 +728,7 @@ def run(cfg: GanonClassifyConfig) -> bool:
             one_fd = (C.c_int * n_lv)(*[out_one[prefix][li].fileno() if write_one else -1 for li in range(n_lv)])
             fds = _lib.OutputFds(n_lv, all_fd, one_fd, out_unc[prefix].fileno() if cfg.output_unclassified else -1)
             for file1, file2 in reads_config[prefix]:
-                fr = sess.classify_files(pid, file1, file2 or None, fds, BLOCK_BYTES, IO_THREADS)
+                fr = sess.classify_files(pid, file1, file2 or None, fds if writer else None, BLOCK_BYTES, IO_THREADS)
                 prof["open"] += fr.ms_open / 1e3
                 prof["read_wait"] += fr.ms_read_wait / 1e3
                 prof["submit"] += fr.ms_submit / 1e3
@@ -685,6 +748,9 @@ def run(cfg: GanonClassifyConfig) -> bool:
     t_class = time.time() - t_class
 
     for pid, prefix in enumerate(prefixes):
+        if not writer:
+            out_rep[prefix].close()
+            continue
         if cfg.reassign_em:
             # reassign.py: `.one` (one per hierarchy label unless there is a single `.all`) and the new `.rep`
             ones, new_rep, info = sess.reassign(pid, cfg.em_threshold[0], cfg.em_max_iter)
@@ -710,11 +776,13 @@ def run(cfg: GanonClassifyConfig) -> bool:
 
     if cfg.verbose and not cfg.quiet:
         print("host pipeline (s): open+pin %.3f, waiting for file blocks %.3f, staging (H2D + record index) %.3f, waiting for results %.3f, writer thread %.3f; %d blocks of <= %d MiB" % (prof["open"], prof["read_wait"], prof["submit"], prof["collect"], prof["write"], prof["blocks"], BLOCK_BYTES >> 20), file=sys.stderr)
-    if not cfg.quiet:
+    if not cfg.quiet and writer:
         _print_stats(cfg, sess, prefixes, labels, t_class, t_load, time.time() - t_start)
     sess.close()
     for d in dbs:
         d.close()
+    if comm is not None:
+        comm.close()
     return True
 
 

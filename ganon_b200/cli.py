@@ -33,6 +33,7 @@ _OPTS = {
     "verbose": (None, "bool", "verbose"),
     "quiet": (None, "bool", "quiet"),
     "device": (None, "int", "device"),  # extension: GPU ordinal
+    "devices": (None, "ints", "devices"),  # extension: several GPUs, the databases bin-sharded over them
     # extension: `ganon classify --multiple-matches em` without the round trip through the .all file (src/ganon/reassign.py)
     "reassign-em": (None, "bool", "reassign_em"),
     "em-max-iter": (None, "int", "em_max_iter"),
@@ -68,6 +69,8 @@ Usage:
       --n-batches arg         (accepted for compatibility)
       --n-reads arg           Number of reads for each batch. Default: 400
       --device arg            CUDA device ordinal. Default: 0
+      --devices arg           Several CUDA devices (comma-separated): every .ibf is split by bin columns over them
+                              (databases larger than one GPU's memory; one process per GPU, results identical)
       --reassign-em           EM reassignment of reads with several matches from the matches kept on the GPU
                               (what `ganon classify --multiple-matches em` does from the .all file): writes prefix.one
                               and the reassigned prefix.rep
@@ -120,6 +123,8 @@ def parse(argv: List[str]) -> Optional[GanonClassifyConfig]:
                 if name in seen:
                     vals = getattr(cfg, attr) + vals
                 setattr(cfg, attr, vals)
+            elif kind == "ints":
+                setattr(cfg, attr, [int(x) for x in inline.split(",")])
             elif kind == "int":
                 setattr(cfg, attr, int(inline))
             else:

@@ -686,8 +686,16 @@ def _run_case(make_session, fq1, fq2):
     _n, cap = s.in_flight()
     blocks = _cut_blocks(fq1, fq2, 5)
     alls, uncs, pending = [], [], 0
+    t1 = t2 = b""
+    keep = []  # submitted blocks stay alive until collected
     for i, (b1, b2) in enumerate(blocks):
-        s.submit(b1, b2, final=i == len(blocks) - 1)
+        # what a block did not consume goes in front of the next one (a FASTA record only ends where the next begins)
+        b1 = t1 + b1
+        b2 = t2 + b2 if b2 is not None else None
+        keep.append((b1, b2))
+        info = s.submit(b1, b2, final=i == len(blocks) - 1)
+        t1 = b1[info.consumed1 :]
+        t2 = b2[info.consumed2 :] if b2 is not None else b""
         pending += 1
         while pending >= cap or (i == len(blocks) - 1 and pending):
             r = s.collect()
@@ -763,3 +771,42 @@ def test_sharded_two_gpus_nccl(golden_dbs, tmp_path):
                 assert res == want[name][0], (rank, name, sliced, form)
     for name in want:
         assert want[name][0] == want[name][1] == want[name][2], name  # the three forms agree unsharded as well
+
+
+@pytest.mark.parametrize("name", ["se_synth_all", "hier_two_levels_single"])
+def test_command_line_devices_two_gpus(name, golden_dbs, tmp_path):
+    """`ganon-classify --devices 0,1`: one process per GPU on column shards of every .ibf (sliced reads of the plain and the
+    gzip-compressed input, exchange inside the library); rank 0 writes the reference's outputs, bit for bit as one GPU does."""
+    import gzip as gz
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    args = SU.expand(SU.load_scenarios()[name], golden_dbs)
+    if any(a.endswith("real4.ibf") or a.endswith("real4b.ibf") or "real4.ibf," in a or "real4b.ibf," in a for a in args):
+        # the one-word fixtures cannot be split into two column shards: use the 3-word fixture in their place
+        args = [a.replace(golden_dbs["real4b"], golden_dbs["synth"]).replace(golden_dbs["real4"], golden_dbs["synth"]) for a in args]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    one = str(tmp_path / "one")
+    assert cli.main(args + ["-o", one, "-t", "4", "--quiet"]) == 0
+    for tag, conv in (("two", lambda a: a), ("two_gz", None)):
+        a2 = list(args)
+        if conv is None:  # the same reads gzip-compressed
+            i = a2.index("-r")
+            files = []
+            for f in a2[i + 1].split(","):
+                g = str(tmp_path / (os.path.basename(f) + ".gz"))
+                with open(f, "rb") as fi, gz.open(g, "wb") as fo:
+                    fo.write(fi.read())
+                files.append(g)
+            a2[i + 1] = ",".join(files)
+        pre = str(tmp_path / tag)
+        done = subprocess.run([sys.executable, os.path.join(root, "bin", "ganon-classify")] + a2 + ["-o", pre, "-t", "4", "--quiet", "--devices", "0,1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert done.returncode == 0, done.stderr[-2000:]
+        want_files = sorted(os.path.basename(p)[len("one") :] for p in glob.glob(one + ".*"))
+        assert sorted(os.path.basename(p)[len(tag) :] for p in glob.glob(pre + ".*")) == want_files
+        for ext in want_files:
+            assert _read_sorted(pre + ext) == _read_sorted(one + ext), (tag, ext)
