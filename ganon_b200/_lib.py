@@ -42,6 +42,9 @@ class DbInfo(C.Structure):
         ("n_ibfs", C.c_uint64),
         ("device_bytes", C.c_uint64),
         ("device", C.c_int),
+        ("n_pages", C.c_uint64),
+        ("n_resident_pages", C.c_uint64),
+        ("host_bytes", C.c_uint64),
     ]
 
 
@@ -145,6 +148,8 @@ SYMBOLS = {
     "gnb_abi_version": (C.c_int, []),
     "gnb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "gnb_db_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "gnb_db_open_paged": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_P)]),
+    "gnb_db_page_out": (C.c_int, [_P, C.c_uint64]),
     "gnb_db_info": (C.c_int, [_P, C.POINTER(DbInfo)]),
     "gnb_db_target": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gnb_db_free": (None, [_P]),

@@ -43,10 +43,18 @@ class Database:
         self._h = C.c_void_p(handle)
 
     @classmethod
-    def open(cls, path: str, hibf: bool = False, device: int = 0, shard: int = 0, n_shards: int = 1) -> "Database":
+    def open(cls, path: str, hibf: bool = False, device: int = 0, shard: int = 0, n_shards: int = 1, hbm_budget: int = 0) -> "Database":
+        """hbm_budget (bytes): a flat filter larger than this is loaded paged (host-resident tier, gnb_db_open_paged)."""
         h = C.c_void_p()
-        check(_lib.lib().gnb_db_open(path.encode(), int(hibf), device, shard, n_shards, C.byref(h)))
+        if hbm_budget and not hibf and n_shards == 1:
+            check(_lib.lib().gnb_db_open_paged(path.encode(), device, hbm_budget, C.byref(h)))
+        else:
+            check(_lib.lib().gnb_db_open(path.encode(), int(hibf), device, shard, n_shards, C.byref(h)))
         return cls(h.value)
+
+    def page_out(self, hbm_budget: int) -> None:
+        """Keep at most hbm_budget bytes of this (whole-in-HBM) filter on the device, the rest in page-locked host memory."""
+        check(_lib.lib().gnb_db_page_out(self._h, hbm_budget))
 
     @classmethod
     def create(cls, bins: int, bin_size_bits: int, hash_functions: int, kmer_size: int, window_size: int, device: int = 0, shard: int = 0, n_shards: int = 1) -> "Database":

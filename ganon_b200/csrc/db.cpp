@@ -92,7 +92,13 @@ struct FileReader
 };
 
 // IBF body as serialised by IBF.hpp:561-571: six u64 + sdsl bit_vector (u8 width, f32 growth, u64 bits, words)
-int read_ibf_body(FileReader &f, IbfHost &ibf, int shard, int n_shards, cudaStream_t st, void *pinned[2], cudaEvent_t ev[2], size_t pinned_bytes)
+} // namespace
+bool plan_pages(const IbfHost &t, uint64_t budget, std::vector<IbfPage> &pages, size_t &n_resident);
+int  alloc_page_storage(IbfHost &t, size_t n_resident);
+namespace
+{
+int read_ibf_body(FileReader &f, IbfHost &ibf, int shard, int n_shards, cudaStream_t st, void *pinned[2], cudaEvent_t ev[2], size_t pinned_bytes,
+                  uint64_t hbm_budget = 0)
 {
     ibf.bins           = f.get<uint64_t>();
     ibf.technical_bins = f.get<uint64_t>();
@@ -118,13 +124,43 @@ int read_ibf_body(FileReader &f, IbfHost &ibf, int shard, int n_shards, cudaStre
         return fail(GNB_ERR_ARG, "more shards than bin-words");
     if (ibf.row_words() >= (1ull << 31))
         return fail(GNB_ERR_LIMIT, "row too wide");
-    GNB_CUDA(cudaMalloc((void **)&ibf.d_data, ibf.device_bytes()));
     const uint64_t row_bytes  = ibf.bin_words * 8;
     uint64_t       rows_per   = pinned_bytes / row_bytes;
     if (rows_per == 0)
         return fail(GNB_ERR_LIMIT, "row larger than the staging buffer");
     int      cur = 0;
     uint64_t row = 0;
+    if (hbm_budget && n_shards == 1 && ibf.device_bytes() > hbm_budget)
+    {
+        // host-resident tier: one pass over the file, every row cut into its column pages -- resident pages go to HBM,
+        // the others to page-locked host memory
+        size_t n_res = 0;
+        if (!plan_pages(ibf, hbm_budget, ibf.pages, n_res))
+            return fail(GNB_ERR_LIMIT, "the HBM budget does not hold three one-word pages of this filter");
+        GNB_TRY(alloc_page_storage(ibf, n_res));
+        while (row < ibf.bin_size)
+        {
+            const uint64_t rows = std::min(rows_per, ibf.bin_size - row);
+            GNB_CUDA(cudaEventSynchronize(ev[cur]));
+            if (!f.read(pinned[cur], rows * row_bytes))
+                return fail(GNB_ERR_IO, "short read in IBF payload");
+            for (auto &p : ibf.pages)
+            {
+                const uint64_t pw = p.w1 - p.w0;
+                const uint8_t *src = (const uint8_t *)pinned[cur] + p.w0 * 8;
+                if (p.d_data)
+                    GNB_CUDA(cudaMemcpy2DAsync(p.d_data + row * pw, pw * 8, src, row_bytes, pw * 8, rows, cudaMemcpyHostToDevice, st));
+                else
+                    for (uint64_t r = 0; r < rows; ++r)
+                        memcpy(p.h_data + (row + r) * pw, src + r * row_bytes, pw * 8);
+            }
+            GNB_CUDA(cudaEventRecord(ev[cur], st));
+            cur ^= 1;
+            row += rows;
+        }
+        return GNB_OK;
+    }
+    GNB_CUDA(cudaMalloc((void **)&ibf.d_data, ibf.device_bytes()));
     while (row < ibf.bin_size)
     {
         const uint64_t rows = std::min(rows_per, ibf.bin_size - row);
@@ -143,6 +179,88 @@ int read_ibf_body(FileReader &f, IbfHost &ibf, int shard, int n_shards, cudaStre
     return GNB_OK;
 }
 
+} // namespace
+
+bool plan_pages(const IbfHost &t, uint64_t budget, std::vector<IbfPage> &pages, size_t &n_resident)
+{
+    pages.clear();
+    n_resident           = 0;
+    const uint64_t words = t.row_words(), col_bytes = t.bin_size * 8; // bytes of one bin-word column
+    // a page takes at most 1/8 of the budget (two of them are staging buffers), whole 64-word chunks where the row allows
+    uint64_t pw = budget / 8 / col_bytes;
+    if (pw >= 64)
+        pw = pw / 64 * 64;
+    if (pw == 0)
+        pw = budget / 3 / col_bytes; // tiny budgets (tests): three pages must fit
+    if (pw == 0)
+        return false;
+    pw = std::min(pw, words);
+    for (uint64_t w = 0; w < words; w += pw)
+    {
+        IbfPage p;
+        p.w0 = t.w0 + w;
+        p.w1 = t.w0 + std::min(words, w + pw);
+        pages.push_back(p);
+    }
+    const uint64_t fit = budget / (pw * col_bytes);
+    n_resident         = fit > 2 ? (size_t)std::min<uint64_t>(fit - 2, pages.size()) : 0;
+    return true;
+}
+
+int alloc_page_storage(IbfHost &t, size_t n_resident)
+{
+    t.stage_bytes = 0;
+    for (size_t i = n_resident; i < t.pages.size(); ++i)
+        t.stage_bytes = std::max(t.stage_bytes, t.page_bytes(t.pages[i]));
+    for (size_t i = 0; i < t.pages.size(); ++i)
+    {
+        IbfPage &p = t.pages[i];
+        if (i < n_resident)
+            GNB_CUDA(cudaMalloc((void **)&p.d_data, t.page_bytes(p)));
+        else
+            GNB_CUDA(cudaMallocHost((void **)&p.h_data, t.page_bytes(p)));
+    }
+    if (t.stage_bytes)
+    {
+        GNB_CUDA(cudaStreamCreateWithFlags(&t.copy_st, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b)
+        {
+            GNB_CUDA(cudaMalloc((void **)&t.d_stage[b], t.stage_bytes));
+            GNB_CUDA(cudaEventCreateWithFlags(&t.ev_ready[b], cudaEventDisableTiming));
+            GNB_CUDA(cudaEventCreateWithFlags(&t.ev_free[b], cudaEventDisableTiming));
+        }
+    }
+    return GNB_OK;
+}
+
+void free_page_storage(IbfHost &t)
+{
+    for (auto &p : t.pages)
+    {
+        if (p.d_data)
+            cudaFree(p.d_data);
+        if (p.h_data)
+            cudaFreeHost(p.h_data);
+    }
+    t.pages.clear();
+    for (int b = 0; b < 2; ++b)
+    {
+        if (t.d_stage[b])
+            cudaFree(t.d_stage[b]);
+        if (t.ev_ready[b])
+            cudaEventDestroy(t.ev_ready[b]);
+        if (t.ev_free[b])
+            cudaEventDestroy(t.ev_free[b]);
+        t.d_stage[b]  = nullptr;
+        t.ev_ready[b] = t.ev_free[b] = nullptr;
+    }
+    if (t.copy_st)
+        cudaStreamDestroy(t.copy_st);
+    t.copy_st = nullptr;
+}
+
+namespace
+{
 void replace_all(std::string &s, const std::string &from, const std::string &to)
 {
     size_t p = 0;
@@ -210,7 +328,23 @@ extern "C" int gnb_device_count(int *n)
     return GNB_OK;
 }
 
+static int open_impl(const char *path, int is_hibf, int device, int shard, int n_shards, uint64_t hbm_budget, gnb_db **out);
+
 extern "C" int gnb_db_open(const char *path, int is_hibf, int device, int shard, int n_shards, gnb_db **out)
+{
+    // GANON_B200_HBM_BUDGET_GB: flat filters larger than this are loaded in the paged form (host-resident tier)
+    uint64_t budget = 0;
+    if (const char *e = getenv("GANON_B200_HBM_BUDGET_GB"))
+        budget = (uint64_t)(atof(e) * (double)(1ull << 30));
+    return open_impl(path, is_hibf, device, shard, n_shards, n_shards == 1 && !is_hibf ? budget : 0, out);
+}
+
+extern "C" int gnb_db_open_paged(const char *path, int device, uint64_t hbm_budget_bytes, gnb_db **out)
+{
+    return open_impl(path, 0, device, 0, 1, hbm_budget_bytes, out);
+}
+
+static int open_impl(const char *path, int is_hibf, int device, int shard, int n_shards, uint64_t hbm_budget, gnb_db **out)
 {
     if (!path || !out || n_shards < 1 || shard < 0 || shard >= n_shards)
         return fail(GNB_ERR_ARG, "gnb_db_open: bad arguments");
@@ -286,7 +420,7 @@ extern "C" int gnb_db_open(const char *path, int is_hibf, int device, int shard,
         if (rc == GNB_OK)
         {
             db->ibfs.resize(1);
-            rc = read_ibf_body(f, db->ibfs[0], shard, n_shards, st, pinned, ev, pinned_bytes);
+            rc = read_ibf_body(f, db->ibfs[0], shard, n_shards, st, pinned, ev, pinned_bytes, hbm_budget);
             if (rc == GNB_OK && (db->ibfs[0].bin_size != bin_size_bits || db->ibfs[0].hash_funs != hash_funs || db->ibfs[0].bins != n_bins))
                 rc = fail(GNB_ERR_FORMAT, "IBFConfig does not match the filter");
             for (auto const &bm : db->bin_map)
@@ -404,8 +538,11 @@ extern "C" void gnb_db_free(gnb_db *db)
         return;
     cudaSetDevice(db->device);
     for (auto &i : db->ibfs)
+    {
         if (i.d_data)
             cudaFree(i.d_data);
+        free_page_storage(i);
+    }
     delete db;
 }
 
@@ -432,6 +569,56 @@ extern "C" int gnb_db_info(const gnb_db *db, gnb_db_info_t *info)
     for (auto const &i : db->ibfs)
         info->device_bytes += i.device_bytes();
     info->device = db->device;
+    info->n_pages = info->n_resident_pages = 0;
+    info->host_bytes = 0;
+    for (auto const &i : db->ibfs)
+    {
+        info->n_pages += i.pages.size();
+        info->host_bytes += i.host_bytes();
+        for (auto const &p : i.pages)
+            info->n_resident_pages += p.d_data ? 1 : 0;
+    }
+    return GNB_OK;
+}
+
+// Host-resident tier: turn a filter that is whole in HBM into its paged form for `hbm_budget_bytes` (tests and the
+// benchmark build their synthetic databases in HBM first; files that never fit are loaded paged by gnb_db_open_paged).
+extern "C" int gnb_db_page_out(gnb_db *db, uint64_t hbm_budget_bytes)
+{
+    if (!db || db->is_hibf || db->ibfs.size() != 1)
+        return fail(GNB_ERR_ARG, "gnb_db_page_out: a flat IBF is needed");
+    IbfHost &t = db->ibfs[0];
+    if (t.paged() || !t.d_data)
+        return fail(GNB_ERR_ARG, "gnb_db_page_out: the filter is already paged");
+    GNB_CUDA(cudaSetDevice(db->device));
+    std::vector<IbfPage> pages;
+    size_t               n_res = 0;
+    if (t.bin_size * t.row_words() * 8 <= hbm_budget_bytes)
+        return GNB_OK; // fits: nothing to do
+    if (!plan_pages(t, hbm_budget_bytes, pages, n_res))
+        return fail(GNB_ERR_LIMIT, "gnb_db_page_out: the budget does not hold three one-word pages of this filter");
+    t.pages = pages;
+    int rc  = alloc_page_storage(t, n_res);
+    if (rc != GNB_OK)
+    {
+        free_page_storage(t);
+        return rc;
+    }
+    const uint64_t pitch = t.row_words() * 8;
+    for (auto &p : t.pages)
+    {
+        const uint64_t width = (p.w1 - p.w0) * 8;
+        const void    *src   = reinterpret_cast<const uint8_t *>(t.d_data) + (p.w0 - t.w0) * 8;
+        cudaError_t    e     = cudaMemcpy2D(p.d_data ? (void *)p.d_data : (void *)p.h_data, width, src, pitch, width, t.bin_size,
+                                            p.d_data ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess)
+        {
+            free_page_storage(t);
+            return fail(GNB_ERR_CUDA, std::string("gnb_db_page_out: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaFree(t.d_data);
+    t.d_data = nullptr;
     return GNB_OK;
 }
 
@@ -498,6 +685,8 @@ extern "C" int gnb_db_fill_random(gnb_db *db, uint64_t seed, int and_terms)
 {
     if (!db || and_terms < 0 || and_terms > 16)
         return fail(GNB_ERR_ARG, "gnb_db_fill_random: bad arguments");
+    if (db->ibfs[0].paged())
+        return fail(GNB_ERR_ARG, "not available on a paged filter (host-resident tier): the bitvector is not whole in HBM");
     GNB_CUDA(cudaSetDevice(db->device));
     for (size_t i = 0; i < db->ibfs.size(); ++i)
     { // sub-IBF i of an HIBF draws from seed + i
@@ -520,6 +709,8 @@ extern "C" int gnb_db_emplace_ibf(gnb_db *db, uint64_t ibf_index, const uint64_t
 {
     if (!db || ibf_index >= db->ibfs.size() || (n && (!hashes || !bins)))
         return fail(GNB_ERR_ARG, "gnb_db_emplace: bad arguments");
+    if (db->ibfs[0].paged())
+        return fail(GNB_ERR_ARG, "not available on a paged filter (host-resident tier): the bitvector is not whole in HBM");
     if (n == 0)
         return GNB_OK;
     GNB_CUDA(cudaSetDevice(db->device));
@@ -565,6 +756,8 @@ extern "C" int gnb_db_read_words(const gnb_db *db, uint64_t ibf_index, uint64_t 
 {
     if (!db || ibf_index >= db->ibfs.size() || !out)
         return fail(GNB_ERR_ARG, "gnb_db_read_words: bad arguments");
+    if (db->ibfs[0].paged())
+        return fail(GNB_ERR_ARG, "not available on a paged filter (host-resident tier): the bitvector is not whole in HBM");
     const IbfHost &t = db->ibfs[ibf_index];
     if (word_offset + n_words > t.bin_size * t.row_words())
         return fail(GNB_ERR_ARG, "gnb_db_read_words: range out of bounds");
@@ -727,6 +920,8 @@ extern "C" int gnb_db_save(const gnb_db *db, const char *path)
     const IbfHost &t = db->ibfs[0];
     if (t.w0 != 0 || t.w1 != t.bin_words)
         return fail(GNB_ERR_ARG, "gnb_db_save: sharded handle");
+    if (db->ibfs[0].paged())
+        return fail(GNB_ERR_ARG, "not available on a paged filter (host-resident tier): the bitvector is not whole in HBM");
     FILE *fp = fopen(path, "wb");
     if (!fp)
         return fail(GNB_ERR_IO, std::string("cannot write ") + path);

@@ -245,6 +245,13 @@ struct FilterRt
     std::vector<double>   node_fpr;   // [n_level_targets] fpr of this filter's target for the node (0 if absent)
     std::vector<uint8_t>  node_fpr_class; // [n_level_targets] index into LevelRt::fpr_classes, 255 = none
     std::vector<uint8_t>  node_multi; // [n_level_targets] 1: node's bins form several segments (partial tuples)
+    // host-resident tier: one device view + tables per column page of a paged filter (`dev` then describes page 0)
+    struct PageRt
+    {
+        IbfDev dev{};
+        DevBuf d_single, d_bin_node, d_seg_off, d_segs;
+    };
+    std::vector<PageRt> pages;
     // HIBF: one IbfDev per sub-IBF (tables carved out of the shared device arrays above)
     bool                  is_hibf = false;
     std::vector<IbfDev>   ibf_table;
@@ -421,6 +428,8 @@ struct gnb_session
     int  device_rep(size_t li, uint32_t prefix_id, unsigned long long **out);
     int  drain_device_rep();
     int  build_level_tables(LevelRt &L);
+    int  build_shard_tables(LevelRt &L, FilterRt &F, uint64_t w0, uint64_t w1, const uint64_t *data, IbfDev &d, DevBuf &d_single, DevBuf &d_bin_node,
+                            DevBuf &d_seg_off, DevBuf &d_segs);
     int  build_hibf_tables(LevelRt &L, FilterRt &F);
     void ensure_prefix(uint32_t prefix_id);
     int  acquire_slot();
@@ -580,6 +589,7 @@ struct BatchCtx
     int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines);
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
+    int  run_paged_count(FilterRt &F, const uint8_t *act, uint32_t n, uint64_t cap);
     int  finish_level(size_t li);
     int  finish_level_device(size_t li, unsigned long long *rep, bool fetch, bool &done);
     int  to_host_state(size_t li);
@@ -602,6 +612,9 @@ gnb_session::~gnb_session()
             f.d_seg_off.release();
             f.d_segs.release();
             f.d_ibf_table.release();
+            for (auto &pg : f.pages)
+                for (DevBuf *b : {&pg.d_single, &pg.d_bin_node, &pg.d_seg_off, &pg.d_segs})
+                    b->release();
         }
     for (auto &l : levels)
     {
@@ -978,18 +991,40 @@ int gnb_session::build_level_tables(LevelRt &L)
         }
         const gnb_db  &db  = *F.db;
         const IbfHost &ibf = db.ibfs[0];
-        IbfDev        &d   = F.dev;
-        d.data       = ibf.d_data;
+        F.node_fpr.assign(L.n_targets, 0.0);
+        F.node_multi.assign(L.n_targets, 0);
+        if (!ibf.paged())
+        {
+            GNB_TRY(build_shard_tables(L, F, ibf.w0, ibf.w1, ibf.d_data, F.dev, F.d_single, F.d_bin_node, F.d_seg_off, F.d_segs));
+            continue;
+        }
+        F.pages.resize(ibf.pages.size());
+        for (size_t p = 0; p < ibf.pages.size(); ++p)
+        {
+            FilterRt::PageRt &P = F.pages[p];
+            GNB_TRY(build_shard_tables(L, F, ibf.pages[p].w0, ibf.pages[p].w1, ibf.pages[p].d_data, P.dev, P.d_single, P.d_bin_node, P.d_seg_off, P.d_segs));
+        }
+        F.dev = F.pages[0].dev;
+    }
+    return GNB_OK;
+}
+
+// device view + bin -> node tables of the bin-word columns [w0, w1) of one flat filter (a whole filter, a shard, or a page)
+int gnb_session::build_shard_tables(LevelRt &L, FilterRt &F, uint64_t w0, uint64_t w1, const uint64_t *data, IbfDev &d, DevBuf &d_single, DevBuf &d_bin_node,
+                                    DevBuf &d_seg_off, DevBuf &d_segs)
+{
+    {
+        const gnb_db  &db  = *F.db;
+        const IbfHost &ibf = db.ibfs[0];
+        d.data       = data;
         d.bin_size   = ibf.bin_size;
         d.hash_shift = (uint32_t)ibf.hash_shift;
         d.hash_funs  = (uint32_t)ibf.hash_funs;
-        d.row_words  = (uint32_t)ibf.row_words();
+        d.row_words  = (uint32_t)(w1 - w0);
         d.n_chunks   = (d.row_words + 63) / 64;
-        const uint64_t bin_lo = ibf.w0 * 64, bin_hi = ibf.w1 * 64;
+        const uint64_t bin_lo = w0 * 64, bin_hi = w1 * 64;
         std::vector<uint32_t> single((size_t)d.n_chunks * 128, 0), bin_node((size_t)d.n_chunks * 4096, 0);
         std::vector<std::vector<Seg>> per_slot((size_t)d.n_chunks * 32);
-        F.node_fpr.assign(L.n_targets, 0.0);
-        F.node_multi.assign(L.n_targets, 0);
         std::unordered_map<std::string, uint32_t> node_of;
         for (uint32_t i = 0; i < L.n_targets; ++i)
             node_of.emplace(L.node_names[i], i);
@@ -1035,12 +1070,12 @@ int gnb_session::build_level_tables(LevelRt &L)
                 any_seg = true;
             }
         }
-        GNB_TRY(F.d_single.ensure(single.size() * 4));
-        GNB_CUDA(cudaMemcpy(F.d_single.p, single.data(), single.size() * 4, cudaMemcpyHostToDevice));
-        GNB_TRY(F.d_bin_node.ensure(bin_node.size() * 4));
-        GNB_CUDA(cudaMemcpy(F.d_bin_node.p, bin_node.data(), bin_node.size() * 4, cudaMemcpyHostToDevice));
-        d.single_mask = F.d_single.as<uint32_t>();
-        d.bin_node    = F.d_bin_node.as<uint32_t>();
+        GNB_TRY(d_single.ensure(single.size() * 4));
+        GNB_CUDA(cudaMemcpy(d_single.p, single.data(), single.size() * 4, cudaMemcpyHostToDevice));
+        GNB_TRY(d_bin_node.ensure(bin_node.size() * 4));
+        GNB_CUDA(cudaMemcpy(d_bin_node.p, bin_node.data(), bin_node.size() * 4, cudaMemcpyHostToDevice));
+        d.single_mask = d_single.as<uint32_t>();
+        d.bin_node    = d_bin_node.as<uint32_t>();
         d.seg_off     = nullptr;
         d.segs        = nullptr;
         if (any_seg)
@@ -1053,12 +1088,12 @@ int gnb_session::build_level_tables(LevelRt &L)
                 segs.insert(segs.end(), per_slot[i].begin(), per_slot[i].end());
             }
             off[per_slot.size()] = (uint32_t)segs.size();
-            GNB_TRY(F.d_seg_off.ensure(off.size() * 4));
-            GNB_CUDA(cudaMemcpy(F.d_seg_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-            GNB_TRY(F.d_segs.ensure(segs.size() * sizeof(Seg)));
-            GNB_CUDA(cudaMemcpy(F.d_segs.p, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
-            d.seg_off = F.d_seg_off.as<uint32_t>();
-            d.segs    = F.d_segs.as<Seg>();
+            GNB_TRY(d_seg_off.ensure(off.size() * 4));
+            GNB_CUDA(cudaMemcpy(d_seg_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+            GNB_TRY(d_segs.ensure(segs.size() * sizeof(Seg)));
+            GNB_CUDA(cudaMemcpy(d_segs.p, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+            d.seg_off = d_seg_off.as<uint32_t>();
+            d.segs    = d_segs.as<Seg>();
         }
     }
     return GNB_OK;
@@ -1294,6 +1329,8 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
                     continue;
                 }
                 const gnb::IbfHost &I = F.db->ibfs[0];
+                if (I.paged() && N > 1)
+                    return fail(GNB_ERR_CONFIG, "a paged filter (host-resident tier) cannot be part of a bin-sharded run: shard it over more GPUs instead");
                 if (I.w0 != r * I.bin_words / N || I.w1 != (r + 1) * I.bin_words / N)
                     return fail(GNB_ERR_ARG, "gnb_session_create: a database is not shard `rank` of `n_ranks` (open it with gnb_db_open(..., shard = rank, n_shards = n_ranks))");
             }
@@ -1869,6 +1906,53 @@ void BatchCtx::signal_done()
     S->chain_cv.notify_all();
 }
 
+// Host-resident tier: K3 over every column page of a paged filter; the tuples of all pages accumulate behind one cursor
+// (a target whose bins straddle a page border yields partial sums, added by K4 like those of a shard border).  Resident
+// pages are counted first; meanwhile the first two streamed pages travel host -> HBM on the filter's copy stream, and
+// every further copy waits for the K3 launch that last read its staging buffer.
+int BatchCtx::run_paged_count(FilterRt &F, const uint8_t *act, uint32_t n, uint64_t cap)
+{
+    IbfHost                    &I = F.db->ibfs[0];
+    std::lock_guard<std::mutex> lock(F.db->page_mu);
+    std::vector<size_t>         streamed;
+    for (size_t p = 0; p < I.pages.size(); ++p)
+        if (!I.pages[p].d_data)
+            streamed.push_back(p);
+    auto issue_copy = [&](size_t k) -> int {
+        const int      b  = (int)(k & 1);
+        const IbfPage &pg = I.pages[streamed[k]];
+        GNB_CUDA(cudaStreamWaitEvent(I.copy_st, I.ev_free[b], 0));
+        GNB_CUDA(cudaMemcpyAsync(I.d_stage[b], pg.h_data, I.page_bytes(pg), cudaMemcpyHostToDevice, I.copy_st));
+        GNB_CUDA(cudaEventRecord(I.ev_ready[b], I.copy_st));
+        timing.h2d_bytes += I.page_bytes(pg);
+        return GNB_OK;
+    };
+    for (size_t k = 0; k < std::min<size_t>(2, streamed.size()); ++k)
+        GNB_TRY(issue_copy(k));
+    const uint32_t mh = std::min<uint32_t>(max_hashes_ub, 65535u);
+    for (size_t p = 0; p < I.pages.size(); ++p)
+        if (I.pages[p].d_data)
+        {
+            launch_ibf_count(F.pages[p].dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), act, n, mh, F.rel_cutoff,
+                             d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
+            launches += 1;
+        }
+    for (size_t k = 0; k < streamed.size(); ++k)
+    {
+        const int b = (int)(k & 1);
+        GNB_CUDA(cudaStreamWaitEvent(st, I.ev_ready[b], 0));
+        IbfDev d = F.pages[streamed[k]].dev;
+        d.data   = I.d_stage[b];
+        launch_ibf_count(d, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), act, n, mh, F.rel_cutoff, d_tuples_a.as<uint64_t>(),
+                         d_cursor.as<unsigned long long>(), cap, st);
+        launches += 1;
+        GNB_CUDA(cudaEventRecord(I.ev_free[b], st));
+        if (k + 2 < streamed.size())
+            GNB_TRY(issue_copy(k + 2));
+    }
+    return GNB_OK;
+}
+
 // K3 (+ sort) for every filter of level li on the reads still active
 int BatchCtx::run_level(size_t li)
 {
@@ -1930,10 +2014,15 @@ int BatchCtx::run_level(size_t li)
         {
             GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
             GNB_CUDA(cudaEventRecord(ev[4], st));
-            launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
-                             d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
+            if (F.pages.empty())
+            {
+                launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
+                                 d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
+                launches += 1;
+            }
+            else
+                GNB_TRY(run_paged_count(F, act, n, cap));
             GNB_CUDA(cudaEventRecord(ev[5], st));
-            launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             timing.d2h_bytes += 8;
             GNB_CUDA(stream_wait(st));
@@ -1950,7 +2039,7 @@ int BatchCtx::run_level(size_t li)
             cap = d_tuples_a.cap / 8;
         }
         if (!F.is_hibf)
-            timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.dev.row_words * 8;
+            timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.db->ibfs[0].row_words() * 8;
         if (S->sharded())
             GNB_TRY(exchange_tuples(produced)); // d_tuples_a now holds the lists of all ranks
         if (produced == 0)
@@ -3705,6 +3794,8 @@ extern "C" int gnb_db_bulk_count(const gnb_db *db, uint64_t ibf_index, const uin
 {
     if (!db || ibf_index >= db->ibfs.size() || !hash_off || !counts || n_reads >= kMaxReadsPerBatch)
         return fail(GNB_ERR_ARG, "gnb_db_bulk_count: bad arguments");
+    if (db->ibfs[ibf_index].paged())
+        return fail(GNB_ERR_ARG, "gnb_db_bulk_count: not available on a paged filter");
     GNB_CUDA(cudaSetDevice(db->device));
     const IbfHost &ibf = db->ibfs[ibf_index];
     IbfDev         d{};

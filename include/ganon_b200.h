@@ -72,9 +72,19 @@ typedef struct
     uint64_t n_ibfs;         /* 1 for a flat IBF                                                 */
     uint64_t device_bytes;   /* HBM held by the bitvector(s)                                     */
     int      device;
+    uint64_t n_pages, n_resident_pages; /* host-resident tier: column pages / those kept in HBM (0 = not paged) */
+    uint64_t host_bytes;     /* page-locked host memory held by streamed pages                   */
 } gnb_db_info_t;
 
 int  gnb_db_open(const char *path, int is_hibf, int device, int shard, int n_shards, gnb_db **out);
+/* Host-resident tier (databases larger than the HBM they may use; the reference keeps every filter whole in host RAM,
+ * GC.cpp:949-965, real ones reach 501 GB, docs/default_databases.md:75): a flat filter above `hbm_budget_bytes` is cut
+ * into column pages (bin-word ranges of every row).  As many pages as fit stay in HBM, the others live in page-locked host
+ * memory and pass through two staging buffers while K3 counts the page before them -- the same K3, the same tuples, the
+ * same results, at PCIe speed for the streamed part.  gnb_db_open applies $GANON_B200_HBM_BUDGET_GB when set;
+ * gnb_db_page_out converts a filter that is whole in HBM (benchmark / tests).  A paged filter serves sessions on one GPU. */
+int  gnb_db_open_paged(const char *path, int device, uint64_t hbm_budget_bytes, gnb_db **out);
+int  gnb_db_page_out(gnb_db *db, uint64_t hbm_budget_bytes);
 int  gnb_db_info(const gnb_db *db, gnb_db_info_t *info);
 /* target i: name, per-target false-positive rate (GC.cpp:969-982 / 932) and number of technical bins */
 int  gnb_db_target(const gnb_db *db, uint64_t i, const char **name, double *fpr, uint64_t *n_bins);

@@ -810,3 +810,66 @@ def test_command_line_devices_two_gpus(name, golden_dbs, tmp_path):
         assert sorted(os.path.basename(p)[len(tag) :] for p in glob.glob(pre + ".*")) == want_files
         for ext in want_files:
             assert _read_sorted(pre + ext) == _read_sorted(one + ext), (tag, ext)
+
+
+def test_paged_filter_host_resident_tier_equals_the_whole(golden_dbs, tmp_path, monkeypatch):
+    """a filter above its HBM budget is cut into column pages, some resident, the others streamed from
+    page-locked host memory through two staging buffers; every form of the call gives the unpaged result bit for bit
+    (targets of 1-3 bins straddle the page borders of the 3-word fixture)."""
+    fq1 = open(os.path.join(SU.GOLDEN, "reads.1.fq"), "rb").read()
+    fq2 = open(os.path.join(SU.GOLDEN, "reads.2.fq"), "rb").read()
+    path = golden_dbs["synth"]
+    whole = Database.open(path)
+    wi = whole.info()
+    assert wi.n_pages == 0
+    col = wi.bin_size_bits * 8  # bytes of one bin-word column
+    mk = lambda db: (lambda: Session([db], [0.1], [0.5], [1e-3], output_all=True, output_unclassified=True))
+    want = _run_case(mk(whole), fq1, fq2)
+    assert want[0] == want[1] == want[2] and want[0][0]
+    for budget, n_res in ((3 * col + 100, 1), (2 * col + 100, 0)):
+        paged = Database.open(path, hbm_budget=budget)
+        pi = paged.info()
+        assert (pi.n_pages, pi.n_resident_pages) == (3, n_res) and pi.host_bytes == (3 - n_res) * col and pi.device_bytes == (n_res + 2) * col
+        got = _run_case(mk(paged), fq1, fq2)
+        assert got == want, budget
+        with pytest.raises(_lib.GnbError):
+            paged.read_words(0, 8)
+        paged.close()
+    # a filter made in HBM, then paged out: 128 words per row in 11 pages of 12 words (6 resident, 5 streamed), a 12-bin
+    # target across the border of two pages and a background target spread over all of them
+    rng = np.random.default_rng(9)
+    k, w = 19, 31
+    db = Database.create(8192, 4099, 3, k, w)
+    db.fill_random(4, 2)
+    genomes = [bytes(rng.choice(list(b"ACGT"), size=2000).astype(np.uint8)) for _ in range(64)]
+    first = [int(x) for x in rng.choice(8100, size=64, replace=False)]
+    first[0] = 3835  # bins 3835..3846 straddle word 59 | 60, the border of pages 4 and 5
+    bin_target = np.full(8192, 64, dtype=np.uint32)  # the rest: one background target
+    names = ["g%d" % i for i in range(64)] + ["bg"]
+    hs, bs, counts = [], [], []
+    for t, g in enumerate(genomes):
+        nb = 12 if t == 0 else 1
+        bin_target[first[t] : first[t] + nb] = t
+        u = np.unique(O.minimiser_hash(g, k, w))
+        hs.append(u)
+        bs.append((first[t] + np.arange(u.size) % nb).astype(np.uint32))
+        counts.append(u.size)
+    db.emplace(np.concatenate(hs), np.concatenate(bs))
+    db.set_targets(names, bin_target, counts + [1000], 500)
+    reads = b"".join(b"@q%d\n%s\n+\n%s\n" % (i, genomes[i % 64][100 + i : 250 + i], b"I" * 150) for i in range(640))
+    mk2 = lambda: Session([db], [0.2], [0.5], [1.0], output_all=True, output_unclassified=True)
+    want2 = _run_case(mk2, reads, None)
+    assert want2[0][0]
+    db.page_out(100 * 4099 * 8)  # room for 100 of the 128 columns: pages of 100 / 8 = 12 words, 8 fit, 2 of them staging
+    di = db.info()
+    assert (di.n_pages, di.n_resident_pages) == (11, 6)
+    assert _run_case(mk2, reads, None) == want2
+    # the command line takes the budget from the environment
+    monkeypatch.setenv("GANON_B200_HBM_BUDGET_GB", "%.9f" % ((2 * col + 100) / (1 << 30)))
+    pre = str(tmp_path / "paged")
+    assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", path, "-c", "0.1", "-d", "0.5", "-o", pre, "-a", "-u", "--quiet"]) == 0
+    monkeypatch.delenv("GANON_B200_HBM_BUDGET_GB")
+    pre2 = str(tmp_path / "whole")
+    assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", path, "-c", "0.1", "-d", "0.5", "-o", pre2, "-a", "-u", "--quiet"]) == 0
+    for ext in (".all", ".unc", ".rep"):
+        assert _read_sorted(pre + ext) == _read_sorted(pre2 + ext)
