@@ -378,6 +378,7 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct read batches cycled through the steps")
     ap.add_argument("--cli", action="store_true", help="also time the drop-in command line (bin/ganon-classify) on a FASTQ file of the pool's batches and the saved database (always on for the c2 sub-record of the default run)")
     ap.add_argument("--em", action="store_true", help="also time the EM reassignment (SURVEY 8f.1) on the matches of the e2e batches kept in HBM, next to the CPU restatement of src/ganon/reassign.py on the same .all text")
+    ap.add_argument("--paged", action="store_true", help="also measure the host-resident tier: the workload's filter with half of it allowed in HBM (always on for the default c3 line)")
     ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (the default for N > 1)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: replicated database, reads sharded (weak scaling) as the headline instead of the bin-sharded arm")
     args = ap.parse_args()
@@ -420,7 +421,7 @@ def main():
             if rank == 0:
                 line.setdefault("extra", {})["replicas_c2"] = sub
     else:
-        line = measure(args, wl_name, ctx, cpu=not args.no_cpu_baseline, cli=args.cli, em=args.em)
+        line = measure(args, wl_name, ctx, cpu=not args.no_cpu_baseline, cli=args.cli, em=args.em, paged=args.paged or (not explicit and world == 1))
         for e in extras:
             try:
                 sub = measure(args, e, ctx, cpu=not args.no_cpu_baseline, cli=(e == "c2"), em=False)
@@ -436,7 +437,7 @@ def main():
     return 0
 
 
-def measure(args, wl_name, ctx, cpu, cli, em):
+def measure(args, wl_name, ctx, cpu, cli, em, paged=False):
     """One workload on every rank's own GPU: database replicated, reads sharded over the ranks (no data-path collective).
     Returns the bench line (rank 0; None elsewhere)."""
     import torch
@@ -589,6 +590,18 @@ def measure(args, wl_name, ctx, cpu, cli, em):
         except Exception as e:
             cli_line = {"error": str(e)[:300]}
 
+    # ------------------------------------------------------------------ host-resident tier: the same filter with half
+    # of it allowed in HBM, the rest streamed from page-locked host memory per batch
+    paged_line = None
+    if paged and rank == 0 and world == 1 and not wl.get("hibf"):
+        try:
+            for s in sessions:
+                s.close()
+            sessions = []
+            paged_line = paged_leg(wl, db, host, dev, Session, result_text)
+        except Exception as e:
+            paged_line = {"error": str(e)[:300]}
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -647,6 +660,8 @@ def measure(args, wl_name, ctx, cpu, cli, em):
             line["em_reassign"] = em_line
         if cli_line is not None:
             line["cli"] = cli_line
+        if paged_line is not None:
+            line["host_resident_tier"] = paged_line
     for s in sessions:
         s.close()
     db.close()
@@ -931,6 +946,45 @@ def parity_against_oracle_sample(wl, dev, genomes, block, sharded_all_text, n_sa
     mine = sorted(ln for ln in sharded_all_text.decode().splitlines() if ln.split("\t", 1)[0].encode() in ids)
     return {"reads": n_sample * (2 if b2 is not None else 1), "all_lines": len(want), "identical": mine == want, "rows_materialised": int(need.size),
             "against": "oracle (CPU restatement, pinned to the reference) on the first %d records of batch 0; filter rows regenerated on the CPU" % n_sample}
+
+
+def paged_leg(wl, db, host, dev, Session, result_text):
+    """The workload's filter with an HBM budget of half its size: column pages, part resident, part streamed per batch."""
+    import torch
+
+    units = 2 if wl["paired"] else 1
+    mk = lambda: Session([db], [REL_CUTOFF], [REL_FILTER], [FPR_QUERY], output_all=True, device=dev)
+    s = mk()
+    want = result_text(s.classify(host[0][0], host[0][1], final=True), "all")
+    s.close()
+    full = int(db.info().device_bytes)
+    budget = full // 2
+    t0 = time.perf_counter()
+    db.page_out(budget)
+    t_out = time.perf_counter() - t0
+    info = db.info()
+    s = mk()
+    got = result_text(s.classify(host[0][0], host[0][1], final=True), "all")
+    # large batches amortise the stream: all pool blocks as one block per step
+    big1 = pinned(np.concatenate([h1.numpy() for h1, _h2 in host]))
+    big2 = pinned(np.concatenate([h2.numpy() for _h1, h2 in host])) if host[0][1] is not None else None
+    n_big = len(host) * wl["reads_per_step"] * units
+    r = s.classify(big1, big2, final=True)
+    torch.cuda.synchronize()
+    steps = 3
+    t0 = time.perf_counter()
+    streamed = 0
+    for _ in range(steps):
+        r = s.classify(big1, big2, final=True)
+        streamed += r.h2d_bytes
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    s.close()
+    return {"filter_bytes": full, "hbm_budget_bytes": budget, "pages": int(info.n_pages), "resident_pages": int(info.n_resident_pages), "hbm_bytes": int(info.device_bytes), "host_bytes": int(info.host_bytes),
+            "resident_fraction": 1.0 - info.host_bytes / full, "page_out_s": t_out, "reads_per_step": n_big, "steps": steps, "ms_per_step": dt / steps * 1e3, "value": steps * n_big / dt, "unit": "reads/s",
+            "h2d_bytes_per_step": streamed // steps, "h2d_GBps": streamed / dt / 1e9, "ms_count_last": r.ms_count,
+            "bound": "PCIe: every batch streams the non-resident pages once; K3 of the resident pages and of the page before overlaps the copies",
+            "parity": {"reads": wl["reads_per_step"] * units, "identical": got == want, "against": "the same session on the filter whole in HBM (byte comparison of the .all text)"}}
 
 
 def cli_leg(wl_name, wl, db, blocks, pool, R, dev):

@@ -170,8 +170,8 @@ struct FinishParams
     uint32_t *match_target, *match_count;
     char     *all_text, *one_text, *unc_text;
     // level
-    const double   *node_fpr;
-    const uint32_t *node_class;   // index of the node's fpr among the level's distinct fpr values
+    const double   *node_fpr;     // [n_filters][n_nodes]: fpr of the filter's target for the node
+    const uint32_t *node_class;   // [n_filters][n_nodes]: index of that fpr among the level's distinct fpr values
     unsigned long long *fpr_memo; // direct-mapped cache of --fpr-query values: [slot] = (key, bits of q)
     uint32_t        fpr_memo_mask;
     const int32_t  *parent;
@@ -179,7 +179,9 @@ struct FinishParams
     const char     *names;
     unsigned long long *rep; // [n_nodes][5]: matches, seqs_lca, seqs_unique, discarded_matches_filter, discarded_matches_fprquery
     int32_t  root;
-    double   rel_cutoff, rel_filter, fpr_query, fpr_band;
+    double   rel_cutoffs[16];     // per filter of the level (--ibf order)
+    uint32_t filter_bits, n_nodes; // low bits of a tuple's node field that hold the filter index; nodes of the level
+    double   rel_filter, fpr_query, fpr_band;
     uint32_t w, level;
     uint8_t  is_hibf, skip_lca, output_lca, output_all, output_unc, first, last;
 };

@@ -1588,6 +1588,7 @@ __device__ double dev_fpr_query_q(uint32_t n_hashes, uint32_t count, double fpr)
 // one aligned 16-byte word written and read with single 128-bit accesses.
 __device__ __forceinline__ double dev_fpr_query_cached(const FinishParams &p, uint32_t node, uint32_t n_hashes, uint32_t count)
 {
+    // node: index into the level's [filter][node] tables (filter * n_nodes + node for levels with several filters)
     const unsigned long long key  = ((unsigned long long)p.node_class[node] << 32) | ((unsigned long long)(n_hashes & 0xFFFF) << 16) | (count & 0xFFFF);
     ulonglong2              *slot = reinterpret_cast<ulonglong2 *>(p.fpr_memo) + (splitmix64(key) & p.fpr_memo_mask);
     const ulonglong2         v    = __ldcg(slot);
@@ -1643,14 +1644,32 @@ __global__ void __launch_bounds__(K4_THREADS) k_finish_select(const FinishParams
             uint32_t       kept = 0, max_c = 0, min_c = nh, all_bytes = 0, one_node = kNoNode, one_cnt = 0;
             if (start != kNoTuple)
             {
-                // ---- pass 1: sum runs of equal (read, node), cap, cutoff ----
-                const uint32_t cutoff = threshold_cutoff(nh, p.rel_cutoff);
+                // ---- pass 1: sum runs of equal (read, node, filter), cap, cutoff; merge the filters of a node ----
+                // Levels with several filters carry the filter index in the low `filter_bits` bits of the tuple's node field,
+                // so the runs of one node come in --ibf order and the cross-filter merge of select_matches (GC.cpp:528-539)
+                // is a walk over them: a filter's count replaces the node's only if it is strictly greater, and max / min of
+                // the read are updated at EVERY such store -- a value overwritten later still lowers min (the reference's
+                // behaviour, kept).
+                const uint32_t fmask = (1u << p.filter_bits) - 1;
                 uint64_t       run_key = ~0ull, sum = 0;
                 bool           partial = false;
-                auto           flush   = [&]() {
+                uint32_t       cur_node = kNoNode, best = 0, best_f = 0;
+                auto           emit    = [&]() {
+                    if (cur_node != kNoNode && best)
+                        p.entries[(uint64_t)start + nacc++] = ((uint64_t)cur_node << 32) | ((uint64_t)best_f << 24) | best;
+                };
+                auto flush = [&]() {
                     if (run_key == ~0ull)
                         return;
-                    bool ok = true;
+                    const uint32_t enc = (uint32_t)run_key & (kMaxNodes - 1), node = enc >> p.filter_bits, fi = enc & fmask;
+                    if (node != cur_node)
+                    {
+                        emit();
+                        cur_node = node;
+                        best     = 0;
+                    }
+                    const uint32_t cutoff = threshold_cutoff(nh, p.rel_cutoffs[fi]);
+                    bool           ok     = true;
                     if (p.is_hibf)
                     {
                         if (partial)
@@ -1667,12 +1686,12 @@ __global__ void __launch_bounds__(K4_THREADS) k_finish_select(const FinishParams
                         if (sum < cutoff)
                             ok = false;
                     }
-                    if (ok)
+                    if (ok && (uint32_t)sum > best)
                     {
-                        const uint32_t node = (uint32_t)run_key & (kMaxNodes - 1), cnt = (uint32_t)sum;
-                        p.entries[(uint64_t)start + nacc++] = ((uint64_t)node << 32) | cnt;
-                        max_c = max(max_c, cnt);
-                        min_c = min(min_c, cnt);
+                        best   = (uint32_t)sum;
+                        best_f = fi;
+                        max_c  = max(max_c, best);
+                        min_c  = min(min_c, best);
                     }
                 };
                 for (uint64_t i = start; i < p.n_tuples; ++i)
@@ -1692,6 +1711,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_finish_select(const FinishParams
                     partial |= ((t >> 16) & 1) != 0;
                 }
                 flush();
+                emit();
                 // ---- pass 2: rel-filter, fpr-query, LCA, sizes ----
                 if (nacc)
                 {
@@ -1700,13 +1720,13 @@ __global__ void __launch_bounds__(K4_THREADS) k_finish_select(const FinishParams
                     for (uint32_t j = 0; j < nacc; ++j)
                     {
                         const uint64_t e    = p.entries[(uint64_t)start + j];
-                        const uint32_t node = (uint32_t)(e >> 32), cnt = (uint32_t)(e & 0xFFFF);
+                        const uint32_t node = (uint32_t)(e >> 32), cnt = (uint32_t)(e & 0xFFFF), fi = (uint32_t)(e >> 24) & 15;
                         uint32_t       status = 0;
                         if ((double)cnt >= threshold_filter)
                         {
                             if (p.fpr_query < 1.0)
                             {
-                                const double q = dev_fpr_query_cached(p, node, nh, cnt);
+                                const double q = dev_fpr_query_cached(p, fi * p.n_nodes + node, nh, cnt);
                                 if (fabs(q - p.fpr_query) <= p.fpr_band)
                                     ambiguous = true;
                                 if (q > p.fpr_query)

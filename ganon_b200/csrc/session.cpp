@@ -265,6 +265,9 @@ struct LevelRt
     std::vector<FilterRt>    filters;
     double                   rel_filter = 0, fpr_query = 1;
     uint32_t                 k = 0, w = 0;
+    // levels with several filters finished by K4: the filter index rides in the low bits of a tuple's node field (0: the
+    // level has one filter, or its cross-filter merge stays in the host finishing stage)
+    uint32_t                 filter_bits = 0;
     std::string              out_one = "one", out_all = "all";
     // nodes: [0, n_targets) targets of the filters, then the remaining taxonomy nodes
     std::vector<std::string> node_names;
@@ -590,6 +593,7 @@ struct BatchCtx
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
     int  run_paged_count(FilterRt &F, const uint8_t *act, uint32_t n, uint64_t cap);
+    int  run_level_merged(size_t li, const uint8_t *act, uint64_t active_hashes);
     int  finish_level(size_t li);
     int  finish_level_device(size_t li, unsigned long long *rep, bool fetch, bool &done);
     int  to_host_state(size_t li);
@@ -637,24 +641,28 @@ gnb_session::~gnb_session()
 int gnb_session::build_finish_tables(LevelRt &L)
 {
     L.device_finish = false;
-    if (L.filters.size() != 1)
-        return GNB_OK; // the cross-filter merge (GC.cpp:531-539) stays in the host finishing stage
+    if (L.filters.size() != 1 && L.filter_bits == 0)
+        return GNB_OK; // this level's cross-filter merge (GC.cpp:531-539) stays in the host finishing stage
     if (const char *e = getenv("GANON_B200_HOST_FINISH"))
         if (e[0] == '1')
             return GNB_OK;
-    const size_t          nn = L.node_names.size();
+    const size_t          nn0 = L.node_names.size(), nf = L.filters.size();
+    const size_t          nn  = nn0 * nf; // [filter][node] tables
     std::vector<double>   fpr(nn, 0.0);
-    const FilterRt       &F = L.filters[0];
-    for (size_t i = 0; i < F.node_fpr.size() && i < nn; ++i)
-        fpr[i] = F.node_fpr[i];
-    std::vector<uint32_t> off(nn + 1, 0);
+    for (size_t f = 0; f < nf; ++f)
+    {
+        const FilterRt &F = L.filters[f];
+        for (size_t i = 0; i < F.node_fpr.size() && i < nn0; ++i)
+            fpr[f * nn0 + i] = F.node_fpr[i];
+    }
+    std::vector<uint32_t> off(nn0 + 1, 0);
     std::string           pool;
-    for (size_t i = 0; i < nn; ++i)
+    for (size_t i = 0; i < nn0; ++i)
     {
         off[i] = (uint32_t)pool.size();
         pool += L.node_names[i];
     }
-    off[nn] = (uint32_t)pool.size();
+    off[nn0] = (uint32_t)pool.size();
     // classes of equal fpr (keys of the --fpr-query cache)
     std::vector<uint32_t> cls(nn, 0);
     {
@@ -671,14 +679,14 @@ int gnb_session::build_finish_tables(LevelRt &L)
     GNB_TRY(L.d_fpr_memo.ensure(kFprMemoSlots * 16));
     GNB_CUDA(cudaMemset(L.d_fpr_memo.p, 0xFF, kFprMemoSlots * 16));
     GNB_TRY(L.d_node_fpr.ensure(nn * 8));
-    GNB_TRY(L.d_parent.ensure(nn * 4));
-    GNB_TRY(L.d_depth.ensure(nn * 4));
-    GNB_TRY(L.d_name_off.ensure((nn + 1) * 4));
+    GNB_TRY(L.d_parent.ensure(nn0 * 4));
+    GNB_TRY(L.d_depth.ensure(nn0 * 4));
+    GNB_TRY(L.d_name_off.ensure((nn0 + 1) * 4));
     GNB_TRY(L.d_names.ensure(pool.size() + 1));
     GNB_CUDA(cudaMemcpy(L.d_node_fpr.p, fpr.data(), nn * 8, cudaMemcpyHostToDevice));
-    GNB_CUDA(cudaMemcpy(L.d_parent.p, L.parent.data(), nn * 4, cudaMemcpyHostToDevice));
-    GNB_CUDA(cudaMemcpy(L.d_depth.p, L.depth.data(), nn * 4, cudaMemcpyHostToDevice));
-    GNB_CUDA(cudaMemcpy(L.d_name_off.p, off.data(), (nn + 1) * 4, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(L.d_parent.p, L.parent.data(), nn0 * 4, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(L.d_depth.p, L.depth.data(), nn0 * 4, cudaMemcpyHostToDevice));
+    GNB_CUDA(cudaMemcpy(L.d_name_off.p, off.data(), (nn0 + 1) * 4, cudaMemcpyHostToDevice));
     if (!pool.empty())
         GNB_CUDA(cudaMemcpy(L.d_names.p, pool.data(), pool.size(), cudaMemcpyHostToDevice));
     L.device_finish = true;
@@ -1029,10 +1037,13 @@ int gnb_session::build_shard_tables(LevelRt &L, FilterRt &F, uint64_t w0, uint64
         for (uint32_t i = 0; i < L.n_targets; ++i)
             node_of.emplace(L.node_names[i], i);
         bool any_seg = false;
+        const uint32_t fi = (uint32_t)(&F - L.filters.data());
         for (size_t t = 0; t < db.target_names.size(); ++t)
         {
-            const uint32_t node = node_of.at(db.target_names[t]);
-            F.node_fpr[node]    = db.target_fpr[t];
+            const uint32_t node_id = node_of.at(db.target_names[t]);
+            F.node_fpr[node_id]    = db.target_fpr[t];
+            // what K3 writes into a tuple's node field: the node, and the filter index below it where K4 merges the filters
+            const uint32_t node = L.filter_bits ? ((node_id << L.filter_bits) | fi) : node_id;
             const auto &bins    = db.target_bins[t];
             if (bins.size() == 1)
             {
@@ -1058,7 +1069,7 @@ int gnb_session::build_shard_tables(LevelRt &L, FilterRt &F, uint64_t w0, uint64
                 }
             const bool complete = regs.size() == 1 && local == bins.size();
             if (!complete)
-                F.node_multi[node] = 1;
+                F.node_multi[node_id] = 1;
             for (auto const &[rg, mask] : regs)
             {
                 Seg s;
@@ -1275,6 +1286,16 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
                 ++d;
             }
             L.depth[i] = d;
+        }
+        L.filter_bits = 0;
+        if (L.filters.size() > 1 && L.filters.size() <= 16 && !L.filters[0].db->is_hibf)
+        {
+            uint32_t bits = 0;
+            while ((1u << bits) < L.filters.size())
+                ++bits;
+            const char *e = getenv("GANON_B200_HOST_FINISH");
+            if (((uint64_t)L.node_names.size() << bits) < kMaxNodes && !(e && e[0] == '1'))
+                L.filter_bits = bits;
         }
         int rc = s->build_level_tables(L);
         if (rc != GNB_OK)
@@ -1953,6 +1974,78 @@ int BatchCtx::run_paged_count(FilterRt &F, const uint8_t *act, uint32_t n, uint6
     return GNB_OK;
 }
 
+// A level with several filters whose cross-filter merge K4 does (LevelRt::filter_bits > 0): K3 of every filter appends
+// behind one cursor -- the tuples carry the filter index below the node -- then one exchange (bin-sharded runs), one sort
+// by (read, node, filter) and the tuples stay in HBM for K4.
+int BatchCtx::run_level_merged(size_t li, const uint8_t *act, uint64_t active_hashes)
+{
+    LevelRt       &L = levels[li];
+    const uint32_t n = n_reads;
+    for (auto &Ft : tuples[li])
+        Ft.clear();
+    tuples_on_device = true;
+    n_tuples_dev     = 0;
+    if (n == 0)
+        return GNB_OK;
+    uint64_t cap = d_tuples_a.cap / 8;
+    if (cap < (uint64_t)n * 2 * L.filters.size() + 1024)
+    {
+        GNB_TRY(d_tuples_a.ensure(((uint64_t)n * 2 * L.filters.size() + 1024) * 8));
+        cap = d_tuples_a.cap / 8;
+    }
+    unsigned long long produced = 0;
+    float              ms_k3 = 0;
+    GNB_TRY(wait_turn());
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+        GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
+        GNB_CUDA(cudaEventRecord(ev[4], st));
+        for (auto &F : L.filters)
+        {
+            if (F.pages.empty())
+            {
+                launch_ibf_count(F.dev, d_hashes.as<uint64_t>(), d_hash_off.as<uint64_t>(), d_counts.as<uint32_t>(), act, n, std::min<uint32_t>(max_hashes_ub, 65535u), F.rel_cutoff,
+                                 d_tuples_a.as<uint64_t>(), d_cursor.as<unsigned long long>(), cap, st);
+                launches += 1;
+            }
+            else
+                GNB_TRY(run_paged_count(F, act, n, cap));
+        }
+        GNB_CUDA(cudaEventRecord(ev[5], st));
+        GNB_CUDA(cudaMemcpyAsync(&produced, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+        timing.d2h_bytes += 8;
+        GNB_CUDA(stream_wait(st));
+        GNB_CUDA(cudaGetLastError());
+        float ms1 = 0;
+        cudaEventElapsedTime(&ms1, ev[4], ev[5]);
+        ms_k3 += ms1;
+        if (produced <= cap)
+            break;
+        GNB_TRY(d_tuples_a.ensure(produced * 8));
+        cap = d_tuples_a.cap / 8;
+    }
+    for (auto &F : L.filters)
+        timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.db->ibfs[0].row_words() * 8;
+    if (S->sharded())
+        GNB_TRY(exchange_tuples(produced));
+    timing.ms_count += ms_k3;
+    timing.ms_exchange += ms_exchange_acc;
+    ms_exchange_acc = 0;
+    if (produced == 0)
+        return GNB_OK;
+    GNB_CUDA(cudaEventRecord(ev[6], st));
+    GNB_TRY(d_tuples_b.ensure(produced * 8));
+    GNB_TRY(d_tmp.ensure(sort_tmp_bytes(produced)));
+    launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
+    GNB_CUDA(cudaEventRecord(ev[7], st));
+    GNB_CUDA(stream_wait(st));
+    n_tuples_dev = produced;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[6], ev[7]);
+    timing.ms_sort += ms;
+    return GNB_OK;
+}
+
 // K3 (+ sort) for every filter of level li on the reads still active
 int BatchCtx::run_level(size_t li)
 {
@@ -1983,6 +2076,8 @@ int BatchCtx::run_level(size_t li)
         for (uint32_t i = 0; i < n; ++i)
             if (h_active[i] && h_counts[i] <= 65535)
                 active_hashes += h_counts[i];
+    if (keep_on_device && L.device_finish && L.filters.size() > 1)
+        return run_level_merged(li, act, active_hashes);
     float ms_sort = 0, ms_k3 = 0;
     for (size_t fi = 0; fi < L.filters.size(); ++fi)
     {
@@ -2189,10 +2284,10 @@ int BatchCtx::finish_level(size_t li)
                 one_filter.clear();
                 while (c < tp.size() && (uint32_t)(tp[c] >> kTupleReadShift) == r)
                 {
-                    const uint32_t node = (uint32_t)(tp[c] >> kTupleNodeShift) & (kMaxNodes - 1);
+                    const uint32_t node = ((uint32_t)(tp[c] >> kTupleNodeShift) & (kMaxNodes - 1)) >> L.filter_bits; // the filter index sits below
                     uint64_t       sum  = 0;
                     bool           partial = false;
-                    while (c < tp.size() && (uint32_t)(tp[c] >> kTupleReadShift) == r && ((uint32_t)(tp[c] >> kTupleNodeShift) & (kMaxNodes - 1)) == node)
+                    while (c < tp.size() && (uint32_t)(tp[c] >> kTupleReadShift) == r && (((uint32_t)(tp[c] >> kTupleNodeShift) & (kMaxNodes - 1)) >> L.filter_bits) == node)
                     {
                         sum += tp[c] & 0xFFFF;
                         partial |= ((tp[c] >> 16) & 1) != 0;
@@ -2418,6 +2513,7 @@ int BatchCtx::to_host_state(size_t li)
 {
     GNB_TRY(fetch_host_records());
     const size_t n = n_reads;
+    bool split = false;
     if (tuples_on_device)
     {
         PinnedVec<uint64_t> &Ft = tuples[li][0];
@@ -2428,6 +2524,7 @@ int BatchCtx::to_host_state(size_t li)
             timing.d2h_bytes += n_tuples_dev * 8;
         }
         tuples_on_device = false;
+        split            = levels[li].filter_bits > 0 && levels[li].filters.size() > 1;
     }
     if (active_on_device && n)
     {
@@ -2437,6 +2534,14 @@ int BatchCtx::to_host_state(size_t li)
     }
     GNB_CUDA(stream_wait(st));
     active_on_device = false;
+    if (split)
+    { // the merged list (sorted by read, node, filter) back into one list per filter, each still sorted by (read, node)
+        const uint32_t      fmask = (1u << levels[li].filter_bits) - 1;
+        PinnedVec<uint64_t> all;
+        all.swap(tuples[li][0]);
+        for (uint64_t t : all)
+            tuples[li][(size_t)((t >> kTupleNodeShift) & fmask)].push_back(t);
+    }
     return GNB_OK;
 }
 
@@ -2518,7 +2623,10 @@ int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch
     P.names       = L.d_names.as<char>();
     P.rep         = rep;
     P.root        = L.root;
-    P.rel_cutoff  = L.filters[0].rel_cutoff;
+    for (size_t f = 0; f < L.filters.size() && f < 16; ++f)
+        P.rel_cutoffs[f] = L.filters[f].rel_cutoff;
+    P.filter_bits = L.filter_bits;
+    P.n_nodes     = (uint32_t)L.node_names.size();
     P.rel_filter  = L.rel_filter;
     P.fpr_query   = L.fpr_query;
     P.fpr_band    = S->fpr_band;

@@ -873,3 +873,26 @@ def test_paged_filter_host_resident_tier_equals_the_whole(golden_dbs, tmp_path, 
     assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", path, "-c", "0.1", "-d", "0.5", "-o", pre2, "-a", "-u", "--quiet"]) == 0
     for ext in (".all", ".unc", ".rep"):
         assert _read_sorted(pre + ext) == _read_sorted(pre2 + ext)
+
+
+def test_levels_with_several_filters_finish_on_the_device(golden_dbs):
+    """The cross-filter merge of select_matches (GC.cpp:528-539: store only a strictly greater count, max / min updated at
+    every store -- the stale-min behaviour) runs in K4: two and three databases on one level report levels_on_device == 1
+    and give the host finishing stage's result (which the golden scenarios pin to the reference binary)."""
+    fq1 = open(os.path.join(SU.GOLDEN, "reads.1.fq"), "rb").read()
+    fq2 = open(os.path.join(SU.GOLDEN, "reads.2.fq"), "rb").read()
+    for names, cutoffs, rel_filter, fpr in ((("real4", "real4b"), [0.1, 0.3], [0.2], [1.0]), (("real4b", "synth", "real4"), [0.05] * 3, [0.3], [0.5]), (("synth", "synth"), [0.3, 0.1], [0.5], [1e-3])):
+        dbs = [Database.open(golden_dbs[n]) for n in names]
+        out = {}
+        for mode in ("device", "host"):
+            if mode == "host":
+                os.environ["GANON_B200_HOST_FINISH"] = "1"
+            try:
+                s = Session(dbs, cutoffs, rel_filter, fpr, output_all=True, output_unclassified=True, output_lca=False)
+                r = s.classify(fq1, fq2, final=True)
+                out[mode] = (sorted(result_text(r, "all").decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), s.report(), r.levels_on_device)
+                s.close()
+            finally:
+                os.environ.pop("GANON_B200_HOST_FINISH", None)
+        assert out["device"][3] == 1 and out["host"][3] == 0, names
+        assert out["device"][:3] == out["host"][:3] and out["device"][0], names
