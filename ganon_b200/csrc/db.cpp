@@ -136,7 +136,7 @@ int read_ibf_body(FileReader &f, IbfHost &ibf, int shard, int n_shards, cudaStre
         // the others to page-locked host memory
         size_t n_res = 0;
         if (!plan_pages(ibf, hbm_budget, ibf.pages, n_res))
-            return fail(GNB_ERR_LIMIT, "the HBM budget does not hold three one-word pages of this filter");
+            return fail(GNB_ERR_LIMIT, "the HBM budget does not hold two one-word pages of this filter");
         GNB_TRY(alloc_page_storage(ibf, n_res));
         while (row < ibf.bin_size)
         {
@@ -191,7 +191,7 @@ bool plan_pages(const IbfHost &t, uint64_t budget, std::vector<IbfPage> &pages, 
     if (pw >= 64)
         pw = pw / 64 * 64;
     if (pw == 0)
-        pw = budget / 3 / col_bytes; // tiny budgets (tests): three pages must fit
+        pw = budget / 2 / col_bytes; // tiny budgets (tests): at least the two staging buffers must fit
     if (pw == 0)
         return false;
     pw = std::min(pw, words);
@@ -596,7 +596,7 @@ extern "C" int gnb_db_page_out(gnb_db *db, uint64_t hbm_budget_bytes)
     if (t.bin_size * t.row_words() * 8 <= hbm_budget_bytes)
         return GNB_OK; // fits: nothing to do
     if (!plan_pages(t, hbm_budget_bytes, pages, n_res))
-        return fail(GNB_ERR_LIMIT, "gnb_db_page_out: the budget does not hold three one-word pages of this filter");
+        return fail(GNB_ERR_LIMIT, "gnb_db_page_out: the budget does not hold two one-word pages of this filter");
     t.pages = pages;
     int rc  = alloc_page_storage(t, n_res);
     if (rc != GNB_OK)

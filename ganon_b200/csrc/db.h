@@ -53,7 +53,7 @@ struct IbfHost
     }
 };
 
-// cut into pages for `budget` bytes of HBM; false: does not fit even as three narrowest pages.  n_resident pages stay in HBM.
+// cut into pages for `budget` bytes of HBM; false: does not even hold two one-word pages.  n_resident pages stay in HBM.
 bool plan_pages(const IbfHost &t, uint64_t budget, std::vector<IbfPage> &pages, size_t &n_resident);
 int  alloc_page_storage(IbfHost &t, size_t n_resident);
 void free_page_storage(IbfHost &t);
