@@ -30,6 +30,59 @@ namespace
 using Clock = std::chrono::steady_clock;
 inline double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
 
+// Page-locked block buffers are expensive to make (~70 ms per 64 MiB) and every file needs a ring of them: buffers of
+// finished files are kept and handed to the next file of the process.
+class PinnedPool
+{
+  public:
+    static PinnedPool &instance()
+    {
+        static PinnedPool *p = new PinnedPool(); // lives until the process ends (the driver frees the pages)
+        return *p;
+    }
+    char *get(size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].second >= bytes && free_[i].second <= bytes + bytes / 2)
+                {
+                    char *p = free_[i].first;
+                    sizes_.emplace_back(p, free_[i].second);
+                    free_.erase(free_.begin() + (long)i);
+                    return p;
+                }
+        }
+        char *p = nullptr;
+        if (cudaMallocHost((void **)&p, bytes) != cudaSuccess)
+            return nullptr;
+        std::lock_guard<std::mutex> l(mu_);
+        sizes_.emplace_back(p, bytes);
+        return p;
+    }
+    void put(char *p)
+    {
+        std::lock_guard<std::mutex> l(mu_);
+        for (size_t i = 0; i < sizes_.size(); ++i)
+            if (sizes_[i].first == p)
+            {
+                free_.push_back(sizes_[i]);
+                sizes_.erase(sizes_.begin() + (long)i);
+                break;
+            }
+        // keep at most 16 idle buffers
+        while (free_.size() > 16)
+        {
+            cudaFreeHost(free_.front().first);
+            free_.erase(free_.begin());
+        }
+    }
+
+  private:
+    std::mutex                             mu_;
+    std::vector<std::pair<char *, size_t>> free_, sizes_;
+};
+
 // One read file as a sequence of blocks.  Stream form (gzip, or any file of an unsliced session): every ring buffer has a
 // headroom in front of the fresh bytes; the unconsumed tail of a block (whole records the session held back, plus the
 // partial record at its end) is copied right-aligned into the next buffer's headroom, so fresh bytes never move and the
@@ -58,11 +111,8 @@ class BlockStream
     {
         release();
         for (auto &b : bufs_)
-            if (cudaMallocHost((void **)&b, head_ + block_ + 64) != cudaSuccess)
-            {
-                b = nullptr;
+            if ((b = PinnedPool::instance().get(head_ + block_ + 64)) == nullptr)
                 return fail(GNB_ERR_CUDA, "cannot allocate page-locked read buffers");
-            }
         cur_ = -1;
         return GNB_OK;
     }
@@ -71,7 +121,7 @@ class BlockStream
         for (auto &b : bufs_)
             if (b)
             {
-                cudaFreeHost(b);
+                PinnedPool::instance().put(b);
                 b = nullptr;
             }
     }
