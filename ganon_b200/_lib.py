@@ -124,6 +124,10 @@ class FilesResult(C.Structure):
     ]
 
 
+class BuildFileStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_sequences", "n_skipped", "n_bases", "n_hashes_total", "n_unique")] + [("parse_error", C.c_int)]
+
+
 class ReassignResult(C.Structure):
     _fields_ = [
         ("n_groups", C.c_uint32),
@@ -158,10 +162,14 @@ SYMBOLS = {
     "gnb_db_fill_random": (C.c_int, [_P, C.c_uint64, C.c_int]),
     "gnb_db_emplace": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gnb_db_set_targets": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), _P, _P, C.c_uint64]),
+    "gnb_db_set_fp": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "gnb_db_read_words": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "gnb_db_save": (C.c_int, [_P, C.c_char_p]),
     "gnb_db_create_hibf": (C.c_int, [C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64, C.POINTER(C.c_char_p), C.c_double, C.c_int, C.POINTER(_P)]),
     "gnb_db_emplace_ibf": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64]),
+    "gnb_build_file_hashes": (C.c_int, [C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_P), C.POINTER(BuildFileStats)]),
+    "gnb_hash_set_data": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "gnb_hash_set_free": (None, [_P]),
     "gnb_comm_unique_id": (C.c_int, [_P, C.c_uint64]),
     "gnb_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "gnb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

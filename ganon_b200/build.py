@@ -420,8 +420,24 @@ class GpuBackend:
             parts.append(self._c.minimisers_batch(full, k, w, device=self.device)[1])
         return np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
 
+    def file_hashes(self, path: str, k: int, w: int, min_length: int):
+        """count_hashes of one file inside the library: native reader (plain / gzip), K2 in segments, sort + unique in
+        HBM.  Returns (distinct hashes or None on a parse error, n_sequences, n_skipped, n_bases)."""
+        h, st = self._c.build_file_hashes(path, k, w, min_length, device=self.device)
+        return h, int(st.n_sequences), int(st.n_skipped), int(st.n_bases)
+
     def create(self, n_bins: int, bin_size_bits: int, hash_functions: int, k: int, w: int) -> None:
         self.db = self._c.Database.create(n_bins, bin_size_bits, hash_functions, k, w, device=self.device)
+
+    def save(self, path: str, counts, layout, params) -> None:
+        """The .ibf written by the library straight from HBM (no host copy of the bitvector)."""
+        import numpy as np
+
+        names = list(counts)
+        index = {t: i for i, t in enumerate(names)}
+        self.db.set_targets(names, np.array([index[t] for t, _f, _l in layout], dtype=np.uint32), np.array([counts[t] for t in names], dtype=np.uint64), params.max_hashes_bin)
+        self.db.set_fp(params.max_fp, params.true_max_fp, params.true_avg_fp)
+        self.db.save(path)
 
     def emplace(self, hashes, bins) -> None:
         self.db.emplace(hashes, bins)
@@ -452,44 +468,87 @@ def run_build(cfg: GanonBuildConfig, backend=None) -> bool:
     own = backend is None
     be = backend or GpuBackend(cfg.device)
     try:
-        # count_hashes (GanonBuild.cpp:184-249): distinct minimisers per target over all its files and sequences
+        # count_hashes (GanonBuild.cpp:184-249): distinct minimisers per target over all its files and sequences.  Like the
+        # reference, every file's set is appended to <tmp-output-folder>/<target>.min when a folder is given, so that only
+        # the counts stay in memory (RefSeq-scale builds); without a folder the sets are kept in host memory.
+        spill = cfg.tmp_output_folder or None
+        if spill:
+            os.makedirs(spill, exist_ok=True)
         hashes: Dict[str, "np.ndarray"] = {}
+        counts: Dict[str, int] = {}
+        min_files: Dict[str, str] = {}
         n_seq = n_skipped = n_bp = 0
+        native = hasattr(be, "file_hashes")
         for target, files in targets.items():
             parts = []
             for f in files:
-                seqs = []
-                records = read_sequences(f)
-                if records is None:
-                    print("Error parsing file [%s]." % f, file=sys.stderr)
-                    continue
-                for s in records:
-                    if len(s) < cfg.min_length:
-                        n_skipped += 1
+                if native:
+                    u, ns, nk, nb = be.file_hashes(f, cfg.kmer_size, cfg.window_size, cfg.min_length)
+                    n_seq += ns
+                    n_skipped += nk
+                    n_bp += nb
+                    if u is None:
+                        print("Error parsing file [%s]." % f, file=sys.stderr)
                         continue
-                    n_seq += 1
-                    n_bp += len(s)
-                    seqs.append(s)
-                parts.append(np.unique(be.minimisers(seqs, cfg.kmer_size, cfg.window_size)))
+                else:
+                    seqs = []
+                    records = read_sequences(f)
+                    if records is None:
+                        print("Error parsing file [%s]." % f, file=sys.stderr)
+                        continue
+                    for s in records:
+                        if len(s) < cfg.min_length:
+                            n_skipped += 1
+                            continue
+                        n_seq += 1
+                        n_bp += len(s)
+                        seqs.append(s)
+                    u = np.unique(be.minimisers(seqs, cfg.kmer_size, cfg.window_size))
+                parts.append(u)
             # the reference counts per file and adds up (a hash shared by two files of a target counts twice) and appends
             # every file's set to the target's .min file: keep the per-file sets concatenated
-            hashes[target] = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
-        counts = {t: int(h.size) for t, h in hashes.items()}
+            counts[target] = int(sum(p.size for p in parts))
+            if spill:
+                min_files[target] = os.path.join(spill, target.replace("/", "_") + ".min")
+                with open(min_files[target], "wb") as fh:
+                    for p in parts:
+                        p.tofile(fh)
+            else:
+                hashes[target] = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
         params = choose_ibf_params(counts, cfg.max_fp, cfg.filter_size, cfg.hash_functions, cfg.mode)
         if params.n_bins == 0:
             print("No valid sequences to build", file=sys.stderr)
             return False
         layout = bin_layout(counts, params)
         be.create(params.n_bins, params.bin_size_bits, params.hash_functions, cfg.kmer_size, cfg.window_size)
-        hs, bs = [], []
+        # insertion target by target, in bounded pieces (at most 2^25 hashes per emplace call)
+        piece = 1 << 25
+        by_target: Dict[str, List[Tuple[int, int, int]]] = {}
         for binno, (target, first, last) in enumerate(layout):
-            hs.append(hashes[target][first : last + 1])
-            bs.append(np.full(last + 1 - first, binno, dtype=np.uint32))
-        be.emplace(np.concatenate(hs), np.concatenate(bs))
-        db = formats.IBFFile(formats.IBF(params.n_bins, params.bin_size_bits, params.hash_functions, be.words()), cfg.kmer_size, cfg.window_size,
-                             params.max_hashes_bin, [(t, c) for t, c in counts.items()], [(b, t) for b, (t, _f, _l) in enumerate(layout)],
-                             max_fp=params.max_fp, true_max_fp=params.true_max_fp, true_avg_fp=params.true_avg_fp)
-        formats.write_ibf(cfg.output_file, db)
+            by_target.setdefault(target, []).append((binno, first, last))
+        for target, bins in by_target.items():
+            th = np.fromfile(min_files[target], dtype=np.uint64) if spill else hashes[target]
+            hs, bs, pending = [], [], 0
+            for binno, first, last in bins:
+                for a in range(first, last + 1, piece):
+                    b = min(last + 1, a + piece)
+                    hs.append(th[a:b])
+                    bs.append(np.full(b - a, binno, dtype=np.uint32))
+                    pending += b - a
+                    if pending >= piece:
+                        be.emplace(np.concatenate(hs), np.concatenate(bs))
+                        hs, bs, pending = [], [], 0
+            if pending:
+                be.emplace(np.concatenate(hs), np.concatenate(bs))
+            if spill:
+                os.remove(min_files[target])
+        if hasattr(be, "save"):
+            be.save(cfg.output_file, counts, layout, params)
+        else:
+            db = formats.IBFFile(formats.IBF(params.n_bins, params.bin_size_bits, params.hash_functions, be.words()), cfg.kmer_size, cfg.window_size,
+                                 params.max_hashes_bin, [(t, c) for t, c in counts.items()], [(b, t) for b, (t, _f, _l) in enumerate(layout)],
+                                 max_fp=params.max_fp, true_max_fp=params.true_max_fp, true_avg_fp=params.true_avg_fp)
+            formats.write_ibf(cfg.output_file, db)
     finally:
         if own:
             be.close()

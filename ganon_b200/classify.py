@@ -114,6 +114,9 @@ class Database:
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         check(_lib.lib().gnb_db_set_targets(self._h, len(names), arr, bt.ctypes.data, th.ctypes.data, max_hashes_bin))
 
+    def set_fp(self, max_fp: float, true_max_fp: float, true_avg_fp: float) -> None:
+        check(_lib.lib().gnb_db_set_fp(self._h, max_fp, true_max_fp, true_avg_fp))
+
     def read_words(self, offset: int, n: int, ibf_index: int = 0):
         import numpy as np
 
@@ -149,6 +152,23 @@ class Database:
             self.close()
         except Exception:
             pass
+
+
+def build_file_hashes(path: str, k: int, w: int, min_length: int = 0, device: int = 0, io_threads: int = 0):
+    """ganon-build's count_hashes for one file on the device (gnb_build_file_hashes): (distinct minimisers ascending --
+    None if the file has a parse error --, stats)."""
+    import numpy as np
+
+    h = C.c_void_p()
+    st = _lib.BuildFileStats()
+    check(_lib.lib().gnb_build_file_hashes(device, path.encode(), k, w, min_length, io_threads, C.byref(h), C.byref(st)))
+    try:
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().gnb_hash_set_data(h, C.byref(p), C.byref(n)))
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n.value,)).copy() if n.value else np.empty(0, dtype=np.uint64)
+    finally:
+        _lib.lib().gnb_hash_set_free(h)
+    return (None if st.parse_error else arr), st
 
 
 def minimisers_batch(seqs: Sequence[bytes], k: int, w: int, device: int = 0):

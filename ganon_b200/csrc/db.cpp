@@ -752,6 +752,17 @@ extern "C" int gnb_db_set_targets(gnb_db *db, uint64_t n_targets, const char *co
     return GNB_OK;
 }
 
+extern "C" int gnb_db_set_fp(gnb_db *db, double max_fp, double true_max_fp, double true_avg_fp)
+{
+    if (!db || db->is_hibf)
+        return fail(GNB_ERR_ARG, "gnb_db_set_fp: bad arguments");
+    db->max_fp      = max_fp;
+    db->true_max_fp = true_max_fp;
+    db->true_avg_fp = true_avg_fp;
+    db->derive_targets();
+    return GNB_OK;
+}
+
 extern "C" int gnb_db_read_words(const gnb_db *db, uint64_t ibf_index, uint64_t word_offset, uint64_t n_words, uint64_t *out)
 {
     if (!db || ibf_index >= db->ibfs.size() || !out)

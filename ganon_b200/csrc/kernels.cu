@@ -13,6 +13,7 @@
 // These are HBM-bound integer kernels: no tensor-core work exists on this path.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "gnb_internal.h"
 #include "k2_thread.cuh"
@@ -1513,6 +1514,30 @@ void launch_sort_tuples(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp
     if (n == 0)
         return;
     cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, in, out, (int64_t)n, 16, 64, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// distinct values of a hash list (ganon-build: the minimiser set of a file): radix sort + unique
+// ---------------------------------------------------------------------------------------------------------------------
+size_t unique_tmp_bytes(uint64_t n)
+{
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, a, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)n, 0, 64);
+    cub::DeviceSelect::Unique(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (unsigned long long *)nullptr, (int64_t)n);
+    return std::max(a, b) + 256;
+}
+
+void launch_sort_unique(const uint64_t *in, uint64_t *tmp_keys, uint64_t *out, uint64_t n, unsigned long long *d_n_out, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    if (n == 0)
+    {
+        cudaMemsetAsync(d_n_out, 0, 8, st);
+        return;
+    }
+    size_t bytes = tmp_bytes;
+    cub::DeviceRadixSort::SortKeys(tmp, bytes, in, tmp_keys, (int64_t)n, 0, 64, st);
+    bytes = tmp_bytes;
+    cub::DeviceSelect::Unique(tmp, bytes, tmp_keys, out, d_n_out, (int64_t)n, st);
 }
 
 // =====================================================================================================================

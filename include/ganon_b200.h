@@ -104,6 +104,8 @@ int gnb_db_emplace(gnb_db *db, const uint64_t *hashes, const uint32_t *bins, uin
 /* bin_target[bins]: target index of every bin; target_hashes[n_targets]: hashes_count_std entries */
 int gnb_db_set_targets(gnb_db *db, uint64_t n_targets, const char *const *names, const uint32_t *bin_target,
                        const uint64_t *target_hashes, uint64_t max_hashes_bin);
+/* IBFConfig.max_fp / true_max_fp / true_avg_fp of the file gnb_db_save writes (GanonBuild.cpp:251-288) */
+int gnb_db_set_fp(gnb_db *db, double max_fp, double true_max_fp, double true_avg_fp);
 int gnb_db_read_words(const gnb_db *db, uint64_t ibf_index, uint64_t word_offset, uint64_t n_words, uint64_t *out);
 /* flat: .ibf in the reference layout (save_filter GanonBuild.cpp:251-288); HIBF: raptor 3.0.1 index layout as read by
  * load_filter(THIBF) GC.cpp:875-938 (one path "/db/<target>.minimiser" per user bin) */
@@ -117,6 +119,23 @@ int gnb_db_create_hibf(uint64_t n_ibfs, const uint64_t *bins, const uint64_t *bi
                        uint32_t kmer_size, uint32_t window_size, const int64_t *next_ibf, const int64_t *bin_to_user,
                        uint64_t n_user_bins, const char *const *user_bin_names, double fpr, int device, gnb_db **out);
 int gnb_db_emplace_ibf(gnb_db *db, uint64_t ibf_index, const uint64_t *hashes, const uint32_t *bins, uint64_t n);
+
+/* ganon-build's count_hashes for ONE input file (src/ganon-build/GanonBuild.cpp:184-249): the file (plain / gzip, FASTA /
+ * FASTQ, read like the read files) goes through K2 in segments and the distinct minimisers of all its sequences of at
+ * least min_length bases -- the set the reference builds per file before counting and storing it -- come out of a sort +
+ * unique in HBM.  A parse error drops the file's hashes but keeps the counts (GanonBuild.cpp:241-245).  The hash set
+ * (ascending) stays in page-locked host memory until gnb_hash_set_free. */
+typedef struct gnb_hash_set gnb_hash_set;
+typedef struct
+{
+    uint64_t n_sequences, n_skipped, n_bases; /* Total of GanonBuild.cpp:63-70                       */
+    uint64_t n_hashes_total, n_unique;        /* minimisers emitted / distinct                       */
+    int      parse_error;
+} gnb_build_file_stats;
+int  gnb_build_file_hashes(int device, const char *path, uint32_t k, uint32_t w, uint64_t min_length, int io_threads, gnb_hash_set **out,
+                           gnb_build_file_stats *stats);
+int  gnb_hash_set_data(const gnb_hash_set *s, const uint64_t **hashes, uint64_t *n);
+void gnb_hash_set_free(gnb_hash_set *s);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Bin-sharded runs over several GPUs (one process per GPU).  The reference has no multi-device form: GanonClassify::run
