@@ -25,9 +25,6 @@ struct NcclApi
     ncclResult_t (*CommDestroy)(ncclComm_t)                                                                        = nullptr;
     const char *(*GetErrorString)(ncclResult_t)                                                                    = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)              = nullptr;
-    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)         = nullptr;
-    ncclResult_t (*GroupStart)()                                                                                   = nullptr;
-    ncclResult_t (*GroupEnd)()                                                                                     = nullptr;
     std::string error;
 };
 
@@ -63,9 +60,6 @@ NcclApi &api()
         a.CommDestroy    = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
         a.AllGather      = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
-        a.Broadcast      = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
-        a.GroupStart     = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
-        a.GroupEnd       = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
         if (!ok)
         {
             dlclose(a.handle);
@@ -98,28 +92,6 @@ int comm_all_gather(void *nccl_comm, const void *send, void *recv, size_t bytes_
     return GNB_OK;
 }
 
-int comm_all_gather_v(const gnb_comm *c, const uint64_t *send, uint64_t *recv, const uint64_t *counts, cudaStream_t st)
-{
-    GNB_TRY(need_api());
-    // one grouped launch of n_ranks broadcasts: root r sends its counts[r] words into everybody's recv + offset(r)
-    GNB_NCCL(api().GroupStart());
-    uint64_t off = 0;
-    for (int r = 0; r < c->n_ranks; ++r)
-    {
-        if (counts[r])
-        {
-            ncclResult_t rc = api().Broadcast(r == c->rank ? send : recv + off, recv + off, counts[r], ncclUint64, r, static_cast<ncclComm_t>(c->nccl), st);
-            if (rc != ncclSuccess)
-            {
-                api().GroupEnd();
-                return fail(GNB_ERR_CUDA, std::string("ncclBroadcast: ") + api().GetErrorString(rc));
-            }
-        }
-        off += counts[r];
-    }
-    GNB_NCCL(api().GroupEnd());
-    return GNB_OK;
-}
 } // namespace gnb
 
 using namespace gnb;

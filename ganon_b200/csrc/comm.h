@@ -20,6 +20,4 @@ namespace gnb
 {
 // all ranks contribute `bytes_per_rank` bytes at send (may alias recv + rank * bytes_per_rank); recv holds n_ranks * bytes_per_rank
 int comm_all_gather(void *nccl_comm, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t st);
-// all-gather of lists of different lengths: rank r's `counts[r]` 64-bit words go to recv + sum(counts[0..r)); send = this rank's list
-int comm_all_gather_v(const gnb_comm *c, const uint64_t *send, uint64_t *recv, const uint64_t *counts, cudaStream_t st);
 } // namespace gnb

@@ -480,7 +480,7 @@ struct BatchCtx
     bool   host_block_valid = true; // blk1 / blk2 point at the whole block in host memory
     float  ms_exchange_acc = 0;
     bool   exchange_timed = false;
-    int    exchange_tuples(unsigned long long &produced);
+    int    exchange_tuples(unsigned long long &produced, const uint64_t *&list, uint64_t &n_sort);
     int    ensure_host_block(cudaStream_t stream);
     PinnedVec<uint32_t>   h_counts;
     std::vector<uint8_t>  h_active;
@@ -2026,17 +2026,19 @@ int BatchCtx::run_level_merged(size_t li, const uint8_t *act, uint64_t active_ha
     }
     for (auto &F : L.filters)
         timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.db->ibfs[0].row_words() * 8;
+    const uint64_t *src    = d_tuples_a.as<uint64_t>();
+    uint64_t        n_sort = produced;
     if (S->sharded())
-        GNB_TRY(exchange_tuples(produced));
+        GNB_TRY(exchange_tuples(produced, src, n_sort));
     timing.ms_count += ms_k3;
     timing.ms_exchange += ms_exchange_acc;
     ms_exchange_acc = 0;
     if (produced == 0)
         return GNB_OK;
     GNB_CUDA(cudaEventRecord(ev[6], st));
-    GNB_TRY(d_tuples_b.ensure(produced * 8));
-    GNB_TRY(d_tmp.ensure(sort_tmp_bytes(produced)));
-    launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
+    GNB_TRY(d_tuples_b.ensure(n_sort * 8));
+    GNB_TRY(d_tmp.ensure(sort_tmp_bytes(n_sort)));
+    launch_sort_tuples(src, d_tuples_b.as<uint64_t>(), n_sort, d_tmp.p, d_tmp.cap, st);
     GNB_CUDA(cudaEventRecord(ev[7], st));
     GNB_CUDA(stream_wait(st));
     n_tuples_dev = produced;
@@ -2135,15 +2137,17 @@ int BatchCtx::run_level(size_t li)
         }
         if (!F.is_hibf)
             timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.db->ibfs[0].row_words() * 8;
+        const uint64_t *src    = d_tuples_a.as<uint64_t>();
+        uint64_t        n_sort = produced;
         if (S->sharded())
-            GNB_TRY(exchange_tuples(produced)); // d_tuples_a now holds the lists of all ranks
+            GNB_TRY(exchange_tuples(produced, src, n_sort)); // the lists of all ranks (padded slots: all-ones sort last)
         if (produced == 0)
             continue;
         GNB_CUDA(cudaEventRecord(ev[6], st));
-        GNB_TRY(d_tuples_b.ensure(produced * 8));
-        const size_t tb = sort_tmp_bytes(produced);
+        GNB_TRY(d_tuples_b.ensure(n_sort * 8));
+        const size_t tb = sort_tmp_bytes(n_sort);
         GNB_TRY(d_tmp.ensure(tb));
-        launch_sort_tuples(d_tuples_a.as<uint64_t>(), d_tuples_b.as<uint64_t>(), produced, d_tmp.p, d_tmp.cap, st);
+        launch_sort_tuples(src, d_tuples_b.as<uint64_t>(), n_sort, d_tmp.p, d_tmp.cap, st);
         GNB_CUDA(cudaEventRecord(ev[7], st));
         if (stay)
             n_tuples_dev = produced;
@@ -2169,42 +2173,56 @@ int BatchCtx::run_level(size_t li)
 // Bin-sharded run: this rank's K3 saw only its bin-word columns, so d_tuples_a holds the candidates of
 // its own bins -- finished counts for targets inside the shard, partial sums (flag bit 16) for targets that straddle a
 // shard boundary.  Every rank needs all of them (K4 then adds the partial sums, applies cap / cutoff / rel-filter /
-// fpr-query / LCA exactly as on one GPU and produces the identical result everywhere).  Two collectives on the compute
-// stream, inside this batch's GPU turn, hence in the same order on every rank: an all-gather of the list lengths
-// (8 bytes per rank; the host needs them to size the buffers) and one grouped launch of n_ranks broadcasts that moves the
-// lists themselves (a few bytes per read, against 2 * bins bytes per read for the count vectors a dense allreduce
-// would move).  On return d_tuples_a holds the concatenation in rank order and `produced` its length.
-int BatchCtx::exchange_tuples(unsigned long long &produced)
+// fpr-query / LCA exactly as on one GPU and produces the identical result everywhere).  ONE collective on the compute
+// stream, inside this batch's GPU turn, hence in the same order on every rank: an all-gather of fixed-size slots
+// `[cap tuples | count]` (a few bytes per read, against 2 * bins bytes per read for the count vectors a dense allreduce
+// would move).  The slot size is a function of the batch's read count and, after an overflow, of the gathered counts, so
+// all ranks agree on it without talking; unused slot words are all-ones and sort behind every tuple.  One host sync (the
+// counts).  On return `list` points at the gathered slots, `n_sort` is their length in words and `produced` the number
+// of real tuples among them.
+int BatchCtx::exchange_tuples(unsigned long long &produced, const uint64_t *&list, uint64_t &n_sort)
 {
     gnb_comm    *cm = S->comm;
-    const size_t N  = (size_t)cm->n_ranks;
-    GNB_TRY(d_xch.ensure(N * 8));
-    GNB_TRY(h_xch.ensure(N * 8));
+    const size_t N  = (size_t)cm->n_ranks, r = (size_t)cm->rank;
+    GNB_TRY(h_xch.ensure(64 + N * 8));
+    uint64_t *cnt = h_xch.as<uint64_t>() + 8;
+    uint64_t  cap = (uint64_t)n_reads / 4 + 1024;
     GNB_CUDA(cudaEventRecord(ev[12], st));
-    // d_cursor holds this rank's `produced` (the last K3 attempt fitted: produced <= capacity)
-    GNB_TRY(comm_all_gather(cm->nccl, d_cursor.p, d_xch.p, 8, st));
-    GNB_CUDA(cudaMemcpyAsync(h_xch.p, d_xch.p, N * 8, cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(stream_wait(st));
-    const uint64_t *cnt   = h_xch.as<uint64_t>();
-    uint64_t        total = 0;
-    for (size_t r = 0; r < N; ++r)
-        total += cnt[r];
-    if (cnt[cm->rank] != produced)
-        return fail(GNB_ERR_CUDA, "sharded exchange: tuple count mismatch on this rank");
-    timing.d2h_bytes += N * 8;
-    if (total)
+    for (;;)
     {
-        GNB_TRY(d_gather.ensure(total * 8));
-        GNB_TRY(comm_all_gather_v(cm, d_tuples_a.as<uint64_t>(), d_gather.as<uint64_t>(), cnt, st));
-        std::swap(d_tuples_a, d_gather);
+        const uint64_t slot = cap + 1;
+        GNB_TRY(d_gather.ensure(N * slot * 8));
+        uint64_t *own = d_gather.as<uint64_t>() + r * slot;
+        GNB_CUDA(cudaMemsetAsync(own, 0xFF, slot * 8, st));
+        if (produced)
+            GNB_CUDA(cudaMemcpyAsync(own, d_tuples_a.p, std::min<uint64_t>(produced, cap) * 8, cudaMemcpyDeviceToDevice, st));
+        // d_cursor holds this rank's `produced` (the last K3 attempt fitted: produced <= capacity of d_tuples_a)
+        GNB_CUDA(cudaMemcpyAsync(own + cap, d_cursor.p, 8, cudaMemcpyDeviceToDevice, st));
+        GNB_TRY(comm_all_gather(cm->nccl, own, d_gather.p, slot * 8, st));
+        GNB_CUDA(cudaMemcpy2DAsync(cnt, 8, d_gather.as<uint64_t>() + cap, slot * 8, 8, N, cudaMemcpyDeviceToHost, st));
+        GNB_CUDA(cudaMemset2DAsync(d_gather.as<uint64_t>() + cap, slot * 8, 0xFF, 8, N, st)); // the counts must not be sorted as tuples
+        GNB_CUDA(cudaEventRecord(ev[13], st));
+        GNB_CUDA(stream_wait(st));
+        timing.d2h_bytes += N * 8;
+        uint64_t mx = 0;
+        for (size_t q = 0; q < N; ++q)
+            mx = std::max(mx, cnt[q]);
+        if (cnt[r] != produced)
+            return fail(GNB_ERR_CUDA, "sharded exchange: tuple count mismatch on this rank");
+        if (mx <= cap)
+            break;
+        cap = 2 * mx; // the same decision on every rank: go again with slots that hold the longest list
     }
-    GNB_CUDA(cudaEventRecord(ev[13], st));
-    GNB_CUDA(stream_wait(st));
+    uint64_t total = 0;
+    for (size_t q = 0; q < N; ++q)
+        total += cnt[q];
     float ms = 0;
     cudaEventElapsedTime(&ms, ev[12], ev[13]);
     ms_exchange_acc += ms;
     timing.exchanged_bytes += total * 8;
     produced = total;
+    list     = d_gather.as<uint64_t>();
+    n_sort   = total ? N * (cap + 1) : 0;
     trace_mark(this, "exchange.done");
     return GNB_OK;
 }
