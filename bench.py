@@ -379,6 +379,7 @@ def main():
     ap.add_argument("--cli", action="store_true", help="also time the drop-in command line (bin/ganon-classify) on a FASTQ file of the pool's batches and the saved database (always on for the c2 sub-record of the default run)")
     ap.add_argument("--em", action="store_true", help="also time the EM reassignment (SURVEY 8f.1) on the matches of the e2e batches kept in HBM, next to the CPU restatement of src/ganon/reassign.py on the same .all text")
     ap.add_argument("--paged", action="store_true", help="also measure the host-resident tier: the workload's filter with half of it allowed in HBM (always on for the default c3 line)")
+    ap.add_argument("--build", action="store_true", help="also time the drop-in ganon-build on the GPU next to the reference builder (always on for the default N = 1 line)")
     ap.add_argument("--shard-db", action="store_true", help="bin-shard the database over the GPUs (the default for N > 1)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: replicated database, reads sharded (weak scaling) as the headline instead of the bin-sharded arm")
     args = ap.parse_args()
@@ -429,6 +430,11 @@ def main():
                 sub = {"error": str(ex)[:300]}
             if rank == 0:
                 line.setdefault("extra", {})[e] = sub
+    if rank == 0 and world == 1 and (args.build or not explicit):
+        try:
+            line.setdefault("extra", {})["ganon_build"] = build_leg(local_rank)
+        except Exception as ex:
+            line.setdefault("extra", {})["ganon_build"] = {"error": str(ex)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -985,6 +991,77 @@ def paged_leg(wl, db, host, dev, Session, result_text):
             "h2d_bytes_per_step": streamed // steps, "h2d_GBps": streamed / dt / 1e9, "ms_count_last": r.ms_count,
             "bound": "PCIe: every batch streams the non-resident pages once; K3 of the resident pages and of the page before overlaps the copies",
             "parity": {"reads": wl["reads_per_step"] * units, "identical": got == want, "against": "the same session on the filter whole in HBM (byte comparison of the .all text)"}}
+
+
+def build_leg(dev, n_targets=256, genome_len=1_000_000):
+    """`ganon-build`: the drop-in builder on the GPU next to the unmodified reference builder with all host
+    threads, same FASTA files and input table; parity on what is invariant in the reference (IBF parameters, per-target hash
+    counts, number of bins per target) and on classification: both filters classify the same reads identically."""
+    from ganon_b200 import formats, synth
+    from ganon_b200.classify import Database, Session, result_text
+
+    ref_build = os.path.join(ROOT, "oracle", "_ref", "ganon-build")
+    d = os.path.join(CACHE, "build")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    make_room(n_targets * genome_len * 3)
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    table = []
+    for t in range(n_targets):
+        g = acgt[rng.integers(0, 4, size=genome_len, dtype=np.uint8)]
+        lines = np.empty((genome_len // 80, 81), dtype=np.uint8)
+        lines[:, :80] = g[: genome_len // 80 * 80].reshape(-1, 80)
+        lines[:, 80] = ord("\n")
+        path = os.path.join(d, "g%04d.fna" % t)
+        with open(path, "wb") as f:
+            f.write(b">contig%d\n" % t)
+            f.write(lines.tobytes())
+        table.append("%s\tT%d" % (path, t))
+    tab = os.path.join(d, "input.tsv")
+    with open(tab, "w") as f:
+        f.write("\n".join(table) + "\n")
+    n_bp = n_targets * (genome_len // 80 * 80)
+    common = ["--input-file", tab, "--kmer-size", "19", "--window-size", "31", "--max-fp", "0.05", "--hash-functions", "4", "--verbose"]
+    out_gpu, out_ref = os.path.join(d, "gpu.ibf"), os.path.join(d, "ref.ibf")
+    t0 = time.perf_counter()
+    pg = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "ganon-build")] + common + ["--output-file", out_gpu, "--tmp-output-folder", os.path.join(d, "tmp_gpu") + "/", "--device", str(dev)],
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    t_gpu = time.perf_counter() - t0
+    line = {"targets": n_targets, "bases": n_bp, "gpu_rc": pg.returncode, "gpu_wall_s": t_gpu, "gpu_mbp_per_s": n_bp / 1e6 / t_gpu, "gpu_stderr_tail": pg.stderr[-200:] if pg.returncode else ""}
+    if os.path.exists(ref_build) and pg.returncode == 0:
+        os.makedirs(os.path.join(d, "tmp_ref"), exist_ok=True)
+        t0 = time.perf_counter()
+        pr = subprocess.run([ref_build] + common + ["--output-file", out_ref, "--tmp-output-folder", os.path.join(d, "tmp_ref") + "/", "--threads", str(reference_threads())],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        t_ref = time.perf_counter() - t0
+        line.update(ref_rc=pr.returncode, ref_wall_s=t_ref, ref_mbp_per_s=n_bp / 1e6 / t_ref, ref_threads=reference_threads(), ref_stderr_tail=pr.stderr[-200:] if pr.returncode else "")
+        if pr.returncode == 0:
+            a, b = formats.read_ibf(out_gpu, load_data=False), formats.read_ibf(out_ref, load_data=False)
+            same_cfg = (a.ibf.bins, a.ibf.bin_size, a.ibf.hash_funs, a.kmer_size, a.window_size, a.max_hashes_bin) == (b.ibf.bins, b.ibf.bin_size, b.ibf.hash_funs, b.kmer_size, b.window_size, b.max_hashes_bin)
+            same_counts = dict(a.hashes_count) == dict(b.hashes_count)
+            nb = lambda x: sorted((t, sum(1 for _b, tt in x.bin_map if tt == t)) for t in dict(x.hashes_count))
+            # classification with both filters: reads sampled from the genomes
+            reads = []
+            for i in range(20000):
+                t = int(rng.integers(0, n_targets))
+                with open(os.path.join(d, "g%04d.fna" % t), "rb") as f:
+                    f.seek(len(b">contig%d\n" % t) + int(rng.integers(0, genome_len // 80 - 4)) * 81)
+                    s = f.read(81 * 3).replace(b"\n", b"")[:150]
+                reads.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+            fq = b"".join(reads)
+            outs = []
+            for path in (out_gpu, out_ref):
+                dbx = Database.open(path, device=dev)
+                sx = Session([dbx], [0.5], [0.1], [1.0], output_all=True, device=dev)
+                outs.append(sorted(result_text(sx.classify(fq, final=True), "all").decode().splitlines()))
+                sx.close()
+                dbx.close()
+            line["parity"] = {"ibf_parameters_equal": same_cfg, "per_target_hash_counts_equal": same_counts, "bins_per_target_equal": nb(a) == nb(b),
+                              "classification_equal": outs[0] == outs[1], "classified_lines": len(outs[0]),
+                              "note": "bit layout inside a target's bins follows hash-table iteration order in the reference: compared on the invariants"}
+    shutil.rmtree(d, ignore_errors=True)
+    return line
 
 
 def cli_leg(wl_name, wl, db, blocks, pool, R, dev):

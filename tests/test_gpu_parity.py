@@ -896,3 +896,43 @@ def test_levels_with_several_filters_finish_on_the_device(golden_dbs):
                 os.environ.pop("GANON_B200_HOST_FINISH", None)
         assert out["device"][3] == 1 and out["host"][3] == 0, names
         assert out["device"][:3] == out["host"][:3] and out["device"][0], names
+
+
+def test_build_file_hashes_equal_the_oracle_minimiser_sets(tmp_path):
+    """gnb_build_file_hashes (ganon-build's count_hashes for one file): sequences cut into segments of 2048 windows, K2, sort
+    + unique in HBM -- the distinct minimisers equal the set the oracle finds over the whole sequences; wrapped FASTA, gzip,
+    --min-length, sequences shorter than the window (clamped window) and shorter than k."""
+    import gzip as gz
+
+    from ganon_b200.classify import build_file_hashes
+
+    rng = np.random.default_rng(21)
+    k, w = 19, 31
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=n).astype(np.uint8)) for n in (50_000, 7, 25, 30, 31, 2048 + 30, 2049 + 30, 4096 + 31, 300, 12_345)]
+    seqs[8] = b"ACGTN" * 60  # IUPAC letters count as A
+    fa = b"".join(b">s%d some text\n" % i + b"\n".join(s[a : a + 70] for a in range(0, len(s), 70)) + b"\n" for i, s in enumerate(seqs))
+    (tmp_path / "g.fa").write_bytes(fa)
+    with gz.open(tmp_path / "g.fa.gz", "wb") as f:
+        f.write(fa)
+    fq = b"".join(b"@q%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(seqs))
+    (tmp_path / "g.fq").write_bytes(fq)
+
+    def oracle_set(min_length):
+        parts = []
+        for s in seqs:
+            if len(s) < min_length or len(s) < k:
+                continue
+            parts.append(O.minimiser_hash(s, k, min(w, len(s))))
+        return np.unique(np.concatenate(parts))
+
+    for name in ("g.fa", "g.fa.gz", "g.fq"):
+        for min_length in (0, 26, 301):
+            got, st = build_file_hashes(str(tmp_path / name), k, w, min_length)
+            want = oracle_set(min_length)
+            assert np.array_equal(got, want), (name, min_length, got.size, want.size)
+            assert st.n_sequences == sum(len(s) >= min_length for s in seqs) and st.n_skipped == sum(len(s) < min_length for s in seqs)
+            assert st.n_bases == sum(len(s) for s in seqs if len(s) >= min_length) and st.n_unique == want.size and not st.parse_error
+    # a parse error drops the file's hashes, the counts stay
+    (tmp_path / "bad.fq").write_bytes(fq + b"@broken\nACGT\n+\nII\n")
+    got, st = build_file_hashes(str(tmp_path / "bad.fq"), k, w, 0)
+    assert got is None and st.parse_error and st.n_sequences == len(seqs)
