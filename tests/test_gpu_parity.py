@@ -936,3 +936,38 @@ def test_build_file_hashes_equal_the_oracle_minimiser_sets(tmp_path):
     (tmp_path / "bad.fq").write_bytes(fq + b"@broken\nACGT\n+\nII\n")
     got, st = build_file_hashes(str(tmp_path / "bad.fq"), k, w, 0)
     assert got is None and st.parse_error and st.n_sequences == len(seqs)
+
+
+@pytest.mark.parametrize("bad_at", [2801, 2912, 2913, 5000, 5601, 9999])
+def test_parse_error_chunk_rule_across_blocks(golden_dbs, tmp_path, monkeypatch, bad_at):
+    """The file is read in blocks (here 256 KiB ~ 2900 records); a parse error in a later block must still retract exactly
+    the reference's chunks: a block that does not end the file hands on floor((end - 1) / n_reads) * n_reads records and
+    keeps the rest for the next block, so nothing already classified has to be taken back."""
+    import ganon_b200.classify as K
+
+    monkeypatch.setattr(K, "BLOCK_BYTES", 256 << 10)
+    recs = [b"@r%05d\n%s\n+\n%s\n" % (i, b"ACGT" * 10, b"I" * 40) for i in range(10000)]
+    recs[bad_at] = b"@bad\nACGTXXXX\n+\nIIIIIIII\n"
+    f = str(tmp_path / "bad.fq")
+    open(f, "wb").write(b"".join(recs))
+    pre = str(tmp_path / "o")
+    assert cli.main(["-r", f, "-i", golden_dbs["synth"], "-o", pre, "-u", "--quiet", "--n-reads", "400"]) == 0
+    rep = dict(l.split("\t") for l in open(pre + ".rep").read().splitlines() if l.startswith("#"))
+    assert int(rep.get("#total_unclassified", 0)) + int(rep.get("#total_classified", 0)) == (bad_at - 1) // 400 * 400
+    assert len(open(pre + ".unc").read().splitlines()) == int(rep.get("#total_unclassified", 0))
+
+
+def test_file_format_follows_the_file_name_like_seqan3(golden_dbs, tmp_path):
+    """seqan3 picks the reader from the extension (compression suffix stripped): FASTQ content in a .fa file is a parse error
+    on the first record (nothing classified, the run goes on), an unknown extension ends the reference's run -- here an error."""
+    fq = open(os.path.join(SU.GOLDEN, "reads.se.fq"), "rb").read()
+    ok, wrong, unknown = str(tmp_path / "r.fastq"), str(tmp_path / "r.fa"), str(tmp_path / "r.txt")
+    for p in (ok, wrong, unknown):
+        open(p, "wb").write(fq)
+    pre = str(tmp_path / "o")
+    assert cli.main(["-r", ok, "-i", golden_dbs["synth"], "-o", pre, "-u", "--quiet"]) == 0
+    n_ok = len(open(pre + ".rep").read().splitlines())
+    assert n_ok > 2
+    assert cli.main(["-r", wrong + "," + ok, "-i", golden_dbs["synth"], "-o", pre + "2", "-u", "--quiet"]) == 0
+    assert open(pre + "2.rep").read() == open(pre + ".rep").read()  # the mis-named file contributes nothing, the next one is read
+    assert cli.main(["-r", unknown, "-i", golden_dbs["synth"], "-o", pre + "3", "-u", "--quiet"]) != 0
