@@ -1024,6 +1024,7 @@ def build_leg(dev, n_targets=256, genome_len=1_000_000):
     n_bp = n_targets * (genome_len // 80 * 80)
     common = ["--input-file", tab, "--kmer-size", "19", "--window-size", "31", "--max-fp", "0.05", "--hash-functions", "4", "--verbose"]
     out_gpu, out_ref = os.path.join(d, "gpu.ibf"), os.path.join(d, "ref.ibf")
+    os.makedirs(os.path.join(d, "tmp_gpu"), exist_ok=True)  # both builders want an existing folder
     t0 = time.perf_counter()
     pg = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "ganon-build")] + common + ["--output-file", out_gpu, "--tmp-output-folder", os.path.join(d, "tmp_gpu") + "/", "--device", str(dev)],
                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)

@@ -2571,7 +2571,9 @@ int BatchCtx::finish_level_device(size_t li, unsigned long long *rep, bool fetch
     done             = false;
     LevelRt       &L = levels[li];
     const uint32_t n = n_reads;
-    if (!L.device_finish || !tuples_on_device || max_hashes_ub > 4096 || n_tuples_dev >= 0xFFFFFFFFull)
+    // (the device evaluates --fpr-query with CUDA's lgamma / exp / pow, trusted inside the guard band up to 4096 minimisers:
+    // longer reads take the host stage only when --fpr-query is in use)
+    if (!L.device_finish || !tuples_on_device || (max_hashes_ub > 4096 && L.fpr_query < 1.0) || n_tuples_dev >= 0xFFFFFFFFull)
         return GNB_OK;
     const bool first = li == 0, last = li + 1 == levels.size();
     LevelOut  &O     = lv[li];
