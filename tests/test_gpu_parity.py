@@ -971,3 +971,25 @@ def test_file_format_follows_the_file_name_like_seqan3(golden_dbs, tmp_path):
     assert cli.main(["-r", wrong + "," + ok, "-i", golden_dbs["synth"], "-o", pre + "2", "-u", "--quiet"]) == 0
     assert open(pre + "2.rep").read() == open(pre + ".rep").read()  # the mis-named file contributes nothing, the next one is read
     assert cli.main(["-r", unknown, "-i", golden_dbs["synth"], "-o", pre + "3", "-u", "--quiet"]) != 0
+
+
+def test_long_reads_finish_on_the_device_when_fpr_query_is_off(golden_dbs):
+    """Reads of tens of thousands of minimisers (long-read data) stay on K4 unless --fpr-query needs the device's libm-style
+    evaluation (trusted up to 4096 minimisers): same result as the host stage; with --fpr-query the level goes to the host."""
+    rng = np.random.default_rng(31)
+    reads = b"".join(b"@long%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(list(b"ACGT"), size=n).astype(np.uint8)), b"I" * n) for i, n in enumerate((60_000, 150, 120_000, 9_000)))
+    db = Database.open(golden_dbs["synth"])
+    out = {}
+    for mode, fpr in (("device", 1.0), ("host", 1.0), ("device_fpr", 1e-3)):
+        if mode == "host":
+            os.environ["GANON_B200_HOST_FINISH"] = "1"
+        try:
+            s = Session([db], [0.0], [1.0], [fpr], output_all=True, output_unclassified=True)
+            r = s.classify(reads, final=True)
+            out[mode] = (sorted(result_text(r, "all").decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), s.report(), r.levels_on_device, max(r.n_hashes[i] for i in range(4)))
+            s.close()
+        finally:
+            os.environ.pop("GANON_B200_HOST_FINISH", None)
+    assert out["device"][4] > 10_000
+    assert out["device"][3] == 1 and out["host"][3] == 0 and out["device_fpr"][3] == 0
+    assert out["device"][:3] == out["host"][:3] and out["device"][0]
