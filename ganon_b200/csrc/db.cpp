@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
+#include <functional>
 #include <memory>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -111,12 +112,14 @@ int read_ibf_body(FileReader &f, IbfHost &ibf, int shard, int n_shards, cudaStre
     const uint64_t n_bits = f.get<uint64_t>();
     if (!f.ok)
         return fail(GNB_ERR_IO, "truncated IBF header");
-    if (width != 1 || ibf.bin_words == 0 || ibf.technical_bins != ibf.bin_words * 64 || ibf.bins > ibf.technical_bins ||
-        n_bits != ibf.technical_bins * ibf.bin_size || ibf.hash_funs < 1 || ibf.hash_funs > 5 || ibf.bin_size == 0 ||
-        ibf.hash_shift != (uint64_t)__builtin_clzll(ibf.bin_size))
+    // (untrusted file: the products are checked for overflow before they are compared with anything)
+    uint64_t tech_bits = 0, want_bits = 0;
+    if (width != 1 || ibf.bin_words == 0 || ibf.bin_size == 0 || __builtin_mul_overflow(ibf.bin_words, (uint64_t)64, &tech_bits) || ibf.technical_bins != tech_bits ||
+        ibf.bins > ibf.technical_bins || __builtin_mul_overflow(ibf.technical_bins, ibf.bin_size, &want_bits) || n_bits != want_bits || ibf.hash_funs < 1 ||
+        ibf.hash_funs > 5 || ibf.hash_shift != (uint64_t)__builtin_clzll(ibf.bin_size))
         return fail(GNB_ERR_FORMAT, "inconsistent interleaved_bloom_filter header");
-    const uint64_t n_words = (n_bits + 63) >> 6;
-    if (f.pos + n_words * 8 > f.size)
+    const uint64_t n_words = n_bits / 64 + (n_bits % 64 ? 1 : 0);
+    if (f.pos > f.size || n_words > (f.size - f.pos) / 8)
         return fail(GNB_ERR_IO, "truncated IBF payload");
     ibf.w0 = ibf.bin_words * (uint64_t)shard / (uint64_t)n_shards;
     ibf.w1 = ibf.bin_words * (uint64_t)(shard + 1) / (uint64_t)n_shards;
@@ -363,23 +366,43 @@ static int open_impl(const char *path, int is_hibf, int device, int shard, int n
 
     const size_t pinned_bytes = 64u << 20;
     void        *pinned[2]    = {nullptr, nullptr};
-    cudaEvent_t  ev[2];
-    cudaStream_t st;
+    cudaEvent_t  ev[2]        = {nullptr, nullptr};
+    cudaStream_t st           = nullptr;
+    bool         cleaned      = false;
+    auto cleanup = [&]() {
+        if (cleaned)
+            return;
+        cleaned = true;
+        if (st)
+            cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; ++i)
+        {
+            if (pinned[i])
+                cudaFreeHost(pinned[i]);
+            if (ev[i])
+                cudaEventDestroy(ev[i]);
+        }
+        if (st)
+            cudaStreamDestroy(st);
+    };
+    // every exit path below releases the staging resources and, through gnb_db_free, whatever the handle already holds
+    struct Guard
+    {
+        std::function<void()> fn;
+        std::unique_ptr<gnb_db> &db;
+        ~Guard()
+        {
+            fn();
+            if (db)
+                gnb_db_free(db.release());
+        }
+    } guard{cleanup, db};
     GNB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i)
     {
         GNB_CUDA(cudaMallocHost(&pinned[i], pinned_bytes));
         GNB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     }
-    auto cleanup = [&]() {
-        cudaStreamSynchronize(st);
-        for (int i = 0; i < 2; ++i)
-        {
-            cudaFreeHost(pinned[i]);
-            cudaEventDestroy(ev[i]);
-        }
-        cudaStreamDestroy(st);
-    };
     int rc = GNB_OK;
     if (!is_hibf)
     {
@@ -474,7 +497,7 @@ static int open_impl(const char *path, int is_hibf, int device, int shard, int n
             rc = read_ibf_body(f, db->ibfs[i], 0, 1, st, pinned, ev, pinned_bytes);
         auto read_vv = [&](std::vector<std::vector<int64_t>> &vv) {
             uint64_t n = f.get<uint64_t>();
-            if (!f.ok || n > f.size)
+            if (!f.ok || n > (f.size - std::min(f.size, f.pos)) / 8)
             {
                 rc = fail(GNB_ERR_FORMAT, "truncated hibf tables");
                 return;
@@ -483,7 +506,7 @@ static int open_impl(const char *path, int is_hibf, int device, int shard, int n
             for (auto &v : vv)
             {
                 uint64_t m = f.get<uint64_t>();
-                if (!f.ok || m > f.size)
+                if (!f.ok || m > (f.size - std::min(f.size, f.pos)) / 8)
                 {
                     rc = fail(GNB_ERR_FORMAT, "truncated hibf tables");
                     return;
