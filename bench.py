@@ -1095,6 +1095,15 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
            "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
     mh = re.search(r"host pipeline \(s\): ([^\n]*)", pr.stderr)
     out["host_pipeline_s"] = mh.group(1) if mh else None
+    if os.environ.get("GANON_B200_BENCH_CLI_VARIANTS"):
+        # diagnosis aid: the same command under other host settings
+        out["variants"] = {}
+        for tag, env in (("io_threads_4", {"GANON_B200_IO_THREADS": "4"}), ("io_threads_8", {"GANON_B200_IO_THREADS": "8"}), ("sync_block", {"GANON_B200_SYNC": "block"}),
+                         ("block_256MiB", {"GANON_B200_BLOCK_BYTES": str(256 << 20)})):
+            pv = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, **env))
+            mv = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pv.stderr)
+            mp = re.search(r"host pipeline \(s\): ([^\n]*)", pv.stderr)
+            out["variants"][tag] = {"classify_s": float(mv.group(1)) if mv else None, "host_pipeline_s": mp.group(1) if mp else None}
     # the same reads as ordinary single-member gzip files (what sequencers / archives deliver): the library inflates them
     # with all host threads (csrc/gzstream.cpp)
     try:

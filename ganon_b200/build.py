@@ -423,7 +423,7 @@ class GpuBackend:
     def file_hashes(self, path: str, k: int, w: int, min_length: int):
         """count_hashes of one file inside the library: native reader (plain / gzip), K2 in segments, sort + unique in
         HBM.  Returns (distinct hashes or None on a parse error, n_sequences, n_skipped, n_bases)."""
-        h, st = self._c.build_file_hashes(path, k, w, min_length, device=self.device)
+        h, st = self._c.build_file_hashes(path, k, w, min_length, device=self.device, io_threads=2)
         return h, int(st.n_sequences), int(st.n_skipped), int(st.n_bases)
 
     def create(self, n_bins: int, bin_size_bits: int, hash_functions: int, k: int, w: int) -> None:
@@ -479,11 +479,26 @@ def run_build(cfg: GanonBuildConfig, backend=None) -> bool:
         min_files: Dict[str, str] = {}
         n_seq = n_skipped = n_bp = 0
         native = hasattr(be, "file_hashes")
+        results = None
+        pool = None
+        if native:
+            # files are independent: several host threads read and index them while the device hashes others (the library
+            # keeps per-call buffers and streams); results are consumed in input order, at most 64 files ahead
+            from concurrent.futures import ThreadPoolExecutor
+
+            todo = [f for files in targets.values() for f in files]
+            pool = ThreadPoolExecutor(max(1, min(8, cfg.threads if cfg.threads > 1 else (os.cpu_count() or 1))))
+
+            def windowed():
+                for a in range(0, len(todo), 64):
+                    yield from pool.map(lambda p: be.file_hashes(p, cfg.kmer_size, cfg.window_size, cfg.min_length), todo[a : a + 64])
+
+            results = windowed()
         for target, files in targets.items():
             parts = []
             for f in files:
                 if native:
-                    u, ns, nk, nb = be.file_hashes(f, cfg.kmer_size, cfg.window_size, cfg.min_length)
+                    u, ns, nk, nb = next(results)
                     n_seq += ns
                     n_skipped += nk
                     n_bp += nb
@@ -515,6 +530,8 @@ def run_build(cfg: GanonBuildConfig, backend=None) -> bool:
                         p.tofile(fh)
             else:
                 hashes[target] = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
+        if pool is not None:
+            pool.shutdown()
         params = choose_ibf_params(counts, cfg.max_fp, cfg.filter_size, cfg.hash_functions, cfg.mode)
         if params.n_bins == 0:
             print("No valid sequences to build", file=sys.stderr)

@@ -7,8 +7,11 @@
 // A sequence shorter than the window gets a window of its own length (seqan3 minimiser.hpp:298-299), one shorter than k
 // has no k-mer.  A parse error drops the file's hashes (GanonBuild.cpp:241-245) but keeps the sequence counts.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -28,13 +31,9 @@ using namespace gnb;
 struct gnb_hash_set
 {
     int       device = 0;
-    uint64_t *h = nullptr; // page-locked host copy of the distinct hashes (ascending)
+    uint64_t *h = nullptr; // host copy of the distinct hashes (ascending)
     uint64_t  n = 0;
-    ~gnb_hash_set()
-    {
-        if (h)
-            cudaFreeHost(h);
-    }
+    ~gnb_hash_set() { free(h); }
 };
 
 namespace
@@ -72,11 +71,36 @@ struct DevMem
     }
 };
 
+// Device and host buffers of one gnb_build_file_hashes call; finished calls hand them to the next one (a build makes one
+// call per input file, possibly from several host threads at once: allocations and the zeroing of a fresh 256 MiB host buffer
+// would otherwise dominate small genomes).
 struct Builder
 {
-    uint32_t k, w;
+    int      device = 0;
+    uint32_t k = 0, w = 0;
+    cudaStream_t st = nullptr;
     DevMem   d_blk, d_off, d_len, d_cnt, d_hoff, d_tmp, d_all, d_sorted, d_uniq, d_n;
     uint64_t n_all = 0;
+    std::unique_ptr<char[]> host; // file block (not zero-initialised)
+    size_t   host_cap = 0;
+    ~Builder()
+    {
+        if (st)
+            cudaStreamDestroy(st);
+    }
+    int ensure_host(size_t bytes, size_t keep)
+    {
+        if (bytes <= host_cap)
+            return GNB_OK;
+        std::unique_ptr<char[]> nb(new (std::nothrow) char[bytes]);
+        if (!nb)
+            return fail(GNB_ERR_LIMIT, "out of host memory for the file block");
+        if (keep)
+            memcpy(nb.get(), host.get(), keep);
+        host.swap(nb);
+        host_cap = bytes;
+        return GNB_OK;
+    }
 
     // K2 over segments (off / len relative to the block text already in d_blk) with window w_eff; appends to d_all
     int hash_segments(const std::vector<uint32_t> &off, const std::vector<uint32_t> &len, uint32_t w_eff)
@@ -90,27 +114,55 @@ struct Builder
             GNB_TRY(d_cnt.ensure(n * 4));
             GNB_TRY(d_hoff.ensure((n + 1) * 8));
             GNB_TRY(d_tmp.ensure(scan_tmp_bytes((uint32_t)n)));
-            GNB_CUDA(cudaMemcpy(d_off.p, off.data() + done, n * 4, cudaMemcpyHostToDevice));
-            GNB_CUDA(cudaMemcpy(d_len.p, len.data() + done, n * 4, cudaMemcpyHostToDevice));
+            GNB_CUDA(cudaMemcpyAsync(d_off.p, off.data() + done, n * 4, cudaMemcpyHostToDevice, st));
+            GNB_CUDA(cudaMemcpyAsync(d_len.p, len.data() + done, n * 4, cudaMemcpyHostToDevice, st));
             launch_minimisers(d_blk.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w_eff, 0, d_cnt.as<uint32_t>(),
-                              nullptr, nullptr, nullptr, nullptr, 0);
-            launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
+                              nullptr, nullptr, nullptr, nullptr, st);
+            launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, st);
             uint64_t total = 0;
-            GNB_CUDA(cudaMemcpy(&total, d_hoff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost));
+            GNB_CUDA(cudaMemcpyAsync(&total, d_hoff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaStreamSynchronize(st));
             if (total)
             {
                 GNB_TRY(d_all.ensure((n_all + total) * 8, true, n_all * 8));
                 // the write pass places read i at hash_off[i]: hand it the tail of d_all as its output array
                 launch_minimisers(d_blk.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w_eff, 1, nullptr,
-                                  d_hoff.as<uint64_t>(), d_all.as<uint64_t>() + n_all, nullptr, nullptr, 0);
+                                  d_hoff.as<uint64_t>(), d_all.as<uint64_t>() + n_all, nullptr, nullptr, st);
                 n_all += total;
             }
+            GNB_CUDA(cudaStreamSynchronize(st)); // off / len are reused by the next piece
             GNB_CUDA(cudaGetLastError());
             done += n;
         }
         return GNB_OK;
     }
 };
+std::mutex                            g_pool_mu;
+std::vector<std::unique_ptr<Builder>> g_pool;
+
+std::unique_ptr<Builder> take_builder(int device)
+{
+    {
+        std::lock_guard<std::mutex> l(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i]->device == device)
+            {
+                std::unique_ptr<Builder> b = std::move(g_pool[i]);
+                g_pool.erase(g_pool.begin() + (long)i);
+                return b;
+            }
+    }
+    std::unique_ptr<Builder> b(new Builder);
+    b->device = device;
+    return b;
+}
+
+void give_builder(std::unique_ptr<Builder> b)
+{
+    std::lock_guard<std::mutex> l(g_pool_mu);
+    if (g_pool.size() < 16)
+        g_pool.push_back(std::move(b));
+}
 } // namespace
 
 extern "C" int gnb_build_file_hashes(int device, const char *path, uint32_t k, uint32_t w, uint64_t min_length, int io_threads, gnb_hash_set **out,
@@ -125,11 +177,30 @@ extern "C" int gnb_build_file_hashes(int device, const char *path, uint32_t k, u
     auto        src = open_byte_source(path, io_threads, err);
     if (!src)
         return fail(GNB_ERR_IO, err);
-    Builder B;
-    B.k = k;
-    B.w = w;
-    size_t            block = 256u << 20;
-    std::vector<char> buf(block);
+    std::unique_ptr<Builder> Bp = take_builder(device);
+    struct Return
+    {
+        std::unique_ptr<Builder> &b;
+        ~Return() { give_builder(std::move(b)); }
+    } give_back{Bp};
+    Builder &B = *Bp;
+    B.k     = k;
+    B.w     = w;
+    B.n_all = 0;
+    if (!B.st)
+        GNB_CUDA(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
+    // block size: the whole file when it is a small plain one, else 256 MiB (grown for longer records)
+    size_t block = 256u << 20;
+    if (!src->is_gzip() && src->size() + 64 < block)
+        block = (size_t)src->size() + 64;
+    GNB_TRY(B.ensure_host(block, 0));
+    struct
+    {
+        Builder &B;
+        size_t   n;
+        char    *data() { return B.host.get(); }
+        size_t   size() const { return n; }
+    } buf{B, block};
     size_t            have = 0;
     bool              eof = false, parse_error = false;
     RecTable          t;
@@ -159,7 +230,8 @@ extern "C" int gnb_build_file_hashes(int device, const char *path, uint32_t k, u
         {
             if (buf.size() >= (1ull << 31) - (1u << 20))
                 return fail(GNB_ERR_LIMIT, "a single sequence record does not fit a 2 GiB block");
-            buf.resize(std::min<size_t>(buf.size() * 2, (1ull << 31) - (1u << 20)));
+            buf.n = std::min<size_t>(buf.size() * 2, (1ull << 31) - (1u << 20));
+            GNB_TRY(B.ensure_host(buf.n, have));
             continue;
         }
         // ---- segments of this block's records ----
@@ -196,9 +268,9 @@ extern "C" int gnb_build_file_hashes(int device, const char *path, uint32_t k, u
         {
             // block text, then the reader's side buffer (sequences assembled from wrapped lines): offsets >= have point there
             GNB_TRY(B.d_blk.ensure(have + t.aux.size() + 64));
-            GNB_CUDA(cudaMemcpy(B.d_blk.p, buf.data(), have, cudaMemcpyHostToDevice));
+            GNB_CUDA(cudaMemcpyAsync(B.d_blk.p, buf.data(), have, cudaMemcpyHostToDevice, B.st));
             if (!t.aux.empty())
-                GNB_CUDA(cudaMemcpy(B.d_blk.as<char>() + have, t.aux.data(), t.aux.size(), cudaMemcpyHostToDevice));
+                GNB_CUDA(cudaMemcpyAsync(B.d_blk.as<char>() + have, t.aux.data(), t.aux.size(), cudaMemcpyHostToDevice, B.st));
             GNB_TRY(B.hash_segments(off, len, w));
             // short sequences: grouped by length, each group with its own (clamped) window
             std::vector<size_t> order(s_off.size());
@@ -240,15 +312,19 @@ extern "C" int gnb_build_file_hashes(int device, const char *path, uint32_t k, u
         GNB_TRY(B.d_uniq.ensure(B.n_all * 8));
         GNB_TRY(B.d_n.ensure(8));
         GNB_TRY(B.d_tmp.ensure(unique_tmp_bytes(B.n_all)));
-        launch_sort_unique(B.d_all.as<uint64_t>(), B.d_sorted.as<uint64_t>(), B.d_uniq.as<uint64_t>(), B.n_all, B.d_n.as<unsigned long long>(), B.d_tmp.p, B.d_tmp.cap, 0);
+        launch_sort_unique(B.d_all.as<uint64_t>(), B.d_sorted.as<uint64_t>(), B.d_uniq.as<uint64_t>(), B.n_all, B.d_n.as<unsigned long long>(), B.d_tmp.p, B.d_tmp.cap, B.st);
         unsigned long long nu = 0;
-        GNB_CUDA(cudaMemcpy(&nu, B.d_n.p, 8, cudaMemcpyDeviceToHost));
+        GNB_CUDA(cudaMemcpyAsync(&nu, B.d_n.p, 8, cudaMemcpyDeviceToHost, B.st));
+        GNB_CUDA(cudaStreamSynchronize(B.st));
         GNB_CUDA(cudaGetLastError());
         hs->n = nu;
         if (nu)
         {
-            GNB_CUDA(cudaMallocHost((void **)&hs->h, nu * 8));
-            GNB_CUDA(cudaMemcpy(hs->h, B.d_uniq.p, nu * 8, cudaMemcpyDeviceToHost));
+            hs->h = static_cast<uint64_t *>(malloc(nu * 8));
+            if (!hs->h)
+                return fail(GNB_ERR_LIMIT, "out of host memory for the hash set");
+            GNB_CUDA(cudaMemcpyAsync(hs->h, B.d_uniq.p, nu * 8, cudaMemcpyDeviceToHost, B.st));
+            GNB_CUDA(cudaStreamSynchronize(B.st));
         }
     }
     S.n_unique = hs->n;
