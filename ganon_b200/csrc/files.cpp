@@ -24,6 +24,7 @@ namespace gnb
 {
 // session.cpp: how the session takes its blocks (bin-sharded runs with sliced ingest read only this rank's slice)
 void session_ingest_mode(const gnb_session *s, int *sliced, int *rank, int *n_ranks);
+int  set_blocking_waits(int on);
 
 namespace
 {
@@ -420,6 +421,11 @@ extern "C" int gnb_session_classify_files(gnb_session *s, uint32_t prefix_id, co
         return fail(GNB_ERR_ARG, "gnb_session_classify_files: batches are in flight, collect first");
     int sliced = 0, rank = 0, n_ranks = 1;
     session_ingest_mode(s, &sliced, &rank, &n_ranks);
+    struct BlockingWaits
+    {
+        int prev = set_blocking_waits(1);
+        ~BlockingWaits() { set_blocking_waits(prev); }
+    } blocking_waits;
     const bool paired = file2 && file2[0];
     auto       t_open = Clock::now();
     std::unique_ptr<BlockStream> st[2];

@@ -1167,13 +1167,13 @@ std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int thread
         err = "cannot stat " + path;
         return nullptr;
     }
-    if (threads <= 0)
-        threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     unsigned char magic[2] = {0, 0};
     const ssize_t got      = pread(fd, magic, 2, 0);
     if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
-        return std::unique_ptr<ByteSource>(new GzSource(fd, (uint64_t)st.st_size, threads));
-    return std::unique_ptr<ByteSource>(new PlainSource(fd, (uint64_t)st.st_size, threads));
+        return std::unique_ptr<ByteSource>(new GzSource(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)std::min(16u, hw)));
+    // page-cache copies: a few threads saturate them, more only take cores from the rest of the pipeline (measured: 4-8)
+    return std::unique_ptr<ByteSource>(new PlainSource(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)std::min(6u, std::max(2u, hw / 2))));
 }
 
 } // namespace gnb

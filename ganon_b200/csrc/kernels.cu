@@ -1152,7 +1152,14 @@ __global__ void __launch_bounds__(K3_WARPS * 32, 2)
 #pragma unroll
         for (int j = 0; j < NP; ++j)
             P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0;
-        if (v0)
+        // With G > 1 the G lanes of an item would each hash the same 4 x H (minimiser, hash function) pairs of a block: 64-bit
+        // multiplies that made up half of the kernel's instructions (ncu, round 2: 1050 warp-instructions per block, issue
+        // slots 49 % busy at 4 warps per scheduler).  Instead every pair is hashed by ONE lane of the group and handed round
+        // with shuffles inside the group (all lanes of a group share the item, hence the trip count of the loop below; the
+        // loop is entered by the whole group and only the loads depend on the lane's columns).
+        constexpr int      PAIRS = 4 * H, PER = (PAIRS + G - 1) / G;
+        const uint32_t     gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(uint32_t)(G - 1)));
+        if (G > 1 ? n != 0 : v0)
         {
             // the four minimisers of the next block are fetched while the rows of the current one are in flight
             uint64_t xn[4];
@@ -1169,6 +1176,17 @@ __global__ void __launch_bounds__(K3_WARPS * 32, 2)
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     xn[q] = (m + 4 + q) < n ? ldg_u64(hashes + h0 + m + 4 + q) : 0;
+                uint64_t mine[PER]; // word offsets of the rows this lane hashed for its group
+                if (G > 1)
+                {
+#pragma unroll
+                    for (int j = 0; j < PER; ++j)
+                    {
+                        const uint32_t pr = sub + (uint32_t)j * G, q = pr / H, i = pr % H;
+                        const uint64_t x  = q == 0 ? xc[0] : q == 1 ? xc[1] : q == 2 ? xc[2] : xc[3];
+                        mine[j]           = pr < (uint32_t)PAIRS ? ibf_row(x, ibf_seed(i), hash_shift, bin_size) * row_words : 0;
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                 {
@@ -1177,10 +1195,22 @@ __global__ void __launch_bounds__(K3_WARPS * 32, 2)
 #pragma unroll
                     for (int i = 0; i < H; ++i)
                     {
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (ok)
+                        uint64_t off;
+                        if (G > 1)
                         {
-                            const uint64_t *p = lane_base + ibf_row(x, ibf_seed(i), hash_shift, bin_size) * row_words;
+                            constexpr int dummy = 0;
+                            (void)dummy;
+                            const int      pr = q * H + i;
+                            const uint64_t mv = mine[pr / G];
+                            const uint32_t lo = __shfl_sync(gmask, (uint32_t)mv, pr % G, G), hi = __shfl_sync(gmask, (uint32_t)(mv >> 32), pr % G, G);
+                            off               = ((uint64_t)hi << 32) | lo;
+                        }
+                        else
+                            off = ibf_row(x, ibf_seed(i), hash_shift, bin_size) * row_words;
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (ok && v0)
+                        {
+                            const uint64_t *p = lane_base + off;
                             if (al)
                                 v = ldg_stream16(p);
                             else

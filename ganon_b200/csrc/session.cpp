@@ -53,9 +53,13 @@ inline void trace_mark(const void *ctx, const char *what)
 // Host wait for a stream.  Default: cudaStreamSynchronize (spins: lowest latency).  GANON_B200_SYNC=block: wait on an
 // event created with cudaEventBlockingSync, so that the waiting thread sleeps -- several ranks per node with a few
 // threads each would otherwise keep more spinning threads than the host has cores.
+// gnb_session_classify_files turns blocking waits on for its duration unless GANON_B200_SYNC=spin says otherwise: its reader,
+// inflater and writer threads need the cores the spinning waits would burn (measured on a 16-core host, c2 file to file:
+// 33.6 -> 51 M reads/s).
+std::atomic<int> g_sync_block{[] { const char *e = getenv("GANON_B200_SYNC"); return e && e[0] == 'b' ? 1 : 0; }()};
 inline cudaError_t stream_wait(cudaStream_t st)
 {
-    static const bool block = [] { const char *e = getenv("GANON_B200_SYNC"); return e && e[0] == 'b'; }();
+    const bool block = g_sync_block.load(std::memory_order_relaxed) != 0;
     if (!block)
         return cudaStreamSynchronize(st);
     thread_local cudaEvent_t ev     = nullptr;
@@ -3462,6 +3466,14 @@ extern "C" int gnb_session_classify(gnb_session *s, uint32_t prefix_id, const ch
 
 namespace gnb
 {
+// blocking host waits on / off (files.cpp); returns the previous setting.  GANON_B200_SYNC=spin keeps spinning.
+int set_blocking_waits(int on)
+{
+    static const bool pinned_spin = [] { const char *e = getenv("GANON_B200_SYNC"); return e && e[0] == 's'; }();
+    if (pinned_spin)
+        return g_sync_block.load();
+    return g_sync_block.exchange(on);
+}
 void session_ingest_mode(const gnb_session *s, int *sliced, int *rank, int *n_ranks)
 {
     *sliced  = s->sharded() && s->sliced_ingest ? 1 : 0;

@@ -1,13 +1,12 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "long_reads or build_file_hashes or several_filters or paged" > gpurun_out/pytest_new.log 2>&1
-echo "pytest new rc=$?"; tail -5 gpurun_out/pytest_new.log | cut -c1-400
-python bench.py --workload tiny --build --steps 3 --no-cpu-baseline > gpurun_out/bench_tiny_build.json 2> gpurun_out/bench_tiny_build.err
+./tools/rowgather_bench > gpurun_out/rowgather.jsonl 2>&1; cat gpurun_out/rowgather.jsonl
+python bench.py --workload c2 --cli --build --steps 8 --no-cpu-baseline > gpurun_out/bench_c2_cli.json 2> gpurun_out/bench_c2_cli.err
 python - <<'PY'
 import json
-d = json.loads(open("gpurun_out/bench_tiny_build.json").read().strip().splitlines()[-1])
+d = json.loads(open("gpurun_out/bench_c2_cli.json").read().strip().splitlines()[-1])
+c = d.get("cli", {})
+print("cli", c.get("reads_per_s"), c.get("classify_s"), c.get("host_pipeline_s")); print("gz", c.get("gz", {}).get("reads_per_s"), c.get("gz", {}).get("host_pipeline_s"))
 print("build", d.get("extra", {}).get("ganon_build"))
 PY
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_hibf_count_narrow" -c 1 -o gpurun_out/r02_k3h_round0_full python bench.py --workload c4 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_k3h.log 2>&1
-tail -2 gpurun_out/ncu_k3h.log | cut -c1-300
