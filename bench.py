@@ -357,6 +357,10 @@ TRAFFIC_CAPTURES = {
 }
 
 
+# useful GB/s of a pure random row gather by row width (bytes), measured with tools/rowgather_bench.cu on B200
+ROW_GATHER_GBPS = {8: 334.0, 32: 1168.5, 64: 2334.8, 128: 4652.3, 256: 6389.4, 512: 6799.0}
+
+
 def traffic_for(wl_name, reads_per_launch):
     cap = TRAFFIC_CAPTURES.get(wl_name)
     if cap and cap[1] == reads_per_launch:
@@ -499,6 +503,7 @@ def measure(args, wl_name, ctx, cpu, cli, em, paged=False):
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
+    hibf_rounds = sessions[(args.warmup + args.steps - 1) % pool].hibf_rounds() if wl.get("hibf") else None
     if world > 1:
         t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -662,6 +667,18 @@ def measure(args, wl_name, ctx, cpu, cli, em, paged=False):
             "db_file_check": file_check,
             "setup_s": t_setup,
         }
+        if hibf_rounds:
+            # an HIBF traversal gathers rows of very different widths; the copy peak is the wrong yardstick for narrow rows:
+            # tools/rowgather_bench.cu measures what random rows of each width can reach on this GPU
+            rowb = [wl["top_bins"] // 8, wl["child_bins"] // 8, wl["grand_bins"] // 8]
+            line["roofline"]["rounds"] = []
+            for i, (ms_r, by_r, it_r) in enumerate(hibf_rounds):
+                rb = rowb[min(i, len(rowb) - 1)]
+                gp = ROW_GATHER_GBPS.get(rb)
+                gb = by_r / 1e9 / (ms_r / 1e3) if ms_r > 0 else 0.0
+                line["roofline"]["rounds"].append({"round": i, "items": it_r, "row_bytes": rb, "ms": ms_r, "algorithmic_bytes": by_r, "achieved_GBps": gb,
+                                                   "row_gather_roofline_GBps": gp, "frac_of_row_gather_roofline": gb / gp if gp else None})
+            line["roofline"]["row_gather_roofline_source"] = "profiles/r02_rowgather_bench.jsonl (tools/rowgather_bench.cu on B200: random rows from 32 GiB, 16 loads in flight per lane)"
         if em_line is not None:
             line["em_reassign"] = em_line
         if cli_line is not None:

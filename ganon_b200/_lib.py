@@ -195,6 +195,7 @@ SYMBOLS = {
     "gnb_session_level_tuples_device": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gnb_session_set_level_tuples_device": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64]),
     "gnb_session_finish_level_device": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "gnb_session_hibf_rounds": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint32)]),
     "gnb_session_staged_timings": (C.c_int, [_P, C.POINTER(BatchResult)]),
     "gnb_reads_file_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "gnb_reads_file_read": (C.c_int64, [_P, _P, C.c_uint64]),

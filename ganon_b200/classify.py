@@ -409,6 +409,14 @@ class Session:
     def finish_level_device(self, level: int, prefix_id: int = 0) -> None:
         check(_lib.lib().gnb_session_finish_level_device(self._h, level, prefix_id))
 
+    def hibf_rounds(self):
+        """[(kernel ms, algorithmic bytes, items)] per traversal round of the last HIBF filter run (staged forms)."""
+        import numpy as np
+
+        ms, by, it, n = np.zeros(16, np.float32), np.zeros(16, np.uint64), np.zeros(16, np.uint64), C.c_uint32()
+        check(_lib.lib().gnb_session_hibf_rounds(self._h, 16, ms.ctypes.data, by.ctypes.data, it.ctypes.data, C.byref(n)))
+        return [(float(ms[i]), int(by[i]), int(it[i])) for i in range(min(16, n.value))]
+
     def staged_timings(self) -> BatchResult:
         res = BatchResult()
         check(_lib.lib().gnb_session_staged_timings(self._h, C.byref(res)))

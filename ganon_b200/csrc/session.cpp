@@ -493,6 +493,8 @@ struct BatchCtx
     bool                  d_counts_valid = false;
     uint64_t              hibf_bytes = 0;
     float                 hibf_ms = 0;
+    std::vector<float>    hibf_round_ms;    // traversal rounds of the last HIBF filter run: kernel time,
+    std::vector<uint64_t> hibf_round_bytes, hibf_round_items; // algorithmic bytes and worklist length
     std::vector<std::vector<PinnedVec<uint64_t>>> tuples; // [level][filter], sorted by (read, node)
     // K4: finishing stage on the device
     struct LevelOut
@@ -1829,6 +1831,9 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     const uint32_t n = n_reads;
     hibf_bytes = 0;
     hibf_ms    = 0;
+    hibf_round_ms.clear();
+    hibf_round_bytes.clear();
+    hibf_round_items.clear();
     // worklist of round 0 on the device: d_status[8..9] = item cursor of the seeding, d_status[10..11] = bytes of all rounds
     unsigned long long *d_seed  = reinterpret_cast<unsigned long long *>(d_status.as<uint32_t>() + 8);
     unsigned long long *d_bytes = reinterpret_cast<unsigned long long *>(d_status.as<uint32_t>() + 10);
@@ -1842,12 +1847,14 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
     GNB_CUDA(stream_wait(st));
     timing.d2h_bytes += 8;
-    unsigned long long tuples_before = 0;
+    unsigned long long tuples_before = 0, round_bytes_sum = 0;
     DevBuf *cur = &d_items_a, *nxt = &d_items_b;
     for (size_t round = 0; n_items; ++round)
     {
         const uint32_t lanes = round < F.round_lanes.size() ? F.round_lanes[round] : 0;
-        unsigned long long got_tuples = 0, got_items = 0;
+        unsigned long long got_tuples = 0, got_items = 0, bytes_so_far = 0;
+        const unsigned long long items_in = n_items;
+        float                    ms_round = 0;
         for (int attempt = 0; attempt < 3; ++attempt)
         {
             const uint64_t cap = d_tuples_a.cap / 8, icap = nxt->cap / sizeof(uint2);
@@ -1862,12 +1869,14 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
             launches += 1;
             GNB_CUDA(cudaMemcpyAsync(&got_tuples, d_cursor.p, 8, cudaMemcpyDeviceToHost, st));
             GNB_CUDA(cudaMemcpyAsync(&got_items, d_items_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            GNB_CUDA(cudaMemcpyAsync(&bytes_so_far, d_bytes, 8, cudaMemcpyDeviceToHost, st));
             GNB_CUDA(stream_wait(st));
             GNB_CUDA(cudaGetLastError());
-            timing.d2h_bytes += 16;
+            timing.d2h_bytes += 24;
             float ms1 = 0;
             cudaEventElapsedTime(&ms1, ev[4], ev[5]);
             hibf_ms += ms1;
+            ms_round = ms1;
             if (got_tuples <= cap && got_items <= icap)
                 break;
             // a buffer was too small: the exact need is known now.  Tuples of earlier rounds must survive the growth.
@@ -1884,6 +1893,11 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
             if (got_items > icap)
                 GNB_TRY(nxt->ensure(got_items * sizeof(uint2)));
         }
+        // per-round record (measurement): time of the attempt that fitted, algorithmic bytes of the round, items in
+        hibf_round_ms.push_back(ms_round);
+        hibf_round_bytes.push_back(bytes_so_far - (hibf_round_bytes.empty() ? 0 : round_bytes_sum));
+        round_bytes_sum = bytes_so_far;
+        hibf_round_items.push_back(items_in);
         tuples_before = got_tuples;
         n_items       = got_items;
         std::swap(cur, nxt);
@@ -3355,6 +3369,24 @@ extern "C" int gnb_session_finish_level_device(gnb_session *s, uint32_t level, u
     {
         GNB_CUDA(cudaMemcpyAsync(c.h_read_level.data(), c.d_read_level.p, c.n_reads, cudaMemcpyDeviceToHost, c.st));
         GNB_CUDA(stream_wait(c.st));
+    }
+    return GNB_OK;
+}
+
+extern "C" int gnb_session_hibf_rounds(gnb_session *s, uint32_t cap, float *ms, uint64_t *bytes, uint64_t *items, uint32_t *n_rounds)
+{
+    if (!s || !n_rounds)
+        return fail(GNB_ERR_ARG, "gnb_session_hibf_rounds: bad arguments");
+    const BatchCtx &c = *s->slots[0];
+    *n_rounds         = (uint32_t)c.hibf_round_ms.size();
+    for (uint32_t i = 0; i < *n_rounds && i < cap; ++i)
+    {
+        if (ms)
+            ms[i] = c.hibf_round_ms[i];
+        if (bytes)
+            bytes[i] = c.hibf_round_bytes[i];
+        if (items)
+            items[i] = c.hibf_round_items[i];
     }
     return GNB_OK;
 }

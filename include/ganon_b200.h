@@ -283,6 +283,9 @@ int gnb_session_run_level_device(gnb_session *s, uint32_t level);
 int gnb_session_level_tuples_device(gnb_session *s, uint32_t level, const uint64_t **dev_tuples, uint64_t *n);
 int gnb_session_set_level_tuples_device(gnb_session *s, uint32_t level, const uint64_t *dev_tuples, uint64_t n);
 int gnb_session_finish_level_device(gnb_session *s, uint32_t level, uint32_t prefix_id);
+/* Measurement: the traversal rounds of the last HIBF filter run of the staged forms (gnb_session_run_staged ...): kernel time,
+ * algorithmic bytes (sum over the round's (read, sub-IBF) items of n_hashes x h x row bytes) and worklist length per round. */
+int gnb_session_hibf_rounds(gnb_session *s, uint32_t cap, float *ms, uint64_t *bytes, uint64_t *items, uint32_t *n_rounds);
 /* device timings / byte counts of the staged batch so far (level-wise forms; the batch stays staged) */
 int gnb_session_staged_timings(gnb_session *s, gnb_batch_result *timings);
 

@@ -35,13 +35,17 @@ __global__ void __launch_bounds__(256) k_gather(const uint8_t *data, uint64_t n_
     const uint32_t lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     uint32_t acc = 0;
+    // one splitmix per (warp, group), then a 64-bit LCG per load and a fastrange multiply: the address arithmetic must stay
+    // far below the issue budget, or the benchmark measures the ALUs instead of the DRAM
+    uint64_t state = mix((warp << 8) ^ grp);
     for (uint32_t it = 0; it < iters; ++it)
     {
         uint4 v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
         {
-            const uint64_t row = mix((warp << 32) ^ ((uint64_t)it << 12) ^ ((uint64_t)j << 6) ^ grp) % n_rows;
+            state              = state * 6364136223846793005ull + 1442695040888963407ull;
+            const uint64_t row = __umul64hi(state, n_rows);
             const uint8_t *p   = data + row * ROW_BYTES + sub * 16;
             if (ROW_BYTES >= 16)
                 v[j] = ld16(p);
