@@ -139,3 +139,47 @@ def test_bytes_match_gzip_command_on_a_real_gzip_file(tmp_path, fastq):
     for threads, chunk in ((1, None), (4, 100000), (4, 30000)):
         got, err = read_all_with_chunk(str(p) + ".gz", threads, chunk)
         assert err is None and got == fastq
+
+
+def _bgzf(data: bytes, block: int = 65280) -> bytes:
+    """Real BGZF (htslib / bgzip / bcl2fastq layout): every member carries the 'BC' extra field with its compressed size and
+    the file ends with the empty end-of-file member."""
+    import struct
+
+    out = []
+    for a in list(range(0, len(data), block)) + [None]:
+        piece = b"" if a is None else data[a : a + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(piece) + co.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + body + struct.pack("<II", zlib.crc32(piece), len(piece)))
+    return b"".join(out)
+
+
+def test_bgzf_and_flush_points(tmp_path, fastq):
+    """BGZF with its extra fields and end-of-file member; streams with sync / full flush points (empty stored blocks,
+    byte-aligned restarts: what pigz and streaming writers emit); a header with name and comment."""
+    rng = np.random.default_rng(5)
+    (tmp_path / "real.bgzf.fq.gz").write_bytes(_bgzf(fastq[:3_000_000]))
+    for threads, chunk in ((4, None), (3, 30000), (2, 4096)):
+        got, err = read_all_with_chunk(tmp_path / "real.bgzf.fq.gz", threads, chunk)
+        assert err is None and got == fastq[:3_000_000]
+    for seed in range(4):
+        data = fastq[: 1_500_000 + 1000 * seed]
+        co = zlib.compressobj(int(rng.integers(1, 10)), zlib.DEFLATED, 31)
+        parts, pos = [], 0
+        while pos < len(data):
+            n = int(rng.integers(1, 200_000))
+            parts.append(co.compress(data[pos : pos + n]))
+            pos += n
+            if rng.random() < 0.5:
+                parts.append(co.flush(zlib.Z_FULL_FLUSH if rng.random() < 0.5 else zlib.Z_SYNC_FLUSH))
+        parts.append(co.flush())
+        z = b"".join(parts)
+        # a header with FNAME and FCOMMENT in place of the plain one
+        z = b"\x1f\x8b\x08\x18\x00\x00\x00\x00\x00\x03" + b"reads.fq\x00" + b"a comment\x00" + z[10:]
+        (tmp_path / "flush.gz").write_bytes(z)
+        assert zlib.decompress(z, 31) == data
+        for threads, chunk in ((4, 20000), (2, 4096), (4, None)):
+            got, err = read_all_with_chunk(tmp_path / "flush.gz", threads, chunk)
+            assert err is None and got == data, (seed, threads, chunk)
