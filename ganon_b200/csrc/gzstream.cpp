@@ -429,8 +429,16 @@ struct Chunk
     bool                  ran_out = false; // failed because the buffered data ended (not an error if the file goes on)
     std::string           err;
     std::vector<MemberEnd> ends;
-    std::vector<uint8_t>  bytes; // markers resolved
-    std::vector<std::pair<uint64_t, uint32_t>> crcs; // (length, crc) of the pieces between member ends
+};
+
+// a decoded chunk on its way to the consumer: symbols with markers, the 32 KiB history that resolves them
+struct Piece
+{
+    std::vector<uint16_t>  sym;
+    size_t                 n_out = 0;
+    std::vector<uint8_t>   window;
+    std::vector<MemberEnd> ends;
+    std::vector<std::pair<uint64_t, uint32_t>> crcs; // (length, crc) of the runs between member ends, filled by the consumer
 };
 
 // gzip member header (RFC 1952 2.3); in.pos must be byte aligned.  false = not a gzip header / truncated
@@ -824,7 +832,7 @@ inline void resolve_markers(const uint16_t *s, size_t n, const uint8_t *w, uint8
 class GzSource : public ByteSource
 {
   public:
-    GzSource(int fd, uint64_t size, int threads) : fd_(fd), size_(size), pool_(threads)
+    GzSource(int fd, uint64_t size, int threads) : fd_(fd), size_(size), pool_(threads), pool2_(std::max(1, std::min(threads, 8)))
     {
         chunk_bytes_ = 2u << 20;
         if (const char *e = getenv("GANON_B200_GZ_CHUNK"))
@@ -845,25 +853,30 @@ class GzSource : public ByteSource
     }
     bool     is_gzip() const override { return true; }
     uint64_t size() const override { return size_; }
-    int64_t  read(char *dst, size_t cap) override
+    // Markers are replaced HERE, by the consumer, straight into the caller's buffer (in parallel over the queued pieces):
+    // the decoded bytes are written once, where they are needed.  Only a piece that straddles the end of the caller's
+    // buffer goes through a side buffer.
+    int64_t read(char *dst, size_t cap) override
     {
         size_t got = 0;
+        if (carry_off_ < carry_.size())
+        {
+            const size_t n = std::min(cap, carry_.size() - carry_off_);
+            memcpy(dst, carry_.data() + carry_off_, n);
+            carry_off_ += n;
+            got = n;
+        }
         while (got < cap)
         {
-            if (cur_ == nullptr || cur_off_ == cur_->size())
+            std::vector<Piece> batch;
+            size_t             room = cap - got;
             {
                 std::unique_lock<std::mutex> l(mu_);
-                if (cur_)
-                {
-                    if (bytes_pool_.size() < 64)
-                        bytes_pool_.emplace_back(std::move(ready_.front()));
-                    ready_.pop_front();
-                    cur_ = nullptr;
-                    cv_.notify_all();
-                }
                 cv_.wait(l, [&] { return !ready_.empty() || finished_; });
                 if (ready_.empty())
                 {
+                    if (perr_.empty() && len_run_ != 0)
+                        perr_ = "gzip stream ends inside a member";
                     if (!perr_.empty())
                     {
                         err_ = perr_;
@@ -871,13 +884,82 @@ class GzSource : public ByteSource
                     }
                     break;
                 }
-                cur_     = &ready_.front();
-                cur_off_ = 0;
+                while (!ready_.empty() && batch.size() < 64 && (batch.empty() || ready_.front().n_out <= room))
+                {
+                    room -= std::min(room, ready_.front().n_out);
+                    queued_ -= ready_.front().n_out;
+                    batch.emplace_back(std::move(ready_.front()));
+                    ready_.pop_front();
+                }
+                cv_.notify_all();
             }
-            const size_t n = std::min(cap - got, cur_->size() - cur_off_);
-            memcpy(dst + got, cur_->data() + cur_off_, n);
-            got += n;
-            cur_off_ += n;
+            // where every piece goes: the caller's buffer, or (a first piece larger than the room left) the side buffer
+            std::vector<uint8_t *> where(batch.size());
+            size_t                 off = got;
+            bool                   to_carry = false;
+            for (size_t i = 0; i < batch.size(); ++i)
+            {
+                if (batch[i].n_out <= cap - off)
+                {
+                    where[i] = reinterpret_cast<uint8_t *>(dst) + off;
+                    off += batch[i].n_out;
+                }
+                else
+                {
+                    carry_.resize(batch[i].n_out);
+                    carry_off_ = 0;
+                    where[i]   = carry_.data();
+                    to_carry   = true;
+                }
+            }
+            pool2_.parallel_for(batch.size(), [&](size_t i) {
+                Piece               &pc = batch[i];
+                std::vector<uint8_t> lut;
+                resolve_markers(pc.sym.data() + kWindow, pc.n_out, pc.window.data(), where[i], lut);
+                uint64_t from = 0;
+                for (size_t m = 0; m <= pc.ends.size(); ++m)
+                {
+                    const uint64_t to = m < pc.ends.size() ? pc.ends[m].out_off : pc.n_out;
+                    pc.crcs.emplace_back(to - from, (uint32_t)crc32_z(0, where[i] + from, (size_t)(to - from)));
+                    from = to;
+                }
+            });
+            // trailers of the members that end in these pieces (sequential: crc32_combine)
+            for (auto &pc : batch)
+                for (size_t m = 0; m < pc.crcs.size(); ++m)
+                {
+                    crc_run_ = (uint32_t)crc32_combine(crc_run_, pc.crcs[m].second, (z_off_t)pc.crcs[m].first);
+                    len_run_ += pc.crcs[m].first;
+                    if (m < pc.ends.size())
+                    {
+                        if (crc_run_ != pc.ends[m].crc || (uint32_t)len_run_ != pc.ends[m].isize)
+                        {
+                            std::lock_guard<std::mutex> l(mu_);
+                            perr_ = "gzip CRC / length check failed";
+                        }
+                        crc_run_ = 0;
+                        len_run_ = 0;
+                    }
+                }
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                for (auto &pc : batch)
+                    if (sym_pool_.size() < 128)
+                        sym_pool_.emplace_back(std::move(pc.sym));
+                if (!perr_.empty())
+                {
+                    err_ = perr_;
+                    return GNB_ERR_IO; // never hand out bytes of a member that failed its check
+                }
+            }
+            got = off;
+            if (to_carry)
+            {
+                const size_t n = std::min(cap - got, carry_.size());
+                memcpy(dst + got, carry_.data(), n);
+                carry_off_ = n;
+                got += n;
+            }
         }
         return (int64_t)got;
     }
@@ -890,8 +972,6 @@ class GzSource : public ByteSource
         uint64_t    file_off  = 0;    // compressed bytes of the file before buf_
         uint64_t    start_bit = 0;    // where the next wave's first chunk starts, relative to buf_
         bool        at_header = true; // the very first chunk starts at the gzip header
-        uint32_t    crc_run = 0;      // CRC-32 of the current member so far
-        uint64_t    len_run = 0;
         std::vector<uint8_t> buf;
         uint64_t    buf_valid = 0; // compressed bytes in buf (without padding)
         bool        file_done = false;
@@ -940,12 +1020,15 @@ class GzSource : public ByteSource
             const uint64_t wave_end_bit  = wave_end_byte * 8;
             const size_t   n_chunks     = (size_t)std::max<uint64_t>(1, (wave_end_bit - start_bit + chunk_bytes_ * 8 - 1) / (chunk_bytes_ * 8));
             std::vector<Chunk> chunks(n_chunks);
-            for (auto &c : chunks)
-                if (!sym_pool_.empty())
-                {
-                    c.sym.swap(sym_pool_.back());
-                    sym_pool_.pop_back();
-                }
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                for (auto &c : chunks)
+                    if (!sym_pool_.empty())
+                    {
+                        c.sym.swap(sym_pool_.back());
+                        sym_pool_.pop_back();
+                    }
+            }
             chunks[0].start_bit = start_bit;
             chunks[0].found     = true;
             pool_.parallel_for(n_chunks - 1, [&](size_t k) {
@@ -1003,8 +1086,9 @@ class GzSource : public ByteSource
             if (need_more)
             {
                 look_ahead = look_ahead ? look_ahead * 2 : 2;
+                std::lock_guard<std::mutex> l(mu_);
                 for (auto &c : chunks)
-                    if (c.sym.capacity())
+                    if (c.sym.capacity() && sym_pool_.size() < 128)
                         sym_pool_.emplace_back(std::move(c.sym));
                 continue;
             }
@@ -1037,70 +1121,36 @@ class GzSource : public ByteSource
                 }
                 window_.swap(nw);
             }
-            // ---- markers -> bytes, CRC of the pieces between member ends (parallel) ----
-            pool_.parallel_for(chain.size(), [&](size_t k) {
-                Chunk          &c = chunks[chain[k]];
-                const uint16_t *s = c.sym.data() + kWindow;
-                const uint8_t  *w = win[k].data();
-                c.bytes = take_bytes_();
-                c.bytes.resize(c.n_out);
-                uint8_t *d = c.bytes.data();
-                std::vector<uint8_t> lut;
-                resolve_markers(s, c.n_out, w, d, lut);
-                uint64_t from = 0;
-                for (size_t m = 0; m <= c.ends.size(); ++m)
-                {
-                    const uint64_t to = m < c.ends.size() ? c.ends[m].out_off : c.n_out;
-                    c.crcs.emplace_back(to - from, (uint32_t)crc32_z(0, d + from, (size_t)(to - from)));
-                    from = to;
-                }
-            });
-            // ---- trailers, then hand the pieces over in order ----
-            for (size_t k = 0; k < chain.size() && err.empty(); ++k)
-            {
-                Chunk &c = chunks[chain[k]];
-                for (size_t m = 0; m < c.crcs.size(); ++m)
-                {
-                    crc_run = (uint32_t)crc32_combine(crc_run, c.crcs[m].second, (z_off_t)c.crcs[m].first);
-                    len_run += c.crcs[m].first;
-                    if (m < c.ends.size())
-                    {
-                        if (crc_run != c.ends[m].crc || (uint32_t)len_run != c.ends[m].isize)
-                        {
-                            err = "gzip CRC / length check failed";
-                            break;
-                        }
-                        crc_run = 0;
-                        len_run = 0;
-                    }
-                }
-            }
-            if (!err.empty())
-                break;
+            // ---- hand the chunks over in order; the consumer replaces the markers (read()) ----
             bool eos = false;
             for (size_t k = 0; k < chain.size(); ++k)
             {
                 Chunk &c = chunks[chain[k]];
                 eos |= c.eos;
-                if (c.bytes.empty())
+                if (c.n_out == 0 && c.ends.empty())
                     continue;
+                Piece pc;
+                pc.sym.swap(c.sym);
+                pc.n_out = c.n_out;
+                pc.window.swap(win[k]);
+                pc.ends.swap(c.ends);
                 std::unique_lock<std::mutex> l(mu_);
-                cv_.wait(l, [&] { return cancel_ || queued_bytes_() < max_queued_; });
+                cv_.wait(l, [&] { return cancel_ || queued_ < max_queued_; });
                 if (cancel_)
                     return;
-                ready_.emplace_back(std::move(c.bytes));
+                queued_ += pc.n_out;
+                ready_.emplace_back(std::move(pc));
                 cv_.notify_all();
             }
             start_bit = chunks[chain.back()].end_bit;
-            for (auto &c : chunks)
-                if (c.sym.capacity())
-                    sym_pool_.emplace_back(std::move(c.sym));
-            if (eos)
             {
-                if (len_run != 0)
-                    err = "gzip stream ends inside a member";
-                break;
+                std::lock_guard<std::mutex> l(mu_);
+                for (auto &c : chunks)
+                    if (c.sym.capacity() && sym_pool_.size() < 128)
+                        sym_pool_.emplace_back(std::move(c.sym));
             }
+            if (eos)
+                break;
             if (file_done && start_bit >= total_bits)
             {
                 err = "unexpected end of the gzip stream";
@@ -1112,42 +1162,24 @@ class GzSource : public ByteSource
         finished_ = true;
         cv_.notify_all();
     }
-    std::vector<uint8_t> take_bytes_()
-    {
-        std::lock_guard<std::mutex> l(mu_);
-        std::vector<uint8_t>        v;
-        if (!bytes_pool_.empty())
-        {
-            v.swap(bytes_pool_.back());
-            bytes_pool_.pop_back();
-        }
-        return v;
-    }
-    size_t queued_bytes_() const
-    {
-        size_t n = 0;
-        for (auto const &v : ready_)
-            n += v.size();
-        return n;
-    }
-
     int      fd_;
     uint64_t size_;
-    Pool     pool_;
+    Pool     pool_, pool2_; // producer (find + decode) / consumer (marker replacement + CRC)
     uint64_t chunk_bytes_;
     size_t   wave_chunks_;
     std::vector<uint8_t> window_;
     std::thread          producer_;
     std::mutex           mu_;
     std::condition_variable cv_;
-    std::deque<std::vector<uint8_t>> ready_;
-    std::vector<std::vector<uint8_t>>  bytes_pool_; // consumed buffers, reused (guarded by mu_)
-    std::vector<std::vector<uint16_t>> sym_pool_;   // symbol buffers of finished waves (producer thread only)
-    const std::vector<uint8_t>      *cur_ = nullptr;
-    size_t                           cur_off_ = 0;
-    size_t                           max_queued_ = 512u << 20;
-    bool                             finished_ = false, cancel_ = false;
-    std::string                      perr_;
+    std::deque<Piece>    ready_;
+    size_t               queued_ = 0, max_queued_ = 512u << 20; // output bytes waiting in ready_
+    std::vector<std::vector<uint16_t>> sym_pool_;                // symbol buffers for reuse (guarded by mu_)
+    std::vector<uint8_t> carry_;                                 // a piece that straddled the end of the caller's buffer
+    size_t               carry_off_ = 0;
+    uint32_t             crc_run_ = 0; // CRC-32 / length of the current member so far (consumer)
+    uint64_t             len_run_ = 0;
+    bool                 finished_ = false, cancel_ = false;
+    std::string          perr_;
 };
 
 } // namespace
