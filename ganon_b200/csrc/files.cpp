@@ -126,7 +126,6 @@ class BlockStream
                 b = nullptr;
             }
     }
-    bool        is_gzip() const { return src_->is_gzip(); }
     const char *ptr() const { return positional_ ? bufs_[cur_] : bufs_[cur_] + start_; }
     size_t      fill() const { return fill_; }
     bool        eof() const { return eof_; }
