@@ -50,9 +50,10 @@ inline void trace_mark(const void *ctx, const char *what)
     fprintf(stderr, "[gnb-trace] %p %-18s %9.3f ms\n", ctx, what, ms_since(t0));
 }
 
-// Host wait for a stream.  Default: cudaStreamSynchronize (spins: lowest latency).  GANON_B200_SYNC=block: wait on an
-// event created with cudaEventBlockingSync, so that the waiting thread sleeps -- several ranks per node with a few
-// threads each would otherwise keep more spinning threads than the host has cores.
+// Host wait for a stream.  Default: cudaStreamSynchronize (spins: lowest latency).  GANON_B200_SYNC=block (and every file
+// run, see set_blocking_waits): a yielding wait, so that the waiting thread gives its core away -- several ranks per node
+// with a few threads each, or a file run with its reader / inflater / writer threads, would otherwise keep more spinning
+// threads than the host has cores.
 // gnb_session_classify_files turns blocking waits on for its duration unless GANON_B200_SYNC=spin says otherwise: its reader,
 // inflater and writer threads need the cores the spinning waits would burn (measured on a 16-core host, c2 file to file:
 // 33.6 -> 51 M reads/s).
@@ -62,21 +63,19 @@ inline cudaError_t stream_wait(cudaStream_t st)
     const bool block = g_sync_block.load(std::memory_order_relaxed) != 0;
     if (!block)
         return cudaStreamSynchronize(st);
-    thread_local cudaEvent_t ev     = nullptr;
-    thread_local int         ev_dev = -1;
-    int                      dev    = 0;
-    cudaGetDevice(&dev);
-    if (!ev || ev_dev != dev)
+    // Yielding wait: poll the stream, spinning for the first 50 us and sleeping 40 us between polls after that.  The core
+    // is free during a long kernel, and the wake-up costs ~0.1 ms at most (an interrupt-driven cudaEventBlockingSync wait
+    // was measured at milliseconds per wake-up on some hosts, which stalls a chain of ~8 waits per batch).
+    const auto t0 = Clock::now();
+    for (;;)
     {
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
-        if (e != cudaSuccess)
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady)
             return e;
-        ev_dev = dev;
+        if (std::chrono::duration<double, std::micro>(Clock::now() - t0).count() < 50.0)
+            continue;
+        std::this_thread::sleep_for(std::chrono::microseconds(40));
     }
-    cudaError_t e = cudaEventRecord(ev, st);
-    if (e != cudaSuccess)
-        return e;
-    return cudaEventSynchronize(ev);
 }
 
 struct DevBuf
@@ -1418,7 +1417,7 @@ int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records
     launches += 1;
     uint32_t nl = 0;
     GNB_CUDA(cudaMemcpyAsync(&nl, d_status.as<uint32_t>() + 8 + side, 4, cudaMemcpyDeviceToHost, st_in));
-    GNB_CUDA(stream_wait(st_in));
+    GNB_CUDA(cudaStreamSynchronize(st_in)); // short wait on the caller's thread: spin (a blocking wake-up can cost milliseconds)
     (void)fin;
     n_lines   = nl;
     n_records = std::min<uint32_t>(nl / 4, kMaxReadsPerBatch - 1);
@@ -1517,7 +1516,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             GNB_CUDA(cudaMemcpyAsync(ends + 2, d_blk2.p, 1, cudaMemcpyDeviceToHost, st_in));
             GNB_CUDA(cudaMemcpyAsync(ends + 3, d_blk2.as<char>() + len2 - 1, 1, cudaMemcpyDeviceToHost, st_in));
         }
-        GNB_CUDA(stream_wait(st_in));
+        GNB_CUDA(cudaStreamSynchronize(st_in)); // short wait on the caller's thread: spin (a blocking wake-up can cost milliseconds)
         if (len1)
             first1 = ends[0], last1 = ends[1];
         if (len2)
@@ -1591,7 +1590,7 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
                 GNB_CUDA(cudaMemcpyAsync((void *)p_slen2, d_len2.p, n * 4, cudaMemcpyDeviceToHost, st_in));
             timing.d2h_bytes += (uint64_t)n * 4 * (paired ? 4 : 3);
         }
-        GNB_CUDA(stream_wait(st_in));
+        GNB_CUDA(cudaStreamSynchronize(st_in)); // short wait on the caller's thread: spin (a blocking wake-up can cost milliseconds)
         GNB_CUDA(cudaGetLastError());
         timing.d2h_bytes += 24;
         consumed1 = h_cons[0];
