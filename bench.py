@@ -1119,7 +1119,7 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
     if os.environ.get("GANON_B200_BENCH_CLI_VARIANTS"):
         # diagnosis aid: the same command under other host settings
         out["variants"] = {}
-        for tag, env in (("io_threads_4", {"GANON_B200_IO_THREADS": "4"}), ("io_threads_8", {"GANON_B200_IO_THREADS": "8"}), ("sync_block", {"GANON_B200_SYNC": "block"}),
+        for tag, env in (("io_threads_4", {"GANON_B200_IO_THREADS": "4"}), ("io_threads_8", {"GANON_B200_IO_THREADS": "8"}), ("sync_spin", {"GANON_B200_SYNC": "spin"}),
                          ("block_256MiB", {"GANON_B200_BLOCK_BYTES": str(256 << 20)})):
             pv = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, **env))
             mv = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pv.stderr)
