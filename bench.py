@@ -1102,6 +1102,7 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
             for _ in range(reps):
                 for _b1, b2 in blocks:
                     b2.tofile(f2)
+    os.sync()  # the files were just written: let the write-back finish, or it competes with the run for the host's memory system
     n_cli = reps * pool * R * (2 if wl["paired"] else 1)
     reads = ["-p", fq1 + "," + fq2] if fq2 else ["-r", fq1]
     cmd = [sys.executable, os.path.join(ROOT, "bin", "ganon-classify")] + (["--hibf"] if wl.get("hibf") else []) + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", os.path.join(CACHE, "cli_out"), "--verbose", "--device", str(dev)]
@@ -1135,6 +1136,7 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
         if gz2:
             write_single_member_gzip(gz2, [b2 for _b1, b2 in blocks])
         t_gz = time.perf_counter() - t0
+        os.sync()
         n_gz = pool * R * (2 if wl["paired"] else 1)
         reads_gz = ["-p", gz1 + "," + gz2] if gz2 else ["-r", gz1]
         cmd_gz = [c for c in cmd]
