@@ -183,3 +183,54 @@ def test_bgzf_and_flush_points(tmp_path, fastq):
         for threads, chunk in ((4, 20000), (2, 4096), (4, None)):
             got, err = read_all_with_chunk(tmp_path / "flush.gz", threads, chunk)
             assert err is None and got == data, (seed, threads, chunk)
+
+
+def test_fuzz_against_zlib(tmp_path):
+    """Random payload kinds (noise, DNA text, long runs, FASTQ, zeros, byte runs) x random deflate settings (level 0-9, window
+    2^9..2^15, memLevel, strategies incl. RLE / Huffman-only / fixed), 1-3 members, random sync / full flush points, random
+    thread counts and chunk sizes: the bytes must be zlib's.  (A 1000-case campaign of the same generator ran clean in
+    development.)"""
+    rng = np.random.default_rng(2024)
+
+    def make(kind, n):
+        if kind == 0:
+            return rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        if kind == 1:
+            return bytes(rng.choice(list(b"ACGT\n"), size=n).astype(np.uint8))
+        if kind == 2:
+            return (b"A" * int(rng.integers(1, 5000)) + b"\n") * max(1, n // 2500)
+        if kind == 3:
+            recs, size = [], 0
+            while size < n:
+                L = int(rng.integers(30, 300))
+                s = bytes(rng.choice(list(b"ACGTN"), size=L).astype(np.uint8))
+                q = bytes(rng.choice(list(b"FFFF:,#"), size=L).astype(np.uint8))
+                recs.append(b"@read%d some/1\n%s\n+\n%s\n" % (len(recs), s, q))
+                size += len(recs[-1])
+            return b"".join(recs)
+        if kind == 4:
+            return bytes(n)
+        return b"".join(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 400)) for _ in range(n // 200 + 1))[:n]
+
+    for case in range(24):
+        data = make(int(rng.integers(0, 6)), int(rng.integers(1, 1_200_000)))
+        level, wbits, mem = int(rng.integers(0, 10)), int(rng.integers(9, 16)), int(rng.integers(1, 10))
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        members = int(rng.integers(1, 4))
+        cuts = sorted(rng.integers(0, len(data) + 1, size=members - 1).tolist()) + [len(data)]
+        parts, pos = [], 0
+        for e in cuts:
+            co = zlib.compressobj(level, zlib.DEFLATED, 16 + wbits, mem, strat)
+            piece, p = data[pos:e], 0
+            pos = e
+            while p < len(piece):
+                m = int(rng.integers(1, 300000))
+                parts.append(co.compress(piece[p : p + m]))
+                p += m
+                if rng.random() < 0.2:
+                    parts.append(co.flush(zlib.Z_SYNC_FLUSH if rng.random() < 0.5 else zlib.Z_FULL_FLUSH))
+            parts.append(co.flush())
+        (tmp_path / "f.gz").write_bytes(b"".join(parts))
+        threads, chunk = int(rng.integers(1, 7)), int(rng.choice([4096, 8000, 20000, 65536, 300000, 0])) or None
+        got, err = read_all_with_chunk(tmp_path / "f.gz", threads, chunk)
+        assert err is None and got == data, (case, level, wbits, mem, strat, members, threads, chunk, err)
