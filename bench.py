@@ -55,8 +55,29 @@ WORKLOADS = {
 REL_CUTOFF, REL_FILTER, FPR_QUERY = 0.75, 0.1, 1e-5  # ganon CLI defaults (src/ganon/config.py:603,612,711)
 DB_SEED, READ_SEED = 1, 2
 CACHE = os.environ.get("GANON_B200_BENCH_DIR", "/tmp/ganon_b200_bench")
-REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ganon-classify")
-REF_FLAGS = "g++ -std=c++20 -O3 -DNDEBUG -mavx2 -mbmi2 -mpopcnt (oracle/Makefile; built where /root/reference exists, so not -march=native of the bench box)"
+def _pick_reference_binary():
+    """The unmodified reference compiled by oracle/Makefile where /root/reference exists.  Its sources do not travel, so it
+    cannot be rebuilt -march=native on the bench box; two builds travel instead and the one for the widest instruction set
+    this host runs is used: x86-64-v4 (AVX-512) when /proc/cpuinfo lists it and the binary starts, else AVX2 + BMI2."""
+    base = os.path.join(ROOT, "oracle", "_ref", "ganon-classify")
+    common = "g++ -std=c++20 -O3 -DNDEBUG %s (oracle/Makefile; the reference's sources do not travel to the bench box, so -march=native is not possible there)"
+    v4 = base + ".v4"
+    try:
+        flags = set()
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    flags = set(ln.split(":", 1)[1].split())
+                    break
+        if os.path.exists(v4) and {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags and not os.environ.get("GANON_B200_REF_AVX2"):
+            if subprocess.run([v4, "--version"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=20).returncode == 0:
+                return v4, common % "-march=x86-64-v4"
+    except Exception:
+        pass
+    return base, common % "-mavx2 -mbmi2 -mpopcnt"
+
+
+REF_BIN, REF_FLAGS = _pick_reference_binary()
 
 
 def measured_peak_gbs():
