@@ -519,6 +519,7 @@ class GanonClassifyConfig:
     # not in the reference: which GPU to use, or several GPUs with every .ibf bin-sharded over them (one process per GPU)
     device: int = 0
     devices: List[int] = field(default_factory=list)
+    hbm_budget_gb: float = 0.0  # > 0: flat filters above this size are loaded paged (host-resident tier)
     # not in the reference binary: the EM step of `ganon classify` (src/ganon/reassign.py) from the matches in HBM
     reassign_em: bool = False
     em_max_iter: int = 10
@@ -693,7 +694,7 @@ def _run_rank(cfg: GanonClassifyConfig, rank: int, n_ranks: int, uid: Optional[b
     dbs: List[Database] = []
     try:
         for path in cfg.ibf:
-            dbs.append(Database.open(path, hibf=cfg.hibf, device=device, shard=rank, n_shards=n_ranks))
+            dbs.append(Database.open(path, hibf=cfg.hibf, device=device, shard=rank, n_shards=n_ranks, hbm_budget=int(cfg.hbm_budget_gb * (1 << 30)) if n_ranks == 1 else 0))
         comm = Comm(uid, rank, n_ranks, device) if n_ranks > 1 else None
     except _lib.GnbError as e:
         print("ERROR: loading ibf or tax files (%s)" % e.msg, file=sys.stderr)

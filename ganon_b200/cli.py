@@ -34,6 +34,7 @@ _OPTS = {
     "quiet": (None, "bool", "quiet"),
     "device": (None, "int", "device"),  # extension: GPU ordinal
     "devices": (None, "ints", "devices"),  # extension: several GPUs, the databases bin-sharded over them
+    "hbm-budget-gb": (None, "float", "hbm_budget_gb"),  # extension: host-resident tier for filters above this many GiB
     # extension: `ganon classify --multiple-matches em` without the round trip through the .all file (src/ganon/reassign.py)
     "reassign-em": (None, "bool", "reassign_em"),
     "em-max-iter": (None, "int", "em_max_iter"),
@@ -71,6 +72,8 @@ Usage:
       --device arg            CUDA device ordinal. Default: 0
       --devices arg           Several CUDA devices (comma-separated): every .ibf is split by bin columns over them
                               (databases larger than one GPU's memory; one process per GPU, results identical)
+      --hbm-budget-gb arg     Keep at most this many GiB of a flat .ibf in GPU memory; the rest stays in host memory
+                              and is streamed per batch (host-resident tier; results identical)
       --reassign-em           EM reassignment of reads with several matches from the matches kept on the GPU
                               (what `ganon classify --multiple-matches em` does from the .all file): writes prefix.one
                               and the reassigned prefix.rep
@@ -125,6 +128,8 @@ def parse(argv: List[str]) -> Optional[GanonClassifyConfig]:
                 setattr(cfg, attr, vals)
             elif kind == "ints":
                 setattr(cfg, attr, [int(x) for x in inline.split(",")])
+            elif kind == "float":
+                setattr(cfg, attr, float(inline))
             elif kind == "int":
                 setattr(cfg, attr, int(inline))
             else:

@@ -869,10 +869,13 @@ def test_paged_filter_host_resident_tier_equals_the_whole(golden_dbs, tmp_path, 
     pre = str(tmp_path / "paged")
     assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", path, "-c", "0.1", "-d", "0.5", "-o", pre, "-a", "-u", "--quiet"]) == 0
     monkeypatch.delenv("GANON_B200_HBM_BUDGET_GB")
+    pre3 = str(tmp_path / "paged_flag")  # the same through the command-line flag
+    assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", path, "-c", "0.1", "-d", "0.5", "-o", pre3, "-a", "-u", "--quiet", "--hbm-budget-gb", "%.9f" % ((2 * col + 100) / (1 << 30))]) == 0
     pre2 = str(tmp_path / "whole")
     assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", path, "-c", "0.1", "-d", "0.5", "-o", pre2, "-a", "-u", "--quiet"]) == 0
     for ext in (".all", ".unc", ".rep"):
         assert _read_sorted(pre + ext) == _read_sorted(pre2 + ext)
+        assert _read_sorted(pre3 + ext) == _read_sorted(pre2 + ext)
 
 
 def test_levels_with_several_filters_finish_on_the_device(golden_dbs):
