@@ -125,3 +125,19 @@ def test_classify_wrapper_argument_mapping(tmp_path, monkeypatch):
     assert K.classify(types.SimpleNamespace(multiple_matches="lca", **base))
     c = seen.pop("cfg")
     assert not c.skip_lca and c.output_lca and not c.output_all and not c.reassign_em
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under ganon_b200/, bin/ or include/ may import, include, link or run it."""
+    import glob
+
+    hits = []
+    for pat in ("ganon_b200/*.py", "ganon_b200/csrc/*.cpp", "ganon_b200/csrc/*.cu", "ganon_b200/csrc/*.h", "ganon_b200/csrc/*.cuh", "ganon_b200/csrc/Makefile", "bin/*", "include/*.h"):
+        for p in glob.glob(os.path.join(ROOT, pat)):
+            with open(p, errors="replace") as f:
+                for i, line in enumerate(f, 1):
+                    if re.search(r"\boracle\b", line) and not re.search(r"oracle's|the oracle|against the oracle|vs the oracle|oracle/", line):
+                        hits.append((p, i, line.strip()))
+                    if re.search(r"(import|from|include|dlopen|CDLL).*oracle", line):
+                        hits.append((p, i, line.strip()))
+    assert not hits, hits
