@@ -1127,13 +1127,22 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
     n_cli = reps * pool * R * (2 if wl["paired"] else 1)
     reads = ["-p", fq1 + "," + fq2] if fq2 else ["-r", fq1]
     cmd = [sys.executable, os.path.join(ROOT, "bin", "ganon-classify")] + (["--hibf"] if wl.get("hibf") else []) + reads + ["-i", ibf_path, "-c", str(REL_CUTOFF), "-d", str(REL_FILTER), "-f", str(FPR_QUERY), "-a", "-o", os.path.join(CACHE, "cli_out"), "--verbose", "--device", str(dev)]
-    t0 = time.perf_counter()
-    pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    wall = time.perf_counter() - t0
-    mc = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+    # two consecutive runs, the second one reported: the classification phase lasts well under a second, and the first run
+    # starts on a GPU that sat idle while this benchmark wrote its input files (clocks ramp up during it; measured: its
+    # staging calls take 2-3 x longer than in any following run, whatever the host settings)
+    first_cs = None
+    for attempt in range(2):
+        t0 = time.perf_counter()
+        pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        wall = time.perf_counter() - t0
+        mc = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
+        if attempt == 0:
+            first_cs = float(mc.group(1)) if mc else None
+            if pr.returncode != 0:
+                break
     ml = re.search(r"loading filter\(s\)\s+elapsed \(s\): ([0-9.eE+-]+)", pr.stderr)
     cs = float(mc.group(1)) if mc else None
-    out = {"rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
+    out = {"first_run_classify_s": first_cs, "rc": pr.returncode, "reads": n_cli, "fastq_bytes": os.path.getsize(fq1) + (os.path.getsize(fq2) if fq2 else 0), "classify_s": cs, "load_s": float(ml.group(1)) if ml else None, "wall_s": wall,
            "reads_per_s": n_cli / cs if cs else None, "all_bytes": os.path.getsize(os.path.join(CACHE, "cli_out.all")) if os.path.exists(os.path.join(CACHE, "cli_out.all")) else None,
            "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
     mh = re.search(r"host pipeline \(s\): ([^\n]*)", pr.stderr)
