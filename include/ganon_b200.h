@@ -254,7 +254,9 @@ int gnb_session_finish_staged(gnb_session *s, uint32_t prefix_id, gnb_batch_resu
 
 /* Asynchronous form of gnb_session_classify for streaming a file: submit indexes the block and copies it to the device
  * in the calling thread (staged_info->n_reads / consumed1 / consumed2 / parse_error are valid on return, so the caller
- * can cut the next block), then kernels and host finishing run in a worker thread on the slot's own CUDA stream while the
+ * can cut the next block; a block that does not end the file may leave up to 2 x --n-reads complete records unconsumed --
+ * they must come back at the front of the next block: the parse-error rule of GC.cpp:1240-1283 retracts whole --n-reads
+ * chunks, and nothing already classified can be taken back), then kernels and host finishing run in a worker thread on the slot's own CUDA stream while the
  * next block is staged.  collect returns the oldest submitted batch (submission order).  The blocks passed to submit
  * must stay untouched until their batch has been collected; a collected result stays valid until the next collect.
  * gnb_session_in_flight: batches submitted and not collected, and how many may be in flight at once. */
