@@ -235,6 +235,7 @@ size_t fastq_index_tmp_bytes(uint64_t n_bytes);
 void   launch_fastq_count(const uint8_t *blk, uint64_t n_bytes, uint32_t *n_lines_dev, void *tmp, size_t tmp_bytes, cudaStream_t st);
 void   launch_fastq_line_starts(const uint8_t *blk, uint64_t n_bytes, uint32_t *line_start, uint32_t cap_lines, void *tmp, cudaStream_t st);
 void   launch_fastq_records(const uint8_t *blk, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st);
+void   launch_fasta_records(const uint8_t *blk, uint64_t n_bytes, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st); // 2 lines per record
 
 // error plumbing
 void        set_error(const std::string &msg);

@@ -2330,6 +2330,29 @@ __global__ void k_fastq_records(const uint8_t *__restrict__ blk, const uint32_t 
     }
 }
 
+// Unwrapped FASTA (">id\nSEQUENCE\n" per record, what read files in FASTA format look like): spans from line_start[2r..2r+2].
+// A sequence line that starts like a header, or a header line that does not, makes the block irregular (wrapped sequences,
+// ';' comment lines, blanks: the host reader reproduces seqan3's format_fasta there).
+__global__ void k_fasta_records(const uint8_t *__restrict__ blk, uint64_t n_bytes, const uint32_t *__restrict__ line_start, uint32_t n_records, FastqIndexOut out)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records)
+        return;
+    const uint32_t l0 = line_start[2 * r], l1 = line_start[2 * r + 1], l2 = line_start[2 * r + 2];
+    out.id_off[r]  = l0 + 1;
+    out.id_len[r]  = l1 - 1 - (l0 + 1);
+    out.seq_off[r] = l1;
+    out.seq_len[r] = l2 - 1 - l1;
+    // the line after the sequence line must open the next record (or be the end of the block): otherwise the sequence is
+    // wrapped over several lines and this is not the 2-line form
+    const bool ok = blk[l0] == '>' && l2 - 1 > l1 && blk[l1] != '>' && blk[l1] != ';' && (l2 >= n_bytes || blk[l2] == '>');
+    if (!ok)
+    {
+        atomicAdd(&out.status[1], 1u);
+        atomicMin(&out.status[2], r);
+    }
+}
+
 // warp per record: every sequence character must be legal for dna15 (parse_error otherwise)
 __global__ void k_validate_seq(const uint8_t *__restrict__ blk, const uint32_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
                                uint32_t n_records, uint32_t *__restrict__ status)
@@ -2388,6 +2411,15 @@ void launch_fastq_line_starts(const uint8_t *blk, uint64_t n_bytes, uint32_t *li
 }
 
 // Phase 2: record spans + marker / length / alphabet validation.  out.status must be {0, 0, 0xffffffff, 0} on entry.
+void launch_fasta_records(const uint8_t *blk, uint64_t n_bytes, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st)
+{
+    if (n_records == 0)
+        return;
+    k_fasta_records<<<(n_records + 255) / 256, 256, 0, st>>>(blk, n_bytes, line_start, n_records, out);
+    const uint64_t threads = (uint64_t)n_records * 32;
+    k_validate_seq<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(blk, out.seq_off, out.seq_len, n_records, out.status);
+}
+
 void launch_fastq_records(const uint8_t *blk, const uint32_t *line_start, uint32_t n_records, FastqIndexOut out, cudaStream_t st)
 {
     if (n_records == 0)

@@ -594,7 +594,7 @@ struct BatchCtx
     int  run_hibf_filter(size_t li, size_t fi, uint64_t &produced);
     int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
     size_t hold_back(size_t n) const;
-    int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines);
+    int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines, uint32_t lines_per_record);
     int  compute_hashes(uint32_t k, uint32_t w);
     int  run_level(size_t li);
     int  run_paged_count(FilterRt &F, const uint8_t *act, uint32_t n, uint64_t cap);
@@ -1405,7 +1405,7 @@ void gnb_session::ensure_prefix(uint32_t prefix_id)
 // stage: copy the block(s) to the device and index the records -- on the device (K1) for strict 4-line FASTQ, on the
 // host (reads.cpp: FASTA, wrapped FASTQ, blanks, and the exact parse-error behaviour) for everything else
 // ---------------------------------------------------------------------------------------------------------------------
-int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines)
+int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines, uint32_t lines_per_record)
 {
     DevBuf        &blk   = side == 0 ? d_blk1 : d_blk2;
     DevBuf        &lines = side == 0 ? d_lines1 : d_lines2;
@@ -1418,10 +1418,13 @@ int BatchCtx::device_index(int side, uint64_t len, bool fin, uint32_t &n_records
     uint32_t nl = 0;
     GNB_CUDA(cudaMemcpyAsync(&nl, d_status.as<uint32_t>() + 8 + side, 4, cudaMemcpyDeviceToHost, st_in));
     GNB_CUDA(cudaStreamSynchronize(st_in)); // short wait on the caller's thread: spin (a blocking wake-up can cost milliseconds)
-    (void)fin;
     n_lines   = nl;
-    n_records = std::min<uint32_t>(nl / 4, kMaxReadsPerBatch - 1);
-    const uint32_t cap_lines = 4 * n_records + 1;
+    n_records = std::min<uint32_t>(nl / lines_per_record, kMaxReadsPerBatch - 1);
+    // unwrapped FASTA: whether the last sequence line is the whole sequence is only known from the line after it (a header,
+    // or the end of the file), so a block that does not end the file keeps its last record back
+    if (lines_per_record == 2 && !fin && n_records > 0)
+        --n_records;
+    const uint32_t cap_lines = lines_per_record * n_records + 1;
     GNB_TRY(lines.ensure((size_t)cap_lines * 4 + 16));
     launch_fastq_line_starts(blk.as<uint8_t>(), n, lines.as<uint32_t>(), cap_lines, tmp.p, st_in);
     launches += 1;
@@ -1526,7 +1529,11 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
     GNB_CUDA(cudaEventRecord(ev[1], st_in));
 
     size_t n = 0;
-    bool   on_device = use_device_index && len1 > 0 && first1 == '@' && (!paired || (len2 > 0 && first2 == '@'));
+    // K1 takes strict 4-line FASTQ and unwrapped 2-line FASTA (both mates in the same format); everything else, and any
+    // irregular block, goes to the host reader
+    const bool     fasta = first1 == '>';
+    const uint32_t lpr   = fasta ? 2 : 4; // lines per record
+    bool on_device = use_device_index && len1 > 0 && (first1 == '@' || first1 == '>') && (!paired || (len2 > 0 && first2 == first1));
     if (on_device)
     {
         GNB_CUDA(cudaEventRecord(ev[8], st_in));
@@ -1542,9 +1549,9 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             e2 = len2 + 1;
         }
         uint32_t n1 = 0, n2 = 0, nl1 = 0, nl2 = 0;
-        GNB_TRY(device_index(0, e1, final_block, n1, nl1));
+        GNB_TRY(device_index(0, e1, final_block, n1, nl1, lpr));
         if (paired)
-            GNB_TRY(device_index(1, e2, final_block, n2, nl2));
+            GNB_TRY(device_index(1, e2, final_block, n2, nl2, lpr));
         n = paired ? std::min(n1, n2) : n1;
         n = hold_back(n);
         const uint32_t init_status[4] = {0, 0, 0xffffffffu, 0};
@@ -1554,7 +1561,10 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         GNB_TRY(d_idoff.ensure(n * 4 + 4));
         GNB_TRY(d_idlen.ensure(n * 4 + 4));
         FastqIndexOut o1{d_idoff.as<uint32_t>(), d_idlen.as<uint32_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), d_status.as<uint32_t>()};
-        launch_fastq_records(d_blk1.as<uint8_t>(), d_lines1.as<uint32_t>(), (uint32_t)n, o1, st_in);
+        if (fasta)
+            launch_fasta_records(d_blk1.as<uint8_t>(), e1, d_lines1.as<uint32_t>(), (uint32_t)n, o1, st_in);
+        else
+            launch_fastq_records(d_blk1.as<uint8_t>(), d_lines1.as<uint32_t>(), (uint32_t)n, o1, st_in);
         launches += 2;
         if (paired)
         {
@@ -1563,7 +1573,10 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
             GNB_TRY(d_idoff2.ensure(n * 4 + 4));
             GNB_TRY(d_idlen2.ensure(n * 4 + 4));
             FastqIndexOut o2{d_idoff2.as<uint32_t>(), d_idlen2.as<uint32_t>(), d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), d_status.as<uint32_t>()};
-            launch_fastq_records(d_blk2.as<uint8_t>(), d_lines2.as<uint32_t>(), (uint32_t)n, o2, st_in);
+            if (fasta)
+                launch_fasta_records(d_blk2.as<uint8_t>(), e2, d_lines2.as<uint32_t>(), (uint32_t)n, o2, st_in);
+            else
+                launch_fastq_records(d_blk2.as<uint8_t>(), d_lines2.as<uint32_t>(), (uint32_t)n, o2, st_in);
             launches += 2;
         }
         GNB_CUDA(cudaEventRecord(ev[9], st_in));
@@ -1576,9 +1589,9 @@ int BatchCtx::stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, in
         p_slen1 = p_idlen + n;
         p_slen2 = p_slen1 + n;
         GNB_CUDA(cudaMemcpyAsync(h_status, d_status.p, 16, cudaMemcpyDeviceToHost, st_in));
-        GNB_CUDA(cudaMemcpyAsync(h_cons, d_lines1.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st_in));
+        GNB_CUDA(cudaMemcpyAsync(h_cons, d_lines1.as<uint32_t>() + lpr * n, 4, cudaMemcpyDeviceToHost, st_in));
         if (paired)
-            GNB_CUDA(cudaMemcpyAsync(h_cons + 1, d_lines2.as<uint32_t>() + 4 * n, 4, cudaMemcpyDeviceToHost, st_in));
+            GNB_CUDA(cudaMemcpyAsync(h_cons + 1, d_lines2.as<uint32_t>() + lpr * n, 4, cudaMemcpyDeviceToHost, st_in));
         // the host finishing stage needs the record table; with K4 on every level it is fetched only on demand
         host_records_valid = !S->all_device_finish;
         if (n && host_records_valid)

@@ -996,3 +996,39 @@ def test_long_reads_finish_on_the_device_when_fpr_query_is_off(golden_dbs):
     assert out["device"][4] > 10_000
     assert out["device"][3] == 1 and out["host"][3] == 0 and out["device_fpr"][3] == 0
     assert out["device"][:3] == out["host"][:3] and out["device"][0]
+
+
+def test_unwrapped_fasta_is_indexed_on_the_device(golden_dbs, monkeypatch):
+    """K1 takes 2-line FASTA records (">id\\nSEQ\\n"): same result as the host reader over blocks that end anywhere, with and
+    without a final newline; a wrapped FASTA block is recognised (the line after a sequence line is not a header) and goes to
+    the host reader."""
+    fq = open(os.path.join(SU.GOLDEN, "reads.se.fq"), "rb").read().split(b"\n")
+    recs = [(fq[i][1:], fq[i + 1]) for i in range(0, len(fq) - 1, 4)]
+    flat = b"".join(b">%s\n%s\n" % (i, s) for i, s in recs)
+    wrapped = b"".join(b">%s\n%s\n" % (i, b"\n".join(s[a : a + 60] for a in range(0, len(s), 60))) for i, s in recs)
+    db = Database.open(golden_dbs["synth"])
+    out = {}
+    for name, text, host_index in (("flat_dev", flat, "0"), ("flat_dev_no_newline", flat.rstrip(b"\n"), "0"), ("flat_host", flat, "1"), ("wrapped", wrapped, "0")):
+        monkeypatch.setenv("GANON_B200_HOST_INDEX", host_index)
+        sess = Session([db], [0.0], [1.0], [1.0], output_all=True, output_unclassified=True)
+        lines, uncs, pos, total, on_dev = [], [], 0, 0, 0
+        while True:
+            end = min(len(text), pos + 30011)
+            final = end == len(text)
+            r = sess.classify(text[pos:end], final=final)
+            lines += result_text(r, "all").decode().splitlines()
+            uncs += result_text(r, "unc").decode().splitlines()
+            total += r.n_reads
+            on_dev += r.ms_index > 0
+            pos += r.consumed1
+            if final:
+                break
+            assert r.n_reads > 0
+        out[name] = (total, sorted(lines), sorted(uncs), sess.report())
+        sess.close()
+        if name.startswith("flat_dev"):
+            assert on_dev > 3, name  # the device index took the blocks
+        else:
+            assert on_dev == 0, name
+    assert out["flat_dev"][0] == len(recs) and out["flat_dev"][1]
+    assert out["flat_dev"] == out["flat_host"] == out["flat_dev_no_newline"] == out["wrapped"]
