@@ -2345,7 +2345,8 @@ __global__ void k_fasta_records(const uint8_t *__restrict__ blk, uint64_t n_byte
     out.seq_len[r] = l2 - 1 - l1;
     // the line after the sequence line must open the next record (or be the end of the block): otherwise the sequence is
     // wrapped over several lines and this is not the 2-line form
-    const bool ok = blk[l0] == '>' && l2 - 1 > l1 && blk[l1] != '>' && blk[l1] != ';' && (l2 >= n_bytes || blk[l2] == '>');
+    // (seqan3 skips blanks between '>' and the id: such headers go to the host reader as well)
+    const bool ok = blk[l0] == '>' && blk[l0 + 1] != ' ' && blk[l0 + 1] != '\t' && l2 - 1 > l1 && blk[l1] != '>' && blk[l1] != ';' && (l2 >= n_bytes || blk[l2] == '>');
     if (!ok)
     {
         atomicAdd(&out.status[1], 1u);

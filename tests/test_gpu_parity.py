@@ -1011,15 +1011,16 @@ def test_unwrapped_fasta_is_indexed_on_the_device(golden_dbs, monkeypatch):
     for name, text, host_index in (("flat_dev", flat, "0"), ("flat_dev_no_newline", flat.rstrip(b"\n"), "0"), ("flat_host", flat, "1"), ("wrapped", wrapped, "0")):
         monkeypatch.setenv("GANON_B200_HOST_INDEX", host_index)
         sess = Session([db], [0.0], [1.0], [1.0], output_all=True, output_unclassified=True)
-        lines, uncs, pos, total, on_dev = [], [], 0, 0, 0
+        lines, uncs, pos, total, on_dev, flags = [], [], 0, 0, 0, []
         while True:
-            end = min(len(text), pos + 30011)
+            end = min(len(text), pos + 9011)
             final = end == len(text)
             r = sess.classify(text[pos:end], final=final)
             lines += result_text(r, "all").decode().splitlines()
             uncs += result_text(r, "unc").decode().splitlines()
             total += r.n_reads
             on_dev += r.ms_index > 0
+            flags.append(int(r.ms_index > 0))
             pos += r.consumed1
             if final:
                 break
@@ -1027,7 +1028,7 @@ def test_unwrapped_fasta_is_indexed_on_the_device(golden_dbs, monkeypatch):
         out[name] = (total, sorted(lines), sorted(uncs), sess.report())
         sess.close()
         if name.startswith("flat_dev"):
-            assert on_dev > 3, name  # the device index took the blocks
+            assert on_dev >= len(flags) - 1 and on_dev > 3, (name, flags)  # the device index took the blocks
         else:
             assert on_dev == 0, name
     assert out["flat_dev"][0] == len(recs) and out["flat_dev"][1]
