@@ -591,7 +591,7 @@ struct BatchCtx
     }
     int init(cudaStream_t external);
 
-    int  run_hibf_filter(size_t li, size_t fi, uint64_t &produced);
+    int  run_hibf_filter(size_t li, size_t fi, uint64_t &produced, uint64_t start_tuples = 0);
     int  stage(const char *b1, uint64_t l1, const char *b2, uint64_t l2, int fin);
     size_t hold_back(size_t n) const;
     int  device_index(int side, uint64_t len, bool fin, uint32_t &n_records, uint32_t &n_lines, uint32_t lines_per_record);
@@ -839,6 +839,7 @@ int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
     F.is_hibf = true;
     F.node_fpr.assign(L.n_targets, 0.0);
     F.node_multi.assign(L.n_targets, 0);
+    const uint32_t filter_index = (uint32_t)(&F - L.filters.data());
     std::unordered_map<std::string, uint32_t> node_of;
     for (uint32_t i = 0; i < L.n_targets; ++i)
         node_of.emplace(L.node_names[i], i);
@@ -893,7 +894,9 @@ int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
             uint64_t e = b + 1;
             while (e < ibf.bins && pos[e] == fi)
                 ++e;
-            const uint32_t node = node_of_user_bin[(size_t)fi];
+            const uint32_t node_id = node_of_user_bin[(size_t)fi];
+            // what K3h writes into a tuple's node field: the node, and the filter index below it where K4 merges the filters
+            const uint32_t node = node_id == 0xffffffffu ? node_id : (L.filter_bits ? ((node_id << L.filter_bits) | filter_index) : node_id);
             if (node != 0xffffffffu)
             {
                 if (e - b == 1)
@@ -910,7 +913,7 @@ int gnb_session::build_hibf_tables(LevelRt &L, FilterRt &F)
                     // sum of the counter type, then the threshold, HIBF.hpp:437-458); a longer run yields partial sums
                     const uint16_t complete = regs.size() == 1 ? 2 : 0;
                     if (!complete)
-                        F.node_multi[node] = 1;
+                        F.node_multi[node_id] = 1;
                     for (auto const &[rg, mask] : regs)
                     {
                         per_slot[rg >> 2].push_back(Seg{mask, node, (uint16_t)(rg & 3), complete});
@@ -1293,7 +1296,7 @@ extern "C" int gnb_session_create(const gnb_session_config *cfg, gnb_session **o
             L.depth[i] = d;
         }
         L.filter_bits = 0;
-        if (L.filters.size() > 1 && L.filters.size() <= 16 && !L.filters[0].db->is_hibf)
+        if (L.filters.size() > 1 && L.filters.size() <= 16)
         {
             uint32_t bits = 0;
             while ((1u << bits) < L.filters.size())
@@ -1837,7 +1840,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
 
 // HIBF traversal (counting_agent_type::bulk_count, HIBF.hpp:433-460, 506-523) as level-synchronous rounds over a
 // worklist of (read, sub-IBF) items; tuples accumulate in d_tuples_a across the rounds.
-int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
+int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out, uint64_t start_tuples)
 {
     FilterRt &F = levels[li].filters[fi];
     const uint32_t n = n_reads;
@@ -1859,7 +1862,7 @@ int BatchCtx::run_hibf_filter(size_t li, size_t fi, uint64_t &produced_out)
     GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
     GNB_CUDA(stream_wait(st));
     timing.d2h_bytes += 8;
-    unsigned long long tuples_before = 0, round_bytes_sum = 0;
+    unsigned long long tuples_before = start_tuples, round_bytes_sum = 0; // tuples of earlier filters of the level stay in front
     DevBuf *cur = &d_items_a, *nxt = &d_items_b;
     for (size_t round = 0; n_items; ++round)
     {
@@ -2026,6 +2029,20 @@ int BatchCtx::run_level_merged(size_t li, const uint8_t *act, uint64_t active_ha
     unsigned long long produced = 0;
     float              ms_k3 = 0;
     GNB_TRY(wait_turn());
+    if (L.filters[0].is_hibf)
+    { // every HIBF's traversal appends behind the tuples of the filters before it (run_hibf_filter grows the buffer itself)
+        uint64_t so_far = 0;
+        for (size_t fi = 0; fi < L.filters.size(); ++fi)
+        {
+            uint64_t prod = 0;
+            GNB_TRY(run_hibf_filter(li, fi, prod, so_far));
+            so_far = prod;
+            timing.count_kernel_bytes += hibf_bytes;
+            ms_k3 += hibf_ms;
+        }
+        produced = so_far;
+    }
+    else
     for (int attempt = 0; attempt < 2; ++attempt)
     {
         GNB_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, st));
@@ -2054,8 +2071,9 @@ int BatchCtx::run_level_merged(size_t li, const uint8_t *act, uint64_t active_ha
         GNB_TRY(d_tuples_a.ensure(produced * 8));
         cap = d_tuples_a.cap / 8;
     }
-    for (auto &F : L.filters)
-        timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.db->ibfs[0].row_words() * 8;
+    if (!L.filters[0].is_hibf)
+        for (auto &F : L.filters)
+            timing.count_kernel_bytes += active_hashes * F.dev.hash_funs * (uint64_t)F.db->ibfs[0].row_words() * 8;
     const uint64_t *src    = d_tuples_a.as<uint64_t>();
     uint64_t        n_sort = produced;
     if (S->sharded())

@@ -1033,3 +1033,24 @@ def test_unwrapped_fasta_is_indexed_on_the_device(golden_dbs, monkeypatch):
             assert on_dev == 0, name
     assert out["flat_dev"][0] == len(recs) and out["flat_dev"][1]
     assert out["flat_dev"] == out["flat_host"] == out["flat_dev_no_newline"] == out["wrapped"]
+
+
+def test_hibf_levels_with_several_filters_finish_on_the_device(golden_dbs):
+    """Two and three HIBFs on one hierarchy level (ordinary ganon usage: several --db-prefix): every traversal appends behind
+    the tuples of the filters before it, K4 merges the filters of a node; same result as the host finishing stage."""
+    fq = open(os.path.join(SU.GOLDEN, "reads.hibf.fq"), "rb").read()
+    for cutoffs, rel_filter, fpr in (([0.3, 0.05], [0.5], [1.0]), ([0.0, 0.2, 0.6], [1.0], [1e-2])):
+        dbs = [Database.open(golden_dbs["synth_hibf"], hibf=True) for _ in cutoffs]
+        out = {}
+        for mode in ("device", "host"):
+            if mode == "host":
+                os.environ["GANON_B200_HOST_FINISH"] = "1"
+            try:
+                s = Session(dbs, cutoffs, rel_filter, fpr, output_all=True, output_unclassified=True)
+                r = s.classify(fq, final=True)
+                out[mode] = (sorted(result_text(r, "all").decode().splitlines()), sorted(result_text(r, "unc").decode().splitlines()), s.report(), r.levels_on_device)
+                s.close()
+            finally:
+                os.environ.pop("GANON_B200_HOST_FINISH", None)
+        assert out["device"][3] == 1 and out["host"][3] == 0, cutoffs
+        assert out["device"][:3] == out["host"][:3] and out["device"][0], cutoffs
