@@ -654,14 +654,19 @@ __global__ void k_hash_upper_bounds(const uint32_t *__restrict__ len1, const uin
 
 void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
                        const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, int mode, uint32_t *counts,
-                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count, cudaStream_t st)
+                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count, cudaStream_t st,
+                       uint32_t avg_windows)
 {
     if (n_reads == 0)
         return;
     const uint32_t W      = w - k + 1;
+    // a thread per read needs many reads to fill the GPU: few long sequences (long-read data, genomes) are better served by
+    // the warp-per-read kernel, which walks a sequence in tiles of 128 windows
+    const bool few_long = n_reads < 65536 && avg_windows > 512;
     // K2t is the default where its parameter range allows (measured on B200, c2: 0.99 ms vs 3.07 ms per 2^21 reads);
-    // GANON_B200_K2=warp keeps every read on the warp-per-read kernel (read once per process)
-    static const bool thread_path = [] { const char *e = getenv("GANON_B200_K2"); return !(e && e[0] == 'w'); }();
+    // GANON_B200_K2=warp keeps every read on the warp-per-read kernel, =thread every read K2t can take on K2t (read once per process)
+    static const int forced = [] { const char *e = getenv("GANON_B200_K2"); return e && e[0] == 'w' ? 1 : e && e[0] == 't' ? 2 : 0; }();
+    const bool thread_path = forced == 2 || (forced == 0 && !few_long);
     if (thread_path && k <= k2t::kMaxK && W <= k2t::kMaxW)
     { // K2t: one thread per read, CTAs of 128 reads (k2_thread.cuh)
         int dev_t = 0, sms_t = 148;

@@ -1791,6 +1791,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     timing.d2h_bytes += 8;
     uint64_t total = 0;
     uint32_t mx    = 0;
+    const uint32_t avg_windows = (uint32_t)std::min<uint64_t>(total_ub / n, 0xffffffffu); // windows per read (pair): picks the K2 kernel
     struct
     {
         uint32_t           mx, pad;
@@ -1800,7 +1801,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     {
         GNB_TRY(d_hashes.ensure((total_ub + 1) * 8));
         launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 2,
-                          d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), d_max, d_sum, st);
+                          d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), d_max, d_sum, st, avg_windows);
         launches += 1;
         GNB_CUDA(cudaEventRecord(ev[3], st));
         GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
@@ -1814,7 +1815,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     else
     {
         launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 0,
-                          d_counts.as<uint32_t>(), nullptr, nullptr, d_max, d_sum, st);
+                          d_counts.as<uint32_t>(), nullptr, nullptr, d_max, d_sum, st, avg_windows);
         launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
         launches += 2;
         GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
@@ -1824,7 +1825,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
         mx    = agg.mx;
         GNB_TRY(d_hashes.ensure((total + 1) * 8));
         launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 1,
-                          nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, nullptr, st);
+                          nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, nullptr, st, avg_windows);
         launches += 1;
         GNB_CUDA(cudaEventRecord(ev[3], st));
         d_counts_valid = true; // exact layout: counts equal the offset differences
@@ -3952,8 +3953,9 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         GNB_CUDA(cudaMemcpy(d_seq.p, seqs, seq_off[n], cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_off.p, off.data(), n * 4, cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_len.p, len.data(), n * 4, cudaMemcpyHostToDevice));
+        const uint32_t avg_windows = (uint32_t)std::min<uint64_t>(seq_off[n] / n, 0xffffffffu);
         launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, 0,
-                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, 0);
+                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, 0, avg_windows);
         launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
         GNB_CUDA(cudaMemcpy(hash_off, d_hoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
         const uint64_t total = hash_off[n];
@@ -3961,7 +3963,7 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         {
             GNB_TRY(d_h.ensure(total * 8));
             launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, 1, nullptr,
-                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, nullptr, 0);
+                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, nullptr, 0, avg_windows);
             GNB_CUDA(cudaMemcpy(hashes, d_h.p, total * 8, cudaMemcpyDeviceToHost));
         }
         GNB_CUDA(cudaGetLastError());

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from ganon_b200 import _lib, cli, formats
-from ganon_b200.classify import Database, Session, minimisers, result_text
+from ganon_b200.classify import Database, Session, minimisers, minimisers_batch, result_text
 from oracle import oracle as O
 from tests import scenario_util as SU
 
@@ -42,21 +42,45 @@ def test_minimisers_random_and_adversarial(k, w):
         assert minimisers(s, k, w).tolist() == O.minimiser_hash(s, k, w).tolist(), (k, w, len(s), s[:40])
 
 
-def test_warp_per_read_minimiser_kernel_passes_the_k2_and_scenario_tests():
-    """The thread-per-read kernel (k2_thread.cuh) is the default for k <= 29, w-k+1 <= 32; GANON_B200_K2=warp (read once
-    per process) keeps the warp-per-read kernel, which still serves every other (k, w): re-run the K2 tests, the golden
-    scenarios (single, paired, FASTA, several levels) and the oracle session test of this file in a child process with
-    the switch set, so that both kernels stay pinned."""
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_either_minimiser_kernel_alone_passes_the_k2_and_scenario_tests(kernel):
+    """For k <= 29, w-k+1 <= 32 the library picks per batch: the thread-per-read kernel (k2_thread.cuh), or the warp-per-read
+    kernel when the batch is a few long sequences (< 65536 reads averaging > 512 windows) -- and the warp kernel for every other
+    (k, w).  GANON_B200_K2=warp / =thread (read once per process) pin one kernel: re-run the K2 tests, the golden scenarios
+    (single, paired, FASTA, several levels) and the oracle session test of this file in a child process under each, so that
+    both kernels stay pinned on short and on long sequences."""
     import subprocess
     import sys
 
-    if os.environ.get("GANON_B200_K2", "").startswith("w"):
+    if os.environ.get("GANON_B200_K2", ""):
         pytest.skip("already inside the child run")
-    env = dict(os.environ, GANON_B200_K2="warp")
-    sel = "minimisers_seqan3 or minimisers_random or (golden_scenarios and device) or session_matches_oracle or device_and_host_record_index"
+    env = dict(os.environ, GANON_B200_K2=kernel)
+    sel = "minimisers_seqan3 or minimisers_random or long_sequence or (golden_scenarios and device) or session_matches_oracle or device_and_host_record_index"
     done = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", sel, "-p", "no:cacheprovider"], env=env,
                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert done.returncode == 0, done.stdout[-2000:]
+
+
+def test_long_sequence_batches_hash_like_the_oracle():
+    """A batch of a few long reads (the shape that goes to the warp kernel by default) and the same reads inside a batch of
+    many short ones (which keeps them on K2t): same minimisers as the oracle either way."""
+    rng = np.random.default_rng(77)
+    long_reads = [bytes(rng.choice(list(b"ACGTN"), p=[0.2499, 0.2499, 0.2499, 0.2499, 0.0004], size=n).astype(np.uint8)) for n in (30_000, 2_000, 70_001, 640)]
+    want = [O.minimiser_hash(s, 19, 31) for s in long_reads]
+
+    def batch(seqs):
+        hoff, h = minimisers_batch(seqs, 19, 31)
+        return h, hoff
+
+    h, hoff = batch(long_reads)
+    for i, wnt in enumerate(want):
+        assert np.array_equal(h[int(hoff[i]) : int(hoff[i + 1])], wnt), i
+    short = [bytes(rng.choice(list(b"ACGT"), size=40).astype(np.uint8)) for _ in range(70_000)]
+    h, hoff = batch(short[:35_000] + long_reads + short[35_000:])
+    for i, wnt in enumerate(want):
+        j = 35_000 + i
+        assert np.array_equal(h[int(hoff[j]) : int(hoff[j + 1])], wnt), i
+    assert np.array_equal(h[: int(hoff[1])], O.minimiser_hash(short[0], 19, 31))
 
 
 # ------------------------------------------------------------------------------------------------------------------ K3
