@@ -116,8 +116,18 @@ GNB_HD uint32_t threshold_cutoff(uint32_t n_hashes, double rel_cutoff)
 void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2,
                        const uint32_t *off2, const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, int mode,
                        uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count,
-                       cudaStream_t st, uint32_t avg_windows = 0);
-void launch_hash_upper_bounds(const uint32_t *len1, const uint32_t *len2, uint32_t n, uint32_t w, uint32_t *ub, cudaStream_t st);
+                       cudaStream_t st);
+// ub[i] = windows of read (pair) i; optional: items[i] = its segments (K2t over segments), *max_windows = most windows of one mate
+void launch_hash_upper_bounds(const uint32_t *len1, const uint32_t *len2, uint32_t n, uint32_t w, uint32_t *ub, cudaStream_t st, uint32_t *items = nullptr,
+                              uint32_t *max_windows = nullptr);
+// K2t over segments of long reads (k2_thread.cuh): whether a batch takes it; an upper bound of its items; the three launches
+// (segments, compaction, flagged reads + totals).  hash_off is the upper-bound layout, item_off the exclusive scan of items.
+bool     minimisers_segmented(uint32_t k, uint32_t w, uint32_t n_reads, uint32_t max_windows);
+uint64_t minimiser_segments_bound(uint64_t total_windows, uint32_t n_reads);
+void     launch_minimisers_segmented(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
+                                     const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, const uint64_t *item_off, uint64_t item_bound,
+                                     uint32_t *seg_cnt, uint8_t *flags, uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count,
+                                     unsigned long long *sum_count, cudaStream_t st);
 // exclusive scan of counts (values > 65535 are kept in the offsets; K3 skips such reads) -> hash_off[n+1]
 void   launch_scan_counts(const uint32_t *counts, uint64_t *hash_off, uint32_t n_reads, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t scan_tmp_bytes(uint32_t n_reads);

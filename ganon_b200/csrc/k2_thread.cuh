@@ -1,4 +1,4 @@
-// K2t -- minimisers, one THREAD per read (switch GANON_B200_K2=thread; k <= 29, w - k + 1 <= 32).
+// K2t -- minimisers, one THREAD per read, or per segment of a long read (k <= 29, w - k + 1 <= 32).
 //
 // The warp-per-read kernel (k_minimisers) spends ~1350 warp-instructions per 150 bp read, half of them on the doubled
 // position-tagged minima that emulate the reference's sliding window with parallel scans (profiles/r01_ncu_summary_k2_k4_k3h.md).
@@ -143,9 +143,16 @@ struct BaseStream
 // Minimisers of one mate: bases p[0..L), L >= w = k + W - 1.  ring: shared-space address of slot 0 of this thread's W slots,
 // slot x at ring + x * stride_bytes; lut: shared-space address of 256 entries of lut_entry(c, k).  Returns the number of
 // minimisers; WRITE stores them at out[0..).
-template <bool WRITE>
+//
+// SEG: the walk starts inside a longer sequence (segment(), below).  Windows before local k-mer index emit_from are a warm-up
+// and emit nothing.  The state machine started afresh holds the right VALUE from its first complete window on (the tracked
+// value is always the minimum of the window) but, among equal values, maybe not the reference's POSITION.  The position is
+// certain again after a strictly smaller value entered (both walks move to it), or after the tracked value left and the
+// minimum of the next window is larger (no equal value was in the window: both walks tracked the one that left, both
+// rescan).  *synced: such an event happened at a window in (first complete, emit_from].
+template <bool WRITE, bool SEG = false>
 K2T_D uint32_t mate(const uint8_t *p, uint32_t L, uint32_t k, uint32_t W, uint64_t seed, uint64_t mask, saddr_t lut, uint64_t *out, saddr_t ring,
-                    uint32_t stride_bytes)
+                    uint32_t stride_bytes, uint32_t emit_from = 0, bool *synced = nullptr)
 {
     const uint32_t mhi = opaque(2 * (k - 1) >= 32 ? ~0u : 0u); // the complement enters the high / the low word
     const uint32_t mlo = ~mhi;
@@ -184,6 +191,7 @@ K2T_D uint32_t mate(const uint8_t *p, uint32_t L, uint32_t k, uint32_t W, uint64
     uint32_t  j  = 0;
     uint32_t  n  = 0;
     uint64_t *op = out;
+    bool      sync = false;
     auto step = [&](uint32_t c8) {
         roll(c8);
         const uint64_t v   = min_key(f ^ seed, r ^ seed);
@@ -200,6 +208,7 @@ K2T_D uint32_t mate(const uint8_t *p, uint32_t L, uint32_t k, uint32_t W, uint64
         const bool     leave  = j >= mq;              // first window, or the minimiser left (minimiser.hpp:455-461)
         const bool     dec    = v < cur;              // minimiser.hpp:463-468
         const uint32_t mq_w   = bq - ((uint32_t)wk & kTagMask) - (take_s ? W : 0u); // index of the window minimum + W
+        const uint64_t was    = cur;
         if (dec)
         {
             cur = v;
@@ -210,7 +219,9 @@ K2T_D uint32_t mate(const uint8_t *p, uint32_t L, uint32_t k, uint32_t W, uint64
             cur = wk >> kTagBits;
             mq  = mq_w;
         }
-        if (leave | dec)
+        if (SEG)
+            sync |= (dec | (leave & (cur > was))) & (j >= W) & (j <= emit_from);
+        if ((leave | dec) && (!SEG || j >= emit_from))
         {
             if (WRITE)
                 *op++ = cur;
@@ -265,7 +276,31 @@ K2T_D uint32_t mate(const uint8_t *p, uint32_t L, uint32_t k, uint32_t W, uint64
             }
         }
     }
+    if (SEG)
+        *synced = sync;
     return WRITE ? (uint32_t)(op - out) : n;
+}
+
+// ---- long sequences: segments of kSegWindows windows, one thread each ------------------------------------------------------------
+// A sequence of many windows is cut into segments; the thread of segment g walks windows [g * kSegWindows - kSegWarm, end of g)
+// and emits from window g * kSegWindows on, at out + g * kSegWindows (every window could emit: the caller's layout has one
+// slot per window).  A segment whose warm-up saw no certain state (repeats shorter than the window all along: homopolymers,
+// tandem repeats) is flagged in the returned count and its sequence is walked again by one thread from the start.
+constexpr uint32_t kSegWindows = 512;
+constexpr uint32_t kSegWarm    = 64; // >= 2 * kMaxW: a minimiser lives for at most W windows unless an equal value follows it
+constexpr uint32_t kSegFlag    = 0x80000000u;
+
+K2T_D uint32_t segments_of(uint32_t L, uint32_t w) { return L >= w ? (L - w + kSegWindows) / kSegWindows : 0u; }
+
+K2T_D uint32_t segment(const uint8_t *p, uint32_t L, uint32_t seg, uint32_t k, uint32_t w, uint64_t seed, uint64_t mask, saddr_t lut, uint64_t *out,
+                       saddr_t ring, uint32_t stride_bytes)
+{
+    const uint32_t W = w - k + 1, windows = L - w + 1;
+    const uint32_t s = seg * kSegWindows, e = windows - s < kSegWindows ? windows : s + kSegWindows;
+    const uint32_t warm = s < kSegWarm ? s : kSegWarm, s0 = s - warm;
+    bool           synced = false;
+    const uint32_t n = mate<true, true>(p + s0, (e - s0) + w - 1, k, W, seed, mask, lut, out + s, ring, stride_bytes, W - 1 + warm, &synced);
+    return n | (warm != 0 && !synced ? kSegFlag : 0u);
 }
 
 // One read (pair) of a batch: the rules of GanonClassify.cpp:690-700 -- a read shorter than the window is skipped entirely, a

@@ -591,7 +591,8 @@ template <int KMODE> // as k_minimisers
 __global__ void __launch_bounds__(k2t::kThreads)
     k_minimisers_thread(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1, const uint8_t *__restrict__ blk2,
                         const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2, uint32_t n_reads, uint32_t k, uint32_t w, uint32_t *__restrict__ counts,
-                        const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count, unsigned long long *__restrict__ sum_count)
+                        const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ max_count, unsigned long long *__restrict__ sum_count,
+                        const uint8_t *__restrict__ only)
 {
     extern __shared__ __align__(16) uint64_t k2t_smem[]; // [256] character table, then the rings [W][kThreads]: slot-major, a warp's lanes side by side
     k2t::LutEntry *lut = reinterpret_cast<k2t::LutEntry *>(k2t_smem);
@@ -611,7 +612,10 @@ __global__ void __launch_bounds__(k2t::kThreads)
         const uint32_t read = first + tid;
         if (read >= n_reads)
             continue;
-        const uint32_t total = k2t::read_pair<KMODE>(read, blk1, off1, len1, blk2, off2, len2, k, w, seed, mask, lut_s, ring_s, kStride, counts, hash_off, hashes);
+        // only: the segment kernels did the batch, this pass walks the reads they flagged from the start (and sums up the counts)
+        const uint32_t total = only != nullptr && !only[read]
+                                   ? counts[read]
+                                   : k2t::read_pair<KMODE>(read, blk1, off1, len1, blk2, off2, len2, k, w, seed, mask, lut_s, ring_s, kStride, counts, hash_off, hashes);
         my_max = max(my_max, total);
         my_sum += total;
     }
@@ -633,41 +637,166 @@ __global__ void __launch_bounds__(k2t::kThreads)
     }
 }
 
-// upper bound of the minimisers of a read (pair): every window could emit (GC.cpp:690-700)
-__global__ void k_hash_upper_bounds(const uint32_t *__restrict__ len1, const uint32_t *__restrict__ len2, uint32_t n, uint32_t w, uint32_t *__restrict__ ub)
+// upper bound of the minimisers of a read (pair): every window could emit (GC.cpp:690-700); items: its segments (k2_thread.cuh);
+// max_windows: the most windows of one mate in the batch
+__global__ void k_hash_upper_bounds(const uint32_t *__restrict__ len1, const uint32_t *__restrict__ len2, uint32_t n, uint32_t w, uint32_t *__restrict__ ub,
+                                    uint32_t *__restrict__ items, uint32_t *__restrict__ max_windows)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    const uint32_t a = len1[i];
-    uint32_t       u = 0;
-    if (a >= w)
+    uint32_t       u = 0, it = 0, mx = 0;
+    if (i < n)
     {
-        u = a - w + 1;
-        if (len2 != nullptr && len2[i] >= w)
-            u += len2[i] - w + 1;
+        const uint32_t a = len1[i];
+        if (a >= w)
+        {
+            u  = a - w + 1;
+            mx = u;
+            it = k2t::segments_of(a, w);
+            if (len2 != nullptr && len2[i] >= w)
+            {
+                u += len2[i] - w + 1;
+                mx = max(mx, len2[i] - w + 1);
+                it += k2t::segments_of(len2[i], w);
+            }
+        }
+        ub[i] = u;
+        if (items != nullptr)
+            items[i] = it;
     }
-    ub[i] = u;
+    if (max_windows != nullptr)
+    {
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0 && mx)
+            atomicMax(max_windows, mx);
+    }
+}
+
+// ---- K2t over segments: long reads (k2_thread.cuh, segment()) ----------------------------------------------------------------
+// One thread per item = (read, mate, segment of kSegWindows windows); item_off[read] = first item of the read.  Hashes go to the
+// upper-bound layout (one slot per window) at the slot of the segment's first window, seg_cnt[item] = count | flag.
+__global__ void __launch_bounds__(k2t::kThreads)
+    k_minimisers_segments(const uint8_t *__restrict__ blk1, const uint32_t *__restrict__ off1, const uint32_t *__restrict__ len1, const uint8_t *__restrict__ blk2,
+                          const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2, uint32_t n_reads, uint32_t k, uint32_t w,
+                          const uint64_t *__restrict__ item_off, const uint64_t *__restrict__ hash_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ seg_cnt)
+{
+    extern __shared__ __align__(16) uint64_t k2t_smem[];
+    k2t::LutEntry *lut = reinterpret_cast<k2t::LutEntry *>(k2t_smem);
+    const uint32_t tid = threadIdx.x;
+    const uint64_t seed = kMinimiserSeed >> (64 - 2 * k);
+    const uint64_t mask = (1ull << (2 * k)) - 1;
+    const uint32_t lut_s  = (uint32_t)__cvta_generic_to_shared(k2t_smem);
+    const uint32_t ring_s = lut_s + k2t::kLutBytes + tid * 8;
+    constexpr uint32_t kStride = k2t::kThreads * 8;
+    for (uint32_t c = tid; c < 256; c += k2t::kThreads)
+        lut[c] = k2t::lut_entry(c, k);
+    __syncthreads();
+    const uint64_t n_items = item_off[n_reads];
+    for (uint64_t first = (uint64_t)blockIdx.x * k2t::kThreads; first < n_items; first += (uint64_t)gridDim.x * k2t::kThreads)
+    {
+        const uint64_t item = first + tid;
+        if (item >= n_items)
+            continue;
+        uint32_t lo = 0, hi = n_reads; // the last read whose first item is <= item (reads without items share their successor's)
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (item_off[mid] <= item)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t read = lo, local = (uint32_t)(item - item_off[read]);
+        const uint32_t L1 = len1[read], s1 = k2t::segments_of(L1, w);
+        const bool     second = local >= s1;
+        const uint8_t *p   = second ? blk2 + off2[read] : blk1 + off1[read];
+        const uint32_t L   = second ? len2[read] : L1;
+        uint64_t      *out = hashes + hash_off[read] + (second ? L1 - w + 1 : 0u);
+        seg_cnt[item]      = k2t::segment(p, L, second ? local - s1 : local, k, w, seed, mask, lut_s, out, ring_s, kStride);
+    }
+}
+
+// One warp per read: the segments' hashes move left to follow each other from hash_off[read] (in place: a destination is never
+// right of its source, and values are read before the lanes store), counts[read] = their sum, flags[read] = a segment was flagged.
+__global__ void __launch_bounds__(256)
+    k_segments_compact(const uint32_t *__restrict__ len1, uint32_t n_reads, uint32_t w, const uint64_t *__restrict__ item_off, const uint64_t *__restrict__ hash_off,
+                       uint64_t *hashes, const uint32_t *__restrict__ seg_cnt, uint32_t *__restrict__ counts, uint8_t *__restrict__ flags)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t read = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; read < n_reads; read += warps)
+    {
+        const uint64_t i0 = item_off[read], i1 = item_off[read + 1];
+        uint32_t       dst = 0, flag = 0;
+        if (i1 - i0 == 1)
+        { // a short read: one segment, already in place
+            const uint32_t c = seg_cnt[i0];
+            dst  = c & ~k2t::kSegFlag;
+            flag = c >> 31;
+        }
+        else if (i1 > i0)
+        {
+            uint64_t *h = hashes + hash_off[read];
+            const uint32_t L1 = len1[read], s1 = k2t::segments_of(L1, w), win1 = L1 - w + 1;
+            for (uint64_t base = i0; base < i1; base += 32)
+            { // 32 segments at a time: counts by the lanes, destinations by a scan
+                const uint32_t m   = (uint32_t)min((uint64_t)32, i1 - base);
+                const uint32_t raw = lane < m ? seg_cnt[base + lane] : 0u;
+                const uint32_t c   = raw & ~k2t::kSegFlag;
+                flag |= __ballot_sync(0xffffffffu, raw >> 31) != 0;
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((int)lane >= d)
+                        incl += t;
+                }
+                for (uint32_t g = 0; g < m; ++g)
+                {
+                    const uint32_t cg    = __shfl_sync(0xffffffffu, c, g);
+                    const uint32_t dg    = dst + __shfl_sync(0xffffffffu, incl, g) - cg;
+                    const uint32_t local = (uint32_t)(base - i0) + g;
+                    const uint32_t src   = local < s1 ? local * k2t::kSegWindows : win1 + (local - s1) * k2t::kSegWindows;
+                    if (src != dg)
+                        for (uint32_t i = 0; i < cg; i += 128)
+                        {
+                            uint64_t v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                v[u] = i + u * 32 + lane < cg ? h[src + i + u * 32 + lane] : 0;
+                            __syncwarp();
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (i + u * 32 + lane < cg)
+                                    h[dg + i + u * 32 + lane] = v[u];
+                            __syncwarp();
+                        }
+                }
+                dst += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        if (lane == 0)
+        {
+            counts[read] = dst;
+            flags[read]  = (uint8_t)flag;
+        }
+    }
 }
 
 } // namespace
 
+static int k2_forced();
+
 void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2,
                        const uint32_t *len2, uint32_t n_reads, uint32_t k, uint32_t w, int mode, uint32_t *counts,
-                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count, cudaStream_t st,
-                       uint32_t avg_windows)
+                       const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count, cudaStream_t st)
 {
     if (n_reads == 0)
         return;
     const uint32_t W      = w - k + 1;
-    // a thread per read needs many reads to fill the GPU: few long sequences (long-read data, genomes) are better served by
-    // the warp-per-read kernel, which walks a sequence in tiles of 128 windows
-    const bool few_long = n_reads < 65536 && avg_windows > 512;
     // K2t is the default where its parameter range allows (measured on B200, c2: 0.99 ms vs 3.07 ms per 2^21 reads);
     // GANON_B200_K2=warp keeps every read on the warp-per-read kernel, =thread every read K2t can take on K2t (read once per process)
-    static const int forced = [] { const char *e = getenv("GANON_B200_K2"); return e && e[0] == 'w' ? 1 : e && e[0] == 't' ? 2 : 0; }();
-    const bool thread_path = forced == 2 || (forced == 0 && !few_long);
-    if (thread_path && k <= k2t::kMaxK && W <= k2t::kMaxW)
+    if (k2_forced() != 1 && k <= k2t::kMaxK && W <= k2t::kMaxW)
     { // K2t: one thread per read, CTAs of 128 reads (k2_thread.cuh)
         int dev_t = 0, sms_t = 148;
         cudaGetDevice(&dev_t);
@@ -677,11 +806,11 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
         const uint32_t cap_t  = (uint32_t)sms_t * 128;         // short-lived CTAs: the tail of the grid stays small
         const uint32_t grid_t = want_t < cap_t ? want_t : cap_t;
         if (mode == 0)
-            k_minimisers_thread<0><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count);
+            k_minimisers_thread<0><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count, nullptr);
         else if (mode == 1)
-            k_minimisers_thread<1><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count);
+            k_minimisers_thread<1><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count, nullptr);
         else
-            k_minimisers_thread<2><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count);
+            k_minimisers_thread<2><<<grid_t, k2t::kThreads, smem_t, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count, nullptr);
         return;
     }
     const uint32_t nv_cap = (K2_TILE + W + 2 + 1) & ~1u;          // values per warp and level
@@ -721,10 +850,49 @@ void launch_minimisers(const uint8_t *blk1, const uint32_t *off1, const uint32_t
 #undef GNB_K2
 }
 
-void launch_hash_upper_bounds(const uint32_t *len1, const uint32_t *len2, uint32_t n, uint32_t w, uint32_t *ub, cudaStream_t st)
+void launch_hash_upper_bounds(const uint32_t *len1, const uint32_t *len2, uint32_t n, uint32_t w, uint32_t *ub, cudaStream_t st, uint32_t *items,
+                              uint32_t *max_windows)
 {
     if (n)
-        k_hash_upper_bounds<<<(n + 255) / 256, 256, 0, st>>>(len1, len2, n, w, ub);
+        k_hash_upper_bounds<<<(n + 255) / 256, 256, 0, st>>>(len1, len2, n, w, ub, items, max_windows);
+}
+
+static int k2_forced() // GANON_B200_K2=warp / =thread: one kernel for every read (read once per process); 0: the library picks
+{
+    static const int forced = [] { const char *e = getenv("GANON_B200_K2"); return e && e[0] == 'w' ? 1 : e && e[0] == 't' ? 2 : 0; }();
+    return forced;
+}
+
+bool minimisers_segmented(uint32_t k, uint32_t w, uint32_t n_reads, uint32_t max_windows)
+{
+    if (k2_forced() != 0 || k > k2t::kMaxK || w - k + 1 > k2t::kMaxW)
+        return false;
+    // a batch of many reads of a few thousand bases fills the GPU with a thread per read; one very long read in it would be its tail
+    return max_windows > 2 * k2t::kSegWindows && (n_reads < 131072 || max_windows > 8 * k2t::kSegWindows);
+}
+
+uint64_t minimiser_segments_bound(uint64_t total_windows, uint32_t n_reads) { return total_windows / k2t::kSegWindows + 2ull * n_reads; }
+
+void launch_minimisers_segmented(const uint8_t *blk1, const uint32_t *off1, const uint32_t *len1, const uint8_t *blk2, const uint32_t *off2, const uint32_t *len2,
+                                 uint32_t n_reads, uint32_t k, uint32_t w, const uint64_t *item_off, uint64_t item_bound, uint32_t *seg_cnt, uint8_t *flags,
+                                 uint32_t *counts, const uint64_t *hash_off, uint64_t *hashes, uint32_t *max_count, unsigned long long *sum_count, cudaStream_t st)
+{
+    if (n_reads == 0)
+        return;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t W    = w - k + 1;
+    const size_t   smem = k2t::kLutBytes + (size_t)W * k2t::kThreads * 8;
+    const uint64_t want = (item_bound + k2t::kThreads - 1) / k2t::kThreads;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms * 128);
+    k_minimisers_segments<<<grid, k2t::kThreads, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, item_off, hash_off, hashes, seg_cnt);
+    const uint32_t grid_c = (uint32_t)std::min<uint64_t>(((uint64_t)n_reads * 32 + 255) / 256, (uint64_t)sms * 64);
+    k_segments_compact<<<grid_c, 256, 0, st>>>(len1, n_reads, w, item_off, hash_off, hashes, seg_cnt, counts, flags);
+    // reads with a flagged segment (repeats all along a warm-up) are walked from the start by one thread; the pass also sums up
+    const uint32_t want_t = (n_reads + k2t::kThreads - 1) / k2t::kThreads;
+    const uint32_t grid_t = std::min<uint32_t>(want_t, (uint32_t)sms * 128);
+    k_minimisers_thread<2><<<grid_t, k2t::kThreads, smem, st>>>(blk1, off1, len1, blk2, off2, len2, n_reads, k, w, counts, hash_off, hashes, max_count, sum_count, flags);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

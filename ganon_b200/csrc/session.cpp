@@ -478,6 +478,7 @@ struct BatchCtx
     PinBuf h_pin;
     // bin-sharded runs: tuple counts of all ranks, the gathered tuple list, host copies of sliced blocks (on demand)
     DevBuf d_xch, d_gather;
+    DevBuf d_seg, d_seg_cnt; // K2t over segments: items per read, their offsets, flags | counts per segment
     PinBuf h_xch;
     std::vector<char> h_blk1_copy, h_blk2_copy;
     bool   host_block_valid = true; // blk1 / blk2 point at the whole block in host memory
@@ -566,7 +567,7 @@ struct BatchCtx
         for (DevBuf *b : {&d_blk1, &d_blk2, &d_off1, &d_len1, &d_off2, &d_len2, &d_idoff, &d_idlen, &d_counts, &d_hash_off, &d_hashes, &d_active,
                           &d_tuples_a, &d_tuples_b, &d_cursor, &d_tmp, &d_lines1, &d_lines2, &d_k1tmp1, &d_k1tmp2, &d_idoff2, &d_idlen2, &d_status,
                           &d_items_a, &d_items_b, &d_items_cursor, &d_tstart, &d_nacc, &d_sizes, &d_offs, &d_one, &d_ftotals, &d_read_level, &d_moff,
-                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc, &d_em_sizes, &d_em_offs, &d_xch, &d_gather})
+                          &d_mt, &d_mc, &d_all, &d_one_txt, &d_unc, &d_em_sizes, &d_em_offs, &d_xch, &d_gather, &d_seg, &d_seg_cnt})
             b->release();
         h_pin.release();
         h_xch.release();
@@ -1781,17 +1782,24 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     // before K2 runs; K2 writes the hashes and the real counts.  If that layout would be too large (very long
     // reads) fall back to count -> scan -> write with exact offsets.
     GNB_TRY(d_tmp.ensure(scan_tmp_bytes(n)));
-    launch_hash_upper_bounds(d_len1.as<uint32_t>(), l2, n, w, d_counts.as<uint32_t>(), st);
+    // segments of long reads (K2t over segments): items per read | their offsets | flags
+    const uint64_t seg_items_at = 0, seg_off_at = (((uint64_t)n * 4 + 7) & ~7ull), seg_flags_at = seg_off_at + ((uint64_t)n + 1) * 8;
+    GNB_TRY(d_seg.ensure(seg_flags_at + n));
+    uint32_t *d_items    = reinterpret_cast<uint32_t *>(d_seg.as<uint8_t>() + seg_items_at);
+    uint64_t *d_item_off = reinterpret_cast<uint64_t *>(d_seg.as<uint8_t>() + seg_off_at);
+    uint32_t *d_max_windows = d_status.as<uint32_t>() + 13;
+    launch_hash_upper_bounds(d_len1.as<uint32_t>(), l2, n, w, d_counts.as<uint32_t>(), st, d_items, d_max_windows);
     launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
     launches += 2;
     uint64_t total_ub = 0;
+    uint32_t max_windows = 0;
     GNB_CUDA(cudaMemcpyAsync(&total_ub, d_hash_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    GNB_CUDA(cudaMemcpyAsync(&max_windows, d_max_windows, 4, cudaMemcpyDeviceToHost, st));
     GNB_CUDA(stream_wait(st));
     trace_mark(this, "k2.scan_done");
-    timing.d2h_bytes += 8;
+    timing.d2h_bytes += 12;
     uint64_t total = 0;
     uint32_t mx    = 0;
-    const uint32_t avg_windows = (uint32_t)std::min<uint64_t>(total_ub / n, 0xffffffffu); // windows per read (pair): picks the K2 kernel
     struct
     {
         uint32_t           mx, pad;
@@ -1800,9 +1808,22 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     if (total_ub * 8 <= (6ull << 30))
     {
         GNB_TRY(d_hashes.ensure((total_ub + 1) * 8));
-        launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 2,
-                          d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), d_max, d_sum, st, avg_windows);
-        launches += 1;
+        if (minimisers_segmented(k, w, n, max_windows))
+        { // long reads: a thread per segment of 512 windows, then the segments of a read are moved together
+            const uint64_t bound = minimiser_segments_bound(total_ub, n);
+            GNB_TRY(d_seg_cnt.ensure(bound * 4));
+            launch_scan_counts(d_items, d_item_off, n, d_tmp.p, d_tmp.cap, st);
+            launch_minimisers_segmented(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w,
+                                        d_item_off, bound, d_seg_cnt.as<uint32_t>(), d_seg.as<uint8_t>() + seg_flags_at, d_counts.as<uint32_t>(),
+                                        d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), d_max, d_sum, st);
+            launches += 4;
+        }
+        else
+        {
+            launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 2,
+                              d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), d_max, d_sum, st);
+            launches += 1;
+        }
         GNB_CUDA(cudaEventRecord(ev[3], st));
         GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
         GNB_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -1815,7 +1836,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
     else
     {
         launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 0,
-                          d_counts.as<uint32_t>(), nullptr, nullptr, d_max, d_sum, st, avg_windows);
+                          d_counts.as<uint32_t>(), nullptr, nullptr, d_max, d_sum, st);
         launch_scan_counts(d_counts.as<uint32_t>(), d_hash_off.as<uint64_t>(), n, d_tmp.p, d_tmp.cap, st);
         launches += 2;
         GNB_CUDA(cudaMemcpyAsync(&agg, d_max, 16, cudaMemcpyDeviceToHost, st));
@@ -1825,7 +1846,7 @@ int BatchCtx::compute_hashes(uint32_t k, uint32_t w)
         mx    = agg.mx;
         GNB_TRY(d_hashes.ensure((total + 1) * 8));
         launch_minimisers(d_blk1.as<uint8_t>(), d_off1.as<uint32_t>(), d_len1.as<uint32_t>(), b2, d_off2.as<uint32_t>(), d_len2.as<uint32_t>(), n, k, w, 1,
-                          nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, nullptr, st, avg_windows);
+                          nullptr, d_hash_off.as<uint64_t>(), d_hashes.as<uint64_t>(), nullptr, nullptr, st);
         launches += 1;
         GNB_CUDA(cudaEventRecord(ev[3], st));
         d_counts_valid = true; // exact layout: counts equal the offset differences
@@ -3953,9 +3974,58 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         GNB_CUDA(cudaMemcpy(d_seq.p, seqs, seq_off[n], cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_off.p, off.data(), n * 4, cudaMemcpyHostToDevice));
         GNB_CUDA(cudaMemcpy(d_len.p, len.data(), n * 4, cudaMemcpyHostToDevice));
-        const uint32_t avg_windows = (uint32_t)std::min<uint64_t>(seq_off[n] / n, 0xffffffffu);
+        uint32_t max_windows = 0;
+        uint64_t windows     = 0;
+        for (uint64_t i = 0; i < n; ++i)
+            if (len[i] >= w)
+            {
+                max_windows = std::max(max_windows, len[i] - w + 1);
+                windows += len[i] - w + 1;
+            }
+        if (minimisers_segmented(k, w, (uint32_t)n, max_windows))
+        { // the session's path for long reads: one slot per window, a thread per segment, the lists moved together on the host side here
+            DevBuf d_ub, d_uoff, d_items, d_ioff, d_seg_cnt, d_flags;
+            auto   drop = [&]() {
+                for (DevBuf *b : {&d_ub, &d_uoff, &d_items, &d_ioff, &d_seg_cnt, &d_flags})
+                    b->release();
+            };
+            auto seg = [&]() -> int {
+                const uint64_t bound = minimiser_segments_bound(windows, (uint32_t)n);
+                GNB_TRY(d_ub.ensure(n * 4));
+                GNB_TRY(d_uoff.ensure((n + 1) * 8));
+                GNB_TRY(d_items.ensure(n * 4));
+                GNB_TRY(d_ioff.ensure((n + 1) * 8));
+                GNB_TRY(d_seg_cnt.ensure(bound * 4));
+                GNB_TRY(d_flags.ensure(n));
+                GNB_TRY(d_h.ensure((windows + 1) * 8));
+                launch_hash_upper_bounds(d_len.as<uint32_t>(), nullptr, (uint32_t)n, w, d_ub.as<uint32_t>(), 0, d_items.as<uint32_t>(), nullptr);
+                launch_scan_counts(d_ub.as<uint32_t>(), d_uoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
+                launch_scan_counts(d_items.as<uint32_t>(), d_ioff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
+                launch_minimisers_segmented(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w,
+                                            d_ioff.as<uint64_t>(), bound, d_seg_cnt.as<uint32_t>(), d_flags.as<uint8_t>(), d_cnt.as<uint32_t>(), d_uoff.as<uint64_t>(),
+                                            d_h.as<uint64_t>(), nullptr, nullptr, 0);
+                std::vector<uint32_t> cnt(n);
+                std::vector<uint64_t> uoff(n + 1);
+                GNB_CUDA(cudaMemcpy(cnt.data(), d_cnt.p, n * 4, cudaMemcpyDeviceToHost));
+                GNB_CUDA(cudaMemcpy(uoff.data(), d_uoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
+                for (uint64_t i = 0; i < n; ++i)
+                    hash_off[i + 1] = hash_off[i] + cnt[i];
+                if (hashes && hash_off[n] <= cap && windows)
+                {
+                    std::vector<uint64_t> slots(windows);
+                    GNB_CUDA(cudaMemcpy(slots.data(), d_h.p, windows * 8, cudaMemcpyDeviceToHost));
+                    for (uint64_t i = 0; i < n; ++i)
+                        memcpy(hashes + hash_off[i], slots.data() + uoff[i], (size_t)cnt[i] * 8);
+                }
+                GNB_CUDA(cudaGetLastError());
+                return GNB_OK;
+            };
+            const int rc_seg = seg();
+            drop();
+            return rc_seg;
+        }
         launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, 0,
-                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, 0, avg_windows);
+                          d_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, 0);
         launch_scan_counts(d_cnt.as<uint32_t>(), d_hoff.as<uint64_t>(), (uint32_t)n, d_tmp.p, d_tmp.cap, 0);
         GNB_CUDA(cudaMemcpy(hash_off, d_hoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
         const uint64_t total = hash_off[n];
@@ -3963,7 +4033,7 @@ extern "C" int gnb_minimisers_batch(int device, uint32_t k, uint32_t w, const ch
         {
             GNB_TRY(d_h.ensure(total * 8));
             launch_minimisers(d_seq.as<uint8_t>(), d_off.as<uint32_t>(), d_len.as<uint32_t>(), nullptr, nullptr, nullptr, (uint32_t)n, k, w, 1, nullptr,
-                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, nullptr, 0, avg_windows);
+                              d_hoff.as<uint64_t>(), d_h.as<uint64_t>(), nullptr, nullptr, 0);
             GNB_CUDA(cudaMemcpy(hashes, d_h.p, total * 8, cudaMemcpyDeviceToHost));
         }
         GNB_CUDA(cudaGetLastError());

@@ -69,3 +69,32 @@ extern "C" long k2t_host_batch(const uint8_t *blk1, const uint32_t *off1, const 
     free(ring);
     return (long)sum;
 }
+
+// A long sequence through k2t::segment, one call per segment as the segment kernel's threads make them: out has one slot per
+// window (segment g writes from slot g * kSegWindows), seg_cnt[g] = count | kSegFlag.  Returns the number of segments.
+extern "C" long k2t_host_segments(const uint8_t *seq, uint32_t L, uint32_t k, uint32_t w, uint32_t misalign, uint32_t stride, uint32_t lane, uint64_t *out,
+                                  uint32_t *seg_cnt)
+{
+    if (k < 1 || k > k2t::kMaxK || w < k || w - k + 1 > k2t::kMaxW || L < w || lane >= stride)
+        return -1;
+    const uint32_t W   = w - k + 1;
+    uint8_t       *raw = (uint8_t *)aligned_alloc(64, ((size_t)L + 128 + 63) / 64 * 64);
+    memset(raw, '#', (size_t)L + 128);
+    uint8_t *p = raw + 64 + (misalign & 7);
+    memcpy(p, seq, L);
+    uint64_t      *ring = (uint64_t *)malloc((size_t)W * stride * 8);
+    const uint64_t seed = 0x8F3F73B5CF1C9ADEull >> (64 - 2 * k);
+    const uint64_t mask = (1ull << (2 * k)) - 1;
+    k2t::LutEntry  lut[256];
+    for (uint32_t c = 0; c < 256; ++c)
+        lut[c] = k2t::lut_entry(c, k);
+    const uint32_t n_seg = k2t::segments_of(L, w);
+    for (uint32_t g = 0; g < n_seg; ++g)
+    {
+        memset(ring, 0xA5 ^ g, (size_t)W * stride * 8);
+        seg_cnt[g] = k2t::segment(p, L, g, k, w, seed, mask, (k2t::saddr_t)lut, out, (k2t::saddr_t)(ring + lane), stride * 8);
+    }
+    free(ring);
+    free(raw);
+    return n_seg;
+}

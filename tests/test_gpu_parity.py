@@ -44,26 +44,25 @@ def test_minimisers_random_and_adversarial(k, w):
 
 @pytest.mark.parametrize("kernel", ["warp", "thread"])
 def test_either_minimiser_kernel_alone_passes_the_k2_and_scenario_tests(kernel):
-    """For k <= 29, w-k+1 <= 32 the library picks per batch: the thread-per-read kernel (k2_thread.cuh), or the warp-per-read
-    kernel when the batch is a few long sequences (< 65536 reads averaging > 512 windows) -- and the warp kernel for every other
-    (k, w).  GANON_B200_K2=warp / =thread (read once per process) pin one kernel: re-run the K2 tests, the golden scenarios
-    (single, paired, FASTA, several levels) and the oracle session test of this file in a child process under each, so that
-    both kernels stay pinned on short and on long sequences."""
+    """For k <= 29, w-k+1 <= 32 the library runs the thread-per-read kernel (k2_thread.cuh), over segments when the batch holds
+    long reads, and the warp-per-read kernel for every other (k, w).  GANON_B200_K2=warp / =thread (read once per process) pin
+    one kernel on whole reads: re-run the K2 tests, the golden scenarios (single, paired, FASTA, several levels) and the oracle
+    session tests of this file in a child process under each, so that all three stay pinned on short and on long sequences."""
     import subprocess
     import sys
 
     if os.environ.get("GANON_B200_K2", ""):
         pytest.skip("already inside the child run")
     env = dict(os.environ, GANON_B200_K2=kernel)
-    sel = "minimisers_seqan3 or minimisers_random or long_sequence or (golden_scenarios and device) or session_matches_oracle or device_and_host_record_index"
+    sel = "minimisers_seqan3 or minimisers_random or long_sequence or long_read_session or (golden_scenarios and device) or session_matches_oracle or device_and_host_record_index"
     done = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", sel, "-p", "no:cacheprovider"], env=env,
                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert done.returncode == 0, done.stdout[-2000:]
 
 
 def test_long_sequence_batches_hash_like_the_oracle():
-    """A batch of a few long reads (the shape that goes to the warp kernel by default) and the same reads inside a batch of
-    many short ones (which keeps them on K2t): same minimisers as the oracle either way."""
+    """A batch of a few long reads and the same reads inside batches of many short ones (K2t over segments of 512 windows;
+    GANON_B200_K2=thread / =warp walk every read whole): same minimisers as the oracle either way."""
     rng = np.random.default_rng(77)
     long_reads = [bytes(rng.choice(list(b"ACGTN"), p=[0.2499, 0.2499, 0.2499, 0.2499, 0.0004], size=n).astype(np.uint8)) for n in (30_000, 2_000, 70_001, 640)]
     want = [O.minimiser_hash(s, 19, 31) for s in long_reads]
@@ -81,6 +80,20 @@ def test_long_sequence_batches_hash_like_the_oracle():
         j = 35_000 + i
         assert np.array_equal(h[int(hoff[j]) : int(hoff[j + 1])], wnt), i
     assert np.array_equal(h[: int(hoff[1])], O.minimiser_hash(short[0], 19, 31))
+    # repeats: homopolymers and tandem repeats keep equal values in every window -- segments inside them cannot know the state
+    # of the walk and hand their read to one thread; around their ends either outcome must be exact
+    rnd = lambda n: bytes(rng.choice(list(b"ACGT"), size=n).astype(np.uint8))
+    odd = [b"A" * 9000, b"TTAGGG" * 1500, rnd(1700) + b"C" * 2600 + rnd(3000), rnd(5000) + b"AT" * 900, b"GA" * 333 + rnd(4000) + b"N" * 1500 + rnd(30),
+           bytes(rng.choice(list(b"AT"), size=6000).astype(np.uint8)), rnd(37) * 200]
+    for k, w in ((19, 31), (4, 8), (29, 60), (12, 12), (10, 41)):
+        hoff, h = minimisers_batch(odd + long_reads, k, w)
+        for i, s in enumerate(odd + long_reads):
+            assert np.array_equal(h[int(hoff[i]) : int(hoff[i + 1])], O.minimiser_hash(s, k, w)), (k, w, i)
+    # a big batch keeps reads of a few thousand bases on a thread each and cuts only from 4096 windows on
+    many = short + short
+    hoff, h = minimisers_batch(many[:100] + [long_reads[1], long_reads[0]] + many[100:], 19, 31)
+    for j, s in ((100, long_reads[1]), (101, long_reads[0]), (102, many[100]), (len(many) + 1, many[-1])):
+        assert np.array_equal(h[int(hoff[j]) : int(hoff[j + 1])], O.minimiser_hash(s, 19, 31)), j
 
 
 # ------------------------------------------------------------------------------------------------------------------ K3
@@ -264,6 +277,58 @@ def test_session_matches_oracle_multibin_targets_and_blocks(finish_mode):
         assert t.input_seqs == len(reads) and t.seqs_skipped_small == 1 and t.seqs_classified == sum(1 for r in want if r["matches"])
         assert t.discarded_matches_filter == sum(len(r["discarded_filter"]) for r in want)
         assert t.discarded_matches_fprquery == sum(len(r["discarded_fpr"]) for r in want)
+        sess.close()
+    db.close()
+
+
+def test_long_read_session_matches_oracle():
+    """Long reads (tens of kbp: K2t over segments of 512 windows), single and paired, mixed with short ones and with reads that
+    hold homopolymers and tandem repeats (segments inside them are flagged and their read is walked from the start): hash counts
+    and classification like the oracle's."""
+    rng = np.random.default_rng(41)
+    k, w, h = 19, 31, 3
+    names = ["g%d" % i for i in range(24)]
+    genomes = [bytes(rng.choice(list(b"ACGT"), size=40_000).astype(np.uint8)) for _ in names]
+    db = Database.create(len(names), 60_013, h, k, w)
+    hs, bs, counts = [], [], []
+    for t, g in enumerate(genomes):
+        u = np.unique(O.minimiser_hash(g, k, w))
+        hs.append(u)
+        bs.append(np.full(u.size, t, dtype=np.uint32))
+        counts.append(u.size)
+    db.emplace(np.concatenate(hs), np.concatenate(bs))
+    db.set_targets(names, list(range(len(names))), counts, max(counts))
+    rc = lambda x: x[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))
+    reads = []
+    for i in range(60):
+        g = genomes[int(rng.integers(0, len(names)))]
+        n = int(rng.choice([150, 600, 1100, 5_000, 12_345, 30_000]))
+        p = int(rng.integers(0, len(g) - n + 1))
+        m1 = bytearray(g[p : p + n])
+        for _ in range(n // 400):
+            m1[int(rng.integers(0, n))] = rng.choice(list(b"ACGTN"))
+        if i % 7 == 0 and n > 3000:  # a homopolymer / a tandem repeat over a few segments, or up to the end of the read
+            a = int(rng.integers(0, n // 2))
+            rep = (b"A", b"TTAGGG", b"CA")[i // 7 % 3]
+            ln = n - a if i % 14 == 0 else int(rng.integers(700, 2500))
+            m1[a : a + ln] = (rep * (ln // len(rep) + 1))[: min(ln, n - a)]
+        m2 = rc(g[p : p + n])[: int(rng.choice([20, 150, 4000, n]))]
+        reads.append((b"lr%d" % i, bytes(m1), m2))
+    info = db.info()
+    oibf = O.OracleIBF(info.bins, info.bin_size_bits, info.hash_functions, db.read_words(0, info.bin_size_bits * info.bin_words))
+    fpr = [t[1] for t in db.targets()]
+    filt = O.OracleFilter(oibf, names, [[t] for t in range(len(names))], fpr, 0.2, k, w)
+    for paired in (False, True):
+        rs = reads if paired else [(i, a, None) for i, a, _ in reads]
+        want = O.classify_level([filt], rs, 0.1, 1.0)
+        fq1 = b"".join(b"@%s\n%s\n+\n%s\n" % (i, a, b"F" * len(a)) for i, a, _ in rs)
+        fq2 = b"".join(b"@%s\n%s\n+\n%s\n" % (i, c, b"F" * len(c)) for i, _, c in rs) if paired else None
+        sess = Session([db], [0.2], [0.1], [1.0], output_all=True, output_unclassified=True)
+        res = sess.classify(fq1, fq2, final=True)
+        assert [res.n_hashes[i] for i in range(res.n_reads)] == [r["n_hashes"] for r in want], paired
+        assert max(r["n_hashes"] for r in want) > 3000
+        assert sorted(result_text(res, "all").decode().splitlines()) == O.all_lines(want)
+        assert sorted(result_text(res, "unc").decode().splitlines()) == sorted(r["id"].decode() for r in want if not r["matches"])
         sess.close()
     db.close()
 

@@ -12,6 +12,7 @@ import pytest
 from oracle import oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEG, WARM = 512, 64  # k2t::kSegWindows, kSegWarm
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +35,20 @@ def k2t(tmp_path_factory):
         assert n >= 0, (n, k, w, len(seq))
         return out[:n]
 
+    lib.k2t_host_segments.restype = ctypes.c_long
+    lib.k2t_host_segments.argtypes = [ctypes.c_char_p] + [ctypes.c_uint32] * 6 + [ctypes.c_void_p, ctypes.c_void_p]
+
+    def segments(seq, k, w, misalign=0, stride=1, lane=0):
+        """[(values emitted by the segment, flagged)] of k2t::segment over every segment of seq."""
+        windows = len(seq) - w + 1
+        out = np.full(windows + 1, 0xDEAD, dtype=np.uint64)
+        cnt = np.zeros((windows + SEG - 1) // SEG + 1, dtype=np.uint32)
+        n = lib.k2t_host_segments(seq, len(seq), k, w, misalign, stride, lane, out.ctypes.data, cnt.ctypes.data)
+        assert n == (windows + SEG - 1) // SEG
+        return [(out[g * SEG : g * SEG + int(cnt[g] & 0x7FFFFFFF)], bool(cnt[g] >> 31)) for g in range(n)]
+
     run.batch = lib.k2t_host_batch
+    run.segments = segments
     return run
 
 
@@ -139,3 +153,93 @@ def test_batches_follow_the_classify_rules(k2t, k, w, paired):
     assert counts2.tolist() == counts.tolist()
     for i in range(n):
         assert hashes2[int(off2[i]) : int(off2[i]) + int(counts2[i])].tolist() == want[i].tolist(), i
+
+
+# --------------------------------------------------------------------------------------------------- segments of long sequences
+def _emissions(seq, k, w):
+    """(window index, value) of every minimiser the reference's state machine emits (minimiser.hpp:421-472), written out window by
+    window: the k-mer values come from the oracle (window = k: one value per k-mer); pinned to the oracle's list below."""
+    vals = O.minimiser_hash(seq, k, k).tolist()
+    assert len(vals) == len(seq) - k + 1
+    W = w - k + 1
+    rightmost_min = lambda a: max(i for i, v in enumerate(a) if v == min(a))
+    pos = rightmost_min(vals[:W])  # absolute k-mer index of the tracked minimiser
+    out = [(0, vals[pos])]
+    for j in range(W, len(vals)):  # k-mer j enters, window index j - W + 1
+        if pos == j - W:
+            pos = j - W + 1 + rightmost_min(vals[j - W + 1 : j + 1])
+            out.append((j - W + 1, vals[pos]))
+        elif vals[j] < vals[pos]:
+            pos = j
+            out.append((j - W + 1, vals[j]))
+    assert [v for _, v in out] == O.minimiser_hash(seq, k, w).tolist()
+    return out
+
+
+def _check_segments(k2t, seq, k, w, **kw):
+    """Every segment that is not flagged holds exactly the reference's minimisers of its windows; returns the flags."""
+    want = _emissions(seq, k, w)
+    got = k2t.segments(seq, k, w, **kw)
+    for g, (vals, flagged) in enumerate(got):
+        if not flagged:
+            assert vals.tolist() == [v for j, v in want if g * SEG <= j < (g + 1) * SEG], (g, k, w, len(seq), seq[:50])
+    assert not got[0][1]  # the first segment starts where the sequence does
+    return [f for _, f in got]
+
+
+@pytest.mark.parametrize("k,w", [(19, 31), (4, 8), (29, 60), (12, 12), (1, 32), (10, 41), (27, 29)])
+def test_segments_of_random_sequences_are_exact_and_never_flagged(k2t, k, w):
+    rng = np.random.default_rng(k * 77 + w)
+    for i, L in enumerate([w + SEG - 1, w + SEG, w + SEG + 1, w + 2 * SEG - 1, w + 2 * SEG, 3000, 5 * SEG + w + 17]):
+        seq = bytes(rng.choice(list(b"ACGT"), size=L).astype(np.uint8))
+        flags = _check_segments(k2t, seq, k, w, misalign=i & 7, stride=1 + i % 3, lane=i % (1 + i % 3))
+        if k >= 10:  # no repeated k-mer within a window in random text of this k: every warm-up reaches a certain state
+            assert not any(flags), (k, w, L)
+
+
+def test_segments_inside_repeats_are_flagged_not_wrong(k2t):
+    """Homopolymers and tandem repeats with a period below the window keep equal values in every window: the state of a walk that
+    starts inside depends on where the repeat began, so those segments must come back flagged; the segments after the repeat
+    ended (a warm-up past it) are exact again."""
+    rng = np.random.default_rng(5)
+    rnd = lambda n: bytes(rng.choice(list(b"ACGT"), size=n).astype(np.uint8))
+    k, w = 19, 31
+    flags = _check_segments(k2t, b"A" * 3000, k, w)
+    assert flags == [False] + [True] * (len(flags) - 1)
+    flags = _check_segments(k2t, b"TTAGGG" * 500, k, w)
+    assert all(flags[1:])
+    flags = _check_segments(k2t, rnd(700) + b"A" * 1500 + rnd(1500), k, w)  # repeat over windows ~[690, 2200)
+    assert flags[:2] == [False, False] and flags[2:5] == [True, True, True] and not any(flags[5:])
+    flags = _check_segments(k2t, rnd(600) + b"AC" * 40 + rnd(1400), k, w)  # a short repeat away from the segment boundaries
+    assert not any(flags)
+    # a repeat that ends inside the warm-up of a segment: exact without a flag if a certain event follows, flagged otherwise
+    for tail in range(0, WARM + 8, 3):
+        _check_segments(k2t, rnd(100) + b"CA" * 180 + rnd(2 * SEG + 40)[: SEG + 200 + tail], k, w)
+        seq = rnd(SEG - 200 - tail) + b"G" * (200 + k) + rnd(SEG + 300)
+        _check_segments(k2t, seq, k, w)
+
+
+def test_segments_random_parameters(k2t):
+    rng = np.random.default_rng(2026101718)
+    alphabets = [b"ACGT", b"AC", b"A", b"ACGTN", b"AT", b"ACGTRYKMSWBDHVN"]
+    n_flagged = n_seg = 0
+    for it in range(250):
+        k = int(rng.integers(1, 30))
+        W = int(rng.integers(1, 33))
+        w = k + W - 1
+        L = w + int(rng.integers(SEG - 2, 4 * SEG))
+        a = alphabets[int(rng.integers(0, len(alphabets)))]
+        parts, left = [], L
+        while left > 0:  # random text interleaved with repeats of random period and length
+            n = min(left, int(rng.integers(1, 900)))
+            if rng.random() < 0.4:
+                per = int(rng.integers(1, 12))
+                parts.append((bytes(rng.choice(list(a), size=per).astype(np.uint8)) * (n // per + 1))[:n])
+            else:
+                parts.append(bytes(rng.choice(list(a), size=n).astype(np.uint8)))
+            left -= n
+        stride = int(rng.integers(1, 6))
+        flags = _check_segments(k2t, b"".join(parts), k, w, misalign=int(rng.integers(0, 8)), stride=stride, lane=int(rng.integers(0, stride)))
+        n_flagged += sum(flags)
+        n_seg += len(flags)
+    assert 0 < n_flagged < n_seg  # both outcomes were exercised
