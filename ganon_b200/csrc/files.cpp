@@ -108,23 +108,54 @@ class BlockStream
         worker_.join();
         release();
     }
+    // Buffers are page-locked when they are first used (pinning 64 MiB takes tens of milliseconds: a ring pinned up front
+    // cost 0.3 s before the first byte was read, and a small file never needs most of it); the prefetch thread pins the
+    // buffer it fills and, once idle, the one after it.
     int alloc()
     {
         release();
-        for (auto &b : bufs_)
-            if ((b = PinnedPool::instance().get(head_ + block_ + 64)) == nullptr)
-                return fail(GNB_ERR_CUDA, "cannot allocate page-locked read buffers");
         cur_ = -1;
         return GNB_OK;
     }
     void release()
     {
+        std::lock_guard<std::mutex> l(alloc_mu_);
+        ++gen_;
         for (auto &b : bufs_)
             if (b)
             {
                 PinnedPool::instance().put(b);
                 b = nullptr;
             }
+    }
+    void resize(size_t head, size_t block)
+    {
+        std::lock_guard<std::mutex> l(alloc_mu_);
+        head_  = head;
+        block_ = block;
+        ++gen_;
+    }
+    char *buffer(int idx)
+    {
+        for (;;)
+        {
+            size_t   bytes;
+            uint64_t gen;
+            {
+                std::lock_guard<std::mutex> l(alloc_mu_);
+                if (bufs_[idx] != nullptr)
+                    return bufs_[idx];
+                bytes = head_ + block_ + 64;
+                gen   = gen_;
+            }
+            char *p = PinnedPool::instance().get(bytes); // not under the lock: the other thread keeps using its buffers
+            if (p == nullptr)
+                return nullptr;
+            std::lock_guard<std::mutex> l(alloc_mu_);
+            if (gen == gen_ && bufs_[idx] == nullptr)
+                return bufs_[idx] = p;
+            PinnedPool::instance().put(p); // the ring was rebuilt with other sizes meanwhile, or the other thread was first
+        }
     }
     const char *ptr() const { return positional_ ? bufs_[cur_] : bufs_[cur_] + start_; }
     size_t      fill() const { return fill_; }
@@ -144,6 +175,8 @@ class BlockStream
             const uint64_t N = (uint64_t)n_ranks_, r = (uint64_t)rank_;
             const uint64_t slice = (((n + N - 1) / N) + 15) & ~15ull; // the session's slicing rule (stage(), session.cpp)
             const uint64_t lo = std::min(n, r * slice), hi = std::min(n, (r + 1) * slice);
+            if (buffer(idx) == nullptr)
+                return fail(GNB_ERR_CUDA, "cannot allocate page-locked read buffers");
             if (hi > lo)
             {
                 const int64_t got = src_->read_at(bufs_[idx] + lo, hi - lo, pos_ + lo);
@@ -164,12 +197,14 @@ class BlockStream
                 fresh.assign(bufs_[idx] + head_, (size_t)pf_n_);
             const bool had = pf_idx_ == idx;
             const int64_t n_prev = pf_n_;
-            head_ = 2 * tail_.size();
+            resize(2 * tail_.size(), block_);
             GNB_TRY(alloc());
             if (had)
             {
                 if (n_prev < 0)
                     return fail(GNB_ERR_IO, src_->error());
+                if (buffer(0) == nullptr)
+                    return fail(GNB_ERR_CUDA, "cannot allocate page-locked read buffers");
                 memcpy(bufs_[0] + head_, fresh.data(), fresh.size());
                 pf_idx_ = 0;
             }
@@ -189,7 +224,7 @@ class BlockStream
     {
         if (positional_)
         {
-            block_ *= 2;
+            resize(head_, block_ * 2);
             return alloc();
         }
         wait_prefetch();
@@ -199,8 +234,7 @@ class BlockStream
         if (pf_idx_ >= 0 && pf_n_ < 0)
             return fail(GNB_ERR_IO, src_->error());
         pf_idx_ = -1;
-        block_ *= 2;
-        head_ = std::max(head_, 2 * tail_.size());
+        resize(std::max(head_, 2 * tail_.size()), block_ * 2);
         return alloc();
     }
 
@@ -214,11 +248,13 @@ class BlockStream
         {
             wait_prefetch();
             if (pf_n_ < 0)
-                return fail(GNB_ERR_IO, src_->error());
+                return fail(pf_n_ == GNB_ERR_CUDA ? GNB_ERR_CUDA : GNB_ERR_IO, pf_n_ == GNB_ERR_CUDA ? "cannot allocate page-locked read buffers" : src_->error());
             fresh   = pf_n_;
             pf_idx_ = -1;
         }
         cur_ = idx;
+        if (buffer(idx) == nullptr)
+            return fail(GNB_ERR_CUDA, "cannot allocate page-locked read buffers");
         memcpy(bufs_[idx] + head_ - tail_.size(), tail_.data(), tail_.size());
         start_ = head_ - tail_.size();
         fill_  = tail_.size() + (size_t)fresh;
@@ -253,9 +289,12 @@ class BlockStream
                 idx = pf_idx_;
             }
             int64_t total = 0;
-            while ((size_t)total < block_)
+            char   *buf   = buffer(idx);
+            if (buf == nullptr)
+                total = GNB_ERR_CUDA;
+            while (buf != nullptr && (size_t)total < block_)
             {
-                const int64_t got = src_->read(bufs_[idx] + head_ + total, block_ - (size_t)total);
+                const int64_t got = src_->read(buf + head_ + total, block_ - (size_t)total);
                 if (got < 0)
                 {
                     total = got;
@@ -270,10 +309,14 @@ class BlockStream
             }
             if (total > 0)
                 bytes_in_ += (uint64_t)total;
-            std::lock_guard<std::mutex> l(mu_);
-            pf_n_    = total;
-            pf_busy_ = false;
-            cv_.notify_all();
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                pf_n_    = total;
+                pf_busy_ = false;
+                cv_.notify_all();
+            }
+            if (total > 0 && !raw_eof_)
+                buffer((idx + 1) % (int)bufs_.size()); // idle until the next request: pin the buffer it will name
         }
     }
 
@@ -282,6 +325,7 @@ class BlockStream
     bool                        positional_;
     int                         rank_, n_ranks_;
     std::vector<char *>         bufs_;
+    uint64_t                    gen_ = 0; // counts rebuilds of the ring (alloc_mu_)
     int                         cur_ = -1;
     size_t                      start_ = 0, fill_ = 0;
     std::string                 tail_;
@@ -289,7 +333,7 @@ class BlockStream
     volatile bool               raw_eof_ = false;
     uint64_t                    pos_ = 0, bytes_in_ = 0;
     std::thread                 worker_;
-    std::mutex                  mu_;
+    std::mutex                  mu_, alloc_mu_; // alloc_mu_: bufs_ entries
     std::condition_variable     cv_;
     int                         pf_idx_ = -1;
     int64_t                     pf_n_ = 0;

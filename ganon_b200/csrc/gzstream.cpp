@@ -3,11 +3,15 @@
 #include "gzstream.h"
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
+#endif
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
 #endif
 
 #include <algorithm>
@@ -48,7 +52,6 @@ class Pool
         for (auto &t : workers_)
             t.join();
     }
-    int  size() const { return (int)workers_.size() + 1; }
     void parallel_for(size_t n, const std::function<void(size_t)> &fn)
     {
         if (n == 0)
@@ -287,7 +290,8 @@ struct BitIn
 
 // Packed tables for the decode loop, indexed by the next 11 (literal/length) or 9 (distance) stream bits:
 //   literal/length: bits 0-3 code length (0 = longer code: bit-serial walk), bits 4-5 kind (0 literal, 1 end of block,
-//                   2 length, 3 invalid symbol), bits 8-23 literal byte or length base, bits 24-27 extra bits
+//                   2 length, 3 invalid symbol), bits 8-23 literal byte or length base, bits 24-27 extra bits;
+//                   bit 6: TWO literals (bytes in bits 8-15 and 16-23, bits 0-3 = both code lengths together)
 //   distance:       bits 0-3 code length, bits 4-7 extra bits, bits 8-23 base, bit 31 invalid symbol
 struct DynHeader
 {
@@ -316,6 +320,15 @@ struct DynHeader
         {
             const uint16_t e = lit.table[i];
             ltab[i]          = (e & 15) ? pack_lit(e >> 4, e & 15) : 0;
+            // two literals whose codes both lie inside the 11 index bits: one entry, one step (bit 6; second byte in 16-23)
+            const int l1 = e & 15;
+            if (l1 != 0 && l1 < 11 && (e >> 4) < 256)
+            {
+                const uint16_t e2 = lit.table[i >> l1];
+                const int      l2 = e2 & 15;
+                if (l2 != 0 && l1 + l2 <= 11 && (e2 >> 4) < 256)
+                    ltab[i] = (uint32_t)(l1 + l2) | (1u << 6) | ((uint32_t)(e >> 4) << 8) | ((uint32_t)(e2 >> 4) << 16);
+            }
         }
         for (int i = 0; i < (1 << 9); ++i)
         {
@@ -474,6 +487,159 @@ bool read_gzip_header(BitIn &in)
     return true;
 }
 
+// The symbols of one Huffman block from the bit buffer (bb, cnt, p) into out[o..]: 0 at the end-of-block symbol, 1 when o
+// came within a match of `stop` (the caller makes room and calls again: the state carries over), < 0 = -(index + 1) into
+// kInflateErrors.  Everything the loop touches lives in locals of this function (the caller's variables are captured by its
+// lambdas, which would keep them in memory and put a store-to-load round trip on every symbol).
+const char *const kInflateErrors[] = {"unexpected end of the gzip stream", "invalid literal/length code", "invalid literal/length symbol", "invalid distance code",
+                                      "invalid distance symbol"};
+
+__attribute__((noinline)) int inflate_symbols(const DynHeader &H, const uint8_t *&p_io, uint64_t &bb_io, int &cnt_io, const uint8_t *const p_end,
+                                              uint16_t *const out, size_t &o_io, size_t stop)
+{
+    const Huff     &L = H.lit, &D = H.dist;
+    const uint32_t *const ltab = H.ltab, *const dtab = H.dtab;
+    const uint8_t *p   = p_io;
+    uint64_t       bb  = bb_io;
+    int            cnt = cnt_io;
+    uint16_t      *wp  = out + o_io;
+    uint16_t *const wstop = out + stop - 300; // a match is at most 258 symbols (+ 7 of a copy step)
+    int            rc  = 0;
+    // one or two literals of a table entry: both slots are written, the second one counts only for a double entry
+#define GNB_PUT_LITERALS(e)                                                         \
+    do                                                                              \
+    {                                                                               \
+        const uint32_t two_ = (((e) >> 8) & 0xffu) | ((((e) >> 16) & 0xffu) << 16); \
+        memcpy(wp, &two_, 4);                                                       \
+        wp += 1 + (((e) >> 6) & 1u);                                                \
+    } while (0)
+#define GNB_REFILL()                       \
+    do                                     \
+    {                                      \
+        bb |= load64(p) << cnt;            \
+        p += (63 - cnt) >> 3;              \
+        cnt |= 56;                         \
+    } while (0)
+#define GNB_LEAVE(code) \
+    do                  \
+    {                   \
+        rc = (code);    \
+        goto leave;     \
+    } while (0)
+    for (;;)
+    {
+        if (wp >= wstop)
+            GNB_LEAVE(1);
+        if (p > p_end)
+            GNB_LEAVE(-1);
+        GNB_REFILL();
+        uint32_t e = ltab[bb & 2047];
+        // up to three table entries of literals per refill (3 x 11 bits <= 56)
+        if ((e & 0x3f) != 0 && (e & 0x30) == 0)
+        {
+            bb >>= e & 15;
+            cnt -= (int)(e & 15);
+            GNB_PUT_LITERALS(e);
+            e = ltab[bb & 2047];
+            if ((e & 0x3f) != 0 && (e & 0x30) == 0)
+            {
+                bb >>= e & 15;
+                cnt -= (int)(e & 15);
+                GNB_PUT_LITERALS(e);
+                e = ltab[bb & 2047];
+                if ((e & 0x3f) != 0 && (e & 0x30) == 0)
+                {
+                    bb >>= e & 15;
+                    cnt -= (int)(e & 15);
+                    GNB_PUT_LITERALS(e);
+                    continue;
+                }
+            }
+            GNB_REFILL();
+        }
+        int used = (int)(e & 15);
+        if (used == 0)
+        {
+            const int sym = L.slow(bb, used);
+            if (sym < 0)
+                GNB_LEAVE(-2);
+            e = DynHeader::pack_lit(sym, used);
+        }
+        bb >>= used;
+        cnt -= used;
+        const uint32_t kind = (e >> 4) & 3;
+        if (kind == 0)
+        {
+            *wp++ = (uint16_t)((e >> 8) & 0xffu);
+            continue;
+        }
+        if (kind == 1)
+            break;
+        if (kind == 3)
+            GNB_LEAVE(-3);
+        const int      xb  = (int)(e >> 24) & 15;
+        const uint32_t len = ((e >> 8) & 0xffff) + (uint32_t)(bb & ((1u << xb) - 1));
+        bb >>= xb;
+        cnt -= xb;
+        uint32_t d = dtab[bb & 511];
+        used       = (int)(d & 15);
+        if (used == 0)
+        {
+            const int dsym = H.dist_empty ? -1 : D.slow(bb, used);
+            if (dsym < 0)
+                GNB_LEAVE(-4);
+            d = DynHeader::pack_dist(dsym, used);
+        }
+        if (d >> 31)
+            GNB_LEAVE(-5);
+        bb >>= used;
+        cnt -= used;
+        const int      dx   = (int)(d >> 4) & 15;
+        const uint32_t dist = ((d >> 8) & 0xffff) + (uint32_t)(bb & ((1u << dx) - 1));
+        bb >>= dx;
+        cnt -= dx;
+        // dist <= 32768 <= symbols before wp: the marker prefix makes every legal distance addressable
+        const uint16_t *sp = wp - dist;
+        uint16_t       *dp = wp;
+        wp += len;
+        // 8 symbols (16 bytes) per step; a step may write up to 7 symbols past the match (the next symbols overwrite them).
+        // Source and destination of one step do not overlap from distance 8 on.
+        if (dist >= 8)
+        {
+            do
+            {
+                memcpy(dp, sp, 16);
+                dp += 8;
+                sp += 8;
+            } while (dp < wp);
+        }
+        else if (dist == 1)
+        {
+            uint64_t v = sp[0];
+            v |= v << 16;
+            v |= v << 32;
+            do
+            {
+                memcpy(dp, &v, 8);
+                memcpy(dp + 4, &v, 8);
+                dp += 8;
+            } while (dp < wp);
+        }
+        else
+            for (uint32_t i = 0; i < len; ++i)
+                dp[i] = sp[i];
+    }
+leave:
+#undef GNB_LEAVE
+#undef GNB_REFILL
+#undef GNB_PUT_LITERALS
+    p_io   = p;
+    bb_io  = bb;
+    cnt_io = cnt;
+    o_io   = (size_t)(wp - out);
+    return rc;
+}
+
 // Decodes deflate blocks from in.pos into c.sym (16-bit symbols, unknown history = markers) until
 //   * a block boundary that equals one of `cands` (ascending bit positions; the ones run past are false positives), or
 //   * the first block boundary at or after limit_bit, or
@@ -553,21 +719,12 @@ void decode_chunk(BitIn in, bool at_header, const uint64_t *cands, size_t n_cand
             }
             if (btype == 2)
                 dyn.pack();
-            const Huff     &L = H->lit, &D = H->dist;
-            const uint32_t *ltab = H->ltab, *dtab = H->dtab;
             // bit buffer: `cnt` valid bits in `bb`, next unread byte at p; stream position = (p - base) * 8 - cnt
             const uint8_t *p   = in.base + (in.pos >> 3);
             uint64_t       bb  = load64(p) >> (in.pos & 7);
             int            cnt = 64 - (int)(in.pos & 7);
             p += 8;
             const uint8_t *const p_end = in.base + (in.total_bits >> 3) + 16; // the buffer's padding keeps loads legal
-#define GNB_REFILL()                       \
-    do                                     \
-    {                                      \
-        bb |= load64(p) << cnt;            \
-        p += (63 - cnt) >> 3;              \
-        cnt |= 56;                         \
-    } while (0)
             // (the first load above took 8 bytes; cnt may be 57..64: bring it into the refill's invariant cnt <= 63)
             if (cnt == 64)
             {
@@ -577,93 +734,14 @@ void decode_chunk(BitIn in, bool at_header, const uint64_t *cands, size_t n_cand
             }
             for (;;)
             {
-                if (o + 1024 > cap)
-                    room(1024 + (1u << 16));
-                if (p > p_end)
-                    return fail("unexpected end of the gzip stream");
-                GNB_REFILL();
-                uint32_t e = ltab[bb & 2047];
-                // up to three literals per refill (3 x 15 bits <= 56)
-                if ((e & 0x3f) != 0 && (e & 0x30) == 0)
-                {
-                    bb >>= e & 15;
-                    cnt -= (int)(e & 15);
-                    out[o++] = (uint16_t)(e >> 8);
-                    e        = ltab[bb & 2047];
-                    if ((e & 0x3f) != 0 && (e & 0x30) == 0)
-                    {
-                        bb >>= e & 15;
-                        cnt -= (int)(e & 15);
-                        out[o++] = (uint16_t)(e >> 8);
-                        e        = ltab[bb & 2047];
-                        if ((e & 0x3f) != 0 && (e & 0x30) == 0)
-                        {
-                            bb >>= e & 15;
-                            cnt -= (int)(e & 15);
-                            out[o++] = (uint16_t)(e >> 8);
-                            continue;
-                        }
-                    }
-                    GNB_REFILL();
-                }
-                int used = (int)(e & 15);
-                if (used == 0)
-                {
-                    const int sym = L.slow(bb, used);
-                    if (sym < 0)
-                        return fail("invalid literal/length code");
-                    e = DynHeader::pack_lit(sym, used);
-                }
-                bb >>= used;
-                cnt -= used;
-                const uint32_t kind = (e >> 4) & 3;
-                if (kind == 0)
-                {
-                    out[o++] = (uint16_t)(e >> 8);
-                    continue;
-                }
-                if (kind == 1)
+                if (o + 1024 + (1u << 16) > cap)
+                    room(1024 + (1u << 17));
+                const int rc = inflate_symbols(*H, p, bb, cnt, p_end, out, o, cap - 1024);
+                if (rc == 0)
                     break;
-                if (kind == 3)
-                    return fail("invalid literal/length symbol");
-                const int      xb  = (int)(e >> 24) & 15;
-                const uint32_t len = ((e >> 8) & 0xffff) + (uint32_t)(bb & ((1u << xb) - 1));
-                bb >>= xb;
-                cnt -= xb;
-                uint32_t d = dtab[bb & 511];
-                used       = (int)(d & 15);
-                if (used == 0)
-                {
-                    const int dsym = H->dist_empty ? -1 : D.slow(bb, used);
-                    if (dsym < 0)
-                        return fail("invalid distance code");
-                    d = DynHeader::pack_dist(dsym, used);
-                }
-                if (d >> 31)
-                    return fail("invalid distance symbol");
-                bb >>= used;
-                cnt -= used;
-                const int      dx   = (int)(d >> 4) & 15;
-                const uint32_t dist = ((d >> 8) & 0xffff) + (uint32_t)(bb & ((1u << dx) - 1));
-                bb >>= dx;
-                cnt -= dx;
-                // dist <= 32768 <= o + kWindow: the marker prefix makes every legal distance addressable
-                const uint16_t *sp = out + o - dist;
-                uint16_t       *dp = out + o;
-                if (dist >= len)
-                    memcpy(dp, sp, (size_t)len * 2);
-                else if (dist == 1)
-                {
-                    const uint16_t v = sp[0];
-                    for (uint32_t i = 0; i < len; ++i)
-                        dp[i] = v;
-                }
-                else
-                    for (uint32_t i = 0; i < len; ++i)
-                        dp[i] = sp[i];
-                o += len;
+                if (rc < 0)
+                    return fail(kInflateErrors[-rc - 1]);
             }
-#undef GNB_REFILL
             const uint64_t pos = (uint64_t)(p - in.base) * 8 - (uint64_t)cnt;
             in.pos = pos;
             if (in.pos > in.total_bits)
@@ -702,39 +780,52 @@ void decode_chunk(BitIn in, bool at_header, const uint64_t *cands, size_t n_cand
 // to its end-of-block symbol, followed by a plausible next block.  ~0 = none.
 uint64_t find_block_start(const uint8_t *base, uint64_t total_bits, uint64_t from_bit, uint64_t to_bit)
 {
+    // Kraft sums (in 128ths) of four 3-bit code lengths at once
+    static const std::vector<uint16_t> kraft4_table = [] {
+        std::vector<uint16_t> t(4096);
+        for (int i = 0; i < 4096; ++i)
+        {
+            int sum = 0;
+            for (int j = 0; j < 4; ++j)
+            {
+                const int l = (i >> (3 * j)) & 7;
+                if (l)
+                    sum += 128 >> l;
+            }
+            t[i] = (uint16_t)sum;
+        }
+        return t;
+    }();
+    const uint16_t *const kraft4 = kraft4_table.data();
+    static const std::vector<uint8_t> head_table = [] {
+        std::vector<uint8_t> t(8192);
+        for (uint32_t i = 0; i < 8192; ++i)
+            t[i] = ((i >> 1) & 3) == 2 && ((i >> 3) & 31) <= 29 && ((i >> 8) & 31) <= 29;
+        return t;
+    }();
+    const uint8_t *const head_ok = head_table.data();
     DynHeader h;
     for (uint64_t b = from_bit; b < to_bit && b + 64 < total_bits; ++b)
     {
         const uint64_t w = load64(base + (b >> 3)) >> (b & 7);
-        // BTYPE = 10 (dynamic), HLIT <= 29, HDIST <= 29
-        if (((w >> 1) & 3) != 2 || ((w >> 3) & 31) > 29 || ((w >> 8) & 31) > 29)
+        // Without branches up to the one that almost never passes (a data-dependent branch per bit position would be
+        // mispredicted a fifth of the time): BTYPE = 10 (dynamic), HLIT <= 29, HDIST <= 29 from a table over the first 13
+        // bits; the code-length code complete (Kraft sum exactly 1 = 128/128), four 3-bit lengths per table lookup.
+        // 57 bits are available in w: 17 header bits + 13 code lengths (39 bits); the rest comes from a second load.
+        const int      hclen = (int)((w >> 13) & 15) + 4;
+        const int      n1    = hclen < 13 ? hclen : 13;
+        const uint64_t v     = (w >> 17) & ((1ull << (3 * n1)) - 1);
+        uint32_t       sum   = (uint32_t)kraft4[v & 4095] + kraft4[(v >> 12) & 4095] + kraft4[(v >> 24) & 4095] + kraft4[v >> 36];
+        const uint32_t maybe = head_ok[w & 8191] & (uint32_t)((sum == 128) | ((hclen > 13) & (sum < 128)));
+        if (!maybe)
             continue;
-        // quick look at the code-length code: complete (Kraft sum exactly 1)
-        const int hclen = (int)((w >> 13) & 15) + 4;
-        int       left  = 128;
+        if (hclen > 13)
         {
-            uint64_t v = w >> 17;
-            int      i = 0;
-            // 57 bits are available in w: 17 header bits + 13 code lengths; the rest comes from a second load
-            for (; i < hclen && i < 13 && left >= 0; ++i, v >>= 3)
-            {
-                const int l = (int)(v & 7);
-                if (l)
-                    left -= 128 >> l;
-            }
-            if (left > 0 && i < hclen)
-            {
-                const uint64_t b2 = b + 17 + 39;
-                uint64_t       v2 = load64(base + (b2 >> 3)) >> (b2 & 7);
-                for (; i < hclen; ++i, v2 >>= 3)
-                {
-                    const int l = (int)(v2 & 7);
-                    if (l)
-                        left -= 128 >> l;
-                }
-            }
+            const uint64_t b2 = b + 17 + 39;
+            const uint64_t v2 = (load64(base + (b2 >> 3)) >> (b2 & 7)) & ((1ull << (3 * (hclen - 13))) - 1);
+            sum += kraft4[v2 & 4095] + kraft4[v2 >> 12];
         }
-        if (left != 0)
+        if (sum != 128)
             continue;
         BitIn in;
         in.base       = base;
@@ -800,16 +891,127 @@ uint64_t find_block_start(const uint8_t *base, uint64_t total_bits, uint64_t fro
     return ~0ull;
 }
 
+// CRC-32 (gzip polynomial) by folding with carry-less multiplication (Gopal et al., "Fast CRC computation for generic
+// polynomials using PCLMULQDQ"): four 128-bit lanes folded by 512 bits per step, then reduced to 32 bits (Barrett).  Used when
+// the CPU has PCLMULQDQ and a start-up comparison with zlib's crc32 over a test pattern agrees; zlib's otherwise.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("pclmul,sse4.1"))) uint32_t crc32_clmul(uint32_t crc, const uint8_t *buf, size_t len) // len >= 64, multiple of 16
+{
+    const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596, 0x0154442bd4);
+    const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009e, 0x01751997d0);
+    const __m128i k5k0 = _mm_set_epi64x(0x0000000000, 0x0163cd6124);
+    const __m128i poly = _mm_set_epi64x(0x01f7011641, 0x01db710641);
+    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+    x1 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+    x2 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+    x3 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+    x4 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+    x0 = k1k2;
+    buf += 64;
+    len -= 64;
+    while (len >= 64)
+    {
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+        x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+        x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+        x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+        y5 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+        y6 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+        y7 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+        y8 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+        x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+        x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+        buf += 64;
+        len -= 64;
+    }
+    // four lanes into one
+    x0 = k3k4;
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+    while (len >= 16)
+    {
+        x2 = _mm_loadu_si128((const __m128i *)buf);
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+        buf += 16;
+        len -= 16;
+    }
+    // 128 -> 64 bits
+    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x1 = _mm_srli_si128(x1, 8);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = k5k0;
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_and_si128(x1, x3);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    // Barrett reduction to 32 bits
+    x0 = poly;
+    x2 = _mm_and_si128(x1, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+    x2 = _mm_and_si128(x2, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#endif
+
+// crc32_z(0, p, n) for a run of output bytes
+inline uint32_t crc32_of(const uint8_t *p, size_t n)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool use_clmul = [] {
+        if (getenv("GANON_B200_GZ_ZLIB_CRC") || !__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("sse4.1"))
+            return false;
+        uint8_t t[1024 + 48];
+        for (size_t i = 0; i < sizeof t; ++i)
+            t[i] = (uint8_t)(i * 131 + (i >> 3) * 7 + 5);
+        for (size_t n : {(size_t)64, (size_t)80, (size_t)1024, (size_t)1072})
+            if ((uint32_t)crc32_z(0, t, n) != ~crc32_clmul(~0u, t, n))
+                return false;
+        if (getenv("GANON_B200_GZ_TRACE"))
+            fprintf(stderr, "[gz] CRC-32 by carry-less multiplication\n");
+        return true;
+    }();
+    if (use_clmul && n >= 64)
+    {
+        const size_t body = n & ~(size_t)15;
+        const uint32_t c  = ~crc32_clmul(~0u, p, body);
+        return body == n ? c : (uint32_t)crc32_z(c, p + body, n - body);
+    }
+#endif
+    return (uint32_t)crc32_z(0, p, n);
+}
+
 // symbols -> bytes: literals as they are, markers through the (now known) 32 KiB history.  Groups of 16 symbols without a
 // marker are narrowed with SSE2; the others go through a 64 Ki-entry table (symbol -> byte), one load per symbol.
-inline void resolve_markers(const uint16_t *s, size_t n, const uint8_t *w, uint8_t *d, std::vector<uint8_t> &lut)
+inline void build_marker_table(const uint8_t *w, std::vector<uint8_t> &lut)
 {
     lut.resize(65536);
     for (int i = 0; i < 256; ++i)
         lut[i] = (uint8_t)i;
     memcpy(lut.data() + kMarker, w, kWindow);
-    const uint8_t *t = lut.data();
-    size_t         i = 0;
+}
+
+inline void resolve_markers(const uint16_t *s, size_t n, const uint8_t *t, uint8_t *d)
+{
+    size_t i = 0;
 #if defined(__SSE2__)
     for (; i + 16 <= n; i += 16)
     {
@@ -829,17 +1031,43 @@ inline void resolve_markers(const uint16_t *s, size_t n, const uint8_t *w, uint8
 // ---------------------------------------------------------------------------------------------------------------------
 // gzip files
 // ---------------------------------------------------------------------------------------------------------------------
+// The compressed file is cut into ranges of chunk_bytes_.  Workers take tasks in stream order from one scheduler:
+//   finder r   the first block start inside range r (range 0: the gzip header), a little ahead of the decoders;
+//   decoder d  from the start found in range d up to the block boundary where a later range's decoder starts;
+//   slices     (ahead of everything else) marker replacement + CRC of decoded pieces for the consumer, read().
+// A sequencer thread follows the chain of chunks that really follow one another (position by position: the chunk found in
+// the range of the current position must start exactly there), propagates the 32 KiB history, and queues the pieces.  Where
+// the chain breaks -- the finder missed a boundary (stored / fixed-Huffman blocks, a block longer than its view), a candidate
+// was a false positive, a decoder ran out of its view -- the sequencer decodes from the known position itself.
+// Compressed bytes live in an anonymous mapping as large as the file, filled range by range with pread (I/O errors stay
+// error codes) and given back to the system behind the sequencer.
 class GzSource : public ByteSource
 {
   public:
-    GzSource(int fd, uint64_t size, int threads) : fd_(fd), size_(size), pool_(threads), pool2_(std::max(1, std::min(threads, 8)))
+    GzSource(int fd, uint64_t size, int threads) : fd_(fd), size_(size)
     {
-        chunk_bytes_ = 2u << 20;
+        chunk_bytes_ = 1u << 20;
         if (const char *e = getenv("GANON_B200_GZ_CHUNK"))
             chunk_bytes_ = std::max<uint64_t>(1u << 12, strtoull(e, nullptr, 10));
-        wave_chunks_ = (size_t)pool_.size() * 2;
+        n_ranges_ = (size_t)((size_ + chunk_bytes_ - 1) / chunk_bytes_);
+        const int T  = std::max(1, threads);
+        in_flight_  = (size_t)T * 2 + kAhead;
+
+        img_bytes_  = (size_t)size_ + (64u << 10);
+        void *m     = mmap(nullptr, img_bytes_, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED)
+        {
+            perr_     = "cannot map the compressed file's image";
+            finished_ = true;
+            return;
+        }
+        img_    = static_cast<uint8_t *>(m);
+        loaded_ = std::vector<std::atomic<uint8_t>>(n_ranges_);
+        slots_.resize(n_ranges_);
         window_.assign(kWindow, 0);
-        producer_ = std::thread([this] { produce(); });
+        for (int i = 0; i < T; ++i)
+            workers_.emplace_back([this] { work(); });
+        sequencer_ = std::thread([this] { sequence(); });
     }
     ~GzSource() override
     {
@@ -847,15 +1075,25 @@ class GzSource : public ByteSource
             std::lock_guard<std::mutex> l(mu_);
             cancel_ = true;
         }
+        {
+            std::lock_guard<std::mutex> l(smu_);
+            stop_ = true;
+        }
         cv_.notify_all();
-        producer_.join();
+        scv_.notify_all();
+        if (sequencer_.joinable())
+            sequencer_.join();
+        for (auto &t : workers_)
+            t.join();
+        if (img_)
+            munmap(img_, img_bytes_);
         close(fd_);
     }
     bool     is_gzip() const override { return true; }
     uint64_t size() const override { return size_; }
-    // Markers are replaced HERE, by the consumer, straight into the caller's buffer (in parallel over the queued pieces):
-    // the decoded bytes are written once, where they are needed.  Only a piece that straddles the end of the caller's
-    // buffer goes through a side buffer.
+    // Markers are replaced HERE, for the consumer, straight into the caller's buffer (slices of the queued pieces on the
+    // workers): the decoded bytes are written once, where they are needed.  Only a piece that straddles the end of the
+    // caller's buffer goes through a side buffer.
     int64_t read(char *dst, size_t cap) override
     {
         size_t got = 0;
@@ -884,7 +1122,7 @@ class GzSource : public ByteSource
                     }
                     break;
                 }
-                while (!ready_.empty() && batch.size() < 64 && (batch.empty() || ready_.front().n_out <= room))
+                while (!ready_.empty() && batch.size() < 256 && (batch.empty() || ready_.front().n_out <= room))
                 {
                     room -= std::min(room, ready_.front().n_out);
                     queued_ -= ready_.front().n_out;
@@ -912,40 +1150,61 @@ class GzSource : public ByteSource
                     to_carry   = true;
                 }
             }
-            pool2_.parallel_for(batch.size(), [&](size_t i) {
-                Piece               &pc = batch[i];
-                std::vector<uint8_t> lut;
-                resolve_markers(pc.sym.data() + kWindow, pc.n_out, pc.window.data(), where[i], lut);
+            // slices of at most 1 MiB that do not cross a member's end: (piece, from, to), CRC of each
+            struct Slice
+            {
+                size_t   piece;
+                uint64_t from, to;
+                uint32_t crc;
+                bool     member_ends; // a gzip member ends where the slice does
+                size_t   end_index;
+            };
+            std::vector<Slice> slices;
+            for (size_t i = 0; i < batch.size(); ++i)
+            {
                 uint64_t from = 0;
-                for (size_t m = 0; m <= pc.ends.size(); ++m)
+                for (size_t m = 0; m <= batch[i].ends.size(); ++m)
                 {
-                    const uint64_t to = m < pc.ends.size() ? pc.ends[m].out_off : pc.n_out;
-                    pc.crcs.emplace_back(to - from, (uint32_t)crc32_z(0, where[i] + from, (size_t)(to - from)));
+                    const uint64_t to = m < batch[i].ends.size() ? batch[i].ends[m].out_off : batch[i].n_out;
+                    uint64_t       a  = from;
+                    do
+                    {
+                        const uint64_t z = std::min<uint64_t>(to, a + (1u << 20));
+                        slices.push_back(Slice{i, a, z, 0, m < batch[i].ends.size() && z == to, m});
+                        a = z;
+                    } while (a < to);
                     from = to;
                 }
+            }
+            std::vector<std::vector<uint8_t>> luts(batch.size());
+            run_hi(batch.size(), [&](size_t i) { build_marker_table(batch[i].window.data(), luts[i]); });
+            run_hi(slices.size(), [&](size_t k) {
+                Slice &sl = slices[k];
+                Piece &pc = batch[sl.piece];
+                resolve_markers(pc.sym.data() + kWindow + sl.from, (size_t)(sl.to - sl.from), luts[sl.piece].data(), where[sl.piece] + sl.from);
+                sl.crc = crc32_of(where[sl.piece] + sl.from, (size_t)(sl.to - sl.from));
             });
             // trailers of the members that end in these pieces (sequential: crc32_combine)
-            for (auto &pc : batch)
-                for (size_t m = 0; m < pc.crcs.size(); ++m)
+            for (auto const &sl : slices)
+            {
+                crc_run_ = (uint32_t)crc32_combine(crc_run_, sl.crc, (z_off_t)(sl.to - sl.from));
+                len_run_ += sl.to - sl.from;
+                if (sl.member_ends)
                 {
-                    crc_run_ = (uint32_t)crc32_combine(crc_run_, pc.crcs[m].second, (z_off_t)pc.crcs[m].first);
-                    len_run_ += pc.crcs[m].first;
-                    if (m < pc.ends.size())
+                    const MemberEnd &me = batch[sl.piece].ends[sl.end_index];
+                    if (crc_run_ != me.crc || (uint32_t)len_run_ != me.isize)
                     {
-                        if (crc_run_ != pc.ends[m].crc || (uint32_t)len_run_ != pc.ends[m].isize)
-                        {
-                            std::lock_guard<std::mutex> l(mu_);
-                            perr_ = "gzip CRC / length check failed";
-                        }
-                        crc_run_ = 0;
-                        len_run_ = 0;
+                        std::lock_guard<std::mutex> l(mu_);
+                        perr_ = "gzip CRC / length check failed";
                     }
+                    crc_run_ = 0;
+                    len_run_ = 0;
                 }
+            }
             {
                 std::lock_guard<std::mutex> l(mu_);
                 for (auto &pc : batch)
-                    if (sym_pool_.size() < 128)
-                        sym_pool_.emplace_back(std::move(pc.sym));
+                    recycle(pc.sym);
                 if (!perr_.empty())
                 {
                     err_ = perr_;
@@ -965,149 +1224,339 @@ class GzSource : public ByteSource
     }
 
   private:
-    // one wave: chunk starts (finder), decoding, history propagation, marker replacement + CRCs; pieces are queued in order
-    void produce()
+    static constexpr size_t kAhead = 3; // a decoder knows the starts found in this many ranges after its own
+
+    struct Slot
     {
-        std::string err;
-        uint64_t    file_off  = 0;    // compressed bytes of the file before buf_
-        uint64_t    start_bit = 0;    // where the next wave's first chunk starts, relative to buf_
-        bool        at_header = true; // the very first chunk starts at the gzip header
-        std::vector<uint8_t> buf;
-        uint64_t    buf_valid = 0; // compressed bytes in buf (without padding)
-        bool        file_done = false;
-        const uint64_t wave_bytes = chunk_bytes_ * wave_chunks_;
-        uint64_t       look_ahead = 0; // extra waves of compressed data kept buffered (grows if one deflate block needs it)
+        int      find_state = 0, dec_state = 0; // 0: not started, 1: running, 2: done (smu_)
+        bool     found = false, discard = false;
+        uint64_t start_bit = 0;
+        Chunk    chunk;
+    };
+
+    void recycle(std::vector<uint16_t> &sym) // mu_ held
+    {
+        if (sym.capacity() && sym_pool_.size() < 256)
+            sym_pool_.emplace_back(std::move(sym));
+        sym = std::vector<uint16_t>();
+    }
+    void take_buffer(Chunk &c)
+    {
+        std::lock_guard<std::mutex> l(mu_);
+        if (!sym_pool_.empty())
+        {
+            c.sym.swap(sym_pool_.back());
+            sym_pool_.pop_back();
+        }
+    }
+    uint64_t file_bits() const { return size_ * 8; }
+    uint64_t range_bits() const { return chunk_bytes_ * 8; }
+
+    // compressed bytes of range r in the image
+    bool ensure_loaded(size_t r)
+    {
+        if (r >= n_ranges_)
+            return true;
+        uint8_t st = loaded_[r].load(std::memory_order_acquire);
+        if (st == 2)
+            return true;
+        uint8_t expect = 0;
+        if (st == 0 && loaded_[r].compare_exchange_strong(expect, 1))
+        {
+            const uint64_t off = (uint64_t)r * chunk_bytes_, n = std::min<uint64_t>(chunk_bytes_, size_ - off);
+            const bool     ok  = pread_all(fd_, reinterpret_cast<char *>(img_) + off, (size_t)n, off);
+            loaded_[r].store(ok ? 2 : 3, std::memory_order_release);
+            return ok;
+        }
+        while ((st = loaded_[r].load(std::memory_order_acquire)) == 1)
+            std::this_thread::yield();
+        return st == 2;
+    }
+    // the view [.., end of range hi]: its length in bits, clipped to the file
+    uint64_t view_bits(size_t hi) const { return std::min<uint64_t>(size_, ((uint64_t)hi + 1) * chunk_bytes_) * 8; }
+
+    void find(size_t r)
+    {
+        bool     found = false;
+        uint64_t start = 0;
+        bool     io_ok = ensure_loaded(r) && ensure_loaded(r + 1);
+        if (io_ok)
+        {
+            if (r == 0)
+                found = true; // the gzip header
+            else
+            {
+                const uint64_t b = find_block_start(img_, view_bits(r + 1), (uint64_t)r * range_bits(), std::min(file_bits(), ((uint64_t)r + 1) * range_bits()));
+                found = b != ~0ull;
+                start = b;
+            }
+        }
+        std::lock_guard<std::mutex> l(smu_);
+        Slot &s      = slots_[r];
+        s.found      = found;
+        s.start_bit  = start;
+        s.find_state = 2;
+        if (!io_ok)
+            io_failed_ = true;
+        scv_.notify_all();
+    }
+
+    void decode(size_t d, std::vector<uint64_t> cands)
+    {
+        Slot        &s  = slots_[d];
+        const size_t hi = std::min(n_ranges_ - 1, d + kAhead + 1);
+        bool         io_ok = true;
+        for (size_t r = d; r <= hi && io_ok; ++r)
+            io_ok = ensure_loaded(r);
+        if (io_ok)
+        {
+            take_buffer(s.chunk);
+            BitIn in;
+            in.base       = img_;
+            in.total_bits = view_bits(hi);
+            in.pos        = s.start_bit;
+            const uint64_t limit = d + kAhead + 1 < n_ranges_ ? ((uint64_t)d + kAhead + 1) * range_bits() : ~0ull;
+            decode_chunk(in, d == 0, cands.data(), cands.size(), limit, in.total_bits == file_bits(), s.chunk);
+        }
+        else
+        {
+            s.chunk.ok  = false;
+            s.chunk.err = "short read";
+        }
+        std::unique_lock<std::mutex> l(smu_);
+        s.dec_state = 2;
+        if (!io_ok)
+            io_failed_ = true;
+        const bool drop = s.discard;
+        scv_.notify_all();
+        l.unlock();
+        if (drop)
+        {
+            std::lock_guard<std::mutex> lm(mu_);
+            recycle(s.chunk.sym);
+        }
+    }
+
+    // the next task in stream order (smu_ held); false: nothing to do right now
+    bool pick(std::function<void()> &job)
+    {
         for (;;)
         {
-            // ---- keep two waves of compressed data buffered: the last chunk's decoder runs into the next wave ----
+            if (next_dec_ < n_ranges_)
             {
-                const uint64_t drop = std::min<uint64_t>(start_bit >> 3, buf_valid);
-                if (drop)
-                {
-                    memmove(buf.data(), buf.data() + drop, buf_valid - drop);
-                    buf_valid -= drop;
-                    file_off += drop;
-                    start_bit -= drop * 8;
+                const size_t need = std::min(n_ranges_ - 1, next_dec_ + kAhead);
+                if (next_find_ <= need)
+                { // the finders a decoder waits for come first
+                    const size_t r         = next_find_++;
+                    slots_[r].find_state = 1;
+                    job                  = [this, r] { find(r); };
+                    return true;
                 }
-                const uint64_t want = std::min<uint64_t>((2 + look_ahead) * wave_bytes, size_ - file_off);
-                buf.resize(want + 64);
-                if (want > buf_valid)
+                if (next_dec_ < seq_range_ + in_flight_)
                 {
-                    const uint64_t lo = buf_valid, n = want - buf_valid;
-                    const size_t   slice = 4u << 20, parts = (size_t)((n + slice - 1) / slice);
-                    std::atomic<bool> ok{true};
-                    pool_.parallel_for(parts, [&](size_t i) {
-                        const uint64_t o = lo + (uint64_t)i * slice, m = std::min<uint64_t>(slice, want - o);
-                        if (!pread_all(fd_, (char *)buf.data() + o, m, file_off + o))
-                            ok = false;
-                    });
-                    if (!ok)
+                    bool ready = true;
+                    for (size_t j = next_dec_; j <= need && ready; ++j)
+                        ready = slots_[j].find_state == 2;
+                    if (ready)
                     {
-                        err = "short read";
-                        break;
+                        const size_t d = next_dec_++;
+                        Slot        &s = slots_[d];
+                        if (!s.found || s.discard || d < seq_range_)
+                        { // no start in this range, or the sequencer is past it already
+                            s.dec_state = 2;
+                            scv_.notify_all();
+                            continue;
+                        }
+                        std::vector<uint64_t> cands;
+                        for (size_t j = d + 1; j <= need; ++j)
+                            if (slots_[j].found)
+                                cands.push_back(slots_[j].start_bit);
+                        s.dec_state = 1;
+                        job         = [this, d, cands] { decode(d, cands); };
+                        return true;
                     }
-                    buf_valid = want;
                 }
-                memset(buf.data() + buf_valid, 0, 64);
-                file_done = file_off + buf_valid >= size_;
             }
-            const uint64_t total_bits = buf_valid * 8;
-            if (start_bit >= total_bits)
-                break; // everything decoded (the previous wave ended at the end of the data)
-            // ---- chunk starts: chunk 0 at start_bit, the others where the finder sees a block start ----
-            // this wave: wave_bytes of compressed data from the start position; the rest of the buffer is look-ahead
-            const uint64_t wave_end_byte = std::min<uint64_t>(buf_valid, (start_bit >> 3) + wave_bytes);
-            const uint64_t wave_end_bit  = wave_end_byte * 8;
-            const size_t   n_chunks     = (size_t)std::max<uint64_t>(1, (wave_end_bit - start_bit + chunk_bytes_ * 8 - 1) / (chunk_bytes_ * 8));
-            std::vector<Chunk> chunks(n_chunks);
+            if (next_find_ < n_ranges_ && next_find_ < next_dec_ + kAhead + 1 + workers_.size())
             {
-                std::lock_guard<std::mutex> l(mu_);
-                for (auto &c : chunks)
-                    if (!sym_pool_.empty())
-                    {
-                        c.sym.swap(sym_pool_.back());
-                        sym_pool_.pop_back();
-                    }
+                const size_t r         = next_find_++;
+                slots_[r].find_state = 1;
+                job                  = [this, r] { find(r); };
+                return true;
             }
-            chunks[0].start_bit = start_bit;
-            chunks[0].found     = true;
-            pool_.parallel_for(n_chunks - 1, [&](size_t k) {
-                const size_t   i    = k + 1;
-                const uint64_t from = start_bit + (uint64_t)i * chunk_bytes_ * 8, to = std::min<uint64_t>(from + chunk_bytes_ * 8, wave_end_bit);
-                const uint64_t b    = find_block_start(buf.data(), total_bits, from, to);
-                chunks[i].found     = b != ~0ull;
-                chunks[i].start_bit = b;
-            });
-            std::vector<uint64_t> cands;
-            for (size_t i = 1; i < n_chunks; ++i)
-                if (chunks[i].found)
-                    cands.push_back(chunks[i].start_bit);
-            // ---- decode ----
-            const bool last_data = file_done;
-            pool_.parallel_for(n_chunks, [&](size_t i) {
-                if (!chunks[i].found)
-                    return;
-                BitIn in;
-                in.base       = buf.data();
-                in.total_bits = total_bits;
-                in.pos        = chunks[i].start_bit;
-                const size_t first = std::upper_bound(cands.begin(), cands.end(), chunks[i].start_bit) - cands.begin();
-                decode_chunk(in, at_header && i == 0, cands.data() + first, cands.size() - first, wave_end_bit, last_data, chunks[i]);
-            });
-            // ---- the chain of chunks that really follow one another ----
-            std::vector<size_t> chain;
-            bool                need_more = false;
+            return false;
+        }
+    }
+
+    void work()
+    {
+        for (;;)
+        {
+            std::function<void()> job;
             {
-                size_t i = 0;
+                std::unique_lock<std::mutex> l(smu_);
                 for (;;)
                 {
-                    if (!chunks[i].ok)
+                    if (stop_)
+                        return;
+                    if (!hi_.empty())
                     {
-                        if (chunks[i].ran_out && !file_done)
-                            need_more = true; // a block reaches beyond the buffered data: buffer more and redo the wave
-                        else
-                            err = chunks[i].err.empty() ? "gzip decoding failed" : chunks[i].err;
+                        job = std::move(hi_.front());
+                        hi_.pop_front();
                         break;
                     }
-                    chain.push_back(i);
-                    if (chunks[i].eos || chunks[i].end_bit >= wave_end_bit)
+                    if (!seq_done_ && pick(job))
                         break;
-                    size_t j = i + 1;
-                    while (j < n_chunks && !(chunks[j].found && chunks[j].start_bit == chunks[i].end_bit))
-                        ++j;
-                    if (j == n_chunks)
-                    {
-                        err = "gzip decoding lost the block chain";
-                        break;
-                    }
-                    i = j;
+                    scv_.wait(l);
                 }
             }
-            if (need_more)
+            job();
+        }
+    }
+
+    // fn(0..n-1) ahead of the decoding tasks, on the workers and the calling thread
+    void run_hi(size_t n, const std::function<void(size_t)> &fn)
+    {
+        if (n == 0)
+            return;
+        if (n == 1)
+            return fn(0);
+        std::mutex              m;
+        std::condition_variable c;
+        size_t                  left = n;
+        {
+            std::lock_guard<std::mutex> l(smu_);
+            for (size_t i = 0; i < n; ++i)
+                hi_.emplace_back([&, i] {
+                    fn(i);
+                    std::lock_guard<std::mutex> lm(m);
+                    if (--left == 0)
+                        c.notify_all();
+                });
+        }
+        scv_.notify_all();
+        for (;;)
+        {
+            std::function<void()> job;
             {
-                look_ahead = look_ahead ? look_ahead * 2 : 2;
-                std::lock_guard<std::mutex> l(mu_);
-                for (auto &c : chunks)
-                    if (c.sym.capacity() && sym_pool_.size() < 128)
-                        sym_pool_.emplace_back(std::move(c.sym));
-                continue;
+                std::lock_guard<std::mutex> l(smu_);
+                if (hi_.empty())
+                    break;
+                job = std::move(hi_.front());
+                hi_.pop_front();
             }
-            if (!err.empty())
-                break;
-            at_header = false;
-            // ---- histories: window before chunk k = last 32 KiB of everything before it (sequential, 32 KiB each) ----
-            std::vector<std::vector<uint8_t>> win(chain.size());
-            for (size_t k = 0; k < chain.size(); ++k)
+            job();
+        }
+        std::unique_lock<std::mutex> lm(m);
+        c.wait(lm, [&] { return left == 0; });
+    }
+
+    // the chunk that starts at `pos`, decoded by the sequencer itself with a view that grows until the chunk fits
+    bool decode_here(uint64_t pos, size_t r, Chunk &c, std::string &err)
+    {
+        for (size_t ahead = kAhead;; ahead *= 2)
+        {
+            const size_t hi = std::min(n_ranges_ - 1, r + ahead + 1);
+            for (size_t j = r; j <= hi; ++j)
+                if (!ensure_loaded(j))
+                {
+                    err = "short read";
+                    return false;
+                }
+            std::vector<uint64_t> cands;
             {
-                win[k] = window_;
-                const Chunk    &c   = chunks[chain[k]];
-                const uint16_t *s   = c.sym.data() + kWindow;
-                const size_t    n   = c.n_out;
+                std::lock_guard<std::mutex> l(smu_);
+                for (size_t j = r; j <= std::min(n_ranges_ - 1, r + ahead); ++j)
+                    if (slots_[j].find_state == 2 && slots_[j].found && !slots_[j].discard && slots_[j].start_bit > pos)
+                        cands.push_back(slots_[j].start_bit);
+            }
+            if (c.sym.empty())
+                take_buffer(c);
+            c.ends.clear();
+            BitIn in;
+            in.base       = img_;
+            in.total_bits = view_bits(hi);
+            in.pos        = pos;
+            const uint64_t limit = r + ahead + 1 < n_ranges_ ? ((uint64_t)r + ahead + 1) * range_bits() : ~0ull;
+            decode_chunk(in, pos == 0, cands.data(), cands.size(), limit, in.total_bits == file_bits(), c);
+            if (c.ok)
+                return true;
+            if (!(c.ran_out && in.total_bits < file_bits()))
+            {
+                err = c.err.empty() ? "gzip decoding failed" : c.err;
+                return false;
+            }
+        }
+    }
+
+    void sequence()
+    {
+        std::string err;
+        uint64_t    pos        = 0; // where the next chunk starts: certain
+        size_t      freed_upto = 0; // ranges [0, freed_upto) of the image were given back
+        size_t      prev_r     = 0;
+        bool        eos        = false;
+        while (!eos)
+        {
+            if (pos >= file_bits())
+            {
+                err = "unexpected end of the gzip stream";
+                break;
+            }
+            const size_t r = (size_t)(pos / range_bits());
+            Slot        &s = slots_[r];
+            bool         spec;
+            {
+                std::unique_lock<std::mutex> l(smu_);
+                seq_range_ = r;
+                // chunks the chain skipped: their buffers go back once their decoders are done
+                for (size_t j = prev_r; j < r; ++j)
+                    drop_slot(j);
+                scv_.notify_all();
+                scv_.wait(l, [&] { return stop_ || io_failed_ || s.find_state == 2; });
+                if (stop_)
+                    return;
+                spec = s.found && s.start_bit == pos && !io_failed_;
+                if (spec)
+                    scv_.wait(l, [&] { return stop_ || s.dec_state == 2; });
+                if (stop_)
+                    return;
+                if (!spec && !(s.found && s.start_bit > pos))
+                    drop_slot(r); // (a start found further on in this range stays a candidate: the chain may come back to it)
+            }
+            if (io_failed_)
+            {
+                err = "short read";
+                break;
+            }
+            Chunk  own;
+            Chunk *c = &s.chunk;
+            if (spec && !s.chunk.ok && !(s.chunk.ran_out && view_bits(std::min(n_ranges_ - 1, r + kAhead + 1)) < file_bits()))
+            {
+                err = s.chunk.err.empty() ? "gzip decoding failed" : s.chunk.err; // the start was certain: a real error
+                break;
+            }
+            if (!spec || !s.chunk.ok)
+            {
+                if (spec)
+                {
+                    std::lock_guard<std::mutex> l(mu_);
+                    own.sym.swap(s.chunk.sym); // ran out of its view: again, with more of the file
+                }
+                if (!decode_here(pos, r, own, err))
+                    break;
+                c = &own;
+            }
+            // ---- history: window before the next chunk = last 32 KiB of everything so far ----
+            std::vector<uint8_t> win = window_;
+            {
+                const uint16_t *sy = c->sym.data() + kWindow;
+                const size_t    n  = c->n_out;
                 std::vector<uint8_t> nw(kWindow);
                 if (n >= kWindow)
                     for (uint32_t i = 0; i < kWindow; ++i)
                     {
-                        const uint16_t v = s[n - kWindow + i];
+                        const uint16_t v = sy[n - kWindow + i];
                         nw[i]            = v < kMarker ? (uint8_t)v : window_[v - kMarker];
                     }
                 else
@@ -1115,25 +1564,21 @@ class GzSource : public ByteSource
                     memcpy(nw.data(), window_.data() + n, kWindow - n);
                     for (size_t i = 0; i < n; ++i)
                     {
-                        const uint16_t v      = s[i];
+                        const uint16_t v      = sy[i];
                         nw[kWindow - n + i] = v < kMarker ? (uint8_t)v : window_[v - kMarker];
                     }
                 }
                 window_.swap(nw);
             }
-            // ---- hand the chunks over in order; the consumer replaces the markers (read()) ----
-            bool eos = false;
-            for (size_t k = 0; k < chain.size(); ++k)
+            eos = c->eos;
+            pos = c->end_bit;
+            if (c->n_out != 0 || !c->ends.empty())
             {
-                Chunk &c = chunks[chain[k]];
-                eos |= c.eos;
-                if (c.n_out == 0 && c.ends.empty())
-                    continue;
                 Piece pc;
-                pc.sym.swap(c.sym);
-                pc.n_out = c.n_out;
-                pc.window.swap(win[k]);
-                pc.ends.swap(c.ends);
+                pc.sym.swap(c->sym);
+                pc.n_out = c->n_out;
+                pc.window.swap(win);
+                pc.ends.swap(c->ends);
                 std::unique_lock<std::mutex> l(mu_);
                 cv_.wait(l, [&] { return cancel_ || queued_ < max_queued_; });
                 if (cancel_)
@@ -1142,39 +1587,70 @@ class GzSource : public ByteSource
                 ready_.emplace_back(std::move(pc));
                 cv_.notify_all();
             }
-            start_bit = chunks[chain.back()].end_bit;
+            else
             {
                 std::lock_guard<std::mutex> l(mu_);
-                for (auto &c : chunks)
-                    if (c.sym.capacity() && sym_pool_.size() < 128)
-                        sym_pool_.emplace_back(std::move(c.sym));
+                recycle(c->sym);
             }
-            if (eos)
-                break;
-            if (file_done && start_bit >= total_bits)
-            {
-                err = "unexpected end of the gzip stream";
-                break;
+            prev_r = r + 1;
+            // compressed bytes behind the position are not needed again
+            const size_t keep_from = (size_t)(pos / range_bits());
+            if (keep_from > freed_upto + 8)
+            { // whole pages inside [freed_upto, keep_from) only: madvise rounds the length up
+                const uint64_t page = 4096, a = ((uint64_t)freed_upto * chunk_bytes_ + page - 1) & ~(page - 1), b = ((uint64_t)keep_from * chunk_bytes_) & ~(page - 1);
+                if (b > a)
+                    madvise(img_ + a, (size_t)(b - a), MADV_DONTNEED);
+                freed_upto = keep_from;
             }
+        }
+        {
+            std::lock_guard<std::mutex> l(smu_);
+            seq_done_ = true; // no more decoding tasks; the workers stay for the consumer's slices
+            for (size_t j = prev_r; j < n_ranges_ && j < next_dec_; ++j)
+                drop_slot(j);
         }
         std::lock_guard<std::mutex> l(mu_);
         perr_     = err;
         finished_ = true;
         cv_.notify_all();
     }
+    void drop_slot(size_t j) // smu_ held
+    {
+        Slot &s = slots_[j];
+        if (s.discard)
+            return;
+        s.discard = true;
+        if (s.dec_state == 2)
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            recycle(s.chunk.sym);
+        }
+    }
+
     int      fd_;
     uint64_t size_;
-    Pool     pool_, pool2_; // producer (find + decode) / consumer (marker replacement + CRC)
     uint64_t chunk_bytes_;
-    size_t   wave_chunks_;
+    size_t   n_ranges_ = 0, in_flight_ = 0;
+    uint8_t *img_ = nullptr;
+    size_t   img_bytes_ = 0;
+    std::vector<std::atomic<uint8_t>> loaded_; // 0: not read, 1: being read, 2: in the image, 3: read error
+    std::vector<Slot>    slots_;
     std::vector<uint8_t> window_;
-    std::thread          producer_;
-    std::mutex           mu_;
+    std::vector<std::thread> workers_;
+    std::thread              sequencer_;
+    // scheduler (smu_): positions of the finder / decoder fronts, the range the sequencer is at, consumer jobs
+    std::mutex              smu_;
+    std::condition_variable scv_;
+    size_t                  next_find_ = 0, next_dec_ = 0, seq_range_ = 0;
+    std::deque<std::function<void()>> hi_;
+    bool                    stop_ = false, seq_done_ = false, io_failed_ = false;
+    // queue to the consumer (mu_)
+    std::mutex              mu_;
     std::condition_variable cv_;
-    std::deque<Piece>    ready_;
-    size_t               queued_ = 0, max_queued_ = 512u << 20; // output bytes waiting in ready_
-    std::vector<std::vector<uint16_t>> sym_pool_;                // symbol buffers for reuse (guarded by mu_)
-    std::vector<uint8_t> carry_;                                 // a piece that straddled the end of the caller's buffer
+    std::deque<Piece>       ready_;
+    size_t                  queued_ = 0, max_queued_ = 128u << 20; // output bytes waiting in ready_
+    std::vector<std::vector<uint16_t>> sym_pool_;                   // symbol buffers for reuse (mu_)
+    std::vector<uint8_t> carry_;                                    // a piece that straddled the end of the caller's buffer
     size_t               carry_off_ = 0;
     uint32_t             crc_run_ = 0; // CRC-32 / length of the current member so far (consumer)
     uint64_t             len_run_ = 0;

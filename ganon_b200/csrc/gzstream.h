@@ -2,14 +2,19 @@
 // its transparent decompression layer (seqan3/io/detail/misc_input.hpp: magic-header detection, then zlib's inflate on one
 // thread, or its BGZF stream); here plain files are read with parallel preads and gzip files -- single-member, multi-member
 // or BGZF alike -- are inflated by all host threads at once:
-//   * the compressed stream is cut into chunks; in every chunk but the first a thread looks for the next deflate block
-//     that starts with a valid dynamic-Huffman header (bit-granular search, RFC 1951 3.2.7) and decodes from there with an
-//     UNKNOWN 32 KiB history: output symbols are 16 bits wide, a back-reference that reaches before the chunk's start
-//     yields a marker naming the history position it wants (the two-pass scheme of pugz / rapidgzip);
-//   * a chunk's decoder stops at the block boundary where the next chunk's decoder started (a candidate it runs past
-//     was a false positive and is dropped: the predecessor simply keeps decoding through it);
-//   * the histories are then propagated chunk by chunk (32 KiB each, sequential), markers are replaced in parallel, and
-//     the CRC-32 / ISIZE trailer of every gzip member is verified from per-chunk CRCs (crc32_combine).
+//   * the compressed stream is cut into ranges of 1 MiB; for every range but the first a worker looks for the first deflate
+//     block that starts with a valid dynamic-Huffman header (bit-granular search without a branch per position, RFC 1951
+//     3.2.7) and another decodes from there with an UNKNOWN 32 KiB history: output symbols are 16 bits wide, a
+//     back-reference that reaches before the chunk's start yields a marker naming the history position it wants (the
+//     two-pass scheme of pugz / rapidgzip);
+//   * a chunk's decoder stops at the block boundary where a later range's decoder started (a candidate it runs past was
+//     a false positive and is dropped: the predecessor simply keeps decoding through it);
+//   * finders, decoders and the consumer's work are tasks of one scheduler taken in stream order (no barriers: a worker
+//     that finishes a chunk takes the next one); a sequencer thread follows the chain of chunks, propagates the
+//     histories (32 KiB each) and decodes a chunk itself where the chain breaks (stored / fixed-Huffman blocks the finder
+//     does not look for, a block longer than a decoder's view);
+//   * markers are replaced by the workers in slices of 1 MiB straight into the caller's buffer, and the CRC-32 / ISIZE
+//     trailer of every gzip member is verified from the slices' CRCs (carry-less multiplication, crc32_combine).
 // Any structural error or CRC mismatch is reported (GNB_ERR_IO), as zlib would.
 #pragma once
 #include <cstddef>
