@@ -1182,6 +1182,15 @@ def cli_leg(wl_name, wl, db, blocks, pool, R, dev):
                      "kind": "single-member gzip (one deflate stream per file, level 6)", "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}
         mh = re.search(r"host pipeline \(s\): ([^\n]*)", pr.stderr)
         out["gz"]["host_pipeline_s"] = mh.group(1) if mh else None
+        if os.environ.get("GANON_B200_BENCH_CLI_VARIANTS"):
+            out["gz"]["variants"] = {}
+            for tag, env in (("io_threads_8", {"GANON_B200_IO_THREADS": "8"}), ("io_threads_10", {"GANON_B200_IO_THREADS": "10"}), ("io_threads_12", {"GANON_B200_IO_THREADS": "12"}),
+                             ("io_threads_14", {"GANON_B200_IO_THREADS": "14"}), ("io_threads_16", {"GANON_B200_IO_THREADS": "16"}), ("default_again", {}),
+                             ("block_32MiB", {"GANON_B200_BLOCK_BYTES": str(32 << 20)}), ("block_16MiB_t14", {"GANON_B200_BLOCK_BYTES": str(16 << 20), "GANON_B200_IO_THREADS": "14"})):
+                pv = subprocess.run(cmd_gz, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, **env))
+                mv = re.search(r"classifying\+printing elapsed \(s\): ([0-9.eE+-]+)", pv.stderr)
+                mp = re.search(r"host pipeline \(s\): ([^\n]*)", pv.stderr)
+                out["gz"]["variants"][tag] = {"classify_s": float(mv.group(1)) if mv else None, "host_pipeline_s": mp.group(1) if mp else None}
         for p in (gz1, gz2):
             if p and os.path.exists(p):
                 os.remove(p)

@@ -586,7 +586,7 @@ class GanonClassifyConfig:
         return True
 
 
-IO_THREADS = int(os.environ.get("GANON_B200_IO_THREADS", "0"))  # 0 = all host threads (at most 16)
+IO_THREADS = int(os.environ.get("GANON_B200_IO_THREADS", "0"))  # 0 = all host threads but two (at most 16; split between paired gzip files)
 
 
 def _parse_reads_config(cfg: GanonClassifyConfig) -> Optional[Dict[str, List[Tuple[str, str]]]]:

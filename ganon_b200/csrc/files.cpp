@@ -475,7 +475,7 @@ extern "C" int gnb_session_classify_files(gnb_session *s, uint32_t prefix_id, co
     for (int k = 0; k < (paired ? 2 : 1); ++k)
     {
         std::string err;
-        auto        src = open_byte_source(k ? file2 : file1, io_threads, err);
+        auto        src = open_byte_source(k ? file2 : file1, io_threads, err, paired ? 2 : 1);
         if (!src)
             return fail(GNB_ERR_IO, err);
         R.is_gzip |= src->is_gzip() ? 1 : 0;

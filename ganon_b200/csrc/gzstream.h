@@ -45,6 +45,7 @@ class ByteSource
 };
 
 // plain or gzip by magic number (1f 8b), like seqan3's make_secondary_istream
-std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int threads, std::string &err);
+// threads: workers of the source (0 = as many as the host suggests, divided by `share` = files read at the same time)
+std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int threads, std::string &err, int share = 1);
 
 } // namespace gnb
