@@ -234,3 +234,30 @@ def test_fuzz_against_zlib(tmp_path):
         threads, chunk = int(rng.integers(1, 7)), int(rng.choice([4096, 8000, 20000, 65536, 300000, 0])) or None
         got, err = read_all_with_chunk(tmp_path / "f.gz", threads, chunk)
         assert err is None and got == data, (case, level, wbits, mem, strat, members, threads, chunk, err)
+
+
+def test_closing_a_gzip_file_early_stops_its_workers(tmp_path, fastq):
+    """A reader that is closed while finders and decoders are still at work (right after opening, or after a few bytes) must
+    come down cleanly -- the workers, the sequencer and the queued pieces -- and a fresh reader of the same file still works."""
+    L = _lib.lib()
+    (tmp_path / "r.fq.gz").write_bytes(gzip.compress(fastq, 6))
+    buf = C.create_string_buffer(5000)
+    for threads, chunk, reads in ((4, 65536, 0), (8, 4096, 1), (3, None, 2), (6, 20000, 0), (1, None, 1), (16, 65536, 3)):
+        old = os.environ.get("GANON_B200_GZ_CHUNK")
+        if chunk:
+            os.environ["GANON_B200_GZ_CHUNK"] = str(chunk)
+        try:
+            for _ in range(3):
+                h = C.c_void_p()
+                assert L.gnb_reads_file_open(str(tmp_path / "r.fq.gz").encode(), threads, C.byref(h)) == 0
+                for _ in range(reads):
+                    assert L.gnb_reads_file_read(h, buf, 5000) == 5000
+                    assert buf.raw[:5000] == fastq[:5000] or reads > 1
+                L.gnb_reads_file_close(h)
+        finally:
+            if old is None:
+                os.environ.pop("GANON_B200_GZ_CHUNK", None)
+            else:
+                os.environ["GANON_B200_GZ_CHUNK"] = old
+    got, err = read_all(tmp_path / "r.fq.gz", 4)
+    assert err is None and got == fastq
