@@ -414,35 +414,6 @@ class Writer
     volatile bool                           failed_ = false;
 };
 
-// seqan3::sequence_file_input picks the format from the file name (compression suffix stripped first): format_fasta.hpp /
-// format_fastq.hpp `file_extensions`.  0 = unknown (seqan3 throws unhandled_extension_error, which ganon-classify does not
-// catch), 1 = FASTA, 2 = FASTQ.  EMBL / GenBank / SAM (seqan3's other sequence formats) are not read here.
-int format_of_extension(std::string name)
-{
-    auto lower = [](std::string x) {
-        for (auto &c : x)
-            c = (char)tolower((unsigned char)c);
-        return x;
-    };
-    auto ext_of = [&](const std::string &x) {
-        const size_t sl = x.find_last_of('/'), dot = x.find_last_of('.');
-        return dot == std::string::npos || (sl != std::string::npos && dot < sl) ? std::string() : lower(x.substr(dot + 1));
-    };
-    std::string e = ext_of(name);
-    if (e == "gz" || e == "bgzf" || e == "bz2" || e == "zst")
-    {
-        name = name.substr(0, name.size() - e.size() - 1);
-        e    = ext_of(name);
-    }
-    for (const char *x : {"fasta", "fa", "fna", "ffn", "faa", "frn", "fas"})
-        if (e == x)
-            return 1;
-    for (const char *x : {"fastq", "fq"})
-        if (e == x)
-            return 2;
-    return 0;
-}
-
 } // namespace
 } // namespace gnb
 
@@ -488,7 +459,8 @@ extern "C" int gnb_session_classify_files(gnb_session *s, uint32_t prefix_id, co
     // of the other format is a parse error on the first record -- nothing of the file is classified (GC.cpp:1278-1283)
     for (int k = 0; k < (paired ? 2 : 1); ++k)
         if (format_of_extension(k ? file2 : file1) == 0)
-            return fail(GNB_ERR_PARSE, std::string("unknown file extension (the reference reads .fasta/.fa/.fna/.ffn/.faa/.frn/.fas and .fastq/.fq, optionally compressed): ") +
+            return fail(GNB_ERR_PARSE, std::string("unknown file extension (the reference reads .fasta/.fa/.fna/.ffn/.faa/.frn/.fas, .fastq/.fq, .embl, "
+                                                   ".genbank/.gb/.gbk and .sam, optionally compressed): ") +
                                            (k ? file2 : file1));
     Writer   writer;
     uint32_t pending = 0;
@@ -544,9 +516,9 @@ extern "C" int gnb_session_classify_files(gnb_session *s, uint32_t prefix_id, co
             bool mismatch = false;
             for (int k = 0; k < (paired ? 2 : 1) && !sliced; ++k)
             {
-                const int  fmt = format_of_extension(k ? file2 : file1);
+                const int  fmt = format_of_extension(k ? file2 : file1); // EMBL / GenBank / SAM arrive rewritten as FASTA
                 const char c   = st[k]->ptr()[0];
-                mismatch |= (fmt == 1 && c != '>' && c != ';') || (fmt == 2 && c != '@');
+                mismatch |= (fmt != kFormatFastq && c != '>' && c != ';') || (fmt == kFormatFastq && c != '@');
             }
             if (mismatch)
             {

@@ -1684,10 +1684,10 @@ std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int thread
         // staging thread (copies, kernel launches, short waits), a writer and the driver's threads, and a worker per core
         // starves them (16-CPU host, c2 reads from gzip: 16 workers 0.68-1.5 s, 14 workers 0.55 s)
         const unsigned automatic = std::max(1u, std::min(16u, hw > 2 ? hw - 2 : 1u) / (unsigned)std::max(1, share));
-        return std::unique_ptr<ByteSource>(new GzSource(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)automatic));
+        return wrap_sequence_format(std::unique_ptr<ByteSource>(new GzSource(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)automatic)), path);
     }
     // page-cache copies: a few threads saturate them, more only take cores from the rest of the pipeline (measured: 4-8)
-    return std::unique_ptr<ByteSource>(new PlainSource(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)std::min(6u, std::max(2u, hw / 2))));
+    return wrap_sequence_format(std::unique_ptr<ByteSource>(new PlainSource(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)std::min(6u, std::max(2u, hw / 2)))), path);
 }
 
 } // namespace gnb

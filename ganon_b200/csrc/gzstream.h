@@ -46,6 +46,23 @@ class ByteSource
 
 // plain or gzip by magic number (1f 8b), like seqan3's make_secondary_istream
 // threads: workers of the source (0 = as many as the host suggests, divided by `share` = files read at the same time)
+// (files named .embl / .genbank / .gb / .gbk / .sam, compressed or not, come out rewritten as two-line FASTA: seqformats.cpp)
 std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int threads, std::string &err, int share = 1);
+
+// seqan3::sequence_file_input picks the format from the file name, compression suffix stripped first (`file_extensions` of
+// format_fasta.hpp / format_fastq.hpp / format_embl.hpp / format_genbank.hpp / format_sam.hpp).  Unknown: seqan3 throws
+// unhandled_extension_error, which ganon-classify does not catch.
+enum
+{
+    kFormatUnknown = 0,
+    kFormatFasta   = 1,
+    kFormatFastq   = 2,
+    kFormatEmbl    = 3,
+    kFormatGenbank = 4,
+    kFormatSam     = 5
+};
+int format_of_extension(std::string name);
+// EMBL / GenBank / SAM by file name: the same stream rewritten record by record as two-line FASTA; anything else: src itself
+std::unique_ptr<ByteSource> wrap_sequence_format(std::unique_ptr<ByteSource> src, const std::string &path);
 
 } // namespace gnb

@@ -3,6 +3,7 @@ the checker is oracle/ (pinned to the reference in tests/test_oracle.py) and the
 reference binary (tests/golden/expected).  Integer work: bit-exact."""
 import ctypes as C
 import glob
+import gzip
 import os
 
 import numpy as np
@@ -1063,6 +1064,43 @@ def test_file_format_follows_the_file_name_like_seqan3(golden_dbs, tmp_path):
     assert cli.main(["-r", wrong + "," + ok, "-i", golden_dbs["synth"], "-o", pre + "2", "-u", "--quiet"]) == 0
     assert open(pre + "2.rep").read() == open(pre + ".rep").read()  # the mis-named file contributes nothing, the next one is read
     assert cli.main(["-r", unknown, "-i", golden_dbs["synth"], "-o", pre + "3", "-u", "--quiet"]) != 0
+
+
+def test_embl_genbank_and_sam_read_files_like_seqan3(golden_dbs, tmp_path):
+    """seqan3::sequence_file_input also reads EMBL, GenBank and SAM, chosen by the file name (csrc/seqformats.cpp rewrites them
+    as two-line FASTA for K1): the same records in every format give the same outputs as the FASTQ file -- GenBank ids are the
+    whole LOCUS line, as the reference returns them -- and a record seqan3 throws on loses the reference's chunk of --n-reads."""
+    from tests import test_seqformats_cpu as SF
+    import random
+
+    fq = open(os.path.join(SU.GOLDEN, "reads.se.fq"), "rb").read().split(b"\n")
+    recs = [(fq[i][1:], fq[i + 1]) for i in range(0, len(fq) - 1, 4)]
+    pre = str(tmp_path / "fq")
+    assert cli.main(["-r", os.path.join(SU.GOLDEN, "reads.se.fq"), "-i", golden_dbs["synth"], "-o", pre, "-a", "-u", "--quiet"]) == 0
+    want_all = sorted(open(pre + ".all", "rb").read().splitlines())
+    want_unc = sorted(open(pre + ".unc", "rb").read().splitlines())
+    assert want_all
+    rng = random.Random(2)
+    for fmt, ext in (("sam", "sam"), ("embl", "embl"), ("genbank", "gbk"), ("sam", "sam.gz")):
+        data = SF.dress(rng, recs, fmt, {"header": True, "tags": True, "minimal": fmt == "genbank"})
+        f = str(tmp_path / ("reads." + ext))
+        open(f, "wb").write(gzip.compress(data) if ext.endswith(".gz") else data)
+        out = str(tmp_path / ("o_" + ext))
+        assert cli.main(["-r", f, "-i", golden_dbs["synth"], "-o", out, "-a", "-u", "--quiet"]) == 0
+        strip = (lambda l: l) if fmt != "genbank" else (lambda l: b"\t".join([l.split(b"\t")[0].split(b" ")[0]] + l.split(b"\t")[1:]))
+        assert sorted(strip(l) for l in open(out + ".all", "rb").read().splitlines()) == want_all, fmt
+        assert sorted(strip(l) for l in open(out + ".unc", "rb").read().splitlines()) == want_unc, fmt
+        assert open(out + ".rep").read() == open(pre + ".rep").read(), fmt
+    # a record without a sequence in a SAM file: parse error at record 450 of --n-reads 400 -> 400 records kept
+    bad = list(recs[:1000]) if len(recs) >= 1000 else [recs[i % len(recs)] for i in range(1000)]
+    bad = [(b"r%d" % i, s) for i, (_id, s) in enumerate(bad)]
+    bad[450] = (b"bad", b"")
+    f = str(tmp_path / "bad.sam")
+    open(f, "wb").write(SF.dress(rng, bad, "sam", {}))
+    out = str(tmp_path / "o_bad")
+    assert cli.main(["-r", f, "-i", golden_dbs["synth"], "-o", out, "-u", "--quiet", "--n-reads", "400"]) == 0
+    rep = dict(l.split("\t") for l in open(out + ".rep").read().splitlines() if l.startswith("#"))
+    assert int(rep.get("#total_unclassified", 0)) + int(rep.get("#total_classified", 0)) == 400
 
 
 def test_long_reads_finish_on_the_device_when_fpr_query_is_off(golden_dbs):
