@@ -29,6 +29,19 @@ struct Lut
 };
 const Lut kLut;
 
+// length of the run of legal letters at s
+inline uint64_t legal_run(const uint8_t *s, uint64_t n)
+{
+    uint64_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        if (!(kLut.legal[s[i]] & kLut.legal[s[i + 1]] & kLut.legal[s[i + 2]] & kLut.legal[s[i + 3]] & kLut.legal[s[i + 4]] & kLut.legal[s[i + 5]] & kLut.legal[s[i + 6]] &
+              kLut.legal[s[i + 7]]))
+            break;
+    while (i < n && kLut.legal[s[i]])
+        ++i;
+    return i;
+}
+
 inline bool all_legal(const uint8_t *s, uint64_t n)
 {
     bool ok = true;
@@ -87,43 +100,48 @@ void index_reads_host(const char *bc, uint64_t len, bool final, uint64_t max_rec
                     error("No sequence information given!");
                 break;
             }
-            // sequence: up to the next '>' / ';' (anywhere), skipping blanks and digits
-            const uint64_t s0   = q;
-            uint64_t       e    = q;
-            bool           simple = true; // one contiguous run followed by a single '\n'
-            bool           bad  = false;
-            uint64_t       n    = 0;
-            for (; e < len && b[e] != '>' && b[e] != ';'; ++e)
+            // sequence: up to the next '>' / ';' (anywhere), blanks and digits skipped.  One pass over runs of letters: a record
+            // whose letters form a single run stays where it is; from the second run on (wrapped lines) the runs are
+            // gathered in aux.
+            const uint64_t s0 = q;
+            uint64_t       n  = legal_run(b + q, len - q);
+            uint64_t       e  = q + n;
+            const uint64_t a0 = t.aux.size();
+            bool           gathered = false, bad = false;
+            for (;;)
             {
-                const uint8_t c = b[e];
-                if (kLut.space[c] || kLut.digit[c])
-                    continue;
-                if (!kLut.legal[c])
+                while (e < len && (kLut.space[b[e]] || kLut.digit[b[e]]))
+                    ++e;
+                if (e >= len || b[e] == '>' || b[e] == ';')
+                    break;
+                if (!kLut.legal[b[e]])
                 {
                     bad = true;
                     break;
                 }
-                ++n;
+                if (!gathered)
+                {
+                    gathered = true;
+                    if (t.aux.capacity() < a0 + (len - s0))
+                        t.aux.reserve(a0 + (len - s0));
+                    t.aux.insert(t.aux.end(), b + s0, b + s0 + n);
+                }
+                const uint64_t r = legal_run(b + e, len - e);
+                t.aux.insert(t.aux.end(), b + e, b + e + r);
+                n += r;
+                e += r;
             }
-            if (bad)
+            if (bad || (e >= len && !final))
             {
-                error("Encountered an unexpected letter");
-                break;
+                t.aux.resize(a0);
+                if (bad)
+                    error("Encountered an unexpected letter");
+                break; // (not final: the record may continue in the next block)
             }
-            if (e >= len && !final)
-                break; // the record may continue in the next block
-            // contiguous iff the n letters are the first n bytes
-            simple = all_legal(b + s0, n) && (s0 + n <= e);
-            if (simple)
+            if (!gathered)
                 push(id0, id1 - id0, s0, n);
             else
-            {
-                const uint64_t a0 = t.aux.size();
-                for (uint64_t i = s0; i < e; ++i)
-                    if (!kLut.space[b[i]] && !kLut.digit[b[i]])
-                        t.aux.push_back(b[i]);
                 push(id0, id1 - id0, len + a0, n);
-            }
             p = e;
         }
         else
