@@ -158,6 +158,16 @@ class BlockStream
         }
     }
     const char *ptr() const { return positional_ ? bufs_[cur_] : bufs_[cur_] + start_; }
+    // first byte of the current block (a rank of a sliced run holds only its slice of the block: read it from the file)
+    bool first_byte(char *c)
+    {
+        if (!positional_ || rank_ == 0)
+        {
+            *c = ptr()[0];
+            return true;
+        }
+        return src_->read_at(c, 1, pos_) == 1;
+    }
     size_t      fill() const { return fill_; }
     bool        eof() const { return eof_; }
     uint64_t    bytes_in() const { return bytes_in_; }
@@ -514,12 +524,19 @@ extern "C" int gnb_session_classify_files(gnb_session *s, uint32_t prefix_id, co
         {
             first_block = false;
             bool mismatch = false;
-            for (int k = 0; k < (paired ? 2 : 1) && !sliced; ++k)
+            for (int k = 0; k < (paired ? 2 : 1); ++k)
             {
-                const int  fmt = format_of_extension(k ? file2 : file1); // EMBL / GenBank / SAM arrive rewritten as FASTA
-                const char c   = st[k]->ptr()[0];
+                const int fmt = format_of_extension(k ? file2 : file1); // EMBL / GenBank / SAM arrive rewritten as FASTA
+                char      c   = 0;
+                if (!st[k]->first_byte(&c))
+                {
+                    rc = fail(GNB_ERR_IO, "short read");
+                    break;
+                }
                 mismatch |= (fmt != kFormatFastq && c != '>' && c != ';') || (fmt == kFormatFastq && c != '@');
             }
+            if (rc != GNB_OK)
+                break;
             if (mismatch)
             {
                 fprintf(stderr, "Error parsing file(s) [%s, %s]: the content is not in the format of the file extension\n", file1, paired ? file2 : "");
