@@ -104,20 +104,27 @@ inline void put_record(std::string &out, const uint8_t *id, size_t id_len, const
     out.push_back('\n');
 }
 
-// letters up to '/' with blanks and digits skipped; p ends ON the '/'
+// letters up to '/' with blanks and digits skipped (run by run); p ends ON the '/'
 Outcome take_sequence(const uint8_t *b, size_t n, bool final, size_t &p, std::string &seq)
 {
     seq.clear();
-    for (; p < n; ++p)
+    while (p < n)
     {
         const uint8_t c = b[p];
         if (kC.space[c] || kC.digit[c])
+        {
+            ++p;
             continue;
+        }
         if (c == '/')
             return kRecord;
         if (!kC.legal[c])
             return kBad;
-        seq.push_back((char)c);
+        size_t q = p + 1;
+        while (q < n && kC.legal[b[q]])
+            ++q;
+        seq.append(reinterpret_cast<const char *>(b + p), q - p);
+        p = q;
     }
     return final ? kBad : kMore;
 }
