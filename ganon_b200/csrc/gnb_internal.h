@@ -228,6 +228,10 @@ void launch_em_assign(EmStoreDev store, uint64_t n_reads, const unsigned long lo
 // `.one` lines: sizes pass (out == nullptr: line_len[r]) and write pass (line_off = exclusive scan of line_len)
 void launch_em_one(EmStoreDev store, uint64_t n_reads, const unsigned long long *weight, const uint32_t *name_off, const char *names, uint64_t *line_len,
                    const uint64_t *line_off, char *out, unsigned long long *n_multi, cudaStream_t st);
+// equal read ids in the store: *n_equal = pairs of equal neighbours among the sorted 64-bit hashes of the ids (0: all ids differ)
+size_t em_equal_ids_tmp_bytes(uint64_t n_reads);
+void   launch_em_equal_ids(EmStoreDev store, uint64_t n_reads, uint64_t *keys_a, uint64_t *keys_b, void *tmp, size_t tmp_bytes, unsigned long long *n_equal,
+                           cudaStream_t st);
 size_t em_scan64_tmp_bytes(uint64_t n);
 void   launch_scan64(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 // build-side

@@ -2333,6 +2333,51 @@ void launch_scan64(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, siz
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int64_t)n, st);
 }
 
+// Equal read ids in the store (reassign.py keys its matches by read id: reads that share one are a single read to it).
+// Every id is hashed (FNV-1a, 64 bits, finished with a multiply-shift mix), the hashes are sorted, equal neighbours are
+// counted: zero means that no two ids are equal; anything else sends the store through the exact regrouping on the host
+// (em_merge.cpp), which compares the bytes.
+namespace
+{
+__global__ void k_em_hash_ids(EmStoreDev st, uint64_t n_reads, uint64_t *__restrict__ hash)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads)
+        return;
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t i = st.id_off[r], e = st.id_off[r + 1]; i < e; ++i)
+        h = (h ^ (uint8_t)st.ids[i]) * 0x100000001b3ull;
+    h ^= h >> 32;
+    h *= 0x9e3779b97f4a7c15ull;
+    hash[r] = h ^ (h >> 29);
+}
+__global__ void k_em_equal_neighbours(const uint64_t *__restrict__ sorted, uint64_t n, unsigned long long *__restrict__ n_equal)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const bool     eq = i + 1 < n && sorted[i] == sorted[i + 1];
+    const unsigned m  = __ballot_sync(0xffffffffu, eq);
+    if ((threadIdx.x & 31) == 0 && m)
+        atomicAdd(n_equal, (unsigned long long)__popc(m));
+}
+} // namespace
+size_t em_equal_ids_tmp_bytes(uint64_t n_reads)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)n_reads);
+    return bytes + 256;
+}
+void launch_em_equal_ids(EmStoreDev store, uint64_t n_reads, uint64_t *keys_a, uint64_t *keys_b, void *tmp, size_t tmp_bytes, unsigned long long *n_equal,
+                         cudaStream_t st)
+{
+    cudaMemsetAsync(n_equal, 0, sizeof(unsigned long long), st);
+    if (n_reads < 2)
+        return;
+    const unsigned blocks = (unsigned)((n_reads + 255) / 256);
+    k_em_hash_ids<<<blocks, 256, 0, st>>>(store, n_reads, keys_a);
+    cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys_a, keys_b, (int64_t)n_reads, 0, 64, st);
+    k_em_equal_neighbours<<<blocks, 256, 0, st>>>(keys_b, n_reads, n_equal);
+}
+
 // =====================================================================================================================
 // build-side helpers
 // =====================================================================================================================

@@ -360,7 +360,6 @@ class TranscodeSource : public ByteSource
             }
             buf_.resize(fill);
         }
-        const size_t before = out_.size();
         while (pos_ < buf_.size())
         {
             size_t        used = 0;
@@ -381,7 +380,6 @@ class TranscodeSource : public ByteSource
         }
         if (eof_ && pos_ >= buf_.size())
             done_ = true;
-        (void)before;
         return 0;
     }
     std::unique_ptr<ByteSource> in_;

@@ -26,6 +26,7 @@
 
 #include "comm.h"
 #include "db.h"
+#include "em_merge.h"
 #include "reads.h"
 
 namespace gnb
@@ -3722,10 +3723,12 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
     s->em_iterations.assign(NG, 0);
     s->em_reassigned.assign(NG, 0);
     s->em_rep.clear();
-    DevBuf d_first, d_initial, d_weight, d_counts, d_len, d_loff, d_text, d_tmp, d_multi;
-    auto   cleanup = [&]() {
-        for (DevBuf *b : {&d_first, &d_initial, &d_weight, &d_counts, &d_len, &d_loff, &d_text, &d_tmp, &d_multi})
+    DevBuf  d_first, d_initial, d_weight, d_counts, d_len, d_loff, d_text, d_tmp, d_multi, d_keys_a, d_keys_b;
+    EmStore merged; // a group's store with reads of equal ids made one (only when there are any)
+    auto    cleanup = [&]() {
+        for (DevBuf *b : {&d_first, &d_initial, &d_weight, &d_counts, &d_len, &d_loff, &d_text, &d_tmp, &d_multi, &d_keys_a, &d_keys_b})
             b->release();
+        merged.release();
     };
     int rc = [&]() -> int {
         GNB_TRY(d_first.ensure(NT * 8 + 8));
@@ -3743,11 +3746,61 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
             std::vector<uint32_t> order; // targets present in the group's `.all`, in order of first appearance
             if (E.n_reads)
             {
-                const EmStoreDev D = E.dev();
+                // reassign.py:78-85 keys the matches by read id: reads that share an id are one read (at the place of the
+                // first, matches in file order).  Equal ids are looked for on the device; only if there are any is the
+                // store regrouped (on the host, em_merge.cpp) -- the targets keep the numbering of the file order.
+                EmStoreDev D       = E.dev();
+                uint64_t   n_reads = E.n_reads;
+                {
+                    GNB_TRY(d_keys_a.ensure(E.n_reads * 8 + 8));
+                    GNB_TRY(d_keys_b.ensure(E.n_reads * 8 + 8));
+                    GNB_TRY(d_tmp.ensure(em_equal_ids_tmp_bytes(E.n_reads)));
+                    launch_em_equal_ids(D, E.n_reads, d_keys_a.as<uint64_t>(), d_keys_b.as<uint64_t>(), d_tmp.p, d_tmp.cap, d_multi.as<unsigned long long>(), st);
+                    unsigned long long n_equal = 0;
+                    GNB_CUDA(cudaMemcpyAsync(&n_equal, d_multi.p, 8, cudaMemcpyDeviceToHost, st));
+                    GNB_CUDA(stream_wait(st));
+                    if (n_equal)
+                    {
+                        EmHost in, out;
+                        in.off.resize(E.n_reads + 1);
+                        in.id_off.resize(E.n_reads + 1);
+                        in.tgt.resize(E.n_matches);
+                        in.cnt.resize(E.n_matches);
+                        in.ids.resize(E.id_bytes);
+                        GNB_CUDA(cudaMemcpy(in.off.data(), E.off.p, (E.n_reads + 1) * 8, cudaMemcpyDeviceToHost));
+                        GNB_CUDA(cudaMemcpy(in.id_off.data(), E.id_off.p, (E.n_reads + 1) * 8, cudaMemcpyDeviceToHost));
+                        if (E.n_matches)
+                        {
+                            GNB_CUDA(cudaMemcpy(in.tgt.data(), E.tgt.p, E.n_matches * 4, cudaMemcpyDeviceToHost));
+                            GNB_CUDA(cudaMemcpy(in.cnt.data(), E.cnt.p, E.n_matches * 4, cudaMemcpyDeviceToHost));
+                        }
+                        if (E.id_bytes)
+                            GNB_CUDA(cudaMemcpy(in.ids.data(), E.ids.p, E.id_bytes, cudaMemcpyDeviceToHost));
+                        if (em_merge_by_id(in, out) != 0)
+                        {
+                            merged.release();
+                            GNB_TRY(merged.reserve(out.n_reads(), out.tgt.size(), out.ids.size()));
+                            GNB_CUDA(cudaMemcpy(merged.off.p, out.off.data(), out.off.size() * 8, cudaMemcpyHostToDevice));
+                            GNB_CUDA(cudaMemcpy(merged.id_off.p, out.id_off.data(), out.id_off.size() * 8, cudaMemcpyHostToDevice));
+                            if (!out.tgt.empty())
+                            {
+                                GNB_CUDA(cudaMemcpy(merged.tgt.p, out.tgt.data(), out.tgt.size() * 4, cudaMemcpyHostToDevice));
+                                GNB_CUDA(cudaMemcpy(merged.cnt.p, out.cnt.data(), out.cnt.size() * 4, cudaMemcpyHostToDevice));
+                            }
+                            if (!out.ids.empty())
+                                GNB_CUDA(cudaMemcpy(merged.ids.p, out.ids.data(), out.ids.size(), cudaMemcpyHostToDevice));
+                            merged.n_reads   = out.n_reads();
+                            merged.n_matches = out.tgt.size();
+                            merged.id_bytes  = out.ids.size();
+                            n_reads          = merged.n_reads;
+                            D                = merged.dev();
+                        }
+                    }
+                }
                 GNB_CUDA(cudaMemsetAsync(d_first.p, 0xFF, NT * 8, st));
                 GNB_CUDA(cudaMemsetAsync(d_initial.p, 0, NT * 8, st));
-                launch_em_first_pos(D, E.n_matches, d_first.as<unsigned long long>(), st);
-                launch_em_initial(D, E.n_reads, d_initial.as<unsigned long long>(), st);
+                launch_em_first_pos(E.dev(), E.n_matches, d_first.as<unsigned long long>(), st); // numbering: file order
+                launch_em_initial(D, n_reads, d_initial.as<unsigned long long>(), st);
                 GNB_CUDA(cudaMemcpyAsync(first.data(), d_first.p, NT * 8, cudaMemcpyDeviceToHost, st));
                 GNB_CUDA(cudaMemcpyAsync(initial.data(), d_initial.p, NT * 8, cudaMemcpyDeviceToHost, st));
                 GNB_CUDA(stream_wait(st));
@@ -3756,7 +3809,7 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                         order.push_back(t);
                 std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; });
                 // reassign.py:94-107: total weight = reads with matches, first probabilities from the unique matches
-                const double total = (double)E.n_reads;
+                const double total = (double)n_reads;
                 uint64_t     uniq  = 0;
                 for (uint32_t t : order)
                     uniq += initial[t];
@@ -3770,7 +3823,7 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                 while (true)
                 { // reassign.py:110-141
                     GNB_CUDA(cudaMemcpyAsync(d_counts.p, d_initial.p, NT * 8, cudaMemcpyDeviceToDevice, st));
-                    launch_em_assign(D, E.n_reads, d_weight.as<unsigned long long>(), d_counts.as<unsigned long long>(), st);
+                    launch_em_assign(D, n_reads, d_weight.as<unsigned long long>(), d_counts.as<unsigned long long>(), st);
                     GNB_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, NT * 8, cudaMemcpyDeviceToHost, st));
                     GNB_CUDA(cudaMemcpyAsync(d_weight.p, d_counts.p, NT * 8, cudaMemcpyDeviceToDevice, st));
                     GNB_CUDA(stream_wait(st));
@@ -3789,21 +3842,21 @@ extern "C" int gnb_session_reassign(gnb_session *s, uint32_t prefix_id, double t
                 }
                 s->em_iterations[g] = it + 1;
                 // `.one` (reassign.py:149-179): the unique match, or the top match under the final probabilities
-                GNB_TRY(d_len.ensure((E.n_reads + 1) * 8));
-                GNB_TRY(d_loff.ensure((E.n_reads + 1) * 8));
-                GNB_TRY(d_tmp.ensure(em_scan64_tmp_bytes(E.n_reads + 1)));
+                GNB_TRY(d_len.ensure((n_reads + 1) * 8));
+                GNB_TRY(d_loff.ensure((n_reads + 1) * 8));
+                GNB_TRY(d_tmp.ensure(em_scan64_tmp_bytes(n_reads + 1)));
                 GNB_CUDA(cudaMemsetAsync(d_multi.p, 0, 8, st));
-                launch_em_one(D, E.n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(), nullptr,
+                launch_em_one(D, n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(), nullptr,
                               nullptr, d_multi.as<unsigned long long>(), st);
-                launch_scan64(d_len.as<uint64_t>(), d_loff.as<uint64_t>(), E.n_reads + 1, d_tmp.p, d_tmp.cap, st);
+                launch_scan64(d_len.as<uint64_t>(), d_loff.as<uint64_t>(), n_reads + 1, d_tmp.p, d_tmp.cap, st);
                 uint64_t           bytes = 0;
                 unsigned long long multi = 0;
-                GNB_CUDA(cudaMemcpyAsync(&bytes, d_loff.as<uint64_t>() + E.n_reads, 8, cudaMemcpyDeviceToHost, st));
+                GNB_CUDA(cudaMemcpyAsync(&bytes, d_loff.as<uint64_t>() + n_reads, 8, cudaMemcpyDeviceToHost, st));
                 GNB_CUDA(cudaMemcpyAsync(&multi, d_multi.p, 8, cudaMemcpyDeviceToHost, st));
                 GNB_CUDA(stream_wait(st));
                 s->em_reassigned[g] = multi;
                 GNB_TRY(d_text.ensure(bytes + 1));
-                launch_em_one(D, E.n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(),
+                launch_em_one(D, n_reads, d_weight.as<unsigned long long>(), s->d_em_name_off.as<uint32_t>(), s->d_em_names.as<char>(), d_len.as<uint64_t>(),
                               d_loff.as<uint64_t>(), d_text.as<char>(), nullptr, st);
                 s->em_one[g].resize(bytes);
                 if (bytes)

@@ -460,6 +460,36 @@ def test_em_reassign_in_hbm_matches_restatement(name, mode, golden_dbs, tmp_path
             assert open(em + suffix).read() == open(plain + suffix).read()
 
 
+def test_em_reassign_makes_one_read_of_reads_that_share_an_id(golden_dbs, tmp_path):
+    """src/ganon/reassign.py:78-85 keys the matches of the `.all` lines by read id: reads with equal ids are ONE read to it
+    (its matches are theirs in file order, it counts once in the total weight, it gets one `.one` line).  The store in HBM
+    keeps reads by position; `gnb_session_reassign` finds equal ids (sorted hashes on the device) and regroups the store
+    (csrc/em_merge.cpp).  Every third record takes the id of the record before it, some ids appear three times."""
+    from oracle import reassign_oracle as RO
+
+    fq = open(os.path.join(SU.GOLDEN, "reads.se.fq"), "rb").read().split(b"\n")
+    recs = [[fq[i], fq[i + 1], fq[i + 2], fq[i + 3]] for i in range(0, len(fq) - 1, 4)]
+    for i in range(len(recs)):
+        if i % 3 == 2 or i % 50 == 1:
+            recs[i][0] = recs[i - 1][0]
+    f = str(tmp_path / "dup.fq")
+    open(f, "wb").write(b"".join(b"\n".join(r) + b"\n" for r in recs))
+    args = SU.expand(SU.load_scenarios()["se_synth_all"], golden_dbs)
+    args[args.index("-r") + 1] = f
+    plain = str(tmp_path / "plain")
+    assert cli.main(args + ["-o", plain, "-t", "4", "--quiet"]) == 0
+    rep, all_text = open(plain + ".rep").read(), open(plain + ".all").read()
+    classified = int(dict(l.split("\t") for l in rep.splitlines() if l.startswith("#"))["#total_classified"])
+    for threshold, max_iter in [(0, 10), (0, 1), (0.05, 0)]:
+        em = str(tmp_path / ("em_%s_%s" % (threshold, max_iter)))
+        assert cli.main(args + ["-o", em, "-t", "4", "--quiet", "--reassign-em", "--em-max-iter", str(max_iter), "--em-threshold", str(threshold)]) == 0
+        ones, new_rep = RO.reassign_texts(rep, {"": all_text}, threshold, max_iter)
+        assert len(ones[""].splitlines()) < classified  # reads were merged
+        assert open(em + ".one").read() == ones[""]
+        assert open(em + ".rep").read() == new_rep
+        assert open(em + ".all").read() == all_text
+
+
 # ------------------------------------------------------------------------------------------------------------------ HIBF
 def test_hibf_sub_ibf_counts_match_oracle(golden_dbs):
     h = formats.read_hibf(golden_dbs["synth_hibf"])
