@@ -1065,6 +1065,7 @@ def build_leg(dev, n_targets=128, genome_len=4_000_000):
     common = ["--input-file", tab, "--kmer-size", "19", "--window-size", "31", "--max-fp", "0.05", "--hash-functions", "4", "--verbose"]
     out_gpu, out_ref = os.path.join(d, "gpu.ibf"), os.path.join(d, "ref.ibf")
     os.makedirs(os.path.join(d, "tmp_gpu"), exist_ok=True)  # both builders want an existing folder
+    os.sync()  # the genomes were just written: let the write-back finish (measured: 1.4 - 4.3 s for the same build without it)
     t0 = time.perf_counter()
     pg = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "ganon-build")] + common + ["--output-file", out_gpu, "--tmp-output-folder", os.path.join(d, "tmp_gpu") + "/", "--device", str(dev)],
                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
@@ -1074,6 +1075,7 @@ def build_leg(dev, n_targets=128, genome_len=4_000_000):
             "gpu_stderr_tail": pg.stderr[-200:] if pg.returncode else "", "note": "wall = whole process (interpreter + CUDA start included); own = the builder's reported time"}
     if os.path.exists(ref_build) and pg.returncode == 0:
         os.makedirs(os.path.join(d, "tmp_ref"), exist_ok=True)
+        os.sync()
         t0 = time.perf_counter()
         pr = subprocess.run([ref_build] + common + ["--output-file", out_ref, "--tmp-output-folder", os.path.join(d, "tmp_ref") + "/", "--threads", str(reference_threads())],
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
