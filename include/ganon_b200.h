@@ -295,6 +295,8 @@ int gnb_session_staged_timings(gnb_session *s, gnb_batch_result *timings);
  * decompression, seqan3/io/detail/misc_input.hpp): plain, or gzip by magic number -- single-member, multi-member and BGZF
  * alike are inflated by `io_threads` host threads at once (0 = all, at most 16; csrc/gzstream.h), CRC-32 and length of every
  * member verified.  gnb_reads_file_read: the next bytes of the decompressed stream (> 0), 0 at the end, < 0 = gnb_status.
+ * Files named .embl / .genbank / .gb / .gbk / .sam (seqan3's other sequence formats, format_embl.hpp / format_genbank.hpp /
+ * format_sam.hpp; compression suffix stripped first) come out rewritten record by record as two-line FASTA (">id\nSEQ\n").
  * No device is involved. */
 typedef struct gnb_reads_file gnb_reads_file;
 int     gnb_reads_file_open(const char *path, int io_threads, gnb_reads_file **out);
@@ -348,7 +350,8 @@ int gnb_session_stats(gnb_session *s, uint32_t prefix_id, const char *prefix_nam
  * the probabilities is <= threshold or max_iter iterations; 0 = until convergence) and returns the `.one` lines
  * (reassign.py:149-179) per EM group -- one group per hierarchy level, or a single one for one level / --output-single,
  * as the reference finds its `.all` files (reassign.py:37-60) -- and the new `.rep` (reassign.py:188-220).
- * Reads are told apart by position in the input, not by id (the reference merges reads that share an id). */
+ * Reads that share an id are one read, as in the reference (its dictionary is keyed by read id, reassign.py:78-85): equal ids
+ * are looked for on the device and the store is regrouped before the iterations only when there are any. */
 typedef struct
 {
     uint32_t           n_groups;
