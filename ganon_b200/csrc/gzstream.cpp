@@ -1676,9 +1676,14 @@ std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int thread
         return nullptr;
     }
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    unsigned char magic[2] = {0, 0};
-    const ssize_t got      = pread(fd, magic, 2, 0);
-    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
+    unsigned char magic[3] = {0, 0, 0};
+    const ssize_t got      = pread(fd, magic, 3, 0);
+    if (got == 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h')
+    {
+        const unsigned automatic = std::max(1u, std::min(16u, hw > 2 ? hw - 2 : 1u) / (unsigned)std::max(1, share));
+        return wrap_sequence_format(open_bz2_source(fd, (uint64_t)st.st_size, threads > 0 ? threads : (int)automatic), path);
+    }
+    if (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b)
     {
         // all host threads but two (at most 16), split between the files read at the same time: a file run also has its
         // staging thread (copies, kernel launches, short waits), a writer and the driver's threads, and a worker per core

@@ -44,7 +44,10 @@ class ByteSource
     std::string err_;
 };
 
-// plain or gzip by magic number (1f 8b), like seqan3's make_secondary_istream
+// bzip2 files ("BZh"): the blocks decoded by `threads` host threads through libbz2 (bz2stream.cpp)
+std::unique_ptr<ByteSource> open_bz2_source(int fd, uint64_t size, int threads);
+
+// plain, gzip (1f 8b) or bzip2 ("BZh") by magic number, like seqan3's make_secondary_istream
 // threads: workers of the source (0 = as many as the host suggests, divided by `share` = files read at the same time)
 // (files named .embl / .genbank / .gb / .gbk / .sam, compressed or not, come out rewritten as two-line FASTA: seqformats.cpp)
 std::unique_ptr<ByteSource> open_byte_source(const std::string &path, int threads, std::string &err, int share = 1);

@@ -1133,6 +1133,33 @@ def test_embl_genbank_and_sam_read_files_like_seqan3(golden_dbs, tmp_path):
     assert int(rep.get("#total_unclassified", 0)) + int(rep.get("#total_classified", 0)) == 400
 
 
+def test_bzip2_read_files(golden_dbs, tmp_path):
+    """`.bz2` read files (the reference reads them through seqan3 + libbz2; csrc/bz2stream.cpp decodes the blocks on all host
+    threads): same outputs as the plain files, single-end and paired, one stream and several."""
+    import bz2
+
+    se = os.path.join(SU.GOLDEN, "reads.se.fq")
+    pre = str(tmp_path / "plain")
+    assert cli.main(["-r", se, "-i", golden_dbs["synth"], "-o", pre, "-a", "-u", "--quiet"]) == 0
+    data = open(se, "rb").read()
+    half = data.index(b"\n@", len(data) // 2) + 1
+    z = str(tmp_path / "reads.se.fq.bz2")
+    open(z, "wb").write(bz2.compress(data[:half], 1) + bz2.compress(data[half:], 9))
+    out = str(tmp_path / "bz")
+    assert cli.main(["-r", z, "-i", golden_dbs["synth"], "-o", out, "-a", "-u", "--quiet"]) == 0
+    for ext in (".all", ".unc", ".rep"):
+        assert open(out + ext).read() == open(pre + ext).read(), ext
+    p1, p2 = os.path.join(SU.GOLDEN, "reads.1.fq"), os.path.join(SU.GOLDEN, "reads.2.fq")
+    assert cli.main(["-p", p1 + "," + p2, "-i", golden_dbs["synth"], "-o", pre + "_pe", "-a", "-u", "--quiet"]) == 0
+    zs = []
+    for f in (p1, p2):
+        zs.append(str(tmp_path / (os.path.basename(f) + ".bz2")))
+        open(zs[-1], "wb").write(bz2.compress(open(f, "rb").read(), 1))
+    assert cli.main(["-p", ",".join(zs), "-i", golden_dbs["synth"], "-o", out + "_pe", "-a", "-u", "--quiet"]) == 0
+    for ext in (".all", ".unc", ".rep"):
+        assert open(out + "_pe" + ext).read() == open(pre + "_pe" + ext).read(), ext
+
+
 def test_long_reads_finish_on_the_device_when_fpr_query_is_off(golden_dbs):
     """Reads of tens of thousands of minimisers (long-read data) stay on K4 unless --fpr-query needs the device's libm-style
     evaluation (trusted up to 4096 minimisers): same result as the host stage; with --fpr-query the level goes to the host."""
