@@ -294,7 +294,8 @@ int gnb_session_staged_timings(gnb_session *s, gnb_batch_result *timings);
 /* Read files as the record reader sees them (parse_reads GC.cpp:1220-1287 opens them through seqan3's transparent
  * decompression, seqan3/io/detail/misc_input.hpp): plain, or gzip by magic number -- single-member, multi-member and BGZF
  * alike are inflated by `io_threads` host threads at once (0 = all, at most 16; csrc/gzstream.h), CRC-32 and length of every
- * member verified.  gnb_reads_file_read: the next bytes of the decompressed stream (> 0), 0 at the end, < 0 = gnb_status.
+ * member verified; bzip2 ("BZh") block-parallel through libbz2 (dlopen; csrc/bz2stream.cpp), block and stream CRCs verified.
+ * gnb_reads_file_read: the next bytes of the decompressed stream (> 0), 0 at the end, < 0 = gnb_status.
  * Files named .embl / .genbank / .gb / .gbk / .sam (seqan3's other sequence formats, format_embl.hpp / format_genbank.hpp /
  * format_sam.hpp; compression suffix stripped first) come out rewritten record by record as two-line FASTA (">id\nSEQ\n").
  * No device is involved. */
